@@ -1,0 +1,142 @@
+/*
+ * diffvg_b200.h -- C ABI of the B200-native differentiable vector-graphics rasteriser.
+ *
+ * This is the drop-in boundary for the hot path BASELINE.json:north_star names.  Each
+ * entry point cites the reference interface it replaces (paths relative to the reference
+ * tree).  Plain pointers and sizes only; no C++/torch types.  Every function returns 0
+ * on success or a non-zero DvgStatus; dvg_last_error() gives the message (thread-local).
+ * Nothing here ever calls exit() (the reference does on CUDA errors, cuda_utils.h:11-16).
+ *
+ * Threading / streams: calls are asynchronous on the cudaStream_t passed as `stream`
+ * (0 = legacy default stream); no device-wide synchronisation is performed (the reference
+ * ends every render() with cudaDeviceSynchronize, diffvg.cpp:1639-1641).  A DvgScene may
+ * be used from one thread at a time; distinct scenes are independent.
+ */
+#ifndef DIFFVG_B200_H
+#define DIFFVG_B200_H
+
+#include <stdint.h>
+#include "dvg_scene_format.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct DvgScene DvgScene;
+
+typedef enum DvgStatus {
+    DVG_OK = 0,
+    DVG_ERR_INVALID = 1,  /* malformed topo / arguments                     */
+    DVG_ERR_CUDA = 2,     /* a CUDA runtime call failed                      */
+    DVG_ERR_SCENE = 3,    /* degenerate scene (scene.cpp:231-240)            */
+    DVG_ERR_UNSUPPORTED = 4 /* e.g. stroked ellipse (within_distance.h:342-345 asserts) */
+} DvgStatus;
+
+/* flags for dvg_render_backward */
+#define DVG_BWD_SKIP_XFORM_GRAD 1u   /* do not accumulate d(shape_to_canvas) (saves 9 scatters / boundary sample) */
+#define DVG_BWD_ACCUMULATE      2u   /* add into d_params instead of overwriting it                               */
+
+/* Version of this ABI; bumped on incompatible change. */
+int dvg_abi_version(void);
+
+/* Thread-local message of the last failing call on this thread. */
+const char *dvg_last_error(void);
+
+/*
+ * Create a scene from its topology.  Replaces the structural half of
+ * `diffvg.Scene(canvas_w, canvas_h, shapes, shape_groups, filter, use_gpu, gpu_index)`
+ * (scene.cpp:919-998, allocate_buffers 686-917) and of the pybind11 object graph built in
+ * render_pytorch.py:206-363.  `topo` is a HOST array in dvg_scene_format.h layout; it is
+ * copied.  `device` is the CUDA ordinal the scene lives on (reference: gpu_index).
+ */
+int dvg_scene_create(const int32_t *topo, int64_t topo_len, int device, DvgScene **out_scene);
+
+/*
+ * Upload the continuous parameters and (re)build everything derived from them on the
+ * GPU: segment table, shape lengths, shape/path sampling CDFs and PMFs, bounding boxes,
+ * reference-topology BVH levels and the tile bins the kernels traverse.  Replaces
+ * copy_and_init_shapes / copy_and_init_shape_groups / compute_shape_length /
+ * build_shape_cdfs / build_path_cdfs / compute_bounding_boxes (scene.cpp:45-684), which
+ * the reference runs single-threaded on the host in every forward.
+ * `params` may be a host pointer (params_on_device = 0: one cudaMemcpyAsync H2D) or a
+ * device pointer on the scene's device (params_on_device = 1: D2D copy).
+ */
+int dvg_scene_set_params(DvgScene *scene, const float *params, int64_t num_params,
+                         int params_on_device, void *stream);
+
+/*
+ * Forward render.  Replaces `diffvg.render(scene, background, render_image, render_sdf,
+ * width, height, nsx, nsy, seed, 0,0,0,0, use_prefiltering, eval_positions, n)`
+ * (diffvg.cpp:1477-1492 with the d_* pointers null; kernels 1115-1312).
+ * All image pointers are DEVICE memory on the scene's device; NULL = not requested.
+ *   background     float[H*W*4] or NULL
+ *   render_image   float[H*W*4] (overwritten)
+ *   render_sdf     float[H*W] or float[num_eval_positions] (overwritten)
+ *   eval_positions float[2*num_eval_positions] or NULL (sdf only, render_kernel 1181-1186)
+ */
+int dvg_render_forward(DvgScene *scene, const float *background, float *render_image, float *render_sdf,
+                       int width, int height, int num_samples_x, int num_samples_y, uint64_t seed,
+                       int use_prefiltering, const float *eval_positions, int num_eval_positions,
+                       void *stream);
+
+/*
+ * Backward render.  Replaces the second `diffvg.render(...)` call with d_render_image /
+ * d_render_sdf set (render_pytorch.py:692-707; diffvg.cpp:1193-1272 interior term,
+ * 1558-1626 boundary term) AND the per-field gradient read-back through
+ * Scene::get_d_shape / get_d_shape_group / get_d_filter_radius (scene.cpp:1024-1034,
+ * render_pytorch.py:713-866): gradients arrive as ONE flat array with the layout of
+ * `params`.
+ *   d_render_image float[H*W*4] or NULL;  d_render_sdf float[H*W] / float[n_eval] or NULL
+ *   d_params       float[num_params]  (device; overwritten unless DVG_BWD_ACCUMULATE)
+ *   d_background   float[H*W*4] or NULL (overwritten)
+ *   d_translation  float[H*W*2] or NULL (overwritten; RenderFunction.render_grad)
+ */
+int dvg_render_backward(DvgScene *scene, const float *background,
+                        const float *d_render_image, const float *d_render_sdf,
+                        int width, int height, int num_samples_x, int num_samples_y, uint64_t seed,
+                        int use_prefiltering, const float *eval_positions, int num_eval_positions,
+                        float *d_params, float *d_background, float *d_translation,
+                        uint32_t flags, void *stream);
+
+/* Destroy the scene and its device buffers (Scene::~Scene, scene.cpp:1000-1022). */
+int dvg_scene_destroy(DvgScene *scene);
+
+/*
+ * Debug export for the bit-exact BVH / CDF / indexing checks (the reference
+ * keeps these private in Scene).  Synchronises `stream`.  `what`:
+ *   0 scene BVH nodes, 1 group BVH (index = group), 2 path BVH (index = shape): records of 7
+ *     32-bit words {child0, child1, box.min.x, box.min.y, box.max.x, box.max.y, max_radius}
+ *     in the reference's node order (scene.cpp:439-494);
+ *   3 shapes_length, 4 sample_shapes_cdf, 5 sample_shapes_pmf,
+ *   6 path_length_cdf (index = shape), 7 path_length_pmf, 8 path_point_id_map,
+ *   9 sample_shape_id, 10 sample_group_id.
+ * Writes raw 32-bit words to the HOST buffer `out`; returns the word count or -1.
+ */
+int64_t dvg_scene_dump(DvgScene *scene, int what, int index, uint32_t *out, int64_t cap, void *stream);
+
+/*
+ * Number of kernels this library launched on behalf of the calling thread's process since
+ * load (monotonic); bench.py uses the delta for `gpu_launches`.
+ */
+int64_t dvg_kernel_launch_count(void);
+
+/*
+ * Sharded variants for one-process-per-GPU runs.  Pixel samples
+ * [sample_begin, sample_end) of the global index space idx = ((y*W+x)*nsy+sy)*nsx+sx and the
+ * same range of boundary-sample indices are processed; RNG streams depend on the global
+ * idx only (pcg.h:32-40), so the union over ranks reproduces the single-GPU sample set.
+ * Row ranges are in pixels: rows [row_begin, row_end) of the image.
+ * The caller all-reduces d_params (NCCL) afterwards.
+ */
+int dvg_render_forward_rows(DvgScene *scene, const float *background, float *render_image,
+                            int width, int height, int num_samples_x, int num_samples_y, uint64_t seed,
+                            int use_prefiltering, int row_begin, int row_end, void *stream);
+int dvg_render_backward_rows(DvgScene *scene, const float *background, const float *d_render_image,
+                             int width, int height, int num_samples_x, int num_samples_y, uint64_t seed,
+                             int use_prefiltering, int row_begin, int row_end,
+                             float *d_params, float *d_background, uint32_t flags, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DIFFVG_B200_H */
