@@ -1,0 +1,57 @@
+"""ctypes binding of libdiffvg_b200.so (C ABI in include/diffvg_b200.h).
+
+There is deliberately no fallback: if the CUDA library has not been built, importing this
+module raises, and every render call needs a CUDA device."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libdiffvg_b200.so')
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError('diffvg_b200: %s is missing. Build it with `python -c "import __graft_entry__ as g; g.build()"` '
+                      '(nvcc, sm_100a); there is no CPU fallback.' % LIB_PATH)
+
+lib = ctypes.CDLL(LIB_PATH)
+
+_vp = ctypes.c_void_p
+_i = ctypes.c_int
+_u64 = ctypes.c_uint64
+_i64 = ctypes.c_int64
+
+lib.dvg_abi_version.restype = _i
+lib.dvg_last_error.restype = ctypes.c_char_p
+lib.dvg_kernel_launch_count.restype = _i64
+lib.dvg_scene_create.argtypes = [_vp, _i64, _i, ctypes.POINTER(_vp)]
+lib.dvg_scene_create.restype = _i
+lib.dvg_scene_set_params.argtypes = [_vp, _vp, _i64, _i, _vp]
+lib.dvg_scene_set_params.restype = _i
+lib.dvg_render_forward.argtypes = [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _u64, _i, _vp, _i, _vp]
+lib.dvg_render_forward.restype = _i
+lib.dvg_render_backward.argtypes = [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _u64, _i, _vp, _i, _vp, _vp, _vp,
+                                    ctypes.c_uint32, _vp]
+lib.dvg_render_backward.restype = _i
+lib.dvg_render_forward_rows.argtypes = [_vp, _vp, _vp, _i, _i, _i, _i, _u64, _i, _i, _i, _vp]
+lib.dvg_render_forward_rows.restype = _i
+lib.dvg_render_backward_rows.argtypes = [_vp, _vp, _vp, _i, _i, _i, _i, _u64, _i, _i, _i, _vp, _vp, ctypes.c_uint32, _vp]
+lib.dvg_render_backward_rows.restype = _i
+lib.dvg_scene_destroy.argtypes = [_vp]
+lib.dvg_scene_destroy.restype = _i
+lib.dvg_scene_dump.argtypes = [_vp, _i, _i, _vp, _i64, _vp]
+lib.dvg_scene_dump.restype = _i64
+
+DVG_ERR_UNSUPPORTED = 4
+DVG_BWD_SKIP_XFORM_GRAD = 1
+DVG_BWD_ACCUMULATE = 2
+
+
+def check(rc):
+    if rc != 0:
+        msg = lib.dvg_last_error().decode()
+        if rc == DVG_ERR_UNSUPPORTED:
+            raise NotImplementedError(msg)
+        raise RuntimeError(msg)
+
+
+def launch_count():
+    return int(lib.dvg_kernel_launch_count())

@@ -1,0 +1,138 @@
+// dvg_build.cu -- per-iteration scene build on the GPU: shape lengths, boundary-sampling
+// CDFs/PMFs, bounding boxes, primitive table and the tile bins the render kernels traverse.
+//
+// Replaces the single-threaded host work the reference redoes in every forward
+// (scene.cpp:113-333 lengths/CDFs, 496-684 boxes + three BVH levels).  Float prefix sums are
+// kept in the reference's sequential order (one thread per path; one thread for the shape
+// CDF) so that CDF entries -- and therefore which shape/segment a boundary sample picks --
+// are bit-identical.
+#include "dvg_internal.h"
+
+namespace dvg {
+
+__global__ void k_build_shapes(BuildView bv) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < bv.num_shapes) build_shape(bv, s);
+}
+__global__ void k_build_groups(BuildView bv) {
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < bv.num_groups) build_group(bv, g);
+}
+__global__ void k_build_prims(BuildView bv) {
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < bv.num_prims) build_prim(bv, e);
+}
+
+// scene.cpp:207-246.  Sequential float prefix sum in the reference's order (single thread),
+// then the normalisation in parallel by the rest of the block.
+__global__ void k_build_shape_cdf(BuildView bv) {
+    __shared__ float s_norm;
+    if (threadIdx.x == 0) s_norm = build_shape_cdf_serial(bv);
+    __syncthreads();
+    float norm = s_norm;
+    for (int i = threadIdx.x; i < bv.num_insts; i += blockDim.x) {
+        bv.shape_cdf[i] /= norm;
+        bv.shape_pmf[i] /= norm;
+    }
+}
+
+// ------------------------------------------------------------------ tile bins
+// One warp per tile.  Pass 0 counts, pass 1 fills (identical traversal; ballot prefix keeps
+// the primitive ids ascending inside a tile, i.e. already in compositing order).
+DVG_D bool overlaps(Box a, float x0, float y0, float x1, float y1) {
+    return a.x0 <= x1 && a.x1 >= x0 && a.y0 <= y1 && a.y1 >= y0;
+}
+
+template <int PASS>
+__global__ void k_bin(BuildView bv, BinBuild bb) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const int ntiles = bb.tiles_x * bb.tiles_y;
+    if (warp >= ntiles) return;
+    const int tx = warp % bb.tiles_x, ty = warp / bb.tiles_x;
+    // tile rectangle in canvas units, with a margin that also covers the +-1e-4 (normalised)
+    // offsets of boundary samples (diffvg.cpp:1416,1420) and float rounding of pt/W*canvas_w
+    const float cw = (float)bv.canvas_w, ch = (float)bv.canvas_h;
+    const float margin = 4e-4f * (cw > ch ? cw : ch) + 1e-4f;
+    const float x0 = ((float)(tx * bb.tile_w) / (float)bb.width) * cw - margin;
+    const float x1 = ((float)((tx + 1) * bb.tile_w) / (float)bb.width) * cw + margin;
+    const float y0 = ((float)(ty * bb.tile_h) / (float)bb.height) * ch - margin;
+    const float y1 = ((float)((ty + 1) * bb.tile_h) / (float)bb.height) * ch + margin;
+    int count = 0;
+    int *out = nullptr;
+    if (PASS == 1) out = bb.items + bb.offsets[warp];
+    for (int g0 = 0; g0 < bv.num_groups; g0 += 32) {
+        int g = g0 + lane;
+        bool hit = false;
+        if (g < bv.num_groups) {
+            if (bv.num_groups == 1) hit = true;
+            else {
+                const GroupInfo &gi = bv.groups[g];
+                Box b = gi.scene_box; float r = gi.scene_r;
+                b.x0 -= r; b.y0 -= r; b.x1 += r; b.y1 += r;
+                hit = overlaps(b, x0, y0, x1, y1) || !(b.x0 == b.x0 && b.x1 == b.x1 && b.y0 == b.y0 && b.y1 == b.y1);
+            }
+        }
+        unsigned gm = __ballot_sync(0xffffffffu, hit);
+        while (gm) {
+            int gl = __ffs(gm) - 1;
+            gm &= gm - 1;
+            const GroupInfo &gi = bv.groups[g0 + gl];
+            for (int e0 = gi.prim_begin; e0 < gi.prim_end; e0 += 32) {
+                int e = e0 + lane;
+                bool ph = e < gi.prim_end && overlaps(bv.prim_cbox[e], x0, y0, x1, y1);
+                unsigned pmask = __ballot_sync(0xffffffffu, ph);
+                if (PASS == 1 && ph) out[count + __popc(pmask & ((1u << lane) - 1))] = e;
+                count += __popc(pmask);
+            }
+        }
+    }
+    if (PASS == 0 && lane == 0) bb.counts[warp] = count;
+}
+
+// Single-block exclusive scan of `n` ints (n up to a few hundred thousand tiles): each thread
+// scans a contiguous slice, then a block-level scan of the slice totals.  out has n+1 entries.
+__global__ void k_exclusive_scan(const int *in, int *out, int n) {
+    __shared__ int s_tot[1024];
+    const int T = blockDim.x, t = threadIdx.x;
+    const int per = (n + T - 1) / T;
+    const int b = t * per, e = min(b + per, n);
+    int sum = 0;
+    for (int i = b; i < e; i++) sum += in[i];
+    s_tot[t] = sum;
+    __syncthreads();
+    for (int off = 1; off < T; off <<= 1) {
+        int v = t >= off ? s_tot[t - off] : 0;
+        __syncthreads();
+        s_tot[t] += v;
+        __syncthreads();
+    }
+    int run = s_tot[t] - sum;
+    for (int i = b; i < e; i++) { out[i] = run; run += in[i]; }
+    if (t == T - 1) out[n] = s_tot[T - 1];
+}
+
+void launch_build(const BuildView &bv, cudaStream_t st) {
+    const int B = 128;
+    DVG_LAUNCH(k_build_shapes, dim3((bv.num_shapes + B - 1) / B), dim3(B), 0, st, bv);
+    DVG_LAUNCH(k_build_groups, dim3((bv.num_groups + B - 1) / B), dim3(B), 0, st, bv);
+    DVG_LAUNCH(k_build_prims, dim3((bv.num_prims + B - 1) / B), dim3(B), 0, st, bv);
+    DVG_LAUNCH(k_build_shape_cdf, dim3(1), dim3(256), 0, st, bv);
+}
+
+void launch_bin_count(const BuildView &bv, const BinBuild &bb, cudaStream_t st) {
+    const int ntiles = bb.tiles_x * bb.tiles_y;
+    const int B = 128;  // 4 warps = 4 tiles per block
+    DVG_LAUNCH(k_bin<0>, dim3((ntiles * 32 + B - 1) / B), dim3(B), 0, st, bv, bb);
+    DVG_LAUNCH(k_exclusive_scan, dim3(1), dim3(1024), 0, st, bb.counts, bb.offsets, ntiles);
+}
+void launch_bin_fill(const BuildView &bv, const BinBuild &bb, cudaStream_t st) {
+    const int ntiles = bb.tiles_x * bb.tiles_y;
+    const int B = 128;
+    DVG_LAUNCH(k_bin<1>, dim3((ntiles * 32 + B - 1) / B), dim3(B), 0, st, bv, bb);
+}
+void launch_scan(const int *in, int *out, int n, cudaStream_t st) {
+    DVG_LAUNCH(k_exclusive_scan, dim3(1), dim3(1024), 0, st, in, out, n);
+}
+
+}  // namespace dvg

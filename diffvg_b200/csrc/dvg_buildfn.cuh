@@ -1,0 +1,313 @@
+// dvg_buildfn.cuh -- per-item bodies of the scene-build kernels (dvg_build.cu), written as
+// host/device functions so the same arithmetic can be exercised by the host-side test
+// harness (tests/host_emul/).  See dvg_build.cu for the launch structure.
+#pragma once
+#include "dvg_scene.cuh"
+#include "dvg_geom.cuh"
+
+namespace dvg {
+
+// Mutable view used by the build kernels (same arrays as SceneView, non-const).
+struct BuildView {
+    int canvas_w, canvas_h;
+    int num_shapes, num_groups, num_insts, num_prims;
+    const int *topo;
+    const float *params;
+    // topology-only maps (host-built at scene creation)
+    const int *inst_group, *inst_shape, *inst_prim_begin;  // inst_prim_begin has num_insts+1 entries
+    const int *prim_inst, *prim_seg, *prim_point_id;
+    // per shape
+    float *shapes_length; Box *shape_box; float *shape_r0;
+    // per segment
+    float *seg_cdf, *seg_pmf; int *seg_point_id;
+    // per instance / group / primitive
+    InstInfo *insts; GroupInfo *groups;
+    F4 *prim_p01, *prim_p23, *prim_rad; Box *prim_box; float *prim_thick; PrimMeta *prim_meta; Box *prim_cbox;
+    float *shape_cdf, *shape_pmf;
+    int *error_flag; float *total_length;
+};
+
+// ------------------------------------------------------------------ shapes
+// shapes_length (scene.cpp:113-205), shapes_bbox (499-629), per-path segment pmf/cdf/point-id
+// map (248-333) and the "first leaf after the y-sort" radius the reference uses as the group
+// radius of thickness paths (scene.cpp:602-618, 650-667).
+DVG_HD_NOINLINE void build_shape(const BuildView &bv, int s) {
+    const int *topo = bv.topo;
+    const float *P = bv.params;
+    const int *r = topo + topo[DVG_H_OFF_SHAPES] + s * DVG_SHAPE_REC_LEN;
+    const float *p = P + r[DVG_S_PARAM_OFF];
+    float stroke_width = r[DVG_S_WIDTH_OFF] >= 0 ? P[r[DVG_S_WIDTH_OFF]] : 0.f;
+    float len = 0.f;
+    Box box;
+    float r0q = stroke_width;
+    const float pi_f = (float)DVG_PI_D;
+    switch (r[DVG_S_TYPE]) {
+        case DVG_SHAPE_CIRCLE:
+            len += (float)(2.f * DVG_PI_D) * p[0];
+            box.x0 = p[1] - p[0]; box.y0 = p[2] - p[0]; box.x1 = p[1] + p[0]; box.y1 = p[2] + p[0];
+            break;
+        case DVG_SHAPE_ELLIPSE: {
+            float a = p[0], b = p[1];
+            len += pi_f * (3 * (a + b) - sqrtf((3 * a + b) * (a + 3 * b)));
+            box.x0 = p[2] - p[0]; box.y0 = p[3] - p[1]; box.x1 = p[2] + p[0]; box.y1 = p[3] + p[1];
+            break;
+        }
+        case DVG_SHAPE_RECT:
+            len += 2 * (p[2] - p[0] + p[3] - p[1]);
+            box.x0 = p[0]; box.y0 = p[1]; box.x1 = p[2]; box.y1 = p[3];
+            break;
+        default: {
+            const int np = r[DVG_S_NUM_POINTS], nseg = r[DVG_S_NUM_SEGS];
+            const int *ncp = topo + topo[DVG_H_OFF_NCP] + r[DVG_S_NCP_OFF];
+            const float *thick = r[DVG_S_THICK_OFF] >= 0 ? P + r[DVG_S_THICK_OFF] : nullptr;
+            float *seg_pmf = bv.seg_pmf + r[DVG_S_NCP_OFF];
+            float *seg_cdf = bv.seg_cdf + r[DVG_S_NCP_OFF];
+            int *seg_pid = bv.seg_point_id + r[DVG_S_NCP_OFF];
+            box.x0 = box.y0 = INFINITY; box.x1 = box.y1 = -INFINITY;
+            if (np > 0) { box.x0 = box.x1 = p[0]; box.y0 = box.y1 = p[1]; }
+            for (int i = 1; i < np; i++) {
+                float x = p[2 * i], y = p[2 * i + 1];
+                box.x0 = rminf(x, box.x0); box.y0 = rminf(y, box.y0);
+                box.x1 = rmaxf(x, box.x1); box.y1 = rmaxf(y, box.y1);
+            }
+            float length = 0.f;
+            int pid = 0;
+            float best_y = INFINITY;
+            // pass 1: total length (scene.cpp:132-191); raw segment lengths parked in seg_pmf
+            for (int i = 0; i < nseg; i++) {
+                seg_pid[i] = pid;
+                float d;
+                float ymin, ymax, th;
+                if (ncp[i] == 0) {
+                    int i0 = pid, i1 = (i0 + 1) % np;
+                    F2 p0 = mk2(p[2 * i0], p[2 * i0 + 1]), p1 = mk2(p[2 * i1], p[2 * i1 + 1]);
+                    d = distance2(p1, p0);
+                    ymin = rminf(p1.y, rminf(p0.y, INFINITY)); ymax = rmaxf(p1.y, rmaxf(p0.y, -INFINITY));
+                    th = thick ? rmaxf(thick[i0], thick[i1]) : stroke_width;
+                    pid += 1;
+                } else if (ncp[i] == 1) {
+                    int i0 = pid, i1 = i0 + 1, i2 = (i0 + 2) % np;
+                    F2 p0 = mk2(p[2 * i0], p[2 * i0 + 1]), p1 = mk2(p[2 * i1], p[2 * i1 + 1]), p2 = mk2(p[2 * i2], p[2 * i2 + 1]);
+                    F2 v1 = eval_quad(p0, p1, p2, 0.5f);
+                    d = distance2(v1, p0) + distance2(v1, p2);
+                    ymin = rminf(p2.y, rminf(p1.y, rminf(p0.y, INFINITY)));
+                    ymax = rmaxf(p2.y, rmaxf(p1.y, rmaxf(p0.y, -INFINITY)));
+                    th = thick ? rmaxf(rmaxf(thick[i0], thick[i1]), thick[i2]) : stroke_width;
+                    pid += 2;
+                } else {
+                    int i0 = pid, i1 = i0 + 1, i2 = i0 + 2, i3 = (i0 + 3) % np;
+                    F2 p0 = mk2(p[2 * i0], p[2 * i0 + 1]), p1 = mk2(p[2 * i1], p[2 * i1 + 1]);
+                    F2 p2 = mk2(p[2 * i2], p[2 * i2 + 1]), p3 = mk2(p[2 * i3], p[2 * i3 + 1]);
+                    F2 v1 = eval_cubic(p0, p1, p2, p3, 1.f / 3.f), v2 = eval_cubic(p0, p1, p2, p3, 2.f / 3.f);
+                    d = distance2(v1, p0) + distance2(v1, v2) + distance2(v2, p3);
+                    ymin = rminf(p3.y, rminf(p2.y, rminf(p1.y, rminf(p0.y, INFINITY))));
+                    ymax = rmaxf(p3.y, rmaxf(p2.y, rmaxf(p1.y, rmaxf(p0.y, -INFINITY))));
+                    th = thick ? rmaxf(rmaxf(rmaxf(thick[i0], thick[i1]), thick[i2]), thick[i3]) : stroke_width;
+                    pid += 3;
+                }
+                length += d;
+                seg_pmf[i] = d;
+                float yc = 0.5f * (ymin + ymax);
+                if (yc < best_y) { best_y = yc; if (thick) r0q = th; }
+            }
+            len += length;
+            // pass 2: pmf / cdf with the reciprocal of the total (scene.cpp:257-326)
+            float inv_length = 1.f / len;
+            float c = 0.f;
+            for (int i = 0; i < nseg; i++) {
+                float d = seg_pmf[i] * inv_length;
+                seg_pmf[i] = d;
+                c = (i == 0) ? d : d + c;
+                seg_cdf[i] = c;
+            }
+            break;
+        }
+    }
+    bv.shapes_length[s] = len;
+    bv.shape_box[s] = box;
+    bv.shape_r0[s] = r0q;
+}
+
+DVG_HD Box box_merge(Box a, Box b) {
+    Box o;
+    o.x0 = rminf(a.x0, b.x0); o.y0 = rminf(a.y0, b.y0); o.x1 = rmaxf(a.x1, b.x1); o.y1 = rmaxf(a.y1, b.y1);
+    return o;
+}
+DVG_HD Box box_merge_pt(Box a, F2 p) {
+    Box o;
+    o.x0 = rminf(p.x, a.x0); o.y0 = rminf(p.y, a.y0); o.x1 = rmaxf(p.x, a.x1); o.y1 = rmaxf(p.y, a.y1);
+    return o;
+}
+DVG_HD Box box_transform(const float *m, Box b) {  // aabb.h:52-60
+    Box o; o.x0 = o.y0 = INFINITY; o.x1 = o.y1 = -INFINITY;
+    o = box_merge_pt(o, xform_pt(m, mk2(b.x0, b.y0)));
+    o = box_merge_pt(o, xform_pt(m, mk2(b.x0, b.y1)));
+    o = box_merge_pt(o, xform_pt(m, mk2(b.x1, b.y0)));
+    o = box_merge_pt(o, xform_pt(m, mk2(b.x1, b.y1)));
+    return o;
+}
+
+
+// ------------------------------------------------------------------ groups
+// transforms, group root box, scene-BVH leaf box and radius (scene.cpp:632-682, shape.h:122-124)
+DVG_HD_NOINLINE void build_group(const BuildView &bv, int g) {
+    const int *topo = bv.topo;
+    const float *P = bv.params;
+    const int *r = topo + topo[DVG_H_OFF_GROUPS] + g * DVG_GROUP_REC_LEN;
+    const int *ids = topo + topo[DVG_H_OFF_GSHAPES] + r[DVG_G_SHAPES_OFF];
+    GroupInfo gi;
+    gi.fill_type = r[DVG_G_FILL_TYPE]; gi.fill_off = r[DVG_G_FILL_OFF]; gi.fill_stops = r[DVG_G_FILL_STOPS];
+    gi.stroke_type = r[DVG_G_STROKE_TYPE]; gi.stroke_off = r[DVG_G_STROKE_OFF]; gi.stroke_stops = r[DVG_G_STROKE_STOPS];
+    gi.num_shapes = r[DVG_G_NUM_SHAPES];
+    gi.inst_begin = r[DVG_G_SHAPES_OFF];
+    gi.prim_begin = bv.inst_prim_begin[gi.inst_begin];
+    gi.prim_end = bv.inst_prim_begin[gi.inst_begin + gi.num_shapes];
+    gi.xform_off = r[DVG_G_XFORM_OFF];
+    gi.pad = 0;
+    const float *m = P + r[DVG_G_XFORM_OFF];
+    for (int k = 0; k < 9; k++) gi.s2c[k] = m[k];
+    inverse3(gi.s2c, gi.c2s);
+    bool ident = m[0] == 1.f && m[1] == 0.f && m[2] == 0.f && m[3] == 0.f && m[4] == 1.f && m[5] == 0.f &&
+                 m[6] == 0.f && m[7] == 0.f && m[8] == 1.f;
+    bool affine = m[6] == 0.f && m[7] == 0.f && m[8] == 1.f;
+    gi.flags = (r[DVG_G_EVEN_ODD] ? DVG_GF_EVEN_ODD : 0) | (ident ? DVG_GF_IDENTITY : 0) | (affine ? DVG_GF_AFFINE : 0);
+    Box lb = bv.shape_box[ids[0]];
+    float max_radius = bv.shape_r0[ids[0]];
+    for (int k = 1; k < gi.num_shapes; k++) {
+        lb = box_merge(lb, bv.shape_box[ids[k]]);
+        float rr = bv.shape_r0[ids[k]];
+        max_radius = max_radius > rr ? max_radius : rr;  // std::max(a, b): (a < b) ? b : a
+    }
+    gi.local_box = lb;
+    gi.scene_box = box_transform(gi.s2c, lb);
+    gi.scene_r = gi.stroke_type < 0 ? 0.f : max_radius;
+    bv.groups[g] = gi;
+}
+
+// ------------------------------------------------------------------ primitives
+// Leaf boxes and radii follow scene.cpp:527-600 (topology-only maps prim -> inst / segment /
+// first point come from the host).
+DVG_HD_NOINLINE void build_prim(const BuildView &bv, int e) {
+    const int *topo = bv.topo;
+    const float *P = bv.params;
+    const int inst = bv.prim_inst[e];
+    const int g = bv.inst_group[inst], s = bv.inst_shape[inst];
+    const GroupInfo &gi = bv.groups[g];
+    const int *r = topo + topo[DVG_H_OFF_SHAPES] + s * DVG_SHAPE_REC_LEN;
+    const float *p = P + r[DVG_S_PARAM_OFF];
+    const float sw = r[DVG_S_WIDTH_OFF] >= 0 ? P[r[DVG_S_WIDTH_OFF]] : 0.f;
+    const bool has_stroke = gi.stroke_type >= 0, has_fill = gi.fill_type >= 0;
+    F4 p01 = mk4(0, 0, 0, 0), p23 = mk4(0, 0, 0, 0), rad = mk4(sw, sw, sw, sw);
+    Box box;
+    float thick = sw;
+    PrimMeta pm;
+    pm.inst = inst; pm.point_id = 0; pm.base_id = 0;
+    int tf;
+    const bool first_in_inst = (e == bv.inst_prim_begin[inst]);
+    switch (r[DVG_S_TYPE]) {
+        case DVG_SHAPE_CIRCLE:
+            tf = PRIM_CIRCLE | DVG_PF_SINGLE;
+            p01 = mk4(p[1], p[2], p[0], 0.f);
+            box = bv.shape_box[s];
+            break;
+        case DVG_SHAPE_ELLIPSE:
+            tf = PRIM_ELLIPSE | DVG_PF_SINGLE;
+            p01 = mk4(p[2], p[3], p[0], p[1]);
+            box = bv.shape_box[s];
+            break;
+        case DVG_SHAPE_RECT:
+            tf = PRIM_RECT | DVG_PF_SINGLE;
+            p01 = mk4(p[0], p[1], p[2], p[3]);
+            box = bv.shape_box[s];
+            break;
+        default: {
+            const int np = r[DVG_S_NUM_POINTS], nseg = r[DVG_S_NUM_SEGS];
+            const int seg = bv.prim_seg[e], pid = bv.prim_point_id[e];
+            const int *ncp = topo + topo[DVG_H_OFF_NCP] + r[DVG_S_NCP_OFF];
+            const float *th = r[DVG_S_THICK_OFF] >= 0 ? P + r[DVG_S_THICK_OFF] : nullptr;
+            pm.point_id = pid; pm.base_id = seg;
+            const int n = ncp[seg];
+            tf = n | (nseg == 1 ? DVG_PF_SINGLE : 0) | (th ? DVG_PF_THICK : 0) |
+                 ((r[DVG_S_FLAGS] & DVG_SF_DISTANCE_APPROX) ? DVG_PF_APPROX : 0);
+            int i0 = pid, i1, i2 = 0, i3 = 0;
+            if (n == 0) { i1 = (i0 + 1) % np; }
+            else if (n == 1) { i1 = i0 + 1; i2 = (i0 + 2) % np; }
+            else { i1 = i0 + 1; i2 = i0 + 2; i3 = (i0 + 3) % np; }
+            F2 q0 = mk2(p[2 * i0], p[2 * i0 + 1]), q1 = mk2(p[2 * i1], p[2 * i1 + 1]);
+            box.x0 = box.y0 = INFINITY; box.x1 = box.y1 = -INFINITY;
+            box = box_merge_pt(box, q0);
+            box = box_merge_pt(box, q1);
+            p01 = mk4(q0.x, q0.y, q1.x, q1.y);
+            if (th) { rad.x = th[i0]; rad.y = th[i1]; thick = rmaxf(rad.x, rad.y); }
+            if (n >= 1) {
+                F2 q2 = mk2(p[2 * i2], p[2 * i2 + 1]);
+                box = box_merge_pt(box, q2);
+                p23.x = q2.x; p23.y = q2.y;
+                if (th) { rad.z = th[i2]; thick = rmaxf(thick, rad.z); }
+            }
+            if (n >= 2) {
+                F2 q3 = mk2(p[2 * i3], p[2 * i3 + 1]);
+                box = box_merge_pt(box, q3);
+                p23.z = q3.x; p23.w = q3.y;
+                if (th) { rad.w = th[i3]; thick = rmaxf(thick, rad.w); }
+            }
+            break;
+        }
+    }
+    if (first_in_inst) tf |= DVG_PF_FIRST;
+    if (e == gi.prim_begin) tf |= DVG_PF_GFIRST;
+    pm.type_flags = tf;
+    bv.prim_p01[e] = p01; bv.prim_p23[e] = p23; bv.prim_rad[e] = rad;
+    bv.prim_box[e] = box; bv.prim_thick[e] = thick; bv.prim_meta[e] = pm;
+    if (first_in_inst) {
+        InstInfo ii;
+        ii.box = bv.shape_box[s];
+        ii.r = has_stroke ? sw : 0.f;   // scene.cpp:638
+        ii.group = g; ii.shape = s; ii.prim_begin = e;
+        bv.insts[inst] = ii;
+    }
+    // Conservative canvas-space bound of the region where this primitive can change a sample
+    // (used only for binning; the exact per-sample predicates are evaluated in the kernels).
+    Box reg; reg.x0 = reg.y0 = INFINITY; reg.x1 = reg.y1 = -INFINITY;
+    if (has_stroke) {
+        Box sb; sb.x0 = box.x0 - thick; sb.y0 = box.y0 - thick; sb.x1 = box.x1 + thick; sb.y1 = box.y1 + thick;
+        reg = box_merge(reg, sb);
+    }
+    if (has_fill) {
+        Box fb; fb.x0 = rminf(gi.local_box.x0, box.x0); fb.y0 = box.y0; fb.x1 = box.x1; fb.y1 = box.y1;
+        reg = box_merge(reg, fb);
+    }
+    Box cb;
+    const float big = 3.0e38f;
+    if (!has_stroke && !has_fill) { cb.x0 = cb.y0 = big; cb.x1 = cb.y1 = -big; }
+    else if (gi.flags & DVG_GF_IDENTITY) cb = reg;
+    else if ((gi.flags & DVG_GF_AFFINE) && reg.x0 <= reg.x1) cb = box_transform(gi.s2c, reg);
+    else { cb.x0 = cb.y0 = -big; cb.x1 = cb.y1 = big; }
+    if (bv.num_groups > 1) {  // the group is only visited inside its scene-BVH leaf box (+ radius)
+        cb.x0 = rmaxf(cb.x0, gi.scene_box.x0 - gi.scene_r); cb.y0 = rmaxf(cb.y0, gi.scene_box.y0 - gi.scene_r);
+        cb.x1 = rminf(cb.x1, gi.scene_box.x1 + gi.scene_r); cb.y1 = rminf(cb.y1, gi.scene_box.y1 + gi.scene_r);
+    }
+    if (!(cb.x0 == cb.x0 && cb.x1 == cb.x1 && cb.y0 == cb.y0 && cb.y1 == cb.y1)) {  // NaN -> everywhere
+        cb.x0 = cb.y0 = -big; cb.x1 = cb.y1 = big;
+    }
+    bv.prim_cbox[e] = cb;
+}
+
+// ------------------------------------------------------------------ shape CDF (sequential part)
+// scene.cpp:207-235: float prefix sum in the reference's order; returns the normalisation.
+DVG_HD_NOINLINE float build_shape_cdf_serial(const BuildView &bv) {
+    float c = 0.f;
+    for (int i = 0; i < bv.num_insts; i++) {
+        float len = bv.shapes_length[bv.inst_shape[i]];
+        c = (i == 0) ? len : len + c;
+        bv.shape_cdf[i] = c;
+        bv.shape_pmf[i] = len;
+    }
+    if (!(c > 0.f)) *bv.error_flag = 1;            // scene.cpp:231-235 (also catches NaN)
+    else if (isinf(c)) *bv.error_flag = 2;          // scene.cpp:236-240
+    else *bv.error_flag = 0;
+    *bv.total_length = c;
+    return c;
+}
+
+}  // namespace dvg

@@ -1,0 +1,518 @@
+// dvg_capi.cu -- host side of the C ABI declared in include/diffvg_b200.h.
+#include "dvg_internal.h"
+#include "../../include/diffvg_b200.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace dvg {
+long long g_launch_count = 0;
+}
+
+using namespace dvg;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+
+#define CK(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e__ = (call);                                                             \
+        if (e__ != cudaSuccess)                                                               \
+            return fail(DVG_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));   \
+    } while (0)
+
+// Grow-only device buffer: no cudaMalloc on the steady-state path (the reference allocates
+// and frees managed memory inside every render(), diffvg.cpp:1509, 1567-1572).
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <typename T> T *as() const { return (T *)p; }
+};
+
+struct DeviceGuard {
+    int old = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&old); if (old != dev) cudaSetDevice(dev); else old = -1; }
+    ~DeviceGuard() { if (old >= 0) cudaSetDevice(old); }
+};
+
+}  // namespace
+
+struct DvgScene {
+    int device = 0;
+    std::vector<int32_t> topo;
+    int canvas_w = 0, canvas_h = 0, num_shapes = 0, num_groups = 0, num_insts = 0, num_prims = 0;
+    int num_params = 0, total_segs = 0;
+    // host topology maps
+    std::vector<int> inst_group, inst_shape, inst_prim_begin, prim_inst, prim_seg, prim_point_id;
+    // device: topology
+    DevBuf d_topo, d_inst_group, d_inst_shape, d_inst_prim_begin, d_prim_inst, d_prim_seg, d_prim_point_id;
+    // device: parameters + derived tables
+    DevBuf d_params, d_shapes_length, d_shape_box, d_shape_r0, d_seg_cdf, d_seg_pmf, d_seg_point_id;
+    DevBuf d_insts, d_groups, d_p01, d_p23, d_rad, d_box, d_thick, d_meta, d_cbox, d_shape_cdf, d_shape_pmf;
+    DevBuf d_flags;  // [0] error flag, [1] total length (float bits)
+    // bins
+    DevBuf d_bin_counts, d_bin_offsets, d_bin_items;
+    int bin_w = 0, bin_h = 0, bin_tw = 0, bin_th = 0;  // configuration the bins were built for (0 = none)
+    // per-render workspaces
+    DevBuf d_weight;
+    int w_w = 0, w_h = 0, w_nsx = 0, w_nsy = 0, w_ftype = -1;
+    uint64_t w_seed = 0; float w_radius = 0; bool w_valid = false;
+    DevBuf d_keys, d_tile_counts, d_tile_offsets, d_tile_fill, d_blk_counts, d_blk_offsets, d_sorted;
+    int32_t *h_pinned = nullptr;  // [0] error flag, [1] total bin items
+    bool params_set = false;
+    bool checked = false;
+    int scene_error = 0;
+    float filter_radius_host = 0.5f;  // refreshed with the error-flag read-back
+
+    BuildView build_view() {
+        BuildView bv;
+        bv.canvas_w = canvas_w; bv.canvas_h = canvas_h;
+        bv.num_shapes = num_shapes; bv.num_groups = num_groups; bv.num_insts = num_insts; bv.num_prims = num_prims;
+        bv.topo = d_topo.as<int>(); bv.params = d_params.as<float>();
+        bv.inst_group = d_inst_group.as<int>(); bv.inst_shape = d_inst_shape.as<int>();
+        bv.inst_prim_begin = d_inst_prim_begin.as<int>();
+        bv.prim_inst = d_prim_inst.as<int>(); bv.prim_seg = d_prim_seg.as<int>(); bv.prim_point_id = d_prim_point_id.as<int>();
+        bv.shapes_length = d_shapes_length.as<float>(); bv.shape_box = d_shape_box.as<Box>(); bv.shape_r0 = d_shape_r0.as<float>();
+        bv.seg_cdf = d_seg_cdf.as<float>(); bv.seg_pmf = d_seg_pmf.as<float>(); bv.seg_point_id = d_seg_point_id.as<int>();
+        bv.insts = d_insts.as<InstInfo>(); bv.groups = d_groups.as<GroupInfo>();
+        bv.prim_p01 = d_p01.as<F4>(); bv.prim_p23 = d_p23.as<F4>(); bv.prim_rad = d_rad.as<F4>();
+        bv.prim_box = d_box.as<Box>(); bv.prim_thick = d_thick.as<float>(); bv.prim_meta = d_meta.as<PrimMeta>();
+        bv.prim_cbox = d_cbox.as<Box>();
+        bv.shape_cdf = d_shape_cdf.as<float>(); bv.shape_pmf = d_shape_pmf.as<float>();
+        bv.error_flag = d_flags.as<int>(); bv.total_length = d_flags.as<float>() + 1;
+        return bv;
+    }
+    SceneView view() {
+        SceneView sc;
+        sc.canvas_w = canvas_w; sc.canvas_h = canvas_h;
+        sc.num_shapes = num_shapes; sc.num_groups = num_groups; sc.num_insts = num_insts; sc.num_prims = num_prims;
+        sc.filter.type = topo[DVG_H_FILTER_TYPE];
+        sc.filter.radius = filter_radius_host;
+        sc.filter_radius_off = topo[DVG_H_FILTER_RADIUS_OFF];
+        sc.topo = d_topo.as<int>(); sc.params = d_params.as<float>();
+        sc.prim_p01 = d_p01.as<F4>(); sc.prim_p23 = d_p23.as<F4>(); sc.prim_rad = d_rad.as<F4>();
+        sc.prim_box = d_box.as<Box>(); sc.prim_thick = d_thick.as<float>(); sc.prim_meta = d_meta.as<PrimMeta>();
+        sc.prim_cbox = d_cbox.as<Box>();
+        sc.insts = d_insts.as<InstInfo>(); sc.groups = d_groups.as<GroupInfo>();
+        sc.shapes_length = d_shapes_length.as<float>();
+        sc.shape_cdf = d_shape_cdf.as<float>(); sc.shape_pmf = d_shape_pmf.as<float>();
+        sc.seg_cdf = d_seg_cdf.as<float>(); sc.seg_pmf = d_seg_pmf.as<float>(); sc.seg_point_id = d_seg_point_id.as<int>();
+        sc.error_flag = d_flags.as<int>();
+        return sc;
+    }
+    BinView bin_view() {
+        BinView b;
+        b.tile_w = bin_tw; b.tile_h = bin_th;
+        b.tiles_x = (bin_w + bin_tw - 1) / bin_tw; b.tiles_y = (bin_h + bin_th - 1) / bin_th;
+        b.offsets = d_bin_offsets.as<int>(); b.items = d_bin_items.as<int>();
+        return b;
+    }
+    void release_all() {
+        DevBuf *all[] = {&d_topo, &d_inst_group, &d_inst_shape, &d_inst_prim_begin, &d_prim_inst, &d_prim_seg,
+                         &d_prim_point_id, &d_params, &d_shapes_length, &d_shape_box, &d_shape_r0, &d_seg_cdf, &d_seg_pmf,
+                         &d_seg_point_id, &d_insts, &d_groups, &d_p01, &d_p23, &d_rad, &d_box, &d_thick, &d_meta, &d_cbox,
+                         &d_shape_cdf, &d_shape_pmf, &d_flags, &d_bin_counts, &d_bin_offsets, &d_bin_items, &d_weight,
+                         &d_keys, &d_tile_counts, &d_tile_offsets, &d_tile_fill, &d_blk_counts, &d_blk_offsets, &d_sorted};
+        for (DevBuf *b : all) b->release();
+        if (h_pinned) cudaFreeHost(h_pinned);
+        h_pinned = nullptr;
+    }
+};
+
+namespace {
+
+template <typename T>
+int upload(DevBuf &buf, const std::vector<T> &v) {
+    size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(T);
+    CK(buf.ensure(bytes));
+    if (!v.empty()) CK(cudaMemcpy(buf.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return DVG_OK;
+}
+
+int validate_topo(const int32_t *t, int64_t len) {
+    if (len < DVG_TOPO_HEADER_LEN) return fail(DVG_ERR_INVALID, "topo shorter than its header");
+    if (t[DVG_H_MAGIC] != DVG_TOPO_MAGIC) return fail(DVG_ERR_INVALID, "bad topo magic");
+    const int ns = t[DVG_H_NUM_SHAPES], ng = t[DVG_H_NUM_GROUPS], np = t[DVG_H_NUM_PARAMS];
+    if (ns <= 0 || ng <= 0) return fail(DVG_ERR_INVALID, "scene needs at least one shape and one shape group");
+    if (t[DVG_H_CANVAS_W] <= 0 || t[DVG_H_CANVAS_H] <= 0) return fail(DVG_ERR_INVALID, "bad canvas size");
+    auto in = [&](int64_t off, int64_t n) { return off >= DVG_TOPO_HEADER_LEN && n >= 0 && off + n <= len; };
+    if (!in(t[DVG_H_OFF_SHAPES], (int64_t)ns * DVG_SHAPE_REC_LEN) || !in(t[DVG_H_OFF_GROUPS], (int64_t)ng * DVG_GROUP_REC_LEN) ||
+        !in(t[DVG_H_OFF_NCP], t[DVG_H_TOTAL_SEGS]) || !in(t[DVG_H_OFF_GSHAPES], t[DVG_H_TOTAL_GSHAPES]))
+        return fail(DVG_ERR_INVALID, "topo section out of bounds");
+    auto pin = [&](int off, int n) { return off >= 0 && n >= 0 && (int64_t)off + n <= np; };
+    if (t[DVG_H_FILTER_TYPE] < 0 || t[DVG_H_FILTER_TYPE] > 3) return fail(DVG_ERR_INVALID, "bad filter type");
+    if (!pin(t[DVG_H_FILTER_RADIUS_OFF], 1)) return fail(DVG_ERR_INVALID, "filter radius offset out of range");
+    for (int i = 0; i < ns; i++) {
+        const int32_t *r = t + t[DVG_H_OFF_SHAPES] + i * DVG_SHAPE_REC_LEN;
+        int nfl;
+        switch (r[DVG_S_TYPE]) {
+            case DVG_SHAPE_CIRCLE: nfl = 3; break;
+            case DVG_SHAPE_ELLIPSE: nfl = 4; break;
+            case DVG_SHAPE_RECT: nfl = 4; break;
+            case DVG_SHAPE_PATH: {
+                const int npts = r[DVG_S_NUM_POINTS], nseg = r[DVG_S_NUM_SEGS];
+                if (npts <= 0 || nseg <= 0) return fail(DVG_ERR_INVALID, "path with no points or segments");
+                if (r[DVG_S_NCP_OFF] < 0 || r[DVG_S_NCP_OFF] + nseg > t[DVG_H_TOTAL_SEGS])
+                    return fail(DVG_ERR_INVALID, "path ncp range out of bounds");
+                const int32_t *ncp = t + t[DVG_H_OFF_NCP] + r[DVG_S_NCP_OFF];
+                int need = 0;
+                for (int k = 0; k < nseg; k++) {
+                    if (ncp[k] < 0 || ncp[k] > 2) return fail(DVG_ERR_INVALID, "num_control_points must be 0, 1 or 2");
+                    need += ncp[k] + 1;
+                }
+                // closed paths wrap the last end point onto point 0; open ones need it explicitly
+                // segment point indices wrap modulo num_points (closed paths), as in the reference
+                if (need > npts) return fail(DVG_ERR_INVALID, "path has fewer points than its segments need");
+                if (r[DVG_S_THICK_OFF] >= 0 && !pin(r[DVG_S_THICK_OFF], npts))
+                    return fail(DVG_ERR_INVALID, "path thickness out of params range");
+                nfl = 2 * npts;
+                break;
+            }
+            default: return fail(DVG_ERR_INVALID, "bad shape type");
+        }
+        if (!pin(r[DVG_S_PARAM_OFF], nfl)) return fail(DVG_ERR_INVALID, "shape params out of range");
+        if (r[DVG_S_WIDTH_OFF] >= 0 && !pin(r[DVG_S_WIDTH_OFF], 1)) return fail(DVG_ERR_INVALID, "stroke width offset out of range");
+    }
+    for (int g = 0; g < ng; g++) {
+        const int32_t *r = t + t[DVG_H_OFF_GROUPS] + g * DVG_GROUP_REC_LEN;
+        if (r[DVG_G_NUM_SHAPES] <= 0 || r[DVG_G_SHAPES_OFF] < 0 || r[DVG_G_SHAPES_OFF] + r[DVG_G_NUM_SHAPES] > t[DVG_H_TOTAL_GSHAPES])
+            return fail(DVG_ERR_INVALID, "group shape list out of bounds");
+        const int32_t *ids = t + t[DVG_H_OFF_GSHAPES] + r[DVG_G_SHAPES_OFF];
+        for (int k = 0; k < r[DVG_G_NUM_SHAPES]; k++) {
+            if (ids[k] < 0 || ids[k] >= ns) return fail(DVG_ERR_INVALID, "group references a shape id out of range");
+            const int32_t *sr = t + t[DVG_H_OFF_SHAPES] + ids[k] * DVG_SHAPE_REC_LEN;
+            if (sr[DVG_S_TYPE] == DVG_SHAPE_ELLIPSE && r[DVG_G_STROKE_TYPE] >= 0)
+                return fail(DVG_ERR_UNSUPPORTED, "stroked ellipses are not supported (the reference asserts: within_distance.h:342-345)");
+        }
+        for (int which = 0; which < 2; which++) {
+            const int type = r[which ? DVG_G_STROKE_TYPE : DVG_G_FILL_TYPE];
+            const int off = r[which ? DVG_G_STROKE_OFF : DVG_G_FILL_OFF];
+            const int stops = r[which ? DVG_G_STROKE_STOPS : DVG_G_FILL_STOPS];
+            if (type < -1 || type > 2) return fail(DVG_ERR_INVALID, "bad colour type");
+            if (type == 0 && !pin(off, 4)) return fail(DVG_ERR_INVALID, "colour out of params range");
+            if (type > 0 && (stops <= 0 || !pin(off, 4 + 5 * stops))) return fail(DVG_ERR_INVALID, "gradient out of params range");
+        }
+        if (!pin(r[DVG_G_XFORM_OFF], 9)) return fail(DVG_ERR_INVALID, "shape_to_canvas out of params range");
+    }
+    return DVG_OK;
+}
+
+void choose_tile(int spp, int *tw, int *th) {
+    if (spp >= 16) { *tw = 8; *th = 2; }
+    else if (spp >= 4) { *tw = 8; *th = 8; }
+    else if (spp >= 2) { *tw = 16; *th = 8; }
+    else { *tw = 16; *th = 16; }
+}
+
+// Synchronise once after the build to learn (a) whether the scene is degenerate
+// (scene.cpp:231-240 throws) and (b) the filter radius / bin size needed by later launches.
+int finish_build(DvgScene *s, cudaStream_t st) {
+    if (s->checked) return s->scene_error ? fail(DVG_ERR_SCENE, g_err) : DVG_OK;
+    CK(cudaMemcpyAsync(s->h_pinned, s->d_flags.p, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(s->h_pinned + 2, s->d_params.as<float>() + s->topo[DVG_H_FILTER_RADIUS_OFF], 4,
+                       cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    s->checked = true;
+    s->scene_error = s->h_pinned[0];
+    float total; memcpy(&total, &s->h_pinned[1], 4);
+    memcpy(&s->filter_radius_host, &s->h_pinned[2], 4);
+    if (s->scene_error) {
+        char buf[256];
+        if (s->scene_error == 1)
+            snprintf(buf, sizeof buf, "The total length of the shape boundaries in the scene is equal or less than 0. Length = %f", total);
+        else
+            snprintf(buf, sizeof buf, "The total length of the shape boundaries in the scene is not a number. Length = %f", total);
+        return fail(DVG_ERR_SCENE, buf);
+    }
+    return DVG_OK;
+}
+
+int ensure_bins(DvgScene *s, int width, int height, int spp, cudaStream_t st) {
+    int tw, th;
+    choose_tile(spp, &tw, &th);
+    if (s->bin_w == width && s->bin_h == height && s->bin_tw == tw && s->bin_th == th) return DVG_OK;
+    BinBuild bb;
+    bb.width = width; bb.height = height; bb.tile_w = tw; bb.tile_h = th;
+    bb.tiles_x = (width + tw - 1) / tw; bb.tiles_y = (height + th - 1) / th;
+    const int ntiles = bb.tiles_x * bb.tiles_y;
+    CK(s->d_bin_counts.ensure(sizeof(int) * ntiles));
+    CK(s->d_bin_offsets.ensure(sizeof(int) * (ntiles + 1)));
+    bb.counts = s->d_bin_counts.as<int>(); bb.offsets = s->d_bin_offsets.as<int>(); bb.items = nullptr;
+    BuildView bv = s->build_view();
+    launch_bin_count(bv, bb, st);
+    CK(cudaMemcpyAsync(s->h_pinned + 3, bb.offsets + ntiles, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const int total = s->h_pinned[3];
+    CK(s->d_bin_items.ensure(sizeof(int) * std::max(total, 1)));
+    bb.items = s->d_bin_items.as<int>();
+    launch_bin_fill(bv, bb, st);
+    CK(cudaGetLastError());
+    s->bin_w = width; s->bin_h = height; s->bin_tw = tw; s->bin_th = th;
+    return DVG_OK;
+}
+
+int ensure_weight(DvgScene *s, const SceneView &sc, RenderArgs &ra, cudaStream_t st) {
+    CK(s->d_weight.ensure(sizeof(float) * (size_t)ra.width * ra.height));
+    ra.weight_image = s->d_weight.as<float>();
+    if (s->w_valid && s->w_w == ra.width && s->w_h == ra.height && s->w_nsx == ra.nsx && s->w_nsy == ra.nsy &&
+        s->w_seed == ra.seed && s->w_ftype == sc.filter.type && s->w_radius == sc.filter.radius)
+        return DVG_OK;  // weights depend only on (size, spp, seed, filter): reuse forward's in backward
+    CK(cudaMemsetAsync(ra.weight_image, 0, sizeof(float) * (size_t)ra.width * ra.height, st));
+    launch_weight(sc, ra, st);
+    s->w_valid = true; s->w_w = ra.width; s->w_h = ra.height; s->w_nsx = ra.nsx; s->w_nsy = ra.nsy;
+    s->w_seed = ra.seed; s->w_ftype = sc.filter.type; s->w_radius = sc.filter.radius;
+    return DVG_OK;
+}
+
+int check_render_args(DvgScene *s, int width, int height, int nsx, int nsy) {
+    if (!s) return fail(DVG_ERR_INVALID, "null scene");
+    if (!s->params_set) return fail(DVG_ERR_INVALID, "dvg_scene_set_params has not been called");
+    if (width <= 0 || height <= 0 || nsx <= 0 || nsy <= 0) return fail(DVG_ERR_INVALID, "bad render size / sample counts");
+    if ((int64_t)width * height * nsx * nsy >= (int64_t)1 << 31)
+        return fail(DVG_ERR_INVALID, "width*height*samples must fit a 32-bit index (reference: parallel.h:39-44)");
+    return DVG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int dvg_abi_version(void) { return 1; }
+
+const char *dvg_last_error(void) { return g_err.c_str(); }
+
+int64_t dvg_kernel_launch_count(void) { return dvg::g_launch_count; }
+
+int dvg_scene_create(const int32_t *topo, int64_t topo_len, int device, DvgScene **out_scene) {
+    if (!topo || !out_scene) return fail(DVG_ERR_INVALID, "null argument");
+    int rc = validate_topo(topo, topo_len);
+    if (rc) return rc;
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(DVG_ERR_INVALID, "bad CUDA device ordinal");
+    DeviceGuard guard(device);
+    DvgScene *s = new DvgScene();
+    s->device = device;
+    s->topo.assign(topo, topo + topo_len);
+    const int32_t *t = s->topo.data();
+    s->canvas_w = t[DVG_H_CANVAS_W]; s->canvas_h = t[DVG_H_CANVAS_H];
+    s->num_shapes = t[DVG_H_NUM_SHAPES]; s->num_groups = t[DVG_H_NUM_GROUPS];
+    s->num_params = t[DVG_H_NUM_PARAMS]; s->total_segs = t[DVG_H_TOTAL_SEGS];
+    s->num_insts = t[DVG_H_TOTAL_GSHAPES];
+    // instances and primitives in (group, shape-in-group, segment) order
+    for (int g = 0; g < s->num_groups; g++) {
+        const int32_t *r = t + t[DVG_H_OFF_GROUPS] + g * DVG_GROUP_REC_LEN;
+        if (r[DVG_G_SHAPES_OFF] != (int)s->inst_group.size()) {
+            delete s;
+            return fail(DVG_ERR_INVALID, "group shape lists must be stored consecutively in group order");
+        }
+        const int32_t *ids = t + t[DVG_H_OFF_GSHAPES] + r[DVG_G_SHAPES_OFF];
+        for (int k = 0; k < r[DVG_G_NUM_SHAPES]; k++) {
+            const int sh = ids[k];
+            const int32_t *sr = t + t[DVG_H_OFF_SHAPES] + sh * DVG_SHAPE_REC_LEN;
+            const int inst = (int)s->inst_group.size();
+            s->inst_group.push_back(g);
+            s->inst_shape.push_back(sh);
+            s->inst_prim_begin.push_back((int)s->prim_inst.size());
+            if (sr[DVG_S_TYPE] == DVG_SHAPE_PATH) {
+                const int32_t *ncp = t + t[DVG_H_OFF_NCP] + sr[DVG_S_NCP_OFF];
+                int pid = 0;
+                for (int seg = 0; seg < sr[DVG_S_NUM_SEGS]; seg++) {
+                    s->prim_inst.push_back(inst);
+                    s->prim_seg.push_back(seg);
+                    s->prim_point_id.push_back(pid);
+                    pid += ncp[seg] + 1;
+                }
+            } else {
+                s->prim_inst.push_back(inst);
+                s->prim_seg.push_back(0);
+                s->prim_point_id.push_back(0);
+            }
+        }
+    }
+    s->inst_prim_begin.push_back((int)s->prim_inst.size());
+    s->num_prims = (int)s->prim_inst.size();
+    rc = upload(s->d_topo, s->topo);
+    if (!rc) rc = upload(s->d_inst_group, s->inst_group);
+    if (!rc) rc = upload(s->d_inst_shape, s->inst_shape);
+    if (!rc) rc = upload(s->d_inst_prim_begin, s->inst_prim_begin);
+    if (!rc) rc = upload(s->d_prim_inst, s->prim_inst);
+    if (!rc) rc = upload(s->d_prim_seg, s->prim_seg);
+    if (!rc) rc = upload(s->d_prim_point_id, s->prim_point_id);
+    auto ens = [&](DevBuf &b, size_t bytes) { if (!rc && b.ensure(std::max<size_t>(bytes, 16)) != cudaSuccess) rc = fail(DVG_ERR_CUDA, "cudaMalloc failed"); };
+    const size_t ns = s->num_shapes, ng = s->num_groups, ni = s->num_insts, npr = s->num_prims, nsg = std::max(s->total_segs, 1);
+    ens(s->d_params, sizeof(float) * s->num_params);
+    ens(s->d_shapes_length, 4 * ns); ens(s->d_shape_box, sizeof(Box) * ns); ens(s->d_shape_r0, 4 * ns);
+    ens(s->d_seg_cdf, 4 * nsg); ens(s->d_seg_pmf, 4 * nsg); ens(s->d_seg_point_id, 4 * nsg);
+    ens(s->d_insts, sizeof(InstInfo) * ni); ens(s->d_groups, sizeof(GroupInfo) * ng);
+    ens(s->d_p01, 16 * npr); ens(s->d_p23, 16 * npr); ens(s->d_rad, 16 * npr); ens(s->d_box, 16 * npr);
+    ens(s->d_thick, 4 * npr); ens(s->d_meta, sizeof(PrimMeta) * npr); ens(s->d_cbox, 16 * npr);
+    ens(s->d_shape_cdf, 4 * ni); ens(s->d_shape_pmf, 4 * ni); ens(s->d_flags, 16);
+    if (!rc && cudaMallocHost((void **)&s->h_pinned, 64) != cudaSuccess) rc = fail(DVG_ERR_CUDA, "cudaMallocHost failed");
+    if (rc) { s->release_all(); delete s; return rc; }
+    *out_scene = s;
+    return DVG_OK;
+}
+
+int dvg_scene_set_params(DvgScene *s, const float *params, int64_t num_params, int params_on_device, void *stream) {
+    if (!s || !params) return fail(DVG_ERR_INVALID, "null argument");
+    if (num_params != s->num_params) return fail(DVG_ERR_INVALID, "params length does not match the topology");
+    DeviceGuard guard(s->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaMemcpyAsync(s->d_params.p, params, sizeof(float) * num_params,
+                       params_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+    launch_build(s->build_view(), st);
+    CK(cudaGetLastError());
+    s->params_set = true;
+    s->checked = false;
+    s->scene_error = 0;
+    s->bin_w = s->bin_h = 0;   // bins depend on the geometry
+    s->w_valid = s->w_valid && true;  // the weight image does not depend on the scene, only on the filter (checked later)
+    return DVG_OK;
+}
+
+int dvg_render_forward_rows(DvgScene *s, const float *background, float *render_image,
+                            int width, int height, int nsx, int nsy, uint64_t seed,
+                            int use_prefiltering, int row_begin, int row_end, void *stream) {
+    int rc = check_render_args(s, width, height, nsx, nsy);
+    if (rc) return rc;
+    if (!render_image) return fail(DVG_ERR_INVALID, "render_image is null");
+    if (use_prefiltering) return fail(DVG_ERR_UNSUPPORTED, "use_prefiltering is not implemented yet in this build");
+    if (row_begin < 0 || row_end > height || row_begin > row_end) return fail(DVG_ERR_INVALID, "bad row range");
+    DeviceGuard guard(s->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    rc = finish_build(s, st);
+    if (rc) return rc;
+    rc = ensure_bins(s, width, height, nsx * nsy, st);
+    if (rc) return rc;
+    if (row_begin % s->bin_th != 0) return fail(DVG_ERR_INVALID, "row_begin must be a multiple of the tile height");
+    SceneView sc = s->view();
+    RenderArgs ra;
+    memset(&ra, 0, sizeof ra);
+    ra.width = width; ra.height = height; ra.nsx = nsx; ra.nsy = nsy; ra.seed = seed;
+    ra.use_prefiltering = use_prefiltering; ra.row_begin = row_begin; ra.row_end = row_end;
+    ra.background = background; ra.render_image = render_image;
+    rc = ensure_weight(s, sc, ra, st);
+    if (rc) return rc;
+    if (row_begin == 0 && row_end == height)
+        CK(cudaMemsetAsync(render_image, 0, sizeof(float) * 4 * (size_t)width * height, st));
+    else
+        CK(cudaMemsetAsync(render_image + 4 * (size_t)row_begin * width, 0, sizeof(float) * 4 * (size_t)width * (row_end - row_begin), st));
+    launch_render_forward(sc, s->bin_view(), ra, st);
+    CK(cudaGetLastError());
+    return DVG_OK;
+}
+
+int dvg_render_forward(DvgScene *s, const float *background, float *render_image, float *render_sdf,
+                       int width, int height, int nsx, int nsy, uint64_t seed,
+                       int use_prefiltering, const float *eval_positions, int num_eval_positions, void *stream) {
+    if (render_sdf || eval_positions || num_eval_positions)
+        return fail(DVG_ERR_UNSUPPORTED, "SDF output / eval_positions are not implemented yet in this build");
+    return dvg_render_forward_rows(s, background, render_image, width, height, nsx, nsy, seed, use_prefiltering, 0, height, stream);
+}
+
+int dvg_render_backward_rows(DvgScene *s, const float *background, const float *d_render_image,
+                             int width, int height, int nsx, int nsy, uint64_t seed,
+                             int use_prefiltering, int row_begin, int row_end,
+                             float *d_params, float *d_background, uint32_t flags, void *stream) {
+    int rc = check_render_args(s, width, height, nsx, nsy);
+    if (rc) return rc;
+    if (!d_render_image || !d_params) return fail(DVG_ERR_INVALID, "d_render_image / d_params is null");
+    if (((uintptr_t)d_render_image & 15) != 0) return fail(DVG_ERR_INVALID, "d_render_image must be 16-byte aligned");
+    if (use_prefiltering) return fail(DVG_ERR_UNSUPPORTED, "use_prefiltering is not implemented yet in this build");
+    if (row_begin < 0 || row_end > height || row_begin > row_end) return fail(DVG_ERR_INVALID, "bad row range");
+    DeviceGuard guard(s->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    rc = finish_build(s, st);
+    if (rc) return rc;
+    rc = ensure_bins(s, width, height, nsx * nsy, st);
+    if (rc) return rc;
+    if (row_begin % s->bin_th != 0) return fail(DVG_ERR_INVALID, "row_begin must be a multiple of the tile height");
+    SceneView sc = s->view();
+    BinView bins = s->bin_view();
+    RenderArgs ra;
+    memset(&ra, 0, sizeof ra);
+    ra.width = width; ra.height = height; ra.nsx = nsx; ra.nsy = nsy; ra.seed = seed;
+    ra.use_prefiltering = use_prefiltering; ra.row_begin = row_begin; ra.row_end = row_end;
+    ra.flags = flags;
+    ra.background = background; ra.d_render_image = d_render_image;
+    ra.d_params = d_params; ra.d_background = d_background;
+    rc = ensure_weight(s, sc, ra, st);
+    if (rc) return rc;
+    if (!(flags & DVG_BWD_ACCUMULATE)) CK(cudaMemsetAsync(d_params, 0, sizeof(float) * s->num_params, st));
+    if (d_background) {
+        if (row_begin == 0 && row_end == height) CK(cudaMemsetAsync(d_background, 0, sizeof(float) * 4 * (size_t)width * height, st));
+        else CK(cudaMemsetAsync(d_background + 4 * (size_t)row_begin * width, 0, sizeof(float) * 4 * (size_t)width * (row_end - row_begin), st));
+    }
+    launch_render_backward(sc, bins, ra, st);
+    CK(cudaGetLastError());
+    // boundary term (diffvg.cpp:1558-1626): boundary-sample indices of the owned rows
+    const int spp = nsx * nsy;
+    const int ntiles = bins.tiles_x * bins.tiles_y;
+    BoundaryWork bw;
+    bw.sample_begin = row_begin * width * spp;
+    bw.num_samples = (row_end - row_begin) * width * spp;
+    if (bw.num_samples > 0) {
+        CK(s->d_keys.ensure(sizeof(int) * (size_t)bw.num_samples));
+        CK(s->d_sorted.ensure(sizeof(int) * (size_t)bw.num_samples));
+        CK(s->d_tile_counts.ensure(sizeof(int) * ntiles)); CK(s->d_tile_fill.ensure(sizeof(int) * ntiles));
+        CK(s->d_blk_counts.ensure(sizeof(int) * ntiles));
+        CK(s->d_tile_offsets.ensure(sizeof(int) * (ntiles + 1))); CK(s->d_blk_offsets.ensure(sizeof(int) * (ntiles + 1)));
+        bw.keys = s->d_keys.as<int>(); bw.sorted_idx = s->d_sorted.as<int>();
+        bw.tile_counts = s->d_tile_counts.as<int>(); bw.tile_fill = s->d_tile_fill.as<int>();
+        bw.blk_counts = s->d_blk_counts.as<int>();
+        bw.tile_offsets = s->d_tile_offsets.as<int>(); bw.blk_offsets = s->d_blk_offsets.as<int>();
+        bw.max_blocks = bw.num_samples / 128 + ntiles;
+        launch_boundary(sc, bins, ra, bw, st);
+        CK(cudaGetLastError());
+    }
+    return DVG_OK;
+}
+
+int dvg_render_backward(DvgScene *s, const float *background, const float *d_render_image, const float *d_render_sdf,
+                        int width, int height, int nsx, int nsy, uint64_t seed,
+                        int use_prefiltering, const float *eval_positions, int num_eval_positions,
+                        float *d_params, float *d_background, float *d_translation, uint32_t flags, void *stream) {
+    if (d_render_sdf || eval_positions || num_eval_positions)
+        return fail(DVG_ERR_UNSUPPORTED, "SDF output / eval_positions are not implemented yet in this build");
+    if (d_translation) return fail(DVG_ERR_UNSUPPORTED, "d_translation is not implemented yet in this build");
+    return dvg_render_backward_rows(s, background, d_render_image, width, height, nsx, nsy, seed, use_prefiltering,
+                                    0, height, d_params, d_background, flags, stream);
+}
+
+int64_t dvg_scene_dump(DvgScene *s, int what, int index, uint32_t *out, int64_t cap, void *stream) {
+    (void)s; (void)what; (void)index; (void)out; (void)cap; (void)stream;
+    fail(DVG_ERR_UNSUPPORTED, "dvg_scene_dump: not implemented yet");
+    return -1;
+}
+
+int dvg_scene_destroy(DvgScene *s) {
+    if (!s) return DVG_OK;
+    {
+        DeviceGuard guard(s->device);
+        s->release_all();
+    }
+    delete s;
+    return DVG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,117 @@
+// dvg_color.cuh -- colour evaluation (constant / linear / radial gradient) and its adjoint.
+// Follows diffvg.cpp:276-368 (sample_color) and 370-504 (d_sample_color).
+#pragma once
+#include "dvg_scene.cuh"
+
+namespace dvg {
+
+#if defined(__CUDA_ARCH__)
+#define DVG_ATOMIC_ADD(ptr, v) atomicAdd((ptr), (v))
+#else
+#define DVG_ATOMIC_ADD(ptr, v) (*(ptr) += (v))
+#endif
+
+// Gradient parameter t for a linear / radial gradient record at params[off..].
+DVG_HD float gradient_t(int type, const float *c, F2 pt) {
+    if (type == 1) {  // diffvg.cpp:288-290
+        F2 beg = mk2(c[0], c[1]), end = mk2(c[2], c[3]);
+        return dot2(pt - beg, end - beg) / rmaxf(dot2(end - beg, end - beg), 1e-3f);
+    } else {  // diffvg.cpp:327-329
+        F2 offset = pt - mk2(c[0], c[1]);
+        F2 no = mk2(offset.x / c[2], offset.y / c[3]);
+        return length2(no);
+    }
+}
+
+DVG_HD F4 load4(const float *p) { return mk4(p[0], p[1], p[2], p[3]); }
+
+// diffvg.cpp:276-368.  `c` points at the colour record inside params.
+DVG_HD F4 eval_color(int type, const float *c, int num_stops, F2 pt) {
+    if (type == 0) return load4(c);
+    float t = gradient_t(type, c, pt);
+    const float *offsets = c + 4;
+    const float *colors = c + 4 + num_stops;
+    if (t < offsets[0]) return load4(colors);
+    for (int i = 0; i < num_stops - 1; i++) {
+        float oc = offsets[i], on = offsets[i + 1];
+        if (t >= oc && t < on) {
+            F4 cc = load4(colors + 4 * i), cn = load4(colors + 4 * (i + 1));
+            float tt = (t - oc) / (on - oc);
+            return cc * (1 - tt) + cn * tt;
+        }
+    }
+    return load4(colors + 4 * (num_stops - 1));
+}
+
+DVG_D void add4(float *d, F4 v) {
+    DVG_ATOMIC_ADD(d + 0, v.x); DVG_ATOMIC_ADD(d + 1, v.y); DVG_ATOMIC_ADD(d + 2, v.z); DVG_ATOMIC_ADD(d + 3, v.w);
+}
+
+// diffvg.cpp:370-504 for the two gradient types (the constant case is reduced by the
+// caller).  `d` points at the record's slot in d_params.  d_translation: 2 floats or null.
+// Q3: the radial branch has no `return` after the matched stop, so d_color is also
+// added to the last stop; reproduced.
+DVG_D void d_eval_gradient(int type, const float *c, int num_stops, F2 pt, F4 d_color, float *d, float *d_translation) {
+    float t = gradient_t(type, c, pt);
+    const float *offsets = c + 4;
+    const float *colors = c + 4 + num_stops;
+    float *d_offsets = d + 4;
+    float *d_colors = d + 4 + num_stops;
+    if (t < offsets[0]) { add4(d_colors, d_color); return; }
+    for (int i = 0; i < num_stops - 1; i++) {
+        float oc = offsets[i], on = offsets[i + 1];
+        if (t >= oc && t < on) {
+            F4 cc = load4(colors + 4 * i), cn = load4(colors + 4 * (i + 1));
+            float tt = (t - oc) / (on - oc);
+            F4 d_cc = d_color * (1 - tt), d_cn = d_color * tt;
+            float d_tt = sum4(d_color * (cn - cc));
+            float d_on = -d_tt * tt / (on - oc);
+            float d_oc = d_tt * ((tt - 1.f) / (on - oc));
+            float d_t = d_tt / (on - oc);
+            add4(d_colors + 4 * i, d_cc);
+            add4(d_colors + 4 * (i + 1), d_cn);
+            DVG_ATOMIC_ADD(d_offsets + i, d_oc);
+            DVG_ATOMIC_ADD(d_offsets + i + 1, d_on);
+            if (type == 1) {
+                F2 beg = mk2(c[0], c[1]), end = mk2(c[2], c[3]);
+                float l = rmaxf(dot2(end - beg, end - beg), 1e-3f);
+                F2 d_beg = (d_t * (-(pt - beg) - (end - beg))) / l;
+                F2 d_end = (d_t * (pt - beg)) / l;
+                float d_l = -d_t * t / l;
+                if (dot2(end - beg, end - beg) > 1e-3f) {
+                    d_beg = d_beg + (2 * d_l) * (beg - end);
+                    d_end = d_end + (2 * d_l) * (end - beg);
+                }
+                DVG_ATOMIC_ADD(d + 0, d_beg.x); DVG_ATOMIC_ADD(d + 1, d_beg.y);
+                DVG_ATOMIC_ADD(d + 2, d_end.x); DVG_ATOMIC_ADD(d + 3, d_end.y);
+                if (d_translation) {
+                    DVG_ATOMIC_ADD(d_translation + 0, d_beg.x + d_end.x);
+                    DVG_ATOMIC_ADD(d_translation + 1, d_beg.y + d_end.y);
+                }
+                return;
+            } else {
+                F2 offset = pt - mk2(c[0], c[1]);
+                F2 radius = mk2(c[2], c[3]);
+                F2 no = mk2(offset.x / radius.x, offset.y / radius.y);
+                // d_length (vector.h:496-503)
+                float l_sq = no.x * no.x + no.y * no.y;
+                float l = sqrtf(l_sq);
+                float d_l_sq = 0.5f * d_t / l;
+                F2 d_no = (2 * d_l_sq) * no;
+                F2 d_offset = mk2(d_no.x / radius.x, d_no.y / radius.y);
+                F2 d_radius = mk2(-d_no.x * offset.x / (radius.x * radius.x), -d_no.y * offset.y / (radius.y * radius.y));
+                F2 d_center = -d_offset;
+                DVG_ATOMIC_ADD(d + 0, d_center.x); DVG_ATOMIC_ADD(d + 1, d_center.y);
+                DVG_ATOMIC_ADD(d + 2, d_radius.x); DVG_ATOMIC_ADD(d + 3, d_radius.y);
+                if (d_translation) {
+                    DVG_ATOMIC_ADD(d_translation + 0, d_center.x);
+                    DVG_ATOMIC_ADD(d_translation + 1, d_center.y);
+                }
+                // no return: falls through the loop (Q3)
+            }
+        }
+    }
+    add4(d_colors + 4 * (num_stops - 1), d_color);
+}
+
+}  // namespace dvg

@@ -1,0 +1,266 @@
+// dvg_geom.cuh -- per-primitive geometric predicates: "is pt within stroke radius of this
+// segment" (within_distance.h) and "signed crossings of the +x ray from pt with this segment"
+// (winding_number.h).  Arithmetic follows the reference expression by expression (types,
+// operation order, float literals inside double expressions) because one flipped sample
+// changes a pixel by 1/spp.
+#pragma once
+#include "dvg_scene.cuh"
+
+namespace dvg {
+
+DVG_HD F2 eval_quad(F2 p0, F2 p1, F2 p2, float t) {  // within_distance.h:75-78
+    float tt = 1 - t;
+    return (tt * tt) * p0 + (2 * tt * t) * p1 + (t * t) * p2;
+}
+DVG_HD F2 eval_cubic(F2 p0, F2 p1, F2 p2, F2 p3, float t) {  // within_distance.h:129-132
+    float tt = 1 - t;
+    return (tt * tt * tt) * p0 + (3 * tt * tt * t) * p1 + (3 * tt * t * t) * p2 + (t * t * t) * p3;
+}
+
+// vector.h:787-817
+DVG_HD F2 quadratic_closest_pt_approx(F2 b0, F2 b1, F2 b2, F2 pt, float *t_out) {
+    b0 = b0 - pt; b1 = b1 - pt; b2 = b2 - pt;
+#define DVG_DET(u, v) ((u).x * (v).y - (u).y * (v).x)
+    float a = DVG_DET(b0, b2), b = 2 * DVG_DET(b1, b0), d = 2 * DVG_DET(b2, b1);
+    float f = b * d - a * a;
+    F2 d21 = b2 - b1, d10 = b1 - b0, d20 = b2 - b0;
+    F2 gf = 2 * (b * d21 + d * d10 + a * d20);
+    gf = mk2(gf.y, -gf.x);
+    F2 pp = (-f * gf) / dot2(gf, gf);
+    F2 d0p = b0 - pp;
+    float ap = DVG_DET(d0p, d20), bp = 2 * DVG_DET(d10, d0p);
+#undef DVG_DET
+    float t = clampf((ap + bp) / (2 * a + b + d), 0.f, 1.f);
+    float tt = 1 - t;
+    if (t_out) *t_out = t;
+    return ((tt * tt) * b0 + (2 * tt * t) * b1 + (t * t) * b2) + pt;
+}
+
+// The normalised quintic whose roots are the stationary points of |q(t) - pt|^2 for a cubic
+// (within_distance.h:161-172).  Coefficients are formed in float and only then widened.
+struct Quintic { double B, C, D, E, F; };
+
+DVG_HD Quintic cubic_quintic(F2 p0, F2 p1, F2 p2, F2 p3, F2 pt) {
+    F2 q3 = -p0 + 3 * p1 - 3 * p2 + p3;
+    F2 q2 = 3 * p0 - 6 * p1 + 3 * p2;
+    F2 q1 = -3 * p0 + 3 * p1;
+    F2 pp = p0 - pt;
+    double A = 3 * sum2(q3 * q3);
+    double B = 5 * sum2(q3 * q2);
+    double C = 4 * sum2(q3 * q1) + 2 * sum2(q2 * q2);
+    double D = 3 * (sum2(q2 * q1) + sum2(q3 * pp));
+    double E = sum2(q1 * q1) + 2 * sum2(pp * q2);
+    double F = sum2(pp * q1);
+    Quintic q;
+    q.B = B / A; q.C = C / A; q.D = D / A; q.E = E / A; q.F = F / A;
+    return q;
+}
+DVG_HD double quintic_eval(const Quintic &q, double t) {  // within_distance.h:211-218
+    return t * t * t * t * t + q.B * t * t * t * t + q.C * t * t * t + q.D * t * t + q.E * t + q.F;
+}
+DVG_HD double quintic_deriv(const Quintic &q, double t) {  // within_distance.h:219-225
+    return 5 * t * t * t * t + 4 * q.B * t * t * t + 3 * q.C * t * t + 2 * q.D * t + q.E;
+}
+// Isolator-polynomial split points (within_distance.h:184-210).  Returns the sorted interval
+// ends.  Q10: when q_root is outside [0,1] the reference reads intervals[0]
+// uninitialised; we then use -1 ("no split point": negative entries are skipped).
+DVG_HD int quintic_intervals(const Quintic &q, float intervals[4]) {
+    double p1A = ((2 / 5.f) * q.C - (4 / 25.f) * q.B * q.B);
+    double p1B = ((3 / 5.f) * q.D - (3 / 25.f) * q.B * q.C);
+    double p1C = ((4 / 5.f) * q.E - (2 / 25.f) * q.B * q.D);
+    double p1D = q.F - q.B * q.E / 25.f;
+    double q_root = -q.B / 5.f;
+    double p_roots[3];
+    int num_sol = solve_cubic_d(p1A, p1B, p1C, p1D, p_roots);
+    intervals[0] = -1.f;
+    if (q_root >= 0 && q_root <= 1) intervals[0] = (float)q_root;
+    for (int j = 0; j < num_sol; j++) intervals[j + 1] = (float)p_roots[j];
+    int n = 1 + num_sol;
+    for (int j = 1; j < n; j++) {
+        for (int k = j; k > 0 && intervals[k - 1] > intervals[k]; k--) {
+            float tmp = intervals[k]; intervals[k] = intervals[k - 1]; intervals[k - 1] = tmp;
+        }
+    }
+    return n;
+}
+// Safeguarded Newton inside one bracket (within_distance.h:233-262).  Returns false when the
+// bracket holds no sign change.
+DVG_HD bool quintic_root_in(const Quintic &q, float lower, float upper, float *t_out) {
+    float lb = lower, ub = upper;
+    double lb_eval = quintic_eval(q, lb);
+    double ub_eval = quintic_eval(q, ub);
+    if (lb_eval * ub_eval > 0) return false;
+    if (lb_eval > ub_eval) { float tmp = lb; lb = ub; ub = tmp; }
+    float t = 0.5f * (lb + ub);
+    for (int it = 0; it < 20; it++) {
+        if (!(t >= lb && t <= ub)) t = 0.5f * (lb + ub);
+        double value = quintic_eval(q, t);
+        if (fabs(value) < 1e-5f || it == 19) break;
+        if (value > 0.f) ub = t; else lb = t;
+        double derivative = quintic_deriv(q, t);
+        t = (float)((double)t - value / derivative);
+    }
+    *t_out = t;
+    return true;
+}
+
+// within_distance.h:119-272 (cubic leaf).  r[] = radius at the four control points.
+DVG_HD bool stroke_hit_cubic(F2 p0, F2 p1, F2 p2, F2 p3, F4 r, F2 pt) {
+    if (dist_sq(p0, pt) < r.x * r.x) return true;  // eval(0) == p0 exactly
+    if (dist_sq(p3, pt) < r.w * r.w) return true;  // eval(1) == p3 exactly
+    Quintic q = cubic_quintic(p0, p1, p2, p3, pt);
+    float intervals[4];
+    int n = quintic_intervals(q, intervals);
+    float lower_bound = 0.f;
+    for (int j = 0; j < n + 1; j++) {
+        if (j < n && intervals[j] < 0.f) continue;
+        float upper_bound = j < n ? rminf(intervals[j], 1.f) : 1.f;
+        float t;
+        if (quintic_root_in(q, lower_bound, upper_bound, &t)) {
+            float tt = 1 - t;
+            float rr = (tt * tt * tt) * r.x + (3 * tt * tt * t) * r.y + (3 * tt * t * t) * r.z + (t * t * t) * r.w;
+            if (dist_sq(eval_cubic(p0, p1, p2, p3, t), pt) < rr * rr) return true;
+            if (upper_bound >= 1.f) break;
+            lower_bound = upper_bound;
+        }
+        // note: when the bracket has no root the reference `continue`s WITHOUT advancing lower_bound
+    }
+    return false;
+}
+
+// within_distance.h:63-118 (quadratic leaf).  *decided is set when use_distance_approx makes
+// the reference return from the whole path traversal (Q9).
+DVG_HD bool stroke_hit_quad(F2 p0, F2 p1, F2 p2, F4 r, float r_shape, bool approx, F2 pt, bool *decided) {
+    if (approx) {
+        F2 cp = quadratic_closest_pt_approx(p0, p1, p2, pt, nullptr);
+        *decided = true;
+        return dist_sq(cp, pt) < r_shape * r_shape;
+    }
+    if (dist_sq(p0, pt) < r.x * r.x) return true;
+    if (dist_sq(p2, pt) < r.z * r.z) return true;
+    F2 a2 = p0 - 2 * p1 + p2;
+    F2 a1 = -p0 + p1;
+    float A = sum2(a2 * a2);
+    float B = sum2(3 * a2 * a1);
+    float C = sum2(2 * a1 * a1 + a2 * (p0 - pt));
+    float D = sum2(a1 * (p0 - pt));
+    float t[3];
+    int num_sol = solve_cubic_f(A, B, C, D, t);
+    for (int j = 0; j < num_sol; j++) {
+        if (t[j] >= 0 && t[j] <= 1) {
+            float tt = 1 - t[j];
+            float rr = (tt * tt) * r.x + (2 * tt * t[j]) * r.y + (t[j] * t[j]) * r.z;
+            F2 p = eval_quad(p0, p1, p2, t[j]);
+            if (dist_sq(p, pt) < rr * rr) return true;
+        }
+    }
+    return false;
+}
+
+// within_distance.h:34-62 (line leaf); also the rect edge test 295-312 with r0 == r1.
+DVG_HD bool stroke_hit_line(F2 p0, F2 p1, float r0, float r1, F2 pt) {
+    float t = dot2(pt - p0, p1 - p0) / dot2(p1 - p0, p1 - p0);
+    if (t < 0) {
+        return dist_sq(p0, pt) < r0 * r0;
+    } else if (t > 1) {
+        return dist_sq(p1, pt) < r1 * r1;
+    } else {
+        float r = r0 + t * (r1 - r0);
+        return dist_sq(p0 + t * (p1 - p0), pt) < r * r;
+    }
+}
+
+// Stroke test of one primitive.  `r_shape` is shape.stroke_width (used by circle/rect and
+// the distance-approx path).  *decided: see stroke_hit_quad.
+DVG_HD bool prim_stroke_hit(int type, bool approx, F4 p01, F4 p23, F4 rad, float r_shape, F2 pt, bool *decided) {
+    switch (type) {
+        case PRIM_LINE:
+            return stroke_hit_line(mk2(p01.x, p01.y), mk2(p01.z, p01.w), rad.x, rad.y, pt);
+        case PRIM_QUAD:
+            return stroke_hit_quad(mk2(p01.x, p01.y), mk2(p01.z, p01.w), mk2(p23.x, p23.y), rad, r_shape, approx, pt, decided);
+        case PRIM_CUBIC:
+            return stroke_hit_cubic(mk2(p01.x, p01.y), mk2(p01.z, p01.w), mk2(p23.x, p23.y), mk2(p23.z, p23.w), rad, pt);
+        case PRIM_CIRCLE: {  // within_distance.h:8-16
+            float d = distance2(mk2(p01.x, p01.y), pt);
+            return fabsf(d - p01.z) < r_shape;
+        }
+        case PRIM_RECT: {  // within_distance.h:292-334
+            F2 lt = mk2(p01.x, p01.y), rt = mk2(p01.z, p01.y), lb = mk2(p01.x, p01.w), rb = mk2(p01.z, p01.w);
+            if (stroke_hit_line(lt, lb, r_shape, r_shape, pt)) return true;
+            if (stroke_hit_line(lt, rt, r_shape, r_shape, pt)) return true;
+            if (stroke_hit_line(rt, rb, r_shape, r_shape, pt)) return true;
+            if (stroke_hit_line(lb, rb, r_shape, r_shape, pt)) return true;
+            return false;
+        }
+        default:  // stroked ellipses are rejected at scene creation (Q6)
+            return false;
+    }
+}
+
+// winding_number.h:62-156 per leaf type + 9-31, 176-186 for the closed-form shapes.
+DVG_HD int prim_winding(int type, F4 p01, F4 p23, F2 pt) {
+    switch (type) {
+        case PRIM_LINE: {
+            F2 p0 = mk2(p01.x, p01.y), p1 = mk2(p01.z, p01.w);
+            if (p1.y != p0.y) {
+                float t = (pt.y - p0.y) / (p1.y - p0.y);
+                if (t >= 0 && t <= 1) {
+                    float tp = p0.x - pt.x + t * (p1.x - p0.x);
+                    if (tp >= 0) return (p1.y - p0.y > 0) ? 1 : -1;
+                }
+            }
+            return 0;
+        }
+        case PRIM_QUAD: {
+            F2 p0 = mk2(p01.x, p01.y), p1 = mk2(p01.z, p01.w), p2 = mk2(p23.x, p23.y);
+            float t[2];
+            int w = 0;
+            if (solve_quadratic_f(p0.y - 2 * p1.y + p2.y, -2 * p0.y + 2 * p1.y, p0.y - pt.y, &t[0], &t[1])) {
+                for (int j = 0; j < 2; j++) {
+                    if (t[j] >= 0 && t[j] <= 1) {
+                        float tp = (p0.x - 2 * p1.x + p2.x) * t[j] * t[j] + (-2 * p0.x + 2 * p1.x) * t[j] + p0.x - pt.x;
+                        if (tp >= 0) {
+                            if (2 * (p0.y - 2 * p1.y + p2.y) * t[j] + (-2 * p0.y + 2 * p1.y) > 0) w += 1;
+                            else w -= 1;
+                        }
+                    }
+                }
+            }
+            return w;
+        }
+        case PRIM_CUBIC: {
+            F2 p0 = mk2(p01.x, p01.y), p1 = mk2(p01.z, p01.w), p2 = mk2(p23.x, p23.y), p3 = mk2(p23.z, p23.w);
+            double t[3];
+            int num_sol = solve_cubic_d((double)(-p0.y + 3 * p1.y - 3 * p2.y + p3.y),
+                                        (double)(3 * p0.y - 6 * p1.y + 3 * p2.y),
+                                        (double)(-3 * p0.y + 3 * p1.y),
+                                        (double)(p0.y - pt.y), t);
+            int w = 0;
+            // float coefficient * double t: the products are formed in double (winding_number.h:142-149)
+            float cx3 = -p0.x + 3 * p1.x - 3 * p2.x + p3.x, cx2 = 3 * p0.x - 6 * p1.x + 3 * p2.x, cx1 = -3 * p0.x + 3 * p1.x;
+            float cy3 = -p0.y + 3 * p1.y - 3 * p2.y + p3.y, cy2 = 3 * p0.y - 6 * p1.y + 3 * p2.y, cy1 = -3 * p0.y + 3 * p1.y;
+            for (int j = 0; j < num_sol; j++) {
+                if (t[j] >= 0 && t[j] <= 1) {
+                    double tp = (double)cx3 * t[j] * t[j] * t[j] + (double)cx2 * t[j] * t[j] + (double)cx1 * t[j] +
+                                (double)p0.x - (double)pt.x;
+                    if (tp > 0) {  // Q13: strict here, >= for lines and quadratics
+                        if ((double)(3 * cy3) * t[j] * t[j] + (double)(2 * cy2) * t[j] + (double)cy1 > 0) w += 1;
+                        else w -= 1;
+                    }
+                }
+            }
+            return w;
+        }
+        case PRIM_CIRCLE:
+            return dist_sq(mk2(p01.x, p01.y), pt) < p01.z * p01.z ? 1 : 0;
+        case PRIM_ELLIPSE: {
+            float ex = p01.x - pt.x, ey = p01.y - pt.y;
+            return (ex * ex) / (p01.z * p01.z) + (ey * ey) / (p01.w * p01.w) < 1 ? 1 : 0;
+        }
+        case PRIM_RECT:
+            return (pt.x > p01.x && pt.x < p01.z && pt.y > p01.y && pt.y < p01.w) ? 1 : 0;
+    }
+    return 0;
+}
+
+}  // namespace dvg

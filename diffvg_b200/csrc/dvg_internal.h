@@ -1,0 +1,53 @@
+// dvg_internal.h -- declarations shared by the .cu translation units of libdiffvg_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "dvg_common.cuh"
+#include "dvg_scene.cuh"
+#include "dvg_geom.cuh"
+#include "dvg_color.cuh"
+#include "dvg_boundary.cuh"
+#include "dvg_trace.cuh"
+#include "dvg_buildfn.cuh"
+
+namespace dvg {
+
+extern long long g_launch_count;  // kernels launched since load (dvg_kernel_launch_count)
+
+#define DVG_LAUNCH(kernel, grid, block, smem, stream, ...)            \
+    do {                                                              \
+        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);   \
+        ::dvg::g_launch_count++;                                      \
+    } while (0)
+
+struct BinBuild {
+    int width, height, tile_w, tile_h, tiles_x, tiles_y;
+    int *counts;   // [tiles]
+    int *offsets;  // [tiles+1]
+    int *items;    // [capacity]
+};
+
+struct BoundaryWork {
+    int num_samples;      // = sample_end - sample_begin
+    int sample_begin;
+    int *keys;            // [num_samples] tile id or -1
+    int *tile_counts;     // [tiles]
+    int *tile_offsets;    // [tiles+1]
+    int *tile_fill;       // [tiles]
+    int *blk_counts;      // [tiles]
+    int *blk_offsets;     // [tiles+1]
+    int *sorted_idx;      // [num_samples]
+    int max_blocks;
+};
+
+void launch_build(const BuildView &bv, cudaStream_t st);
+void launch_bin_count(const BuildView &bv, const BinBuild &bb, cudaStream_t st);
+void launch_bin_fill(const BuildView &bv, const BinBuild &bb, cudaStream_t st);
+void launch_scan(const int *in, int *out, int n, cudaStream_t st);
+
+void launch_weight(const SceneView &sc, const RenderArgs &ra, cudaStream_t st);
+void launch_render_forward(const SceneView &sc, const BinView &bins, const RenderArgs &ra, cudaStream_t st);
+void launch_render_backward(const SceneView &sc, const BinView &bins, const RenderArgs &ra, cudaStream_t st);
+void launch_boundary(const SceneView &sc, const BinView &bins, const RenderArgs &ra, const BoundaryWork &bw, cudaStream_t st);
+
+}  // namespace dvg

@@ -1,0 +1,110 @@
+// dvg_scene.cuh -- device-resident scene layout (SoA, 16-byte records) built every iteration
+// from the flat `params` by the kernels in dvg_build.cu.
+//
+// The reference keeps an AoS object graph behind pointers (scene.h:18-67) and three levels of
+// BVH.  Here the unit of work is a *primitive*: one path segment, or one whole
+// circle/ellipse/rect, instanced per (group, shape-in-group).  Primitives are numbered in
+// (group, shape-in-group, segment) order, so any ascending list of primitive ids is already
+// in compositing order (diffvg.cpp:605-615 sorts fragments by group id).
+#pragma once
+#include "dvg_common.cuh"
+#include "../../include/dvg_scene_format.h"
+
+namespace dvg {
+
+enum PrimType { PRIM_LINE = 0, PRIM_QUAD = 1, PRIM_CUBIC = 2, PRIM_CIRCLE = 3, PRIM_ELLIPSE = 4, PRIM_RECT = 5 };
+
+// prim flags (upper bits of PrimMeta.type_flags)
+#define DVG_PF_TYPE_MASK 0xF
+#define DVG_PF_SINGLE 0x10    // leaf == root of its path BVH: the reference performs no box test
+#define DVG_PF_THICK 0x20     // per-point thickness
+#define DVG_PF_APPROX 0x40    // use_distance_approx
+#define DVG_PF_FIRST 0x80     // first primitive of its shape instance
+#define DVG_PF_GFIRST 0x100   // first primitive of its group
+
+struct PrimMeta {
+    int type_flags;  // PrimType | flags
+    int inst;        // shape instance (index into inst_* arrays)
+    int point_id;    // path: index of the segment's first point
+    int base_id;     // path: segment index (base_point_id)
+};
+
+// One record per shape group.  96 bytes... read through uniform (broadcast) loads.
+struct GroupInfo {
+    Box scene_box;   // leaf box of the reference scene BVH (canvas space), scene.cpp:672-676
+    Box local_box;   // root box of the reference group BVH (local space), diffvg.cpp:42
+    float scene_r;   // leaf max_radius of the scene BVH, scene.cpp:650-681
+    int flags;       // DVG_GF_*
+    int fill_type, fill_off, fill_stops;
+    int stroke_type, stroke_off, stroke_stops;
+    int num_shapes, inst_begin, prim_begin, prim_end;
+    float c2s[9];    // canvas_to_shape = inverse(shape_to_canvas), shape.h:122-124
+    float s2c[9];
+    int xform_off;
+    int pad;
+};
+#define DVG_GF_EVEN_ODD 1
+#define DVG_GF_IDENTITY 2   // shape_to_canvas is exactly the identity: xform_pt is exact, skip it
+#define DVG_GF_AFFINE 4     // last row is exactly (0,0,1)
+
+// Per shape *instance* (a shape referenced by a group).
+struct InstInfo {
+    Box box;        // shapes_bbox[shape], scene.cpp:499-629
+    float r;        // leaf radius in the group BVH: stroke_width if the group strokes else 0, scene.cpp:638
+    int group;
+    int shape;
+    int prim_begin;
+};
+
+// Everything the kernels need, passed by value.
+struct SceneView {
+    int canvas_w, canvas_h;
+    int num_shapes, num_groups, num_insts, num_prims;
+    Filter filter;
+    int filter_radius_off;
+    const int *topo;       // device copy of the topology blob
+    const float *params;   // device copy of the flat parameters
+    // primitives
+    const F4 *prim_p01;    // (p0.x,p0.y,p1.x,p1.y) | circle (cx,cy,r,0) | ellipse (cx,cy,rx,ry) | rect (min,max)
+    const F4 *prim_p23;
+    const F4 *prim_rad;    // stroke radius at each control point (thickness or stroke_width broadcast)
+    const Box *prim_box;   // local-space leaf box, scene.cpp:536-585
+    const float *prim_thick;  // leaf max_radius, scene.cpp:546,569,597
+    const PrimMeta *prim_meta;
+    const Box *prim_cbox;  // canvas-space conservative bound of where this primitive can matter (binning only)
+    const InstInfo *insts;
+    const GroupInfo *groups;
+    // boundary sampling tables (scene.cpp:207-333)
+    const float *shapes_length;   // [num_shapes]
+    const float *shape_cdf;       // [num_insts]
+    const float *shape_pmf;       // [num_insts]
+    const float *seg_cdf;         // [total_segs], indexed by shape.ncp_off + i
+    const float *seg_pmf;
+    const int *seg_point_id;
+    int *error_flag;
+};
+
+// Tile bins for one render configuration.
+struct BinView {
+    int tile_w, tile_h, tiles_x, tiles_y;
+    const int *offsets;   // [tiles+1]
+    const int *items;     // ascending primitive ids per tile
+};
+
+// Arguments of the render / boundary kernels.
+struct RenderArgs {
+    int width, height, nsx, nsy;
+    uint64_t seed;
+    int use_prefiltering;
+    int row_begin, row_end;        // pixel rows owned by this call (sharding); whole image by default
+    uint32_t flags;
+    const float *background;       // [H,W,4] or null
+    float *weight_image;           // [H,W]
+    float *render_image;           // [H,W,4] forward output (accumulated)
+    const float *d_render_image;   // [H,W,4] backward input
+    float *d_params;
+    float *d_background;
+    float *d_translation;
+};
+
+}  // namespace dvg

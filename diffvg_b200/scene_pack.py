@@ -32,150 +32,207 @@ COLOR_NONE, COLOR_CONSTANT, COLOR_LINEAR, COLOR_RADIAL = -1, 0, 1, 2
 SF_CLOSED, SF_DISTANCE_APPROX = 1, 2
 
 
-class _ParamList:
-    """Accumulates float tensors and hands out their offsets in the concatenation."""
+# Parameter tensors are collected into a few "buckets" so that the flat `params` can be built
+# with a handful of torch ops (one cat for all path points, one stack for all stroke widths,
+# one for all constant colours, ...) instead of one reshape per tensor: at 2048 paths the
+# per-tensor version costs ~130 ms of pure Python per iteration, the bucketed one a few ms.
+# A tensor OBJECT that occurs several times (typically the default `shape_to_canvas`
+# torch.eye(3) shared by every ShapeGroup) is stored once; autograd then sums the gradients
+# of all its uses, which is exactly what sharing a tensor means.
+B_POINTS, B_SCALAR, B_VEC4, B_MAT3, B_GENERIC, NUM_BUCKETS = 0, 1, 2, 3, 4, 5
 
+
+class _Buckets:
     def __init__(self):
-        self.tensors = []
-        self.n = 0
+        self.tensors = [[] for _ in range(NUM_BUCKETS)]
+        self.sizes = [0] * NUM_BUCKETS
+        self.seen = {}
 
-    def add(self, t, expect=None):
+    def add(self, bucket, t, numel):
+        off = self.sizes[bucket]
+        self.tensors[bucket].append(t)
+        self.sizes[bucket] = off + numel
+        return off
+
+    def add_generic(self, t, expect):
         if not isinstance(t, torch.Tensor):
             t = torch.as_tensor(t, dtype=torch.float32)
-        k = t.numel()
-        if expect is not None and k != expect:
+        if t.numel() != expect:
             raise ValueError('expected a tensor of %d elements, got shape %s' % (expect, tuple(t.shape)))
-        off = self.n
-        self.tensors.append(t)
-        self.n += k
+        return self.add(B_GENERIC, t, expect)
+
+    def add_shared(self, bucket, t, numel):
+        key = id(t)
+        hit = self.seen.get(key)
+        if hit is not None and hit[0] is t:
+            return hit[1]
+        off = self.add(bucket, t, numel)
+        self.seen[key] = (t, off)
         return off
 
 
-def _pack_color(color, params):
-    """-> (type, params offset, num_stops)"""
+def _np_cached(holder, attr, value):
+    """int32 numpy copy of a small index tensor, cached on the holder object and invalidated
+    by the tensor's identity / in-place version counter."""
+    if not isinstance(value, torch.Tensor):
+        return np.asarray(value, dtype=np.int32).reshape(-1)
+    cache = holder.__dict__.get('_dvg_' + attr)
+    if cache is not None and cache[0] is value and cache[1] == value._version:
+        return cache[2]
+    arr = value.detach().cpu().numpy().astype(np.int32, copy=True).reshape(-1)
+    holder.__dict__['_dvg_' + attr] = (value, value._version, arr)
+    return arr
+
+
+def _pack_color(color, bk):
+    """-> (type, bucket, offset in bucket, num_stops)"""
     if color is None:
-        return COLOR_NONE, 0, 0
+        return COLOR_NONE, B_GENERIC, 0, 0
     if isinstance(color, torch.Tensor):
-        return COLOR_CONSTANT, params.add(color, 4), 0
-    # duck-type so that the reference's own holder classes are accepted too
+        if color.dim() != 1 or color.shape[0] != 4:
+            raise ValueError('a constant colour must be a tensor of 4 elements')
+        return COLOR_CONSTANT, B_VEC4, bk.add(B_VEC4, color, 4), 0
+    # duck-typed so that the reference's own holder classes are accepted too
     if hasattr(color, 'begin') and hasattr(color, 'end'):
         n = color.offsets.shape[0]
         if color.stop_colors.shape[0] != n:
             raise ValueError('gradient offsets / stop_colors length mismatch')
-        off = params.add(color.begin, 2)
-        params.add(color.end, 2)
-        params.add(color.offsets, n)
-        params.add(color.stop_colors, 4 * n)
-        return COLOR_LINEAR, off, n
+        off = bk.add_generic(color.begin, 2)
+        bk.add_generic(color.end, 2)
+        bk.add_generic(color.offsets, n)
+        bk.add_generic(color.stop_colors, 4 * n)
+        return COLOR_LINEAR, B_GENERIC, off, n
     if hasattr(color, 'center') and hasattr(color, 'radius'):
         n = color.offsets.shape[0]
         if color.stop_colors.shape[0] != n:
             raise ValueError('gradient offsets / stop_colors length mismatch')
-        off = params.add(color.center, 2)
-        params.add(color.radius, 2)
-        params.add(color.offsets, n)
-        params.add(color.stop_colors, 4 * n)
-        return COLOR_RADIAL, off, n
+        off = bk.add_generic(color.center, 2)
+        bk.add_generic(color.radius, 2)
+        bk.add_generic(color.offsets, n)
+        bk.add_generic(color.stop_colors, 4 * n)
+        return COLOR_RADIAL, B_GENERIC, off, n
     raise TypeError('unsupported colour %r' % (color,))
 
 
-def _kind(shape):
-    # duck-typed so holders from the reference package work as well
-    n = type(shape).__name__
-    if n in ('Circle', 'Ellipse', 'Path', 'Polygon', 'Rect'):
-        return n
-    raise TypeError('unsupported shape %r' % (shape,))
+def _add_width(bk, sw):
+    if isinstance(sw, torch.Tensor) and sw.dim() == 0:
+        return B_SCALAR, bk.add(B_SCALAR, sw, 1)
+    return B_GENERIC, bk.add_generic(sw, 1)
 
 
 def pack_scene(canvas_width, canvas_height, shapes, shape_groups, filter_type=0, filter_radius=None):
-    """Returns (topo: np.int32[], tensors: list[Tensor]).  `torch.cat([t.reshape(-1) ...])`
-    of `tensors` is `params`."""
-    params = _ParamList()
+    """Returns (topo: np.int32[], buckets: list[list[Tensor]]).  `concat_params(buckets)` is `params`."""
+    bk = _Buckets()
     ns, ng = len(shapes), len(shape_groups)
-    srec = np.zeros((ns, S_LEN), dtype=np.int32)
+    srec = []      # rows of DVG_SHAPE_REC_LEN ints (offsets still bucket-relative)
+    sbucket = []   # (bucket of PARAM_OFF, bucket of WIDTH_OFF, bucket of THICK_OFF)
     ncp_chunks = []
     ncp_total = 0
     points_total = 0
     is_open_path = [False] * ns
     for i, shape in enumerate(shapes):
-        kind = _kind(shape)
-        r = srec[i]
-        use_thickness = False
-        r[3] = -1
-        if kind == 'Circle':
-            r[0] = SHAPE_CIRCLE
-            r[1] = params.add(shape.radius, 1)
-            params.add(shape.center, 2)
-        elif kind == 'Ellipse':
-            r[0] = SHAPE_ELLIPSE
-            r[1] = params.add(shape.radius, 2)
-            params.add(shape.center, 2)
-        elif kind == 'Rect':
-            r[0] = SHAPE_RECT
-            r[1] = params.add(shape.p_min, 2)
-            params.add(shape.p_max, 2)
-        else:
+        kind = type(shape).__name__
+        if kind == 'Path' or kind == 'Polygon':
             pts = shape.points
             if pts.dim() != 2 or pts.shape[1] != 2:
                 raise ValueError('path points must be [N, 2]')
             npts = pts.shape[0]
+            thick_off = -1
+            use_thickness = False
             if kind == 'Path':
-                ncp = shape.num_control_points
-                ncp_np = ncp.detach().cpu().numpy().astype(np.int32, copy=False) if isinstance(ncp, torch.Tensor) \
-                    else np.asarray(ncp, dtype=np.int32)
+                ncp_np = _np_cached(shape, 'ncp', shape.num_control_points)
                 sw = shape.stroke_width
                 if isinstance(sw, torch.Tensor) and sw.dim() > 0 and sw.shape[0] > 1:
                     use_thickness = True
                 flags = (SF_CLOSED if shape.is_closed else 0) | (SF_DISTANCE_APPROX if shape.use_distance_approx else 0)
-            else:  # Polygon
+            else:
                 ncp_np = np.zeros(npts if shape.is_closed else npts - 1, dtype=np.int32)
                 flags = SF_CLOSED if shape.is_closed else 0
-            r[0] = SHAPE_PATH
-            r[1] = params.add(pts, 2 * npts)
+            poff = bk.add(B_POINTS, pts, 2 * npts)
             if use_thickness:
-                r[3] = params.add(shape.stroke_width, npts)
-            r[4] = npts
-            r[5] = ncp_np.shape[0]
-            r[6] = ncp_total
-            r[7] = flags
+                thick_off = bk.add_generic(shape.stroke_width, npts)
+                wb, woff = B_GENERIC, -1
+            else:
+                wb, woff = _add_width(bk, shape.stroke_width)
+            nseg = ncp_np.shape[0]
+            srec.append((SHAPE_PATH, poff, woff, thick_off, npts, nseg, ncp_total, flags))
+            sbucket.append((B_POINTS, wb, B_GENERIC))
             ncp_chunks.append(ncp_np)
-            ncp_total += ncp_np.shape[0]
+            ncp_total += nseg
             points_total += npts
             is_open_path[i] = not shape.is_closed
-        if use_thickness:
-            r[2] = -1
         else:
-            r[2] = params.add(shape.stroke_width, 1)
+            if kind == 'Circle':
+                t = SHAPE_CIRCLE
+                poff = bk.add_generic(shape.radius, 1)
+                bk.add_generic(shape.center, 2)
+            elif kind == 'Ellipse':
+                t = SHAPE_ELLIPSE
+                poff = bk.add_generic(shape.radius, 2)
+                bk.add_generic(shape.center, 2)
+            elif kind == 'Rect':
+                t = SHAPE_RECT
+                poff = bk.add_generic(shape.p_min, 2)
+                bk.add_generic(shape.p_max, 2)
+            else:
+                raise TypeError('unsupported shape %r' % (shape,))
+            wb, woff = _add_width(bk, shape.stroke_width)
+            srec.append((t, poff, woff, -1, 0, 0, 0, 0))
+            sbucket.append((B_GENERIC, wb, B_GENERIC))
 
-    grec = np.zeros((ng, G_LEN), dtype=np.int32)
+    grec = []
+    gbucket = []
     gshape_chunks = []
     gshape_total = 0
+    any_open = any(is_open_path)
     for g, group in enumerate(shape_groups):
-        r = grec[g]
-        ids = group.shape_ids
-        ids_np = ids.detach().cpu().numpy().astype(np.int32, copy=False) if isinstance(ids, torch.Tensor) \
-            else np.asarray(ids, dtype=np.int32)
-        ids_np = ids_np.reshape(-1)
-        if ids_np.size == 0:
+        ids_np = _np_cached(group, 'ids', group.shape_ids)
+        k = ids_np.shape[0]
+        if k == 0:
             raise ValueError('shape group %d has no shapes' % g)
-        if ids_np.min() < 0 or ids_np.max() >= ns:
-            raise ValueError('shape group %d references a shape id out of range' % g)
-        r[0] = gshape_total
-        r[1] = ids_np.shape[0]
-        gshape_chunks.append(ids_np)
-        gshape_total += ids_np.shape[0]
-        r[2], r[3], r[4] = _pack_color(group.fill_color, params)
-        if group.fill_color is not None:
+        ft, fb, foff, fstops = _pack_color(group.fill_color, bk)
+        if ft != COLOR_NONE and any_open:
             # render_pytorch.py:131-136
             for sid in ids_np:
-                if is_open_path[sid]:
+                if 0 <= sid < ns and is_open_path[sid]:
                     warnings.warn('Detected non-closed paths with fill color. This might causes unexpected results.',
                                   Warning)
-        r[5], r[6], r[7] = _pack_color(group.stroke_color, params)
-        r[8] = 1 if group.use_even_odd_rule else 0
-        r[9] = params.add(group.shape_to_canvas, 9)
+        st, sb, soff, sstops = _pack_color(group.stroke_color, bk)
+        xf = group.shape_to_canvas
+        if xf.dim() != 2 or xf.shape[0] != 3 or xf.shape[1] != 3:
+            raise ValueError('shape_to_canvas must be [3, 3]')
+        xoff = bk.add_shared(B_MAT3, xf, 9)
+        grec.append((gshape_total, k, ft, foff, fstops, st, soff, sstops, 1 if group.use_even_odd_rule else 0, xoff, 0, 0))
+        gbucket.append((fb, sb))
+        gshape_chunks.append(ids_np)
+        gshape_total += k
 
-    frad_off = params.add(filter_radius if filter_radius is not None else torch.tensor(0.5), 1)
+    fr = filter_radius if filter_radius is not None else torch.tensor(0.5)
+    frb, froff = _add_width(bk, fr)
+
+    # bucket bases in the final concatenation order
+    base = [0] * NUM_BUCKETS
+    acc = 0
+    for b in range(NUM_BUCKETS):
+        base[b] = acc
+        acc += bk.sizes[b]
+    num_params = acc
+    base_np = np.asarray(base, dtype=np.int64)
+
+    srec = np.asarray(srec, dtype=np.int64).reshape(ns, S_LEN)
+    sb_np = np.asarray(sbucket, dtype=np.int64).reshape(ns, 3)
+    srec[:, 1] += base_np[sb_np[:, 0]]
+    srec[:, 2] = np.where(srec[:, 2] >= 0, srec[:, 2] + base_np[sb_np[:, 1]], -1)
+    srec[:, 3] = np.where(srec[:, 3] >= 0, srec[:, 3] + base_np[sb_np[:, 2]], -1)
+    grec = np.asarray(grec, dtype=np.int64).reshape(ng, G_LEN)
+    gb_np = np.asarray(gbucket, dtype=np.int64).reshape(ng, 2)
+    grec[:, 3] += base_np[gb_np[:, 0]]
+    grec[:, 6] += base_np[gb_np[:, 1]]
+    grec[:, 9] += base[B_MAT3]
+
+    gshapes = np.concatenate(gshape_chunks) if gshape_total else np.zeros(0, np.int32)
+    if gshape_total and (gshapes.min() < 0 or gshapes.max() >= ns):
+        raise ValueError('a shape group references a shape id out of range')
 
     off_shapes = H_LEN
     off_groups = off_shapes + ns * S_LEN
@@ -188,8 +245,8 @@ def pack_scene(canvas_width, canvas_height, shapes, shape_groups, filter_type=0,
     topo[H_NS] = ns
     topo[H_NG] = ng
     topo[H_FTYPE] = int(filter_type)
-    topo[H_FRAD_OFF] = frad_off
-    topo[H_NPARAMS] = params.n
+    topo[H_FRAD_OFF] = froff + base[frb]
+    topo[H_NPARAMS] = num_params
     topo[H_TOTAL_SEGS] = ncp_total
     topo[H_TOTAL_GSHAPES] = gshape_total
     topo[H_OFF_SHAPES] = off_shapes
@@ -202,30 +259,44 @@ def pack_scene(canvas_width, canvas_height, shapes, shape_groups, filter_type=0,
     if ncp_total:
         topo[off_ncp:off_gshapes] = np.concatenate(ncp_chunks)
     if gshape_total:
-        topo[off_gshapes:] = np.concatenate(gshape_chunks)
-    return topo, params.tensors
+        topo[off_gshapes:] = gshapes
+    return topo, bk.tensors
 
 
-def concat_params(tensors, device=None):
+def _flatten_bucket(bucket, tensors, device):
+    """One flat float32 tensor for a bucket, using a single cat/stack when the tensors agree
+    on device and dtype (the common case) and a per-tensor path otherwise."""
+    if not tensors:
+        return None
+    try:
+        if bucket == B_POINTS:
+            return torch.cat(tensors, dim=0).reshape(-1).to(device=device, dtype=torch.float32)
+        if bucket != B_GENERIC:
+            return torch.stack(tensors).reshape(-1).to(device=device, dtype=torch.float32)
+    except (RuntimeError, TypeError):
+        pass
+    return torch.cat([t.to(device=device, dtype=torch.float32).reshape(-1) for t in tensors])
+
+
+def concat_params(buckets, device=None):
     """Differentiable concatenation of the parameter tensors into the flat `params`.
 
-    Gradients flow back to the user's tensors through autograd's CatBackward in C++ instead
-    of the reference's O(#shapes) Python read-back loop (render_pytorch.py:713-866)."""
-    flat = []
-    devs = set()
-    for t in tensors:
-        if t.dtype != torch.float32:
-            t = t.to(torch.float32)
-        flat.append(t.reshape(-1))
-        devs.add(t.device)
-    if len(devs) > 1:
-        target = device if device is not None else torch.device('cpu')
-        flat = [t.to(target) for t in flat]
-    return torch.cat(flat) if len(flat) > 1 else flat[0].clone()
+    Gradients flow back to the user's tensors through autograd's Cat/StackBackward in C++
+    instead of the reference's O(#shapes) Python read-back loop (render_pytorch.py:713-866).
+    `device`: where to build `params` (default: the device of the first path-point tensor,
+    i.e. wherever the user keeps the scene)."""
+    if device is None:
+        for b in buckets:
+            if b:
+                device = b[0].device
+                break
+    parts = [f for f in (_flatten_bucket(b, ts, device) for b, ts in enumerate(buckets)) if f is not None]
+    return torch.cat(parts) if len(parts) > 1 else parts[0].clone()
 
 
 def pack_scene_numpy(canvas_width, canvas_height, shapes, shape_groups, filter_type=0, filter_radius=None):
     """(topo, params) as numpy arrays -- what the oracle entry points take."""
-    topo, tensors = pack_scene(canvas_width, canvas_height, shapes, shape_groups, filter_type, filter_radius)
-    params = concat_params([t.detach().cpu() for t in tensors]).numpy().astype(np.float32, copy=False)
+    topo, buckets = pack_scene(canvas_width, canvas_height, shapes, shape_groups, filter_type, filter_radius)
+    with torch.no_grad():
+        params = concat_params(buckets, torch.device('cpu')).numpy().astype(np.float32, copy=False)
     return topo, np.ascontiguousarray(params)

@@ -1,0 +1,338 @@
+// emul.cpp -- TEST-ONLY host harness.  Compiles the product's host/device arithmetic headers
+// (diffvg_b200/csrc/*.cuh) with g++ and drives them with plain loops, so that the geometric
+// predicates, the per-sample state machine, the scene-build functions and the boundary
+// sampler can be checked against the reference on a machine without a GPU.
+// It is NOT a CPU fallback: nothing in the product imports or links it, the kernels'
+// orchestration (tiles, shared memory, warp reductions) is not represented here, and the
+// product fails loudly when the CUDA library is missing.
+#include "../../diffvg_b200/csrc/dvg_common.cuh"
+#include "../../diffvg_b200/csrc/dvg_scene.cuh"
+#include "../../diffvg_b200/csrc/dvg_geom.cuh"
+#include "../../diffvg_b200/csrc/dvg_color.cuh"
+#include "../../diffvg_b200/csrc/dvg_boundary.cuh"
+#include "../../diffvg_b200/csrc/dvg_trace.cuh"
+#include "../../diffvg_b200/csrc/dvg_buildfn.cuh"
+
+#include <algorithm>
+#include <atomic>
+#include <cstring>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+using namespace dvg;
+
+namespace {
+
+struct HostScene {
+    std::vector<int> topo;
+    std::vector<float> params;
+    std::vector<int> inst_group, inst_shape, inst_prim_begin, prim_inst, prim_seg, prim_point_id;
+    std::vector<float> shapes_length, shape_r0, seg_cdf, seg_pmf, prim_thick, shape_cdf, shape_pmf;
+    std::vector<Box> shape_box, prim_box, prim_cbox;
+    std::vector<int> seg_point_id;
+    std::vector<InstInfo> insts;
+    std::vector<GroupInfo> groups;
+    std::vector<F4> p01, p23, rad;
+    std::vector<PrimMeta> meta;
+    int error_flag = 0;
+    float total_length = 0;
+    SceneView sc;
+};
+
+void build(HostScene &hs, const int32_t *topo, const float *params) {
+    const int ns = topo[DVG_H_NUM_SHAPES], ng = topo[DVG_H_NUM_GROUPS];
+    int topo_len = topo[DVG_H_OFF_GSHAPES] + topo[DVG_H_TOTAL_GSHAPES];
+    topo_len = std::max(topo_len, topo[DVG_H_OFF_NCP] + topo[DVG_H_TOTAL_SEGS]);
+    hs.topo.assign(topo, topo + topo_len);
+    hs.params.assign(params, params + topo[DVG_H_NUM_PARAMS]);
+    const int *t = hs.topo.data();
+    for (int g = 0; g < ng; g++) {
+        const int *r = t + t[DVG_H_OFF_GROUPS] + g * DVG_GROUP_REC_LEN;
+        const int *ids = t + t[DVG_H_OFF_GSHAPES] + r[DVG_G_SHAPES_OFF];
+        for (int k = 0; k < r[DVG_G_NUM_SHAPES]; k++) {
+            const int *sr = t + t[DVG_H_OFF_SHAPES] + ids[k] * DVG_SHAPE_REC_LEN;
+            int inst = (int)hs.inst_group.size();
+            hs.inst_group.push_back(g); hs.inst_shape.push_back(ids[k]);
+            hs.inst_prim_begin.push_back((int)hs.prim_inst.size());
+            if (sr[DVG_S_TYPE] == DVG_SHAPE_PATH) {
+                const int *ncp = t + t[DVG_H_OFF_NCP] + sr[DVG_S_NCP_OFF];
+                int pid = 0;
+                for (int seg = 0; seg < sr[DVG_S_NUM_SEGS]; seg++) {
+                    hs.prim_inst.push_back(inst); hs.prim_seg.push_back(seg); hs.prim_point_id.push_back(pid);
+                    pid += ncp[seg] + 1;
+                }
+            } else {
+                hs.prim_inst.push_back(inst); hs.prim_seg.push_back(0); hs.prim_point_id.push_back(0);
+            }
+        }
+    }
+    hs.inst_prim_begin.push_back((int)hs.prim_inst.size());
+    const int ni = (int)hs.inst_group.size(), np = (int)hs.prim_inst.size(), nsg = std::max(t[DVG_H_TOTAL_SEGS], 1);
+    hs.shapes_length.resize(ns); hs.shape_box.resize(ns); hs.shape_r0.resize(ns);
+    hs.seg_cdf.resize(nsg); hs.seg_pmf.resize(nsg); hs.seg_point_id.resize(nsg);
+    hs.insts.resize(ni); hs.groups.resize(ng);
+    hs.p01.resize(np); hs.p23.resize(np); hs.rad.resize(np); hs.prim_box.resize(np); hs.prim_thick.resize(np);
+    hs.meta.resize(np); hs.prim_cbox.resize(np); hs.shape_cdf.resize(ni); hs.shape_pmf.resize(ni);
+    BuildView bv;
+    bv.canvas_w = t[DVG_H_CANVAS_W]; bv.canvas_h = t[DVG_H_CANVAS_H];
+    bv.num_shapes = ns; bv.num_groups = ng; bv.num_insts = ni; bv.num_prims = np;
+    bv.topo = t; bv.params = hs.params.data();
+    bv.inst_group = hs.inst_group.data(); bv.inst_shape = hs.inst_shape.data(); bv.inst_prim_begin = hs.inst_prim_begin.data();
+    bv.prim_inst = hs.prim_inst.data(); bv.prim_seg = hs.prim_seg.data(); bv.prim_point_id = hs.prim_point_id.data();
+    bv.shapes_length = hs.shapes_length.data(); bv.shape_box = hs.shape_box.data(); bv.shape_r0 = hs.shape_r0.data();
+    bv.seg_cdf = hs.seg_cdf.data(); bv.seg_pmf = hs.seg_pmf.data(); bv.seg_point_id = hs.seg_point_id.data();
+    bv.insts = hs.insts.data(); bv.groups = hs.groups.data();
+    bv.prim_p01 = hs.p01.data(); bv.prim_p23 = hs.p23.data(); bv.prim_rad = hs.rad.data(); bv.prim_box = hs.prim_box.data();
+    bv.prim_thick = hs.prim_thick.data(); bv.prim_meta = hs.meta.data(); bv.prim_cbox = hs.prim_cbox.data();
+    bv.shape_cdf = hs.shape_cdf.data(); bv.shape_pmf = hs.shape_pmf.data();
+    bv.error_flag = &hs.error_flag; bv.total_length = &hs.total_length;
+    for (int s = 0; s < ns; s++) build_shape(bv, s);
+    for (int g = 0; g < ng; g++) build_group(bv, g);
+    for (int e = 0; e < np; e++) build_prim(bv, e);
+    float norm = build_shape_cdf_serial(bv);
+    for (int i = 0; i < ni; i++) { hs.shape_cdf[i] /= norm; hs.shape_pmf[i] /= norm; }
+    SceneView &sc = hs.sc;
+    sc.canvas_w = bv.canvas_w; sc.canvas_h = bv.canvas_h;
+    sc.num_shapes = ns; sc.num_groups = ng; sc.num_insts = ni; sc.num_prims = np;
+    sc.filter.type = t[DVG_H_FILTER_TYPE]; sc.filter.radius = hs.params[t[DVG_H_FILTER_RADIUS_OFF]];
+    sc.filter_radius_off = t[DVG_H_FILTER_RADIUS_OFF];
+    sc.topo = t; sc.params = hs.params.data();
+    sc.prim_p01 = hs.p01.data(); sc.prim_p23 = hs.p23.data(); sc.prim_rad = hs.rad.data(); sc.prim_box = hs.prim_box.data();
+    sc.prim_thick = hs.prim_thick.data(); sc.prim_meta = hs.meta.data(); sc.prim_cbox = hs.prim_cbox.data();
+    sc.insts = hs.insts.data(); sc.groups = hs.groups.data();
+    sc.shapes_length = hs.shapes_length.data(); sc.shape_cdf = hs.shape_cdf.data(); sc.shape_pmf = hs.shape_pmf.data();
+    sc.seg_cdf = hs.seg_cdf.data(); sc.seg_pmf = hs.seg_pmf.data(); sc.seg_point_id = hs.seg_point_id.data();
+    sc.error_flag = &hs.error_flag;
+}
+
+PrimRef prim_ref(const HostScene &hs, int e) {
+    PrimRef pr;
+    pr.p01 = hs.p01[e]; pr.p23 = hs.p23[e]; pr.rad = hs.rad[e]; pr.box = hs.prim_box[e]; pr.thick = hs.prim_thick[e];
+    pr.tf = hs.meta[e].type_flags; pr.inst = hs.meta[e].inst; pr.group = hs.insts[hs.meta[e].inst].group;
+    return pr;
+}
+
+// candidate primitives for a canvas-space rectangle (mirrors the tile-bin test of dvg_build.cu)
+void candidates(const HostScene &hs, float x0, float y0, float x1, float y1, std::vector<int> &out) {
+    out.clear();
+    for (int e = 0; e < hs.sc.num_prims; e++) {
+        const Box &b = hs.prim_cbox[e];
+        if (b.x0 <= x1 && b.x1 >= x0 && b.y0 <= y1 && b.y1 >= y0) out.push_back(e);
+    }
+}
+
+template <typename F>
+void parallel_rows(int n, int nthreads, F f) {
+    std::vector<std::thread> th;
+    std::atomic<int> next{0};
+    for (int t = 0; t < nthreads; t++) th.emplace_back([&] { for (int y; (y = next++) < n;) f(y); });
+    for (auto &t : th) t.join();
+}
+
+}  // namespace
+
+#define EXPORT extern "C" __attribute__((visibility("default")))
+
+// Forward (d_image == null) or backward.  Images are host arrays.  Backward accumulation is
+// serialised with a mutex per call to keep the harness simple.
+EXPORT int emul_render(const int32_t *topo, const float *params, const float *background, float *image,
+                       int W, int H, int nsx, int nsy, uint64_t seed, const float *d_image,
+                       float *d_params, float *d_background, int skip_xform_grad, int nthreads) {
+    HostScene hs;
+    build(hs, topo, params);
+    if (hs.error_flag) return 3;
+    const SceneView &sc = hs.sc;
+    const int spp = nsx * nsy;
+    std::vector<float> weight((size_t)W * H, 0.f);
+    const int ri = (int)ceilf(sc.filter.radius);
+    for (int idx = 0; idx < W * H * spp; idx++) {  // weight_kernel (diffvg.cpp:1115-1158)
+        const int sx = idx % nsx, sy = (idx / nsx) % nsy, x = (idx / spp) % W, y = idx / (spp * W);
+        F2 pt, cpt;
+        sample_position(sc.canvas_w, sc.canvas_h, W, H, nsx, nsy, seed, false, x, y, sx, sy, idx, pt, cpt);
+        for (int dy = -ri; dy <= ri; dy++)
+            for (int dx = -ri; dx <= ri; dx++) {
+                int xx = x + dx, yy = y + dy;
+                if (xx >= 0 && xx < W && yy >= 0 && yy < H)
+                    weight[yy * W + xx] += filter_weight(sc.filter, (xx + 0.5f) - pt.x, (yy + 0.5f) - pt.y);
+            }
+    }
+    const float cw = (float)sc.canvas_w, ch = (float)sc.canvas_h;
+    const float margin = 4e-4f * std::max(cw, ch) + 1e-4f;
+    std::mutex mu;
+    RenderArgs ra;
+    memset(&ra, 0, sizeof ra);
+    ra.width = W; ra.height = H; ra.nsx = nsx; ra.nsy = nsy; ra.seed = seed;
+    ra.background = background; ra.d_render_image = d_image; ra.d_params = d_params; ra.d_background = d_background;
+    ra.weight_image = weight.data();
+    ra.flags = skip_xform_grad ? 1u : 0u;
+
+    parallel_rows(H, nthreads, [&](int y) {
+        std::vector<int> cand;
+        std::vector<int> fkey(DVG_MAXF);
+        std::vector<F4> fprev(DVG_MAXF);
+        std::vector<float> row(d_image ? 0 : (size_t)(2 * ri + 1) * W * 4, 0.f);  // rows y-ri..y+ri
+        for (int x = 0; x < W; x++) {
+            candidates(hs, (float)x / W * cw - margin, (float)y / H * ch - margin, (float)(x + 1) / W * cw + margin,
+                       (float)(y + 1) / H * ch + margin, cand);
+            for (int s = 0; s < spp; s++) {
+                const int sx = s % nsx, sy = s / nsx;
+                const int idx = ((y * W + x) * nsy + sy) * nsx + sx;
+                F2 pt, cpt;
+                sample_position(sc.canvas_w, sc.canvas_h, W, H, nsx, nsy, seed, false, x, y, sx, sy, idx, pt, cpt);
+                const float *bg_px = background ? background + 4 * (y * W + x) : nullptr;
+                F4 first = bg_px ? mk4(bg_px[0], bg_px[1], bg_px[2], bg_px[3]) : mk4(0, 0, 0, 0);
+                if (!d_image) {
+                    SampleTracer<false, false> tr;
+                    tr.init(cpt, true, first, -1, -1, nullptr, nullptr);
+                    for (int e : cand) tr.step(sc, prim_ref(hs, e));
+                    tr.finish(sc);
+                    const F4 color = tr.resolve(bg_px);
+                    for (int dy = -ri; dy <= ri; dy++)
+                        for (int dx = -ri; dx <= ri; dx++) {
+                            int xx = x + dx, yy = y + dy;
+                            if (xx >= 0 && xx < W && yy >= 0 && yy < H && weight[yy * W + xx] > 0) {
+                                float fw = filter_weight(sc.filter, (xx + 0.5f) - pt.x, (yy + 0.5f) - pt.y);
+                                float inv_ws = 1.f / weight[yy * W + xx];
+                                float *d = &row[((size_t)(dy + ri) * W + xx) * 4];
+                                d[0] += (fw * color.x) * inv_ws; d[1] += (fw * color.y) * inv_ws;
+                                d[2] += (fw * color.z) * inv_ws; d[3] += (fw * color.w) * inv_ws;
+                            }
+                        }
+                } else {
+                    SampleTracer<false, true> tr;
+                    tr.init(cpt, true, first, -1, -1, fkey.data(), fprev.data());
+                    for (int e : cand) tr.step(sc, prim_ref(hs, e));
+                    tr.finish(sc);
+                    const F4 color = tr.resolve(bg_px);
+                    const F4 d_color = gather_d_color(sc.filter, d_image, weight.data(), W, H, pt);
+                    std::lock_guard<std::mutex> lk(mu);
+                    float dcr = d_color.x, dcg = d_color.y, dcb = d_color.z, dca = d_color.w;
+                    if (tr.nfrag > 0) {
+                        if (tr.accum.w > 1e-6f) {
+                            const float inv = 1.f / tr.accum.w;
+                            dca -= (d_color.x * color.x + d_color.y * color.y + d_color.z * color.z) / tr.accum.w;
+                            dcr = d_color.x * inv; dcg = d_color.y * inv; dcb = d_color.z * inv;
+                        }
+                        for (int i = tr.sp - 1; i >= 0; i--) {
+                            const int key = fkey[i];
+                            const GroupInfo &g = sc.groups[key >> 1];
+                            const int ctype = (key & 1) ? g.stroke_type : g.fill_type;
+                            const int coff = (key & 1) ? g.stroke_off : g.fill_off;
+                            const int cstops = (key & 1) ? g.stroke_stops : g.fill_stops;
+                            const F4 prev = fprev[i];
+                            const F4 fc = eval_color(ctype, sc.params + coff, cstops, cpt);
+                            const float d_prev_alpha = dca * (1.f - fc.w);
+                            float d_alpha_i = dca * (1.f - prev.w);
+                            d_alpha_i += (dcr * (fc.x - prev.x) + dcg * (fc.y - prev.y)) + dcb * (fc.z - prev.z);
+                            F4 dc = mk4(dcr * fc.w, dcg * fc.w, dcb * fc.w, d_alpha_i);
+                            dcr = dcr * (1 - fc.w); dcg = dcg * (1 - fc.w); dcb = dcb * (1 - fc.w);
+                            dca = d_prev_alpha;
+                            if (ctype == 0) { for (int k = 0; k < 4; k++) d_params[coff + k] += (&dc.x)[k]; }
+                            else if (!(key & 1)) d_eval_gradient(ctype, sc.params + coff, cstops, cpt, dc, d_params + coff, nullptr);
+                        }
+                        if (bg_px && d_background) {
+                            float *d = d_background + 4 * (y * W + x);
+                            d[0] += dcr; d[1] += dcg; d[2] += dcb; d[3] += dca;
+                        }
+                    } else if (bg_px && d_background) {
+                        float *d = d_background + 4 * (y * W + x);
+                        d[0] += d_color.x; d[1] += d_color.y; d[2] += d_color.z; d[3] += d_color.w;
+                    }
+                    for (int dy = -ri; dy <= ri; dy++)
+                        for (int dx = -ri; dx <= ri; dx++) {
+                            int xx = x + dx, yy = y + dy;
+                            if (xx >= 0 && xx < W && yy >= 0 && yy < H && weight[yy * W + xx] > 0) {
+                                const float ws = weight[yy * W + xx];
+                                const float ddx = (xx + 0.5f) - pt.x, ddy = (yy + 0.5f) - pt.y;
+                                const float fw = filter_weight(sc.filter, ddx, ddy);
+                                const float *dp = d_image + 4 * (yy * W + xx);
+                                const float dotv = dp[0] * color.x + dp[1] * color.y + dp[2] * color.z + dp[3] * color.w;
+                                const float d_weight = (dotv * ws - fw * dotv * (ws - fw)) / (ws * ws);
+                                d_params[sc.filter_radius_off] += d_filter_weight_radius(sc.filter, ddx, ddy, d_weight);
+                            }
+                        }
+                }
+            }
+        }
+        if (!d_image) {
+            std::lock_guard<std::mutex> lk(mu);
+            for (int dy = -ri; dy <= ri; dy++) {
+                int yy = y + dy;
+                if (yy < 0 || yy >= H) continue;
+                for (int i = 0; i < W * 4; i++) image[(size_t)yy * W * 4 + i] += row[(size_t)(dy + ri) * W * 4 + i];
+            }
+        }
+    });
+
+    if (d_image) {
+        // boundary term (diffvg.cpp:1558-1626), one boundary sample per pixel sample index
+        const int n = W * H * spp;
+        parallel_rows((n + 4095) / 4096, nthreads, [&](int blk) {
+            std::vector<int> cand;
+            for (int idx = blk * 4096; idx < std::min(n, (blk + 1) * 4096); idx++) {
+                BoundarySample bs;
+                make_boundary_sample(sc, idx, seed, bs);
+                if (bs.inst < 0) continue;
+                const int bx = (int)(bs.pt.x * W), by = (int)(bs.pt.y * H);
+                if (bx < 0 || bx >= W || by < 0 || by >= H) continue;
+                const InstInfo &ii = sc.insts[bs.inst];
+                const float px = bs.pt.x * cw, py = bs.pt.y * ch;
+                candidates(hs, px - 2 * margin, py - 2 * margin, px + 2 * margin, py + 2 * margin, cand);
+                const float *bg_px = background ? background + 4 * (by * W + bx) : nullptr;
+                F4 first = bg_px ? mk4(bg_px[0], bg_px[1], bg_px[2], bg_px[3]) : mk4(0, 0, 0, 0);
+                F4 col[2]; bool hit[2];
+                for (int side = 0; side < 2; side++) {
+                    const F2 off = 1e-4f * bs.normal;
+                    const F2 npt = side ? bs.pt + off : bs.pt - off;
+                    SampleTracer<true, false> tr;
+                    tr.init(mk2(npt.x * sc.canvas_w, npt.y * sc.canvas_h), true, first, ii.group, ii.shape, nullptr, nullptr);
+                    for (int e : cand) tr.step(sc, prim_ref(hs, e));
+                    tr.finish(sc);
+                    col[side] = tr.resolve(bg_px); hit[side] = tr.q_hit();
+                }
+                if (!hit[0] && !hit[1]) continue;
+                F4 c_in = col[0], c_out = col[1];
+                F2 normal = bs.normal;
+                if (!hit[0]) { normal = -normal; c_in = col[1]; c_out = col[0]; }
+                F4 d_color = gather_d_color(sc.filter, d_image, weight.data(), W, H, mk2(bs.pt.x * W, bs.pt.y * H));
+                d_color = d_color * (1.f / (float)(sc.canvas_w * sc.canvas_h));
+                const F4 diff = c_in - c_out;
+                const float contrib = (diff.x * d_color.x + diff.y * d_color.y + diff.z * d_color.z + diff.w * d_color.w) / bs.pdf;
+                std::lock_guard<std::mutex> lk(mu);
+                accumulate_boundary_gradient(sc, ra, bs, ii, sc.groups[ii.group], contrib, normal);
+            }
+        });
+    }
+    return 0;
+}
+
+// Scene-build tables for the bit-exact CDF / indexing checks (same selectors as dvg_scene_dump
+// where applicable: 3 shapes_length, 4 shape cdf, 5 shape pmf, 6/7/8 per-path tables).
+EXPORT int64_t emul_scene_dump(const int32_t *topo, const float *params, int what, int index, uint32_t *out, int64_t cap) {
+    HostScene hs;
+    build(hs, topo, params);
+    std::vector<uint32_t> w;
+    auto pushf = [&](float f) { uint32_t u; memcpy(&u, &f, 4); w.push_back(u); };
+    const int *sr = hs.topo.data() + hs.topo[DVG_H_OFF_SHAPES] + index * DVG_SHAPE_REC_LEN;
+    switch (what) {
+        case 3: for (float f : hs.shapes_length) pushf(f); break;
+        case 4: for (float f : hs.shape_cdf) pushf(f); break;
+        case 5: for (float f : hs.shape_pmf) pushf(f); break;
+        case 6: for (int i = 0; i < sr[DVG_S_NUM_SEGS]; i++) pushf(hs.seg_cdf[sr[DVG_S_NCP_OFF] + i]); break;
+        case 7: for (int i = 0; i < sr[DVG_S_NUM_SEGS]; i++) pushf(hs.seg_pmf[sr[DVG_S_NCP_OFF] + i]); break;
+        case 8: for (int i = 0; i < sr[DVG_S_NUM_SEGS]; i++) w.push_back((uint32_t)hs.seg_point_id[sr[DVG_S_NCP_OFF] + i]); break;
+        default: return -1;
+    }
+    if ((int64_t)w.size() > cap) return -1;
+    memcpy(out, w.data(), w.size() * 4);
+    return (int64_t)w.size();
+}
+
+// PCG known-answer helper: state after init and the first two floats.
+EXPORT void emul_pcg(int idx, uint64_t seed, uint64_t *state, float *rx, float *ry) {
+    Pcg32 r = pcg32_init(idx, seed);
+    *state = r.state;
+    *rx = pcg32_next_float(r);
+    *ry = pcg32_next_float(r);
+}

@@ -1,0 +1,60 @@
+"""Shared helpers for the parity tests."""
+import numpy as np
+import torch
+
+from diffvg_b200 import scene_pack
+
+
+def pack(scene, filter_type=0, filter_radius=0.5):
+    cw, ch, shapes, groups = scene
+    return scene_pack.pack_scene_numpy(cw, ch, shapes, groups, filter_type, torch.tensor(filter_radius))
+
+
+def rel_l2(a, b):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(a), 1e-30))
+
+
+def image_report(ref, got, spp):
+    """max-abs error, number of pixels off by more than 1e-5, and how many of those look like
+    whole-sample flips (error close to a multiple of 1/spp in some channel)."""
+    d = np.abs(ref.astype(np.float64) - got.astype(np.float64))
+    bad = d.max(axis=2) > 1e-5
+    return dict(max_abs=float(d.max()), bad_pixels=int(bad.sum()))
+
+
+def gpu_render(topo, params, width, height, nsx, nsy, seed, background=None, d_render_image=None,
+               skip_xform_grad=False):
+    """Drive the product C ABI directly (ctypes) with device buffers managed through torch."""
+    import ctypes
+    from diffvg_b200 import _native as n
+    dev = torch.device('cuda', 0)
+    h = ctypes.c_void_p()
+    topo = np.ascontiguousarray(topo, np.int32)
+    n.check(n.lib.dvg_scene_create(topo.ctypes.data, topo.shape[0], 0, ctypes.byref(h)))
+    try:
+        stream = torch.cuda.current_stream().cuda_stream
+        p = np.ascontiguousarray(params, np.float32)
+        n.check(n.lib.dvg_scene_set_params(h, p.ctypes.data, p.shape[0], 0, stream))
+        bg = torch.from_numpy(background).to(dev).contiguous() if background is not None else None
+        out = {}
+        if d_render_image is None:
+            img = torch.empty(height, width, 4, device=dev)
+            n.check(n.lib.dvg_render_forward(h, bg.data_ptr() if bg is not None else None, img.data_ptr(), None,
+                                             width, height, nsx, nsy, int(seed), 0, None, 0, stream))
+            out['image'] = img.cpu().numpy()
+        else:
+            dimg = torch.from_numpy(np.ascontiguousarray(d_render_image, np.float32)).to(dev)
+            dpar = torch.empty(p.shape[0], device=dev)
+            dbg = torch.empty_like(bg) if bg is not None else None
+            n.check(n.lib.dvg_render_backward(h, bg.data_ptr() if bg is not None else None, dimg.data_ptr(), None,
+                                              width, height, nsx, nsy, int(seed), 0, None, 0, dpar.data_ptr(),
+                                              dbg.data_ptr() if dbg is not None else None, None,
+                                              1 if skip_xform_grad else 0, stream))
+            out['d_params'] = dpar.cpu().numpy()
+            out['d_background'] = dbg.cpu().numpy() if dbg is not None else None
+        torch.cuda.synchronize()
+        return out
+    finally:
+        n.lib.dvg_scene_destroy(h)
