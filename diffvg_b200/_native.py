@@ -40,6 +40,13 @@ lib.dvg_scene_destroy.restype = _i
 lib.dvg_scene_dump.argtypes = [_vp, _i, _i, _vp, _i64, _vp]
 lib.dvg_scene_dump.restype = _i64
 
+lib.dvg_profile_enable.argtypes = [_i]
+lib.dvg_profile_enable.restype = _i
+lib.dvg_profile_report.argtypes = [ctypes.c_char_p, _i64]
+lib.dvg_profile_report.restype = _i64
+lib.dvg_measure_peak.argtypes = [_i, _i, ctypes.POINTER(ctypes.c_double)]
+lib.dvg_measure_peak.restype = _i
+
 DVG_ERR_UNSUPPORTED = 4
 DVG_BWD_SKIP_XFORM_GRAD = 1
 DVG_BWD_ACCUMULATE = 2
@@ -55,3 +62,26 @@ def check(rc):
 
 def launch_count():
     return int(lib.dvg_kernel_launch_count())
+
+
+def profile_enable(on):
+    check(lib.dvg_profile_enable(1 if on else 0))
+
+
+def profile_report():
+    """{kernel name: (launches, total_ms)} for the launches since the last report."""
+    buf = ctypes.create_string_buffer(1 << 16)
+    n = lib.dvg_profile_report(buf, len(buf))
+    if n < 0:
+        raise RuntimeError(lib.dvg_last_error().decode())
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, cnt, ms = line.rsplit(',', 2)
+        out[name] = (int(cnt), float(ms))
+    return out
+
+
+def measure_peak(which, device=0):
+    v = ctypes.c_double()
+    check(lib.dvg_measure_peak(which, device, ctypes.byref(v)))
+    return v.value

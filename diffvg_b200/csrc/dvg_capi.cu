@@ -10,6 +10,8 @@
 
 namespace dvg {
 long long g_launch_count = 0;
+int prof_report(char *buf, long long cap);
+double peak_probe_flops(int iters, int blocks);
 }
 
 using namespace dvg;
@@ -78,6 +80,8 @@ struct DvgScene {
     uint64_t w_seed = 0; float w_radius = 0; bool w_valid = false;
     DevBuf d_keys, d_tile_counts, d_tile_offsets, d_tile_fill, d_blk_counts, d_blk_offsets, d_sorted;
     int32_t *h_pinned = nullptr;  // [0] error flag, [1] total bin items
+    float *h_params_pinned = nullptr;  // staging for host-resident params (true async H2D)
+    cudaEvent_t h_params_free = nullptr;  // recorded after the H2D copy that last read the staging buffer
     bool params_set = false;
     bool checked = false;
     int scene_error = 0;
@@ -135,6 +139,10 @@ struct DvgScene {
         for (DevBuf *b : all) b->release();
         if (h_pinned) cudaFreeHost(h_pinned);
         h_pinned = nullptr;
+        if (h_params_pinned) cudaFreeHost(h_params_pinned);
+        h_params_pinned = nullptr;
+        if (h_params_free) cudaEventDestroy(h_params_free);
+        h_params_free = nullptr;
     }
 };
 
@@ -378,8 +386,20 @@ int dvg_scene_set_params(DvgScene *s, const float *params, int64_t num_params, i
     if (num_params != s->num_params) return fail(DVG_ERR_INVALID, "params length does not match the topology");
     DeviceGuard guard(s->device);
     cudaStream_t st = (cudaStream_t)stream;
-    CK(cudaMemcpyAsync(s->d_params.p, params, sizeof(float) * num_params,
-                       params_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+    if (params_on_device) {
+        CK(cudaMemcpyAsync(s->d_params.p, params, sizeof(float) * num_params, cudaMemcpyDeviceToDevice, st));
+    } else {
+        // pageable host memory -> pinned staging -> async H2D (the caller may reuse `params` on return)
+        if (!s->h_params_pinned) {
+            CK(cudaMallocHost((void **)&s->h_params_pinned, sizeof(float) * std::max(s->num_params, 1)));
+            CK(cudaEventCreateWithFlags(&s->h_params_free, cudaEventDisableTiming));
+        } else {
+            CK(cudaEventSynchronize(s->h_params_free));
+        }
+        memcpy(s->h_params_pinned, params, sizeof(float) * num_params);
+        CK(cudaMemcpyAsync(s->d_params.p, s->h_params_pinned, sizeof(float) * num_params, cudaMemcpyHostToDevice, st));
+        CK(cudaEventRecord(s->h_params_free, st));
+    }
     launch_build(s->build_view(), st);
     CK(cudaGetLastError());
     s->params_set = true;
@@ -497,6 +517,42 @@ int dvg_render_backward(DvgScene *s, const float *background, const float *d_ren
     if (d_translation) return fail(DVG_ERR_UNSUPPORTED, "d_translation is not implemented yet in this build");
     return dvg_render_backward_rows(s, background, d_render_image, width, height, nsx, nsy, seed, use_prefiltering,
                                     0, height, d_params, d_background, flags, stream);
+}
+
+int dvg_profile_enable(int on) {
+    dvg::g_profile_on = on != 0;
+    return DVG_OK;
+}
+
+int64_t dvg_profile_report(char *buf, int64_t cap) {
+    if (!buf || cap <= 0) { fail(DVG_ERR_INVALID, "null buffer"); return -1; }
+    int n = dvg::prof_report(buf, cap);
+    if (n < 0) fail(DVG_ERR_INVALID, "profile buffer too small");
+    return n;
+}
+
+int dvg_measure_peak(int which, int device, double *tflops) {
+    if (!tflops || which < 0 || which > 1) return fail(DVG_ERR_INVALID, "bad argument");
+    DeviceGuard guard(device);
+    float *d = nullptr;
+    CK(cudaMalloc((void **)&d, 64));
+    cudaEvent_t a, b;
+    CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+    const int iters = which == 0 ? 4096 : 2048;
+    double best = 0;
+    for (int rep = 0; rep < 4; rep++) {
+        CK(cudaEventRecord(a, 0));
+        launch_peak_probe(which, d, iters, 0);
+        CK(cudaEventRecord(b, 0));
+        CK(cudaEventSynchronize(b));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, a, b));
+        double tf = dvg::peak_probe_flops(iters, 148 * 8) / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(d);
+    *tflops = best;
+    return DVG_OK;
 }
 
 int64_t dvg_scene_dump(DvgScene *s, int what, int index, uint32_t *out, int64_t cap, void *stream) {

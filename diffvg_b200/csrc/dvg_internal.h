@@ -14,9 +14,17 @@ namespace dvg {
 
 extern long long g_launch_count;  // kernels launched since load (dvg_kernel_launch_count)
 
+// Optional per-kernel timing with CUDA events on the launching stream (dvg_profile_enable):
+// bench.py uses it to time the dominant kernel live; off by default (zero overhead).
+extern bool g_profile_on;
+void prof_begin(const char *name, cudaStream_t st);
+void prof_end(cudaStream_t st);
+
 #define DVG_LAUNCH(kernel, grid, block, smem, stream, ...)            \
     do {                                                              \
+        if (::dvg::g_profile_on) ::dvg::prof_begin(#kernel, stream);  \
         kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);   \
+        if (::dvg::g_profile_on) ::dvg::prof_end(stream);             \
         ::dvg::g_launch_count++;                                      \
     } while (0)
 
@@ -40,6 +48,7 @@ struct BoundaryWork {
     int max_blocks;
 };
 
+void launch_peak_probe(int which, float *out, int iters, cudaStream_t st);
 void launch_build(const BuildView &bv, cudaStream_t st);
 void launch_bin_count(const BuildView &bv, const BinBuild &bb, cudaStream_t st);
 void launch_bin_fill(const BuildView &bv, const BinBuild &bb, cudaStream_t st);

@@ -121,6 +121,18 @@ int64_t dvg_scene_dump(DvgScene *scene, int what, int index, uint32_t *out, int6
 int64_t dvg_kernel_launch_count(void);
 
 /*
+ * Measurement support (no reference counterpart; the reference only prints wall-clock times,
+ * render_pytorch.py:8-12).  dvg_profile_enable(1) makes every kernel launch record a CUDA-event
+ * pair on its stream; dvg_profile_report synchronises, writes "kernel,launches,total_ms\n" lines
+ * for the launches since the last report and returns the text length (-1 on error).
+ * dvg_measure_peak runs an FMA-chain probe (which: 0 = FP32, 1 = FP64) and returns the achieved
+ * TFLOP/s: the roofline denominator for this CUDA-core-bound path.
+ */
+int dvg_profile_enable(int on);
+int64_t dvg_profile_report(char *buf, int64_t cap);
+int dvg_measure_peak(int which, int device, double *tflops);
+
+/*
  * Sharded variants for one-process-per-GPU runs.  Pixel samples
  * [sample_begin, sample_end) of the global index space idx = ((y*W+x)*nsy+sy)*nsx+sx and the
  * same range of boundary-sample indices are processed; RNG streams depend on the global

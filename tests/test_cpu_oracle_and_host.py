@@ -1,0 +1,244 @@
+"""CPU-only tests (`-m "not gpu"`): the oracle against the reference's known answers and the
+committed golden vectors, the host-side packing logic, and the C-ABI library's exported symbols.
+No kernel is launched here."""
+import ctypes
+import glob
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import emul
+import ref_oracle
+import scenes
+import util
+from diffvg_b200 import scene_pack
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = sorted(glob.glob(os.path.join(ROOT, 'tests', 'golden', '*.npz')))
+
+needs_ref = pytest.mark.skipif(not ref_oracle.available(), reason='oracle/_ref not built (needs /root/reference)')
+
+# (idx, seed) -> (state after init, first two floats), validated against pcg.h
+PCG_KAT = [
+    (0, 0, 0xf6e7b88658a69fc9, 0.452188373, 0.983064532),
+    (1, 0, 0xa78ba0e0f1d19e25, 0.0703772306, 0.112021565),
+    (0, 1, 0x4f39acb3a53c1ef6, 0.863092065, 0.755336404),
+    (262143, 1, 0x400029050581209a, 0.628906608, 0.358397841),
+    (4194303, 7, 0xc727c8286e921ba8, 0.997012258, 0.773138762),
+]
+
+
+def test_pcg_known_answers_product_header():
+    """pcg.h:11-40 restated in dvg_common.cuh, compiled for the host by tests/host_emul."""
+    for idx, seed, state, rx, ry in PCG_KAT:
+        st, x, y = emul.pcg(idx, seed)
+        assert st == state
+        assert np.float32(x) == np.float32(rx) and np.float32(y) == np.float32(ry)
+
+
+def test_golden_fixtures_exist():
+    assert len(GOLDEN) >= 8
+
+
+@needs_ref
+@pytest.mark.parametrize('path', GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_reference_reproduces_golden(path):
+    """The compiled reference (oracle/_ref) still produces the committed vectors: forward bit-exact
+    (SURVEY Q20), gradients to atomic-order noise."""
+    g = np.load(path)
+    W, H, nsx, nsy, seed, ft = [int(v) for v in g['config']]
+    bg = None
+    if 'd_background' in g.files:
+        from golden.make_golden import background_for
+        bg = background_for(os.path.basename(path)[:-4], H, W)
+    from golden.make_golden import d_image_for
+    img = ref_oracle.render(g['topo'], g['params'], W, H, nsx, nsy, seed, background=bg)['image']
+    if ft == 0:
+        assert np.array_equal(img, g['image'])
+    else:
+        assert np.abs(img - g['image']).max() <= 1e-6
+    d_img = d_image_for(os.path.basename(path)[:-4], H, W)
+    bwd = ref_oracle.render(g['topo'], g['params'], W, H, nsx, nsy, seed, background=bg, d_render_image=d_img)
+    assert util.rel_l2(g['d_params'], bwd['d_params']) <= 1e-5
+
+
+@needs_ref
+def test_reference_known_image_sums():
+    """SURVEY 8c known answers captured from the reference's CPU build (256^2, 2x2 spp, seed 0)."""
+    def s(scene, **kw):
+        topo, params = util.pack(scene, kw.pop('ft', 0), kw.pop('fr', 0.5))
+        return ref_oracle.render(topo, params, 256, 256, 2, 2, 0)['image']
+    img = s(scenes.single_circle())
+    assert abs(img.astype(np.float64).sum() - 11052.250240) < 1e-3
+    assert np.allclose(img[128, 128], [.3, .6, .3, 1.0], atol=1e-6)
+    with pytest.warns(Warning):
+        img = s(scenes.single_stroke())
+    assert abs(img.astype(np.float64).sum() - 4938.100155) < 1e-3
+    img = s(scenes.single_stroke([10., 5., 4., 20.], fill=False))
+    assert abs(img.astype(np.float64).sum() - 10697.300335) < 1e-3
+    assert np.allclose(img[60, 135], [.6, .3, .6, .8], atol=1e-6)
+
+
+@needs_ref
+def test_reference_bvh_cdf_known_answers():
+    """SURVEY 8c BVH / CDF KAT (3 open cubic stroke paths)."""
+    from diffvg_b200 import pydiffvg
+    P = [([[10, 10], [20, 40], [40, 20], [60, 60]], [2], 2.0),
+         ([[100, 20], [120, 30], [110, 60], [90, 80], [70, 100], [60, 120], [80, 140]], [2, 2], 1.5),
+         ([[200, 200], [180, 220], [220, 240], [240, 210]], [2], 3.0)]
+    shapes, groups = [], []
+    for i, (pts, ncp, w) in enumerate(P):
+        shapes.append(pydiffvg.Path(torch.tensor(ncp), torch.tensor(pts, dtype=torch.float32), False, torch.tensor(w)))
+        groups.append(pydiffvg.ShapeGroup(torch.tensor([i]), None, stroke_color=torch.tensor([0., 0., 0., 1.])))
+    topo, params = util.pack((256, 256, shapes, groups))
+    f = lambda w: w.view(np.float32)
+    lengths = f(ref_oracle.scene_dump(topo, params, 3))
+    assert np.allclose(lengths, [72.1463623, 137.820312, 67.0436325], rtol=1e-7)
+    assert np.allclose(f(ref_oracle.scene_dump(topo, params, 4)), [0.260446489, 0.757974207, 1.0], rtol=1e-7)
+    assert np.allclose(f(ref_oracle.scene_dump(topo, params, 5)), [0.260446489, 0.497527719, 0.242025763], rtol=1e-7)
+    assert np.allclose(f(ref_oracle.scene_dump(topo, params, 6, 1)), [0.50051403, 1.0], rtol=1e-7)
+    assert list(ref_oracle.scene_dump(topo, params, 8, 1).view(np.int32)) == [0, 3]
+    nodes = ref_oracle.scene_dump(topo, params, 0).reshape(-1, 7)
+    assert [tuple(n[:2].view(np.int32)) for n in nodes] == [(0, -1), (1, -1), (2, -1), (0, 1), (3, 2)]
+    assert np.allclose(nodes[4][2:].view(np.float32), [10, 10, 240, 240, 3])
+    pnodes = ref_oracle.scene_dump(topo, params, 2, 1).reshape(-1, 7)
+    assert [tuple(n[:2].view(np.int32)) for n in pnodes] == [(0, -1), (1, -4), (0, 1)]
+    # the product's host-compiled build functions produce the same tables, bit for bit
+    for what, idx in ((3, 0), (4, 0), (5, 0), (6, 1), (7, 1), (8, 1)):
+        assert np.array_equal(ref_oracle.scene_dump(topo, params, what, idx), emul.scene_dump(topo, params, what, idx))
+
+
+@pytest.mark.parametrize('path', GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_product_arithmetic_on_host_matches_golden(path):
+    """The product's predicate / tracer / boundary headers, compiled for the host
+    (tests/host_emul), against the reference's golden vectors.  Forward tolerance 1e-5 abs
+    (north_star); gradients per-tensor rel-L2 1e-4."""
+    g = np.load(path)
+    name = os.path.basename(path)[:-4]
+    W, H, nsx, nsy, seed, ft = [int(v) for v in g['config']]
+    from golden.make_golden import background_for, d_image_for
+    bg = background_for(name, H, W) if 'd_background' in g.files else None
+    img = emul.render(g['topo'], g['params'], W, H, nsx, nsy, seed, background=bg)['image']
+    assert np.abs(img - g['image']).max() <= 1e-5
+    bwd = emul.render(g['topo'], g['params'], W, H, nsx, nsy, seed, background=bg, d_render_image=d_image_for(name, H, W))
+    assert util.rel_l2(g['d_params'], bwd['d_params']) <= 1e-4
+    if bg is not None and nsx * nsy == 1:  # Q2: d_background is racy in the reference above 1 spp
+        assert np.abs(bwd['d_background'] - g['d_background']).max() <= 1e-5
+
+
+# ------------------------------------------------------------------ host logic: scene packing
+def test_pack_layout_and_semantics():
+    from diffvg_b200 import pydiffvg
+    cw, ch, shapes, groups = scenes.zoo()
+    topo, buckets = scene_pack.pack_scene(cw, ch, shapes, groups, 1, torch.tensor(1.5))
+    params = scene_pack.concat_params(buckets)
+    assert topo[scene_pack.H_MAGIC] == scene_pack.TOPO_MAGIC
+    assert topo[scene_pack.H_NS] == len(shapes) and topo[scene_pack.H_NG] == len(groups)
+    assert topo[scene_pack.H_NPARAMS] == params.numel()
+    assert params[topo[scene_pack.H_FRAD_OFF]].item() == 1.5
+    srec = topo[topo[scene_pack.H_OFF_SHAPES]:topo[scene_pack.H_OFF_GROUPS]].reshape(-1, scene_pack.S_LEN)
+    # shape 4: per-point thickness -> no scalar width, thickness offset set (render_pytorch.py:67-72, 95-98)
+    assert srec[4][0] == scene_pack.SHAPE_PATH and srec[4][2] == -1 and srec[4][3] >= 0
+    th = params[srec[4][3]:srec[4][3] + srec[4][4]]
+    assert torch.equal(th, shapes[4].stroke_width)
+    # shape 5: closed polygon of 4 points -> 4 line segments; shape 7: open polygon -> 3 (render_pytorch.py:75-86)
+    assert srec[5][5] == 4 and srec[7][5] == 3
+    ncp = topo[topo[scene_pack.H_OFF_NCP] + srec[5][6]: topo[scene_pack.H_OFF_NCP] + srec[5][6] + 4]
+    assert (ncp == 0).all()
+    pts = params[srec[3][1]:srec[3][1] + 2 * srec[3][4]].reshape(-1, 2)
+    assert torch.equal(pts, shapes[3].points)
+    grec = topo[topo[scene_pack.H_OFF_GROUPS]:topo[scene_pack.H_OFF_NCP]].reshape(-1, scene_pack.G_LEN)
+    assert grec[1][2] == scene_pack.COLOR_LINEAR and grec[1][4] == 3
+    assert grec[4][2] == scene_pack.COLOR_NONE and grec[4][5] == scene_pack.COLOR_CONSTANT
+    assert grec[5][1] == 2 and list(topo[topo[scene_pack.H_OFF_GSHAPES] + grec[5][0]:][:2]) == [5, 6]
+    xf = params[grec[2][9]:grec[2][9] + 9].reshape(3, 3)
+    assert torch.equal(xf, groups[2].shape_to_canvas)
+
+
+def test_pack_gradients_flow_to_user_tensors():
+    from diffvg_b200 import pydiffvg
+    pts = torch.rand(4, 2, requires_grad=True)
+    w = torch.tensor(2.0, requires_grad=True)
+    col = torch.rand(4, requires_grad=True)
+    shapes = [pydiffvg.Path(torch.tensor([2]), pts, False, w)]
+    groups = [pydiffvg.ShapeGroup(torch.tensor([0]), None, stroke_color=col)]
+    topo, buckets = scene_pack.pack_scene(64, 64, shapes, groups)
+    params = scene_pack.concat_params(buckets)
+    g = torch.arange(params.numel(), dtype=torch.float32)
+    params.backward(g)
+    srec = topo[topo[scene_pack.H_OFF_SHAPES]:][:scene_pack.S_LEN]
+    assert torch.equal(pts.grad.reshape(-1), g[srec[1]:srec[1] + 8])
+    assert w.grad.item() == g[srec[2]].item()
+    grec = topo[topo[scene_pack.H_OFF_GROUPS]:][:scene_pack.G_LEN]
+    assert torch.equal(col.grad, g[grec[6]:grec[6] + 4])
+
+
+def test_shared_transform_is_stored_once():
+    cw, ch, shapes, groups = scenes.painterly(8, 64)
+    eye = torch.eye(3)
+    for g in groups:
+        g.shape_to_canvas = eye
+    topo, buckets = scene_pack.pack_scene(cw, ch, shapes, groups)
+    assert len(buckets[scene_pack.B_MAT3]) == 1
+    grec = topo[topo[scene_pack.H_OFF_GROUPS]:topo[scene_pack.H_OFF_NCP]].reshape(-1, scene_pack.G_LEN)
+    assert len(set(grec[:, 9])) == 1
+
+
+def test_pack_rejects_bad_input():
+    from diffvg_b200 import pydiffvg
+    c = pydiffvg.Circle(torch.tensor(3.0), torch.tensor([1.0, 2.0]))
+    with pytest.raises(ValueError):
+        scene_pack.pack_scene(8, 8, [c], [pydiffvg.ShapeGroup(torch.tensor([1]), torch.rand(4))])
+    with pytest.raises(ValueError):
+        scene_pack.pack_scene(8, 8, [c], [pydiffvg.ShapeGroup(torch.tensor([0]), torch.rand(3))])
+
+
+# ------------------------------------------------------------------ C ABI surface
+def _declared_functions():
+    text = open(os.path.join(ROOT, 'include', 'diffvg_b200.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(dvg_[a-z_0-9]+)\s*\(', text)))
+
+
+def test_c_abi_library_exports_every_declared_symbol():
+    lib_path = os.path.join(ROOT, 'diffvg_b200', 'libdiffvg_b200.so')
+    if not os.path.exists(lib_path):
+        import __graft_entry__
+        __graft_entry__.build_library()
+    lib = ctypes.CDLL(lib_path)
+    names = _declared_functions()
+    assert len(names) >= 10
+    for n in names:
+        assert hasattr(lib, n), 'missing export: ' + n
+    lib.dvg_abi_version.restype = ctypes.c_int
+    assert lib.dvg_abi_version() >= 1
+
+
+def test_c_abi_rejects_malformed_topology_without_a_gpu():
+    """Argument validation happens before any CUDA call, so it is testable on a CPU-only host."""
+    from diffvg_b200 import _native as n
+    h = ctypes.c_void_p()
+    bad = np.zeros(4, np.int32)
+    assert n.lib.dvg_scene_create(bad.ctypes.data, bad.shape[0], 0, ctypes.byref(h)) == 1
+    assert b'header' in n.lib.dvg_last_error()
+    topo, _ = util.pack(scenes.single_circle())
+    topo = topo.copy()
+    topo[scene_pack.H_MAGIC] = 0
+    assert n.lib.dvg_scene_create(topo.ctypes.data, topo.shape[0], 0, ctypes.byref(h)) == 1
+    from diffvg_b200 import pydiffvg
+    e = pydiffvg.Ellipse(torch.tensor([3.0, 2.0]), torch.tensor([1.0, 2.0]), stroke_width=torch.tensor(1.0))
+    topo, _ = util.pack((8, 8, [e], [pydiffvg.ShapeGroup(torch.tensor([0]), None, stroke_color=torch.rand(4))]))
+    assert n.lib.dvg_scene_create(topo.ctypes.data, topo.shape[0], 0, ctypes.byref(h)) == n.DVG_ERR_UNSUPPORTED
+
+
+def test_product_fails_loudly_without_cuda():
+    from diffvg_b200 import pydiffvg
+    if torch.cuda.is_available():
+        pytest.skip('CUDA present')
+    cw, ch, shapes, groups = scenes.single_circle()
+    args = pydiffvg.RenderFunction.serialize_scene(cw, ch, shapes, groups)
+    with pytest.raises(RuntimeError):
+        pydiffvg.RenderFunction.apply(16, 16, 1, 1, 0, None, *args)
