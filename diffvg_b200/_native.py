@@ -6,7 +6,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libdiffvg_b200.so')
+LIB_PATH = os.environ.get('DVG_B200_LIB') or os.path.join(_HERE, 'libdiffvg_b200.so')  # env override: A/B builds
 
 if not os.path.exists(LIB_PATH):
     raise ImportError('diffvg_b200: %s is missing. Build it with `python -c "import __graft_entry__ as g; g.build()"` '

@@ -283,10 +283,10 @@ DVG_HD F4 gather_d_color(const Filter &f, const float *d_img, const float *wimg,
 
 
 // accumulate_boundary_gradient (diffvg.cpp:89-274), scattering into the flat d_params.
+template <typename Sink>
 DVG_D void accumulate_boundary_gradient(const SceneView &sc, const RenderArgs &ra, const BoundarySample &bs,
-                                        const InstInfo &ii, const GroupInfo &g, float contrib, F2 normal) {
+                                        const InstInfo &ii, const GroupInfo &g, float contrib, F2 normal, const Sink &sk) {
     const int *srec = sc.topo + sc.topo[DVG_H_OFF_SHAPES] + ii.shape * DVG_SHAPE_REC_LEN;
-    float *D = ra.d_params;
     const bool is_stroke = bs.point_id_stroke < 0;
     const int point_id = bs.point_id_stroke & 0x7fffffff;
     const int type = srec[DVG_S_TYPE];
@@ -312,51 +312,53 @@ DVG_D void accumulate_boundary_gradient(const SceneView &sc, const RenderArgs &r
     if (is_stroke) {
         const int toff = type == DVG_SHAPE_PATH ? srec[DVG_S_THICK_OFF] : -1;
         if (toff >= 0) {  // diffvg.cpp:110-144
-            DVG_ATOMIC_ADD(D + toff + i0, w0 * contrib);
-            DVG_ATOMIC_ADD(D + toff + i1, w1 * contrib);
-            if (nw > 2) DVG_ATOMIC_ADD(D + toff + i2, w2 * contrib);
-            if (nw > 3) DVG_ATOMIC_ADD(D + toff + i3, w3 * contrib);
+            sk.add(toff + i0, w0 * contrib);
+            sk.add(toff + i1, w1 * contrib);
+            if (nw > 2) sk.add(toff + i2, w2 * contrib);
+            if (nw > 3) sk.add(toff + i3, w3 * contrib);
         } else if (srec[DVG_S_WIDTH_OFF] >= 0) {
-            DVG_ATOMIC_ADD(D + srec[DVG_S_WIDTH_OFF], contrib);
+            sk.add(srec[DVG_S_WIDTH_OFF], contrib);
         }
     }
     switch (type) {
         case DVG_SHAPE_CIRCLE:
-            DVG_ATOMIC_ADD(D + poff + 1, normal.x * contrib);
-            DVG_ATOMIC_ADD(D + poff + 2, normal.y * contrib);
-            DVG_ATOMIC_ADD(D + poff + 0, contrib);
+            sk.add(poff + 1, normal.x * contrib);
+            sk.add(poff + 2, normal.y * contrib);
+            sk.add(poff + 0, contrib);
             break;
         case DVG_SHAPE_ELLIPSE: {
-            DVG_ATOMIC_ADD(D + poff + 2, normal.x * contrib);
-            DVG_ATOMIC_ADD(D + poff + 3, normal.y * contrib);
+            sk.add(poff + 2, normal.x * contrib);
+            sk.add(poff + 3, normal.y * contrib);
             // the reference uses the UN-remapped random number t here (diffvg.cpp:166-167, 1373)
             const float arg = 2 * (float)DVG_PI_D * bs.t;
-            DVG_ATOMIC_ADD(D + poff + 0, cosf(arg) * normal.x * contrib);
-            DVG_ATOMIC_ADD(D + poff + 1, sinf(arg) * normal.y * contrib);
+            sk.add(poff + 0, cosf(arg) * normal.x * contrib);
+            sk.add(poff + 1, sinf(arg) * normal.y * contrib);
             break;
         }
         case DVG_SHAPE_PATH: {
             const float nx = normal.x, ny = normal.y;
-            DVG_ATOMIC_ADD(D + poff + 2 * i0 + 0, w0 * nx * contrib); DVG_ATOMIC_ADD(D + poff + 2 * i0 + 1, w0 * ny * contrib);
-            DVG_ATOMIC_ADD(D + poff + 2 * i1 + 0, w1 * nx * contrib); DVG_ATOMIC_ADD(D + poff + 2 * i1 + 1, w1 * ny * contrib);
-            if (nw > 2) { DVG_ATOMIC_ADD(D + poff + 2 * i2 + 0, w2 * nx * contrib); DVG_ATOMIC_ADD(D + poff + 2 * i2 + 1, w2 * ny * contrib); }
-            if (nw > 3) { DVG_ATOMIC_ADD(D + poff + 2 * i3 + 0, w3 * nx * contrib); DVG_ATOMIC_ADD(D + poff + 2 * i3 + 1, w3 * ny * contrib); }
+            sk.add(poff + 2 * i0 + 0, w0 * nx * contrib); sk.add(poff + 2 * i0 + 1, w0 * ny * contrib);
+            sk.add(poff + 2 * i1 + 0, w1 * nx * contrib); sk.add(poff + 2 * i1 + 1, w1 * ny * contrib);
+            if (nw > 2) { sk.add(poff + 2 * i2 + 0, w2 * nx * contrib); sk.add(poff + 2 * i2 + 1, w2 * ny * contrib); }
+            if (nw > 3) { sk.add(poff + 2 * i3 + 0, w3 * nx * contrib); sk.add(poff + 2 * i3 + 1, w3 * ny * contrib); }
             break;
         }
         default: {  // rect (diffvg.cpp:232-255): exact normal compare in LOCAL orientation
-            if (normal.x == -1.f && normal.y == 0.f) DVG_ATOMIC_ADD(D + poff + 0, -contrib);
-            else if (normal.x == 1.f && normal.y == 0.f) DVG_ATOMIC_ADD(D + poff + 2, contrib);
-            else if (normal.x == 0.f && normal.y == -1.f) DVG_ATOMIC_ADD(D + poff + 1, -contrib);
-            else if (normal.x == 0.f && normal.y == 1.f) DVG_ATOMIC_ADD(D + poff + 3, contrib);
+            if (normal.x == -1.f && normal.y == 0.f) sk.add(poff + 0, -contrib);
+            else if (normal.x == 1.f && normal.y == 0.f) sk.add(poff + 2, contrib);
+            else if (normal.x == 0.f && normal.y == -1.f) sk.add(poff + 1, -contrib);
+            else if (normal.x == 0.f && normal.y == 1.f) sk.add(poff + 3, contrib);
             break;
         }
     }
-    if (!(ra.flags & 1u)) {  // DVG_BWD_SKIP_XFORM_GRAD
-        float dm[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-        F2 dpt = mk2(0, 0);
-        d_xform_pt(g.s2c, bs.local_pt, mk2(normal.x * contrib, normal.y * contrib), dm, dpt);
-        for (int k = 0; k < 9; k++) if (dm[k] != 0.f) DVG_ATOMIC_ADD(D + g.xform_off + k, dm[k]);
-    }
+}
+
+// d_xform_pt part of accumulate_boundary_gradient (diffvg.cpp:256-273): the 9 terms for
+// d_shape_to_canvas.  Kept separate so that the kernel can reduce them across the warp first
+// (groups very often share one transform, so all lanes target the same 9 floats).
+DVG_HD void boundary_xform_gradient(const BoundarySample &bs, const GroupInfo &g, float contrib, F2 normal, float dm[9]) {
+    F2 dpt = mk2(0, 0);
+    d_xform_pt(g.s2c, bs.local_pt, mk2(normal.x * contrib, normal.y * contrib), dm, dpt);
 }
 
 }  // namespace dvg

@@ -54,9 +54,11 @@ __global__ void k_bin(BuildView bv, BinBuild bb) {
     // offsets of boundary samples (diffvg.cpp:1416,1420) and float rounding of pt/W*canvas_w
     const float cw = (float)bv.canvas_w, ch = (float)bv.canvas_h;
     const float margin = 4e-4f * (cw > ch ? cw : ch) + 1e-4f;
-    const float x0 = ((float)(tx * bb.tile_w) / (float)bb.width) * cw - margin;
+    // int(-0.9) == 0: the reference attributes boundary samples lying up to one pixel left of /
+    // above the image to pixel column / row 0 (diffvg.cpp:1405-1409), so border tiles reach out 1 px
+    const float x0 = ((float)(tx * bb.tile_w - (tx == 0 ? 1 : 0)) / (float)bb.width) * cw - margin;
     const float x1 = ((float)((tx + 1) * bb.tile_w) / (float)bb.width) * cw + margin;
-    const float y0 = ((float)(ty * bb.tile_h) / (float)bb.height) * ch - margin;
+    const float y0 = ((float)(ty * bb.tile_h - (ty == 0 ? 1 : 0)) / (float)bb.height) * ch - margin;
     const float y1 = ((float)((ty + 1) * bb.tile_h) / (float)bb.height) * ch + margin;
     int count = 0;
     int *out = nullptr;

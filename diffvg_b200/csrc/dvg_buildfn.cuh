@@ -22,7 +22,7 @@ struct BuildView {
     float *seg_cdf, *seg_pmf; int *seg_point_id;
     // per instance / group / primitive
     InstInfo *insts; GroupInfo *groups;
-    F4 *prim_p01, *prim_p23, *prim_rad; Box *prim_box; float *prim_thick; PrimMeta *prim_meta; Box *prim_cbox;
+    F4 *prim_p01, *prim_p23, *prim_rad; Box *prim_box; float *prim_thick; PrimMeta *prim_meta; Box *prim_cbox; F4 *prim_cap;
     float *shape_cdf, *shape_pmf;
     int *error_flag; float *total_length;
 };
@@ -184,6 +184,56 @@ DVG_HD_NOINLINE void build_group(const BuildView &bv, int g) {
     bv.groups[g] = gi;
 }
 
+// ------------------------------------------------------------------ reject capsules
+DVG_HD float seg_dist(F2 a, F2 d, float inv_len2, F2 p) {
+    F2 w = p - a;
+    float t = clampf(dot2(w, d) * inv_len2, 0.f, 1.f);
+    F2 e = w - t * d;
+    return sqrtf(dot2(e, e));
+}
+DVG_HD void cap_piece(F2 q0, F2 q1, F2 q2, F2 q3, float rmax, float *out) {
+    F2 d = q3 - q0;
+    float len2 = dot2(d, d);
+    float inv = len2 > 1e-12f ? 1.f / len2 : 0.f;
+    if (inv == 0.f) d = mk2(0, 0);
+    float dev = rmaxf(seg_dist(q0, d, inv, q1), seg_dist(q0, d, inv, q2));
+    // margin: float rounding of the de Casteljau split, of eval_cubic in the exact test and of this
+    // test itself are all < 1e-4 px at canvas scales; 1e-2 px + 1e-4 relative is far above that
+    float R = (dev + rmax) * 1.0001f + 1e-2f;
+    out[0] = q0.x; out[1] = q0.y; out[2] = d.x; out[3] = d.y; out[4] = inv; out[5] = R * R;
+}
+DVG_HD void cap_split(F2 p0, F2 p1, F2 p2, F2 p3, F2 *l, F2 *r) {  // de Casteljau at 1/2
+    F2 a = 0.5f * (p0 + p1), b = 0.5f * (p1 + p2), c = 0.5f * (p2 + p3);
+    F2 ab = 0.5f * (a + b), bc = 0.5f * (b + c);
+    F2 m = 0.5f * (ab + bc);
+    l[0] = p0; l[1] = a; l[2] = ab; l[3] = m;
+    r[0] = m; r[1] = bc; r[2] = c; r[3] = p3;
+}
+// type: PRIM_QUAD / PRIM_CUBIC get real capsules; everything else a never-reject record.
+DVG_HD void build_capsules(int type, F4 p01, F4 p23, float rmax, float *out) {
+    bool ok = (type == PRIM_QUAD || type == PRIM_CUBIC) && rmax == rmax;
+    F2 c[4];
+    c[0] = mk2(p01.x, p01.y);
+    if (type == PRIM_CUBIC) { c[1] = mk2(p01.z, p01.w); c[2] = mk2(p23.x, p23.y); c[3] = mk2(p23.z, p23.w); }
+    else {  // degree elevation of the quadratic
+        F2 q1 = mk2(p01.z, p01.w), q2 = mk2(p23.x, p23.y);
+        c[1] = c[0] + (2.f / 3.f) * (q1 - c[0]); c[2] = q2 + (2.f / 3.f) * (q1 - q2); c[3] = q2;
+    }
+    for (int k = 0; k < 4; k++) ok = ok && fabsf(c[k].x) < 1e18f && fabsf(c[k].y) < 1e18f;   // finite, no overflow below
+    if (!ok) {
+        for (int i = 0; i < DVG_CAP_N; i++) { float *o = out + 6 * i; o[0] = o[1] = o[2] = o[3] = o[4] = 0.f; o[5] = INFINITY; }
+        return;
+    }
+    F2 l[4], r[4], ll[4], lr[4], rl[4], rr[4];
+    cap_split(c[0], c[1], c[2], c[3], l, r);
+    cap_split(l[0], l[1], l[2], l[3], ll, lr);
+    cap_split(r[0], r[1], r[2], r[3], rl, rr);
+    cap_piece(ll[0], ll[1], ll[2], ll[3], rmax, out + 0);
+    cap_piece(lr[0], lr[1], lr[2], lr[3], rmax, out + 6);
+    cap_piece(rl[0], rl[1], rl[2], rl[3], rmax, out + 12);
+    cap_piece(rr[0], rr[1], rr[2], rr[3], rmax, out + 18);
+}
+
 // ------------------------------------------------------------------ primitives
 // Leaf boxes and radii follow scene.cpp:527-600 (topology-only maps prim -> inst / segment /
 // first point come from the host).
@@ -259,6 +309,11 @@ DVG_HD_NOINLINE void build_prim(const BuildView &bv, int e) {
     pm.type_flags = tf;
     bv.prim_p01[e] = p01; bv.prim_p23[e] = p23; bv.prim_rad[e] = rad;
     bv.prim_box[e] = box; bv.prim_thick[e] = thick; bv.prim_meta[e] = pm;
+    {
+        float cap[DVG_CAP_N * 6];
+        build_capsules(has_stroke ? (tf & DVG_PF_TYPE_MASK) : -1, p01, p23, thick, cap);
+        for (int k = 0; k < DVG_CAP_F4; k++) bv.prim_cap[(size_t)e * DVG_CAP_F4 + k] = mk4(cap[4 * k], cap[4 * k + 1], cap[4 * k + 2], cap[4 * k + 3]);
+    }
     if (first_in_inst) {
         InstInfo ii;
         ii.box = bv.shape_box[s];

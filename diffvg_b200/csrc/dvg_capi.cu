@@ -19,6 +19,7 @@ using namespace dvg;
 namespace {
 
 thread_local std::string g_err;
+float *g_debug_out = nullptr;  // dvg_debug_set_boundary_dump
 
 int fail(int code, const std::string &msg) {
     g_err = msg;
@@ -69,7 +70,7 @@ struct DvgScene {
     DevBuf d_topo, d_inst_group, d_inst_shape, d_inst_prim_begin, d_prim_inst, d_prim_seg, d_prim_point_id;
     // device: parameters + derived tables
     DevBuf d_params, d_shapes_length, d_shape_box, d_shape_r0, d_seg_cdf, d_seg_pmf, d_seg_point_id;
-    DevBuf d_insts, d_groups, d_p01, d_p23, d_rad, d_box, d_thick, d_meta, d_cbox, d_shape_cdf, d_shape_pmf;
+    DevBuf d_insts, d_groups, d_p01, d_p23, d_rad, d_box, d_thick, d_meta, d_cbox, d_cap, d_shape_cdf, d_shape_pmf;
     DevBuf d_flags;  // [0] error flag, [1] total length (float bits)
     // bins
     DevBuf d_bin_counts, d_bin_offsets, d_bin_items;
@@ -100,7 +101,7 @@ struct DvgScene {
         bv.insts = d_insts.as<InstInfo>(); bv.groups = d_groups.as<GroupInfo>();
         bv.prim_p01 = d_p01.as<F4>(); bv.prim_p23 = d_p23.as<F4>(); bv.prim_rad = d_rad.as<F4>();
         bv.prim_box = d_box.as<Box>(); bv.prim_thick = d_thick.as<float>(); bv.prim_meta = d_meta.as<PrimMeta>();
-        bv.prim_cbox = d_cbox.as<Box>();
+        bv.prim_cbox = d_cbox.as<Box>(); bv.prim_cap = d_cap.as<F4>();
         bv.shape_cdf = d_shape_cdf.as<float>(); bv.shape_pmf = d_shape_pmf.as<float>();
         bv.error_flag = d_flags.as<int>(); bv.total_length = d_flags.as<float>() + 1;
         return bv;
@@ -115,7 +116,7 @@ struct DvgScene {
         sc.topo = d_topo.as<int>(); sc.params = d_params.as<float>();
         sc.prim_p01 = d_p01.as<F4>(); sc.prim_p23 = d_p23.as<F4>(); sc.prim_rad = d_rad.as<F4>();
         sc.prim_box = d_box.as<Box>(); sc.prim_thick = d_thick.as<float>(); sc.prim_meta = d_meta.as<PrimMeta>();
-        sc.prim_cbox = d_cbox.as<Box>();
+        sc.prim_cbox = d_cbox.as<Box>(); sc.prim_cap = d_cap.as<F4>();
         sc.insts = d_insts.as<InstInfo>(); sc.groups = d_groups.as<GroupInfo>();
         sc.shapes_length = d_shapes_length.as<float>();
         sc.shape_cdf = d_shape_cdf.as<float>(); sc.shape_pmf = d_shape_pmf.as<float>();
@@ -133,7 +134,7 @@ struct DvgScene {
     void release_all() {
         DevBuf *all[] = {&d_topo, &d_inst_group, &d_inst_shape, &d_inst_prim_begin, &d_prim_inst, &d_prim_seg,
                          &d_prim_point_id, &d_params, &d_shapes_length, &d_shape_box, &d_shape_r0, &d_seg_cdf, &d_seg_pmf,
-                         &d_seg_point_id, &d_insts, &d_groups, &d_p01, &d_p23, &d_rad, &d_box, &d_thick, &d_meta, &d_cbox,
+                         &d_seg_point_id, &d_insts, &d_groups, &d_p01, &d_p23, &d_rad, &d_box, &d_thick, &d_meta, &d_cbox, &d_cap,
                          &d_shape_cdf, &d_shape_pmf, &d_flags, &d_bin_counts, &d_bin_offsets, &d_bin_items, &d_weight,
                          &d_keys, &d_tile_counts, &d_tile_offsets, &d_tile_fill, &d_blk_counts, &d_blk_offsets, &d_sorted};
         for (DevBuf *b : all) b->release();
@@ -373,7 +374,7 @@ int dvg_scene_create(const int32_t *topo, int64_t topo_len, int device, DvgScene
     ens(s->d_seg_cdf, 4 * nsg); ens(s->d_seg_pmf, 4 * nsg); ens(s->d_seg_point_id, 4 * nsg);
     ens(s->d_insts, sizeof(InstInfo) * ni); ens(s->d_groups, sizeof(GroupInfo) * ng);
     ens(s->d_p01, 16 * npr); ens(s->d_p23, 16 * npr); ens(s->d_rad, 16 * npr); ens(s->d_box, 16 * npr);
-    ens(s->d_thick, 4 * npr); ens(s->d_meta, sizeof(PrimMeta) * npr); ens(s->d_cbox, 16 * npr);
+    ens(s->d_thick, 4 * npr); ens(s->d_meta, sizeof(PrimMeta) * npr); ens(s->d_cbox, 16 * npr); ens(s->d_cap, 16 * DVG_CAP_F4 * npr);
     ens(s->d_shape_cdf, 4 * ni); ens(s->d_shape_pmf, 4 * ni); ens(s->d_flags, 16);
     if (!rc && cudaMallocHost((void **)&s->h_pinned, 64) != cudaSuccess) rc = fail(DVG_ERR_CUDA, "cudaMallocHost failed");
     if (rc) { s->release_all(); delete s; return rc; }
@@ -476,6 +477,7 @@ int dvg_render_backward_rows(DvgScene *s, const float *background, const float *
     ra.flags = flags;
     ra.background = background; ra.d_render_image = d_render_image;
     ra.d_params = d_params; ra.d_background = d_background;
+    ra.debug_out = g_debug_out;
     rc = ensure_weight(s, sc, ra, st);
     if (rc) return rc;
     if (!(flags & DVG_BWD_ACCUMULATE)) CK(cudaMemsetAsync(d_params, 0, sizeof(float) * s->num_params, st));
@@ -518,6 +520,8 @@ int dvg_render_backward(DvgScene *s, const float *background, const float *d_ren
     return dvg_render_backward_rows(s, background, d_render_image, width, height, nsx, nsy, seed, use_prefiltering,
                                     0, height, d_params, d_background, flags, stream);
 }
+
+int dvg_debug_set_boundary_dump(float *device_buf) { g_debug_out = device_buf; return DVG_OK; }
 
 int dvg_profile_enable(int on) {
     dvg::g_profile_on = on != 0;

@@ -11,6 +11,53 @@ namespace dvg {
 #define DVG_ATOMIC_ADD(ptr, v) (*(ptr) += (v))
 #endif
 
+// ---------------------------------------------------------------- gradient sinks
+// The reference scatters every per-sample gradient term with one global float atomic
+// (atomic.h:23-51): ~23 per pixel sample onto ~57 k addresses at the painterly config, and ALL
+// samples onto the same 9 floats when the groups share one shape_to_canvas.  Here terms go to a
+// per-block open-addressed table in shared memory keyed by the parameter index (shared-memory
+// atomics), and the block issues ONE global reduction per distinct parameter it touched.
+// A full table (probe limit) falls back to the global atomic, so the result never depends on it.
+struct DirectSink {   // host harness / fallback: straight into d_params
+    float *D;
+    DVG_HD void add(int idx, float v) const { DVG_ATOMIC_ADD(D + idx, v); }
+};
+
+#if defined(__CUDACC__)
+constexpr int DVG_GC_SLOTS = 1024;  // power of two
+struct GradCache {
+    int keys[DVG_GC_SLOTS];
+    float vals[DVG_GC_SLOTS];
+};
+struct CacheSink {
+    GradCache *gc;
+    float *D;
+    __device__ __forceinline__ void add(int idx, float v) const {
+        if (v == 0.f) return;
+        unsigned h = ((unsigned)idx * 2654435761u) >> 22;  // top 10 bits
+#pragma unroll 1
+        for (int probe = 0; probe < 16; probe++) {
+            int k = gc->keys[h];
+            if (k == -1) k = atomicCAS(&gc->keys[h], -1, idx);
+            if (k == -1 || k == idx) { atomicAdd(&gc->vals[h], v); return; }
+            h = (h + 1) & (DVG_GC_SLOTS - 1);
+        }
+        atomicAdd(D + idx, v);
+    }
+};
+__device__ __forceinline__ void grad_cache_init(GradCache &gc) {
+    for (int i = threadIdx.x; i < DVG_GC_SLOTS; i += blockDim.x) { gc.keys[i] = -1; gc.vals[i] = 0.f; }
+}
+// call after a __syncthreads() that orders all adds before it
+__device__ __forceinline__ void grad_cache_flush(GradCache &gc, float *D) {
+    for (int i = threadIdx.x; i < DVG_GC_SLOTS; i += blockDim.x) {
+        const int k = gc.keys[i];
+        const float v = gc.vals[i];
+        if (k >= 0 && v != 0.f) atomicAdd(D + k, v);
+    }
+}
+#endif
+
 // Gradient parameter t for a linear / radial gradient record at params[off..].
 DVG_HD float gradient_t(int type, const float *c, F2 pt) {
     if (type == 1) {  // diffvg.cpp:288-290
@@ -43,21 +90,23 @@ DVG_HD F4 eval_color(int type, const float *c, int num_stops, F2 pt) {
     return load4(colors + 4 * (num_stops - 1));
 }
 
-DVG_D void add4(float *d, F4 v) {
-    DVG_ATOMIC_ADD(d + 0, v.x); DVG_ATOMIC_ADD(d + 1, v.y); DVG_ATOMIC_ADD(d + 2, v.z); DVG_ATOMIC_ADD(d + 3, v.w);
+template <typename Sink>
+DVG_D void add4(const Sink &sk, int d, F4 v) {
+    sk.add(d + 0, v.x); sk.add(d + 1, v.y); sk.add(d + 2, v.z); sk.add(d + 3, v.w);
 }
 
 // diffvg.cpp:370-504 for the two gradient types (the constant case is reduced by the
 // caller).  `d` points at the record's slot in d_params.  d_translation: 2 floats or null.
 // Q3: the radial branch has no `return` after the matched stop, so d_color is also
 // added to the last stop; reproduced.
-DVG_D void d_eval_gradient(int type, const float *c, int num_stops, F2 pt, F4 d_color, float *d, float *d_translation) {
+template <typename Sink>
+DVG_D void d_eval_gradient(int type, const float *c, int num_stops, F2 pt, F4 d_color, const Sink &sk, int d, float *d_translation) {
     float t = gradient_t(type, c, pt);
     const float *offsets = c + 4;
     const float *colors = c + 4 + num_stops;
-    float *d_offsets = d + 4;
-    float *d_colors = d + 4 + num_stops;
-    if (t < offsets[0]) { add4(d_colors, d_color); return; }
+    const int d_offsets = d + 4;
+    const int d_colors = d + 4 + num_stops;
+    if (t < offsets[0]) { add4(sk, d_colors, d_color); return; }
     for (int i = 0; i < num_stops - 1; i++) {
         float oc = offsets[i], on = offsets[i + 1];
         if (t >= oc && t < on) {
@@ -68,10 +117,10 @@ DVG_D void d_eval_gradient(int type, const float *c, int num_stops, F2 pt, F4 d_
             float d_on = -d_tt * tt / (on - oc);
             float d_oc = d_tt * ((tt - 1.f) / (on - oc));
             float d_t = d_tt / (on - oc);
-            add4(d_colors + 4 * i, d_cc);
-            add4(d_colors + 4 * (i + 1), d_cn);
-            DVG_ATOMIC_ADD(d_offsets + i, d_oc);
-            DVG_ATOMIC_ADD(d_offsets + i + 1, d_on);
+            add4(sk, d_colors + 4 * i, d_cc);
+            add4(sk, d_colors + 4 * (i + 1), d_cn);
+            sk.add(d_offsets + i, d_oc);
+            sk.add(d_offsets + i + 1, d_on);
             if (type == 1) {
                 F2 beg = mk2(c[0], c[1]), end = mk2(c[2], c[3]);
                 float l = rmaxf(dot2(end - beg, end - beg), 1e-3f);
@@ -82,8 +131,8 @@ DVG_D void d_eval_gradient(int type, const float *c, int num_stops, F2 pt, F4 d_
                     d_beg = d_beg + (2 * d_l) * (beg - end);
                     d_end = d_end + (2 * d_l) * (end - beg);
                 }
-                DVG_ATOMIC_ADD(d + 0, d_beg.x); DVG_ATOMIC_ADD(d + 1, d_beg.y);
-                DVG_ATOMIC_ADD(d + 2, d_end.x); DVG_ATOMIC_ADD(d + 3, d_end.y);
+                sk.add(d + 0, d_beg.x); sk.add(d + 1, d_beg.y);
+                sk.add(d + 2, d_end.x); sk.add(d + 3, d_end.y);
                 if (d_translation) {
                     DVG_ATOMIC_ADD(d_translation + 0, d_beg.x + d_end.x);
                     DVG_ATOMIC_ADD(d_translation + 1, d_beg.y + d_end.y);
@@ -101,8 +150,8 @@ DVG_D void d_eval_gradient(int type, const float *c, int num_stops, F2 pt, F4 d_
                 F2 d_offset = mk2(d_no.x / radius.x, d_no.y / radius.y);
                 F2 d_radius = mk2(-d_no.x * offset.x / (radius.x * radius.x), -d_no.y * offset.y / (radius.y * radius.y));
                 F2 d_center = -d_offset;
-                DVG_ATOMIC_ADD(d + 0, d_center.x); DVG_ATOMIC_ADD(d + 1, d_center.y);
-                DVG_ATOMIC_ADD(d + 2, d_radius.x); DVG_ATOMIC_ADD(d + 3, d_radius.y);
+                sk.add(d + 0, d_center.x); sk.add(d + 1, d_center.y);
+                sk.add(d + 2, d_radius.x); sk.add(d + 3, d_radius.y);
                 if (d_translation) {
                     DVG_ATOMIC_ADD(d_translation + 0, d_center.x);
                     DVG_ATOMIC_ADD(d_translation + 1, d_center.y);
@@ -111,7 +160,7 @@ DVG_D void d_eval_gradient(int type, const float *c, int num_stops, F2 pt, F4 d_
             }
         }
     }
-    add4(d_colors + 4 * (num_stops - 1), d_color);
+    add4(sk, d_colors + 4 * (num_stops - 1), d_color);
 }
 
 }  // namespace dvg

@@ -55,16 +55,31 @@ DVG_HD Quintic cubic_quintic(F2 p0, F2 p1, F2 p2, F2 p3, F2 pt) {
     q.B = B / A; q.C = C / A; q.D = D / A; q.E = E / A; q.F = F / A;
     return q;
 }
+// within_distance.h:211-225 evaluate the monic quintic and its derivative term by term in double
+// (19 + 17 rounded operations).  Here: Horner with fused multiply-adds (5 + 4 DFMA).  The two
+// differ by ~1e-16 relative, and every consumer rounds to float (the Newton iterate) or compares
+// against 1e-5 / 0, so the float iterates -- and hence the classification -- are identical except
+// when a double lands within ~1e-9 relative of a float rounding boundary (DESIGN.md "arithmetic
+// contract"; checked bit-for-bit against the reference on the full-size configs).
+#ifdef DVG_FMA_QUINTIC
+DVG_HD double quintic_eval(const Quintic &q, double t) {
+    return fma(fma(fma(fma(t + q.B, t, q.C), t, q.D), t, q.E), t, q.F);
+}
+DVG_HD double quintic_deriv(const Quintic &q, double t) {
+    return fma(fma(fma(fma(5.0, t, 4.0 * q.B), t, 3.0 * q.C), t, 2.0 * q.D), t, q.E);
+}
+#else
 DVG_HD double quintic_eval(const Quintic &q, double t) {  // within_distance.h:211-218
     return t * t * t * t * t + q.B * t * t * t * t + q.C * t * t * t + q.D * t * t + q.E * t + q.F;
 }
 DVG_HD double quintic_deriv(const Quintic &q, double t) {  // within_distance.h:219-225
     return 5 * t * t * t * t + 4 * q.B * t * t * t + 3 * q.C * t * t + 2 * q.D * t + q.E;
 }
+#endif
 // Isolator-polynomial split points (within_distance.h:184-210).  Returns the sorted interval
 // ends.  Q10: when q_root is outside [0,1] the reference reads intervals[0]
 // uninitialised; we then use -1 ("no split point": negative entries are skipped).
-DVG_HD int quintic_intervals(const Quintic &q, float intervals[4]) {
+DVG_HD int quintic_intervals(const Quintic &q, float intervals[4], float stale0 = -1.f) {
     double p1A = ((2 / 5.f) * q.C - (4 / 25.f) * q.B * q.B);
     double p1B = ((3 / 5.f) * q.D - (3 / 25.f) * q.B * q.C);
     double p1C = ((4 / 5.f) * q.E - (2 / 25.f) * q.B * q.D);
@@ -72,7 +87,7 @@ DVG_HD int quintic_intervals(const Quintic &q, float intervals[4]) {
     double q_root = -q.B / 5.f;
     double p_roots[3];
     int num_sol = solve_cubic_d(p1A, p1B, p1C, p1D, p_roots);
-    intervals[0] = -1.f;
+    intervals[0] = stale0;
     if (q_root >= 0 && q_root <= 1) intervals[0] = (float)q_root;
     for (int j = 0; j < num_sol; j++) intervals[j + 1] = (float)p_roots[j];
     int n = 1 + num_sol;
@@ -105,12 +120,12 @@ DVG_HD bool quintic_root_in(const Quintic &q, float lower, float upper, float *t
 }
 
 // within_distance.h:119-272 (cubic leaf).  r[] = radius at the four control points.
-DVG_HD bool stroke_hit_cubic(F2 p0, F2 p1, F2 p2, F2 p3, F4 r, F2 pt) {
+DVG_HD bool stroke_hit_cubic(F2 p0, F2 p1, F2 p2, F2 p3, F4 r, F2 pt, float stale0 = -1.f) {
     if (dist_sq(p0, pt) < r.x * r.x) return true;  // eval(0) == p0 exactly
     if (dist_sq(p3, pt) < r.w * r.w) return true;  // eval(1) == p3 exactly
     Quintic q = cubic_quintic(p0, p1, p2, p3, pt);
     float intervals[4];
-    int n = quintic_intervals(q, intervals);
+    int n = quintic_intervals(q, intervals, stale0);
     float lower_bound = 0.f;
     for (int j = 0; j < n + 1; j++) {
         if (j < n && intervals[j] < 0.f) continue;
@@ -168,6 +183,24 @@ DVG_HD bool stroke_hit_line(F2 p0, F2 p1, float r0, float r1, F2 pt) {
         float r = r0 + t * (r1 - r0);
         return dist_sq(p0 + t * (p1 - p0), pt) < r * r;
     }
+}
+
+// true  => pt is provably farther than the stroke radius from every point of the curve.
+// `cap` = DVG_CAP_N records of 6 floats (see dvg_scene.cuh).  Conservative: chord distance at a
+// slightly inexact t only over-estimates the distance by O(|d|^2 dt^2) << the 1e-2 px margin in R.
+DVG_HD bool capsule_reject(const float *cap, F2 pt) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < DVG_CAP_N; i++) {
+        const float *c = cap + 6 * i;
+        const float wx = pt.x - c[0], wy = pt.y - c[1];
+        float t = (wx * c[2] + wy * c[3]) * c[4];
+        t = t < 0.f ? 0.f : (t > 1.f ? 1.f : t);
+        const float ex = wx - t * c[2], ey = wy - t * c[3];
+        if (!(ex * ex + ey * ey > c[5])) return false;   // (also false for NaN)
+    }
+    return true;
 }
 
 // Stroke test of one primitive.  `r_shape` is shape.stroke_width (used by circle/rect and

@@ -29,6 +29,7 @@ struct Stage {
     Box box[CHUNK];
     float thick[CHUNK];
     int tf[CHUNK], inst[CHUNK], group[CHUNK];
+    F4 cap[CHUNK * DVG_CAP_F4];
 };
 
 // ------------------------------------------------------------------------------------------
@@ -83,11 +84,17 @@ DVG_D void traverse(const SceneView &sc, const BinView &bins, const int tile, St
             st.inst[t] = pm.inst;
             st.group[t] = sc.insts[pm.inst].group;
         }
+        if ((int)threadIdx.x < n * DVG_CAP_F4) {
+            const int t = threadIdx.x;
+            const int e = bins.items[base + t / DVG_CAP_F4];
+            st.cap[t] = sc.prim_cap[(size_t)e * DVG_CAP_F4 + t % DVG_CAP_F4];
+        }
         __syncthreads();
         for (int j = 0; j < n; j++) {
             PrimRef pr;
             pr.p01 = st.p01[j]; pr.p23 = st.p23[j]; pr.rad = st.rad[j]; pr.box = st.box[j];
             pr.thick = st.thick[j]; pr.tf = st.tf[j]; pr.inst = st.inst[j]; pr.group = st.group[j];
+            pr.cap = reinterpret_cast<const float *>(&st.cap[j * DVG_CAP_F4]);
             tr.step(sc, pr);
         }
     }
@@ -107,6 +114,14 @@ template <bool BACKWARD>
 __global__ void __launch_bounds__(RB) k_render(SceneView sc, BinView bins, RenderArgs ra) {
     __shared__ Stage st;
     __shared__ float s_pix[BACKWARD ? 4 : MAX_TILE_PIX * 4];
+    GradCache *gcp = nullptr;
+    if constexpr (BACKWARD) {
+        __shared__ GradCache s_gc;
+        gcp = &s_gc;
+        grad_cache_init(s_gc);
+        __syncthreads();
+    }
+    const CacheSink sk{gcp, ra.d_params};
     const int tile_row0 = ra.row_begin / bins.tile_h;
     const int tile = blockIdx.x + tile_row0 * bins.tiles_x;
     const int tx = tile % bins.tiles_x, ty = tile / bins.tiles_x;
@@ -222,7 +237,7 @@ __global__ void __launch_bounds__(RB) k_render(SceneView sc, BinView bins, Rende
                     dca = d_prev_alpha;
                     if (ctype != 0 && !(key & 1)) {
                         // gradient FILL colours: per-lane scatter (diffvg.cpp:382-499)
-                        d_eval_gradient(ctype, sc.params + coff, cstops, pos.cpt, dc, ra.d_params + coff,
+                        d_eval_gradient(ctype, sc.params + coff, cstops, pos.cpt, dc, sk, coff,
                                         ra.d_translation ? ra.d_translation + 2 * (y * ra.width + x) : nullptr);
                     }
                     // Q4: gradient STROKE colours have no gradient storage in the reference
@@ -231,8 +246,7 @@ __global__ void __launch_bounds__(RB) k_render(SceneView sc, BinView bins, Rende
                 if (ctype == 0) {
                     dc.x = warp_sum(dc.x); dc.y = warp_sum(dc.y); dc.z = warp_sum(dc.z); dc.w = warp_sum(dc.w);
                     if ((tid & 31) == 0) {
-                        float *d = ra.d_params + coff;
-                        atomicAdd(d + 0, dc.x); atomicAdd(d + 1, dc.y); atomicAdd(d + 2, dc.z); atomicAdd(d + 3, dc.w);
+                        sk.add(coff + 0, dc.x); sk.add(coff + 1, dc.y); sk.add(coff + 2, dc.z); sk.add(coff + 3, dc.w);
                     }
                 }
             }
@@ -279,7 +293,9 @@ __global__ void __launch_bounds__(RB) k_render(SceneView sc, BinView bins, Rende
         }
     } else {
         d_radius_acc = warp_sum(d_radius_acc);
-        if ((tid & 31) == 0 && d_radius_acc != 0.f) atomicAdd(ra.d_params + sc.filter_radius_off, d_radius_acc);
+        if ((tid & 31) == 0) sk.add(sc.filter_radius_off, d_radius_acc);
+        __syncthreads();
+        grad_cache_flush(*gcp, ra.d_params);
     }
 }
 
@@ -323,10 +339,12 @@ __global__ void k_boundary_scatter(BoundaryWork bw) {
 // (tile, chunk of EDGE_SPB samples); lanes 2k / 2k+1 evaluate the two sides of sample k.
 __global__ void __launch_bounds__(RB) k_edge(SceneView sc, BinView bins, RenderArgs ra, BoundaryWork bw) {
     __shared__ Stage st;
+    __shared__ GradCache s_gc;
     __shared__ int s_tile;
     const int ntiles = bins.tiles_x * bins.tiles_y;
     const int blk = blockIdx.x;
     if (blk >= bw.blk_offsets[ntiles]) return;  // uniform for the whole block
+    grad_cache_init(s_gc);
     if (threadIdx.x == 0) {
         int lo = 0, hi = ntiles;  // largest t with blk_offsets[t] <= blk
         while (hi - lo > 1) {
@@ -373,24 +391,58 @@ __global__ void __launch_bounds__(RB) k_edge(SceneView sc, BinView bins, RenderA
     other.z = __shfl_xor_sync(0xffffffffu, mine.z, 1);
     other.w = __shfl_xor_sync(0xffffffffu, mine.w, 1);
     const int other_hit = __shfl_xor_sync(0xffffffffu, my_hit, 1);
-    if (!active || side != 0) return;
-    // lane `side == 0` evaluated pt - eps*n  ("inside")
-    if (!my_hit && !other_hit) return;  // occluded (diffvg.cpp:1422-1425)
-    F4 c_in = mine, c_out = other;
-    F2 normal = bs.normal;
-    if (!my_hit) { normal = -normal; c_in = other; c_out = mine; }
-    const F2 spt = mk2(bs.pt.x * ra.width, bs.pt.y * ra.height);
-    F4 d_color = gather_d_color(sc.filter, ra.d_render_image, ra.weight_image, ra.width, ra.height, spt);
-    const float inv_area = 1.f / (float)(sc.canvas_w * sc.canvas_h);
-    d_color = d_color * inv_area;
-    const F4 diff = c_in - c_out;
-    const float contrib = (diff.x * d_color.x + diff.y * d_color.y + diff.z * d_color.z + diff.w * d_color.w) / bs.pdf;
-    const InstInfo &ii = sc.insts[bs.inst];
-    accumulate_boundary_gradient(sc, ra, bs, ii, sc.groups[ii.group], contrib, normal);
-    if (ra.d_translation) {  // diffvg.cpp:1454-1461
-        atomicAdd(ra.d_translation + 2 * (by * ra.width + bx) + 0, normal.x * contrib);
-        atomicAdd(ra.d_translation + 2 * (by * ra.width + bx) + 1, normal.y * contrib);
+    // lane `side == 0` evaluated pt - eps*n ("inside"); it owns the scatter of its sample.
+    // occluded samples contribute nothing (diffvg.cpp:1422-1425)
+    const bool scatter = active && side == 0 && (my_hit || other_hit);
+    const CacheSink sk{&s_gc, ra.d_params};
+    float dm[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    int xoff = -1;
+    if (scatter) {
+        F4 c_in = mine, c_out = other;
+        F2 normal = bs.normal;
+        if (!my_hit) { normal = -normal; c_in = other; c_out = mine; }
+        const F2 spt = mk2(bs.pt.x * ra.width, bs.pt.y * ra.height);
+        F4 d_color = gather_d_color(sc.filter, ra.d_render_image, ra.weight_image, ra.width, ra.height, spt);
+        const float inv_area = 1.f / (float)(sc.canvas_w * sc.canvas_h);
+        d_color = d_color * inv_area;
+        const F4 diff = c_in - c_out;
+        const float contrib = (diff.x * d_color.x + diff.y * d_color.y + diff.z * d_color.z + diff.w * d_color.w) / bs.pdf;
+        const InstInfo &ii = sc.insts[bs.inst];
+        const GroupInfo &g = sc.groups[ii.group];
+        accumulate_boundary_gradient(sc, ra, bs, ii, g, contrib, normal, sk);
+        if (ra.debug_out) {
+            float *o = ra.debug_out + 4 * (size_t)bw.sorted_idx[bw.tile_offsets[tile] + k];
+            o[0] = contrib; o[1] = (float)(my_hit | (other_hit << 1)); o[2] = normal.x; o[3] = normal.y;
+        }
+        if (!(ra.flags & 1u)) {  // DVG_BWD_SKIP_XFORM_GRAD
+            boundary_xform_gradient(bs, g, contrib, normal, dm);
+            xoff = g.xform_off;
+        }
+        if (ra.d_translation) {  // diffvg.cpp:1454-1461
+            atomicAdd(ra.d_translation + 2 * (by * ra.width + bx) + 0, normal.x * contrib);
+            atomicAdd(ra.d_translation + 2 * (by * ra.width + bx) + 1, normal.y * contrib);
+        }
     }
+    // d_shape_to_canvas: warp-reduce when every scattering lane targets the same transform
+    {
+        const unsigned am = __ballot_sync(0xffffffffu, xoff >= 0);
+        if (am) {
+            const int x0 = __shfl_sync(0xffffffffu, xoff, __ffs(am) - 1);
+            const bool uniform = __all_sync(0xffffffffu, xoff < 0 || xoff == x0);
+            if (uniform) {
+#pragma unroll
+                for (int k = 0; k < 9; k++) {
+                    const float v = warp_sum(dm[k]);
+                    if ((threadIdx.x & 31) == 0) sk.add(x0 + k, v);
+                }
+            } else if (xoff >= 0) {
+#pragma unroll
+                for (int k = 0; k < 9; k++) sk.add(xoff + k, dm[k]);
+            }
+        }
+    }
+    __syncthreads();
+    grad_cache_flush(s_gc, ra.d_params);
 }
 
 // ------------------------------------------------------------------------------------------

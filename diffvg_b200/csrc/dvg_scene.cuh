@@ -22,6 +22,14 @@ enum PrimType { PRIM_LINE = 0, PRIM_QUAD = 1, PRIM_CUBIC = 2, PRIM_CIRCLE = 3, P
 #define DVG_PF_FIRST 0x80     // first primitive of its shape instance
 #define DVG_PF_GFIRST 0x100   // first primitive of its group
 
+// Conservative stroke-reject capsules of a curved primitive: the curve is cut into DVG_CAP_N pieces;
+// piece i lies within `dev_i` of its chord A_i -> A_i + d_i, so a point farther than
+// dev_i + max_radius (+ margin) from every chord cannot be within the stroke radius of any curve
+// point and the quintic / cubic root solve of within_distance.h:63-272 can be skipped with the
+// answer the reference would compute (false).  6 floats per piece: A.xy, d.xy, 1/|d|^2, R^2.
+#define DVG_CAP_N 4
+#define DVG_CAP_F4 6   // DVG_CAP_N * 6 floats / 4
+
 struct PrimMeta {
     int type_flags;  // PrimType | flags
     int inst;        // shape instance (index into inst_* arrays)
@@ -72,6 +80,7 @@ struct SceneView {
     const float *prim_thick;  // leaf max_radius, scene.cpp:546,569,597
     const PrimMeta *prim_meta;
     const Box *prim_cbox;  // canvas-space conservative bound of where this primitive can matter (binning only)
+    const F4 *prim_cap;    // DVG_CAP_F4 float4 per primitive: conservative stroke-reject capsules (dvg_geom.cuh)
     const InstInfo *insts;
     const GroupInfo *groups;
     // boundary sampling tables (scene.cpp:207-333)
@@ -105,6 +114,7 @@ struct RenderArgs {
     float *d_params;
     float *d_background;
     float *d_translation;
+    float *debug_out;              // [n,4] per boundary sample (contrib, hit bits, normal) -- debug builds of the tests only
 };
 
 }  // namespace dvg

@@ -31,6 +31,7 @@ struct PrimRef {
     int tf;     // type | flags
     int inst;
     int group;
+    const float *cap;  // DVG_CAP_N * 6 floats (reject capsules)
 };
 
 template <bool EDGE, bool RECORD>
@@ -140,8 +141,15 @@ struct SampleTracer {
             // path-BVH leaf test (within_distance.h:278-285)
             if ((tf & DVG_PF_SINGLE) || box_inside_r(pr.box, lpt, pr.thick)) {
                 bool decided = false;
-                const bool h = prim_stroke_hit(tf & DVG_PF_TYPE_MASK, (tf & DVG_PF_APPROX) != 0, pr.p01, pr.p23, pr.rad,
-                                               shape_r, lpt, &decided);
+                const int ptype = tf & DVG_PF_TYPE_MASK;
+                // conservative early-out for curved segments (exact answer `false`, no root solve)
+                #ifdef DVG_NO_CAPSULE
+                const bool skip = false;
+#else
+                const bool skip = (ptype == PRIM_CUBIC || ptype == PRIM_QUAD) && !(tf & DVG_PF_APPROX) && capsule_reject(pr.cap, lpt);
+#endif
+                const bool h = skip ? false : prim_stroke_hit(ptype, (tf & DVG_PF_APPROX) != 0, pr.p01, pr.p23, pr.rad,
+                                                              shape_r, lpt, &decided);
                 if (decided) sh_done = true;
                 if (h) {
                     sh_hit = true; stroke_hit = true;

@@ -129,6 +129,9 @@ int64_t dvg_kernel_launch_count(void);
  * TFLOP/s: the roofline denominator for this CUDA-core-bound path.
  */
 int dvg_profile_enable(int on);
+/* Test support: when non-NULL, the boundary pass also writes (contrib, hit bits, normal.xy) per boundary
+ * sample index into this DEVICE buffer of 4*W*H*spp floats (sample-level parity debugging). */
+int dvg_debug_set_boundary_dump(float *device_buf);
 int64_t dvg_profile_report(char *buf, int64_t cap);
 int dvg_measure_peak(int which, int device, double *tflops);
 

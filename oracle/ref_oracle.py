@@ -11,20 +11,25 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_lib = None
+_libs = {}
+
+# Two builds of the same unmodified sources (oracle/Makefile):
+#   'det'   -ftrivial-auto-var-init=zero: pins the reference's uninitialised `intervals[0]` read
+#            to "no extra split point"; the PARITY checker (default).
+#   'plain' stock flags; what the CPU baseline times.
+_PATTERN = {'det': 'diffvg_det.so', 'plain': 'diffvg.cpython*.so'}
 
 
 def available():
-    return len(glob.glob(os.path.join(_HERE, '_ref', 'diffvg*.so'))) > 0
+    return all(len(glob.glob(os.path.join(_HERE, '_ref', p))) > 0 for p in _PATTERN.values())
 
 
-def _load():
-    global _lib
-    if _lib is not None:
-        return _lib
-    cands = sorted(glob.glob(os.path.join(_HERE, '_ref', 'diffvg*.so')))
+def _load(variant='det'):
+    if variant in _libs:
+        return _libs[variant]
+    cands = sorted(glob.glob(os.path.join(_HERE, '_ref', _PATTERN[variant])))
     if not cands:
-        raise RuntimeError('oracle/_ref/diffvg*.so not built: run `make -C oracle ref` where /root/reference exists')
+        raise RuntimeError('oracle/_ref/%s not built: run `make -C oracle ref` where /root/reference exists' % _PATTERN[variant])
     lib = ctypes.CDLL(cands[0])
     fp = ctypes.POINTER(ctypes.c_float)
     ip = ctypes.POINTER(ctypes.c_int32)
@@ -35,7 +40,7 @@ def _load():
                                       ctypes.c_int64]
     lib.dvgref_scene_dump.restype = ctypes.c_int64
     lib.dvgref_last_error.restype = ctypes.c_char_p
-    _lib = lib
+    _libs[variant] = lib
     return lib
 
 
@@ -48,12 +53,12 @@ def _f(a):
 
 def render(topo, params, width, height, nsx, nsy, seed, background=None, d_render_image=None,
            d_render_sdf=None, want_image=True, want_sdf=False, use_prefiltering=False,
-           eval_positions=None, want_d_translation=False):
+           eval_positions=None, want_d_translation=False, variant='det'):
     """One reference `Scene(...)` + `render(...)` call (diffvg.cpp:1477).
 
     Forward: returns dict(image=[H,W,4] and/or sdf).  Backward (d_render_image or
     d_render_sdf given): returns dict(d_params=..., d_background=..., d_translation=...)."""
-    lib = _load()
+    lib = _load(variant)
     topo = np.ascontiguousarray(topo, dtype=np.int32)
     params = np.ascontiguousarray(params, dtype=np.float32)
     n_eval = 0 if eval_positions is None else eval_positions.shape[0]

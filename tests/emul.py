@@ -17,7 +17,7 @@ def build():
                     for f in os.listdir(os.path.join(_HERE, '..', 'diffvg_b200', 'csrc')) if f.endswith('.cuh')]
     if os.path.exists(_SO) and all(os.path.getmtime(_SO) >= os.path.getmtime(d) for d in deps):
         return
-    subprocess.check_call(['g++', '-O2', '-std=c++17', '-ffp-contract=off', '-fPIC', '-shared', '-fvisibility=hidden',
+    subprocess.check_call(['g++', '-O2', '-std=c++17', '-ffp-contract=off', '-mfma', '-DDVG_FMA_QUINTIC', '-fPIC', '-shared', '-fvisibility=hidden',
                            '-o', _SO, src, '-lpthread'])
 
 

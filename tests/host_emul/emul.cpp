@@ -15,6 +15,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cstdio>
 #include <cstring>
 #include <mutex>
 #include <thread>
@@ -33,7 +34,7 @@ struct HostScene {
     std::vector<int> seg_point_id;
     std::vector<InstInfo> insts;
     std::vector<GroupInfo> groups;
-    std::vector<F4> p01, p23, rad;
+    std::vector<F4> p01, p23, rad, cap;
     std::vector<PrimMeta> meta;
     int error_flag = 0;
     float total_length = 0;
@@ -73,7 +74,7 @@ void build(HostScene &hs, const int32_t *topo, const float *params) {
     hs.seg_cdf.resize(nsg); hs.seg_pmf.resize(nsg); hs.seg_point_id.resize(nsg);
     hs.insts.resize(ni); hs.groups.resize(ng);
     hs.p01.resize(np); hs.p23.resize(np); hs.rad.resize(np); hs.prim_box.resize(np); hs.prim_thick.resize(np);
-    hs.meta.resize(np); hs.prim_cbox.resize(np); hs.shape_cdf.resize(ni); hs.shape_pmf.resize(ni);
+    hs.meta.resize(np); hs.prim_cbox.resize(np); hs.cap.resize((size_t)np * DVG_CAP_F4); hs.shape_cdf.resize(ni); hs.shape_pmf.resize(ni);
     BuildView bv;
     bv.canvas_w = t[DVG_H_CANVAS_W]; bv.canvas_h = t[DVG_H_CANVAS_H];
     bv.num_shapes = ns; bv.num_groups = ng; bv.num_insts = ni; bv.num_prims = np;
@@ -84,7 +85,7 @@ void build(HostScene &hs, const int32_t *topo, const float *params) {
     bv.seg_cdf = hs.seg_cdf.data(); bv.seg_pmf = hs.seg_pmf.data(); bv.seg_point_id = hs.seg_point_id.data();
     bv.insts = hs.insts.data(); bv.groups = hs.groups.data();
     bv.prim_p01 = hs.p01.data(); bv.prim_p23 = hs.p23.data(); bv.prim_rad = hs.rad.data(); bv.prim_box = hs.prim_box.data();
-    bv.prim_thick = hs.prim_thick.data(); bv.prim_meta = hs.meta.data(); bv.prim_cbox = hs.prim_cbox.data();
+    bv.prim_thick = hs.prim_thick.data(); bv.prim_meta = hs.meta.data(); bv.prim_cbox = hs.prim_cbox.data(); bv.prim_cap = hs.cap.data();
     bv.shape_cdf = hs.shape_cdf.data(); bv.shape_pmf = hs.shape_pmf.data();
     bv.error_flag = &hs.error_flag; bv.total_length = &hs.total_length;
     for (int s = 0; s < ns; s++) build_shape(bv, s);
@@ -99,7 +100,7 @@ void build(HostScene &hs, const int32_t *topo, const float *params) {
     sc.filter_radius_off = t[DVG_H_FILTER_RADIUS_OFF];
     sc.topo = t; sc.params = hs.params.data();
     sc.prim_p01 = hs.p01.data(); sc.prim_p23 = hs.p23.data(); sc.prim_rad = hs.rad.data(); sc.prim_box = hs.prim_box.data();
-    sc.prim_thick = hs.prim_thick.data(); sc.prim_meta = hs.meta.data(); sc.prim_cbox = hs.prim_cbox.data();
+    sc.prim_thick = hs.prim_thick.data(); sc.prim_meta = hs.meta.data(); sc.prim_cbox = hs.prim_cbox.data(); sc.prim_cap = hs.cap.data();
     sc.insts = hs.insts.data(); sc.groups = hs.groups.data();
     sc.shapes_length = hs.shapes_length.data(); sc.shape_cdf = hs.shape_cdf.data(); sc.shape_pmf = hs.shape_pmf.data();
     sc.seg_cdf = hs.seg_cdf.data(); sc.seg_pmf = hs.seg_pmf.data(); sc.seg_point_id = hs.seg_point_id.data();
@@ -110,6 +111,7 @@ PrimRef prim_ref(const HostScene &hs, int e) {
     PrimRef pr;
     pr.p01 = hs.p01[e]; pr.p23 = hs.p23[e]; pr.rad = hs.rad[e]; pr.box = hs.prim_box[e]; pr.thick = hs.prim_thick[e];
     pr.tf = hs.meta[e].type_flags; pr.inst = hs.meta[e].inst; pr.group = hs.insts[hs.meta[e].inst].group;
+    pr.cap = reinterpret_cast<const float *>(&hs.cap[(size_t)e * DVG_CAP_F4]);
     return pr;
 }
 
@@ -136,6 +138,17 @@ void parallel_rows(int n, int nthreads, F f) {
 
 // Forward (d_image == null) or backward.  Images are host arrays.  Backward accumulation is
 // serialised with a mutex per call to keep the harness simple.
+// Gradients are accumulated in DOUBLE here (the per-sample terms are the product's float
+// arithmetic; only the summation is wider), so this harness is also the accuracy yardstick for
+// sums where the reference's sequential float atomics saturate (e.g. d_filter.radius: 4 M terms of
+// ~1e-8 added one by one to a float of magnitude ~1).
+struct DoubleSink {
+    double *D;
+    void add(int idx, float v) const { D[idx] += (double)v; }
+};
+static float *g_debug_out = nullptr;
+EXPORT void emul_set_boundary_dump(float *buf) { g_debug_out = buf; }
+
 EXPORT int emul_render(const int32_t *topo, const float *params, const float *background, float *image,
                        int W, int H, int nsx, int nsy, uint64_t seed, const float *d_image,
                        float *d_params, float *d_background, int skip_xform_grad, int nthreads) {
@@ -167,6 +180,8 @@ EXPORT int emul_render(const int32_t *topo, const float *params, const float *ba
     ra.weight_image = weight.data();
     ra.flags = skip_xform_grad ? 1u : 0u;
 
+    std::vector<double> acc(d_params ? hs.params.size() : 0, 0.0);
+    const DoubleSink dsink{acc.data()};
     parallel_rows(H, nthreads, [&](int y) {
         std::vector<int> cand;
         std::vector<int> fkey(DVG_MAXF);
@@ -228,8 +243,8 @@ EXPORT int emul_render(const int32_t *topo, const float *params, const float *ba
                             F4 dc = mk4(dcr * fc.w, dcg * fc.w, dcb * fc.w, d_alpha_i);
                             dcr = dcr * (1 - fc.w); dcg = dcg * (1 - fc.w); dcb = dcb * (1 - fc.w);
                             dca = d_prev_alpha;
-                            if (ctype == 0) { for (int k = 0; k < 4; k++) d_params[coff + k] += (&dc.x)[k]; }
-                            else if (!(key & 1)) d_eval_gradient(ctype, sc.params + coff, cstops, cpt, dc, d_params + coff, nullptr);
+                            if (ctype == 0) { for (int k = 0; k < 4; k++) acc[coff + k] += (double)(&dc.x)[k]; }
+                            else if (!(key & 1)) d_eval_gradient(ctype, sc.params + coff, cstops, cpt, dc, dsink, coff, nullptr);
                         }
                         if (bg_px && d_background) {
                             float *d = d_background + 4 * (y * W + x);
@@ -249,7 +264,7 @@ EXPORT int emul_render(const int32_t *topo, const float *params, const float *ba
                                 const float *dp = d_image + 4 * (yy * W + xx);
                                 const float dotv = dp[0] * color.x + dp[1] * color.y + dp[2] * color.z + dp[3] * color.w;
                                 const float d_weight = (dotv * ws - fw * dotv * (ws - fw)) / (ws * ws);
-                                d_params[sc.filter_radius_off] += d_filter_weight_radius(sc.filter, ddx, ddy, d_weight);
+                                acc[sc.filter_radius_off] += (double)d_filter_weight_radius(sc.filter, ddx, ddy, d_weight);
                             }
                         }
                 }
@@ -300,10 +315,20 @@ EXPORT int emul_render(const int32_t *topo, const float *params, const float *ba
                 const F4 diff = c_in - c_out;
                 const float contrib = (diff.x * d_color.x + diff.y * d_color.y + diff.z * d_color.z + diff.w * d_color.w) / bs.pdf;
                 std::lock_guard<std::mutex> lk(mu);
-                accumulate_boundary_gradient(sc, ra, bs, ii, sc.groups[ii.group], contrib, normal);
+                if (g_debug_out) {
+                    float *o = g_debug_out + 4 * (size_t)idx;
+                    o[0] = contrib; o[1] = (float)((hit[0] ? 1 : 0) | (hit[1] ? 2 : 0)); o[2] = normal.x; o[3] = normal.y;
+                }
+                accumulate_boundary_gradient(sc, ra, bs, ii, sc.groups[ii.group], contrib, normal, dsink);
+                if (!skip_xform_grad) {
+                    float dm[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+                    boundary_xform_gradient(bs, sc.groups[ii.group], contrib, normal, dm);
+                    for (int k = 0; k < 9; k++) acc[sc.groups[ii.group].xform_off + k] += (double)dm[k];
+                }
             }
         });
     }
+    if (d_params) for (size_t i = 0; i < acc.size(); i++) d_params[i] = (float)acc[i];
     return 0;
 }
 
@@ -335,4 +360,77 @@ EXPORT void emul_pcg(int idx, uint64_t seed, uint64_t *state, float *rx, float *
     *state = r.state;
     *rx = pcg32_next_float(r);
     *ry = pcg32_next_float(r);
+}
+
+// Debug: per-sample report for one pixel (which primitives' stroke tests hit, final colour) and
+// a scan of the reference's uninitialised intervals[0] (Q10) over [0,1].
+EXPORT void emul_debug_pixel(const int32_t *topo, const float *params, int W, int H, int nsx, int nsy, uint64_t seed, int x, int y) {
+    HostScene hs;
+    build(hs, topo, params);
+    const SceneView &sc = hs.sc;
+    const float cw = (float)sc.canvas_w, ch = (float)sc.canvas_h;
+    const float margin = 4e-4f * std::max(cw, ch) + 1e-4f;
+    std::vector<int> cand;
+    candidates(hs, (float)x / W * cw - margin, (float)y / H * ch - margin, (float)(x + 1) / W * cw + margin, (float)(y + 1) / H * ch + margin, cand);
+    printf("pixel %d %d: %d candidates\n", x, y, (int)cand.size());
+    for (int s = 0; s < nsx * nsy; s++) {
+        const int sx = s % nsx, sy = s / nsx;
+        const int idx = ((y * W + x) * nsy + sy) * nsx + sx;
+        F2 pt, cpt;
+        sample_position(sc.canvas_w, sc.canvas_h, W, H, nsx, nsy, seed, false, x, y, sx, sy, idx, pt, cpt);
+        SampleTracer<false, false> tr;
+        tr.init(cpt, true, mk4(0, 0, 0, 0), -1, -1, nullptr, nullptr);
+        for (int e : cand) tr.step(sc, prim_ref(hs, e));
+        tr.finish(sc);
+        F4 c = tr.resolve(nullptr);
+        printf(" sample %2d idx %d pt (%.6f %.6f) nfrag %d color %.6f %.6f %.6f %.6f\n", s, idx, cpt.x, cpt.y, tr.nfrag, c.x, c.y, c.z, c.w);
+        for (int e : cand) {
+            PrimRef pr = prim_ref(hs, e);
+            if ((pr.tf & DVG_PF_TYPE_MASK) != PRIM_CUBIC) continue;
+            if (!((pr.tf & DVG_PF_SINGLE) || box_inside_r(pr.box, cpt, pr.thick))) continue;
+            F2 p0 = mk2(pr.p01.x, pr.p01.y), p1 = mk2(pr.p01.z, pr.p01.w), p2 = mk2(pr.p23.x, pr.p23.y), p3 = mk2(pr.p23.z, pr.p23.w);
+            bool base = stroke_hit_cubic(p0, p1, p2, p3, pr.rad, cpt);
+            Quintic q = cubic_quintic(p0, p1, p2, p3, cpt);
+            double q_root = -q.B / 5.f;
+            int flips = 0; float first_flip = -1;
+            if (!(q_root >= 0 && q_root <= 1)) {
+                for (int k = 0; k <= 2000; k++) {
+                    float st = k / 2000.f;
+                    if (stroke_hit_cubic(p0, p1, p2, p3, pr.rad, cpt, st) != base) { if (!flips) first_flip = st; flips++; }
+                }
+            }
+            float iv[4]; int n = quintic_intervals(q, iv);
+            printf("   prim %d group %d hit %d q_root %.4f intervals(%d) %.5f %.5f %.5f %.5f stale-flips %d (first %.4f)\n", e, pr.group, (int)base, q_root, n, iv[0], n > 1 ? iv[1] : 9.f, n > 2 ? iv[2] : 9.f, n > 3 ? iv[3] : 9.f, flips, first_flip);
+        }
+    }
+}
+
+EXPORT void emul_debug_boundary(const int32_t *topo, const float *params, int W, int H, uint64_t seed, int idx) {
+    HostScene hs;
+    build(hs, topo, params);
+    const SceneView &sc = hs.sc;
+    BoundarySample bs;
+    make_boundary_sample(sc, idx, seed, bs);
+    printf("idx %d inst %d pt (%.7f %.7f) -> px (%.5f %.5f) normal (%.6f %.6f) pdf %g path_t %g base %d pid %d stroke %d\n", idx, bs.inst,
+           bs.pt.x, bs.pt.y, bs.pt.x * W, bs.pt.y * H, bs.normal.x, bs.normal.y, bs.pdf, bs.path_t, bs.base_point_id,
+           bs.point_id_stroke & 0x7fffffff, bs.point_id_stroke < 0);
+    if (bs.inst < 0) return;
+    const InstInfo &ii = sc.insts[bs.inst];
+    printf("  group %d shape %d prim_begin %d\n", ii.group, ii.shape, ii.prim_begin);
+    const float cw = (float)sc.canvas_w, ch = (float)sc.canvas_h;
+    for (int side = 0; side < 2; side++) {
+        const F2 off = 1e-4f * bs.normal;
+        const F2 npt = side ? bs.pt + off : bs.pt - off;
+        F2 cpt = mk2(npt.x * sc.canvas_w, npt.y * sc.canvas_h);
+        for (int e = 0; e < sc.num_prims; e++) {
+            PrimRef pr = prim_ref(hs, e);
+            if (pr.group != ii.group) continue;
+            bool inb = (pr.tf & DVG_PF_SINGLE) || box_inside_r(pr.box, cpt, pr.thick);
+            bool dec = false;
+            bool h = prim_stroke_hit(pr.tf & DVG_PF_TYPE_MASK, false, pr.p01, pr.p23, pr.rad, ii.r, cpt, &dec);
+            const Box &cb = hs.prim_cbox[e];
+            printf("  side %d cpt (%.6f %.6f) prim %d inbox %d hit %d caprej %d cbox (%.4f %.4f %.4f %.4f)\n", side, cpt.x, cpt.y, e, (int)inb, (int)h,
+                   (int)capsule_reject(pr.cap, cpt), cb.x0, cb.y0, cb.x1, cb.y1);
+        }
+    }
 }

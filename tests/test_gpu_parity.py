@@ -25,9 +25,19 @@ FWD_TOL = 1e-5
 GRAD_REL_L2 = 1e-4
 
 
-def grad_close(ref, got, rel=GRAD_REL_L2):
-    ref = np.asarray(ref, np.float64)
-    got = np.asarray(got, np.float64)
+def grad_close(ref, got, rel=GRAD_REL_L2, topo=None):
+    """`topo` given: the d_filter.radius entry is checked apart, at 2e-2.  The reference adds one
+    term per sample to that single float with sequential atomics (filter.h:50-106 via atomic.h), so
+    at millions of samples the running sum absorbs the ~1e-8 terms (float saturation) and its value
+    is off by up to ~1 %; the hierarchical reduction here does not saturate (see
+    test_painterly_c3_full_size_vs_oracle, which pins it against a float64 summation instead)."""
+    ref = np.array(ref, np.float64)
+    got = np.array(got, np.float64)
+    if topo is not None:
+        from diffvg_b200 import scene_pack
+        i = int(topo[scene_pack.H_FRAD_OFF])
+        assert abs(ref[i] - got[i]) <= 2e-2 * abs(ref[i]) + 1e-12, 'd_filter.radius %g vs %g' % (ref[i], got[i])
+        ref[i] = got[i] = 0.0
     assert util.rel_l2(ref, got) <= rel, 'rel-L2 %g' % util.rel_l2(ref, got)
     floor = 1e-3 * np.abs(ref).max()
     assert (np.abs(ref - got) <= 1e-3 * np.abs(ref) + floor).all()
@@ -129,7 +139,15 @@ def test_painterly_c3_full_size_vs_oracle():
     d_img = (2.0 * (got - target) / got.size).astype(np.float32)
     rb = oracle_check.render(topo, params, 512, 512, 4, 4, 0, d_render_image=d_img)
     gb = util.gpu_render(topo, params, 512, 512, 4, 4, 0, d_render_image=d_img)
-    grad_close(rb['d_params'], gb['d_params'])
+    grad_close(rb['d_params'], gb['d_params'], topo=topo)
+    # the same per-sample float arithmetic summed in float64 on the host (tests/host_emul): every entry,
+    # including d_filter.radius, to 1e-4
+    import emul
+    eb = emul.render(topo, params, 512, 512, 4, 4, 0, d_render_image=d_img, nthreads=os.cpu_count())
+    grad_close(eb['d_params'], gb['d_params'])
+    from diffvg_b200 import scene_pack
+    i = int(topo[scene_pack.H_FRAD_OFF])
+    assert abs(eb['d_params'][i] - gb['d_params'][i]) <= 1e-4 * abs(eb['d_params'][i])
 
 
 def test_pydiffvg_api_single_circle_gradients():
