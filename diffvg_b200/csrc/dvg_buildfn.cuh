@@ -191,27 +191,30 @@ DVG_HD float seg_dist(F2 a, F2 d, float inv_len2, F2 p) {
     F2 e = w - t * d;
     return sqrtf(dot2(e, e));
 }
-DVG_HD void cap_piece(F2 q0, F2 q1, F2 q2, F2 q3, float rmax, float *out) {
-    F2 d = q3 - q0;
+DVG_HD void cap_piece(const F2 *q, float rmax, float rmin, float *out) {
+    F2 d = q[3] - q[0];
     float len2 = dot2(d, d);
     float inv = len2 > 1e-12f ? 1.f / len2 : 0.f;
     if (inv == 0.f) d = mk2(0, 0);
-    float dev = rmaxf(seg_dist(q0, d, inv, q1), seg_dist(q0, d, inv, q2));
+    float dev = rmaxf(seg_dist(q[0], d, inv, q[1]), seg_dist(q[0], d, inv, q[2]));
     // margin: float rounding of the de Casteljau split, of eval_cubic in the exact test and of this
     // test itself are all < 1e-4 px at canvas scales; 1e-2 px + 1e-4 relative is far above that
-    float R = (dev + rmax) * 1.0001f + 1e-2f;
-    out[0] = q0.x; out[1] = q0.y; out[2] = d.x; out[3] = d.y; out[4] = inv; out[5] = R * R;
+    float Ro = (dev + rmax) * 1.0001f + 1e-2f;
+    float Ri = (rmin - dev) * 0.9999f - 1e-2f;
+    out[0] = q[0].x; out[1] = q[0].y; out[2] = d.x; out[3] = d.y; out[4] = inv; out[5] = Ro * Ro;
+    out[6] = Ri > 0.f ? Ri * Ri : -1.f;
+    out[7] = 0.f;
 }
-DVG_HD void cap_split(F2 p0, F2 p1, F2 p2, F2 p3, F2 *l, F2 *r) {  // de Casteljau at 1/2
-    F2 a = 0.5f * (p0 + p1), b = 0.5f * (p1 + p2), c = 0.5f * (p2 + p3);
+DVG_HD void cap_split(const F2 *p, F2 *l, F2 *r) {  // de Casteljau at 1/2
+    F2 a = 0.5f * (p[0] + p[1]), b = 0.5f * (p[1] + p[2]), c = 0.5f * (p[2] + p[3]);
     F2 ab = 0.5f * (a + b), bc = 0.5f * (b + c);
     F2 m = 0.5f * (ab + bc);
-    l[0] = p0; l[1] = a; l[2] = ab; l[3] = m;
-    r[0] = m; r[1] = bc; r[2] = c; r[3] = p3;
+    l[0] = p[0]; l[1] = a; l[2] = ab; l[3] = m;
+    r[0] = m; r[1] = bc; r[2] = c; r[3] = p[3];
 }
-// type: PRIM_QUAD / PRIM_CUBIC get real capsules; everything else a never-reject record.
-DVG_HD void build_capsules(int type, F4 p01, F4 p23, float rmax, float *out) {
-    bool ok = (type == PRIM_QUAD || type == PRIM_CUBIC) && rmax == rmax;
+// type: PRIM_QUAD / PRIM_CUBIC get real brackets; everything else a never-decide record.
+DVG_HD void build_capsules(int type, F4 p01, F4 p23, float rmax, float rmin, float *out) {
+    bool ok = (type == PRIM_QUAD || type == PRIM_CUBIC) && rmax == rmax && rmin == rmin;
     F2 c[4];
     c[0] = mk2(p01.x, p01.y);
     if (type == PRIM_CUBIC) { c[1] = mk2(p01.z, p01.w); c[2] = mk2(p23.x, p23.y); c[3] = mk2(p23.z, p23.w); }
@@ -221,17 +224,22 @@ DVG_HD void build_capsules(int type, F4 p01, F4 p23, float rmax, float *out) {
     }
     for (int k = 0; k < 4; k++) ok = ok && fabsf(c[k].x) < 1e18f && fabsf(c[k].y) < 1e18f;   // finite, no overflow below
     if (!ok) {
-        for (int i = 0; i < DVG_CAP_N; i++) { float *o = out + 6 * i; o[0] = o[1] = o[2] = o[3] = o[4] = 0.f; o[5] = INFINITY; }
+        for (int i = 0; i < DVG_CAP_N; i++) {
+            float *o = out + 8 * i;
+            o[0] = o[1] = o[2] = o[3] = o[4] = o[7] = 0.f; o[5] = INFINITY; o[6] = -1.f;
+        }
         return;
     }
-    F2 l[4], r[4], ll[4], lr[4], rl[4], rr[4];
-    cap_split(c[0], c[1], c[2], c[3], l, r);
-    cap_split(l[0], l[1], l[2], l[3], ll, lr);
-    cap_split(r[0], r[1], r[2], r[3], rl, rr);
-    cap_piece(ll[0], ll[1], ll[2], ll[3], rmax, out + 0);
-    cap_piece(lr[0], lr[1], lr[2], lr[3], rmax, out + 6);
-    cap_piece(rl[0], rl[1], rl[2], rl[3], rmax, out + 12);
-    cap_piece(rr[0], rr[1], rr[2], rr[3], rmax, out + 18);
+    // three levels of halving -> 8 pieces, written in curve order
+    F2 h[2][4], q[4][4], e[2][4];
+    cap_split(c, h[0], h[1]);
+    cap_split(h[0], q[0], q[1]);
+    cap_split(h[1], q[2], q[3]);
+    for (int i = 0; i < 4; i++) {
+        cap_split(q[i], e[0], e[1]);
+        cap_piece(e[0], rmax, rmin, out + 8 * (2 * i));
+        cap_piece(e[1], rmax, rmin, out + 8 * (2 * i + 1));
+    }
 }
 
 // ------------------------------------------------------------------ primitives
@@ -310,8 +318,15 @@ DVG_HD_NOINLINE void build_prim(const BuildView &bv, int e) {
     bv.prim_p01[e] = p01; bv.prim_p23[e] = p23; bv.prim_rad[e] = rad;
     bv.prim_box[e] = box; bv.prim_thick[e] = thick; bv.prim_meta[e] = pm;
     {
-        float cap[DVG_CAP_N * 6];
-        build_capsules(has_stroke ? (tf & DVG_PF_TYPE_MASK) : -1, p01, p23, thick, cap);
+        float cap[DVG_CAP_N * 8];
+        const int ptype = tf & DVG_PF_TYPE_MASK;
+        float rmin = thick;   // smallest control-point radius (per-point thickness) or the stroke width
+        if (tf & DVG_PF_THICK) {
+            rmin = rminf(rad.x, rad.y);
+            if (ptype >= PRIM_QUAD) rmin = rminf(rmin, rad.z);
+            if (ptype == PRIM_CUBIC) rmin = rminf(rmin, rad.w);
+        }
+        build_capsules(has_stroke ? ptype : -1, p01, p23, thick, rmin, cap);
         for (int k = 0; k < DVG_CAP_F4; k++) bv.prim_cap[(size_t)e * DVG_CAP_F4 + k] = mk4(cap[4 * k], cap[4 * k + 1], cap[4 * k + 2], cap[4 * k + 3]);
     }
     if (first_in_inst) {

@@ -20,6 +20,7 @@ namespace {
 
 thread_local std::string g_err;
 float *g_debug_out = nullptr;  // dvg_debug_set_boundary_dump
+bool g_fast_accept = false;    // dvg_set_fast_stroke_accept
 
 int fail(int code, const std::string &msg) {
     g_err = msg;
@@ -432,6 +433,7 @@ int dvg_render_forward_rows(DvgScene *s, const float *background, float *render_
     ra.width = width; ra.height = height; ra.nsx = nsx; ra.nsy = nsy; ra.seed = seed;
     ra.use_prefiltering = use_prefiltering; ra.row_begin = row_begin; ra.row_end = row_end;
     ra.background = background; ra.render_image = render_image;
+    if (g_fast_accept) ra.flags |= DVG_RF_FAST_ACCEPT;
     rc = ensure_weight(s, sc, ra, st);
     if (rc) return rc;
     if (row_begin == 0 && row_end == height)
@@ -474,7 +476,7 @@ int dvg_render_backward_rows(DvgScene *s, const float *background, const float *
     memset(&ra, 0, sizeof ra);
     ra.width = width; ra.height = height; ra.nsx = nsx; ra.nsy = nsy; ra.seed = seed;
     ra.use_prefiltering = use_prefiltering; ra.row_begin = row_begin; ra.row_end = row_end;
-    ra.flags = flags;
+    ra.flags = flags | (g_fast_accept ? DVG_RF_FAST_ACCEPT : 0u);
     ra.background = background; ra.d_render_image = d_render_image;
     ra.d_params = d_params; ra.d_background = d_background;
     ra.debug_out = g_debug_out;
@@ -503,7 +505,7 @@ int dvg_render_backward_rows(DvgScene *s, const float *background, const float *
         bw.tile_counts = s->d_tile_counts.as<int>(); bw.tile_fill = s->d_tile_fill.as<int>();
         bw.blk_counts = s->d_blk_counts.as<int>();
         bw.tile_offsets = s->d_tile_offsets.as<int>(); bw.blk_offsets = s->d_blk_offsets.as<int>();
-        bw.max_blocks = bw.num_samples / 128 + ntiles;
+        bw.max_blocks = bw.num_samples / edge_samples_per_block() + ntiles;
         launch_boundary(sc, bins, ra, bw, st);
         CK(cudaGetLastError());
     }
@@ -522,6 +524,8 @@ int dvg_render_backward(DvgScene *s, const float *background, const float *d_ren
 }
 
 int dvg_debug_set_boundary_dump(float *device_buf) { g_debug_out = device_buf; return DVG_OK; }
+
+int dvg_set_fast_stroke_accept(int on) { g_fast_accept = on != 0; return DVG_OK; }
 
 int dvg_profile_enable(int on) {
     dvg::g_profile_on = on != 0;

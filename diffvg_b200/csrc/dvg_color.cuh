@@ -24,7 +24,10 @@ struct DirectSink {   // host harness / fallback: straight into d_params
 };
 
 #if defined(__CUDACC__)
-constexpr int DVG_GC_SLOTS = 1024;  // power of two
+#ifndef DVG_GC_LOG2
+#define DVG_GC_LOG2 10
+#endif
+constexpr int DVG_GC_SLOTS = 1 << DVG_GC_LOG2;
 struct GradCache {
     int keys[DVG_GC_SLOTS];
     float vals[DVG_GC_SLOTS];
@@ -34,7 +37,7 @@ struct CacheSink {
     float *D;
     __device__ __forceinline__ void add(int idx, float v) const {
         if (v == 0.f) return;
-        unsigned h = ((unsigned)idx * 2654435761u) >> 22;  // top 10 bits
+        unsigned h = ((unsigned)idx * 2654435761u) >> (32 - DVG_GC_LOG2);
 #pragma unroll 1
         for (int probe = 0; probe < 16; probe++) {
             int k = gc->keys[h];

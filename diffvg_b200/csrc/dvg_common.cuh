@@ -205,13 +205,18 @@ DVG_HD int solve_cubic_f(float a, float b, float c, float d, float t[3]) {
         return 1;
     }
 }
-// solve.h:29-59 with T = double.
-DVG_HD int solve_cubic_d(double a, double b, double c, double d, double t[3]) {
+// solve.h:29-59 with T = double.  FAST = one division + three multiplies for the normalisation:
+// only for the isolator polynomial of the closest-point quintic, whose roots are rounded to float
+// bracket ends (dvg_geom.cuh quintic_eval note); the winding test compares the double roots with
+// 0 and 1 directly and must keep the reference's exact operation sequence.
+template <bool FAST>
+DVG_HD int solve_cubic_dt(double a, double b, double c, double d, double t[3]) {
     if (fabs(a) < 1e-6f) {
         if (solve_quadratic_d(b, c, d, &t[0], &t[1])) return 2;
         return 0;
     }
-    b /= a; c /= a; d /= a;
+    if (FAST) { const double inv_a = 1.0 / a; b *= inv_a; c *= inv_a; d *= inv_a; }
+    else { b /= a; c /= a; d /= a; }
     double Q = (b * b - 3 * c) / 9.f;
     double R = (2 * b * b * b - 9 * b * c + 27 * d) / 54.f;
     if (R * R < Q * Q * Q) {
@@ -227,6 +232,7 @@ DVG_HD int solve_cubic_d(double a, double b, double c, double d, double t[3]) {
         return 1;
     }
 }
+DVG_HD int solve_cubic_d(double a, double b, double c, double d, double t[3]) { return solve_cubic_dt<false>(a, b, c, d, t); }
 
 // ---------------------------------------------------------------- pixel filters (filter.h)
 struct Filter { int type; float radius; };

@@ -52,7 +52,14 @@ DVG_HD Quintic cubic_quintic(F2 p0, F2 p1, F2 p2, F2 p3, F2 pt) {
     double E = sum2(q1 * q1) + 2 * sum2(pp * q2);
     double F = sum2(pp * q1);
     Quintic q;
+#ifdef DVG_FMA_QUINTIC
+    // one division + five multiplies instead of five divisions (within_distance.h:168-172); the
+    // quotients differ from the reference's by <= 1 ulp of a double, see the note at quintic_eval
+    const double inv_A = 1.0 / A;
+    q.B = B * inv_A; q.C = C * inv_A; q.D = D * inv_A; q.E = E * inv_A; q.F = F * inv_A;
+#else
     q.B = B / A; q.C = C / A; q.D = D / A; q.E = E / A; q.F = F / A;
+#endif
     return q;
 }
 // within_distance.h:211-225 evaluate the monic quintic and its derivative term by term in double
@@ -76,6 +83,72 @@ DVG_HD double quintic_deriv(const Quintic &q, double t) {  // within_distance.h:
     return 5 * t * t * t * t + 4 * q.B * t * t * t + 3 * q.C * t * t + 2 * q.D * t + q.E;
 }
 #endif
+// value / derivative of the Newton update (within_distance.h:261).  The quotient only feeds a
+// float (the next iterate), so ~45 correct bits are as good as 53: reciprocal seed in float, one
+// Newton step in double.  Falls back to the IEEE division outside the float range.
+DVG_HD double newton_quotient(double value, double derivative) {
+#if defined(DVG_FMA_QUINTIC)
+    const float df = (float)derivative;
+    if (fabsf(df) > 1e-30f && fabsf(df) < 1e30f) {
+        const double r0 = (double)(1.0f / df);
+        const double r1 = fma(r0, fma(-derivative, r0, 1.0), r0);
+        return value * r1;
+    }
+#endif
+    return value / derivative;
+}
+
+// Roots of the isolator cubic (within_distance.h:194, solve.h:29-59 with T = double) for use as
+// FLOAT bracket ends.  The reference evaluates the trigonometric / Cardano closed forms in double
+// (acos, 3 x cos or pow: several hundred FP64 instructions on the GPU) and then rounds each root to
+// float.  Here: the same branch decisions in double, a float-precision closed-form estimate, and two
+// Newton steps on the normalised cubic in double.  Both land within ~1e-12 (relative to the root
+// scale) of the true root, so the rounded floats agree except when the value sits that close to a
+// float rounding boundary (~2e-5 of the roots); such a 1-ulp shift of a bracket end changes the
+// final classification only if additionally a quintic root falls inside that 1-ulp gap or the Newton
+// iterate path differs at a sample within an ulp of the stroke edge (~1e-7 each): DESIGN.md
+// "arithmetic contract" gives the measured agreement (0 of 2e8 tests).
+DVG_HD double cubic_polish(double b, double c, double d, double x) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int it = 0; it < 2; it++) {
+        const double f = fma(fma(fma(x, 1.0, b), x, c), x, d);
+        const double fp = fma(fma(3.0, x, 2.0 * b), x, c);
+        if (fp != 0.0) x -= newton_quotient(f, fp);
+    }
+    return x;
+}
+DVG_HD int isolator_roots(double a, double b, double c, double d, double t[3]) {
+    if (fabs(a) < 1e-6f) {
+        if (solve_quadratic_d(b, c, d, &t[0], &t[1])) return 2;
+        return 0;
+    }
+    { const double inv_a = 1.0 / a; b *= inv_a; c *= inv_a; d *= inv_a; }
+    const double Q = (b * b - 3 * c) / 9.f;
+    const double R = (2 * b * b * b - 9 * b * c + 27 * d) / 54.f;
+    const double Q3 = Q * Q * Q;
+    const double b3 = b / 3.0;
+    if (R * R < Q3) {
+        const float sq = sqrtf((float)Q);
+        float x = (float)R / (sq * sq * sq);
+        x = x < -1.f ? -1.f : (x > 1.f ? 1.f : x);
+        const float theta = acosf(x);
+        const float two_pi = 6.28318530717958647692f;
+        const double m2sq = -2.0 * (double)sq;
+        t[0] = cubic_polish(b, c, d, m2sq * (double)cosf(theta / 3.f) - b3);
+        t[1] = cubic_polish(b, c, d, m2sq * (double)cosf((theta + two_pi) / 3.f) - b3);
+        t[2] = cubic_polish(b, c, d, m2sq * (double)cosf((theta - two_pi) / 3.f) - b3);
+        return 3;
+    } else {
+        const float s = (float)sqrt(R * R - Q3);
+        const float Af = R > 0 ? -cbrtf((float)R + s) : cbrtf((float)(-R) + s);
+        const float Bf = fabsf(Af) > 1e-6f ? (float)Q / Af : 0.f;
+        t[0] = cubic_polish(b, c, d, (double)(Af + Bf) - b3);
+        return 1;
+    }
+}
+
 // Isolator-polynomial split points (within_distance.h:184-210).  Returns the sorted interval
 // ends.  Q10: when q_root is outside [0,1] the reference reads intervals[0]
 // uninitialised; we then use -1 ("no split point": negative entries are skipped).
@@ -86,7 +159,11 @@ DVG_HD int quintic_intervals(const Quintic &q, float intervals[4], float stale0 
     double p1D = q.F - q.B * q.E / 25.f;
     double q_root = -q.B / 5.f;
     double p_roots[3];
+#ifdef DVG_FMA_QUINTIC
+    int num_sol = isolator_roots(p1A, p1B, p1C, p1D, p_roots);
+#else
     int num_sol = solve_cubic_d(p1A, p1B, p1C, p1D, p_roots);
+#endif
     intervals[0] = stale0;
     if (q_root >= 0 && q_root <= 1) intervals[0] = (float)q_root;
     for (int j = 0; j < num_sol; j++) intervals[j + 1] = (float)p_roots[j];
@@ -113,7 +190,7 @@ DVG_HD bool quintic_root_in(const Quintic &q, float lower, float upper, float *t
         if (fabs(value) < 1e-5f || it == 19) break;
         if (value > 0.f) ub = t; else lb = t;
         double derivative = quintic_deriv(q, t);
-        t = (float)((double)t - value / derivative);
+        t = (float)((double)t - newton_quotient(value, derivative));
     }
     *t_out = t;
     return true;
@@ -185,23 +262,27 @@ DVG_HD bool stroke_hit_line(F2 p0, F2 p1, float r0, float r1, F2 pt) {
     }
 }
 
-// true  => pt is provably farther than the stroke radius from every point of the curve.
-// `cap` = DVG_CAP_N records of 6 floats (see dvg_scene.cuh).  Conservative: chord distance at a
-// slightly inexact t only over-estimates the distance by O(|d|^2 dt^2) << the 1e-2 px margin in R.
-DVG_HD bool capsule_reject(const float *cap, F2 pt) {
+// Polyline bracket test (see dvg_scene.cuh): -1 = certainly no hit, +1 = hit, 0 = undecided.
+// `cap` = DVG_CAP_N records of 8 floats.  The chord distance evaluated at a slightly inexact t only
+// over-estimates the distance by O(|d|^2 dt^2), far below the 1e-2 px margin folded into R_out / R_in.
+DVG_HD int capsule_classify(const float *cap, F2 pt) {
+    bool all_out = true, any_in = false;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
     for (int i = 0; i < DVG_CAP_N; i++) {
-        const float *c = cap + 6 * i;
+        const float *c = cap + 8 * i;
         const float wx = pt.x - c[0], wy = pt.y - c[1];
         float t = (wx * c[2] + wy * c[3]) * c[4];
         t = t < 0.f ? 0.f : (t > 1.f ? 1.f : t);
         const float ex = wx - t * c[2], ey = wy - t * c[3];
-        if (!(ex * ex + ey * ey > c[5])) return false;   // (also false for NaN)
+        const float d2 = ex * ex + ey * ey;
+        all_out = all_out && (d2 > c[5]);   // false for NaN
+        any_in = any_in || (d2 < c[6]);
     }
-    return true;
+    return all_out ? -1 : (any_in ? 1 : 0);
 }
+DVG_HD bool capsule_reject(const float *cap, F2 pt) { return capsule_classify(cap, pt) < 0; }
 
 // Stroke test of one primitive.  `r_shape` is shape.stroke_width (used by circle/rect and
 // the distance-approx path).  *decided: see stroke_hit_quad.

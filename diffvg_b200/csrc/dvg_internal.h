@@ -49,6 +49,7 @@ struct BoundaryWork {
 };
 
 void launch_peak_probe(int which, float *out, int iters, cudaStream_t st);
+int edge_samples_per_block();
 void launch_build(const BuildView &bv, cudaStream_t st);
 void launch_bin_count(const BuildView &bv, const BinBuild &bb, cudaStream_t st);
 void launch_bin_fill(const BuildView &bv, const BinBuild &bb, cudaStream_t st);

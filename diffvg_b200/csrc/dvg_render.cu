@@ -18,18 +18,22 @@
 
 namespace dvg {
 
-constexpr int RB = 256;      // threads per render block
-constexpr int CHUNK = 32;    // primitives staged per step
+#ifndef DVG_RB
+#define DVG_RB 256
+#endif
+#ifndef DVG_MINB
+#define DVG_MINB 2
+#endif
+constexpr int RB = DVG_RB;   // threads per render block (warps are independent; small blocks keep the tail short)
+constexpr int NWARP = RB / 32;
 constexpr int MAXF = DVG_MAXF;
-constexpr int MAX_TILE_PIX = 256;
 constexpr int EDGE_SPB = RB / 2;  // boundary samples per block (two lanes per sample)
 
-struct Stage {
-    F4 p01[CHUNK], p23[CHUNK], rad[CHUNK];
-    Box box[CHUNK];
-    float thick[CHUNK];
-    int tf[CHUNK], inst[CHUNK], group[CHUNK];
-    F4 cap[CHUNK * DVG_CAP_F4];
+// Per-warp scratch in shared memory for the re-packing of exact tests (see traverse()).
+struct WarpScratch {
+    unsigned int hit[32];            // [lane] bit k: stroke test of candidate k hit
+    unsigned int wind[32][4];        // [lane] 4-bit signed winding contribution of candidate k
+    unsigned short queue[32 * 32];   // work items (owner lane << 5 | candidate k)
 };
 
 // ------------------------------------------------------------------------------------------
@@ -60,43 +64,144 @@ __global__ void k_weight(SceneView sc, RenderArgs ra) {
 }
 
 // ------------------------------------------------------------------------------------------
-// The lockstep tile traversal: all threads of the block walk the tile's candidate list
-// together (staged through shared memory in chunks of CHUNK primitives) and feed it to their
-// own SampleTracer (dvg_trace.cuh), which reproduces sample_color(scene, ...) of
-// diffvg.cpp:525-653 including the EdgeQuery bookkeeping.
+// Tile traversal, one WARP at a time (no block-level barriers).  All 32 lanes (= 32 samples) walk
+// the tile's candidate list (ascending primitive id == compositing order) in chunks of 32:
+//   A  classify : lane k loads candidate k's leaf record; the records are broadcast with shuffles
+//                 and every lane runs the cheap leaf tests of the reference's three BVH levels
+//                 (SampleTracer<TM_CLASSIFY>) -> per-lane bit masks "needs exact stroke test" /
+//                 "needs exact winding test".
+//   D  solve    : the (sample, candidate) pairs that need an exact test are written to a
+//                 candidate-major queue and handed out 32 at a time, so the quintic / cubic root
+//                 solves (FP64, ~1-2 k instructions each) run with all lanes busy instead of the
+//                 1-in-4 lane occupancy of one-thread-one-sample traversal.  Curved strokes first
+//                 go through the conservative capsule early-out and the survivors are re-packed.
+//   E  consume  : every lane replays the candidates in order with its results
+//                 (SampleTracer<TM_CONSUME>): fragments, compositing, EdgeQuery bookkeeping.
+// This reproduces sample_color(scene, ...) of diffvg.cpp:525-653.
+DVG_D F2 local_point(const GroupInfo &g, F2 cpt) {
+    return (g.flags & DVG_GF_IDENTITY) ? cpt : xform_pt(g.c2s, cpt);
+}
+
 template <bool EDGE, bool RECORD>
-DVG_D void traverse(const SceneView &sc, const BinView &bins, const int tile, Stage &st,
-                    SampleTracer<EDGE, RECORD> &tr) {
+DVG_D void traverse(const SceneView &sc, const BinView &bins, const int tile, WarpScratch &ws,
+                    SampleTracer<EDGE, RECORD> &tr, const bool fast_accept) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
     const int beg = bins.offsets[tile], end = bins.offsets[tile + 1];
-    for (int base = beg; base < end; base += CHUNK) {
-        const int n = min(CHUNK, end - base);
-        __syncthreads();
-        if ((int)threadIdx.x < n) {
-            const int t = threadIdx.x;
-            const int e = bins.items[base + t];
-            st.p01[t] = sc.prim_p01[e];
-            st.p23[t] = sc.prim_p23[e];
-            st.rad[t] = sc.prim_rad[e];
-            st.box[t] = sc.prim_box[e];
-            st.thick[t] = sc.prim_thick[e];
+    const F2 cpt = tr.cpt;
+    SampleTracer<false, false> ct;  // classification-only state
+    ct.init(cpt, tr.active, mk4(0, 0, 0, 0), -1, -1, nullptr, nullptr);
+    for (int base = beg; base < end; base += 32) {
+        const int n = min(32, end - base);
+        // lane k holds candidate k
+        int e = 0, tf = 0, inst = 0, group = 0;
+        Box box; box.x0 = box.y0 = box.x1 = box.y1 = 0.f;
+        float thick = 0.f;
+        if (lane < n) {
+            e = bins.items[base + lane];
             const PrimMeta pm = sc.prim_meta[e];
-            st.tf[t] = pm.type_flags;
-            st.inst[t] = pm.inst;
-            st.group[t] = sc.insts[pm.inst].group;
+            tf = pm.type_flags; inst = pm.inst;
+            group = sc.insts[inst].group;
+            box = sc.prim_box[e];
+            thick = sc.prim_thick[e];
         }
-        if ((int)threadIdx.x < n * DVG_CAP_F4) {
-            const int t = threadIdx.x;
-            const int e = bins.items[base + t / DVG_CAP_F4];
-            st.cap[t] = sc.prim_cap[(size_t)e * DVG_CAP_F4 + t % DVG_CAP_F4];
-        }
-        __syncthreads();
-        for (int j = 0; j < n; j++) {
+        // ---- A: classify
+        unsigned need_s = 0, need_f = 0;
+        for (int k = 0; k < n; k++) {
             PrimRef pr;
-            pr.p01 = st.p01[j]; pr.p23 = st.p23[j]; pr.rad = st.rad[j]; pr.box = st.box[j];
-            pr.thick = st.thick[j]; pr.tf = st.tf[j]; pr.inst = st.inst[j]; pr.group = st.group[j];
-            pr.cap = reinterpret_cast<const float *>(&st.cap[j * DVG_CAP_F4]);
-            tr.step(sc, pr);
+            pr.box.x0 = __shfl_sync(FULL, box.x0, k); pr.box.y0 = __shfl_sync(FULL, box.y0, k);
+            pr.box.x1 = __shfl_sync(FULL, box.x1, k); pr.box.y1 = __shfl_sync(FULL, box.y1, k);
+            pr.thick = __shfl_sync(FULL, thick, k);
+            pr.tf = __shfl_sync(FULL, tf, k); pr.inst = __shfl_sync(FULL, inst, k); pr.group = __shfl_sync(FULL, group, k);
+            const int nd = ct.template step<TM_CLASSIFY>(sc, pr);
+            need_s |= (unsigned)(nd & 1) << k;
+            need_f |= (unsigned)((nd >> 1) & 1) << k;
         }
+        ws.hit[lane] = 0u;
+        ws.wind[lane][0] = 0u; ws.wind[lane][1] = 0u; ws.wind[lane][2] = 0u; ws.wind[lane][3] = 0u;
+        // ---- D (strokes, then fills)
+#pragma unroll 1
+        for (int kind = 0; kind < 2; kind++) {
+            const unsigned need = kind == 0 ? need_s : need_f;
+            if (!__any_sync(FULL, need != 0u)) continue;
+            int qn = 0;
+            for (int k = 0; k < n; k++) {  // candidate-major queue: lanes of a round mostly share the primitive
+                const bool mine = (need >> k) & 1u;
+                const unsigned m = __ballot_sync(FULL, mine);
+                if (mine) ws.queue[qn + __popc(m & lt)] = (unsigned short)((lane << 5) | k);
+                qn += __popc(m);
+            }
+            __syncwarp();
+            if (kind == 0) {
+                // D1: polyline bracket (dvg_scene.cuh): decided pairs are answered here, the rest re-packed in place
+                int wn = 0;
+                for (int r = 0; r < qn; r += 32) {
+                    const bool have = r + lane < qn;
+                    const int it = have ? ws.queue[r + lane] : 0;
+                    const int k = it & 31, owner = it >> 5;
+                    const int ek = __shfl_sync(FULL, e, k), tfk = __shfl_sync(FULL, tf, k), gk = __shfl_sync(FULL, group, k);
+                    const F2 op = mk2(__shfl_sync(FULL, cpt.x, owner), __shfl_sync(FULL, cpt.y, owner));
+                    bool keep = have;
+#ifndef DVG_NO_CAPSULE
+                    if (have) {
+                        const int ptype = tfk & DVG_PF_TYPE_MASK;
+                        if ((ptype == PRIM_CUBIC || ptype == PRIM_QUAD) && !(tfk & DVG_PF_APPROX)) {
+                            const int cls = capsule_classify(reinterpret_cast<const float *>(sc.prim_cap + (size_t)ek * DVG_CAP_F4),
+                                                             local_point(sc.groups[gk], op));
+                            // cls > 0 ("certainly inside") is trusted only in the opt-in fast mode: the
+                            // reference's solver has false negatives there (~6e-6 of the samples, Q21)
+                            // which the default mode reproduces by running the exact solve
+                            keep = cls == 0 || (cls > 0 && !fast_accept);
+                            if (cls > 0 && fast_accept) atomicOr(&ws.hit[owner], 1u << k);
+                        }
+                    }
+#endif
+                    __syncwarp();
+                    const unsigned m = __ballot_sync(FULL, keep);
+                    if (keep) ws.queue[wn + __popc(m & lt)] = (unsigned short)it;
+                    wn += __popc(m);
+                    __syncwarp();
+                }
+                qn = wn;
+            }
+            // D2: exact tests, 32 per round
+            for (int r = 0; r < qn; r += 32) {
+                const bool have = r + lane < qn;
+                const int it = have ? ws.queue[r + lane] : 0;
+                const int k = it & 31, owner = it >> 5;
+                const int ek = __shfl_sync(FULL, e, k), tfk = __shfl_sync(FULL, tf, k), gk = __shfl_sync(FULL, group, k);
+                const int ik = __shfl_sync(FULL, inst, k);
+                const F2 op = mk2(__shfl_sync(FULL, cpt.x, owner), __shfl_sync(FULL, cpt.y, owner));
+                if (have) {
+                    const F2 lp = local_point(sc.groups[gk], op);
+                    const F4 p01 = sc.prim_p01[ek], p23 = sc.prim_p23[ek];
+                    if (kind == 0) {
+                        bool decided = false;
+                        const bool h = prim_stroke_hit(tfk & DVG_PF_TYPE_MASK, (tfk & DVG_PF_APPROX) != 0, p01, p23, sc.prim_rad[ek],
+                                                       sc.insts[ik].r, lp, &decided);
+                        if (h) atomicOr(&ws.hit[owner], 1u << k);
+                    } else {
+                        const int w = prim_winding(tfk & DVG_PF_TYPE_MASK, p01, p23, lp);
+                        if (w != 0) atomicOr(&ws.wind[owner][k >> 3], (unsigned)(w & 15) << (4 * (k & 7)));
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        __syncwarp();
+        // ---- E: consume
+        const unsigned hitm = ws.hit[lane];
+        const unsigned w0 = ws.wind[lane][0], w1 = ws.wind[lane][1], w2 = ws.wind[lane][2], w3 = ws.wind[lane][3];
+        for (int k = 0; k < n; k++) {
+            PrimRef pr;
+            pr.tf = __shfl_sync(FULL, tf, k); pr.inst = __shfl_sync(FULL, inst, k); pr.group = __shfl_sync(FULL, group, k);
+            const int nd = (int)((need_s >> k) & 1u) | ((int)((need_f >> k) & 1u) << 1);
+            const unsigned ww = (k < 8 ? w0 : (k < 16 ? w1 : (k < 24 ? w2 : w3)));
+            const int nib = (int)((ww >> (4 * (k & 7))) & 15u);
+            tr.template step<TM_CONSUME>(sc, pr, nd, ((hitm >> k) & 1u) != 0u, (nib ^ 8) - 8);
+        }
+        __syncwarp();
     }
     tr.finish(sc);
 }
@@ -111,9 +216,8 @@ DVG_D float warp_sum(float v) {
 // variant: recompute the forward, then d_sample_color (diffvg.cpp:656-705), d_background and
 // the filter-radius gradient (1250-1268).
 template <bool BACKWARD>
-__global__ void __launch_bounds__(RB) k_render(SceneView sc, BinView bins, RenderArgs ra) {
-    __shared__ Stage st;
-    __shared__ float s_pix[BACKWARD ? 4 : MAX_TILE_PIX * 4];
+__global__ void __launch_bounds__(RB, DVG_MINB) k_render(SceneView sc, BinView bins, RenderArgs ra) {
+    __shared__ WarpScratch s_ws[NWARP];
     GradCache *gcp = nullptr;
     if constexpr (BACKWARD) {
         __shared__ GradCache s_gc;
@@ -122,23 +226,26 @@ __global__ void __launch_bounds__(RB) k_render(SceneView sc, BinView bins, Rende
         __syncthreads();
     }
     const CacheSink sk{gcp, ra.d_params};
+    WarpScratch &ws = s_ws[threadIdx.x >> 5];
     const int tile_row0 = ra.row_begin / bins.tile_h;
-    const int tile = blockIdx.x + tile_row0 * bins.tiles_x;
-    const int tx = tile % bins.tiles_x, ty = tile / bins.tiles_x;
     const int spp = ra.nsx * ra.nsy;
     const int npix = bins.tile_w * bins.tile_h;
     const int ns = npix * spp;
-    const int rounds = (ns + RB - 1) / RB;
+    const int parts = (ns + RB - 1) / RB;   // blocks per tile
+    const int tile = blockIdx.x / parts + tile_row0 * bins.tiles_x;
+    const int part = blockIdx.x % parts;
+    const int tx = tile % bins.tiles_x, ty = tile / bins.tiles_x;
     const int tid = threadIdx.x;
-    if (!BACKWARD) {
-        for (int i = tid; i < npix * 4; i += RB) s_pix[i] = 0.f;
-    }
+    // samples of one pixel sit in `grp` consecutive lanes when spp is a power of two (<= 32, or a
+    // multiple of 32): their splat onto the own pixel is pre-reduced with shuffles
+    const bool pow2 = (spp & (spp - 1)) == 0;
+    const int grp = pow2 ? (spp < 32 ? spp : 32) : 1;
     int fkey[BACKWARD ? MAXF : 1];
     F4 fprev[BACKWARD ? MAXF : 1];
     float d_radius_acc = 0.f;
 
-    for (int round = 0; round < rounds; round++) {
-        const int l = round * RB + tid;
+    {
+        const int l = part * RB + tid;
         const int s = l % spp, p = l / spp;
         const int px = p % bins.tile_w, py = p / bins.tile_w;
         const int x = tx * bins.tile_w + px, y = ty * bins.tile_h + py;
@@ -161,14 +268,16 @@ __global__ void __launch_bounds__(RB) k_render(SceneView sc, BinView bins, Rende
         }
         SampleTracer<false, BACKWARD> tr;
         tr.init(pos.cpt, active, first, -1, -1, fkey, fprev);
-        traverse<false, BACKWARD>(sc, bins, tile, st, tr);
+        traverse<false, BACKWARD>(sc, bins, tile, ws, tr, (ra.flags & DVG_RF_FAST_ACCEPT) != 0);
         const F4 color = tr.resolve(bg_px);
         struct { F4 accum; int nfrag, sp; } to;
         to.accum = tr.accum; to.nfrag = tr.nfrag; to.sp = tr.sp;
 
         if (!BACKWARD) {
+            // splat (diffvg.cpp:1224-1249): the sample's own pixel is reduced across the lanes of
+            // the pixel first; the (rare for box 0.5) neighbours go straight to global memory
+            F4 own = mk4(0, 0, 0, 0);
             if (active) {
-                // splat (diffvg.cpp:1224-1249)
                 const int ri = (int)ceilf(sc.filter.radius);
                 for (int dy = -ri; dy <= ri; dy++) {
                     for (int dx = -ri; dx <= ri; dx++) {
@@ -176,22 +285,30 @@ __global__ void __launch_bounds__(RB) k_render(SceneView sc, BinView bins, Rende
                         if (xx >= 0 && xx < ra.width && yy >= 0 && yy < ra.height) {
                             const float fw = filter_weight(sc.filter, (xx + 0.5f) - pos.pt.x, (yy + 0.5f) - pos.pt.y);
                             if (fw == 0.f) continue;
-                            const float ws = ra.weight_image[yy * ra.width + xx];
-                            if (!(ws > 0)) continue;
-                            const float inv_ws = 1.f / ws;  // Vector4 / scalar == * (1.f / s)
+                            const float wsum = ra.weight_image[yy * ra.width + xx];
+                            if (!(wsum > 0)) continue;
+                            const float inv_ws = 1.f / wsum;  // Vector4 / scalar == * (1.f / s)
                             const F4 wc = mk4((fw * color.x) * inv_ws, (fw * color.y) * inv_ws,
                                               (fw * color.z) * inv_ws, (fw * color.w) * inv_ws);
-                            const int lx = xx - tx * bins.tile_w, ly = yy - ty * bins.tile_h;
-                            if (lx >= 0 && lx < bins.tile_w && ly >= 0 && ly < bins.tile_h) {
-                                float *d = &s_pix[4 * (ly * bins.tile_w + lx)];
-                                atomicAdd(d + 0, wc.x); atomicAdd(d + 1, wc.y); atomicAdd(d + 2, wc.z); atomicAdd(d + 3, wc.w);
-                            } else {
+                            if (dx == 0 && dy == 0) own = wc;
+                            else {
                                 float *d = ra.render_image + 4 * (yy * ra.width + xx);
                                 atomicAdd(d + 0, wc.x); atomicAdd(d + 1, wc.y); atomicAdd(d + 2, wc.z); atomicAdd(d + 3, wc.w);
                             }
                         }
                     }
                 }
+            }
+            for (int o = grp >> 1; o > 0; o >>= 1) {
+                own.x += __shfl_xor_sync(0xffffffffu, own.x, o); own.y += __shfl_xor_sync(0xffffffffu, own.y, o);
+                own.z += __shfl_xor_sync(0xffffffffu, own.z, o); own.w += __shfl_xor_sync(0xffffffffu, own.w, o);
+            }
+            if (active && (tid & (grp - 1)) == 0) {
+                float *d = ra.render_image + 4 * (y * ra.width + x);
+                if (own.x != 0.f) atomicAdd(d + 0, own.x);
+                if (own.y != 0.f) atomicAdd(d + 1, own.y);
+                if (own.z != 0.f) atomicAdd(d + 2, own.z);
+                if (own.w != 0.f) atomicAdd(d + 3, own.w);
             }
         } else {
             // ---- interior backward.  All 32 lanes stay converged: fragments are popped in
@@ -277,21 +394,7 @@ __global__ void __launch_bounds__(RB) k_render(SceneView sc, BinView bins, Rende
             }
         }
     }
-    if (!BACKWARD) {
-        __syncthreads();
-        for (int i = tid; i < npix; i += RB) {
-            const int lx = i % bins.tile_w, ly = i / bins.tile_w;
-            const int x = tx * bins.tile_w + lx, y = ty * bins.tile_h + ly;
-            if (x < ra.width && y < ra.height) {
-                float *d = ra.render_image + 4 * (y * ra.width + x);
-                const float *s = &s_pix[4 * i];
-                if (s[0] != 0.f) atomicAdd(d + 0, s[0]);
-                if (s[1] != 0.f) atomicAdd(d + 1, s[1]);
-                if (s[2] != 0.f) atomicAdd(d + 2, s[2]);
-                if (s[3] != 0.f) atomicAdd(d + 3, s[3]);
-            }
-        }
-    } else {
+    if (BACKWARD) {
         d_radius_acc = warp_sum(d_radius_acc);
         if ((tid & 31) == 0) sk.add(sc.filter_radius_off, d_radius_acc);
         __syncthreads();
@@ -337,8 +440,8 @@ __global__ void k_boundary_scatter(BoundaryWork bw) {
 
 // Boundary pass, step 2: render_edge_kernel (diffvg.cpp:1388-1475).  One block per
 // (tile, chunk of EDGE_SPB samples); lanes 2k / 2k+1 evaluate the two sides of sample k.
-__global__ void __launch_bounds__(RB) k_edge(SceneView sc, BinView bins, RenderArgs ra, BoundaryWork bw) {
-    __shared__ Stage st;
+__global__ void __launch_bounds__(RB, DVG_MINB) k_edge(SceneView sc, BinView bins, RenderArgs ra, BoundaryWork bw) {
+    __shared__ WarpScratch s_ws[NWARP];
     __shared__ GradCache s_gc;
     __shared__ int s_tile;
     const int ntiles = bins.tiles_x * bins.tiles_y;
@@ -382,7 +485,7 @@ __global__ void __launch_bounds__(RB) k_edge(SceneView sc, BinView bins, RenderA
     }
     SampleTracer<true, false> tr;
     tr.init(cpt, active, first, q_group, q_shape, nullptr, nullptr);
-    traverse<true, false>(sc, bins, tile, st, tr);
+    traverse<true, false>(sc, bins, tile, s_ws[threadIdx.x >> 5], tr, (ra.flags & DVG_RF_FAST_ACCEPT) != 0);
     const F4 mine = tr.resolve(bg_px);
     const int my_hit = tr.q_hit() ? 1 : 0;
     F4 other;
@@ -446,9 +549,16 @@ __global__ void __launch_bounds__(RB) k_edge(SceneView sc, BinView bins, RenderA
 }
 
 // ------------------------------------------------------------------------------------------
+int edge_samples_per_block() { return EDGE_SPB; }
+
 void launch_weight(const SceneView &sc, const RenderArgs &ra, cudaStream_t st) {
     const int n = ra.width * ra.height * ra.nsx * ra.nsy;
     DVG_LAUNCH(k_weight, dim3((n + 255) / 256), dim3(256), 0, st, sc, ra);
+}
+
+static int parts_per_tile(const BinView &bins, const RenderArgs &ra) {
+    const int ns = bins.tile_w * bins.tile_h * ra.nsx * ra.nsy;
+    return (ns + RB - 1) / RB;
 }
 
 static int tile_rows_in(const BinView &bins, const RenderArgs &ra) {
@@ -458,13 +568,13 @@ static int tile_rows_in(const BinView &bins, const RenderArgs &ra) {
 }
 
 void launch_render_forward(const SceneView &sc, const BinView &bins, const RenderArgs &ra, cudaStream_t st) {
-    const int nblk = tile_rows_in(bins, ra) * bins.tiles_x;
+    const int nblk = tile_rows_in(bins, ra) * bins.tiles_x * parts_per_tile(bins, ra);
     if (nblk <= 0) return;
     DVG_LAUNCH(k_render<false>, dim3(nblk), dim3(RB), 0, st, sc, bins, ra);
 }
 
 void launch_render_backward(const SceneView &sc, const BinView &bins, const RenderArgs &ra, cudaStream_t st) {
-    const int nblk = tile_rows_in(bins, ra) * bins.tiles_x;
+    const int nblk = tile_rows_in(bins, ra) * bins.tiles_x * parts_per_tile(bins, ra);
     if (nblk <= 0) return;
     DVG_LAUNCH(k_render<true>, dim3(nblk), dim3(RB), 0, st, sc, bins, ra);
 }

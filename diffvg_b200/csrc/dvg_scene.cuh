@@ -22,13 +22,17 @@ enum PrimType { PRIM_LINE = 0, PRIM_QUAD = 1, PRIM_CUBIC = 2, PRIM_CIRCLE = 3, P
 #define DVG_PF_FIRST 0x80     // first primitive of its shape instance
 #define DVG_PF_GFIRST 0x100   // first primitive of its group
 
-// Conservative stroke-reject capsules of a curved primitive: the curve is cut into DVG_CAP_N pieces;
-// piece i lies within `dev_i` of its chord A_i -> A_i + d_i, so a point farther than
-// dev_i + max_radius (+ margin) from every chord cannot be within the stroke radius of any curve
-// point and the quintic / cubic root solve of within_distance.h:63-272 can be skipped with the
-// answer the reference would compute (false).  6 floats per piece: A.xy, d.xy, 1/|d|^2, R^2.
-#define DVG_CAP_N 4
-#define DVG_CAP_F4 6   // DVG_CAP_N * 6 floats / 4
+// Polyline bracket of a curved stroke primitive: the curve is cut into DVG_CAP_N pieces; piece i lies
+// within `dev_i` of its chord A_i -> A_i + d_i and every chord point has a curve point within dev_i.
+// With D = distance(pt, chord_i):
+//   D > max_radius + dev_i + margin for ALL i  => no curve point is within the stroke radius: the
+//       quintic / cubic root solve of within_distance.h:63-272 would return false (always exact);
+//   D < min_radius - dev_i - margin for SOME i => a curve point is within the stroke radius, i.e. the
+//       reference's closest-point solve returns true (see DESIGN.md "polyline bracket" for the
+//       measured agreement);
+//   otherwise the exact solve runs.  8 floats per piece: A.xy, d.xy, 1/|d|^2, R_out^2, R_in^2, pad.
+#define DVG_CAP_N 8
+#define DVG_CAP_F4 (2 * DVG_CAP_N)
 
 struct PrimMeta {
     int type_flags;  // PrimType | flags
@@ -99,6 +103,9 @@ struct BinView {
     const int *offsets;   // [tiles+1]
     const int *items;     // ascending primitive ids per tile
 };
+
+// RenderArgs.flags: low bits = DVG_BWD_* of the C ABI; internal bits from 16 up
+#define DVG_RF_FAST_ACCEPT (1u << 16)
 
 // Arguments of the render / boundary kernels.
 struct RenderArgs {

@@ -23,6 +23,10 @@ namespace dvg {
 
 constexpr int DVG_MAXF = 256;  // fragment capacity per sample (diffvg.cpp:542)
 
+enum { TM_IMMEDIATE = 0, TM_CLASSIFY = 1, TM_CONSUME = 2 };
+#define DVG_NEED_STROKE 1
+#define DVG_NEED_FILL 2
+
 // One staged primitive, as the tracer sees it.
 struct PrimRef {
     F4 p01, p23, rad;
@@ -119,7 +123,6 @@ struct SampleTracer {
     }
 
     DVG_HD void begin_shape(const SceneView &sc, int inst) {
-        end_shape();
         cur_inst = inst;
         const InstInfo &ii = sc.insts[inst];
         cur_shape = ii.shape;
@@ -130,38 +133,83 @@ struct SampleTracer {
         s_fill_ok = g_fill_ok && (!multi || box_inside(ii.box, lpt));
     }
 
-    // Consume one candidate primitive.  Group / shape changes are detected here; in the
-    // kernels they are uniform across the block because all threads walk the same list.
-    DVG_HD void step(const SceneView &sc, const PrimRef &pr) {
-        if (pr.group != cur_g) { end_group(sc.params); begin_group(sc, pr.group); }
-        if (pr.inst != cur_inst) begin_shape(sc, pr.inst);
+    // Consume one candidate primitive.  Group / shape changes are detected here; in the kernels
+    // they are uniform across the warp because all lanes walk the same list.
+    //
+    // Three modes (the kernels split the work so that the expensive exact tests can be
+    // re-packed across the lanes of a warp, see dvg_render.cu):
+    //   TM_IMMEDIATE  evaluate the exact predicates inline (host harness; reference order);
+    //   TM_CLASSIFY   only the cheap leaf tests: returns which exact tests this sample needs for
+    //                 this primitive (DVG_NEED_*), no compositing state is touched;
+    //   TM_CONSUME    replay with the results of the exact tests (`need`, `res_hit`, `res_wind`).
+    // Skipping a test because the shape / group was already hit (IMMEDIATE) and evaluating it
+    // anyway (CLASSIFY + CONSUME) give the same flags: hits are OR-ed, windings only summed.
+    template <int MODE>
+    DVG_HD int step(const SceneView &sc, const PrimRef &pr, int need = 0, bool res_hit = false, int res_wind = 0) {
+        if (pr.group != cur_g) {
+            if (MODE != TM_CLASSIFY) end_group(sc.params);
+            begin_group(sc, pr.group);
+        }
+        if (pr.inst != cur_inst) {
+            if (MODE != TM_CLASSIFY) end_shape();
+            begin_shape(sc, pr.inst);
+        }
         const int tf = pr.tf;
+        if (MODE == TM_CONSUME) {
+            if ((need & DVG_NEED_STROKE) && res_hit) {
+                sh_hit = true; stroke_hit = true;
+                if (EDGE && cur_g == q_group && cur_shape == q_shape) hit0 = true;  // within_distance.h:426-429
+            }
+            if (need & DVG_NEED_FILL) w_shape += res_wind;
+            return 0;
+        }
+        int out = 0;
         const bool is_q_group = EDGE && cur_g == q_group;
-        if (s_stroke_ok && !sh_hit && !sh_done && (!stroke_hit || is_q_group)) {
+        bool test_stroke = s_stroke_ok && !sh_done;
+        if (MODE == TM_IMMEDIATE) test_stroke = test_stroke && !sh_hit && (!stroke_hit || is_q_group);
+        if (test_stroke) {
             // path-BVH leaf test (within_distance.h:278-285)
             if ((tf & DVG_PF_SINGLE) || box_inside_r(pr.box, lpt, pr.thick)) {
-                bool decided = false;
-                const int ptype = tf & DVG_PF_TYPE_MASK;
-                // conservative early-out for curved segments (exact answer `false`, no root solve)
-                #ifdef DVG_NO_CAPSULE
-                const bool skip = false;
+                if (MODE == TM_CLASSIFY) {
+                    if (tf & DVG_PF_APPROX) sh_done = true;  // Q9: the reference returns after the first candidate
+                    out |= DVG_NEED_STROKE;
+                } else {
+                    bool decided = false;
+                    const int ptype = tf & DVG_PF_TYPE_MASK;
+                    // conservative early-out for curved segments (exact answer `false`, no root solve)
+#ifdef DVG_NO_CAPSULE
+                    const bool skip = false; const int cls = 0;
 #else
-                const bool skip = (ptype == PRIM_CUBIC || ptype == PRIM_QUAD) && !(tf & DVG_PF_APPROX) && capsule_reject(pr.cap, lpt);
+                    const int cls = ((ptype == PRIM_CUBIC || ptype == PRIM_QUAD) && !(tf & DVG_PF_APPROX)) ? capsule_classify(pr.cap, lpt) : 0;
+                    const bool skip = cls < 0;   // cls > 0 still runs the exact solve (default mode, see dvg_render.cu)
 #endif
-                const bool h = skip ? false : prim_stroke_hit(ptype, (tf & DVG_PF_APPROX) != 0, pr.p01, pr.p23, pr.rad,
-                                                              shape_r, lpt, &decided);
-                if (decided) sh_done = true;
-                if (h) {
-                    sh_hit = true; stroke_hit = true;
-                    if (is_q_group && cur_shape == q_shape) hit0 = true;  // within_distance.h:426-429
+#ifdef DVG_CAPSULE_STATS
+                    {
+                        bool dd = false;
+                        const bool ex = prim_stroke_hit(ptype, (tf & DVG_PF_APPROX) != 0, pr.p01, pr.p23, pr.rad, shape_r, lpt, &dd);
+                        dvg_capsule_stats(cls, ex);
+                        if (cls > 0 && !ex && ptype == PRIM_CUBIC) dvg_capsule_dump(pr.p01, pr.p23, pr.rad, lpt);
+                    }
+#endif
+                    const bool h = skip ? false : prim_stroke_hit(ptype, (tf & DVG_PF_APPROX) != 0, pr.p01, pr.p23, pr.rad,
+                                                                      shape_r, lpt, &decided);
+                    if (decided) sh_done = true;
+                    if (h) {
+                        sh_hit = true; stroke_hit = true;
+                        if (is_q_group && cur_shape == q_shape) hit0 = true;  // within_distance.h:426-429
+                    }
                 }
             }
         }
         if (s_fill_ok) {
-            if ((tf & DVG_PF_SINGLE) || box_ray_intersect(pr.box, lpt))  // winding_number.h:162-169
-                w_shape += prim_winding(tf & DVG_PF_TYPE_MASK, pr.p01, pr.p23, lpt);
+            if ((tf & DVG_PF_SINGLE) || box_ray_intersect(pr.box, lpt)) {  // winding_number.h:162-169
+                if (MODE == TM_CLASSIFY) out |= DVG_NEED_FILL;
+                else w_shape += prim_winding(tf & DVG_PF_TYPE_MASK, pr.p01, pr.p23, lpt);
+            }
         }
+        return out;
     }
+    DVG_HD void step(const SceneView &sc, const PrimRef &pr) { step<TM_IMMEDIATE>(sc, pr); }
 
     DVG_HD void finish(const SceneView &sc) { end_group(sc.params); cur_g = -1; }
 

@@ -129,6 +129,12 @@ int64_t dvg_kernel_launch_count(void);
  * TFLOP/s: the roofline denominator for this CUDA-core-bound path.
  */
 int dvg_profile_enable(int on);
+/* Opt-in speed mode (off by default; process-wide).  A sample that the polyline bracket of a curved
+ * stroke proves to be inside the stroke radius is accepted without running the reference's quintic
+ * closest-point solve.  Geometrically that answer is right, but the reference's solver has false
+ * negatives at near-tangent quintics (~6e-6 of the samples at the painterly config), so
+ * with this on roughly 20-30 pixels per 512x512 image differ from the reference by one sample's weight. */
+int dvg_set_fast_stroke_accept(int on);
 /* Test support: when non-NULL, the boundary pass also writes (contrib, hit bits, normal.xy) per boundary
  * sample index into this DEVICE buffer of 4*W*H*spp floats (sample-level parity debugging). */
 int dvg_debug_set_boundary_dump(float *device_buf);

@@ -5,6 +5,13 @@
 // It is NOT a CPU fallback: nothing in the product imports or links it, the kernels'
 // orchestration (tiles, shared memory, warp reductions) is not represented here, and the
 // product fails loudly when the CUDA library is missing.
+#ifdef DVG_CAPSULE_STATS
+#include <atomic>
+static std::atomic<long long> g_cs[6];   // [cls+1][exact]
+static inline void dvg_capsule_stats(int cls, bool ex) { g_cs[(cls + 1) * 2 + (ex ? 1 : 0)]++; }
+namespace dvg { struct F4; struct F2; }
+static void dvg_capsule_dump(const dvg::F4 &p01, const dvg::F4 &p23, const dvg::F4 &rad, const dvg::F2 &pt);
+#endif
 #include "../../diffvg_b200/csrc/dvg_common.cuh"
 #include "../../diffvg_b200/csrc/dvg_scene.cuh"
 #include "../../diffvg_b200/csrc/dvg_geom.cuh"
@@ -434,3 +441,33 @@ EXPORT void emul_debug_boundary(const int32_t *topo, const float *params, int W,
         }
     }
 }
+
+#ifdef DVG_CAPSULE_STATS
+static std::atomic<int> g_dump_left{12};
+static void dvg_capsule_dump(const F4 &p01, const F4 &p23, const F4 &rad, const F2 &pt) {
+    if (g_dump_left-- <= 0) return;
+    F2 p0 = mk2(p01.x, p01.y), p1 = mk2(p01.z, p01.w), p2 = mk2(p23.x, p23.y), p3 = mk2(p23.z, p23.w);
+    Quintic q = cubic_quintic(p0, p1, p2, p3, pt);
+    float iv[4]; int n = quintic_intervals(q, iv);
+    // brute force closest point
+    double best = 1e30, bt = 0;
+    for (int i = 0; i <= 100000; i++) { float t = i / 100000.f; F2 e = eval_cubic(p0, p1, p2, p3, t); double d = sqrt((double)dist_sq(e, pt)); if (d < best) { best = d; bt = t; } }
+    printf("FAIL pts (%.4f %.4f)(%.4f %.4f)(%.4f %.4f)(%.4f %.4f) r %.4f pt (%.5f %.5f) brute d %.5f at t %.5f | q_root %.5f intervals", p0.x, p0.y, p1.x, p1.y, p2.x, p2.y, p3.x, p3.y, rad.x, pt.x, pt.y, best, bt, -q.B / 5.f);
+    for (int j = 0; j < n; j++) printf(" %.6f", iv[j]);
+    printf(" | coeffs B %.4g C %.4g D %.4g E %.4g F %.4g\n   evals:", q.B, q.C, q.D, q.E, q.F);
+    for (int j = 0; j <= 20; j++) printf(" %.3g", quintic_eval(q, j / 20.0));
+    printf("\n   brackets:");
+    float lower = 0.f;
+    for (int j = 0; j < n + 1; j++) {
+        if (j < n && iv[j] < 0.f) continue;
+        float upper = j < n ? rminf(iv[j], 1.f) : 1.f;
+        float t; bool ok = quintic_root_in(q, lower, upper, &t);
+        printf(" [%.6f,%.6f]->%s", lower, upper, ok ? "root" : "none");
+        if (ok) { printf("(t=%.6f d=%.5f)", t, sqrt((double)dist_sq(eval_cubic(p0, p1, p2, p3, t), pt))); if (upper >= 1.f) break; lower = upper; }
+    }
+    printf("\n");
+}
+EXPORT void emul_capsule_stats(long long *out, int reset) {
+    for (int i = 0; i < 6; i++) { out[i] = g_cs[i]; if (reset) g_cs[i] = 0; }
+}
+#endif
