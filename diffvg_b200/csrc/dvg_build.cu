@@ -82,7 +82,7 @@ __global__ void k_bin(BuildView bv, BinBuild bb) {
             const GroupInfo &gi = bv.groups[g0 + gl];
             for (int e0 = gi.prim_begin; e0 < gi.prim_end; e0 += 32) {
                 int e = e0 + lane;
-                bool ph = e < gi.prim_end && overlaps(bv.prim_cbox[e], x0, y0, x1, y1);
+                bool ph = e < gi.prim_end && overlaps(bb.prefilter ? bv.prim_cbox_pf[e] : bv.prim_cbox[e], x0, y0, x1, y1);
                 unsigned pmask = __ballot_sync(0xffffffffu, ph);
                 if (PASS == 1 && ph) out[count + __popc(pmask & ((1u << lane) - 1))] = e;
                 count += __popc(pmask);

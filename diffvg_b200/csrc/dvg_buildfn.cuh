@@ -22,7 +22,7 @@ struct BuildView {
     float *seg_cdf, *seg_pmf; int *seg_point_id;
     // per instance / group / primitive
     InstInfo *insts; GroupInfo *groups;
-    F4 *prim_p01, *prim_p23, *prim_rad; Box *prim_box; float *prim_thick; PrimMeta *prim_meta; Box *prim_cbox; F4 *prim_cap;
+    F4 *prim_p01, *prim_p23, *prim_rad; Box *prim_box; float *prim_thick; PrimMeta *prim_meta; Box *prim_cbox; Box *prim_cbox_pf; F4 *prim_cap;
     float *shape_cdf, *shape_pmf;
     int *error_flag; float *total_length;
 };
@@ -361,6 +361,26 @@ DVG_HD_NOINLINE void build_prim(const BuildView &bv, int e) {
         cb.x0 = cb.y0 = -big; cb.x1 = cb.y1 = big;
     }
     bv.prim_cbox[e] = cb;
+    // Same for the SDF-prefiltering path (diffvg.cpp:835-1113): a stroked group runs an unbounded
+    // closest-point search over all its segments wherever the group is visited; a fill-only group
+    // searches within radius 1 (compute_distance(..., 1.f, ...)) and casts the winding ray.
+    Box cp;
+    if (!has_stroke && !has_fill) { cp.x0 = cp.y0 = big; cp.x1 = cp.y1 = -big; }
+    else if (has_stroke) { cp.x0 = cp.y0 = -big; cp.x1 = cp.y1 = big; }
+    else {
+        Box rp; rp.x0 = rminf(gi.local_box.x0, box.x0 - 1.f); rp.y0 = box.y0 - 1.f; rp.x1 = box.x1 + 1.f; rp.y1 = box.y1 + 1.f;
+        if (gi.flags & DVG_GF_IDENTITY) cp = rp;
+        else if (gi.flags & DVG_GF_AFFINE) cp = box_transform(gi.s2c, rp);
+        else { cp.x0 = cp.y0 = -big; cp.x1 = cp.y1 = big; }
+    }
+    if (bv.num_groups > 1) {
+        cp.x0 = rmaxf(cp.x0, gi.scene_box.x0 - gi.scene_r); cp.y0 = rmaxf(cp.y0, gi.scene_box.y0 - gi.scene_r);
+        cp.x1 = rminf(cp.x1, gi.scene_box.x1 + gi.scene_r); cp.y1 = rminf(cp.y1, gi.scene_box.y1 + gi.scene_r);
+    }
+    if (!(cp.x0 == cp.x0 && cp.x1 == cp.x1 && cp.y0 == cp.y0 && cp.y1 == cp.y1)) {
+        cp.x0 = cp.y0 = -big; cp.x1 = cp.y1 = big;
+    }
+    bv.prim_cbox_pf[e] = cp;
 }
 
 // ------------------------------------------------------------------ shape CDF (sequential part)

@@ -71,11 +71,11 @@ struct DvgScene {
     DevBuf d_topo, d_inst_group, d_inst_shape, d_inst_prim_begin, d_prim_inst, d_prim_seg, d_prim_point_id;
     // device: parameters + derived tables
     DevBuf d_params, d_shapes_length, d_shape_box, d_shape_r0, d_seg_cdf, d_seg_pmf, d_seg_point_id;
-    DevBuf d_insts, d_groups, d_p01, d_p23, d_rad, d_box, d_thick, d_meta, d_cbox, d_cap, d_shape_cdf, d_shape_pmf;
+    DevBuf d_insts, d_groups, d_p01, d_p23, d_rad, d_box, d_thick, d_meta, d_cbox, d_cbox_pf, d_cap, d_shape_cdf, d_shape_pmf;
     DevBuf d_flags;  // [0] error flag, [1] total length (float bits)
     // bins
     DevBuf d_bin_counts, d_bin_offsets, d_bin_items;
-    int bin_w = 0, bin_h = 0, bin_tw = 0, bin_th = 0;  // configuration the bins were built for (0 = none)
+    int bin_w = 0, bin_h = 0, bin_tw = 0, bin_th = 0, bin_pf = 0;  // configuration the bins were built for (0 = none)
     // per-render workspaces
     DevBuf d_weight;
     int w_w = 0, w_h = 0, w_nsx = 0, w_nsy = 0, w_ftype = -1;
@@ -102,7 +102,7 @@ struct DvgScene {
         bv.insts = d_insts.as<InstInfo>(); bv.groups = d_groups.as<GroupInfo>();
         bv.prim_p01 = d_p01.as<F4>(); bv.prim_p23 = d_p23.as<F4>(); bv.prim_rad = d_rad.as<F4>();
         bv.prim_box = d_box.as<Box>(); bv.prim_thick = d_thick.as<float>(); bv.prim_meta = d_meta.as<PrimMeta>();
-        bv.prim_cbox = d_cbox.as<Box>(); bv.prim_cap = d_cap.as<F4>();
+        bv.prim_cbox = d_cbox.as<Box>(); bv.prim_cbox_pf = d_cbox_pf.as<Box>(); bv.prim_cap = d_cap.as<F4>();
         bv.shape_cdf = d_shape_cdf.as<float>(); bv.shape_pmf = d_shape_pmf.as<float>();
         bv.error_flag = d_flags.as<int>(); bv.total_length = d_flags.as<float>() + 1;
         return bv;
@@ -117,7 +117,7 @@ struct DvgScene {
         sc.topo = d_topo.as<int>(); sc.params = d_params.as<float>();
         sc.prim_p01 = d_p01.as<F4>(); sc.prim_p23 = d_p23.as<F4>(); sc.prim_rad = d_rad.as<F4>();
         sc.prim_box = d_box.as<Box>(); sc.prim_thick = d_thick.as<float>(); sc.prim_meta = d_meta.as<PrimMeta>();
-        sc.prim_cbox = d_cbox.as<Box>(); sc.prim_cap = d_cap.as<F4>();
+        sc.prim_cbox = d_cbox.as<Box>(); sc.prim_cbox_pf = d_cbox_pf.as<Box>(); sc.prim_cap = d_cap.as<F4>();
         sc.insts = d_insts.as<InstInfo>(); sc.groups = d_groups.as<GroupInfo>();
         sc.shapes_length = d_shapes_length.as<float>();
         sc.shape_cdf = d_shape_cdf.as<float>(); sc.shape_pmf = d_shape_pmf.as<float>();
@@ -135,7 +135,7 @@ struct DvgScene {
     void release_all() {
         DevBuf *all[] = {&d_topo, &d_inst_group, &d_inst_shape, &d_inst_prim_begin, &d_prim_inst, &d_prim_seg,
                          &d_prim_point_id, &d_params, &d_shapes_length, &d_shape_box, &d_shape_r0, &d_seg_cdf, &d_seg_pmf,
-                         &d_seg_point_id, &d_insts, &d_groups, &d_p01, &d_p23, &d_rad, &d_box, &d_thick, &d_meta, &d_cbox, &d_cap,
+                         &d_seg_point_id, &d_insts, &d_groups, &d_p01, &d_p23, &d_rad, &d_box, &d_thick, &d_meta, &d_cbox, &d_cbox_pf, &d_cap,
                          &d_shape_cdf, &d_shape_pmf, &d_flags, &d_bin_counts, &d_bin_offsets, &d_bin_items, &d_weight,
                          &d_keys, &d_tile_counts, &d_tile_offsets, &d_tile_fill, &d_blk_counts, &d_blk_offsets, &d_sorted};
         for (DevBuf *b : all) b->release();
@@ -256,12 +256,12 @@ int finish_build(DvgScene *s, cudaStream_t st) {
     return DVG_OK;
 }
 
-int ensure_bins(DvgScene *s, int width, int height, int spp, cudaStream_t st) {
+int ensure_bins(DvgScene *s, int width, int height, int spp, int pf, cudaStream_t st) {
     int tw, th;
     choose_tile(spp, &tw, &th);
-    if (s->bin_w == width && s->bin_h == height && s->bin_tw == tw && s->bin_th == th) return DVG_OK;
+    if (s->bin_w == width && s->bin_h == height && s->bin_tw == tw && s->bin_th == th && s->bin_pf == pf) return DVG_OK;
     BinBuild bb;
-    bb.width = width; bb.height = height; bb.tile_w = tw; bb.tile_h = th;
+    bb.width = width; bb.height = height; bb.tile_w = tw; bb.tile_h = th; bb.prefilter = pf;
     bb.tiles_x = (width + tw - 1) / tw; bb.tiles_y = (height + th - 1) / th;
     const int ntiles = bb.tiles_x * bb.tiles_y;
     CK(s->d_bin_counts.ensure(sizeof(int) * ntiles));
@@ -276,7 +276,7 @@ int ensure_bins(DvgScene *s, int width, int height, int spp, cudaStream_t st) {
     bb.items = s->d_bin_items.as<int>();
     launch_bin_fill(bv, bb, st);
     CK(cudaGetLastError());
-    s->bin_w = width; s->bin_h = height; s->bin_tw = tw; s->bin_th = th;
+    s->bin_w = width; s->bin_h = height; s->bin_tw = tw; s->bin_th = th; s->bin_pf = pf;
     return DVG_OK;
 }
 
@@ -375,7 +375,7 @@ int dvg_scene_create(const int32_t *topo, int64_t topo_len, int device, DvgScene
     ens(s->d_seg_cdf, 4 * nsg); ens(s->d_seg_pmf, 4 * nsg); ens(s->d_seg_point_id, 4 * nsg);
     ens(s->d_insts, sizeof(InstInfo) * ni); ens(s->d_groups, sizeof(GroupInfo) * ng);
     ens(s->d_p01, 16 * npr); ens(s->d_p23, 16 * npr); ens(s->d_rad, 16 * npr); ens(s->d_box, 16 * npr);
-    ens(s->d_thick, 4 * npr); ens(s->d_meta, sizeof(PrimMeta) * npr); ens(s->d_cbox, 16 * npr); ens(s->d_cap, 16 * DVG_CAP_F4 * npr);
+    ens(s->d_thick, 4 * npr); ens(s->d_meta, sizeof(PrimMeta) * npr); ens(s->d_cbox, 16 * npr); ens(s->d_cbox_pf, 16 * npr); ens(s->d_cap, 16 * DVG_CAP_F4 * npr);
     ens(s->d_shape_cdf, 4 * ni); ens(s->d_shape_pmf, 4 * ni); ens(s->d_flags, 16);
     if (!rc && cudaMallocHost((void **)&s->h_pinned, 64) != cudaSuccess) rc = fail(DVG_ERR_CUDA, "cudaMallocHost failed");
     if (rc) { s->release_all(); delete s; return rc; }
@@ -412,21 +412,27 @@ int dvg_scene_set_params(DvgScene *s, const float *params, int64_t num_params, i
     return DVG_OK;
 }
 
-int dvg_render_forward_rows(DvgScene *s, const float *background, float *render_image,
-                            int width, int height, int nsx, int nsy, uint64_t seed,
-                            int use_prefiltering, int row_begin, int row_end, void *stream) {
+static int sdf_args_check(const float *eval_positions, int num_eval_positions) {
+    if ((eval_positions != nullptr) != (num_eval_positions > 0) || num_eval_positions < 0)
+        return fail(DVG_ERR_INVALID, "eval_positions and num_eval_positions must be given together");
+    return DVG_OK;
+}
+
+static int render_forward_impl(DvgScene *s, const float *background, float *render_image, float *render_sdf,
+                               int width, int height, int nsx, int nsy, uint64_t seed, int use_prefiltering,
+                               const float *eval_positions, int num_eval_positions, int row_begin, int row_end, void *stream) {
     int rc = check_render_args(s, width, height, nsx, nsy);
     if (rc) return rc;
-    if (!render_image) return fail(DVG_ERR_INVALID, "render_image is null");
-    if (use_prefiltering) return fail(DVG_ERR_UNSUPPORTED, "use_prefiltering is not implemented yet in this build");
+    if (!render_image && !render_sdf) return fail(DVG_ERR_INVALID, "render_image and render_sdf are both null");
+    rc = sdf_args_check(eval_positions, num_eval_positions);
+    if (rc) return rc;
+    // diffvg.cpp:1504-1520: no weight image exists with eval_positions, so colour output is impossible there
+    if (eval_positions && render_image) return fail(DVG_ERR_INVALID, "eval_positions can only be used with the SDF output");
     if (row_begin < 0 || row_end > height || row_begin > row_end) return fail(DVG_ERR_INVALID, "bad row range");
     DeviceGuard guard(s->device);
     cudaStream_t st = (cudaStream_t)stream;
     rc = finish_build(s, st);
     if (rc) return rc;
-    rc = ensure_bins(s, width, height, nsx * nsy, st);
-    if (rc) return rc;
-    if (row_begin % s->bin_th != 0) return fail(DVG_ERR_INVALID, "row_begin must be a multiple of the tile height");
     SceneView sc = s->view();
     RenderArgs ra;
     memset(&ra, 0, sizeof ra);
@@ -434,93 +440,136 @@ int dvg_render_forward_rows(DvgScene *s, const float *background, float *render_
     ra.use_prefiltering = use_prefiltering; ra.row_begin = row_begin; ra.row_end = row_end;
     ra.background = background; ra.render_image = render_image;
     if (g_fast_accept) ra.flags |= DVG_RF_FAST_ACCEPT;
-    rc = ensure_weight(s, sc, ra, st);
-    if (rc) return rc;
-    if (row_begin == 0 && row_end == height)
-        CK(cudaMemsetAsync(render_image, 0, sizeof(float) * 4 * (size_t)width * height, st));
-    else
+    if (render_image) {
+        rc = ensure_bins(s, width, height, nsx * nsy, use_prefiltering ? 1 : 0, st);
+        if (rc) return rc;
+        if (row_begin % s->bin_th != 0) return fail(DVG_ERR_INVALID, "row_begin must be a multiple of the tile height");
+        rc = ensure_weight(s, sc, ra, st);
+        if (rc) return rc;
         CK(cudaMemsetAsync(render_image + 4 * (size_t)row_begin * width, 0, sizeof(float) * 4 * (size_t)width * (row_end - row_begin), st));
-    launch_render_forward(sc, s->bin_view(), ra, st);
-    CK(cudaGetLastError());
+        if (use_prefiltering) launch_render_pf_forward(sc, s->bin_view(), ra, st);
+        else launch_render_forward(sc, s->bin_view(), ra, st);
+        CK(cudaGetLastError());
+    }
+    if (render_sdf) {
+        if (row_begin != 0 || row_end != height) return fail(DVG_ERR_UNSUPPORTED, "the SDF output is not row-sharded");
+        SdfArgs sa;
+        sa.sdf = render_sdf; sa.d_sdf = nullptr; sa.eval_positions = eval_positions; sa.num_eval = num_eval_positions;
+        const size_t n_out = eval_positions ? (size_t)num_eval_positions : (size_t)width * height;
+        CK(cudaMemsetAsync(render_sdf, 0, sizeof(float) * n_out, st));
+        launch_sdf(sc, ra, sa, false, st);
+        CK(cudaGetLastError());
+    }
     return DVG_OK;
+}
+
+int dvg_render_forward_rows(DvgScene *s, const float *background, float *render_image,
+                            int width, int height, int nsx, int nsy, uint64_t seed,
+                            int use_prefiltering, int row_begin, int row_end, void *stream) {
+    if (!render_image) return fail(DVG_ERR_INVALID, "render_image is null");
+    return render_forward_impl(s, background, render_image, nullptr, width, height, nsx, nsy, seed, use_prefiltering,
+                               nullptr, 0, row_begin, row_end, stream);
 }
 
 int dvg_render_forward(DvgScene *s, const float *background, float *render_image, float *render_sdf,
                        int width, int height, int nsx, int nsy, uint64_t seed,
                        int use_prefiltering, const float *eval_positions, int num_eval_positions, void *stream) {
-    if (render_sdf || eval_positions || num_eval_positions)
-        return fail(DVG_ERR_UNSUPPORTED, "SDF output / eval_positions are not implemented yet in this build");
-    return dvg_render_forward_rows(s, background, render_image, width, height, nsx, nsy, seed, use_prefiltering, 0, height, stream);
+    return render_forward_impl(s, background, render_image, render_sdf, width, height, nsx, nsy, seed, use_prefiltering,
+                               eval_positions, num_eval_positions, 0, height, stream);
 }
 
-int dvg_render_backward_rows(DvgScene *s, const float *background, const float *d_render_image,
-                             int width, int height, int nsx, int nsy, uint64_t seed,
-                             int use_prefiltering, int row_begin, int row_end,
-                             float *d_params, float *d_background, uint32_t flags, void *stream) {
+static int render_backward_impl(DvgScene *s, const float *background, const float *d_render_image, const float *d_render_sdf,
+                                int width, int height, int nsx, int nsy, uint64_t seed, int use_prefiltering,
+                                const float *eval_positions, int num_eval_positions, int row_begin, int row_end,
+                                float *d_params, float *d_background, float *d_translation, uint32_t flags, void *stream) {
     int rc = check_render_args(s, width, height, nsx, nsy);
     if (rc) return rc;
-    if (!d_render_image || !d_params) return fail(DVG_ERR_INVALID, "d_render_image / d_params is null");
-    if (((uintptr_t)d_render_image & 15) != 0) return fail(DVG_ERR_INVALID, "d_render_image must be 16-byte aligned");
-    if (use_prefiltering) return fail(DVG_ERR_UNSUPPORTED, "use_prefiltering is not implemented yet in this build");
+    if (!d_params) return fail(DVG_ERR_INVALID, "d_params is null");
+    if (!d_render_image && !d_render_sdf) return fail(DVG_ERR_INVALID, "d_render_image and d_render_sdf are both null");
+    if (d_render_image && ((uintptr_t)d_render_image & 15) != 0) return fail(DVG_ERR_INVALID, "d_render_image must be 16-byte aligned");
+    rc = sdf_args_check(eval_positions, num_eval_positions);
+    if (rc) return rc;
+    if (eval_positions && d_render_image) return fail(DVG_ERR_INVALID, "eval_positions can only be used with the SDF output");
     if (row_begin < 0 || row_end > height || row_begin > row_end) return fail(DVG_ERR_INVALID, "bad row range");
+    const bool whole = row_begin == 0 && row_end == height;
+    if (!whole && (d_render_sdf || d_translation)) return fail(DVG_ERR_UNSUPPORTED, "the SDF output / d_translation are not row-sharded");
     DeviceGuard guard(s->device);
     cudaStream_t st = (cudaStream_t)stream;
     rc = finish_build(s, st);
     if (rc) return rc;
-    rc = ensure_bins(s, width, height, nsx * nsy, st);
-    if (rc) return rc;
-    if (row_begin % s->bin_th != 0) return fail(DVG_ERR_INVALID, "row_begin must be a multiple of the tile height");
     SceneView sc = s->view();
-    BinView bins = s->bin_view();
     RenderArgs ra;
     memset(&ra, 0, sizeof ra);
     ra.width = width; ra.height = height; ra.nsx = nsx; ra.nsy = nsy; ra.seed = seed;
     ra.use_prefiltering = use_prefiltering; ra.row_begin = row_begin; ra.row_end = row_end;
     ra.flags = flags | (g_fast_accept ? DVG_RF_FAST_ACCEPT : 0u);
     ra.background = background; ra.d_render_image = d_render_image;
-    ra.d_params = d_params; ra.d_background = d_background;
+    ra.d_params = d_params; ra.d_background = d_background; ra.d_translation = d_translation;
     ra.debug_out = g_debug_out;
-    rc = ensure_weight(s, sc, ra, st);
-    if (rc) return rc;
     if (!(flags & DVG_BWD_ACCUMULATE)) CK(cudaMemsetAsync(d_params, 0, sizeof(float) * s->num_params, st));
-    if (d_background) {
-        if (row_begin == 0 && row_end == height) CK(cudaMemsetAsync(d_background, 0, sizeof(float) * 4 * (size_t)width * height, st));
-        else CK(cudaMemsetAsync(d_background + 4 * (size_t)row_begin * width, 0, sizeof(float) * 4 * (size_t)width * (row_end - row_begin), st));
+    if (d_background)
+        CK(cudaMemsetAsync(d_background + 4 * (size_t)row_begin * width, 0, sizeof(float) * 4 * (size_t)width * (row_end - row_begin), st));
+    if (d_translation) CK(cudaMemsetAsync(d_translation, 0, sizeof(float) * 2 * (size_t)width * height, st));
+    if (d_render_image) {
+        rc = ensure_bins(s, width, height, nsx * nsy, use_prefiltering ? 1 : 0, st);
+        if (rc) return rc;
+        if (row_begin % s->bin_th != 0) return fail(DVG_ERR_INVALID, "row_begin must be a multiple of the tile height");
+        BinView bins = s->bin_view();
+        rc = ensure_weight(s, sc, ra, st);
+        if (rc) return rc;
+        if (use_prefiltering) {
+            // interior term only: the SDF coverage is differentiable, no boundary pass (diffvg.cpp:1558)
+            launch_render_pf_backward(sc, bins, ra, st);
+            CK(cudaGetLastError());
+        } else {
+            launch_render_backward(sc, bins, ra, st);
+            CK(cudaGetLastError());
+            // boundary term (diffvg.cpp:1558-1626): boundary-sample indices of the owned rows
+            const int spp = nsx * nsy;
+            const int ntiles = bins.tiles_x * bins.tiles_y;
+            BoundaryWork bw;
+            bw.sample_begin = row_begin * width * spp;
+            bw.num_samples = (row_end - row_begin) * width * spp;
+            if (bw.num_samples > 0) {
+                CK(s->d_keys.ensure(sizeof(int) * (size_t)bw.num_samples));
+                CK(s->d_sorted.ensure(sizeof(int) * (size_t)bw.num_samples));
+                CK(s->d_tile_counts.ensure(sizeof(int) * ntiles)); CK(s->d_tile_fill.ensure(sizeof(int) * ntiles));
+                CK(s->d_blk_counts.ensure(sizeof(int) * ntiles));
+                CK(s->d_tile_offsets.ensure(sizeof(int) * (ntiles + 1))); CK(s->d_blk_offsets.ensure(sizeof(int) * (ntiles + 1)));
+                bw.keys = s->d_keys.as<int>(); bw.sorted_idx = s->d_sorted.as<int>();
+                bw.tile_counts = s->d_tile_counts.as<int>(); bw.tile_fill = s->d_tile_fill.as<int>();
+                bw.blk_counts = s->d_blk_counts.as<int>();
+                bw.tile_offsets = s->d_tile_offsets.as<int>(); bw.blk_offsets = s->d_blk_offsets.as<int>();
+                bw.max_blocks = bw.num_samples / edge_samples_per_block() + ntiles;
+                launch_boundary(sc, bins, ra, bw, st);
+                CK(cudaGetLastError());
+            }
+        }
     }
-    launch_render_backward(sc, bins, ra, st);
-    CK(cudaGetLastError());
-    // boundary term (diffvg.cpp:1558-1626): boundary-sample indices of the owned rows
-    const int spp = nsx * nsy;
-    const int ntiles = bins.tiles_x * bins.tiles_y;
-    BoundaryWork bw;
-    bw.sample_begin = row_begin * width * spp;
-    bw.num_samples = (row_end - row_begin) * width * spp;
-    if (bw.num_samples > 0) {
-        CK(s->d_keys.ensure(sizeof(int) * (size_t)bw.num_samples));
-        CK(s->d_sorted.ensure(sizeof(int) * (size_t)bw.num_samples));
-        CK(s->d_tile_counts.ensure(sizeof(int) * ntiles)); CK(s->d_tile_fill.ensure(sizeof(int) * ntiles));
-        CK(s->d_blk_counts.ensure(sizeof(int) * ntiles));
-        CK(s->d_tile_offsets.ensure(sizeof(int) * (ntiles + 1))); CK(s->d_blk_offsets.ensure(sizeof(int) * (ntiles + 1)));
-        bw.keys = s->d_keys.as<int>(); bw.sorted_idx = s->d_sorted.as<int>();
-        bw.tile_counts = s->d_tile_counts.as<int>(); bw.tile_fill = s->d_tile_fill.as<int>();
-        bw.blk_counts = s->d_blk_counts.as<int>();
-        bw.tile_offsets = s->d_tile_offsets.as<int>(); bw.blk_offsets = s->d_blk_offsets.as<int>();
-        bw.max_blocks = bw.num_samples / edge_samples_per_block() + ntiles;
-        launch_boundary(sc, bins, ra, bw, st);
+    if (d_render_sdf) {
+        SdfArgs sa;
+        sa.sdf = nullptr; sa.d_sdf = d_render_sdf; sa.eval_positions = eval_positions; sa.num_eval = num_eval_positions;
+        launch_sdf(sc, ra, sa, true, st);
         CK(cudaGetLastError());
     }
     return DVG_OK;
+}
+
+int dvg_render_backward_rows(DvgScene *s, const float *background, const float *d_render_image,
+                             int width, int height, int nsx, int nsy, uint64_t seed,
+                             int use_prefiltering, int row_begin, int row_end,
+                             float *d_params, float *d_background, uint32_t flags, void *stream) {
+    if (!d_render_image) return fail(DVG_ERR_INVALID, "d_render_image is null");
+    return render_backward_impl(s, background, d_render_image, nullptr, width, height, nsx, nsy, seed, use_prefiltering,
+                                nullptr, 0, row_begin, row_end, d_params, d_background, nullptr, flags, stream);
 }
 
 int dvg_render_backward(DvgScene *s, const float *background, const float *d_render_image, const float *d_render_sdf,
                         int width, int height, int nsx, int nsy, uint64_t seed,
                         int use_prefiltering, const float *eval_positions, int num_eval_positions,
                         float *d_params, float *d_background, float *d_translation, uint32_t flags, void *stream) {
-    if (d_render_sdf || eval_positions || num_eval_positions)
-        return fail(DVG_ERR_UNSUPPORTED, "SDF output / eval_positions are not implemented yet in this build");
-    if (d_translation) return fail(DVG_ERR_UNSUPPORTED, "d_translation is not implemented yet in this build");
-    return dvg_render_backward_rows(s, background, d_render_image, width, height, nsx, nsy, seed, use_prefiltering,
-                                    0, height, d_params, d_background, flags, stream);
+    return render_backward_impl(s, background, d_render_image, d_render_sdf, width, height, nsx, nsy, seed, use_prefiltering,
+                                eval_positions, num_eval_positions, 0, height, d_params, d_background, d_translation, flags, stream);
 }
 
 int dvg_debug_set_boundary_dump(float *device_buf) { g_debug_out = device_buf; return DVG_OK; }

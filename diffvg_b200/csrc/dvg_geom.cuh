@@ -8,6 +8,15 @@
 
 namespace dvg {
 
+#ifdef DVG_FMA_QUINTIC
+#ifndef DVG_FQ_SELECT
+#define DVG_FQ_HORNER
+#define DVG_FQ_RECIP
+#define DVG_FQ_NEWTON
+#define DVG_FQ_ISOL
+#endif
+#endif
+
 DVG_HD F2 eval_quad(F2 p0, F2 p1, F2 p2, float t) {  // within_distance.h:75-78
     float tt = 1 - t;
     return (tt * tt) * p0 + (2 * tt * t) * p1 + (t * t) * p2;
@@ -52,7 +61,7 @@ DVG_HD Quintic cubic_quintic(F2 p0, F2 p1, F2 p2, F2 p3, F2 pt) {
     double E = sum2(q1 * q1) + 2 * sum2(pp * q2);
     double F = sum2(pp * q1);
     Quintic q;
-#ifdef DVG_FMA_QUINTIC
+#ifdef DVG_FQ_RECIP
     // one division + five multiplies instead of five divisions (within_distance.h:168-172); the
     // quotients differ from the reference's by <= 1 ulp of a double, see the note at quintic_eval
     const double inv_A = 1.0 / A;
@@ -68,7 +77,7 @@ DVG_HD Quintic cubic_quintic(F2 p0, F2 p1, F2 p2, F2 p3, F2 pt) {
 // against 1e-5 / 0, so the float iterates -- and hence the classification -- are identical except
 // when a double lands within ~1e-9 relative of a float rounding boundary (DESIGN.md "arithmetic
 // contract"; checked bit-for-bit against the reference on the full-size configs).
-#ifdef DVG_FMA_QUINTIC
+#ifdef DVG_FQ_HORNER
 DVG_HD double quintic_eval(const Quintic &q, double t) {
     return fma(fma(fma(fma(t + q.B, t, q.C), t, q.D), t, q.E), t, q.F);
 }
@@ -87,7 +96,7 @@ DVG_HD double quintic_deriv(const Quintic &q, double t) {  // within_distance.h:
 // float (the next iterate), so ~45 correct bits are as good as 53: reciprocal seed in float, one
 // Newton step in double.  Falls back to the IEEE division outside the float range.
 DVG_HD double newton_quotient(double value, double derivative) {
-#if defined(DVG_FMA_QUINTIC)
+#if defined(DVG_FQ_NEWTON)
     const float df = (float)derivative;
     if (fabsf(df) > 1e-30f && fabsf(df) < 1e30f) {
         const double r0 = (double)(1.0f / df);
@@ -152,6 +161,11 @@ DVG_HD int isolator_roots(double a, double b, double c, double d, double t[3]) {
 // Isolator-polynomial split points (within_distance.h:184-210).  Returns the sorted interval
 // ends.  Q10: when q_root is outside [0,1] the reference reads intervals[0]
 // uninitialised; we then use -1 ("no split point": negative entries are skipped).
+// EXACT_ISOLATOR: the distance queries (dvg_distance.cuh) feed the root parameter into a continuous
+// output, so a quintic root the reference finds (or misses) because of where its isolator split points
+// fall must be found (or missed) here too; they evaluate the isolator cubic with the reference's own
+// closed form.  The stroke classification only needs hit / no hit and uses the fast roots.
+template <bool EXACT_ISOLATOR = false>
 DVG_HD int quintic_intervals(const Quintic &q, float intervals[4], float stale0 = -1.f) {
     double p1A = ((2 / 5.f) * q.C - (4 / 25.f) * q.B * q.B);
     double p1B = ((3 / 5.f) * q.D - (3 / 25.f) * q.B * q.C);
@@ -159,8 +173,8 @@ DVG_HD int quintic_intervals(const Quintic &q, float intervals[4], float stale0 
     double p1D = q.F - q.B * q.E / 25.f;
     double q_root = -q.B / 5.f;
     double p_roots[3];
-#ifdef DVG_FMA_QUINTIC
-    int num_sol = isolator_roots(p1A, p1B, p1C, p1D, p_roots);
+#ifdef DVG_FQ_ISOL
+    int num_sol = EXACT_ISOLATOR ? solve_cubic_d(p1A, p1B, p1C, p1D, p_roots) : isolator_roots(p1A, p1B, p1C, p1D, p_roots);
 #else
     int num_sol = solve_cubic_d(p1A, p1B, p1C, p1D, p_roots);
 #endif

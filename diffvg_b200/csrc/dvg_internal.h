@@ -8,6 +8,7 @@
 #include "dvg_color.cuh"
 #include "dvg_boundary.cuh"
 #include "dvg_trace.cuh"
+#include "dvg_distance.cuh"
 #include "dvg_buildfn.cuh"
 
 namespace dvg {
@@ -30,6 +31,7 @@ void prof_end(cudaStream_t st);
 
 struct BinBuild {
     int width, height, tile_w, tile_h, tiles_x, tiles_y;
+    int prefilter;  // 1: bin with prim_cbox_pf (SDF-prefiltering candidate regions)
     int *counts;   // [tiles]
     int *offsets;  // [tiles+1]
     int *items;    // [capacity]
@@ -48,6 +50,14 @@ struct BoundaryWork {
     int max_blocks;
 };
 
+// SDF output (OutputType.sdf): device pointers, NULL = absent
+struct SdfArgs {
+    float *sdf;                   // [H*W] or [num_eval]
+    const float *d_sdf;           // backward input, same shape
+    const float *eval_positions;  // [2*num_eval] or null
+    int num_eval;
+};
+
 void launch_peak_probe(int which, float *out, int iters, cudaStream_t st);
 int edge_samples_per_block();
 void launch_build(const BuildView &bv, cudaStream_t st);
@@ -58,6 +68,9 @@ void launch_scan(const int *in, int *out, int n, cudaStream_t st);
 void launch_weight(const SceneView &sc, const RenderArgs &ra, cudaStream_t st);
 void launch_render_forward(const SceneView &sc, const BinView &bins, const RenderArgs &ra, cudaStream_t st);
 void launch_render_backward(const SceneView &sc, const BinView &bins, const RenderArgs &ra, cudaStream_t st);
+void launch_render_pf_forward(const SceneView &sc, const BinView &bins, const RenderArgs &ra, cudaStream_t st);
+void launch_render_pf_backward(const SceneView &sc, const BinView &bins, const RenderArgs &ra, cudaStream_t st);
+void launch_sdf(const SceneView &sc, const RenderArgs &ra, const SdfArgs &sa, bool backward, cudaStream_t st);
 void launch_boundary(const SceneView &sc, const BinView &bins, const RenderArgs &ra, const BoundaryWork &bw, cudaStream_t st);
 
 }  // namespace dvg

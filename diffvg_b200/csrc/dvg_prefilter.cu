@@ -1,0 +1,202 @@
+// dvg_prefilter.cu -- the SDF-prefiltering variant of the render kernel
+// (sample_color_prefiltered, diffvg.cpp:835-1113; selected by use_prefiltering) and the SDF
+// output (sample_distance, diffvg.cpp:709-775; OutputType.sdf / eval_positions).
+//
+// Same tiling as dvg_render.cu: a block owns (part of) a pixel tile, a thread owns one sample and
+// walks the tile's candidate list (prefilter bins: a stroked group contributes all its segments
+// wherever the group is visited, because its closest-point search is unbounded; a fill-only
+// group the segments within radius 1 plus those its winding ray can cross).  Per sample the state
+// is PrefilterTracer (dvg_distance.cuh); the backward variant keeps the <= 64 fragment records
+// of the reference in local memory and scatters through the block's shared-memory GradCache.
+#include "dvg_internal.h"
+#include "dvg_kernel_util.cuh"
+
+namespace dvg {
+
+constexpr int PB = 256;  // threads per block
+
+DVG_D PrimRef load_prim(const SceneView &sc, int e) {
+    PrimRef pr;
+    const PrimMeta pm = sc.prim_meta[e];
+    pr.p01 = sc.prim_p01[e]; pr.p23 = sc.prim_p23[e];
+    pr.rad = mk4(0, 0, 0, 0);
+    pr.box = sc.prim_box[e]; pr.thick = 0.f;
+    pr.tf = pm.type_flags; pr.inst = pm.inst; pr.group = sc.insts[pm.inst].group;
+    pr.base_id = pm.base_id; pr.point_id = pm.point_id;
+    pr.cap = nullptr;
+    return pr;
+}
+
+template <bool BACKWARD>
+__global__ void __launch_bounds__(PB) k_render_pf(SceneView sc, BinView bins, RenderArgs ra) {
+    GradCache *gcp = nullptr;
+    if constexpr (BACKWARD) {
+        __shared__ GradCache s_gc;
+        gcp = &s_gc;
+        grad_cache_init(s_gc);
+        __syncthreads();
+    }
+    const CacheSink sk{gcp, ra.d_params};
+    const int tile_row0 = ra.row_begin / bins.tile_h;
+    const int spp = ra.nsx * ra.nsy;
+    const int ns = bins.tile_w * bins.tile_h * spp;
+    const int parts = (ns + PB - 1) / PB;
+    const int tile = blockIdx.x / parts + tile_row0 * bins.tiles_x;
+    const int part = blockIdx.x % parts;
+    const int tx = tile % bins.tiles_x, ty = tile / bins.tiles_x;
+    const int tid = threadIdx.x;
+    const bool pow2 = (spp & (spp - 1)) == 0;
+    const int grp = pow2 ? (spp < 32 ? spp : 32) : 1;
+    PfFragment frags[BACKWARD ? DVG_MAXPF : 1];
+    float d_radius_acc = 0.f;
+
+    const int l = part * PB + tid;
+    const int s = l % spp, p = l / spp;
+    const int px = p % bins.tile_w, py = p / bins.tile_w;
+    const int x = tx * bins.tile_w + px, y = ty * bins.tile_h + py;
+    const bool active = l < ns && x < ra.width && y < ra.height && y >= ra.row_begin && y < ra.row_end;
+    F2 pt = mk2(0, 0), cpt = mk2(0, 0);
+    const float *bg_px = nullptr;
+    F4 first = mk4(0, 0, 0, 0);
+    if (active) {
+        const int sx = s % ra.nsx, sy = s / ra.nsx;
+        const int idx = ((y * ra.width + x) * ra.nsy + sy) * ra.nsx + sx;
+        sample_position(sc.canvas_w, sc.canvas_h, ra.width, ra.height, ra.nsx, ra.nsy, ra.seed, true, x, y, sx, sy, idx, pt, cpt);
+        if (ra.background) {
+            bg_px = ra.background + 4 * (y * ra.width + x);
+            first = mk4(bg_px[0], bg_px[1], bg_px[2], bg_px[3]);
+        }
+    }
+    PrefilterTracer<BACKWARD> tr;
+    tr.init(cpt, active, first, frags);
+    const int beg = bins.offsets[tile], end = bins.offsets[tile + 1];
+    for (int i = beg; i < end; i++) {
+        const PrimRef pr = load_prim(sc, bins.items[i]);   // block-uniform loads
+        tr.step(sc, pr);
+    }
+    tr.finish(sc);
+    const F4 color = tr.resolve(bg_px);
+    if constexpr (!BACKWARD) {
+        splat_color(sc, ra, x, y, pt, color, active, grp, tid);
+    } else {
+        if (active) {
+            const F4 d_color = gather_d_color(sc.filter, ra.d_render_image, ra.weight_image, ra.width, ra.height, pt);
+            float *dtr = ra.d_translation ? ra.d_translation + 2 * (y * ra.width + x) : nullptr;
+            if (tr.nfrag > 0) {
+                F4 d_bg;
+                prefilter_backward(sc, tr, color, d_color, sk, dtr, d_bg);
+                if (bg_px && ra.d_background) {
+                    float *d = ra.d_background + 4 * (y * ra.width + x);
+                    atomicAdd(d + 0, d_bg.x); atomicAdd(d + 1, d_bg.y); atomicAdd(d + 2, d_bg.z); atomicAdd(d + 3, d_bg.w);
+                }
+            } else if (bg_px && ra.d_background) {
+                float *d = ra.d_background + 4 * (y * ra.width + x);
+                atomicAdd(d + 0, d_color.x); atomicAdd(d + 1, d_color.y); atomicAdd(d + 2, d_color.z); atomicAdd(d + 3, d_color.w);
+            }
+            d_radius_acc = filter_radius_grad(sc, ra, x, y, pt, color);
+        }
+        d_radius_acc = warp_sum(d_radius_acc);
+        if ((tid & 31) == 0) sk.add(sc.filter_radius_off, d_radius_acc);
+        __syncthreads();
+        grad_cache_flush(*gcp, ra.d_params);
+    }
+}
+
+// sample_distance for every pixel sample (eval_positions == null) or every evaluation position.
+// One thread per sample; groups are searched from the last to the first with a strict `<`, as in
+// diffvg.cpp:726-739.  SDF scenes are small (the reference loops over ALL groups without any
+// culling here), so there is no binning.
+template <bool BACKWARD>
+__global__ void __launch_bounds__(PB) k_sdf(SceneView sc, RenderArgs ra, SdfArgs sa) {
+    GradCache *gcp = nullptr;
+    if constexpr (BACKWARD) {
+        __shared__ GradCache s_gc;
+        gcp = &s_gc;
+        grad_cache_init(s_gc);
+        __syncthreads();
+    }
+    const CacheSink sk{gcp, ra.d_params};
+    const int spp = ra.nsx * ra.nsy;
+    const int n = sa.eval_positions ? sa.num_eval : ra.width * ra.height * spp;
+    const int idx = blockIdx.x * PB + threadIdx.x;
+    if (idx < n) {
+        F2 pt, cpt;
+        int x, y;
+        if (!sa.eval_positions) {
+            const int sx = idx % ra.nsx, sy = (idx / ra.nsx) % ra.nsy;
+            x = (idx / spp) % ra.width; y = idx / (spp * ra.width);
+            sample_position(sc.canvas_w, sc.canvas_h, ra.width, ra.height, ra.nsx, ra.nsy, ra.seed, ra.use_prefiltering != 0,
+                            x, y, sx, sy, idx, pt, cpt);
+        } else {
+            pt = mk2(sa.eval_positions[2 * idx], sa.eval_positions[2 * idx + 1]);
+            x = (int)pt.x; y = (int)pt.y;
+            F2 npt = pt;
+            npt.x /= ra.width; npt.y /= ra.height;
+            cpt = mk2(npt.x * sc.canvas_w, npt.y * sc.canvas_h);
+        }
+        const float weight = sa.eval_positions ? 1.f : 1.f / spp;
+        int min_g = -1;
+        DistHit best;
+        dist_hit_init(best, 0.f);
+        for (int g = sc.num_groups - 1; g >= 0; g--) {
+            DistHit h;
+            group_distance(sc, g, cpt, h);
+            if (h.found && (min_g == -1 || h.dist < best.dist)) { best = h; min_g = g; }
+        }
+        float dist = 0.f;
+        if (min_g >= 0) {
+            dist = best.dist * weight;
+            bool inside = false;
+            if (sc.groups[min_g].fill_type >= 0) {
+                inside = group_is_inside(sc, min_g, cpt);
+                if (inside) dist = -dist;
+            }
+            if constexpr (BACKWARD) {
+                const float dd = sa.eval_positions ? sa.d_sdf[idx] : sa.d_sdf[y * ra.width + x];
+                const float d_abs = inside ? -dd : dd;
+                // d_translation is indexed by the pixel (diffvg.cpp:1281); out-of-image evaluation positions
+                // would write out of bounds in the reference -- skipped here
+                float *dtr = nullptr;
+                if (ra.d_translation && x >= 0 && x < ra.width && y >= 0 && y < ra.height) dtr = ra.d_translation + 2 * (y * ra.width + x);
+                d_compute_distance(sc, sc.groups[min_g], best.inst, cpt, best.cp, best.base_id, best.point_id, best.t_root, d_abs, sk, dtr);
+            }
+        }
+        if (!BACKWARD && sa.sdf) {
+            if (sa.eval_positions) sa.sdf[idx] = dist;   // one sample per slot
+            else atomicAdd(sa.sdf + y * ra.width + x, dist);
+        }
+    }
+    if (BACKWARD) {
+        __syncthreads();
+        grad_cache_flush(*gcp, ra.d_params);
+    }
+}
+
+static int pf_blocks(const BinView &bins, const RenderArgs &ra) {
+    const int ns = bins.tile_w * bins.tile_h * ra.nsx * ra.nsy;
+    const int parts = (ns + PB - 1) / PB;
+    const int r0 = ra.row_begin / bins.tile_h;
+    const int r1 = (ra.row_end + bins.tile_h - 1) / bins.tile_h;
+    return (r1 - r0) * bins.tiles_x * parts;
+}
+
+void launch_render_pf_forward(const SceneView &sc, const BinView &bins, const RenderArgs &ra, cudaStream_t st) {
+    const int nblk = pf_blocks(bins, ra);
+    if (nblk <= 0) return;
+    DVG_LAUNCH(k_render_pf<false>, dim3(nblk), dim3(PB), 0, st, sc, bins, ra);
+}
+
+void launch_render_pf_backward(const SceneView &sc, const BinView &bins, const RenderArgs &ra, cudaStream_t st) {
+    const int nblk = pf_blocks(bins, ra);
+    if (nblk <= 0) return;
+    DVG_LAUNCH(k_render_pf<true>, dim3(nblk), dim3(PB), 0, st, sc, bins, ra);
+}
+
+void launch_sdf(const SceneView &sc, const RenderArgs &ra, const SdfArgs &sa, bool backward, cudaStream_t st) {
+    const int n = sa.eval_positions ? sa.num_eval : ra.width * ra.height * ra.nsx * ra.nsy;
+    if (n <= 0) return;
+    if (backward) DVG_LAUNCH(k_sdf<true>, dim3((n + PB - 1) / PB), dim3(PB), 0, st, sc, ra, sa);
+    else DVG_LAUNCH(k_sdf<false>, dim3((n + PB - 1) / PB), dim3(PB), 0, st, sc, ra, sa);
+}
+
+}  // namespace dvg

@@ -15,6 +15,7 @@
 //   * pixel sums are accumulated in shared memory and flushed once per tile; colour
 //     gradients are reduced across the warp before touching global memory.
 #include "dvg_internal.h"
+#include "dvg_kernel_util.cuh"
 
 namespace dvg {
 
@@ -206,11 +207,6 @@ DVG_D void traverse(const SceneView &sc, const BinView &bins, const int tile, Wa
     tr.finish(sc);
 }
 
-DVG_D float warp_sum(float v) {
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-
 // ------------------------------------------------------------------------------------------
 // render_kernel (diffvg.cpp:1161-1272), colour output.  BACKWARD = the d_render_image != null
 // variant: recompute the forward, then d_sample_color (diffvg.cpp:656-705), d_background and
@@ -274,42 +270,7 @@ __global__ void __launch_bounds__(RB, DVG_MINB) k_render(SceneView sc, BinView b
         to.accum = tr.accum; to.nfrag = tr.nfrag; to.sp = tr.sp;
 
         if (!BACKWARD) {
-            // splat (diffvg.cpp:1224-1249): the sample's own pixel is reduced across the lanes of
-            // the pixel first; the (rare for box 0.5) neighbours go straight to global memory
-            F4 own = mk4(0, 0, 0, 0);
-            if (active) {
-                const int ri = (int)ceilf(sc.filter.radius);
-                for (int dy = -ri; dy <= ri; dy++) {
-                    for (int dx = -ri; dx <= ri; dx++) {
-                        const int xx = x + dx, yy = y + dy;
-                        if (xx >= 0 && xx < ra.width && yy >= 0 && yy < ra.height) {
-                            const float fw = filter_weight(sc.filter, (xx + 0.5f) - pos.pt.x, (yy + 0.5f) - pos.pt.y);
-                            if (fw == 0.f) continue;
-                            const float wsum = ra.weight_image[yy * ra.width + xx];
-                            if (!(wsum > 0)) continue;
-                            const float inv_ws = 1.f / wsum;  // Vector4 / scalar == * (1.f / s)
-                            const F4 wc = mk4((fw * color.x) * inv_ws, (fw * color.y) * inv_ws,
-                                              (fw * color.z) * inv_ws, (fw * color.w) * inv_ws);
-                            if (dx == 0 && dy == 0) own = wc;
-                            else {
-                                float *d = ra.render_image + 4 * (yy * ra.width + xx);
-                                atomicAdd(d + 0, wc.x); atomicAdd(d + 1, wc.y); atomicAdd(d + 2, wc.z); atomicAdd(d + 3, wc.w);
-                            }
-                        }
-                    }
-                }
-            }
-            for (int o = grp >> 1; o > 0; o >>= 1) {
-                own.x += __shfl_xor_sync(0xffffffffu, own.x, o); own.y += __shfl_xor_sync(0xffffffffu, own.y, o);
-                own.z += __shfl_xor_sync(0xffffffffu, own.z, o); own.w += __shfl_xor_sync(0xffffffffu, own.w, o);
-            }
-            if (active && (tid & (grp - 1)) == 0) {
-                float *d = ra.render_image + 4 * (y * ra.width + x);
-                if (own.x != 0.f) atomicAdd(d + 0, own.x);
-                if (own.y != 0.f) atomicAdd(d + 1, own.y);
-                if (own.z != 0.f) atomicAdd(d + 2, own.z);
-                if (own.w != 0.f) atomicAdd(d + 3, own.w);
-            }
+            splat_color(sc, ra, x, y, pos.pt, color, active, grp, tid);
         } else {
             // ---- interior backward.  All 32 lanes stay converged: fragments are popped in
             // warp-uniform steps so that lanes sharing a (group, stroke/fill) key are reduced
@@ -371,27 +332,7 @@ __global__ void __launch_bounds__(RB, DVG_MINB) k_render(SceneView sc, BinView b
                 float *d = ra.d_background + 4 * (y * ra.width + x);
                 atomicAdd(d + 0, dcr); atomicAdd(d + 1, dcg); atomicAdd(d + 2, dcb); atomicAdd(d + 3, dca);
             }
-            if (active) {
-                // filter-radius gradient (diffvg.cpp:1250-1268).  The reference evaluates
-                // d_compute_filter_weight for every in-range pixel with weight > 0, even where
-                // the filter weight itself is zero.
-                const int ri = (int)ceilf(sc.filter.radius);
-                for (int dy = -ri; dy <= ri; dy++) {
-                    for (int dx = -ri; dx <= ri; dx++) {
-                        const int xx = x + dx, yy = y + dy;
-                        if (xx >= 0 && xx < ra.width && yy >= 0 && yy < ra.height) {
-                            const float ws = ra.weight_image[yy * ra.width + xx];
-                            if (!(ws > 0)) continue;
-                            const float ddx = (xx + 0.5f) - pos.pt.x, ddy = (yy + 0.5f) - pos.pt.y;
-                            const float fw = filter_weight(sc.filter, ddx, ddy);
-                            const float4 dp = *reinterpret_cast<const float4 *>(ra.d_render_image + 4 * (yy * ra.width + xx));
-                            const float dotv = dp.x * color.x + dp.y * color.y + dp.z * color.z + dp.w * color.w;
-                            const float d_weight = (dotv * ws - fw * dotv * (ws - fw)) / (ws * ws);
-                            d_radius_acc += d_filter_weight_radius(sc.filter, ddx, ddy, d_weight);
-                        }
-                    }
-                }
-            }
+            if (active) d_radius_acc += filter_radius_grad(sc, ra, x, y, pos.pt, color);
         }
     }
     if (BACKWARD) {

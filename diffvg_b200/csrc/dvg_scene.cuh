@@ -84,6 +84,7 @@ struct SceneView {
     const float *prim_thick;  // leaf max_radius, scene.cpp:546,569,597
     const PrimMeta *prim_meta;
     const Box *prim_cbox;  // canvas-space conservative bound of where this primitive can matter (binning only)
+    const Box *prim_cbox_pf;  // same for the prefiltering path (binning only)
     const F4 *prim_cap;    // DVG_CAP_F4 float4 per primitive: conservative stroke-reject capsules (dvg_geom.cuh)
     const InstInfo *insts;
     const GroupInfo *groups;

@@ -35,6 +35,7 @@ struct PrimRef {
     int tf;     // type | flags
     int inst;
     int group;
+    int base_id, point_id;  // path segment index / first point index (prefilter path only)
     const float *cap;  // DVG_CAP_N * 6 floats (reject capsules)
 };
 

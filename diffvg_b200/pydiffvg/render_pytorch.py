@@ -147,9 +147,12 @@ class RenderFunction(torch.autograd.Function):
         packed, params = args
         n = _native()
         dev = _cuda_device()
-        if packed.output_type != OutputType.color:
-            raise NotImplementedError('OutputType.sdf is not implemented yet in this build')
-        assert packed.eval_positions.shape[0] == 0
+        output_type = packed.output_type
+        eval_positions = packed.eval_positions
+        if output_type == OutputType.color:
+            assert eval_positions.shape[0] == 0
+        else:
+            assert output_type == OutputType.sdf
         start = time.time()
         ns = _get_native_scene(packed, dev.index)
         with torch.cuda.device(dev):
@@ -157,7 +160,15 @@ class RenderFunction(torch.autograd.Function):
             version = ns.set_params(params, stream)
             if print_timing:
                 print('Scene construction, time: %.5f s' % (time.time() - start))
-            rendered_image = torch.empty(height, width, 4, device=dev, dtype=torch.float32)
+            if output_type == OutputType.color:
+                rendered_image = torch.empty(height, width, 4, device=dev, dtype=torch.float32)
+            elif eval_positions.shape[0] == 0:
+                rendered_image = torch.empty(height, width, 1, device=dev, dtype=torch.float32)
+            else:
+                rendered_image = torch.empty(eval_positions.shape[0], 1, device=dev, dtype=torch.float32)
+            eval_dev = None
+            if eval_positions.shape[0] > 0:
+                eval_dev = eval_positions.detach().to(dev).float().contiguous()
             if background_image is not None:
                 background_image = background_image.to(dev)
                 if background_image.shape[2] == 3:
@@ -169,11 +180,16 @@ class RenderFunction(torch.autograd.Function):
             start = time.time()
             n.check(n.lib.dvg_render_forward(
                 ns.handle, background_image.data_ptr() if background_image is not None else None,
-                rendered_image.data_ptr(), None, width, height, num_samples_x, num_samples_y, int(seed),
-                1 if packed.use_prefiltering else 0, None, 0, stream))
+                rendered_image.data_ptr() if output_type == OutputType.color else None,
+                rendered_image.data_ptr() if output_type == OutputType.sdf else None,
+                width, height, num_samples_x, num_samples_y, int(seed),
+                1 if packed.use_prefiltering else 0,
+                eval_dev.data_ptr() if eval_dev is not None else None,
+                eval_dev.shape[0] if eval_dev is not None else 0, stream))
             if print_timing:
                 torch.cuda.synchronize(dev)
                 print('Forward pass, time: %.5f s' % (time.time() - start))
+        ctx.eval_dev = eval_dev
         ctx.native_scene = ns
         ctx.scene_version = version
         ctx.packed = packed
@@ -187,6 +203,48 @@ class RenderFunction(torch.autograd.Function):
         ctx.params_device = params.device
         ctx.save_for_backward(params)
         return rendered_image
+
+    @staticmethod
+    def render_grad(grad_img, width, height, num_samples_x, num_samples_y, seed, background_image, *args):
+        """Per-pixel translation gradient image [H, W, 2] (reference: render_pytorch.py:430-666; used by
+        apps/finite_difference_comp.py).  Q18: the reference reads an undefined `rendered_image` when a
+        background is passed; here the background is simply validated against (height, width)."""
+        packed, params = args
+        n = _native()
+        dev = _cuda_device()
+        if not grad_img.is_contiguous():
+            grad_img = grad_img.contiguous()
+        assert torch.isfinite(grad_img).all()
+        is_color = packed.output_type == OutputType.color
+        assert grad_img.shape[-1] == (4 if is_color else 1)
+        ns = _get_native_scene(packed, dev.index)
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream().cuda_stream
+            ns.set_params(params, stream)
+            grad_img = grad_img.to(dev).float().contiguous()
+            if background_image is not None:
+                background_image = background_image.to(dev)
+                if background_image.shape[2] == 3:
+                    background_image = torch.cat((background_image, torch.ones(
+                        background_image.shape[0], background_image.shape[1], 1, device=dev)), dim=2)
+                background_image = background_image.contiguous().float()
+                assert background_image.shape[0] == height and background_image.shape[1] == width
+                assert background_image.shape[2] == 4
+            eval_positions = packed.eval_positions
+            eval_dev = eval_positions.detach().to(dev).float().contiguous() if eval_positions.shape[0] > 0 else None
+            translation_grad_image = torch.empty(height, width, 2, device=dev, dtype=torch.float32)
+            d_params = torch.empty(packed.num_params, device=dev, dtype=torch.float32)
+            start = time.time()
+            n.check(n.lib.dvg_render_backward(
+                ns.handle, background_image.data_ptr() if background_image is not None else None,
+                grad_img.data_ptr() if is_color else None, None if is_color else grad_img.data_ptr(),
+                width, height, num_samples_x, num_samples_y, int(seed), 1 if packed.use_prefiltering else 0,
+                eval_dev.data_ptr() if eval_dev is not None else None, eval_dev.shape[0] if eval_dev is not None else 0,
+                d_params.data_ptr(), None, translation_grad_image.data_ptr(), 0, stream))
+            if print_timing:
+                torch.cuda.synchronize(dev)
+                print('Gradient pass, time: %.5f s' % (time.time() - start))
+        return translation_grad_image
 
     @staticmethod
     def backward(ctx, grad_img):
@@ -207,11 +265,15 @@ class RenderFunction(torch.autograd.Function):
                 ctx.scene_version = ns.set_params(params, stream)
             d_params = torch.empty(ctx.packed.num_params, device=dev, dtype=torch.float32)
             d_background = torch.empty_like(background_image) if background_image is not None else None
+            is_color = ctx.packed.output_type == OutputType.color
+            eval_dev = ctx.eval_dev
             start = time.time()
             n.check(n.lib.dvg_render_backward(
                 ns.handle, background_image.data_ptr() if background_image is not None else None,
-                grad_img.data_ptr(), None, ctx.width, ctx.height, ctx.num_samples_x, ctx.num_samples_y,
-                int(ctx.seed), 1 if ctx.packed.use_prefiltering else 0, None, 0,
+                grad_img.data_ptr() if is_color else None, None if is_color else grad_img.data_ptr(),
+                ctx.width, ctx.height, ctx.num_samples_x, ctx.num_samples_y,
+                int(ctx.seed), 1 if ctx.packed.use_prefiltering else 0,
+                eval_dev.data_ptr() if eval_dev is not None else None, eval_dev.shape[0] if eval_dev is not None else 0,
                 d_params.data_ptr(), d_background.data_ptr() if d_background is not None else None, None,
                 0, stream))
             if print_timing:

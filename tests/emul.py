@@ -85,3 +85,62 @@ def pcg(idx, seed):
     ry = ctypes.c_float()
     lib.emul_pcg(idx, seed, ctypes.byref(st), ctypes.byref(rx), ctypes.byref(ry))
     return st.value, rx.value, ry.value
+
+
+def render_pf(topo, params, width, height, nsx, nsy, seed, background=None, d_render_image=None,
+              want_d_translation=False, nthreads=8):
+    """use_prefiltering=True colour render (forward, or backward when d_render_image is given)."""
+    lib = _load()
+    fp = ctypes.POINTER(ctypes.c_float)
+    ip = ctypes.POINTER(ctypes.c_int32)
+    lib.emul_render_pf.argtypes = [ip, fp, fp, fp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_uint64,
+                                   fp, fp, fp, fp, ctypes.c_int]
+    lib.emul_render_pf.restype = ctypes.c_int
+    topo = np.ascontiguousarray(topo, dtype=np.int32)
+    params = np.ascontiguousarray(params, dtype=np.float32)
+    out = {}
+    tp = topo.ctypes.data_as(ip)
+    if d_render_image is None:
+        img = np.zeros((height, width, 4), np.float32)
+        rc = lib.emul_render_pf(tp, _f(params), _f(background), _f(img), width, height, nsx, nsy, int(seed),
+                                None, None, None, None, nthreads)
+        out['image'] = img
+    else:
+        d_params = np.zeros_like(params)
+        d_bg = np.zeros((height, width, 4), np.float32) if background is not None else None
+        d_tr = np.zeros((height, width, 2), np.float32) if want_d_translation else None
+        rc = lib.emul_render_pf(tp, _f(params), _f(background), None, width, height, nsx, nsy, int(seed),
+                                _f(np.ascontiguousarray(d_render_image, dtype=np.float32)), _f(d_params), _f(d_bg), _f(d_tr),
+                                nthreads)
+        out.update(d_params=d_params, d_background=d_bg, d_translation=d_tr)
+    if rc != 0:
+        raise RuntimeError('emul_render_pf failed: %d' % rc)
+    return out
+
+
+def sdf(topo, params, width, height, nsx, nsy, seed, eval_positions=None, d_render_sdf=None, want_d_translation=False):
+    lib = _load()
+    fp = ctypes.POINTER(ctypes.c_float)
+    ip = ctypes.POINTER(ctypes.c_int32)
+    lib.emul_sdf.argtypes = [ip, fp, fp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_uint64,
+                             fp, ctypes.c_int, fp, fp, fp]
+    lib.emul_sdf.restype = ctypes.c_int
+    topo = np.ascontiguousarray(topo, dtype=np.int32)
+    params = np.ascontiguousarray(params, dtype=np.float32)
+    n_eval = 0 if eval_positions is None else eval_positions.shape[0]
+    ep = None if eval_positions is None else np.ascontiguousarray(eval_positions, dtype=np.float32)
+    out = {}
+    if d_render_sdf is None:
+        s = np.zeros((n_eval, 1) if n_eval else (height, width, 1), np.float32)
+        rc = lib.emul_sdf(topo.ctypes.data_as(ip), _f(params), _f(s), width, height, nsx, nsy, int(seed), _f(ep), n_eval,
+                          None, None, None)
+        out['sdf'] = s
+    else:
+        d_params = np.zeros_like(params)
+        d_tr = np.zeros((height, width, 2), np.float32) if want_d_translation else None
+        rc = lib.emul_sdf(topo.ctypes.data_as(ip), _f(params), None, width, height, nsx, nsy, int(seed), _f(ep), n_eval,
+                          _f(np.ascontiguousarray(d_render_sdf, dtype=np.float32)), _f(d_params), _f(d_tr))
+        out.update(d_params=d_params, d_translation=d_tr)
+    if rc != 0:
+        raise RuntimeError('emul_sdf failed: %d' % rc)
+    return out

@@ -48,6 +48,73 @@ def background_for(name, H, W):
     return np.random.RandomState(seed).rand(H, W, 4).astype(np.float32)
 
 
+# Other render modes of the path: SDF prefiltering ('pf'), SDF output ('sdf', with or without
+# eval_positions) and the per-pixel translation gradient of render_grad ('dtrans'), stored under
+# tests/golden_modes/.  name -> (mode, scene, W, H, nsx, nsy, seed, filter_type, filter_radius, use_background)
+MODE_CASES = {
+    'pf_stroke':     ('pf', lambda: scenes.single_stroke(), 64, 64, 1, 1, 0, 0, 0.5, False),
+    'pf_zoo':        ('pf', lambda: scenes.zoo_prefilter(), 96, 96, 2, 2, 5, 0, 0.5, False),
+    'pf_zoo_bg':     ('pf', lambda: scenes.zoo_prefilter(), 80, 48, 1, 1, 2, 0, 0.5, True),
+    'pf_zoo_hann':   ('pf', lambda: scenes.zoo_prefilter(), 64, 64, 2, 2, 5, 3, 1.5, False),
+    'pf_blobs':      ('pf', lambda: scenes.blobs(48, 128), 64, 64, 2, 2, 1, 0, 0.5, False),
+    'sdf_stroke':    ('sdf', lambda: scenes.single_stroke(), 48, 48, 2, 2, 0, 0, 0.5, False),
+    'sdf_zoo':       ('sdf', lambda: scenes.zoo_prefilter(), 64, 64, 2, 2, 5, 0, 0.5, False),
+    'sdf_zoo_eval':  ('sdf_eval', lambda: scenes.zoo_prefilter(), 128, 128, 1, 1, 0, 0, 0.5, False),
+    'sdf_circle':    ('sdf', lambda: scenes.single_circle(), 32, 32, 1, 1, 0, 0, 0.5, False),
+    'dtrans_zoo':    ('dtrans', lambda: scenes.zoo(), 64, 64, 2, 2, 3, 0, 0.5, False),
+}
+MODES_DIR = os.path.join(os.path.dirname(HERE), 'golden_modes')
+
+
+def eval_positions_for(name, H, W, n=300):
+    seed = 5 + sum(ord(c) for c in name)
+    return (np.random.RandomState(seed).rand(n, 2) * np.asarray([W, H])).astype(np.float32)
+
+
+def d_sdf_for(name, shape):
+    seed = 9 + sum(ord(c) for c in name)
+    return (np.random.RandomState(seed).rand(*shape).astype(np.float32) - 0.5)
+
+
+def run_mode(render, name, mode, topo, params, W, H, nsx, nsy, seed, use_bg):
+    """One mode case through `render` (ref_oracle.render, or an emulation / GPU front end with the same
+    keyword surface).  Returns the dict of arrays a fixture stores."""
+    bg = background_for(name, H, W) if use_bg else None
+    out = {}
+    if mode == 'pf':
+        out['image'] = render(topo, params, W, H, nsx, nsy, seed, background=bg, use_prefiltering=True)['image']
+        b = render(topo, params, W, H, nsx, nsy, seed, background=bg, use_prefiltering=True,
+                   d_render_image=d_image_for(name, H, W), want_d_translation=True)
+        out['d_params'] = b['d_params']
+        out['d_translation'] = b['d_translation']
+        if use_bg:
+            out['d_background'] = b['d_background']
+    elif mode in ('sdf', 'sdf_eval'):
+        ep = eval_positions_for(name, H, W) if mode == 'sdf_eval' else None
+        out['sdf'] = render(topo, params, W, H, nsx, nsy, seed, want_image=False, want_sdf=True, eval_positions=ep)['sdf']
+        b = render(topo, params, W, H, nsx, nsy, seed, eval_positions=ep, d_render_sdf=d_sdf_for(name, out['sdf'].shape),
+                   want_d_translation=True)
+        out['d_params'] = b['d_params']
+        out['d_translation'] = b['d_translation']
+    else:  # dtrans: plain colour render, boundary term writes the translation gradient
+        b = render(topo, params, W, H, nsx, nsy, seed, d_render_image=d_image_for(name, H, W), want_d_translation=True)
+        out['d_params'] = b['d_params']
+        out['d_translation'] = b['d_translation']
+    return out
+
+
+def main_modes():
+    os.makedirs(MODES_DIR, exist_ok=True)
+    for name, (mode, mk, W, H, nsx, nsy, seed, ft, fr, use_bg) in MODE_CASES.items():
+        topo, params = util.pack(mk(), ft, fr)
+        out = run_mode(ref_oracle.render, name, mode, topo, params, W, H, nsx, nsy, seed, use_bg)
+        out.update(topo=topo, params=params, config=np.asarray([W, H, nsx, nsy, seed, ft], np.int64), filter_radius=np.float32(fr))
+        np.savez_compressed(os.path.join(MODES_DIR, name + '.npz'), **out)
+        first = out.get('image', out.get('sdf', out['d_translation']))
+        print('%-14s %-8s sum %.6f |d_params| %.6g' % (name, mode, first.astype(np.float64).sum(),
+                                                       np.linalg.norm(out['d_params'].astype(np.float64))))
+
+
 def main():
     for name, (mk, W, H, nsx, nsy, seed, ft, fr, use_bg) in CASES.items():
         topo, params = util.pack(mk(), ft, fr)
@@ -65,4 +132,7 @@ def main():
 
 
 if __name__ == '__main__':
-    main()
+    if len(sys.argv) < 2 or sys.argv[1] != 'modes':
+        main()
+    if len(sys.argv) < 2 or sys.argv[1] == 'modes':
+        main_modes()

@@ -18,6 +18,7 @@ static void dvg_capsule_dump(const dvg::F4 &p01, const dvg::F4 &p23, const dvg::
 #include "../../diffvg_b200/csrc/dvg_color.cuh"
 #include "../../diffvg_b200/csrc/dvg_boundary.cuh"
 #include "../../diffvg_b200/csrc/dvg_trace.cuh"
+#include "../../diffvg_b200/csrc/dvg_distance.cuh"
 #include "../../diffvg_b200/csrc/dvg_buildfn.cuh"
 
 #include <algorithm>
@@ -37,7 +38,7 @@ struct HostScene {
     std::vector<float> params;
     std::vector<int> inst_group, inst_shape, inst_prim_begin, prim_inst, prim_seg, prim_point_id;
     std::vector<float> shapes_length, shape_r0, seg_cdf, seg_pmf, prim_thick, shape_cdf, shape_pmf;
-    std::vector<Box> shape_box, prim_box, prim_cbox;
+    std::vector<Box> shape_box, prim_box, prim_cbox, prim_cbox_pf;
     std::vector<int> seg_point_id;
     std::vector<InstInfo> insts;
     std::vector<GroupInfo> groups;
@@ -81,7 +82,7 @@ void build(HostScene &hs, const int32_t *topo, const float *params) {
     hs.seg_cdf.resize(nsg); hs.seg_pmf.resize(nsg); hs.seg_point_id.resize(nsg);
     hs.insts.resize(ni); hs.groups.resize(ng);
     hs.p01.resize(np); hs.p23.resize(np); hs.rad.resize(np); hs.prim_box.resize(np); hs.prim_thick.resize(np);
-    hs.meta.resize(np); hs.prim_cbox.resize(np); hs.cap.resize((size_t)np * DVG_CAP_F4); hs.shape_cdf.resize(ni); hs.shape_pmf.resize(ni);
+    hs.meta.resize(np); hs.prim_cbox.resize(np); hs.prim_cbox_pf.resize(np); hs.cap.resize((size_t)np * DVG_CAP_F4); hs.shape_cdf.resize(ni); hs.shape_pmf.resize(ni);
     BuildView bv;
     bv.canvas_w = t[DVG_H_CANVAS_W]; bv.canvas_h = t[DVG_H_CANVAS_H];
     bv.num_shapes = ns; bv.num_groups = ng; bv.num_insts = ni; bv.num_prims = np;
@@ -92,7 +93,7 @@ void build(HostScene &hs, const int32_t *topo, const float *params) {
     bv.seg_cdf = hs.seg_cdf.data(); bv.seg_pmf = hs.seg_pmf.data(); bv.seg_point_id = hs.seg_point_id.data();
     bv.insts = hs.insts.data(); bv.groups = hs.groups.data();
     bv.prim_p01 = hs.p01.data(); bv.prim_p23 = hs.p23.data(); bv.prim_rad = hs.rad.data(); bv.prim_box = hs.prim_box.data();
-    bv.prim_thick = hs.prim_thick.data(); bv.prim_meta = hs.meta.data(); bv.prim_cbox = hs.prim_cbox.data(); bv.prim_cap = hs.cap.data();
+    bv.prim_thick = hs.prim_thick.data(); bv.prim_meta = hs.meta.data(); bv.prim_cbox = hs.prim_cbox.data(); bv.prim_cbox_pf = hs.prim_cbox_pf.data(); bv.prim_cap = hs.cap.data();
     bv.shape_cdf = hs.shape_cdf.data(); bv.shape_pmf = hs.shape_pmf.data();
     bv.error_flag = &hs.error_flag; bv.total_length = &hs.total_length;
     for (int s = 0; s < ns; s++) build_shape(bv, s);
@@ -107,7 +108,7 @@ void build(HostScene &hs, const int32_t *topo, const float *params) {
     sc.filter_radius_off = t[DVG_H_FILTER_RADIUS_OFF];
     sc.topo = t; sc.params = hs.params.data();
     sc.prim_p01 = hs.p01.data(); sc.prim_p23 = hs.p23.data(); sc.prim_rad = hs.rad.data(); sc.prim_box = hs.prim_box.data();
-    sc.prim_thick = hs.prim_thick.data(); sc.prim_meta = hs.meta.data(); sc.prim_cbox = hs.prim_cbox.data(); sc.prim_cap = hs.cap.data();
+    sc.prim_thick = hs.prim_thick.data(); sc.prim_meta = hs.meta.data(); sc.prim_cbox = hs.prim_cbox.data(); sc.prim_cbox_pf = hs.prim_cbox_pf.data(); sc.prim_cap = hs.cap.data();
     sc.insts = hs.insts.data(); sc.groups = hs.groups.data();
     sc.shapes_length = hs.shapes_length.data(); sc.shape_cdf = hs.shape_cdf.data(); sc.shape_pmf = hs.shape_pmf.data();
     sc.seg_cdf = hs.seg_cdf.data(); sc.seg_pmf = hs.seg_pmf.data(); sc.seg_point_id = hs.seg_point_id.data();
@@ -118,15 +119,16 @@ PrimRef prim_ref(const HostScene &hs, int e) {
     PrimRef pr;
     pr.p01 = hs.p01[e]; pr.p23 = hs.p23[e]; pr.rad = hs.rad[e]; pr.box = hs.prim_box[e]; pr.thick = hs.prim_thick[e];
     pr.tf = hs.meta[e].type_flags; pr.inst = hs.meta[e].inst; pr.group = hs.insts[hs.meta[e].inst].group;
+    pr.base_id = hs.meta[e].base_id; pr.point_id = hs.meta[e].point_id;
     pr.cap = reinterpret_cast<const float *>(&hs.cap[(size_t)e * DVG_CAP_F4]);
     return pr;
 }
 
 // candidate primitives for a canvas-space rectangle (mirrors the tile-bin test of dvg_build.cu)
-void candidates(const HostScene &hs, float x0, float y0, float x1, float y1, std::vector<int> &out) {
+void candidates(const HostScene &hs, float x0, float y0, float x1, float y1, std::vector<int> &out, bool pf = false) {
     out.clear();
     for (int e = 0; e < hs.sc.num_prims; e++) {
-        const Box &b = hs.prim_cbox[e];
+        const Box &b = pf ? hs.prim_cbox_pf[e] : hs.prim_cbox[e];
         if (b.x0 <= x1 && b.x1 >= x0 && b.y0 <= y1 && b.y1 >= y0) out.push_back(e);
     }
 }
@@ -471,3 +473,153 @@ EXPORT void emul_capsule_stats(long long *out, int reset) {
     for (int i = 0; i < 6; i++) { out[i] = g_cs[i]; if (reset) g_cs[i] = 0; }
 }
 #endif
+
+// ------------------------------------------------------------------------------------------
+// SDF prefiltering (use_prefiltering = true): forward (d_image == null) or backward.  No boundary
+// pass (diffvg.cpp:1558).  The weight image uses JITTERED positions (Q1), the colour samples use
+// sub-pixel centres.
+EXPORT int emul_render_pf(const int32_t *topo, const float *params, const float *background, float *image,
+                          int W, int H, int nsx, int nsy, uint64_t seed, const float *d_image,
+                          float *d_params, float *d_background, float *d_translation, int nthreads) {
+    HostScene hs;
+    build(hs, topo, params);
+    if (hs.error_flag) return 3;
+    const SceneView &sc = hs.sc;
+    const int spp = nsx * nsy;
+    std::vector<float> weight((size_t)W * H, 0.f);
+    const int ri = (int)ceilf(sc.filter.radius);
+    for (int idx = 0; idx < W * H * spp; idx++) {
+        const int sx = idx % nsx, sy = (idx / nsx) % nsy, x = (idx / spp) % W, y = idx / (spp * W);
+        F2 pt, cpt;
+        sample_position(sc.canvas_w, sc.canvas_h, W, H, nsx, nsy, seed, false, x, y, sx, sy, idx, pt, cpt);
+        for (int dy = -ri; dy <= ri; dy++)
+            for (int dx = -ri; dx <= ri; dx++) {
+                int xx = x + dx, yy = y + dy;
+                if (xx >= 0 && xx < W && yy >= 0 && yy < H)
+                    weight[yy * W + xx] += filter_weight(sc.filter, (xx + 0.5f) - pt.x, (yy + 0.5f) - pt.y);
+            }
+    }
+    const float cw = (float)sc.canvas_w, ch = (float)sc.canvas_h;
+    const float margin = 4e-4f * std::max(cw, ch) + 1e-4f;
+    std::mutex mu;
+    std::vector<double> acc(d_params ? hs.params.size() : 0, 0.0);
+    const DoubleSink dsink{acc.data()};
+    std::vector<float> img_acc(d_image ? 0 : (size_t)W * H * 4, 0.f);
+    parallel_rows(H, nthreads, [&](int y) {
+        std::vector<int> cand;
+        std::vector<PfFragment> frags(DVG_MAXPF);
+        for (int x = 0; x < W; x++) {
+            candidates(hs, (float)x / W * cw - margin, (float)y / H * ch - margin, (float)(x + 1) / W * cw + margin,
+                       (float)(y + 1) / H * ch + margin, cand, true);
+            for (int s = 0; s < spp; s++) {
+                const int sx = s % nsx, sy = s / nsx;
+                const int idx = ((y * W + x) * nsy + sy) * nsx + sx;
+                F2 pt, cpt;
+                sample_position(sc.canvas_w, sc.canvas_h, W, H, nsx, nsy, seed, true, x, y, sx, sy, idx, pt, cpt);
+                const float *bg_px = background ? background + 4 * (y * W + x) : nullptr;
+                F4 first = bg_px ? mk4(bg_px[0], bg_px[1], bg_px[2], bg_px[3]) : mk4(0, 0, 0, 0);
+                PrefilterTracer<true> tr;
+                tr.init(cpt, true, first, frags.data());
+                for (int e : cand) tr.step(sc, prim_ref(hs, e));
+                tr.finish(sc);
+                const F4 color = tr.resolve(bg_px);
+                std::lock_guard<std::mutex> lk(mu);
+                if (!d_image) {
+                    for (int dy = -ri; dy <= ri; dy++)
+                        for (int dx = -ri; dx <= ri; dx++) {
+                            int xx = x + dx, yy = y + dy;
+                            if (xx >= 0 && xx < W && yy >= 0 && yy < H && weight[yy * W + xx] > 0) {
+                                float fw = filter_weight(sc.filter, (xx + 0.5f) - pt.x, (yy + 0.5f) - pt.y);
+                                float inv_ws = 1.f / weight[yy * W + xx];
+                                float *d = &image[((size_t)yy * W + xx) * 4];
+                                d[0] += (fw * color.x) * inv_ws; d[1] += (fw * color.y) * inv_ws;
+                                d[2] += (fw * color.z) * inv_ws; d[3] += (fw * color.w) * inv_ws;
+                            }
+                        }
+                } else {
+                    const F4 d_color = gather_d_color(sc.filter, d_image, weight.data(), W, H, pt);
+                    float *dtr = d_translation ? d_translation + 2 * (y * W + x) : nullptr;
+                    if (tr.nfrag > 0) {
+                        F4 d_bg;
+                        prefilter_backward(sc, tr, color, d_color, dsink, dtr, d_bg);
+                        if (bg_px && d_background) {
+                            float *d = d_background + 4 * (y * W + x);
+                            d[0] += d_bg.x; d[1] += d_bg.y; d[2] += d_bg.z; d[3] += d_bg.w;
+                        }
+                    } else if (bg_px && d_background) {
+                        float *d = d_background + 4 * (y * W + x);
+                        d[0] += d_color.x; d[1] += d_color.y; d[2] += d_color.z; d[3] += d_color.w;
+                    }
+                    for (int dy = -ri; dy <= ri; dy++)
+                        for (int dx = -ri; dx <= ri; dx++) {
+                            int xx = x + dx, yy = y + dy;
+                            if (xx >= 0 && xx < W && yy >= 0 && yy < H && weight[yy * W + xx] > 0) {
+                                const float ws = weight[yy * W + xx];
+                                const float ddx = (xx + 0.5f) - pt.x, ddy = (yy + 0.5f) - pt.y;
+                                const float fw = filter_weight(sc.filter, ddx, ddy);
+                                const float *dp = d_image + 4 * (yy * W + xx);
+                                const float dotv = dp[0] * color.x + dp[1] * color.y + dp[2] * color.z + dp[3] * color.w;
+                                const float d_weight = (dotv * ws - fw * dotv * (ws - fw)) / (ws * ws);
+                                acc[sc.filter_radius_off] += (double)d_filter_weight_radius(sc.filter, ddx, ddy, d_weight);
+                            }
+                        }
+                }
+            }
+        }
+    });
+    if (d_params) for (size_t i = 0; i < acc.size(); i++) d_params[i] = (float)acc[i];
+    return 0;
+}
+
+// SDF output (sample_distance, diffvg.cpp:709-775).  eval_positions == null: one sample per pixel
+// sample, accumulated into sdf[H*W]; else sdf[n_eval].  Backward when d_sdf != null.
+EXPORT int emul_sdf(const int32_t *topo, const float *params, float *sdf, int W, int H, int nsx, int nsy, uint64_t seed,
+                    const float *eval_positions, int n_eval, const float *d_sdf, float *d_params, float *d_translation) {
+    HostScene hs;
+    build(hs, topo, params);
+    if (hs.error_flag) return 3;
+    const SceneView &sc = hs.sc;
+    const int spp = nsx * nsy;
+    const int n = eval_positions ? n_eval : W * H * spp;
+    std::vector<double> acc(d_params ? hs.params.size() : 0, 0.0);
+    const DoubleSink dsink{acc.data()};
+    for (int idx = 0; idx < n; idx++) {
+        F2 pt, cpt;
+        int x, y;
+        if (!eval_positions) {
+            const int sx = idx % nsx, sy = (idx / nsx) % nsy;
+            x = (idx / spp) % W; y = idx / (spp * W);
+            sample_position(sc.canvas_w, sc.canvas_h, W, H, nsx, nsy, seed, false, x, y, sx, sy, idx, pt, cpt);
+        } else {
+            pt = mk2(eval_positions[2 * idx], eval_positions[2 * idx + 1]);
+            x = (int)pt.x; y = (int)pt.y;
+            F2 npt = pt; npt.x /= W; npt.y /= H;
+            cpt = mk2(npt.x * sc.canvas_w, npt.y * sc.canvas_h);
+        }
+        const float weight = eval_positions ? 1.f : 1.f / spp;
+        int min_g = -1; DistHit best; dist_hit_init(best, 0.f);
+        for (int g = sc.num_groups - 1; g >= 0; g--) {
+            DistHit h;
+            group_distance(sc, g, cpt, h);
+            if (h.found && (min_g == -1 || h.dist < best.dist)) { best = h; min_g = g; }
+        }
+        float dist = 0.f;
+        if (min_g >= 0) {
+            dist = best.dist * weight;
+            bool inside = false;
+            if (sc.groups[min_g].fill_type >= 0) {
+                inside = group_is_inside(sc, min_g, cpt);
+                if (inside) dist = -dist;
+            }
+            if (d_sdf) {
+                const float dd = eval_positions ? d_sdf[idx] : d_sdf[y * W + x];
+                const float d_abs = inside ? -dd : dd;
+                d_compute_distance(sc, sc.groups[min_g], best.inst, cpt, best.cp, best.base_id, best.point_id, best.t_root, d_abs, dsink,
+                                   d_translation ? d_translation + 2 * (y * W + x) : nullptr);
+            }
+        }
+        if (sdf) { if (eval_positions) sdf[idx] += dist; else sdf[y * W + x] += dist; }
+    }
+    if (d_params) for (size_t i = 0; i < acc.size(); i++) d_params[i] = (float)acc[i];
+    return 0;
+}

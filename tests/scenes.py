@@ -152,3 +152,46 @@ def batched_strokes(scene_index, canvas=64, num_strokes=16):
         groups.append(pydiffvg.ShapeGroup(torch.tensor([i]), fill_color=None,
                                           stroke_color=torch.stack([torch.tensor(1.0), torch.tensor(1.0), torch.tensor(1.0), a])))
     return canvas, canvas, shapes, groups
+
+
+def zoo_prefilter(canvas=128):
+    """Shapes the reference's SDF-prefiltering path supports (closest_point asserts on ellipses and never
+    finds circles, compute_distance.h:18-24, 354-372): rect, mixed path, thick open path, polygon +
+    filled circle group, open cubic stroke over a closed blob."""
+    shapes, groups = [], []
+    shapes.append(pydiffvg.Rect(p_min=torch.tensor([-14.0, -9.0]), p_max=torch.tensor([14.0, 9.0]), stroke_width=torch.tensor(1.5)))
+    groups.append(pydiffvg.ShapeGroup(torch.tensor([0]), fill_color=torch.tensor([0.2, 0.8, 0.8, 0.6]),
+                                      stroke_color=torch.tensor([0.0, 0.0, 0.0, 0.9]),
+                                      shape_to_canvas=torch.tensor([[1.0, 0.0, 40.0], [0.0, 1.0, 92.0], [0.0, 0.0, 1.0]])))
+    shapes.append(pydiffvg.Path(num_control_points=torch.tensor([0, 1, 2, 0]),
+                                points=torch.tensor([[-25.0, -25.0], [15.0, -23.0], [27.0, -5.0], [17.0, 15.0],
+                                                     [5.0, 30.0], [-15.0, 25.0], [-27.0, 17.0]]),
+                                is_closed=True, stroke_width=torch.tensor(2.0)))
+    c, s = 0.8660254 * 0.9, 0.5 * 0.9
+    groups.append(pydiffvg.ShapeGroup(torch.tensor([1]), use_even_odd_rule=False, fill_color=pydiffvg.RadialGradient(
+        center=torch.tensor([95.0, 95.0]), radius=torch.tensor([30.0, 24.0]), offsets=torch.tensor([0.1, 0.9]),
+        stop_colors=torch.tensor([[0.9, 0.9, 0.1, 1.0], [0.3, 0.1, 0.6, 0.5]])),
+        stroke_color=torch.tensor([0.4, 0.2, 0.1, 1.0]),
+        shape_to_canvas=torch.tensor([[c, -s, 95.0], [s, c, 95.0], [0.0, 0.0, 1.0]])))
+    shapes.append(pydiffvg.Path(num_control_points=torch.tensor([1, 2]),
+                                points=torch.tensor([[10.0, 70.0], [30.0, 50.0], [50.0, 75.0], [60.0, 95.0], [30.0, 100.0], [15.0, 118.0]]),
+                                is_closed=False, stroke_width=torch.tensor(2.25)))
+    groups.append(pydiffvg.ShapeGroup(torch.tensor([2]), fill_color=None, stroke_color=torch.tensor([0.5, 0.7, 0.2, 0.75])))
+    shapes.append(pydiffvg.Polygon(points=torch.tensor([[0.0, 0.0], [30.0, 4.0], [26.0, 28.0], [4.0, 22.0]]), is_closed=True,
+                                   stroke_width=torch.tensor(1.0)))
+    shapes.append(pydiffvg.Circle(radius=torch.tensor(9.0), center=torch.tensor([14.0, 13.0]), stroke_width=torch.tensor(1.0)))
+    groups.append(pydiffvg.ShapeGroup(torch.tensor([3, 4]), fill_color=torch.tensor([0.3, 0.3, 0.9, 0.85]),
+                                      stroke_color=torch.tensor([0.9, 0.6, 0.1, 1.0]),
+                                      shape_to_canvas=torch.tensor([[1.0, 0.0, 88.0], [0.0, 1.0, 4.0], [0.0, 0.0, 1.0]])))
+    shapes.append(pydiffvg.Path(num_control_points=torch.tensor([2, 2, 2]),
+                                points=torch.tensor([[20.0, 20.0], [35.0, 8.0], [52.0, 12.0], [60.0, 28.0], [66.0, 42.0],
+                                                     [48.0, 56.0], [34.0, 50.0], [22.0, 46.0], [12.0, 34.0]]),
+                                is_closed=True, stroke_width=torch.tensor(1.0)))
+    groups.append(pydiffvg.ShapeGroup(torch.tensor([5]), fill_color=pydiffvg.LinearGradient(
+        begin=torch.tensor([20.0, 10.0]), end=torch.tensor([60.0, 50.0]), offsets=torch.tensor([0.0, 1.0]),
+        stop_colors=torch.tensor([[0.9, 0.2, 0.1, 0.9], [0.1, 0.3, 0.9, 0.7]]))))
+    shapes.append(pydiffvg.Path(num_control_points=torch.tensor([2]),
+                                points=torch.tensor([[15.0, 15.0], [50.0, 20.0], [30.0, 60.0], [70.0, 55.0]]),
+                                is_closed=False, stroke_width=torch.tensor(3.0)))
+    groups.append(pydiffvg.ShapeGroup(torch.tensor([6]), fill_color=None, stroke_color=torch.tensor([0.1, 0.1, 0.1, 0.8])))
+    return canvas, canvas, shapes, groups

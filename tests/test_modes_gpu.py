@@ -1,0 +1,95 @@
+"""GPU parity tests (`-m gpu`) for SDF prefiltering, SDF output / eval_positions and the translation
+gradient of render_grad, through the C ABI, against the committed reference fixtures
+(tests/golden_modes/) and, where oracle/_ref is available, against the reference at larger sizes."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle_check
+import ref_oracle
+import scenes
+import util
+from golden import make_golden as mg
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+FIX = sorted(glob.glob(os.path.join(ROOT, 'tests', 'golden_modes', '*.npz')))
+
+
+def _check(g, out):
+    for k in ('image', 'sdf'):
+        if k in g.files:
+            assert np.abs(out[k] - g[k]).max() <= 1e-5, k            # forward: 1e-5 absolute
+    if np.linalg.norm(g['d_params']) > 0:
+        assert util.rel_l2(g['d_params'], out['d_params']) <= 1e-4   # gradients: 1e-4 relative (rel-L2)
+    else:
+        assert np.all(out['d_params'] == 0)
+    ref_t = g['d_translation']
+    assert util.rel_l2(ref_t, out['d_translation']) <= 1e-4 or np.abs(ref_t).max() == 0
+    if 'd_background' in g.files and int(g['config'][2]) * int(g['config'][3]) == 1:
+        assert np.abs(out['d_background'] - g['d_background']).max() <= 1e-5
+
+
+@pytest.mark.parametrize('path', FIX, ids=[os.path.basename(p)[:-4] for p in FIX])
+def test_mode_fixtures(path):
+    g = np.load(path)
+    name = os.path.basename(path)[:-4]
+    mode, _, W, H, nsx, nsy, seed, ft, fr, use_bg = mg.MODE_CASES[name]
+    out = mg.run_mode(util.gpu_render, name, mode, g['topo'], g['params'], W, H, nsx, nsy, seed, use_bg)
+    _check(g, out)
+
+
+@pytest.mark.skipif(not ref_oracle.available(), reason='oracle/_ref not built')
+def test_prefilter_blobs_512_vs_oracle():
+    """Fill-heavy proxy of the flower config: 1024 closed cubic blobs, 512^2, 2x2 spp, prefiltered."""
+    topo, params = util.pack(scenes.blobs())
+    W = H = 512
+    ref = oracle_check.render(topo, params, W, H, 2, 2, 0, use_prefiltering=True)['image']
+    got = util.gpu_render(topo, params, W, H, 2, 2, 0, use_prefiltering=True)['image']
+    assert np.abs(ref - got).max() <= 1e-5
+    assert abs(ref.astype(np.float64).sum() - 356627.6572) < 0.05   # SURVEY 8d known answer
+    d_img = np.random.RandomState(1).rand(H, W, 4).astype(np.float32) - 0.5
+    rb = oracle_check.render(topo, params, W, H, 2, 2, 0, use_prefiltering=True, d_render_image=d_img)
+    gb = util.gpu_render(topo, params, W, H, 2, 2, 0, use_prefiltering=True, d_render_image=d_img)
+    assert util.rel_l2(rb['d_params'], gb['d_params']) <= 1e-4
+
+
+@pytest.mark.skipif(not ref_oracle.available(), reason='oracle/_ref not built')
+def test_prefilter_painterly_strokes_vs_oracle():
+    topo, params = util.pack(scenes.painterly(256, 256))
+    W = H = 256
+    ref = oracle_check.render(topo, params, W, H, 2, 2, 3, use_prefiltering=True)['image']
+    got = util.gpu_render(topo, params, W, H, 2, 2, 3, use_prefiltering=True)['image']
+    assert np.abs(ref - got).max() <= 1e-5
+    d_img = np.random.RandomState(2).rand(H, W, 4).astype(np.float32) - 0.5
+    rb = oracle_check.render(topo, params, W, H, 2, 2, 3, use_prefiltering=True, d_render_image=d_img)
+    gb = util.gpu_render(topo, params, W, H, 2, 2, 3, use_prefiltering=True, d_render_image=d_img)
+    assert util.rel_l2(rb['d_params'], gb['d_params']) <= 1e-4
+
+
+def test_pydiffvg_sdf_and_eval_positions_api():
+    """test_eval_positions.py of the reference: SDF at explicit positions equals the SDF image sampled there."""
+    from diffvg_b200 import pydiffvg
+    pydiffvg.set_use_gpu(True)
+    pydiffvg.set_device(torch.device('cuda', 0))
+    cw, ch, shapes, groups = scenes.single_stroke()
+    shapes[0].points.requires_grad_(True)
+    args = pydiffvg.RenderFunction.serialize_scene(cw, ch, shapes, groups, output_type=pydiffvg.OutputType.sdf)
+    sdf = pydiffvg.RenderFunction.apply(256, 256, 1, 1, 0, None, *args)
+    assert sdf.shape == (256, 256, 1)
+    ep = torch.tensor([[100.5, 40.5], [30.25, 200.75], [128.0, 128.0]])
+    args2 = pydiffvg.RenderFunction.serialize_scene(cw, ch, shapes, groups, output_type=pydiffvg.OutputType.sdf,
+                                                    eval_positions=ep)
+    vals = pydiffvg.RenderFunction.apply(256, 256, 1, 1, 0, None, *args2)
+    assert vals.shape == (3, 1)
+    vals.sum().backward()
+    assert shapes[0].points.grad is not None and torch.isfinite(shapes[0].points.grad).all()
+    assert shapes[0].points.grad.abs().sum() > 0
+    # render_grad: translation gradient image
+    args3 = pydiffvg.RenderFunction.serialize_scene(cw, ch, shapes, groups)
+    tg = pydiffvg.RenderFunction.render_grad(torch.ones(256, 256, 4), 256, 256, 2, 2, 0, None, *args3)
+    assert tg.shape == (256, 256, 2) and torch.isfinite(tg).all() and tg.abs().sum() > 0

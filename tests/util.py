@@ -25,8 +25,10 @@ def image_report(ref, got, spp):
 
 
 def gpu_render(topo, params, width, height, nsx, nsy, seed, background=None, d_render_image=None,
-               skip_xform_grad=False):
-    """Drive the product C ABI directly (ctypes) with device buffers managed through torch."""
+               skip_xform_grad=False, use_prefiltering=False, want_image=True, want_sdf=False, eval_positions=None,
+               d_render_sdf=None, want_d_translation=False):
+    """Drive the product C ABI directly (ctypes) with device buffers managed through torch.  Same
+    keyword surface as oracle/ref_oracle.render."""
     import ctypes
     from diffvg_b200 import _native as n
     dev = torch.device('cuda', 0)
@@ -38,22 +40,32 @@ def gpu_render(topo, params, width, height, nsx, nsy, seed, background=None, d_r
         p = np.ascontiguousarray(params, np.float32)
         n.check(n.lib.dvg_scene_set_params(h, p.ctypes.data, p.shape[0], 0, stream))
         bg = torch.from_numpy(background).to(dev).contiguous() if background is not None else None
+        ep = torch.from_numpy(np.ascontiguousarray(eval_positions, np.float32)).to(dev) if eval_positions is not None else None
+        n_eval = 0 if ep is None else ep.shape[0]
+        ptr = lambda t: t.data_ptr() if t is not None else None
+        pf = 1 if use_prefiltering else 0
         out = {}
-        if d_render_image is None:
-            img = torch.empty(height, width, 4, device=dev)
-            n.check(n.lib.dvg_render_forward(h, bg.data_ptr() if bg is not None else None, img.data_ptr(), None,
-                                             width, height, nsx, nsy, int(seed), 0, None, 0, stream))
-            out['image'] = img.cpu().numpy()
+        if d_render_image is None and d_render_sdf is None:
+            img = torch.empty(height, width, 4, device=dev) if want_image else None
+            sdf = None
+            if want_sdf:
+                sdf = torch.empty((n_eval, 1) if n_eval else (height, width, 1), device=dev)
+            n.check(n.lib.dvg_render_forward(h, ptr(bg), ptr(img), ptr(sdf), width, height, nsx, nsy, int(seed), pf,
+                                             ptr(ep), n_eval, stream))
+            out['image'] = img.cpu().numpy() if img is not None else None
+            out['sdf'] = sdf.cpu().numpy() if sdf is not None else None
         else:
-            dimg = torch.from_numpy(np.ascontiguousarray(d_render_image, np.float32)).to(dev)
+            dimg = torch.from_numpy(np.ascontiguousarray(d_render_image, np.float32)).to(dev) if d_render_image is not None else None
+            dsdf = torch.from_numpy(np.ascontiguousarray(d_render_sdf, np.float32)).to(dev) if d_render_sdf is not None else None
             dpar = torch.empty(p.shape[0], device=dev)
             dbg = torch.empty_like(bg) if bg is not None else None
-            n.check(n.lib.dvg_render_backward(h, bg.data_ptr() if bg is not None else None, dimg.data_ptr(), None,
-                                              width, height, nsx, nsy, int(seed), 0, None, 0, dpar.data_ptr(),
-                                              dbg.data_ptr() if dbg is not None else None, None,
+            dtr = torch.empty(height, width, 2, device=dev) if want_d_translation else None
+            n.check(n.lib.dvg_render_backward(h, ptr(bg), ptr(dimg), ptr(dsdf), width, height, nsx, nsy, int(seed), pf,
+                                              ptr(ep), n_eval, dpar.data_ptr(), ptr(dbg), ptr(dtr),
                                               1 if skip_xform_grad else 0, stream))
             out['d_params'] = dpar.cpu().numpy()
             out['d_background'] = dbg.cpu().numpy() if dbg is not None else None
+            out['d_translation'] = dtr.cpu().numpy() if dtr is not None else None
         torch.cuda.synchronize()
         return out
     finally:
