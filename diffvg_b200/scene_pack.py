@@ -30,6 +30,7 @@ G_LEN = 12
 SHAPE_CIRCLE, SHAPE_ELLIPSE, SHAPE_PATH, SHAPE_RECT = 0, 1, 2, 3
 COLOR_NONE, COLOR_CONSTANT, COLOR_LINEAR, COLOR_RADIAL = -1, 0, 1, 2
 SF_CLOSED, SF_DISTANCE_APPROX = 1, 2
+_OPEN_FILL_WARNING = 'Detected non-closed paths with fill color. This might causes unexpected results.'
 
 
 # Parameter tensors are collected into a few "buckets" so that the flat `params` can be built
@@ -40,6 +41,7 @@ SF_CLOSED, SF_DISTANCE_APPROX = 1, 2
 # torch.eye(3) shared by every ShapeGroup) is stored once; autograd then sums the gradients
 # of all its uses, which is exactly what sharing a tensor means.
 B_POINTS, B_SCALAR, B_VEC4, B_MAT3, B_GENERIC, NUM_BUCKETS = 0, 1, 2, 3, 4, 5
+SRC_SHAPE, SRC_GROUP, SRC_FILTER = 0, 1, 2
 
 
 class _Buckets:
@@ -47,26 +49,34 @@ class _Buckets:
         self.tensors = [[] for _ in range(NUM_BUCKETS)]
         self.sizes = [0] * NUM_BUCKETS
         self.seen = {}
+        # where every entry came from: (holder list code, holder index, attribute, sub-attribute, numel);
+        # replayed by the memoised fast path of pack_scene
+        self.sources = [[] for _ in range(NUM_BUCKETS)]
+        self.src = (SRC_FILTER, 0)
 
-    def add(self, bucket, t, numel):
+    def at(self, code, index):
+        self.src = (code, index)
+
+    def add(self, bucket, t, numel, attr=None, sub=None):
         off = self.sizes[bucket]
         self.tensors[bucket].append(t)
+        self.sources[bucket].append((self.src[0], self.src[1], attr, sub, numel))
         self.sizes[bucket] = off + numel
         return off
 
-    def add_generic(self, t, expect):
+    def add_generic(self, t, expect, attr=None, sub=None):
         if not isinstance(t, torch.Tensor):
             t = torch.as_tensor(t, dtype=torch.float32)
         if t.numel() != expect:
             raise ValueError('expected a tensor of %d elements, got shape %s' % (expect, tuple(t.shape)))
-        return self.add(B_GENERIC, t, expect)
+        return self.add(B_GENERIC, t, expect, attr, sub)
 
-    def add_shared(self, bucket, t, numel):
+    def add_shared(self, bucket, t, numel, attr=None):
         key = id(t)
         hit = self.seen.get(key)
         if hit is not None and hit[0] is t:
             return hit[1]
-        off = self.add(bucket, t, numel)
+        off = self.add(bucket, t, numel, attr)
         self.seen[key] = (t, off)
         return off
 
@@ -84,45 +94,46 @@ def _np_cached(holder, attr, value):
     return arr
 
 
-def _pack_color(color, bk):
+def _pack_color(color, bk, attr):
     """-> (type, bucket, offset in bucket, num_stops)"""
     if color is None:
         return COLOR_NONE, B_GENERIC, 0, 0
     if isinstance(color, torch.Tensor):
         if color.dim() != 1 or color.shape[0] != 4:
             raise ValueError('a constant colour must be a tensor of 4 elements')
-        return COLOR_CONSTANT, B_VEC4, bk.add(B_VEC4, color, 4), 0
+        return COLOR_CONSTANT, B_VEC4, bk.add(B_VEC4, color, 4, attr), 0
     # duck-typed so that the reference's own holder classes are accepted too
     if hasattr(color, 'begin') and hasattr(color, 'end'):
         n = color.offsets.shape[0]
         if color.stop_colors.shape[0] != n:
             raise ValueError('gradient offsets / stop_colors length mismatch')
-        off = bk.add_generic(color.begin, 2)
-        bk.add_generic(color.end, 2)
-        bk.add_generic(color.offsets, n)
-        bk.add_generic(color.stop_colors, 4 * n)
+        off = bk.add_generic(color.begin, 2, attr, 'begin')
+        bk.add_generic(color.end, 2, attr, 'end')
+        bk.add_generic(color.offsets, n, attr, 'offsets')
+        bk.add_generic(color.stop_colors, 4 * n, attr, 'stop_colors')
         return COLOR_LINEAR, B_GENERIC, off, n
     if hasattr(color, 'center') and hasattr(color, 'radius'):
         n = color.offsets.shape[0]
         if color.stop_colors.shape[0] != n:
             raise ValueError('gradient offsets / stop_colors length mismatch')
-        off = bk.add_generic(color.center, 2)
-        bk.add_generic(color.radius, 2)
-        bk.add_generic(color.offsets, n)
-        bk.add_generic(color.stop_colors, 4 * n)
+        off = bk.add_generic(color.center, 2, attr, 'center')
+        bk.add_generic(color.radius, 2, attr, 'radius')
+        bk.add_generic(color.offsets, n, attr, 'offsets')
+        bk.add_generic(color.stop_colors, 4 * n, attr, 'stop_colors')
         return COLOR_RADIAL, B_GENERIC, off, n
     raise TypeError('unsupported colour %r' % (color,))
 
 
-def _add_width(bk, sw):
+def _add_width(bk, sw, attr='stroke_width'):
     if isinstance(sw, torch.Tensor) and sw.dim() == 0:
-        return B_SCALAR, bk.add(B_SCALAR, sw, 1)
-    return B_GENERIC, bk.add_generic(sw, 1)
+        return B_SCALAR, bk.add(B_SCALAR, sw, 1, attr)
+    return B_GENERIC, bk.add_generic(sw, 1, attr)
 
 
-def pack_scene(canvas_width, canvas_height, shapes, shape_groups, filter_type=0, filter_radius=None):
-    """Returns (topo: np.int32[], buckets: list[list[Tensor]]).  `concat_params(buckets)` is `params`."""
+def _pack_scene_full(canvas_width, canvas_height, shapes, shape_groups, filter_type, filter_radius):
+    """The complete walk: validates everything, returns (topo, _Buckets, warned)."""
     bk = _Buckets()
+    warned = False
     ns, ng = len(shapes), len(shape_groups)
     srec = []      # rows of DVG_SHAPE_REC_LEN ints (offsets still bucket-relative)
     sbucket = []   # (bucket of PARAM_OFF, bucket of WIDTH_OFF, bucket of THICK_OFF)
@@ -131,6 +142,7 @@ def pack_scene(canvas_width, canvas_height, shapes, shape_groups, filter_type=0,
     points_total = 0
     is_open_path = [False] * ns
     for i, shape in enumerate(shapes):
+        bk.at(SRC_SHAPE, i)
         kind = type(shape).__name__
         if kind == 'Path' or kind == 'Polygon':
             pts = shape.points
@@ -148,9 +160,9 @@ def pack_scene(canvas_width, canvas_height, shapes, shape_groups, filter_type=0,
             else:
                 ncp_np = np.zeros(npts if shape.is_closed else npts - 1, dtype=np.int32)
                 flags = SF_CLOSED if shape.is_closed else 0
-            poff = bk.add(B_POINTS, pts, 2 * npts)
+            poff = bk.add(B_POINTS, pts, 2 * npts, 'points')
             if use_thickness:
-                thick_off = bk.add_generic(shape.stroke_width, npts)
+                thick_off = bk.add_generic(shape.stroke_width, npts, 'stroke_width')
                 wb, woff = B_GENERIC, -1
             else:
                 wb, woff = _add_width(bk, shape.stroke_width)
@@ -164,16 +176,16 @@ def pack_scene(canvas_width, canvas_height, shapes, shape_groups, filter_type=0,
         else:
             if kind == 'Circle':
                 t = SHAPE_CIRCLE
-                poff = bk.add_generic(shape.radius, 1)
-                bk.add_generic(shape.center, 2)
+                poff = bk.add_generic(shape.radius, 1, 'radius')
+                bk.add_generic(shape.center, 2, 'center')
             elif kind == 'Ellipse':
                 t = SHAPE_ELLIPSE
-                poff = bk.add_generic(shape.radius, 2)
-                bk.add_generic(shape.center, 2)
+                poff = bk.add_generic(shape.radius, 2, 'radius')
+                bk.add_generic(shape.center, 2, 'center')
             elif kind == 'Rect':
                 t = SHAPE_RECT
-                poff = bk.add_generic(shape.p_min, 2)
-                bk.add_generic(shape.p_max, 2)
+                poff = bk.add_generic(shape.p_min, 2, 'p_min')
+                bk.add_generic(shape.p_max, 2, 'p_max')
             else:
                 raise TypeError('unsupported shape %r' % (shape,))
             wb, woff = _add_width(bk, shape.stroke_width)
@@ -186,29 +198,31 @@ def pack_scene(canvas_width, canvas_height, shapes, shape_groups, filter_type=0,
     gshape_total = 0
     any_open = any(is_open_path)
     for g, group in enumerate(shape_groups):
+        bk.at(SRC_GROUP, g)
         ids_np = _np_cached(group, 'ids', group.shape_ids)
         k = ids_np.shape[0]
         if k == 0:
             raise ValueError('shape group %d has no shapes' % g)
-        ft, fb, foff, fstops = _pack_color(group.fill_color, bk)
+        ft, fb, foff, fstops = _pack_color(group.fill_color, bk, 'fill_color')
         if ft != COLOR_NONE and any_open:
             # render_pytorch.py:131-136
             for sid in ids_np:
                 if 0 <= sid < ns and is_open_path[sid]:
-                    warnings.warn('Detected non-closed paths with fill color. This might causes unexpected results.',
-                                  Warning)
-        st, sb, soff, sstops = _pack_color(group.stroke_color, bk)
+                    warned = True
+                    warnings.warn(_OPEN_FILL_WARNING, Warning)
+        st, sb, soff, sstops = _pack_color(group.stroke_color, bk, 'stroke_color')
         xf = group.shape_to_canvas
         if xf.dim() != 2 or xf.shape[0] != 3 or xf.shape[1] != 3:
             raise ValueError('shape_to_canvas must be [3, 3]')
-        xoff = bk.add_shared(B_MAT3, xf, 9)
+        xoff = bk.add_shared(B_MAT3, xf, 9, 'shape_to_canvas')
         grec.append((gshape_total, k, ft, foff, fstops, st, soff, sstops, 1 if group.use_even_odd_rule else 0, xoff, 0, 0))
         gbucket.append((fb, sb))
         gshape_chunks.append(ids_np)
         gshape_total += k
 
     fr = filter_radius if filter_radius is not None else torch.tensor(0.5)
-    frb, froff = _add_width(bk, fr)
+    bk.at(SRC_FILTER, 0)
+    frb, froff = _add_width(bk, fr, None)
 
     # bucket bases in the final concatenation order
     base = [0] * NUM_BUCKETS
@@ -260,6 +274,145 @@ def pack_scene(canvas_width, canvas_height, shapes, shape_groups, filter_type=0,
         topo[off_ncp:off_gshapes] = np.concatenate(ncp_chunks)
     if gshape_total:
         topo[off_gshapes:] = gshapes
+    return topo, bk, warned
+
+
+# ---------------------------------------------------------------------------------------------
+# Memoised front: an optimisation loop calls serialize_scene every iteration with the same
+# holders and only the VALUES of their tensors changed.  The structural signature below (types,
+# point counts, flags, identity + version of the integer tensors, identity of the transform
+# tensors that decide sharing) is cheap to compute; when it matches a previous call, the topology
+# blob is reused and the parameter tensors are re-collected by replaying the recorded sources
+# (each checked against its recorded element count; any surprise falls back to the full walk).
+_MEMO = []
+_MEMO_MAX = 8
+_T = torch.Tensor
+
+
+def _sig_tensor(ap, t):
+    """Appends the structural facts of one parameter tensor as plain scalars (tuples and torch.Size
+    objects are avoided on purpose: thousands of live containers per call make the cyclic GC run)."""
+    if isinstance(t, _T):
+        n = t.dim()
+        ap(n)
+        ap(t.shape[0] if n else -1)
+    else:
+        ap(None)
+        ap(type(t))
+
+
+def _sig_color(ap, c):
+    if c is None:
+        ap(0)
+    elif isinstance(c, _T):
+        ap(1)
+        _sig_tensor(ap, c)
+    else:
+        ap(type(c))
+        _sig_tensor(ap, getattr(c, 'offsets', None))
+        _sig_tensor(ap, getattr(c, 'stop_colors', None))
+
+
+def _signature(canvas_width, canvas_height, shapes, shape_groups, filter_type, filter_radius):
+    sig = [int(canvas_width), int(canvas_height), int(filter_type), len(shapes), len(shape_groups)]
+    ap = sig.append
+    _sig_tensor(ap, filter_radius)
+    keep = []
+    kp = keep.append
+    for s in shapes:   # hot loop: inlined on purpose
+        d = s.__dict__
+        pts = d.get('points')
+        ap(type(s))
+        if pts is not None:
+            ncp = d.get('num_control_points')
+            kp(ncp)
+            ap(pts.shape[0])
+            ap(d.get('is_closed'))
+            ap(d.get('use_distance_approx'))
+            ap(id(ncp))
+            ap(ncp._version if ncp is not None else None)
+        sw = d.get('stroke_width')
+        if isinstance(sw, _T):
+            n = sw.dim()
+            ap(n)
+            if n:
+                ap(sw.shape[0])
+        else:
+            ap(type(sw))
+    for g in shape_groups:
+        d = g.__dict__
+        ids, xf = d['shape_ids'], d['shape_to_canvas']
+        kp(ids)
+        kp(xf)
+        ap(id(ids))
+        ap(ids._version)
+        ap(id(xf))
+        ap(d['use_even_odd_rule'])
+        c = d['fill_color']
+        if c is None:
+            ap(0)
+        elif isinstance(c, _T):
+            ap(c.dim())
+            ap(c.shape[0])
+        else:
+            _sig_color(ap, c)
+        c = d['stroke_color']
+        if c is None:
+            ap(0)
+        elif isinstance(c, _T):
+            ap(c.dim())
+            ap(c.shape[0])
+        else:
+            _sig_color(ap, c)
+    return sig, keep
+
+
+def _replay(sources, shapes, shape_groups, filter_radius):
+    holders = (shapes, shape_groups)
+    out = []
+    for bucket_sources in sources:
+        ts = []
+        for code, index, attr, sub, numel in bucket_sources:
+            if code == SRC_FILTER:
+                t = filter_radius
+            else:
+                t = getattr(holders[code][index], attr)
+                if sub is not None:
+                    t = getattr(t, sub)
+            if not isinstance(t, _T):
+                t = torch.as_tensor(t, dtype=torch.float32)
+            if t.numel() != numel:
+                return None
+            ts.append(t)
+        out.append(ts)
+    return out
+
+
+def pack_scene(canvas_width, canvas_height, shapes, shape_groups, filter_type=0, filter_radius=None):
+    """Returns (topo: np.int32[], buckets: list[list[Tensor]]).  `concat_params(buckets)` is `params`."""
+    if filter_radius is None:
+        filter_radius = torch.tensor(0.5)
+    sig = keep = None
+    try:
+        sig, keep = _signature(canvas_width, canvas_height, shapes, shape_groups, filter_type, filter_radius)
+    except Exception:
+        sig = None   # malformed holders: the full walk raises the proper error
+    if sig is not None:
+        for k, m in enumerate(_MEMO):
+            if m[0] == sig:
+                tensors = _replay(m[3], shapes, shape_groups, filter_radius)
+                if tensors is None:
+                    break
+                if m[4]:
+                    warnings.warn(_OPEN_FILL_WARNING, Warning)
+                if k:
+                    _MEMO.insert(0, _MEMO.pop(k))
+                return m[2], tensors
+    topo, bk, warned = _pack_scene_full(canvas_width, canvas_height, shapes, shape_groups, filter_type, filter_radius)
+    if sig is not None:
+        topo.setflags(write=False)
+        _MEMO.insert(0, (sig, keep, topo, bk.sources, warned))
+        del _MEMO[_MEMO_MAX:]
     return topo, bk.tensors
 
 

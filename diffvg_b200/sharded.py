@@ -1,0 +1,157 @@
+"""One-process-per-GPU sharding of the render path.
+
+The path shards with no data-path exchange: every pixel sample and every boundary sample is
+independent given the replicated scene, and its RNG stream is a function of the GLOBAL sample
+index only (pcg.h:32-40), so any partition of the index space reproduces the single-GPU sample
+set.  Two partitions are offered:
+
+  * one large render (C3 / C4): rank r owns a contiguous band of pixel rows, aligned to the
+    tile height, and the boundary-sample indices of the same rows (`row_partition`,
+    `ShardedRenderFunction`).  Forward: the bands are assembled with one all-gather (a band is
+    rows*W*4 floats).  Backward: every rank holds the full d_image (the loss is computed on the
+    assembled image), runs `dvg_render_backward_rows` on its band, and the per-rank gradient
+    buffers `float[num_params]` are summed with ONE all-reduce.
+  * batched scenes (C5): scenes are dealt to ranks by index (`batch_partition`); per-scene
+    gradients need no exchange, shared upstream parameters are all-reduced by the caller (DDP).
+
+`torch.distributed` is plumbing only (NCCL on the GPUs, gloo in the CPU tests); the kernels are
+in libdiffvg_b200.so.  The collectives operate on whatever device the tensors live on, which
+is what lets tests/test_sharding_cpu.py exercise this file with world_size 2 on gloo.
+"""
+import torch
+import torch.distributed as dist
+
+
+def row_partition(height, world, align=1):
+    """[(row_begin, row_end)] * world: contiguous bands covering [0, height), every interior
+    boundary a multiple of `align` (the tile height, so that no tile is split between ranks).
+    Ranks may receive empty bands when height / align < world."""
+    assert height >= 0 and world >= 1 and align >= 1
+    units = (height + align - 1) // align
+    out = []
+    for r in range(world):
+        b = min(height, ((units * r) // world) * align)
+        e = min(height, ((units * (r + 1)) // world) * align)
+        out.append((b, e))
+    return out
+
+
+def stripe_partition(height, world, stripe=16):
+    """Round-robin stripes of `stripe` rows: [[(b, e), ...]] * world.  Balances non-uniform content
+    (SURVEY 8e 'efficiency risks'); each stripe is one *_rows call."""
+    out = [[] for _ in range(world)]
+    for k, b in enumerate(range(0, height, stripe)):
+        out[k % world].append((b, min(height, b + stripe)))
+    return out
+
+
+def batch_partition(num_scenes, world):
+    """[range] * world: scene b goes to rank b % world (seeds differ per scene, so the deal is
+    cost-balanced in expectation)."""
+    return [range(r, num_scenes, world) for r in range(world)]
+
+
+def sample_range(rows, width, spp):
+    """Global sample-index range [begin, end) of a row band: idx = ((y*W + x)*nsy + sy)*nsx + sx
+    (diffvg.cpp:1168-1176) is row-major in y, so a band of rows is one contiguous range; the same
+    range of boundary-sample indices goes with it (diffvg.cpp:1332-1336)."""
+    b, e = rows
+    return b * width * spp, e * width * spp
+
+
+def allgather_rows(band, bands, group=None):
+    """Assemble the full image from per-rank row bands (band: [rows_r, W, C])."""
+    world = dist.get_world_size(group)
+    if world == 1:
+        return band
+    assert len(bands) == world
+    w, c = band.shape[1], band.shape[2]
+    rmax = max(e - b for b, e in bands)   # bands differ by at most one alignment unit: pad to equal size
+    mine = band.contiguous()
+    if mine.shape[0] < rmax:
+        mine = torch.cat([mine, mine.new_zeros(rmax - mine.shape[0], w, c)], dim=0)
+    buf = torch.empty(world, rmax, w, c, dtype=band.dtype, device=band.device)
+    dist.all_gather_into_tensor(buf, mine, group=group) if band.is_cuda else \
+        dist.all_gather(list(buf.unbind(0)), mine, group=group)
+    return torch.cat([buf[r, :e - b] for r, (b, e) in enumerate(bands)], dim=0)
+
+
+def allreduce_gradients(d_params, group=None):
+    """Sum the per-rank gradient buffers in place (the only collective on the backward path:
+    num_params floats, 155 KB at the painterly config -- latency-bound on NVSwitch)."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(d_params, op=dist.ReduceOp.SUM, group=group)
+    return d_params
+
+
+class ShardedRenderFunction(torch.autograd.Function):
+    """`RenderFunction.apply` for one large render split by pixel rows over the ranks of `group`.
+    Every rank calls it with the same scene / seed and gets the full image; gradients w.r.t. the packed
+    parameters are complete (summed over ranks) on every rank.  Colour output only."""
+
+    @staticmethod
+    def forward(ctx, width, height, num_samples_x, num_samples_y, seed, background_image, packed, params, group=None):
+        from .pydiffvg import render_pytorch as rp
+        n = rp._native()
+        dev = rp._cuda_device()
+        assert packed.output_type == rp.OutputType.color, 'the SDF output is not row-sharded'
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
+        ns = rp._get_native_scene(packed, dev.index)
+        tile_h = tile_height(num_samples_x * num_samples_y)
+        bands = row_partition(height, world, tile_h)
+        rb, re = bands[rank]
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream().cuda_stream
+            version = ns.set_params(params, stream)
+            if background_image is not None:
+                background_image = background_image.to(dev).contiguous().float()
+                assert background_image.shape == (height, width, 4)
+            full = torch.zeros(height, width, 4, device=dev, dtype=torch.float32)
+            n.check(n.lib.dvg_render_forward_rows(
+                ns.handle, background_image.data_ptr() if background_image is not None else None, full.data_ptr(),
+                width, height, num_samples_x, num_samples_y, int(seed), 1 if packed.use_prefiltering else 0,
+                rb, re, stream))
+            img = allgather_rows(full[rb:re], bands, group) if world > 1 else full
+        ctx.native_scene, ctx.scene_version, ctx.packed = ns, version, packed
+        ctx.background_image = background_image
+        ctx.geom = (width, height, num_samples_x, num_samples_y, seed, rb, re)
+        ctx.device, ctx.params_device, ctx.group = dev, params.device, group
+        ctx.save_for_backward(params)
+        return img
+
+    @staticmethod
+    def backward(ctx, grad_img):
+        from .pydiffvg import render_pytorch as rp
+        n = rp._native()
+        dev, ns = ctx.device, ctx.native_scene
+        (params,) = ctx.saved_tensors
+        width, height, nsx, nsy, seed, rb, re = ctx.geom
+        bg = ctx.background_image
+        grad_img = grad_img.to(dev).float().contiguous()
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream().cuda_stream
+            if ns.version != ctx.scene_version:
+                ctx.scene_version = ns.set_params(params, stream)
+            d_params = torch.empty(ctx.packed.num_params, device=dev, dtype=torch.float32)
+            d_bg = torch.zeros_like(bg) if bg is not None else None
+            n.check(n.lib.dvg_render_backward_rows(
+                ns.handle, bg.data_ptr() if bg is not None else None, grad_img.data_ptr(),
+                width, height, nsx, nsy, int(seed), 1 if ctx.packed.use_prefiltering else 0, rb, re,
+                d_params.data_ptr(), d_bg.data_ptr() if d_bg is not None else None, 0, stream))
+            allreduce_gradients(d_params, ctx.group)
+            if d_bg is not None:
+                allreduce_gradients(d_bg, ctx.group)
+        if d_params.device != ctx.params_device:
+            d_params = d_params.to(ctx.params_device)
+        return None, None, None, None, None, d_bg, None, d_params, None
+
+
+def tile_height(spp):
+    """Tile height the library bins with for `spp` samples per pixel (csrc/dvg_capi.cu choose_tile):
+    row bands are aligned to it so that a tile never straddles two ranks."""
+    if spp >= 16:
+        return 2
+    if spp >= 2:
+        return 8
+    return 16

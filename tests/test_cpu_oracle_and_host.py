@@ -242,3 +242,40 @@ def test_product_fails_loudly_without_cuda():
     args = pydiffvg.RenderFunction.serialize_scene(cw, ch, shapes, groups)
     with pytest.raises(RuntimeError):
         pydiffvg.RenderFunction.apply(16, 16, 1, 1, 0, None, *args)
+
+
+def test_pack_scene_memo_reuses_topology_and_tracks_changes():
+    """The memoised front of pack_scene (scene_pack.py): same holders + new VALUES -> same topology
+    object, tensors re-collected; any structural change -> a fresh full walk with a different blob."""
+    import scenes
+    cw, ch, shapes, groups = scenes.painterly(num_paths=16, canvas=64)
+    fr = torch.tensor(0.5)
+    topo0, b0 = scene_pack.pack_scene(cw, ch, shapes, groups, 0, fr)
+    p0 = scene_pack.concat_params(b0)
+    shapes[3].points = shapes[3].points + 1.0                 # new tensor object, same structure
+    topo1, b1 = scene_pack.pack_scene(cw, ch, shapes, groups, 0, fr)
+    assert topo1 is topo0
+    p1 = scene_pack.concat_params(b1)
+    assert p1.shape == p0.shape and not torch.equal(p0, p1)
+    # against an un-memoised walk
+    topo_full, bk, _ = scene_pack._pack_scene_full(cw, ch, shapes, groups, 0, fr)
+    assert np.array_equal(topo_full, topo1)
+    assert torch.equal(scene_pack.concat_params(bk.tensors), p1)
+    # structural changes must miss the memo
+    shapes[5].is_closed = True
+    topo2, _ = scene_pack.pack_scene(cw, ch, shapes, groups, 0, fr)
+    assert topo2 is not topo0 and not np.array_equal(topo2, topo0)
+    shapes[5].is_closed = False
+    groups[2].fill_color = torch.tensor([0.1, 0.2, 0.3, 1.0])
+    with pytest.warns(Warning):
+        topo3, b3 = scene_pack.pack_scene(cw, ch, shapes, groups, 0, fr)
+    assert int(topo3[scene_pack.H_NPARAMS]) == int(topo0[scene_pack.H_NPARAMS]) + 4
+    groups[2].fill_color = None
+    shapes[7].stroke_width = torch.tensor([1.0, 2.0, 1.5, 0.5][:shapes[7].points.shape[0]] +
+                                          [1.0] * max(0, shapes[7].points.shape[0] - 4))   # per-point thickness
+    topo4, _ = scene_pack.pack_scene(cw, ch, shapes, groups, 0, fr)
+    assert not np.array_equal(topo4, topo0)
+    # a tensor whose element count no longer matches the recorded one falls back to the full walk (which raises)
+    groups[1].stroke_color = torch.rand(3)
+    with pytest.raises(ValueError):
+        scene_pack.pack_scene(cw, ch, shapes, groups, 0, fr)
