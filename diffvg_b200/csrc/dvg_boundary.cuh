@@ -46,7 +46,7 @@ struct BoundarySample {
 
 // cos/sin of 2*pi*t as the reference computes them: float argument, double ::cos/::sin,
 // multiplied by a float radius in double, rounded on store (sample_boundary.h:31-34).
-DVG_HD F2 circle_offset(float radius, float t) {
+DVG_HD_NOINLINE F2 circle_offset(float radius, float t) {
     float arg = 2 * (float)DVG_PI_D * t;
     return mk2((float)((double)radius * cos((double)arg)), (float)((double)radius * sin((double)arg)));
 }

@@ -21,6 +21,9 @@ namespace {
 thread_local std::string g_err;
 float *g_debug_out = nullptr;  // dvg_debug_set_boundary_dump
 bool g_fast_accept = false;    // dvg_set_fast_stroke_accept
+// A/B switch for measurements: DVG_FUSED=1 in the environment selects the one-kernel-per-pass form of
+// dvg_render.cu instead of the wavefront passes of dvg_wave.cu (same arithmetic, same results).
+bool g_fused = getenv("DVG_FUSED") != nullptr && getenv("DVG_FUSED")[0] == '1';
 
 int fail(int code, const std::string &msg) {
     g_err = msg;
@@ -81,6 +84,14 @@ struct DvgScene {
     int w_w = 0, w_h = 0, w_nsx = 0, w_nsy = 0, w_ftype = -1;
     uint64_t w_seed = 0; float w_radius = 0; bool w_valid = false;
     DevBuf d_keys, d_tile_counts, d_tile_offsets, d_tile_fill, d_blk_counts, d_blk_offsets, d_sorted;
+    // wavefront passes (dvg_wave.cu)
+    DevBuf d_wave_hit, d_wave_wind, d_wave_pairs_s, d_wave_pairs_f, d_wave_counters, d_tile_nch, d_tile_choff,
+        d_edge_chunks, d_edge_choff, d_wave_max;
+    int total_chunks = 0, max_nch = 0;   // of the current bins (read back with the bin total)
+    bool has_fills = false;
+    // which pixel pass the result words currently hold (forward's are reused by the interior backward pass)
+    bool wpx_valid = false;
+    int wpx_w = 0, wpx_h = 0, wpx_nsx = 0, wpx_nsy = 0, wpx_r0 = 0, wpx_r1 = 0, wpx_pf = 0; uint64_t wpx_seed = 0; uint32_t wpx_fast = 0;
     int32_t *h_pinned = nullptr;  // [0] error flag, [1] total bin items
     float *h_params_pinned = nullptr;  // staging for host-resident params (true async H2D)
     cudaEvent_t h_params_free = nullptr;  // recorded after the H2D copy that last read the staging buffer
@@ -137,7 +148,9 @@ struct DvgScene {
                          &d_prim_point_id, &d_params, &d_shapes_length, &d_shape_box, &d_shape_r0, &d_seg_cdf, &d_seg_pmf,
                          &d_seg_point_id, &d_insts, &d_groups, &d_p01, &d_p23, &d_rad, &d_box, &d_thick, &d_meta, &d_cbox, &d_cbox_pf, &d_cap,
                          &d_shape_cdf, &d_shape_pmf, &d_flags, &d_bin_counts, &d_bin_offsets, &d_bin_items, &d_weight,
-                         &d_keys, &d_tile_counts, &d_tile_offsets, &d_tile_fill, &d_blk_counts, &d_blk_offsets, &d_sorted};
+                         &d_keys, &d_tile_counts, &d_tile_offsets, &d_tile_fill, &d_blk_counts, &d_blk_offsets, &d_sorted,
+                         &d_wave_hit, &d_wave_wind, &d_wave_pairs_s, &d_wave_pairs_f, &d_wave_counters, &d_tile_nch, &d_tile_choff,
+                         &d_edge_chunks, &d_edge_choff, &d_wave_max};
         for (DevBuf *b : all) b->release();
         if (h_pinned) cudaFreeHost(h_pinned);
         h_pinned = nullptr;
@@ -269,9 +282,18 @@ int ensure_bins(DvgScene *s, int width, int height, int spp, int pf, cudaStream_
     bb.counts = s->d_bin_counts.as<int>(); bb.offsets = s->d_bin_offsets.as<int>(); bb.items = nullptr;
     BuildView bv = s->build_view();
     launch_bin_count(bv, bb, st);
+    CK(s->d_tile_nch.ensure(sizeof(int) * ntiles));
+    CK(s->d_tile_choff.ensure(sizeof(int) * (ntiles + 1)));
+    CK(s->d_wave_max.ensure(sizeof(int)));
+    launch_wave_tile_chunks(bb.offsets, s->d_tile_nch.as<int>(), s->d_tile_choff.as<int>(), s->d_wave_max.as<int>(), ntiles, st);
     CK(cudaMemcpyAsync(s->h_pinned + 3, bb.offsets + ntiles, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(s->h_pinned + 4, s->d_tile_choff.as<int>() + ntiles, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(s->h_pinned + 5, s->d_wave_max.p, 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     const int total = s->h_pinned[3];
+    s->total_chunks = s->h_pinned[4];
+    s->max_nch = s->h_pinned[5];
+    s->wpx_valid = false;
     CK(s->d_bin_items.ensure(sizeof(int) * std::max(total, 1)));
     bb.items = s->d_bin_items.as<int>();
     launch_bin_fill(bv, bb, st);
@@ -290,6 +312,103 @@ int ensure_weight(DvgScene *s, const SceneView &sc, RenderArgs &ra, cudaStream_t
     launch_weight(sc, ra, st);
     s->w_valid = true; s->w_w = ra.width; s->w_h = ra.height; s->w_nsx = ra.nsx; s->w_nsy = ra.nsy;
     s->w_seed = ra.seed; s->w_ftype = sc.filter.type; s->w_radius = sc.filter.radius;
+    return DVG_OK;
+}
+
+// ---- wavefront passes: workspace sizing and the classify -> (count read-back) -> solve sequence
+int wave_view(DvgScene *s, int64_t chunk_slots, int64_t evals, WaveView *out) {
+    const int64_t words = chunk_slots * 32;
+    if (words >= ((int64_t)1 << 27)) return fail(DVG_ERR_UNSUPPORTED, "render too large for the 27-bit result-word index of the pair queue");
+    CK(s->d_wave_hit.ensure(sizeof(unsigned) * (size_t)std::max<int64_t>(words, 1)));
+    if (s->has_fills) CK(s->d_wave_wind.ensure(sizeof(unsigned) * 4 * (size_t)std::max<int64_t>(words, 1)));
+    CK(s->d_wave_counters.ensure(sizeof(int) * 2));
+    CK(s->d_edge_choff.ensure(sizeof(int) * 4));   // real size set by the boundary pass
+    // first guess for the pair queues: two exact tests per evaluation; grown on demand (wave_classify_and_solve)
+    if (!s->d_wave_pairs_s.p) CK(s->d_wave_pairs_s.ensure(sizeof(WavePair) * (size_t)std::max<int64_t>(2 * evals, 1 << 16)));
+    if (s->has_fills && !s->d_wave_pairs_f.p) CK(s->d_wave_pairs_f.ensure(sizeof(WavePair) * (size_t)std::max<int64_t>(4 * evals, 1 << 16)));
+    WaveView wv;
+    wv.hit = s->d_wave_hit.as<unsigned>();
+    wv.wind = s->has_fills ? s->d_wave_wind.as<unsigned>() : nullptr;
+    wv.pairs_s = s->d_wave_pairs_s.as<WavePair>(); wv.cap_s = (int)std::min<size_t>(s->d_wave_pairs_s.cap / sizeof(WavePair), 0x7fffffff);
+    wv.pairs_f = s->d_wave_pairs_f.as<WavePair>(); wv.cap_f = (int)std::min<size_t>(s->d_wave_pairs_f.cap / sizeof(WavePair), 0x7fffffff);
+    wv.counters = s->d_wave_counters.as<int>();
+    wv.tile_choff = s->d_tile_choff.as<int>();
+    wv.edge_choff = s->d_edge_choff.as<int>();
+    *out = wv;
+    return DVG_OK;
+}
+
+// Runs `classify` (W1), reads the two pair counts back (the one synchronisation of a pass), grows a queue and
+// repeats W1 if it overflowed, then launches the exact tests (W2).
+template <typename Classify>
+int wave_classify_and_solve(DvgScene *s, const SceneView &sc, WaveView &wv, cudaStream_t st, const Classify &classify) {
+    for (int attempt = 0; attempt < 3; attempt++) {
+        CK(cudaMemsetAsync(wv.counters, 0, sizeof(int) * 2, st));
+        classify(wv);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(s->h_pinned + 6, wv.counters, sizeof(int) * 2, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        const int ns = s->h_pinned[6], nf = s->h_pinned[7];
+        if (ns < 0 || nf < 0) return fail(DVG_ERR_UNSUPPORTED, "more than 2^31 exact tests in one pass");
+        if (ns <= wv.cap_s && nf <= wv.cap_f) {
+            launch_wave_solve(sc, wv, ns, nf, st);
+            CK(cudaGetLastError());
+            return DVG_OK;
+        }
+        if (ns > wv.cap_s) {
+            CK(s->d_wave_pairs_s.ensure(sizeof(WavePair) * (size_t)ns));
+            wv.pairs_s = s->d_wave_pairs_s.as<WavePair>(); wv.cap_s = (int)std::min<size_t>(s->d_wave_pairs_s.cap / sizeof(WavePair), 0x7fffffff);
+        }
+        if (nf > wv.cap_f) {
+            CK(s->d_wave_pairs_f.ensure(sizeof(WavePair) * (size_t)nf));
+            wv.pairs_f = s->d_wave_pairs_f.as<WavePair>(); wv.cap_f = (int)std::min<size_t>(s->d_wave_pairs_f.cap / sizeof(WavePair), 0x7fffffff);
+        }
+    }
+    return fail(DVG_ERR_CUDA, "pair queue kept overflowing");
+}
+
+// Pixel pass (forward, or the interior term of the backward pass): the result words of a forward pass are
+// reused by the backward pass of the same (scene, size, samples, seed, rows).
+int wave_pixel_pass(DvgScene *s, const SceneView &sc, const BinView &bins, const RenderArgs &ra, bool backward, cudaStream_t st) {
+    const int64_t wpt = wave_items_per_tile(bins, ra);
+    const int items = wave_pixel_items(bins, ra);
+    WaveView wv;
+    int rc = wave_view(s, (int64_t)s->total_chunks * wpt, (int64_t)items * 32, &wv);
+    if (rc) return rc;
+    const uint32_t fast = ra.flags & DVG_RF_FAST_ACCEPT;
+    const bool reuse = s->wpx_valid && s->wpx_w == ra.width && s->wpx_h == ra.height && s->wpx_nsx == ra.nsx && s->wpx_nsy == ra.nsy &&
+                       s->wpx_seed == ra.seed && s->wpx_r0 == ra.row_begin && s->wpx_r1 == ra.row_end &&
+                       s->wpx_pf == ra.use_prefiltering && s->wpx_fast == fast;
+    if (!reuse) {
+        s->wpx_valid = false;
+        rc = wave_classify_and_solve(s, sc, wv, st, [&](const WaveView &v) { launch_wave_classify_px(sc, bins, ra, v, st); });
+        if (rc) return rc;
+        s->wpx_valid = true; s->wpx_w = ra.width; s->wpx_h = ra.height; s->wpx_nsx = ra.nsx; s->wpx_nsy = ra.nsy;
+        s->wpx_seed = ra.seed; s->wpx_r0 = ra.row_begin; s->wpx_r1 = ra.row_end; s->wpx_pf = ra.use_prefiltering; s->wpx_fast = fast;
+    }
+    launch_wave_composite_px(sc, bins, ra, wv, backward, st);
+    CK(cudaGetLastError());
+    return DVG_OK;
+}
+
+// Boundary pass (diffvg.cpp:1558-1626).  `bw` comes with its sort buffers bound.
+int wave_edge_pass(DvgScene *s, const SceneView &sc, const BinView &bins, const RenderArgs &ra, BoundaryWork &bw, cudaStream_t st) {
+    const int ntiles = bins.tiles_x * bins.tiles_y;
+    const int spi = wave_edge_samples_per_item();
+    bw.max_blocks = bw.num_samples / spi + ntiles;        // upper bound on the boundary items
+    CK(s->d_edge_chunks.ensure(sizeof(int) * ntiles));
+    CK(s->d_edge_choff.ensure(sizeof(int) * (ntiles + 1)));
+    WaveView wv;
+    // every item of a tile has that tile's chunk count: bounded by max_nch without another read-back
+    int rc = wave_view(s, (int64_t)bw.max_blocks * std::max(s->max_nch, 1), (int64_t)bw.max_blocks * 32, &wv);
+    if (rc) return rc;
+    s->wpx_valid = false;   // the result words are about to be overwritten
+    launch_wave_boundary_sort(sc, bins, ra, bw, wv, s->d_edge_chunks.as<int>(), st);
+    CK(cudaGetLastError());
+    rc = wave_classify_and_solve(s, sc, wv, st, [&](const WaveView &v) { launch_wave_classify_edge(sc, bins, ra, bw, v, st); });
+    if (rc) return rc;
+    launch_wave_composite_edge(sc, bins, ra, bw, wv, st);
+    CK(cudaGetLastError());
     return DVG_OK;
 }
 
@@ -328,6 +447,8 @@ int dvg_scene_create(const int32_t *topo, int64_t topo_len, int device, DvgScene
     s->num_shapes = t[DVG_H_NUM_SHAPES]; s->num_groups = t[DVG_H_NUM_GROUPS];
     s->num_params = t[DVG_H_NUM_PARAMS]; s->total_segs = t[DVG_H_TOTAL_SEGS];
     s->num_insts = t[DVG_H_TOTAL_GSHAPES];
+    for (int g = 0; g < s->num_groups; g++)
+        if (t[t[DVG_H_OFF_GROUPS] + g * DVG_GROUP_REC_LEN + DVG_G_FILL_TYPE] >= 0) s->has_fills = true;
     // instances and primitives in (group, shape-in-group, segment) order
     for (int g = 0; g < s->num_groups; g++) {
         const int32_t *r = t + t[DVG_H_OFF_GROUPS] + g * DVG_GROUP_REC_LEN;
@@ -408,6 +529,7 @@ int dvg_scene_set_params(DvgScene *s, const float *params, int64_t num_params, i
     s->checked = false;
     s->scene_error = 0;
     s->bin_w = s->bin_h = 0;   // bins depend on the geometry
+    s->wpx_valid = false;
     s->w_valid = s->w_valid && true;  // the weight image does not depend on the scene, only on the filter (checked later)
     return DVG_OK;
 }
@@ -448,7 +570,8 @@ static int render_forward_impl(DvgScene *s, const float *background, float *rend
         if (rc) return rc;
         CK(cudaMemsetAsync(render_image + 4 * (size_t)row_begin * width, 0, sizeof(float) * 4 * (size_t)width * (row_end - row_begin), st));
         if (use_prefiltering) launch_render_pf_forward(sc, s->bin_view(), ra, st);
-        else launch_render_forward(sc, s->bin_view(), ra, st);
+        else if (g_fused) launch_render_forward(sc, s->bin_view(), ra, st);
+        else { rc = wave_pixel_pass(s, sc, s->bin_view(), ra, false, st); if (rc) return rc; }
         CK(cudaGetLastError());
     }
     if (render_sdf) {
@@ -522,7 +645,8 @@ static int render_backward_impl(DvgScene *s, const float *background, const floa
             launch_render_pf_backward(sc, bins, ra, st);
             CK(cudaGetLastError());
         } else {
-            launch_render_backward(sc, bins, ra, st);
+            if (g_fused) launch_render_backward(sc, bins, ra, st);
+            else { rc = wave_pixel_pass(s, sc, bins, ra, true, st); if (rc) return rc; }
             CK(cudaGetLastError());
             // boundary term (diffvg.cpp:1558-1626): boundary-sample indices of the owned rows
             const int spp = nsx * nsy;
@@ -540,9 +664,14 @@ static int render_backward_impl(DvgScene *s, const float *background, const floa
                 bw.tile_counts = s->d_tile_counts.as<int>(); bw.tile_fill = s->d_tile_fill.as<int>();
                 bw.blk_counts = s->d_blk_counts.as<int>();
                 bw.tile_offsets = s->d_tile_offsets.as<int>(); bw.blk_offsets = s->d_blk_offsets.as<int>();
-                bw.max_blocks = bw.num_samples / edge_samples_per_block() + ntiles;
-                launch_boundary(sc, bins, ra, bw, st);
-                CK(cudaGetLastError());
+                if (g_fused) {
+                    bw.max_blocks = bw.num_samples / edge_samples_per_block() + ntiles;
+                    launch_boundary(sc, bins, ra, bw, st);
+                    CK(cudaGetLastError());
+                } else {
+                    rc = wave_edge_pass(s, sc, bins, ra, bw, st);
+                    if (rc) return rc;
+                }
             }
         }
     }

@@ -35,8 +35,8 @@ struct GradCache {
 struct CacheSink {
     GradCache *gc;
     float *D;
-    __device__ __forceinline__ void add(int idx, float v) const {
-        if (v == 0.f) return;
+    // out of line on purpose: the boundary kernel has ~30 call sites and is instruction-fetch bound
+    __device__ __noinline__ void add_slow(int idx, float v) const {
         unsigned h = ((unsigned)idx * 2654435761u) >> (32 - DVG_GC_LOG2);
 #pragma unroll 1
         for (int probe = 0; probe < 16; probe++) {
@@ -46,6 +46,10 @@ struct CacheSink {
             h = (h + 1) & (DVG_GC_SLOTS - 1);
         }
         atomicAdd(D + idx, v);
+    }
+    __device__ __forceinline__ void add(int idx, float v) const {
+        if (v == 0.f) return;
+        add_slow(idx, v);
     }
 };
 __device__ __forceinline__ void grad_cache_init(GradCache &gc) {
@@ -76,8 +80,7 @@ DVG_HD float gradient_t(int type, const float *c, F2 pt) {
 DVG_HD F4 load4(const float *p) { return mk4(p[0], p[1], p[2], p[3]); }
 
 // diffvg.cpp:276-368.  `c` points at the colour record inside params.
-DVG_HD F4 eval_color(int type, const float *c, int num_stops, F2 pt) {
-    if (type == 0) return load4(c);
+DVG_HD_NOINLINE F4 eval_color_gradient(int type, const float *c, int num_stops, F2 pt) {
     float t = gradient_t(type, c, pt);
     const float *offsets = c + 4;
     const float *colors = c + 4 + num_stops;
@@ -92,6 +95,10 @@ DVG_HD F4 eval_color(int type, const float *c, int num_stops, F2 pt) {
     }
     return load4(colors + 4 * (num_stops - 1));
 }
+DVG_HD F4 eval_color(int type, const float *c, int num_stops, F2 pt) {
+    if (type == 0) return load4(c);
+    return eval_color_gradient(type, c, num_stops, pt);
+}
 
 template <typename Sink>
 DVG_D void add4(const Sink &sk, int d, F4 v) {
@@ -103,7 +110,7 @@ DVG_D void add4(const Sink &sk, int d, F4 v) {
 // Q3: the radial branch has no `return` after the matched stop, so d_color is also
 // added to the last stop; reproduced.
 template <typename Sink>
-DVG_D void d_eval_gradient(int type, const float *c, int num_stops, F2 pt, F4 d_color, const Sink &sk, int d, float *d_translation) {
+DVG_D_NOINLINE void d_eval_gradient(int type, const float *c, int num_stops, F2 pt, F4 d_color, const Sink &sk, int d, float *d_translation) {
     float t = gradient_t(type, c, pt);
     const float *offsets = c + 4;
     const float *colors = c + 4 + num_stops;

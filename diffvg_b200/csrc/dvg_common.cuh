@@ -16,10 +16,12 @@
 #define DVG_HD __host__ __device__ __forceinline__
 #define DVG_HD_NOINLINE static __host__ __device__ __noinline__
 #define DVG_D __device__ __forceinline__
+#define DVG_D_NOINLINE __device__ __noinline__
 #else
 #define DVG_HD inline
 #define DVG_HD_NOINLINE static inline
 #define DVG_D inline
+#define DVG_D_NOINLINE inline
 #endif
 
 namespace dvg {
@@ -163,7 +165,7 @@ DVG_HD bool solve_quadratic_f(float a, float b, float c, float *t0, float *t1) {
     if (*t0 > *t1) { float tmp = *t0; *t0 = *t1; *t1 = tmp; }
     return true;
 }
-DVG_HD bool solve_quadratic_d(double a, double b, double c, double *t0, double *t1) {
+DVG_HD_NOINLINE bool solve_quadratic_d(double a, double b, double c, double *t0, double *t1) {
     double discrim = b * b - 4 * a * c;
     if (discrim < 0) return false;
     double root_discrim = sqrt(discrim);
@@ -180,7 +182,7 @@ DVG_HD bool solve_quadratic_d(double a, double b, double c, double *t0, double *
 
 // solve.h:29-59 with T = float.  The reference calls the *double* ::sqrt/::acos/::cos/::pow
 // on float arguments and only rounds when storing to a float; the promotions are explicit here.
-DVG_HD int solve_cubic_f(float a, float b, float c, float d, float t[3]) {
+DVG_HD_NOINLINE int solve_cubic_f(float a, float b, float c, float d, float t[3]) {
     if (fabsf(a) < 1e-6f) {
         if (solve_quadratic_f(b, c, d, &t[0], &t[1])) return 2;
         return 0;
@@ -210,7 +212,7 @@ DVG_HD int solve_cubic_f(float a, float b, float c, float d, float t[3]) {
 // bracket ends (dvg_geom.cuh quintic_eval note); the winding test compares the double roots with
 // 0 and 1 directly and must keep the reference's exact operation sequence.
 template <bool FAST>
-DVG_HD int solve_cubic_dt(double a, double b, double c, double d, double t[3]) {
+DVG_HD_NOINLINE int solve_cubic_dt(double a, double b, double c, double d, double t[3]) {
     if (fabs(a) < 1e-6f) {
         if (solve_quadratic_d(b, c, d, &t[0], &t[1])) return 2;
         return 0;
@@ -260,7 +262,7 @@ DVG_HD float filter_weight(Filter f, float dx, float dy) {
 }
 
 // filter.h:50-106: returns the value the reference atomically adds to d_filter.radius.
-DVG_HD float d_filter_weight_radius(Filter f, float dx, float dy, float d_return) {
+DVG_HD_NOINLINE float d_filter_weight_radius(Filter f, float dx, float dy, float d_return) {
     float r = f.radius;
     if (f.type == 0) {
         float w = 2 * r;

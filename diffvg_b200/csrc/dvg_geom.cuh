@@ -95,6 +95,7 @@ DVG_HD double quintic_deriv(const Quintic &q, double t) {  // within_distance.h:
 // value / derivative of the Newton update (within_distance.h:261).  The quotient only feeds a
 // float (the next iterate), so ~45 correct bits are as good as 53: reciprocal seed in float, one
 // Newton step in double.  Falls back to the IEEE division outside the float range.
+DVG_HD_NOINLINE double ieee_quotient(double value, double derivative) { return value / derivative; }
 DVG_HD double newton_quotient(double value, double derivative) {
 #if defined(DVG_FQ_NEWTON)
     const float df = (float)derivative;
@@ -104,7 +105,7 @@ DVG_HD double newton_quotient(double value, double derivative) {
         return value * r1;
     }
 #endif
-    return value / derivative;
+    return ieee_quotient(value, derivative);   // out of line: ~350 instructions, almost never taken
 }
 
 // Roots of the isolator cubic (within_distance.h:194, solve.h:29-59 with T = double) for use as
@@ -236,7 +237,7 @@ DVG_HD bool stroke_hit_cubic(F2 p0, F2 p1, F2 p2, F2 p3, F4 r, F2 pt, float stal
 
 // within_distance.h:63-118 (quadratic leaf).  *decided is set when use_distance_approx makes
 // the reference return from the whole path traversal (Q9).
-DVG_HD bool stroke_hit_quad(F2 p0, F2 p1, F2 p2, F4 r, float r_shape, bool approx, F2 pt, bool *decided) {
+DVG_HD_NOINLINE bool stroke_hit_quad(F2 p0, F2 p1, F2 p2, F4 r, float r_shape, bool approx, F2 pt, bool *decided) {
     if (approx) {
         F2 cp = quadratic_closest_pt_approx(p0, p1, p2, pt, nullptr);
         *decided = true;
@@ -325,8 +326,16 @@ DVG_HD bool prim_stroke_hit(int type, bool approx, F4 p01, F4 p23, F4 rad, float
     }
 }
 
+// The same without the cubic case: the render kernels answer cubic strokes with the warp solver
+// (dvg_wsolve.cuh) and keep this rarely used remainder out of line (the quadratic's closed-form roots go
+// through double acos / cos / pow: ~2 k instructions that would otherwise sit in the middle of the hot loop).
+DVG_HD_NOINLINE bool prim_stroke_hit_nocubic(int type, bool approx, F4 p01, F4 p23, F4 rad, float r_shape, F2 pt, bool *decided) {
+    if (type == PRIM_CUBIC) return false;
+    return prim_stroke_hit(type, approx, p01, p23, rad, r_shape, pt, decided);
+}
+
 // winding_number.h:62-156 per leaf type + 9-31, 176-186 for the closed-form shapes.
-DVG_HD int prim_winding(int type, F4 p01, F4 p23, F2 pt) {
+DVG_HD_NOINLINE int prim_winding(int type, F4 p01, F4 p23, F2 pt) {
     switch (type) {
         case PRIM_LINE: {
             F2 p0 = mk2(p01.x, p01.y), p1 = mk2(p01.z, p01.w);

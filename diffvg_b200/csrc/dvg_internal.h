@@ -50,6 +50,18 @@ struct BoundaryWork {
     int max_blocks;
 };
 
+// Wavefront passes (dvg_wave.cu): queues and result words in global memory.
+struct WavePair { float x, y; int prim; unsigned ref; };   // shape-local sample position, primitive, word << 5 | candidate
+struct WaveView {
+    unsigned *hit;        // one word per (evaluation, chunk of 32 candidates): bit k = stroke test of candidate k hit
+    unsigned *wind;       // four words per (evaluation, chunk): 4-bit signed winding per candidate; null without fills
+    WavePair *pairs_s, *pairs_f;   // exact stroke tests / winding tests still to run
+    int cap_s, cap_f;
+    int *counters;        // [0] stroke pairs appended, [1] fill pairs appended (may exceed the capacity: host re-runs)
+    int *tile_choff;      // [tiles+1] exclusive scan of chunks per tile
+    int *edge_choff;      // [tiles+1] exclusive scan of boundary items * chunks per tile
+};
+
 // SDF output (OutputType.sdf): device pointers, NULL = absent
 struct SdfArgs {
     float *sdf;                   // [H*W] or [num_eval]
@@ -72,5 +84,21 @@ void launch_render_pf_forward(const SceneView &sc, const BinView &bins, const Re
 void launch_render_pf_backward(const SceneView &sc, const BinView &bins, const RenderArgs &ra, cudaStream_t st);
 void launch_sdf(const SceneView &sc, const RenderArgs &ra, const SdfArgs &sa, bool backward, cudaStream_t st);
 void launch_boundary(const SceneView &sc, const BinView &bins, const RenderArgs &ra, const BoundaryWork &bw, cudaStream_t st);
+void launch_boundary_sort(const SceneView &sc, const BinView &bins, const RenderArgs &ra, const BoundaryWork &bw, cudaStream_t st);
+
+void launch_wave_tile_chunks(const int *bin_offsets, int *nch, int *choff, int *max_nch, int ntiles, cudaStream_t st);
+int wave_pixel_items(const BinView &bins, const RenderArgs &ra);
+int wave_items_per_tile(const BinView &bins, const RenderArgs &ra);
+int wave_edge_samples_per_item();
+void launch_wave_classify_px(const SceneView &sc, const BinView &bins, const RenderArgs &ra, const WaveView &wv, cudaStream_t st);
+void launch_wave_solve(const SceneView &sc, const WaveView &wv, int n_stroke, int n_fill, cudaStream_t st);
+void launch_wave_composite_px(const SceneView &sc, const BinView &bins, const RenderArgs &ra, const WaveView &wv, bool backward,
+                              cudaStream_t st);
+void launch_wave_boundary_sort(const SceneView &sc, const BinView &bins, const RenderArgs &ra, const BoundaryWork &bw,
+                               const WaveView &wv, int *edge_chunks, cudaStream_t st);
+void launch_wave_classify_edge(const SceneView &sc, const BinView &bins, const RenderArgs &ra, const BoundaryWork &bw,
+                               const WaveView &wv, cudaStream_t st);
+void launch_wave_composite_edge(const SceneView &sc, const BinView &bins, const RenderArgs &ra, const BoundaryWork &bw,
+                                const WaveView &wv, cudaStream_t st);
 
 }  // namespace dvg

@@ -520,6 +520,17 @@ void launch_render_backward(const SceneView &sc, const BinView &bins, const Rend
     DVG_LAUNCH(k_render<true>, dim3(nblk), dim3(RB), 0, st, sc, bins, ra);
 }
 
+// tile keys + counting sort of the boundary samples by tile (fills tile_counts, tile_offsets, sorted_idx)
+void launch_boundary_sort(const SceneView &sc, const BinView &bins, const RenderArgs &ra, const BoundaryWork &bw, cudaStream_t st) {
+    const int ntiles = bins.tiles_x * bins.tiles_y;
+    if (bw.num_samples <= 0) return;
+    cudaMemsetAsync(bw.tile_counts, 0, sizeof(int) * ntiles, st);
+    cudaMemsetAsync(bw.tile_fill, 0, sizeof(int) * ntiles, st);
+    DVG_LAUNCH(k_boundary_keys, dim3((bw.num_samples + 255) / 256), dim3(256), 0, st, sc, bins, ra, bw);
+    launch_scan(bw.tile_counts, bw.tile_offsets, ntiles, st);
+    DVG_LAUNCH(k_boundary_scatter, dim3((bw.num_samples + 255) / 256), dim3(256), 0, st, bw);
+}
+
 void launch_boundary(const SceneView &sc, const BinView &bins, const RenderArgs &ra, const BoundaryWork &bw, cudaStream_t st) {
     const int ntiles = bins.tiles_x * bins.tiles_y;
     if (bw.num_samples <= 0) return;

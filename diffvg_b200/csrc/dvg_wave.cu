@@ -1,0 +1,575 @@
+// dvg_wave.cu -- the render passes as a WAVEFRONT of small kernels.
+//
+// One fused kernel per pass (classify -> exact root solves -> composite in one warp program, dvg_render.cu)
+// measured on B200: 128 registers (25% occupancy), 13-15 k SASS instructions (stall_no_inst 27%: the
+// warps of an SM sit in different phases and thrash the instruction cache), 9-14 of 32 lanes active in the
+// FP64 root solves, 19% of warp samples waiting at the block barrier before the gradient flush.
+// None of that is compulsory: HBM is idle (< 1% of 6.4 TB/s), so the phases are separated and talk through
+// global memory instead:
+//
+//   W1 classify   one warp per ITEM (32 evaluations = pixel samples, or boundary-sample sides, on one
+//                 tile).  Walks the tile's candidate list in chunks of 32, runs the flat leaf predicates of
+//                 the reference's three BVH levels and the polyline bracket, and APPENDS every
+//                 (evaluation, candidate) pair that needs an exact test to a global queue (16 B records,
+//                 warp-aggregated atomic append, coalesced).  Writes one `hit` word per (evaluation, chunk).
+//   W2 solve      one THREAD per queued pair: the exact stroke test (within_distance.h) or winding
+//                 contribution (winding_number.h); a hit is OR-ed into the evaluation's word.  Every lane
+//                 has work, whatever the mix of decided / undecided samples in a tile.
+//   W3 composite  one warp per item again: replays the candidate list with the result words (fragments,
+//                 "over" compositing, EdgeQuery), then splat (forward), d_sample_color (interior backward)
+//                 or the Reynolds term (boundary pass).
+//
+// Traffic at the painterly config, forward: 4.4 M words written + read twice, ~6 M pairs x 16 B written +
+// read: < 200 MB per pass, ~30 us at the measured HBM rate.  Arithmetic is the same functions as before
+// (dvg_geom.cuh / dvg_trace.cuh), so results are unchanged.
+#include "dvg_internal.h"
+#include "dvg_kernel_util.cuh"
+
+namespace dvg {
+
+constexpr int WB = 256;            // threads per block of the per-item kernels (8 items)
+constexpr int WNW = WB / 32;
+constexpr int W_EDGE_SPI = 16;     // boundary samples per item (two lanes per sample)
+constexpr int W_MAXF = DVG_MAXF;
+
+struct WaveScratch {
+    unsigned int hit[32];            // [lane] bit k: candidate k answered "hit" without an exact test
+    unsigned short queue[32 * 32];   // (owner lane << 5 | candidate k)
+};
+
+DVG_D F2 w_local_point(const GroupInfo &g, F2 cpt) {
+    return (g.flags & DVG_GF_IDENTITY) ? cpt : xform_pt(g.c2s, cpt);
+}
+
+// Append `count` records of this warp to a global queue: one atomic per warp, returns the base index.
+DVG_D int warp_reserve(int *counter, int count) {
+    int base = 0;
+    if ((threadIdx.x & 31) == 0) base = atomicAdd(counter, count);
+    return __shfl_sync(0xffffffffu, base, 0);
+}
+
+// ------------------------------------------------------------------------------------------ W1
+// Classification of one item.  `cb` = first chunk slot of the item; the word of (lane, chunk c) is
+// (cb + c) * 32 + lane.  Reproduces the tests of sample_color's traversal (diffvg.cpp:544-594,
+// within_distance.h:278-285, 362-388, winding_number.h:162-169) up to, not including, the exact
+// per-segment tests.
+DVG_D void wave_classify(const SceneView &sc, const BinView &bins, const WaveView &wv, int tile, int64_t cb,
+                         F2 cpt, bool active, WaveScratch &ws, bool fast_accept) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    const int beg = bins.offsets[tile], end = bins.offsets[tile + 1];
+    SampleTracer<false, false> ct;
+    ct.init(cpt, active, mk4(0, 0, 0, 0), -1, -1, nullptr, nullptr);
+    int c = 0;
+    for (int base = beg; base < end; base += 32, c++) {
+        const int n = min(32, end - base);
+        int e = 0, tf = 0, inst = 0, group = 0;
+        Box box; box.x0 = box.y0 = box.x1 = box.y1 = 0.f;
+        float thick = 0.f;
+        if (lane < n) {
+            e = bins.items[base + lane];
+            const PrimMeta pm = sc.prim_meta[e];
+            tf = pm.type_flags; inst = pm.inst;
+            group = sc.insts[inst].group;
+            box = sc.prim_box[e];
+            thick = sc.prim_thick[e];
+        }
+        unsigned need_s = 0, need_f = 0;
+        for (int k = 0; k < n; k++) {
+            PrimRef pr;
+            pr.box.x0 = __shfl_sync(FULL, box.x0, k); pr.box.y0 = __shfl_sync(FULL, box.y0, k);
+            pr.box.x1 = __shfl_sync(FULL, box.x1, k); pr.box.y1 = __shfl_sync(FULL, box.y1, k);
+            pr.thick = __shfl_sync(FULL, thick, k);
+            pr.tf = __shfl_sync(FULL, tf, k); pr.inst = __shfl_sync(FULL, inst, k); pr.group = __shfl_sync(FULL, group, k);
+            const int nd = ct.template step<TM_CLASSIFY>(sc, pr);
+            need_s |= (unsigned)(nd & 1) << k;
+            need_f |= (unsigned)((nd >> 1) & 1) << k;
+        }
+        ws.hit[lane] = 0u;
+        const int64_t word0 = (cb + c) * 32;
+#pragma unroll 1
+        for (int kind = 0; kind < 2; kind++) {
+            const unsigned need = kind == 0 ? need_s : need_f;
+            if (!__any_sync(FULL, need != 0u)) continue;
+            int qn = 0;
+            for (int k = 0; k < n; k++) {  // candidate-major queue
+                const bool mine = (need >> k) & 1u;
+                const unsigned m = __ballot_sync(FULL, mine);
+                if (mine) ws.queue[qn + __popc(m & lt)] = (unsigned short)((lane << 5) | k);
+                qn += __popc(m);
+            }
+            __syncwarp();
+            WavePair *out = kind == 0 ? wv.pairs_s : wv.pairs_f;
+            const int cap = kind == 0 ? wv.cap_s : wv.cap_f;
+            for (int r = 0; r < qn; r += 32) {
+                const bool have = r + lane < qn;
+                const int it = have ? ws.queue[r + lane] : 0;
+                const int k = it & 31, owner = it >> 5;
+                const int ek = __shfl_sync(FULL, e, k), tfk = __shfl_sync(FULL, tf, k), gk = __shfl_sync(FULL, group, k);
+                const F2 op = mk2(__shfl_sync(FULL, cpt.x, owner), __shfl_sync(FULL, cpt.y, owner));
+                bool keep = have;
+                F2 lp = mk2(0, 0);
+                if (have) {
+                    lp = w_local_point(sc.groups[gk], op);
+                    const int ptype = tfk & DVG_PF_TYPE_MASK;
+                    if (kind == 0 && (ptype == PRIM_CUBIC || ptype == PRIM_QUAD) && !(tfk & DVG_PF_APPROX)) {
+                        // polyline bracket (dvg_scene.cuh): "certainly outside" is exact; "certainly inside" is
+                        // trusted only in the opt-in fast mode (the reference's solver has false negatives, Q21)
+                        const int cls = capsule_classify(reinterpret_cast<const float *>(sc.prim_cap + (size_t)ek * DVG_CAP_F4), lp);
+                        keep = cls == 0 || (cls > 0 && !fast_accept);
+                        if (cls > 0 && fast_accept) atomicOr(&ws.hit[owner], 1u << k);
+                    }
+                }
+                const unsigned m = __ballot_sync(FULL, keep);
+                const int cnt = __popc(m);
+                if (cnt) {
+                    const int pos = warp_reserve(&wv.counters[kind], cnt) + __popc(m & lt);
+                    if (keep && pos < cap) {
+                        WavePair p;
+                        p.x = lp.x; p.y = lp.y; p.prim = ek;
+                        p.ref = ((unsigned)(word0 + owner) << 5) | (unsigned)k;
+                        out[pos] = p;
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        __syncwarp();
+        wv.hit[word0 + lane] = ws.hit[lane];
+        if (wv.wind) {
+            uint4 z; z.x = z.y = z.z = z.w = 0u;
+            reinterpret_cast<uint4 *>(wv.wind)[word0 + lane] = z;
+        }
+        __syncwarp();
+    }
+}
+
+// Geometry of a pixel item: item -> tile, lane -> sample.
+struct PixelItem {
+    int tile, x, y, sx, sy, idx;
+    bool active;
+    int64_t cb;
+};
+DVG_D PixelItem pixel_item(const BinView &bins, const RenderArgs &ra, const WaveView &wv, int item) {
+    PixelItem pi;
+    const int spp = ra.nsx * ra.nsy;
+    const int ns = bins.tile_w * bins.tile_h * spp;
+    const int wpt = (ns + 31) / 32;
+    const int tile_row0 = ra.row_begin / bins.tile_h;
+    pi.tile = item / wpt + tile_row0 * bins.tiles_x;
+    const int part = item % wpt;
+    const int tx = pi.tile % bins.tiles_x, ty = pi.tile / bins.tiles_x;
+    const int l = part * 32 + (threadIdx.x & 31);
+    const int s = l % spp, p = l / spp;
+    pi.x = tx * bins.tile_w + p % bins.tile_w;
+    pi.y = ty * bins.tile_h + p / bins.tile_w;
+    pi.sx = s % ra.nsx; pi.sy = s / ra.nsx;
+    pi.active = l < ns && pi.x < ra.width && pi.y < ra.height && pi.y >= ra.row_begin && pi.y < ra.row_end;
+    pi.idx = ((pi.y * ra.width + pi.x) * ra.nsy + pi.sy) * ra.nsx + pi.sx;
+    const int c0 = wv.tile_choff[pi.tile];
+    const int nch = wv.tile_choff[pi.tile + 1] - c0;
+    pi.cb = (int64_t)c0 * wpt + (int64_t)part * nch;
+    return pi;
+}
+
+__global__ void __launch_bounds__(WB) k_wave_classify_px(SceneView sc, BinView bins, RenderArgs ra, WaveView wv, int num_items) {
+    __shared__ WaveScratch s_ws[WNW];
+    const int item = blockIdx.x * WNW + (threadIdx.x >> 5);
+    if (item >= num_items) return;
+    const PixelItem pi = pixel_item(bins, ra, wv, item);
+    F2 pt = mk2(0, 0), cpt = mk2(0, 0);
+    if (pi.active)
+        sample_position(sc.canvas_w, sc.canvas_h, ra.width, ra.height, ra.nsx, ra.nsy, ra.seed, ra.use_prefiltering != 0,
+                        pi.x, pi.y, pi.sx, pi.sy, pi.idx, pt, cpt);
+    wave_classify(sc, bins, wv, pi.tile, pi.cb, cpt, pi.active, s_ws[threadIdx.x >> 5], (ra.flags & DVG_RF_FAST_ACCEPT) != 0);
+}
+
+// Geometry of a boundary item: 16 boundary samples of one tile; lanes 2k / 2k+1 = the two sides of sample k.
+struct EdgeItem {
+    int tile, k;
+    bool valid;
+    int64_t cb;
+};
+DVG_D EdgeItem edge_item(const BinView &bins, const BoundaryWork &bw, const WaveView &wv, int item) {
+    EdgeItem ei;
+    const int ntiles = bins.tiles_x * bins.tiles_y;
+    int lo = 0, hi = ntiles;  // largest t with blk_offsets[t] <= item
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (bw.blk_offsets[mid] <= item) lo = mid; else hi = mid;
+    }
+    ei.tile = lo;
+    const int chunk = item - bw.blk_offsets[lo];
+    ei.k = chunk * W_EDGE_SPI + ((threadIdx.x & 31) >> 1);
+    ei.valid = ei.k < bw.tile_counts[lo];
+    const int nch = wv.tile_choff[lo + 1] - wv.tile_choff[lo];
+    ei.cb = (int64_t)wv.edge_choff[lo] + (int64_t)chunk * nch;
+    return ei;
+}
+
+struct EdgeLane {
+    BoundarySample bs;
+    bool active;
+    F2 cpt;
+    int bx, by;
+};
+DVG_D EdgeLane edge_lane(const SceneView &sc, const RenderArgs &ra, const BoundaryWork &bw, const EdgeItem &ei) {
+    EdgeLane el;
+    el.bs.inst = -1; el.bs.pt = mk2(0, 0); el.bs.normal = mk2(0, 0);
+    if (ei.valid) make_boundary_sample(sc, bw.sorted_idx[bw.tile_offsets[ei.tile] + ei.k], ra.seed, el.bs);
+    el.active = ei.valid && el.bs.inst >= 0;
+    el.cpt = mk2(0, 0); el.bx = el.by = 0;
+    if (el.active) {
+        el.bx = (int)(el.bs.pt.x * ra.width); el.by = (int)(el.bs.pt.y * ra.height);
+        const F2 off = 1e-4f * el.bs.normal;
+        const F2 npt = (threadIdx.x & 1) ? el.bs.pt + off : el.bs.pt - off;  // diffvg.cpp:1416,1420
+        el.cpt = mk2(npt.x * sc.canvas_w, npt.y * sc.canvas_h);
+    }
+    return el;
+}
+
+__global__ void __launch_bounds__(WB) k_wave_classify_edge(SceneView sc, BinView bins, RenderArgs ra, BoundaryWork bw, WaveView wv) {
+    __shared__ WaveScratch s_ws[WNW];
+    const int ntiles = bins.tiles_x * bins.tiles_y;
+    const int item = blockIdx.x * WNW + (threadIdx.x >> 5);
+    if (item >= bw.blk_offsets[ntiles]) return;
+    const EdgeItem ei = edge_item(bins, bw, wv, item);
+    const EdgeLane el = edge_lane(sc, ra, bw, ei);
+    wave_classify(sc, bins, wv, ei.tile, ei.cb, el.cpt, el.active, s_ws[threadIdx.x >> 5], (ra.flags & DVG_RF_FAST_ACCEPT) != 0);
+}
+
+// ------------------------------------------------------------------------------------------ W2
+__global__ void __launch_bounds__(128) k_wave_solve_stroke(SceneView sc, WaveView wv, int count) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const WavePair p = wv.pairs_s[i];
+    const PrimMeta pm = sc.prim_meta[p.prim];
+    bool decided = false;
+    const bool h = prim_stroke_hit(pm.type_flags & DVG_PF_TYPE_MASK, (pm.type_flags & DVG_PF_APPROX) != 0, sc.prim_p01[p.prim],
+                                   sc.prim_p23[p.prim], sc.prim_rad[p.prim], sc.insts[pm.inst].r, mk2(p.x, p.y), &decided);
+    if (h) atomicOr(&wv.hit[p.ref >> 5], 1u << (p.ref & 31u));
+}
+
+__global__ void __launch_bounds__(128) k_wave_solve_fill(SceneView sc, WaveView wv, int count) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const WavePair p = wv.pairs_f[i];
+    const PrimMeta pm = sc.prim_meta[p.prim];
+    const int w = prim_winding(pm.type_flags & DVG_PF_TYPE_MASK, sc.prim_p01[p.prim], sc.prim_p23[p.prim], mk2(p.x, p.y));
+    const unsigned k = p.ref & 31u;
+    if (w != 0) atomicOr(&wv.wind[(size_t)(p.ref >> 5) * 4 + (k >> 3)], (unsigned)(w & 15) << (4 * (k & 7)));
+}
+
+// ------------------------------------------------------------------------------------------ W3
+// Replay of one item's candidate list with the result words: sample_color's fragment collection and
+// compositing (diffvg.cpp:555-653).
+template <bool EDGE, bool RECORD>
+DVG_D void wave_consume(const SceneView &sc, const BinView &bins, const WaveView &wv, int tile, int64_t cb,
+                        SampleTracer<EDGE, RECORD> &tr) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int beg = bins.offsets[tile], end = bins.offsets[tile + 1];
+    int c = 0;
+    for (int base = beg; base < end; base += 32, c++) {
+        const int n = min(32, end - base);
+        int tf = 0, inst = 0, group = 0;
+        if (lane < n) {
+            const PrimMeta pm = sc.prim_meta[bins.items[base + lane]];
+            tf = pm.type_flags; inst = pm.inst;
+            group = sc.insts[inst].group;
+        }
+        const int64_t word = (cb + c) * 32 + lane;
+        const unsigned hitm = wv.hit[word];
+        uint4 wd; wd.x = wd.y = wd.z = wd.w = 0u;
+        if (wv.wind) wd = reinterpret_cast<const uint4 *>(wv.wind)[word];
+        for (int k = 0; k < n; k++) {
+            PrimRef pr;
+            pr.tf = __shfl_sync(FULL, tf, k); pr.inst = __shfl_sync(FULL, inst, k); pr.group = __shfl_sync(FULL, group, k);
+            const unsigned ww = (k < 8 ? wd.x : (k < 16 ? wd.y : (k < 24 ? wd.z : wd.w)));
+            const int nib = (int)((ww >> (4 * (k & 7))) & 15u);
+            tr.template step<TM_CONSUME>(sc, pr, DVG_NEED_STROKE | DVG_NEED_FILL, ((hitm >> k) & 1u) != 0u, (nib ^ 8) - 8);
+        }
+    }
+    tr.finish(sc);
+}
+
+// render_kernel (diffvg.cpp:1161-1272), colour output, after the candidates have been answered.
+template <bool BACKWARD>
+__global__ void __launch_bounds__(WB) k_wave_composite_px(SceneView sc, BinView bins, RenderArgs ra, WaveView wv, int num_items) {
+    GradCache *gcp = nullptr;
+    if constexpr (BACKWARD) {
+        __shared__ GradCache s_gc;
+        gcp = &s_gc;
+        grad_cache_init(s_gc);
+        __syncthreads();
+    }
+    const CacheSink sk{gcp, ra.d_params};
+    const int lane = threadIdx.x & 31;
+    const int item = blockIdx.x * WNW + (threadIdx.x >> 5);
+    const int spp = ra.nsx * ra.nsy;
+    const bool pow2 = (spp & (spp - 1)) == 0;
+    const int grp = pow2 ? (spp < 32 ? spp : 32) : 1;
+    int fkey[BACKWARD ? W_MAXF : 1];
+    F4 fprev[BACKWARD ? W_MAXF : 1];
+    float d_radius_acc = 0.f;
+    if (item < num_items) {
+        const PixelItem pi = pixel_item(bins, ra, wv, item);
+        const int x = pi.x, y = pi.y;
+        const bool active = pi.active;
+        F2 pt = mk2(0, 0), cpt = mk2(0, 0);
+        const float *bg_px = nullptr;
+        F4 first = mk4(0, 0, 0, 0);
+        F4 d_color = mk4(0, 0, 0, 0);
+        if (active) {
+            sample_position(sc.canvas_w, sc.canvas_h, ra.width, ra.height, ra.nsx, ra.nsy, ra.seed, ra.use_prefiltering != 0,
+                            x, y, pi.sx, pi.sy, pi.idx, pt, cpt);
+            if (ra.background) {
+                bg_px = ra.background + 4 * (y * ra.width + x);
+                first = mk4(bg_px[0], bg_px[1], bg_px[2], bg_px[3]);
+            }
+            if (BACKWARD) d_color = gather_d_color(sc.filter, ra.d_render_image, ra.weight_image, ra.width, ra.height, pt);
+        }
+        SampleTracer<false, BACKWARD> tr;
+        tr.init(cpt, active, first, -1, -1, fkey, fprev);
+        wave_consume<false, BACKWARD>(sc, bins, wv, pi.tile, pi.cb, tr);
+        const F4 color = tr.resolve(bg_px);
+        if (!BACKWARD) {
+            splat_color(sc, ra, x, y, pt, color, active, grp, lane);
+        } else {
+            // interior backward, d_sample_color (diffvg.cpp:656-705).  All 32 lanes stay converged: fragments
+            // are popped in warp-uniform steps so that lanes sharing a (group, stroke/fill) key are reduced with
+            // shuffles and scattered by ONE lane (atomic.h:23-51 does one global atomic per component per sample).
+            float dcr = d_color.x, dcg = d_color.y, dcb = d_color.z, dca = d_color.w;
+            int sp = tr.sp;
+            if (tr.nfrag > 0) {
+                if (tr.accum.w > 1e-6f) {
+                    const float inv = 1.f / tr.accum.w;
+                    dca -= (d_color.x * color.x + d_color.y * color.y + d_color.z * color.z) / tr.accum.w;
+                    dcr = d_color.x * inv; dcg = d_color.y * inv; dcb = d_color.z * inv;
+                }
+            } else {
+                sp = 0;
+                if (active && bg_px && ra.d_background) {  // diffvg.cpp:598-600 (Q2: accumulated, not assigned)
+                    float *d = ra.d_background + 4 * (y * ra.width + x);
+                    atomicAdd(d + 0, d_color.x); atomicAdd(d + 1, d_color.y); atomicAdd(d + 2, d_color.z); atomicAdd(d + 3, d_color.w);
+                }
+            }
+            const bool had_frags = sp > 0;
+            while (true) {
+                const int mykey = sp > 0 ? fkey[sp - 1] : -1;
+                const unsigned m = __ballot_sync(0xffffffffu, mykey >= 0);
+                if (!m) break;
+                const int key = __shfl_sync(0xffffffffu, mykey, __ffs(m) - 1);
+                const GroupInfo &g = sc.groups[key >> 1];
+                const int ctype = (key & 1) ? g.stroke_type : g.fill_type;
+                const int coff = (key & 1) ? g.stroke_off : g.fill_off;
+                const int cstops = (key & 1) ? g.stroke_stops : g.fill_stops;
+                F4 dc = mk4(0, 0, 0, 0);
+                if (mykey == key) {
+                    sp--;
+                    const F4 prev = fprev[sp];
+                    const F4 fc = eval_color(ctype, sc.params + coff, cstops, cpt);
+                    // diffvg.cpp:673-679
+                    const float d_prev_alpha = dca * (1.f - fc.w);
+                    float d_alpha_i = dca * (1.f - prev.w);
+                    d_alpha_i += (dcr * (fc.x - prev.x) + dcg * (fc.y - prev.y)) + dcb * (fc.z - prev.z);
+                    dc = mk4(dcr * fc.w, dcg * fc.w, dcb * fc.w, d_alpha_i);
+                    dcr = dcr * (1 - fc.w); dcg = dcg * (1 - fc.w); dcb = dcb * (1 - fc.w);
+                    dca = d_prev_alpha;
+                    if (ctype != 0 && !(key & 1)) {
+                        // gradient FILL colours: per-lane scatter (diffvg.cpp:382-499)
+                        d_eval_gradient(ctype, sc.params + coff, cstops, cpt, dc, sk, coff,
+                                        ra.d_translation ? ra.d_translation + 2 * (y * ra.width + x) : nullptr);
+                    }
+                    // Q4: gradient STROKE colours have no gradient storage in the reference (scene.cpp:868,887)
+                }
+                if (ctype == 0) {
+                    dc.x = warp_sum(dc.x); dc.y = warp_sum(dc.y); dc.z = warp_sum(dc.z); dc.w = warp_sum(dc.w);
+                    if (lane == 0) {
+                        sk.add(coff + 0, dc.x); sk.add(coff + 1, dc.y); sk.add(coff + 2, dc.z); sk.add(coff + 3, dc.w);
+                    }
+                }
+            }
+            if (active && had_frags && bg_px && ra.d_background) {  // diffvg.cpp:699-704
+                float *d = ra.d_background + 4 * (y * ra.width + x);
+                atomicAdd(d + 0, dcr); atomicAdd(d + 1, dcg); atomicAdd(d + 2, dcb); atomicAdd(d + 3, dca);
+            }
+            if (active) d_radius_acc += filter_radius_grad(sc, ra, x, y, pt, color);
+        }
+    }
+    if (BACKWARD) {
+        d_radius_acc = warp_sum(d_radius_acc);
+        if (lane == 0) sk.add(sc.filter_radius_off, d_radius_acc);
+        __syncthreads();
+        grad_cache_flush(*gcp, ra.d_params);
+    }
+}
+
+// render_edge_kernel (diffvg.cpp:1388-1475) after the candidates of both sides have been answered.
+__global__ void __launch_bounds__(WB) k_wave_composite_edge(SceneView sc, BinView bins, RenderArgs ra, BoundaryWork bw, WaveView wv) {
+    __shared__ GradCache s_gc;
+    grad_cache_init(s_gc);
+    __syncthreads();
+    const CacheSink sk{&s_gc, ra.d_params};
+    const int lane = threadIdx.x & 31;
+    const int ntiles = bins.tiles_x * bins.tiles_y;
+    const int item = blockIdx.x * WNW + (threadIdx.x >> 5);
+    if (item < bw.blk_offsets[ntiles]) {
+        const EdgeItem ei = edge_item(bins, bw, wv, item);
+        const EdgeLane el = edge_lane(sc, ra, bw, ei);
+        const BoundarySample &bs = el.bs;
+        const bool active = el.active;
+        const int side = lane & 1;
+        int q_group = -1, q_shape = -1;
+        const float *bg_px = nullptr;
+        F4 first = mk4(0, 0, 0, 0);
+        if (active) {
+            const InstInfo &ii = sc.insts[bs.inst];
+            q_group = ii.group; q_shape = ii.shape;
+            if (ra.background) {
+                bg_px = ra.background + 4 * (el.by * ra.width + el.bx);
+                first = mk4(bg_px[0], bg_px[1], bg_px[2], bg_px[3]);
+            }
+        }
+        SampleTracer<true, false> tr;
+        tr.init(el.cpt, active, first, q_group, q_shape, nullptr, nullptr);
+        wave_consume<true, false>(sc, bins, wv, ei.tile, ei.cb, tr);
+        const F4 mine = tr.resolve(bg_px);
+        const int my_hit = tr.q_hit() ? 1 : 0;
+        F4 other;
+        other.x = __shfl_xor_sync(0xffffffffu, mine.x, 1);
+        other.y = __shfl_xor_sync(0xffffffffu, mine.y, 1);
+        other.z = __shfl_xor_sync(0xffffffffu, mine.z, 1);
+        other.w = __shfl_xor_sync(0xffffffffu, mine.w, 1);
+        const int other_hit = __shfl_xor_sync(0xffffffffu, my_hit, 1);
+        // lane `side == 0` evaluated pt - eps*n ("inside"); it owns the scatter of its sample.
+        // occluded samples contribute nothing (diffvg.cpp:1422-1425)
+        const bool scatter = active && side == 0 && (my_hit || other_hit);
+        float dm[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        int xoff = -1;
+        if (scatter) {
+            F4 c_in = mine, c_out = other;
+            F2 normal = bs.normal;
+            if (!my_hit) { normal = -normal; c_in = other; c_out = mine; }
+            const F2 spt = mk2(bs.pt.x * ra.width, bs.pt.y * ra.height);
+            F4 d_color = gather_d_color(sc.filter, ra.d_render_image, ra.weight_image, ra.width, ra.height, spt);
+            const float inv_area = 1.f / (float)(sc.canvas_w * sc.canvas_h);
+            d_color = d_color * inv_area;
+            const F4 diff = c_in - c_out;
+            const float contrib = (diff.x * d_color.x + diff.y * d_color.y + diff.z * d_color.z + diff.w * d_color.w) / bs.pdf;
+            const InstInfo &ii = sc.insts[bs.inst];
+            const GroupInfo &g = sc.groups[ii.group];
+            accumulate_boundary_gradient(sc, ra, bs, ii, g, contrib, normal, sk);
+            if (ra.debug_out) {
+                float *o = ra.debug_out + 4 * (size_t)bw.sorted_idx[bw.tile_offsets[ei.tile] + ei.k];
+                o[0] = contrib; o[1] = (float)(my_hit | (other_hit << 1)); o[2] = normal.x; o[3] = normal.y;
+            }
+            if (!(ra.flags & 1u)) {  // DVG_BWD_SKIP_XFORM_GRAD
+                boundary_xform_gradient(bs, g, contrib, normal, dm);
+                xoff = g.xform_off;
+            }
+            if (ra.d_translation) {  // diffvg.cpp:1454-1461
+                atomicAdd(ra.d_translation + 2 * (el.by * ra.width + el.bx) + 0, normal.x * contrib);
+                atomicAdd(ra.d_translation + 2 * (el.by * ra.width + el.bx) + 1, normal.y * contrib);
+            }
+        }
+        // d_shape_to_canvas: warp-reduce when every scattering lane targets the same transform
+        const unsigned am = __ballot_sync(0xffffffffu, xoff >= 0);
+        if (am) {
+            const int x0 = __shfl_sync(0xffffffffu, xoff, __ffs(am) - 1);
+            const bool uniform = __all_sync(0xffffffffu, xoff < 0 || xoff == x0);
+            if (uniform) {
+#pragma unroll
+                for (int c = 0; c < 9; c++) {
+                    const float v = warp_sum(dm[c]);
+                    if (lane == 0) sk.add(x0 + c, v);
+                }
+            } else if (xoff >= 0) {
+#pragma unroll
+                for (int c = 0; c < 9; c++) sk.add(xoff + c, dm[c]);
+            }
+        }
+    }
+    __syncthreads();
+    grad_cache_flush(s_gc, ra.d_params);
+}
+
+// ------------------------------------------------------------------------------------------ host side
+// chunks per tile (ceil(count / 32)) and their maximum, for sizing the result words
+__global__ void k_wave_tile_chunks(const int *bin_offsets, int *nch, int *max_nch, int ntiles) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ntiles) return;
+    const int c = (bin_offsets[t + 1] - bin_offsets[t] + 31) / 32;
+    nch[t] = c;
+    atomicMax(max_nch, c);
+}
+
+// per tile: boundary items (ceil(samples / 16)) and items * chunks
+__global__ void k_wave_edge_counts(BoundaryWork bw, const int *tile_choff, int *edge_chunks, int ntiles) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ntiles) return;
+    const int items = (bw.tile_counts[t] + W_EDGE_SPI - 1) / W_EDGE_SPI;
+    bw.blk_counts[t] = items;
+    edge_chunks[t] = items * (tile_choff[t + 1] - tile_choff[t]);
+}
+
+void launch_wave_tile_chunks(const int *bin_offsets, int *nch, int *choff, int *max_nch, int ntiles, cudaStream_t st) {
+    cudaMemsetAsync(max_nch, 0, sizeof(int), st);
+    DVG_LAUNCH(k_wave_tile_chunks, dim3((ntiles + 255) / 256), dim3(256), 0, st, bin_offsets, nch, max_nch, ntiles);
+    launch_scan(nch, choff, ntiles, st);
+}
+
+int wave_pixel_items(const BinView &bins, const RenderArgs &ra) {
+    const int ns = bins.tile_w * bins.tile_h * ra.nsx * ra.nsy;
+    const int wpt = (ns + 31) / 32;
+    const int r0 = ra.row_begin / bins.tile_h;
+    const int r1 = (ra.row_end + bins.tile_h - 1) / bins.tile_h;
+    return (r1 - r0) * bins.tiles_x * wpt;
+}
+int wave_items_per_tile(const BinView &bins, const RenderArgs &ra) {
+    return (bins.tile_w * bins.tile_h * ra.nsx * ra.nsy + 31) / 32;
+}
+int wave_edge_samples_per_item() { return W_EDGE_SPI; }
+
+void launch_wave_classify_px(const SceneView &sc, const BinView &bins, const RenderArgs &ra, const WaveView &wv, cudaStream_t st) {
+    const int items = wave_pixel_items(bins, ra);
+    if (items <= 0) return;
+    DVG_LAUNCH(k_wave_classify_px, dim3((items + WNW - 1) / WNW), dim3(WB), 0, st, sc, bins, ra, wv, items);
+}
+
+void launch_wave_solve(const SceneView &sc, const WaveView &wv, int n_stroke, int n_fill, cudaStream_t st) {
+    if (n_stroke > 0) DVG_LAUNCH(k_wave_solve_stroke, dim3((n_stroke + 127) / 128), dim3(128), 0, st, sc, wv, n_stroke);
+    if (n_fill > 0) DVG_LAUNCH(k_wave_solve_fill, dim3((n_fill + 127) / 128), dim3(128), 0, st, sc, wv, n_fill);
+}
+
+void launch_wave_composite_px(const SceneView &sc, const BinView &bins, const RenderArgs &ra, const WaveView &wv, bool backward,
+                              cudaStream_t st) {
+    const int items = wave_pixel_items(bins, ra);
+    if (items <= 0) return;
+    if (backward) DVG_LAUNCH(k_wave_composite_px<true>, dim3((items + WNW - 1) / WNW), dim3(WB), 0, st, sc, bins, ra, wv, items);
+    else DVG_LAUNCH(k_wave_composite_px<false>, dim3((items + WNW - 1) / WNW), dim3(WB), 0, st, sc, bins, ra, wv, items);
+}
+
+// Boundary pass, ordering step (shared with the fused path's kernels in dvg_render.cu): tile keys, counting
+// sort, then per-tile item counts and chunk-slot offsets.
+void launch_wave_boundary_sort(const SceneView &sc, const BinView &bins, const RenderArgs &ra, const BoundaryWork &bw,
+                               const WaveView &wv, int *edge_chunks, cudaStream_t st) {
+    const int ntiles = bins.tiles_x * bins.tiles_y;
+    launch_boundary_sort(sc, bins, ra, bw, st);
+    DVG_LAUNCH(k_wave_edge_counts, dim3((ntiles + 255) / 256), dim3(256), 0, st, bw, wv.tile_choff, edge_chunks, ntiles);
+    launch_scan(bw.blk_counts, bw.blk_offsets, ntiles, st);
+    launch_scan(edge_chunks, wv.edge_choff, ntiles, st);
+}
+
+void launch_wave_classify_edge(const SceneView &sc, const BinView &bins, const RenderArgs &ra, const BoundaryWork &bw,
+                               const WaveView &wv, cudaStream_t st) {
+    DVG_LAUNCH(k_wave_classify_edge, dim3((bw.max_blocks + WNW - 1) / WNW), dim3(WB), 0, st, sc, bins, ra, bw, wv);
+}
+
+void launch_wave_composite_edge(const SceneView &sc, const BinView &bins, const RenderArgs &ra, const BoundaryWork &bw,
+                                const WaveView &wv, cudaStream_t st) {
+    DVG_LAUNCH(k_wave_composite_edge, dim3((bw.max_blocks + WNW - 1) / WNW), dim3(WB), 0, st, sc, bins, ra, bw, wv);
+}
+
+}  // namespace dvg
