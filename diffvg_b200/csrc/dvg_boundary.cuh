@@ -353,6 +353,86 @@ DVG_D void accumulate_boundary_gradient(const SceneView &sc, const RenderArgs &r
     }
 }
 
+// The same scatter as accumulate_boundary_gradient, as a fixed-slot record: every lane that targets the same
+// (segment, fill / stroke side) produces the same `addr[]`, so a warp can sum the values of such lanes with
+// shuffles and issue ONE atomic per address (dvg_wave.cu warp_scatter_grouped).  Slots: 0-7 point
+// coordinates (circle: centre.x, centre.y, radius; ellipse: centre.xy, radius.xy; rect: the one edge
+// coordinate), 8 stroke width, 9-12 per-point thickness.  addr < 0 = unused.  key < 0 = nothing to add.
+#define DVG_GREC_N 13
+struct GradRec {
+    int key;
+    int addr[DVG_GREC_N];
+    float val[DVG_GREC_N];
+};
+DVG_HD void boundary_gradient_record(const SceneView &sc, const BoundarySample &bs, const InstInfo &ii, float contrib,
+                                     F2 normal, GradRec &gr) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int j = 0; j < DVG_GREC_N; j++) { gr.addr[j] = -1; gr.val[j] = 0.f; }
+    const int *srec = sc.topo + sc.topo[DVG_H_OFF_SHAPES] + ii.shape * DVG_SHAPE_REC_LEN;
+    const bool is_stroke = bs.point_id_stroke < 0;
+    const int point_id = bs.point_id_stroke & 0x7fffffff;
+    const int type = srec[DVG_S_TYPE];
+    const int poff = srec[DVG_S_PARAM_OFF];
+    const float nx = normal.x, ny = normal.y;
+    if (type == DVG_SHAPE_PATH) {
+        const int np = srec[DVG_S_NUM_POINTS];
+        const int ncp = sc.topo[sc.topo[DVG_H_OFF_NCP] + srec[DVG_S_NCP_OFF] + bs.base_point_id];
+        const float t = bs.path_t;
+        float w0, w1, w2 = 0.f, w3 = 0.f;
+        int i0 = point_id, i1, i2 = -1, i3 = -1;
+        if (ncp == 0) {
+            i1 = (point_id + 1) % np;
+            w0 = 1 - t; w1 = t;
+        } else if (ncp == 1) {
+            i1 = point_id + 1; i2 = (point_id + 2) % np;
+            w0 = (1 - t) * (1 - t); w1 = 2 * (1 - t) * t; w2 = t * t;
+        } else {
+            i1 = point_id + 1; i2 = point_id + 2; i3 = (point_id + 3) % np;
+            const float omt = 1 - t;
+            w0 = omt * omt * omt; w1 = 3 * (omt * omt) * t; w2 = 3 * omt * t * t; w3 = t * t * t;
+        }
+        gr.addr[0] = poff + 2 * i0; gr.addr[1] = poff + 2 * i0 + 1; gr.val[0] = w0 * nx * contrib; gr.val[1] = w0 * ny * contrib;
+        gr.addr[2] = poff + 2 * i1; gr.addr[3] = poff + 2 * i1 + 1; gr.val[2] = w1 * nx * contrib; gr.val[3] = w1 * ny * contrib;
+        if (i2 >= 0) { gr.addr[4] = poff + 2 * i2; gr.addr[5] = poff + 2 * i2 + 1; gr.val[4] = w2 * nx * contrib; gr.val[5] = w2 * ny * contrib; }
+        if (i3 >= 0) { gr.addr[6] = poff + 2 * i3; gr.addr[7] = poff + 2 * i3 + 1; gr.val[6] = w3 * nx * contrib; gr.val[7] = w3 * ny * contrib; }
+        if (is_stroke) {
+            const int toff = srec[DVG_S_THICK_OFF];
+            if (toff >= 0) {  // diffvg.cpp:110-144
+                gr.addr[9] = toff + i0; gr.val[9] = w0 * contrib;
+                gr.addr[10] = toff + i1; gr.val[10] = w1 * contrib;
+                if (i2 >= 0) { gr.addr[11] = toff + i2; gr.val[11] = w2 * contrib; }
+                if (i3 >= 0) { gr.addr[12] = toff + i3; gr.val[12] = w3 * contrib; }
+            } else if (srec[DVG_S_WIDTH_OFF] >= 0) {
+                gr.addr[8] = srec[DVG_S_WIDTH_OFF]; gr.val[8] = contrib;
+            }
+        }
+    } else {
+        if (is_stroke && srec[DVG_S_WIDTH_OFF] >= 0) { gr.addr[8] = srec[DVG_S_WIDTH_OFF]; gr.val[8] = contrib; }
+        if (type == DVG_SHAPE_CIRCLE) {
+            gr.addr[0] = poff + 1; gr.val[0] = nx * contrib;
+            gr.addr[1] = poff + 2; gr.val[1] = ny * contrib;
+            gr.addr[2] = poff + 0; gr.val[2] = contrib;
+        } else if (type == DVG_SHAPE_ELLIPSE) {
+            gr.addr[0] = poff + 2; gr.val[0] = nx * contrib;
+            gr.addr[1] = poff + 3; gr.val[1] = ny * contrib;
+            // the reference uses the UN-remapped random number t here (diffvg.cpp:166-167, 1373)
+            const float arg = 2 * (float)DVG_PI_D * bs.t;
+            gr.addr[2] = poff + 0; gr.val[2] = cosf(arg) * nx * contrib;
+            gr.addr[3] = poff + 1; gr.val[3] = sinf(arg) * ny * contrib;
+        } else {  // rect (diffvg.cpp:232-255): exact normal compare in LOCAL orientation
+            if (nx == -1.f && ny == 0.f) { gr.addr[0] = poff + 0; gr.val[0] = -contrib; }
+            else if (nx == 1.f && ny == 0.f) { gr.addr[0] = poff + 2; gr.val[0] = contrib; }
+            else if (nx == 0.f && ny == -1.f) { gr.addr[0] = poff + 1; gr.val[0] = -contrib; }
+            else if (nx == 0.f && ny == 1.f) { gr.addr[0] = poff + 3; gr.val[0] = contrib; }
+        }
+    }
+    // lanes with equal keys have equal addr[]: the first point address identifies the segment / shape / rect
+    // edge, bit 0 the stroke side (which decides slots 8-12); rect samples off the four exact normals add nothing
+    gr.key = gr.addr[0] >= 0 ? gr.addr[0] * 2 + (is_stroke ? 1 : 0) : (gr.addr[8] >= 0 ? gr.addr[8] * 2 + 1 : -1);
+}
+
 // d_xform_pt part of accumulate_boundary_gradient (diffvg.cpp:256-273): the 9 terms for
 // d_shape_to_canvas.  Kept separate so that the kernel can reduce them across the warp first
 // (groups very often share one transform, so all lanes target the same 9 floats).

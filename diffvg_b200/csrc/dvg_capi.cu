@@ -85,8 +85,8 @@ struct DvgScene {
     uint64_t w_seed = 0; float w_radius = 0; bool w_valid = false;
     DevBuf d_keys, d_tile_counts, d_tile_offsets, d_tile_fill, d_blk_counts, d_blk_offsets, d_sorted;
     // wavefront passes (dvg_wave.cu)
-    DevBuf d_wave_hit, d_wave_wind, d_wave_pairs_s, d_wave_pairs_f, d_wave_counters, d_tile_nch, d_tile_choff,
-        d_edge_chunks, d_edge_choff, d_wave_max;
+    DevBuf d_wave_hit, d_wave_wind, d_wave_pairs_s, d_wave_pairs_f, d_wave_units_a, d_wave_units_d, d_wave_counters, d_tile_nch, d_tile_choff,
+        d_edge_chunks, d_edge_choff, d_wave_max, d_bsamples, d_item_tile;
     int total_chunks = 0, max_nch = 0;   // of the current bins (read back with the bin total)
     bool has_fills = false;
     // which pixel pass the result words currently hold (forward's are reused by the interior backward pass)
@@ -149,8 +149,8 @@ struct DvgScene {
                          &d_seg_point_id, &d_insts, &d_groups, &d_p01, &d_p23, &d_rad, &d_box, &d_thick, &d_meta, &d_cbox, &d_cbox_pf, &d_cap,
                          &d_shape_cdf, &d_shape_pmf, &d_flags, &d_bin_counts, &d_bin_offsets, &d_bin_items, &d_weight,
                          &d_keys, &d_tile_counts, &d_tile_offsets, &d_tile_fill, &d_blk_counts, &d_blk_offsets, &d_sorted,
-                         &d_wave_hit, &d_wave_wind, &d_wave_pairs_s, &d_wave_pairs_f, &d_wave_counters, &d_tile_nch, &d_tile_choff,
-                         &d_edge_chunks, &d_edge_choff, &d_wave_max};
+                         &d_wave_hit, &d_wave_wind, &d_wave_pairs_s, &d_wave_pairs_f, &d_wave_units_a, &d_wave_units_d, &d_wave_counters, &d_tile_nch, &d_tile_choff,
+                         &d_edge_chunks, &d_edge_choff, &d_wave_max, &d_bsamples, &d_item_tile};
         for (DevBuf *b : all) b->release();
         if (h_pinned) cudaFreeHost(h_pinned);
         h_pinned = nullptr;
@@ -321,12 +321,13 @@ int wave_view(DvgScene *s, int64_t chunk_slots, int64_t evals, WaveView *out) {
     if (words >= ((int64_t)1 << 27)) return fail(DVG_ERR_UNSUPPORTED, "render too large for the 27-bit result-word index of the pair queue");
     CK(s->d_wave_hit.ensure(sizeof(unsigned) * (size_t)std::max<int64_t>(words, 1)));
     if (s->has_fills) CK(s->d_wave_wind.ensure(sizeof(unsigned) * 4 * (size_t)std::max<int64_t>(words, 1)));
-    CK(s->d_wave_counters.ensure(sizeof(int) * 2));
+    CK(s->d_wave_counters.ensure(sizeof(int) * 4));
     CK(s->d_edge_choff.ensure(sizeof(int) * 4));   // real size set by the boundary pass
     // first guess for the pair queues: two exact tests per evaluation; grown on demand (wave_classify_and_solve)
     if (!s->d_wave_pairs_s.p) CK(s->d_wave_pairs_s.ensure(sizeof(WavePair) * (size_t)std::max<int64_t>(2 * evals, 1 << 16)));
     if (s->has_fills && !s->d_wave_pairs_f.p) CK(s->d_wave_pairs_f.ensure(sizeof(WavePair) * (size_t)std::max<int64_t>(4 * evals, 1 << 16)));
     WaveView wv;
+    wv.units_a = wv.units_d = nullptr; wv.cap_ua = wv.cap_ud = 0;
     wv.hit = s->d_wave_hit.as<unsigned>();
     wv.wind = s->has_fills ? s->d_wave_wind.as<unsigned>() : nullptr;
     wv.pairs_s = s->d_wave_pairs_s.as<WavePair>(); wv.cap_s = (int)std::min<size_t>(s->d_wave_pairs_s.cap / sizeof(WavePair), 0x7fffffff);
@@ -351,6 +352,13 @@ int wave_classify_and_solve(DvgScene *s, const SceneView &sc, WaveView &wv, cuda
         const int ns = s->h_pinned[6], nf = s->h_pinned[7];
         if (ns < 0 || nf < 0) return fail(DVG_ERR_UNSUPPORTED, "more than 2^31 exact tests in one pass");
         if (ns <= wv.cap_s && nf <= wv.cap_f) {
+            // root-bracket queues of the cubic pairs: 1.5 ascending / 0.75 descending brackets per pair cover every
+            // scene measured (1.0 / 0.25 at the painterly config); a fuller queue is answered inline by W2a
+            wv.cap_ua = (int)std::min<int64_t>((int64_t)ns + ns / 2 + 1024, 0x7fffffff);
+            wv.cap_ud = (int)std::min<int64_t>((int64_t)ns - ns / 4 + 1024, 0x7fffffff);
+            CK(s->d_wave_units_a.ensure(sizeof(WaveUnit) * (size_t)wv.cap_ua));
+            CK(s->d_wave_units_d.ensure(sizeof(WaveUnit) * (size_t)wv.cap_ud));
+            wv.units_a = s->d_wave_units_a.as<WaveUnit>(); wv.units_d = s->d_wave_units_d.as<WaveUnit>();
             launch_wave_solve(sc, wv, ns, nf, st);
             CK(cudaGetLastError());
             return DVG_OK;
@@ -398,6 +406,10 @@ int wave_edge_pass(DvgScene *s, const SceneView &sc, const BinView &bins, const 
     bw.max_blocks = bw.num_samples / spi + ntiles;        // upper bound on the boundary items
     CK(s->d_edge_chunks.ensure(sizeof(int) * ntiles));
     CK(s->d_edge_choff.ensure(sizeof(int) * (ntiles + 1)));
+    CK(s->d_bsamples.ensure(sizeof(BoundarySample) * (size_t)bw.num_samples));
+    CK(s->d_item_tile.ensure(sizeof(int) * (size_t)bw.max_blocks));
+    bw.samples = s->d_bsamples.as<BoundarySample>();
+    bw.item_tile = s->d_item_tile.as<int>();
     WaveView wv;
     // every item of a tile has that tile's chunk count: bounded by max_nch without another read-back
     int rc = wave_view(s, (int64_t)bw.max_blocks * std::max(s->max_nch, 1), (int64_t)bw.max_blocks * 32, &wv);
@@ -652,6 +664,7 @@ static int render_backward_impl(DvgScene *s, const float *background, const floa
             const int spp = nsx * nsy;
             const int ntiles = bins.tiles_x * bins.tiles_y;
             BoundaryWork bw;
+            bw.samples = nullptr; bw.item_tile = nullptr;
             bw.sample_begin = row_begin * width * spp;
             bw.num_samples = (row_end - row_begin) * width * spp;
             if (bw.num_samples > 0) {

@@ -286,14 +286,21 @@ DVG_HD int capsule_classify(const float *cap, F2 pt) {
 #pragma unroll
 #endif
     for (int i = 0; i < DVG_CAP_N; i++) {
+#if defined(__CUDA_ARCH__)
+        // the records are 16-byte aligned (SceneView::prim_cap is an F4 array): two 128-bit loads per piece
+        const float4 ca = reinterpret_cast<const float4 *>(cap)[2 * i], cb = reinterpret_cast<const float4 *>(cap)[2 * i + 1];
+        const float c0 = ca.x, c1 = ca.y, c2 = ca.z, c3 = ca.w, c4 = cb.x, c5 = cb.y, c6 = cb.z;
+#else
         const float *c = cap + 8 * i;
-        const float wx = pt.x - c[0], wy = pt.y - c[1];
-        float t = (wx * c[2] + wy * c[3]) * c[4];
+        const float c0 = c[0], c1 = c[1], c2 = c[2], c3 = c[3], c4 = c[4], c5 = c[5], c6 = c[6];
+#endif
+        const float wx = pt.x - c0, wy = pt.y - c1;
+        float t = (wx * c2 + wy * c3) * c4;
         t = t < 0.f ? 0.f : (t > 1.f ? 1.f : t);
-        const float ex = wx - t * c[2], ey = wy - t * c[3];
+        const float ex = wx - t * c2, ey = wy - t * c3;
         const float d2 = ex * ex + ey * ey;
-        all_out = all_out && (d2 > c[5]);   // false for NaN
-        any_in = any_in || (d2 < c[6]);
+        all_out = all_out && (d2 > c5);   // false for NaN
+        any_in = any_in || (d2 < c6);
     }
     return all_out ? -1 : (any_in ? 1 : 0);
 }

@@ -48,16 +48,22 @@ struct BoundaryWork {
     int *blk_offsets;     // [tiles+1]
     int *sorted_idx;      // [num_samples]
     int max_blocks;
+    BoundarySample *samples;  // [num_samples] by index - sample_begin, or null (wavefront path: made once, read twice)
+    int *item_tile;           // [max_blocks] tile of every boundary item, or null
 };
 
 // Wavefront passes (dvg_wave.cu): queues and result words in global memory.
 struct WavePair { float x, y; int prim; unsigned ref; };   // shape-local sample position, primitive, word << 5 | candidate
+struct WaveUnit { float lb, ub; int pair; int pad; };     // one root bracket of a cubic pair's closest-point quintic
 struct WaveView {
+    WaveUnit *units_a, *units_d;   // ascending brackets (safeguarded Newton) / descending (the reference bisects)
+    int cap_ua, cap_ud;
     unsigned *hit;        // one word per (evaluation, chunk of 32 candidates): bit k = stroke test of candidate k hit
     unsigned *wind;       // four words per (evaluation, chunk): 4-bit signed winding per candidate; null without fills
     WavePair *pairs_s, *pairs_f;   // exact stroke tests / winding tests still to run
     int cap_s, cap_f;
-    int *counters;        // [0] stroke pairs appended, [1] fill pairs appended (may exceed the capacity: host re-runs)
+    int *counters;        // [0] stroke pairs appended, [1] fill pairs appended (may exceed the capacity: host re-runs),
+                          // [2] ascending units, [3] descending units (never exceed: overflow is solved inline)
     int *tile_choff;      // [tiles+1] exclusive scan of chunks per tile
     int *edge_choff;      // [tiles+1] exclusive scan of boundary items * chunks per tile
 };

@@ -363,6 +363,7 @@ __global__ void k_boundary_keys(SceneView sc, BinView bins, RenderArgs ra, Bound
         }
     }
     bw.keys[k] = key;
+    if (bw.samples) bw.samples[k] = bs;
 }
 
 __global__ void k_boundary_blocks(BoundaryWork bw, int ntiles) {

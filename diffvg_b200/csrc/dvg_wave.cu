@@ -48,6 +48,45 @@ DVG_D int warp_reserve(int *counter, int count) {
     return __shfl_sync(0xffffffffu, base, 0);
 }
 
+// Gradient scatter.  The fused kernels pre-reduce in a shared-memory hash (GradCache) that needs a block
+// barrier before its flush and, having no native shared-memory float add, spins on CAS: 30% of the boundary
+// composite.  Here lanes that target the same segment are summed with shuffles and the leader issues one
+// fire-and-forget `red.global.add.f32` per address (atomic.h:23-51 does one atomic per component per sample).
+struct GlobalSink {
+    float *D;
+    __device__ __forceinline__ void add(int idx, float v) const {
+        if (v != 0.f) atomicAdd(D + idx, v);
+    }
+};
+
+DVG_D void warp_scatter_grouped(const GradRec &gr, float *D) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    unsigned remaining = __ballot_sync(FULL, gr.key >= 0);
+    while (remaining) {
+        const int leader = __ffs(remaining) - 1;
+        const int k = __shfl_sync(FULL, gr.key, leader);
+        const bool mine = gr.key == k;
+        const unsigned grp = __ballot_sync(FULL, mine);
+        if (__popc(grp) == 1) {
+            if (lane == leader) {
+#pragma unroll
+                for (int j = 0; j < DVG_GREC_N; j++)
+                    if (gr.addr[j] >= 0 && gr.val[j] != 0.f) atomicAdd(D + gr.addr[j], gr.val[j]);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < DVG_GREC_N; j++) {
+                const int a = __shfl_sync(FULL, gr.addr[j], leader);
+                if (a < 0) continue;   // uniform
+                const float v = warp_sum(mine ? gr.val[j] : 0.f);
+                if (lane == leader && v != 0.f) atomicAdd(D + a, v);
+            }
+        }
+        remaining &= ~grp;
+    }
+}
+
 // ------------------------------------------------------------------------------------------ W1
 // Classification of one item.  `cb` = first chunk slot of the item; the word of (lane, chunk c) is
 // (cb + c) * 32 + lane.  Reproduces the tests of sample_color's traversal (diffvg.cpp:544-594,
@@ -193,12 +232,7 @@ struct EdgeItem {
 };
 DVG_D EdgeItem edge_item(const BinView &bins, const BoundaryWork &bw, const WaveView &wv, int item) {
     EdgeItem ei;
-    const int ntiles = bins.tiles_x * bins.tiles_y;
-    int lo = 0, hi = ntiles;  // largest t with blk_offsets[t] <= item
-    while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (bw.blk_offsets[mid] <= item) lo = mid; else hi = mid;
-    }
+    const int lo = bw.item_tile[item];
     ei.tile = lo;
     const int chunk = item - bw.blk_offsets[lo];
     ei.k = chunk * W_EDGE_SPI + ((threadIdx.x & 31) >> 1);
@@ -217,7 +251,7 @@ struct EdgeLane {
 DVG_D EdgeLane edge_lane(const SceneView &sc, const RenderArgs &ra, const BoundaryWork &bw, const EdgeItem &ei) {
     EdgeLane el;
     el.bs.inst = -1; el.bs.pt = mk2(0, 0); el.bs.normal = mk2(0, 0);
-    if (ei.valid) make_boundary_sample(sc, bw.sorted_idx[bw.tile_offsets[ei.tile] + ei.k], ra.seed, el.bs);
+    if (ei.valid) el.bs = bw.samples[bw.sorted_idx[bw.tile_offsets[ei.tile] + ei.k] - bw.sample_begin];   // made by k_boundary_keys
     el.active = ei.valid && el.bs.inst >= 0;
     el.cpt = mk2(0, 0); el.bx = el.by = 0;
     if (el.active) {
@@ -240,15 +274,143 @@ __global__ void __launch_bounds__(WB) k_wave_classify_edge(SceneView sc, BinView
 }
 
 // ------------------------------------------------------------------------------------------ W2
-__global__ void __launch_bounds__(128) k_wave_solve_stroke(SceneView sc, WaveView wv, int count) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= count) return;
-    const WavePair p = wv.pairs_s[i];
-    const PrimMeta pm = sc.prim_meta[p.prim];
-    bool decided = false;
-    const bool h = prim_stroke_hit(pm.type_flags & DVG_PF_TYPE_MASK, (pm.type_flags & DVG_PF_APPROX) != 0, sc.prim_p01[p.prim],
-                                   sc.prim_p23[p.prim], sc.prim_rad[p.prim], sc.insts[pm.inst].r, mk2(p.x, p.y), &decided);
-    if (h) atomicOr(&wv.hit[p.ref >> 5], 1u << (p.ref & 31u));
+// Exact stroke tests, cubic segments (within_distance.h:119-272), in two steps so that every lane stays busy:
+//   W2a (thread = pair)   end-point checks, the monic quintic of the stationary points of the squared
+//        distance, the isolator split points, and the sign tests of ALL brackets.  Which brackets hold a root,
+//        and where each starts (`lower` only advances past a bracket that held one, :233-271), is a function of
+//        those signs alone, so the brackets of a pair are independent UNITS; the pair's answer is the OR of their
+//        radius tests (the reference's early return only skips work).  Other segment types are answered here.
+//   W2b (thread = unit)   the reference's safeguarded Newton on one bracket (<= 20 evaluations), then the radius
+//        test at the root found.  Ascending and descending brackets are queued apart: after the reference's swap a
+//        descending bracket has lb > ub, its "t in [lb, ub]" guard never holds and it bisects (~3x the trips).
+// Per-bracket arithmetic is dvg_geom.cuh's, evaluated on the same inputs: results are unchanged.
+constexpr int W2A_B = 256;
+
+__global__ void __launch_bounds__(W2A_B) k_wave_stroke_setup(SceneView sc, WaveView wv, int count) {
+    __shared__ int s_wsum[2][W2A_B / 32];
+    __shared__ int s_base[2];
+    const int i = blockIdx.x * W2A_B + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float lbs[5], ubs[5];
+    unsigned valid = 0u, desc = 0u;   // bit j: bracket j holds a root / is descending
+    bool hit = false;
+    WavePair p; p.x = p.y = 0.f; p.prim = 0; p.ref = 0u;
+    F4 p01 = mk4(0, 0, 0, 0), p23 = p01, rad = p01;
+    if (i < count) {
+        p = wv.pairs_s[i];
+        const PrimMeta pm = sc.prim_meta[p.prim];
+        const int ptype = pm.type_flags & DVG_PF_TYPE_MASK;
+        p01 = sc.prim_p01[p.prim]; p23 = sc.prim_p23[p.prim]; rad = sc.prim_rad[p.prim];
+        const F2 pt = mk2(p.x, p.y);
+        if (ptype != PRIM_CUBIC) {
+            bool decided = false;
+            hit = prim_stroke_hit_nocubic(ptype, (pm.type_flags & DVG_PF_APPROX) != 0, p01, p23, rad, sc.insts[pm.inst].r, pt, &decided);
+        } else {
+            const F2 p0 = mk2(p01.x, p01.y), p1 = mk2(p01.z, p01.w), p2 = mk2(p23.x, p23.y), p3 = mk2(p23.z, p23.w);
+            if (dist_sq(p0, pt) < rad.x * rad.x || dist_sq(p3, pt) < rad.w * rad.w) {
+                hit = true;
+            } else {
+                const Quintic q = cubic_quintic(p0, p1, p2, p3, pt);
+                float iv[4];
+                const int n = quintic_intervals(q, iv);
+                float lower = 0.f;
+                double f_lower = quintic_eval(q, lower);
+                bool open = true;
+#pragma unroll
+                for (int j = 0; j < 5; j++) {
+                    lbs[j] = 0.f; ubs[j] = 0.f;
+                    const float ivj = iv[j < 4 ? j : 3];
+                    if (open && j < n + 1 && !(j < n && ivj < 0.f)) {
+                        const float upper = j < n ? rminf(ivj, 1.f) : 1.f;
+                        const double f_upper = quintic_eval(q, upper);
+                        if (!(f_lower * f_upper > 0)) {                 // :238 (a NaN product counts as a bracket)
+                            const bool d = f_lower > f_upper;         // :239-242
+                            lbs[j] = d ? upper : lower; ubs[j] = d ? lower : upper;
+                            valid |= 1u << j;
+                            if (d) desc |= 1u << j;
+                            if (upper >= 1.f) open = false;            // :268
+                            lower = upper; f_lower = f_upper;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (hit) atomicOr(&wv.hit[p.ref >> 5], 1u << (p.ref & 31u));
+    // block-level append: one atomic per queue per block
+    const int na = __popc(valid & ~desc), nd = __popc(valid & desc);
+    int sa = na, sd = nd;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int ta = __shfl_up_sync(0xffffffffu, sa, o), td = __shfl_up_sync(0xffffffffu, sd, o);
+        if (lane >= o) { sa += ta; sd += td; }
+    }
+    if (lane == 31) { s_wsum[0][warp] = sa; s_wsum[1][warp] = sd; }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        int tot = 0;
+        for (int w = 0; w < W2A_B / 32; w++) { const int v = s_wsum[threadIdx.x][w]; s_wsum[threadIdx.x][w] = tot; tot += v; }
+        s_base[threadIdx.x] = tot ? atomicAdd(&wv.counters[2 + threadIdx.x], tot) : 0;
+    }
+    __syncthreads();
+    int pa = s_base[0] + s_wsum[0][warp] + sa - na;
+    int pd = s_base[1] + s_wsum[1][warp] + sd - nd;
+#pragma unroll
+    for (int j = 0; j < 5; j++) {
+        if (!((valid >> j) & 1u)) continue;
+        const bool d = (desc >> j) & 1u;
+        const int pos = d ? pd++ : pa++;
+        WaveUnit *dst = d ? wv.units_d : wv.units_a;
+        if (pos < (d ? wv.cap_ud : wv.cap_ua)) {
+            WaveUnit u; u.lb = lbs[j]; u.ub = ubs[j]; u.pair = i; u.pad = 0;
+            dst[pos] = u;
+        } else {
+            // queue full (sized 1.5 / 0.75 units per pair): answer the bracket here, same arithmetic as W2b
+            const F2 pt = mk2(p.x, p.y);
+            const Quintic q = cubic_quintic(mk2(p01.x, p01.y), mk2(p01.z, p01.w), mk2(p23.x, p23.y), mk2(p23.z, p23.w), pt);
+            float lb = lbs[j], ub = ubs[j];
+            float t = 0.5f * (lb + ub);
+            for (int it = 0; it < 20; it++) {
+                if (!(t >= lb && t <= ub)) t = 0.5f * (lb + ub);
+                const double value = quintic_eval(q, t);
+                if (fabs(value) < 1e-5f || it == 19) break;
+                if (value > 0.f) ub = t; else lb = t;
+                const double derivative = quintic_deriv(q, t);
+                t = (float)((double)t - newton_quotient(value, derivative));
+            }
+            const float tt = 1 - t;
+            const float rr = (tt * tt * tt) * rad.x + (3 * tt * tt * t) * rad.y + (3 * tt * t * t) * rad.z + (t * t * t) * rad.w;
+            if (dist_sq(eval_cubic(mk2(p01.x, p01.y), mk2(p01.z, p01.w), mk2(p23.x, p23.y), mk2(p23.z, p23.w), t), pt) < rr * rr)
+                atomicOr(&wv.hit[p.ref >> 5], 1u << (p.ref & 31u));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_wave_stroke_newton(SceneView sc, WaveView wv, int which) {
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    const int count = min(wv.counters[2 + which], which ? wv.cap_ud : wv.cap_ua);
+    if (u >= count) return;
+    const WaveUnit un = (which ? wv.units_d : wv.units_a)[u];
+    const WavePair p = wv.pairs_s[un.pair];
+    const unsigned bit = 1u << (p.ref & 31u);
+    if (wv.hit[p.ref >> 5] & bit) return;   // another bracket of the pair already answered "hit"
+    const F4 p01 = sc.prim_p01[p.prim], p23 = sc.prim_p23[p.prim], rad = sc.prim_rad[p.prim];
+    const F2 p0 = mk2(p01.x, p01.y), p1 = mk2(p01.z, p01.w), p2 = mk2(p23.x, p23.y), p3 = mk2(p23.z, p23.w);
+    const F2 pt = mk2(p.x, p.y);
+    const Quintic q = cubic_quintic(p0, p1, p2, p3, pt);
+    float lb = un.lb, ub = un.ub;
+    float t = 0.5f * (lb + ub);
+    for (int it = 0; it < 20; it++) {                              // within_distance.h:244-262
+        if (!(t >= lb && t <= ub)) t = 0.5f * (lb + ub);
+        const double value = quintic_eval(q, t);
+        if (fabs(value) < 1e-5f || it == 19) break;
+        if (value > 0.f) ub = t; else lb = t;
+        const double derivative = quintic_deriv(q, t);
+        t = (float)((double)t - newton_quotient(value, derivative));
+    }
+    const float tt = 1 - t;                                        // :263-267
+    const float rr = (tt * tt * tt) * rad.x + (3 * tt * tt * t) * rad.y + (3 * tt * t * t) * rad.z + (t * t * t) * rad.w;
+    if (dist_sq(eval_cubic(p0, p1, p2, p3, t), pt) < rr * rr) atomicOr(&wv.hit[p.ref >> 5], bit);
 }
 
 __global__ void __launch_bounds__(128) k_wave_solve_fill(SceneView sc, WaveView wv, int count) {
@@ -297,14 +459,12 @@ DVG_D void wave_consume(const SceneView &sc, const BinView &bins, const WaveView
 // render_kernel (diffvg.cpp:1161-1272), colour output, after the candidates have been answered.
 template <bool BACKWARD>
 __global__ void __launch_bounds__(WB) k_wave_composite_px(SceneView sc, BinView bins, RenderArgs ra, WaveView wv, int num_items) {
-    GradCache *gcp = nullptr;
-    if constexpr (BACKWARD) {
-        __shared__ GradCache s_gc;
-        gcp = &s_gc;
-        grad_cache_init(s_gc);
+    __shared__ float s_d_radius;
+    if (BACKWARD) {
+        if (threadIdx.x == 0) s_d_radius = 0.f;
         __syncthreads();
     }
-    const CacheSink sk{gcp, ra.d_params};
+    const GlobalSink sk{ra.d_params};
     const int lane = threadIdx.x & 31;
     const int item = blockIdx.x * WNW + (threadIdx.x >> 5);
     const int spp = ra.nsx * ra.nsy;
@@ -398,20 +558,22 @@ __global__ void __launch_bounds__(WB) k_wave_composite_px(SceneView sc, BinView 
             if (active) d_radius_acc += filter_radius_grad(sc, ra, x, y, pt, color);
         }
     }
-    if (BACKWARD) {
+    if (BACKWARD) {   // every sample adds to d_filter.radius: one global atomic per block
         d_radius_acc = warp_sum(d_radius_acc);
-        if (lane == 0) sk.add(sc.filter_radius_off, d_radius_acc);
+        if (lane == 0 && d_radius_acc != 0.f) atomicAdd(&s_d_radius, d_radius_acc);
         __syncthreads();
-        grad_cache_flush(*gcp, ra.d_params);
+        if (threadIdx.x == 0) sk.add(sc.filter_radius_off, s_d_radius);
     }
 }
 
 // render_edge_kernel (diffvg.cpp:1388-1475) after the candidates of both sides have been answered.
 __global__ void __launch_bounds__(WB) k_wave_composite_edge(SceneView sc, BinView bins, RenderArgs ra, BoundaryWork bw, WaveView wv) {
-    __shared__ GradCache s_gc;
-    grad_cache_init(s_gc);
+    __shared__ float s_dm[9];
+    __shared__ int s_xoff;
+    if (threadIdx.x < 9) s_dm[threadIdx.x] = 0.f;
+    if (threadIdx.x == 0) s_xoff = -1;
     __syncthreads();
-    const CacheSink sk{&s_gc, ra.d_params};
+    const GlobalSink sk{ra.d_params};
     const int lane = threadIdx.x & 31;
     const int ntiles = bins.tiles_x * bins.tiles_y;
     const int item = blockIdx.x * WNW + (threadIdx.x >> 5);
@@ -448,6 +610,10 @@ __global__ void __launch_bounds__(WB) k_wave_composite_edge(SceneView sc, BinVie
         const bool scatter = active && side == 0 && (my_hit || other_hit);
         float dm[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
         int xoff = -1;
+        GradRec gr;
+        gr.key = -1;
+#pragma unroll
+        for (int j = 0; j < DVG_GREC_N; j++) { gr.addr[j] = -1; gr.val[j] = 0.f; }
         if (scatter) {
             F4 c_in = mine, c_out = other;
             F2 normal = bs.normal;
@@ -460,7 +626,7 @@ __global__ void __launch_bounds__(WB) k_wave_composite_edge(SceneView sc, BinVie
             const float contrib = (diff.x * d_color.x + diff.y * d_color.y + diff.z * d_color.z + diff.w * d_color.w) / bs.pdf;
             const InstInfo &ii = sc.insts[bs.inst];
             const GroupInfo &g = sc.groups[ii.group];
-            accumulate_boundary_gradient(sc, ra, bs, ii, g, contrib, normal, sk);
+            boundary_gradient_record(sc, bs, ii, contrib, normal, gr);
             if (ra.debug_out) {
                 float *o = ra.debug_out + 4 * (size_t)bw.sorted_idx[bw.tile_offsets[ei.tile] + ei.k];
                 o[0] = contrib; o[1] = (float)(my_hit | (other_hit << 1)); o[2] = normal.x; o[3] = normal.y;
@@ -474,16 +640,27 @@ __global__ void __launch_bounds__(WB) k_wave_composite_edge(SceneView sc, BinVie
                 atomicAdd(ra.d_translation + 2 * (el.by * ra.width + el.bx) + 1, normal.y * contrib);
             }
         }
-        // d_shape_to_canvas: warp-reduce when every scattering lane targets the same transform
+        warp_scatter_grouped(gr, ra.d_params);
+        // d_shape_to_canvas: groups very often share ONE transform tensor (the default eye(3)), so every warp of
+        // the launch would add to the same 9 addresses.  Warp-reduce, then accumulate per block in shared
+        // memory for the transform the block saw first; one set of 9 global atomics per block.
         const unsigned am = __ballot_sync(0xffffffffu, xoff >= 0);
         if (am) {
             const int x0 = __shfl_sync(0xffffffffu, xoff, __ffs(am) - 1);
             const bool uniform = __all_sync(0xffffffffu, xoff < 0 || xoff == x0);
             if (uniform) {
+                int owner = 0;
+                if (lane == 0) {
+                    owner = atomicCAS(&s_xoff, -1, x0);
+                    if (owner == -1) owner = x0;
+                }
+                owner = __shfl_sync(0xffffffffu, owner, 0);
 #pragma unroll
                 for (int c = 0; c < 9; c++) {
                     const float v = warp_sum(dm[c]);
-                    if (lane == 0) sk.add(x0 + c, v);
+                    if (lane == 0 && v != 0.f) {
+                        if (owner == x0) atomicAdd(&s_dm[c], v); else atomicAdd(ra.d_params + x0 + c, v);
+                    }
                 }
             } else if (xoff >= 0) {
 #pragma unroll
@@ -492,7 +669,7 @@ __global__ void __launch_bounds__(WB) k_wave_composite_edge(SceneView sc, BinVie
         }
     }
     __syncthreads();
-    grad_cache_flush(s_gc, ra.d_params);
+    if (threadIdx.x < 9 && s_xoff >= 0 && s_dm[threadIdx.x] != 0.f) atomicAdd(ra.d_params + s_xoff + threadIdx.x, s_dm[threadIdx.x]);
 }
 
 // ------------------------------------------------------------------------------------------ host side
@@ -512,6 +689,14 @@ __global__ void k_wave_edge_counts(BoundaryWork bw, const int *tile_choff, int *
     const int items = (bw.tile_counts[t] + W_EDGE_SPI - 1) / W_EDGE_SPI;
     bw.blk_counts[t] = items;
     edge_chunks[t] = items * (tile_choff[t + 1] - tile_choff[t]);
+}
+
+// item -> tile table (one thread per tile writes its run of items)
+__global__ void k_wave_edge_items(BoundaryWork bw, int ntiles) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ntiles) return;
+    const int b = bw.blk_offsets[t], e = bw.blk_offsets[t + 1];
+    for (int i = b; i < e; i++) bw.item_tile[i] = t;
 }
 
 void launch_wave_tile_chunks(const int *bin_offsets, int *nch, int *choff, int *max_nch, int ntiles, cudaStream_t st) {
@@ -539,7 +724,13 @@ void launch_wave_classify_px(const SceneView &sc, const BinView &bins, const Ren
 }
 
 void launch_wave_solve(const SceneView &sc, const WaveView &wv, int n_stroke, int n_fill, cudaStream_t st) {
-    if (n_stroke > 0) DVG_LAUNCH(k_wave_solve_stroke, dim3((n_stroke + 127) / 128), dim3(128), 0, st, sc, wv, n_stroke);
+    if (n_stroke > 0) {
+        cudaMemsetAsync(wv.counters + 2, 0, sizeof(int) * 2, st);
+        DVG_LAUNCH(k_wave_stroke_setup, dim3((n_stroke + W2A_B - 1) / W2A_B), dim3(W2A_B), 0, st, sc, wv, n_stroke);
+        // the unit counts stay on the device: grids cover the queue capacities, surplus threads exit at once
+        DVG_LAUNCH(k_wave_stroke_newton, dim3((wv.cap_ua + 255) / 256), dim3(256), 0, st, sc, wv, 0);
+        DVG_LAUNCH(k_wave_stroke_newton, dim3((wv.cap_ud + 255) / 256), dim3(256), 0, st, sc, wv, 1);
+    }
     if (n_fill > 0) DVG_LAUNCH(k_wave_solve_fill, dim3((n_fill + 127) / 128), dim3(128), 0, st, sc, wv, n_fill);
 }
 
@@ -560,6 +751,7 @@ void launch_wave_boundary_sort(const SceneView &sc, const BinView &bins, const R
     DVG_LAUNCH(k_wave_edge_counts, dim3((ntiles + 255) / 256), dim3(256), 0, st, bw, wv.tile_choff, edge_chunks, ntiles);
     launch_scan(bw.blk_counts, bw.blk_offsets, ntiles, st);
     launch_scan(edge_chunks, wv.edge_choff, ntiles, st);
+    DVG_LAUNCH(k_wave_edge_items, dim3((ntiles + 255) / 256), dim3(256), 0, st, bw, ntiles);
 }
 
 void launch_wave_classify_edge(const SceneView &sc, const BinView &bins, const RenderArgs &ra, const BoundaryWork &bw,

@@ -115,6 +115,7 @@ class PackedScene:
         self.use_prefiltering = use_prefiltering
         self.eval_positions = eval_positions
         self.num_params = int(topo[scene_pack.H_NPARAMS])
+        self.needs_xform_grad = True
 
 
 def _cuda_device():
@@ -139,7 +140,11 @@ class RenderFunction(torch.autograd.Function):
         topo, tensors = scene_pack.pack_scene(canvas_width, canvas_height, shapes, shape_groups,
                                               int(filter.type), filter.radius)
         params = scene_pack.concat_params(tensors)
-        return [PackedScene(topo, canvas_width, canvas_height, output_type, use_prefiltering, eval_positions), params]
+        packed = PackedScene(topo, canvas_width, canvas_height, output_type, use_prefiltering, eval_positions)
+        # d_shape_to_canvas is only worth accumulating when some transform tensor takes part in autograd (every
+        # boundary sample adds to the 9 entries of its group's transform; groups usually share one constant eye(3))
+        packed.needs_xform_grad = any(t.requires_grad for t in tensors[scene_pack.B_MAT3])
+        return [packed, params]
 
     @staticmethod
     def forward(ctx, width, height, num_samples_x, num_samples_y, seed, background_image, *args):
@@ -275,7 +280,7 @@ class RenderFunction(torch.autograd.Function):
                 int(ctx.seed), 1 if ctx.packed.use_prefiltering else 0,
                 eval_dev.data_ptr() if eval_dev is not None else None, eval_dev.shape[0] if eval_dev is not None else 0,
                 d_params.data_ptr(), d_background.data_ptr() if d_background is not None else None, None,
-                0, stream))
+                0 if ctx.packed.needs_xform_grad else n.DVG_BWD_SKIP_XFORM_GRAD, stream))
             if print_timing:
                 torch.cuda.synchronize(dev)
                 print('Backward pass, time: %.5f s' % (time.time() - start))
