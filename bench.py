@@ -44,6 +44,23 @@ EVALS_FWD = 1.0          # colour evaluations per pixel sample, forward
 EVALS_INTERIOR = 1.0     # interior backward (forward recompute)
 EVALS_BOUNDARY = 1.918   # boundary pass (two sides x 96% valid samples)
 
+# Share of the event model per kernel: flop per colour evaluation, the passes the kernel serves in one step
+# (the interior backward pass re-uses the forward pass's classification and exact tests), and the pipe it is
+# bound by.  E2 group-leaf visits 75 + E9 fixed 40 | E4 set-up 986 + E5 bracket evaluations 553 |
+# E6 Newton 1277 + E7 accepted roots 350 | E8 fragments 23 (per pixel sample at this config).
+KERNEL_MODEL = {
+    'k_wave_classify_px': (115.0, ('fwd',), 'fp32'),
+    'k_wave_classify_edge': (115.0, ('edge',), 'fp32'),
+    'k_wave_stroke_setup': (1539.0, ('fwd', 'edge'), 'fp64'),
+    'k_wave_stroke_newton': (1627.0, ('fwd', 'edge'), 'fp64'),
+    'k_wave_composite_px<false>': (63.0, ('fwd',), 'fp32'),
+    'k_wave_composite_px<true>': (63.0, ('interior',), 'fp32'),
+    'k_wave_composite_edge': (63.0, ('edge',), 'fp32'),
+    'k_edge': (3304.0, ('edge',), 'fp32'),
+    'k_render<true>': (3304.0, ('interior',), 'fp32'),
+    'k_render<false>': (3304.0, ('fwd',), 'fp32'),
+}
+
 METRIC = 'fwd+bwd iters/s'
 UNIT = 'it/s'
 WORKLOAD = 'painterly: 2048 open cubic strokes (1-3 segments, width 1-4), 512x512, 4x4 spp, L2 loss, fwd+bwd'
@@ -295,26 +312,33 @@ def main():
         kernels = {k: {'launches': c, 'ms_per_step': ms / args.steps} for k, (c, ms) in rep.items()}
         total_k = sum(v['ms_per_step'] for v in kernels.values())
         top = max(kernels, key=lambda k: kernels[k]['ms_per_step'])
-        evals = {'k_edge': EVALS_BOUNDARY, 'k_render<true>': EVALS_INTERIOR, 'k_render<false>': EVALS_FWD}.get(top, 1.0)
         fp32_peak = n.measure_peak(0, local_rank)
         fp64_peak = n.measure_peak(1, local_rank)
-        flops = FALG_PER_EVAL * evals * N_SAMPLES
-        top_ms = kernels[top]['ms_per_step'] / max(kernels[top]['launches'] / args.steps, 1)
+        # algorithmic flops of the kernel per STEP: its share of the event model (KERNEL_MODEL) times the colour
+        # evaluations of the passes it serves; a kernel launched by several passes is timed over all its launches
+        flops_per_eval, passes, bound = KERNEL_MODEL.get(top, (FALG_PER_EVAL, ('fwd', 'edge'), 'fp32'))
+        evals = sum({'fwd': EVALS_FWD, 'interior': EVALS_INTERIOR, 'edge': EVALS_BOUNDARY}[p] for p in passes)
+        flops = flops_per_eval * evals * N_SAMPLES
+        top_ms = kernels[top]['ms_per_step']
         achieved = flops / (top_ms * 1e-3) / 1e12
+        peak = fp64_peak if bound == 'fp64' else fp32_peak
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
         except Exception:
             pass
-        # compulsory DRAM traffic of that kernel: scene tables + d_image + weight image + gradient buffer
-        alg_bytes = W * H * 4 * 4 + W * H * 4 + 2 * params_np.nbytes * 8
-        roofline = {'bound': 'fp32', 'kernel': top, 'achieved': achieved, 'peak': fp32_peak, 'unit': 'TFLOP/s',
-                    'frac': achieved / fp32_peak if fp32_peak else None,
-                    'peak_source': 'FFMA-chain probe measured live in this run (MEASURED_PEAKS.json has no FP32 figure); '
-                                   'FP64 DFMA probe %.2f TFLOP/s' % fp64_peak,
-                    'kernel_ms': top_ms, 'kernel_share_of_step': kernels[top]['ms_per_step'] / total_k,
-                    'algorithmic_flops_per_launch': flops,
-                    'hbm': {'algorithmic_bytes': alg_bytes, 'achieved_gbs': alg_bytes / (top_ms * 1e-3) / 1e9,
+        # compulsory DRAM traffic of the whole step: queues + result words + images + scene tables
+        alg_bytes = W * H * 4 * 4 * 2 + W * H * 4 + 2 * params_np.nbytes * 8
+        roofline = {'bound': bound, 'kernel': top, 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
+                    'frac': achieved / peak if peak else None,
+                    'peak_source': 'FMA-chain probes measured live in this run (MEASURED_PEAKS.json has no CUDA-core figure): '
+                                   'FP32 %.2f, FP64 %.2f TFLOP/s' % (fp32_peak, fp64_peak),
+                    'kernel_ms_per_step': top_ms, 'kernel_launches_per_step': kernels[top]['launches'] / args.steps,
+                    'kernel_share_of_step': top_ms / total_k,
+                    'algorithmic_flops_per_step': flops, 'model': 'SURVEY 8d event model: %.0f flop per colour evaluation '
+                    'for this kernel (%s), %.3f evaluations per pixel sample' % (flops_per_eval, '+'.join(passes), evals),
+                    'step_achieved_tflops': FALG_PER_EVAL * (EVALS_FWD + EVALS_INTERIOR + EVALS_BOUNDARY) * N_SAMPLES / (ms_per_step * 1e-3) / 1e12,
+                    'hbm': {'algorithmic_bytes': alg_bytes, 'achieved_gbs': alg_bytes / (ms_per_step * 1e-3) / 1e9,
                             'peak_gbs': peaks.get('hbm_gbs', 6650.0),
                             'peak_source': 'measured' if 'hbm_gbs' in peaks else 'fallback'},
                     'traffic': None}

@@ -26,10 +26,39 @@ __global__ void k_build_prims(BuildView bv) {
 // scene.cpp:207-246.  Sequential float prefix sum in the reference's order (single thread),
 // then the normalisation in parallel by the rest of the block.
 __global__ void k_build_shape_cdf(BuildView bv) {
-    __shared__ float s_norm;
-    if (threadIdx.x == 0) s_norm = build_shape_cdf_serial(bv);
+    // The prefix sum itself must run in the reference's sequential float order (which shape a boundary sample
+    // picks depends on it bit for bit), but its operands need not be fetched by the summing thread: the block
+    // stages 4096 lengths at a time in shared memory (two dependent global loads per element would cost the
+    // lone thread ~0.3 ms at 2048 shapes), thread 0 sums them there, and the block writes the results back.
+    constexpr int CH = 4096;
+    __shared__ float s_len[CH];
+    __shared__ float s_cdf[CH];
+    __shared__ float s_carry;
+    if (threadIdx.x == 0) s_carry = 0.f;
+    for (int base = 0; base < bv.num_insts; base += CH) {
+        const int n = min(CH, bv.num_insts - base);
+        for (int i = threadIdx.x; i < n; i += blockDim.x) s_len[i] = bv.shapes_length[bv.inst_shape[base + i]];
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float c = s_carry;
+            for (int i = 0; i < n; i++) {
+                c = (base + i == 0) ? s_len[i] : s_len[i] + c;   // scene.cpp:217-222
+                s_cdf[i] = c;
+            }
+            s_carry = c;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += blockDim.x) { bv.shape_cdf[base + i] = s_cdf[i]; bv.shape_pmf[base + i] = s_len[i]; }
+        __syncthreads();
+    }
+    const float norm = s_carry;
+    if (threadIdx.x == 0) {
+        if (!(norm > 0.f)) *bv.error_flag = 1;            // scene.cpp:231-235 (also catches NaN)
+        else if (isinf(norm)) *bv.error_flag = 2;         // scene.cpp:236-240
+        else *bv.error_flag = 0;
+        *bv.total_length = norm;
+    }
     __syncthreads();
-    float norm = s_norm;
     for (int i = threadIdx.x; i < bv.num_insts; i += blockDim.x) {
         bv.shape_cdf[i] /= norm;
         bv.shape_pmf[i] /= norm;

@@ -27,6 +27,9 @@
 
 namespace dvg {
 
+#ifndef DVG_WB_MIN
+#define DVG_WB_MIN 4
+#endif
 constexpr int WB = 256;            // threads per block of the per-item kernels (8 items)
 constexpr int WNW = WB / 32;
 constexpr int W_EDGE_SPI = 16;     // boundary samples per item (two lanes per sample)
@@ -212,7 +215,7 @@ DVG_D PixelItem pixel_item(const BinView &bins, const RenderArgs &ra, const Wave
     return pi;
 }
 
-__global__ void __launch_bounds__(WB) k_wave_classify_px(SceneView sc, BinView bins, RenderArgs ra, WaveView wv, int num_items) {
+__global__ void __launch_bounds__(WB, DVG_WB_MIN) k_wave_classify_px(SceneView sc, BinView bins, RenderArgs ra, WaveView wv, int num_items) {
     __shared__ WaveScratch s_ws[WNW];
     const int item = blockIdx.x * WNW + (threadIdx.x >> 5);
     if (item >= num_items) return;
@@ -263,7 +266,7 @@ DVG_D EdgeLane edge_lane(const SceneView &sc, const RenderArgs &ra, const Bounda
     return el;
 }
 
-__global__ void __launch_bounds__(WB) k_wave_classify_edge(SceneView sc, BinView bins, RenderArgs ra, BoundaryWork bw, WaveView wv) {
+__global__ void __launch_bounds__(WB, DVG_WB_MIN) k_wave_classify_edge(SceneView sc, BinView bins, RenderArgs ra, BoundaryWork bw, WaveView wv) {
     __shared__ WaveScratch s_ws[WNW];
     const int ntiles = bins.tiles_x * bins.tiles_y;
     const int item = blockIdx.x * WNW + (threadIdx.x >> 5);
@@ -458,7 +461,7 @@ DVG_D void wave_consume(const SceneView &sc, const BinView &bins, const WaveView
 
 // render_kernel (diffvg.cpp:1161-1272), colour output, after the candidates have been answered.
 template <bool BACKWARD>
-__global__ void __launch_bounds__(WB) k_wave_composite_px(SceneView sc, BinView bins, RenderArgs ra, WaveView wv, int num_items) {
+__global__ void __launch_bounds__(WB, DVG_WB_MIN) k_wave_composite_px(SceneView sc, BinView bins, RenderArgs ra, WaveView wv, int num_items) {
     __shared__ float s_d_radius;
     if (BACKWARD) {
         if (threadIdx.x == 0) s_d_radius = 0.f;
@@ -567,7 +570,7 @@ __global__ void __launch_bounds__(WB) k_wave_composite_px(SceneView sc, BinView 
 }
 
 // render_edge_kernel (diffvg.cpp:1388-1475) after the candidates of both sides have been answered.
-__global__ void __launch_bounds__(WB) k_wave_composite_edge(SceneView sc, BinView bins, RenderArgs ra, BoundaryWork bw, WaveView wv) {
+__global__ void __launch_bounds__(WB, DVG_WB_MIN) k_wave_composite_edge(SceneView sc, BinView bins, RenderArgs ra, BoundaryWork bw, WaveView wv) {
     __shared__ float s_dm[9];
     __shared__ int s_xoff;
     if (threadIdx.x < 9) s_dm[threadIdx.x] = 0.f;

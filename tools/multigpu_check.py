@@ -1,0 +1,61 @@
+#!/usr/bin/env python
+"""Multi-GPU check of the row-sharded render (diffvg_b200/sharded.py), run under torchrun on one box:
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
+        tools/multigpu_check.py
+
+Every rank renders its band of pixel rows of the SAME scene / seed (forward: all-gather of the bands;
+backward: boundary samples of the same rows, NCCL all-reduce of the gradient buffer) and compares the
+assembled image and the summed gradients with an unsharded render of its own.  Prints one line per rank."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, 'tests')):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+
+def main():
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+    dist.init_process_group('nccl', device_id=dev)
+    from diffvg_b200 import pydiffvg, sharded
+    import scenes
+    pydiffvg.set_use_gpu(True)
+    pydiffvg.set_device(dev)
+    ok = True
+    for name, scene, (w, h, nsx, nsy) in (('painterly256', scenes.painterly(num_paths=256, canvas=128), (128, 128, 4, 4)),
+                                          ('blobs64', scenes.blobs(num_paths=64, canvas=96), (96, 96, 2, 2))):
+        cw, ch, shapes, groups = scene
+        args = pydiffvg.RenderFunction.serialize_scene(cw, ch, shapes, groups)
+        packed, params = args
+        params = params.detach().to(dev).requires_grad_(True)
+        target = torch.rand(h, w, 4, generator=torch.Generator().manual_seed(3)).to(dev)
+        img1 = pydiffvg.RenderFunction.apply(w, h, nsx, nsy, 7, None, packed, params)
+        (g1,) = torch.autograd.grad((img1 - target).pow(2).mean(), params)
+        img2 = sharded.ShardedRenderFunction.apply(w, h, nsx, nsy, 7, None, packed, params)
+        (g2,) = torch.autograd.grad((img2 - target).pow(2).mean(), params)
+        d_img = float((img1 - img2).abs().max())
+        rel = float((g1 - g2).norm() / g1.norm().clamp_min(1e-30))
+        good = d_img <= 1e-6 and rel <= 1e-4
+        ok = ok and good
+        print('rank %d/%d %-12s bands %s image max-abs %.3g grad rel-L2 %.3g %s' % (
+            rank, world, name, sharded.row_partition(h, world, sharded.tile_height(nsx * nsy)), d_img, rel, 'OK' if good else 'MISMATCH'),
+            flush=True)
+    flag = torch.tensor([0 if ok else 1], device=dev)
+    dist.all_reduce(flag)
+    dist.destroy_process_group()
+    sys.exit(int(flag.item() != 0))
+
+
+if __name__ == '__main__':
+    main()
