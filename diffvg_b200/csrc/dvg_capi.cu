@@ -86,7 +86,7 @@ struct DvgScene {
     DevBuf d_keys, d_tile_counts, d_tile_offsets, d_tile_fill, d_blk_counts, d_blk_offsets, d_sorted;
     // wavefront passes (dvg_wave.cu)
     DevBuf d_wave_hit, d_wave_wind, d_wave_pairs_s, d_wave_pairs_f, d_wave_units_a, d_wave_units_d, d_wave_counters, d_tile_nch, d_tile_choff,
-        d_edge_chunks, d_edge_choff, d_wave_max, d_bsamples, d_item_tile;
+        d_edge_chunks, d_edge_choff, d_wave_max, d_bsamples, d_item_tile, d_grad_rep;
     int total_chunks = 0, max_nch = 0;   // of the current bins (read back with the bin total)
     bool has_fills = false;
     // which pixel pass the result words currently hold (forward's are reused by the interior backward pass)
@@ -150,7 +150,7 @@ struct DvgScene {
                          &d_shape_cdf, &d_shape_pmf, &d_flags, &d_bin_counts, &d_bin_offsets, &d_bin_items, &d_weight,
                          &d_keys, &d_tile_counts, &d_tile_offsets, &d_tile_fill, &d_blk_counts, &d_blk_offsets, &d_sorted,
                          &d_wave_hit, &d_wave_wind, &d_wave_pairs_s, &d_wave_pairs_f, &d_wave_units_a, &d_wave_units_d, &d_wave_counters, &d_tile_nch, &d_tile_choff,
-                         &d_edge_chunks, &d_edge_choff, &d_wave_max, &d_bsamples, &d_item_tile};
+                         &d_edge_chunks, &d_edge_choff, &d_wave_max, &d_bsamples, &d_item_tile, &d_grad_rep};
         for (DevBuf *b : all) b->release();
         if (h_pinned) cudaFreeHost(h_pinned);
         h_pinned = nullptr;
@@ -642,6 +642,13 @@ static int render_backward_impl(DvgScene *s, const float *background, const floa
     ra.d_params = d_params; ra.d_background = d_background; ra.d_translation = d_translation;
     ra.debug_out = g_debug_out;
     if (!(flags & DVG_BWD_ACCUMULATE)) CK(cudaMemsetAsync(d_params, 0, sizeof(float) * s->num_params, st));
+    const bool wave_grads = d_render_image && !use_prefiltering && !g_fused;
+    if (wave_grads) {   // private copies of the gradient buffer for the wavefront composite kernels (dvg_wave.cu grad_replica)
+        ra.grad_reps = 32; ra.num_params = s->num_params;
+        CK(s->d_grad_rep.ensure(sizeof(float) * (size_t)ra.grad_reps * s->num_params));
+        ra.d_params_rep = s->d_grad_rep.as<float>();
+        CK(cudaMemsetAsync(ra.d_params_rep, 0, sizeof(float) * (size_t)ra.grad_reps * s->num_params, st));
+    }
     if (d_background)
         CK(cudaMemsetAsync(d_background + 4 * (size_t)row_begin * width, 0, sizeof(float) * 4 * (size_t)width * (row_end - row_begin), st));
     if (d_translation) CK(cudaMemsetAsync(d_translation, 0, sizeof(float) * 2 * (size_t)width * height, st));
@@ -685,6 +692,10 @@ static int render_backward_impl(DvgScene *s, const float *background, const floa
                     rc = wave_edge_pass(s, sc, bins, ra, bw, st);
                     if (rc) return rc;
                 }
+            }
+            if (wave_grads) {
+                launch_wave_reduce_grads(ra, st);
+                CK(cudaGetLastError());
             }
         }
     }

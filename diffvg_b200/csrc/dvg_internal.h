@@ -94,6 +94,7 @@ void launch_boundary_sort(const SceneView &sc, const BinView &bins, const Render
 
 void launch_wave_tile_chunks(const int *bin_offsets, int *nch, int *choff, int *max_nch, int ntiles, cudaStream_t st);
 int wave_pixel_items(const BinView &bins, const RenderArgs &ra);
+void launch_wave_reduce_grads(const RenderArgs &ra, cudaStream_t st);
 int wave_items_per_tile(const BinView &bins, const RenderArgs &ra);
 int wave_edge_samples_per_item();
 void launch_wave_classify_px(const SceneView &sc, const BinView &bins, const RenderArgs &ra, const WaveView &wv, cudaStream_t st);

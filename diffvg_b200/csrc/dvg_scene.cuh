@@ -120,6 +120,8 @@ struct RenderArgs {
     float *render_image;           // [H,W,4] forward output (accumulated)
     const float *d_render_image;   // [H,W,4] backward input
     float *d_params;
+    float *d_params_rep;           // wavefront path: grad_reps private copies of the gradient buffer (see dvg_wave.cu), summed at the end
+    int grad_reps, num_params;
     float *d_background;
     float *d_translation;
     float *debug_out;              // [n,4] per boundary sample (contrib, hit bits, normal) -- debug builds of the tests only

@@ -55,6 +55,23 @@ DVG_D int warp_reserve(int *counter, int count) {
 // barrier before its flush and, having no native shared-memory float add, spins on CAS: 30% of the boundary
 // composite.  Here lanes that target the same segment are summed with shuffles and the leader issues one
 // fire-and-forget `red.global.add.f32` per address (atomic.h:23-51 does one atomic per component per sample).
+// Contention: some addresses are hit by EVERY warp of a launch (d_filter.radius; d_shape_to_canvas of a transform
+// tensor shared by all groups, typically the default eye(3)).  Instead of reducing them per block in shared memory
+// behind a barrier (warps of a block finish at very different times: the barrier was 27% of the interior backward
+// kernel), every block adds into one of `grad_reps` private copies of the whole gradient buffer, chosen by block
+// index; k_wave_reduce_grads sums the copies.  32 copies x 155 KB at the painterly config.
+DVG_D float *grad_replica(const RenderArgs &ra) {
+    return ra.d_params_rep + (size_t)(blockIdx.x & (unsigned)(ra.grad_reps - 1)) * (size_t)ra.num_params;
+}
+
+__global__ void k_wave_reduce_grads(const float *rep, int reps, int n, float *out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float s = 0.f;
+    for (int r = 0; r < reps; r++) s += rep[(size_t)r * n + i];
+    if (s != 0.f) out[i] += s;
+}
+
 struct GlobalSink {
     float *D;
     __device__ __forceinline__ void add(int idx, float v) const {
@@ -462,12 +479,7 @@ DVG_D void wave_consume(const SceneView &sc, const BinView &bins, const WaveView
 // render_kernel (diffvg.cpp:1161-1272), colour output, after the candidates have been answered.
 template <bool BACKWARD>
 __global__ void __launch_bounds__(WB, DVG_WB_MIN) k_wave_composite_px(SceneView sc, BinView bins, RenderArgs ra, WaveView wv, int num_items) {
-    __shared__ float s_d_radius;
-    if (BACKWARD) {
-        if (threadIdx.x == 0) s_d_radius = 0.f;
-        __syncthreads();
-    }
-    const GlobalSink sk{ra.d_params};
+    const GlobalSink sk{BACKWARD ? grad_replica(ra) : nullptr};
     const int lane = threadIdx.x & 31;
     const int item = blockIdx.x * WNW + (threadIdx.x >> 5);
     const int spp = ra.nsx * ra.nsy;
@@ -561,26 +573,21 @@ __global__ void __launch_bounds__(WB, DVG_WB_MIN) k_wave_composite_px(SceneView 
             if (active) d_radius_acc += filter_radius_grad(sc, ra, x, y, pt, color);
         }
     }
-    if (BACKWARD) {   // every sample adds to d_filter.radius: one global atomic per block
+    if (BACKWARD) {   // every sample adds to d_filter.radius
         d_radius_acc = warp_sum(d_radius_acc);
-        if (lane == 0 && d_radius_acc != 0.f) atomicAdd(&s_d_radius, d_radius_acc);
-        __syncthreads();
-        if (threadIdx.x == 0) sk.add(sc.filter_radius_off, s_d_radius);
+        if (lane == 0) sk.add(sc.filter_radius_off, d_radius_acc);
     }
 }
 
 // render_edge_kernel (diffvg.cpp:1388-1475) after the candidates of both sides have been answered.
 __global__ void __launch_bounds__(WB, DVG_WB_MIN) k_wave_composite_edge(SceneView sc, BinView bins, RenderArgs ra, BoundaryWork bw, WaveView wv) {
-    __shared__ float s_dm[9];
-    __shared__ int s_xoff;
-    if (threadIdx.x < 9) s_dm[threadIdx.x] = 0.f;
-    if (threadIdx.x == 0) s_xoff = -1;
-    __syncthreads();
-    const GlobalSink sk{ra.d_params};
+    float *const D = grad_replica(ra);
+    const GlobalSink sk{D};
     const int lane = threadIdx.x & 31;
     const int ntiles = bins.tiles_x * bins.tiles_y;
     const int item = blockIdx.x * WNW + (threadIdx.x >> 5);
-    if (item < bw.blk_offsets[ntiles]) {
+    if (item >= bw.blk_offsets[ntiles]) return;
+    {
         const EdgeItem ei = edge_item(bins, bw, wv, item);
         const EdgeLane el = edge_lane(sc, ra, bw, ei);
         const BoundarySample &bs = el.bs;
@@ -643,27 +650,17 @@ __global__ void __launch_bounds__(WB, DVG_WB_MIN) k_wave_composite_edge(SceneVie
                 atomicAdd(ra.d_translation + 2 * (el.by * ra.width + el.bx) + 1, normal.y * contrib);
             }
         }
-        warp_scatter_grouped(gr, ra.d_params);
-        // d_shape_to_canvas: groups very often share ONE transform tensor (the default eye(3)), so every warp of
-        // the launch would add to the same 9 addresses.  Warp-reduce, then accumulate per block in shared
-        // memory for the transform the block saw first; one set of 9 global atomics per block.
+        warp_scatter_grouped(gr, D);
+        // d_shape_to_canvas: warp-reduce when every scattering lane targets the same transform
         const unsigned am = __ballot_sync(0xffffffffu, xoff >= 0);
         if (am) {
             const int x0 = __shfl_sync(0xffffffffu, xoff, __ffs(am) - 1);
             const bool uniform = __all_sync(0xffffffffu, xoff < 0 || xoff == x0);
             if (uniform) {
-                int owner = 0;
-                if (lane == 0) {
-                    owner = atomicCAS(&s_xoff, -1, x0);
-                    if (owner == -1) owner = x0;
-                }
-                owner = __shfl_sync(0xffffffffu, owner, 0);
 #pragma unroll
                 for (int c = 0; c < 9; c++) {
                     const float v = warp_sum(dm[c]);
-                    if (lane == 0 && v != 0.f) {
-                        if (owner == x0) atomicAdd(&s_dm[c], v); else atomicAdd(ra.d_params + x0 + c, v);
-                    }
+                    if (lane == 0) sk.add(x0 + c, v);
                 }
             } else if (xoff >= 0) {
 #pragma unroll
@@ -671,8 +668,6 @@ __global__ void __launch_bounds__(WB, DVG_WB_MIN) k_wave_composite_edge(SceneVie
             }
         }
     }
-    __syncthreads();
-    if (threadIdx.x < 9 && s_xoff >= 0 && s_dm[threadIdx.x] != 0.f) atomicAdd(ra.d_params + s_xoff + threadIdx.x, s_dm[threadIdx.x]);
 }
 
 // ------------------------------------------------------------------------------------------ host side
@@ -706,6 +701,11 @@ void launch_wave_tile_chunks(const int *bin_offsets, int *nch, int *choff, int *
     cudaMemsetAsync(max_nch, 0, sizeof(int), st);
     DVG_LAUNCH(k_wave_tile_chunks, dim3((ntiles + 255) / 256), dim3(256), 0, st, bin_offsets, nch, max_nch, ntiles);
     launch_scan(nch, choff, ntiles, st);
+}
+
+void launch_wave_reduce_grads(const RenderArgs &ra, cudaStream_t st) {
+    DVG_LAUNCH(k_wave_reduce_grads, dim3((ra.num_params + 255) / 256), dim3(256), 0, st, ra.d_params_rep, ra.grad_reps, ra.num_params,
+               ra.d_params);
 }
 
 int wave_pixel_items(const BinView &bins, const RenderArgs &ra) {

@@ -195,3 +195,44 @@ def test_error_paths():
     args = pydiffvg.RenderFunction.serialize_scene(cw, ch, shapes, groups)
     with pytest.raises(NotImplementedError):
         pydiffvg.RenderFunction.apply(16, 16, 1, 1, 0, torch.ones(16, 16, 3), *args)
+
+
+def test_pydiffvg_backward_reuses_forward_result_words_and_matches_oracle():
+    """Forward and backward on ONE native scene object (the pydiffvg path): the interior backward term re-uses
+    the result words of the forward pass, the boundary pass then overwrites them, and a second iteration with a
+    new seed must not see stale words.  Compared with the oracle entry by entry; also the flag that skips
+    d_shape_to_canvas when no transform takes part in autograd must only zero those entries."""
+    from diffvg_b200 import pydiffvg, scene_pack
+    pydiffvg.set_use_gpu(True)
+    cw, ch, shapes, groups = scenes.zoo()
+    args = pydiffvg.RenderFunction.serialize_scene(cw, ch, shapes, groups)
+    packed, params0 = args
+    assert packed.needs_xform_grad is False
+    topo, params_np = util.pack((cw, ch, shapes, groups))
+    target = torch.rand(96, 96, 4, generator=torch.Generator().manual_seed(11))
+    for seed in (3, 4):
+        params = params0.detach().clone().requires_grad_(True)
+        img = pydiffvg.RenderFunction.apply(96, 96, 2, 2, seed, None, packed, params)
+        loss = (img.cpu() - target).pow(2).mean()
+        (g,) = torch.autograd.grad(loss, params)
+        ref = oracle_check.render(topo, params_np, 96, 96, 2, 2, seed)
+        assert np.abs(ref['image'] - img.detach().cpu().numpy()).max() <= FWD_TOL
+        d_img = (2.0 * (img.detach().cpu().numpy() - target.numpy()) / target.numel()).astype(np.float32)
+        rb = oracle_check.render(topo, params_np, 96, 96, 2, 2, seed, d_render_image=d_img)['d_params'].copy()
+        got = g.cpu().numpy().copy()
+        # transform entries: skipped (zero) here, present in the oracle
+        goff = int(topo[scene_pack.H_OFF_GROUPS])
+        for gi in range(int(topo[scene_pack.H_NG])):
+            xo = int(topo[goff + gi * scene_pack.G_LEN + 9])
+            assert not got[xo:xo + 9].any()
+            rb[xo:xo + 9] = 0.0
+        grad_close(rb, got, topo=topo)
+    # with a transform that requires a gradient nothing is skipped
+    xf = torch.eye(3, requires_grad=True)
+    for gr in groups:
+        gr.shape_to_canvas = xf
+    packed2, params2 = pydiffvg.RenderFunction.serialize_scene(cw, ch, shapes, groups)
+    assert packed2.needs_xform_grad is True
+    img = pydiffvg.RenderFunction.apply(96, 96, 2, 2, 3, None, packed2, params2)
+    (img.cpu() - target).pow(2).mean().backward()
+    assert xf.grad is not None and float(xf.grad.abs().sum()) > 0

@@ -52,7 +52,8 @@ def main():
                          capture_output=True, text=True).stdout
     # the report may hold several kernels matching: split on the "Kernel Name" header rows
     blocks = re.split(r'(?m)^"Kernel Name",', txt)
-    mangled = {'k_edge': 'k_edge', 'k_render<1>': 'k_renderILb1', 'k_render<0>': 'k_renderILb0'}
+    mangled = {'k_edge': 'k_edge', 'k_render<1>': 'k_renderILb1', 'k_render<0>': 'k_renderILb0',
+               'k_wave_composite_px<1>': 'k_wave_composite_pxILb1', 'k_wave_composite_px<0>': 'k_wave_composite_pxILb0'}
     for blk in blocks[1:]:
         name = blk.splitlines()[0]
         rows = list(csv.reader(io.StringIO('\n'.join(blk.splitlines()[1:]))))
