@@ -195,6 +195,8 @@ def main():
     dev = torch.device('cuda', local_rank)
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        if os.environ.get('NCCL_DEBUG', '').upper() in ('VERSION', ''):
+            os.environ['NCCL_DEBUG'] = 'WARN'      # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group('nccl', device_id=dev)
     n_gpus = world
 
@@ -223,14 +225,14 @@ def main():
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     inv_numel = 2.0 / img.numel()
 
-    def device_step(i):
+    def device_step(i, collective=True):
         seed = i * world + rank
         n.check(n.lib.dvg_scene_set_params(h, params_dev.data_ptr(), params_dev.numel(), 1, stream))
         n.check(n.lib.dvg_render_forward(h, None, img.data_ptr(), None, W, H, NSX, NSY, seed, 0, None, 0, stream))
         d_img = (img - target) * inv_numel          # d/d img of mean((img - target)^2)
         n.check(n.lib.dvg_render_backward(h, None, d_img.data_ptr(), None, W, H, NSX, NSY, seed, 0, None, 0,
                                           d_params.data_ptr(), None, None, 0, stream))
-        if world > 1:
+        if world > 1 and collective:
             dist.all_reduce(d_params)
 
     def timed(step_fn, steps, first):
@@ -305,7 +307,7 @@ def main():
         n.profile_enable(True)
         for k in range(args.steps):
             flush_buf.fill_(k & 0xff)
-            device_step(args.warmup + k)
+            device_step(args.warmup + k, collective=False)   # rank 0 alone: no collective in this pass
         torch.cuda.synchronize(dev)
         rep = n.profile_report()
         n.profile_enable(False)

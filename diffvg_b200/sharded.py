@@ -138,7 +138,8 @@ class ShardedRenderFunction(torch.autograd.Function):
             n.check(n.lib.dvg_render_backward_rows(
                 ns.handle, bg.data_ptr() if bg is not None else None, grad_img.data_ptr(),
                 width, height, nsx, nsy, int(seed), 1 if ctx.packed.use_prefiltering else 0, rb, re,
-                d_params.data_ptr(), d_bg.data_ptr() if d_bg is not None else None, 0, stream))
+                d_params.data_ptr(), d_bg.data_ptr() if d_bg is not None else None,
+                0 if ctx.packed.needs_xform_grad else n.DVG_BWD_SKIP_XFORM_GRAD, stream))
             allreduce_gradients(d_params, ctx.group)
             if d_bg is not None:
                 allreduce_gradients(d_bg, ctx.group)

@@ -44,7 +44,7 @@ def main():
         (g1,) = torch.autograd.grad((img1 - target).pow(2).mean(), params)
         img2 = sharded.ShardedRenderFunction.apply(w, h, nsx, nsy, 7, None, packed, params)
         (g2,) = torch.autograd.grad((img2 - target).pow(2).mean(), params)
-        d_img = float((img1 - img2).abs().max())
+        d_img = float((img1 - img2).detach().abs().max())
         rel = float((g1 - g2).norm() / g1.norm().clamp_min(1e-30))
         good = d_img <= 1e-6 and rel <= 1e-4
         ok = ok and good
