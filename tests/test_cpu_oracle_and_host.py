@@ -279,3 +279,57 @@ def test_pack_scene_memo_reuses_topology_and_tracks_changes():
     groups[1].stroke_color = torch.rand(3)
     with pytest.raises(ValueError):
         scene_pack.pack_scene(cw, ch, shapes, groups, 0, fr)
+
+
+# ------------------------------------------------------------------ plain-C restatement (oracle/dvg_oracle.c)
+def _c_oracle():
+    import subprocess
+    import c_oracle
+    if not c_oracle.available():
+        subprocess.check_call(['make', '-C', os.path.join(os.path.dirname(__file__), '..', 'oracle'), 'oracle'])
+    return c_oracle
+
+
+def test_c_restatement_pcg_known_answers():
+    """(idx, seed) -> (state, rx, ry), validated against pcg.h."""
+    c = _c_oracle()
+    kats = [((0, 0), 0xf6e7b88658a69fc9, 0.452188373, 0.983064532),
+            ((1, 0), 0xa78ba0e0f1d19e25, 0.0703772306, 0.112021565),
+            ((0, 1), 0x4f39acb3a53c1ef6, 0.863092065, 0.755336404),
+            ((262143, 1), 0x400029050581209a, 0.628906608, 0.358397841),
+            ((4194303, 7), 0xc727c8286e921ba8, 0.997012258, 0.773138762)]
+    for (idx, seed), state, rx, ry in kats:
+        st, x, y = c.pcg(idx, seed)
+        assert st == state and abs(x - rx) < 1e-8 and abs(y - ry) < 1e-8
+
+
+@pytest.mark.parametrize('path', sorted(glob.glob(os.path.join(os.path.dirname(__file__), 'golden', '*.npz'))),
+                         ids=lambda p: os.path.basename(p)[:-4])
+def test_c_restatement_forward_matches_reference_golden(path):
+    """The restatement is pinned against outputs of the compiled reference (tests/golden/*.npz, made by
+    tests/golden/make_golden.py): forward images within the 1e-5 bar (bit-identical except where the pixel
+    filter spreads a sample over several pixels and the summation order differs)."""
+    c = _c_oracle()
+    g = np.load(path)
+    name = os.path.basename(path)[:-4]
+    W, H, nsx, nsy, seed, ft = [int(v) for v in g['config']]
+    from golden.make_golden import background_for
+    bg = background_for(name, H, W) if 'd_background' in g.files else None
+    img = c.render(g['topo'], g['params'], W, H, nsx, nsy, seed, background=bg)['image']
+    assert np.abs(img - g['image']).max() <= 1e-5
+
+
+def test_c_restatement_known_image_sums():
+    """SURVEY 8c known answers from the reference CPU build (256^2, 2x2 spp, seed 0, float64 sums)."""
+    c = _c_oracle()
+    for scene, want in ((scenes.single_circle(), 11052.250240), (scenes.single_stroke(), 4938.100155)):
+        topo, params = util.pack(scene)
+        img = c.render(topo, params, 256, 256, 2, 2, 0)['image']
+        assert abs(img.astype(np.float64).sum() - want) < 2e-3
+
+
+def test_c_restatement_refuses_what_it_does_not_restate():
+    c = _c_oracle()
+    topo, params = util.pack(scenes.single_circle())
+    with pytest.raises(RuntimeError):
+        c.render(topo, params, 32, 32, 1, 1, 0, d_render_image=np.zeros((32, 32, 4), np.float32))
