@@ -72,6 +72,38 @@ DVG_D bool overlaps(Box a, float x0, float y0, float x1, float y1) {
     return a.x0 <= x1 && a.x1 >= x0 && a.y0 <= y1 && a.y1 >= y0;
 }
 
+// Tight binning of curved strokes.  A diagonal 40-px stroke has a 900 px^2 bounding box and a 100 px^2
+// footprint; binned by box, two thirds of a tile's candidates are strokes that no sample of the tile can touch,
+// and every one of them costs each sample a leaf test + an 8-piece bracket test in the classify kernels.  The
+// polyline bracket (dvg_scene.cuh) proves "farther than R_out from every chord => the exact stroke test returns
+// false"; here the same statement is made for a whole tile: the tile is cut into squares, and a square whose
+// centre is farther than R_out + half-diagonal from a chord cannot contain such a point.  NaN records keep.
+DVG_D bool bracket_reaches_tile(const F4 *cap, float x0, float y0, float x1, float y1) {
+    const float w = x1 - x0, h = y1 - y0;
+    const bool wide = w >= h;
+    const float side = wide ? h : w;
+    const int nsq = min(8, max(1, (int)ceilf((wide ? w : h) / fmaxf(side, 1e-6f))));
+    const float step = (wide ? w : h) / nsq;
+    const float hd = 0.5f * sqrtf(step * step + side * side);   // half diagonal of one piece of the tile
+    bool far_all = true;
+#pragma unroll 1
+    for (int i = 0; i < DVG_CAP_N; i++) {
+        const F4 ca = cap[2 * i], cb = cap[2 * i + 1];   // A.xy, d.xy | 1/|d|^2, R_out^2, R_in^2, pad
+        const float R = sqrtf(cb.y) + hd;
+        const float thr = R * R;
+        for (int q = 0; q < nsq; q++) {
+            const float cx = wide ? x0 + (q + 0.5f) * step : 0.5f * (x0 + x1);
+            const float cy = wide ? 0.5f * (y0 + y1) : y0 + (q + 0.5f) * step;
+            const float wx = cx - ca.x, wy = cy - ca.y;
+            float t = (wx * ca.z + wy * ca.w) * cb.x;
+            t = t < 0.f ? 0.f : (t > 1.f ? 1.f : t);
+            const float ex = wx - t * ca.z, ey = wy - t * ca.w;
+            far_all = far_all && (ex * ex + ey * ey > thr);   // false for NaN / inf
+        }
+    }
+    return !far_all;
+}
+
 template <int PASS>
 __global__ void k_bin(BuildView bv, BinBuild bb) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -112,6 +144,8 @@ __global__ void k_bin(BuildView bv, BinBuild bb) {
             for (int e0 = gi.prim_begin; e0 < gi.prim_end; e0 += 32) {
                 int e = e0 + lane;
                 bool ph = e < gi.prim_end && overlaps(bb.prefilter ? bv.prim_cbox_pf[e] : bv.prim_cbox[e], x0, y0, x1, y1);
+                if (ph && !bb.prefilter && (bv.prim_meta[e].type_flags & DVG_PF_TIGHT))
+                    ph = bracket_reaches_tile(bv.prim_cap + (size_t)e * DVG_CAP_F4, x0, y0, x1, y1);
                 unsigned pmask = __ballot_sync(0xffffffffu, ph);
                 if (PASS == 1 && ph) out[count + __popc(pmask & ((1u << lane) - 1))] = e;
                 count += __popc(pmask);

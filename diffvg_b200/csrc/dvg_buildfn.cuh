@@ -314,6 +314,11 @@ DVG_HD_NOINLINE void build_prim(const BuildView &bv, int e) {
     }
     if (first_in_inst) tf |= DVG_PF_FIRST;
     if (e == gi.prim_begin) tf |= DVG_PF_GFIRST;
+    {
+        const int pt0 = tf & DVG_PF_TYPE_MASK;
+        if (has_stroke && !has_fill && (gi.flags & DVG_GF_IDENTITY) && (pt0 == PRIM_CUBIC || pt0 == PRIM_QUAD) && !(tf & DVG_PF_APPROX))
+            tf |= DVG_PF_TIGHT;
+    }
     pm.type_flags = tf;
     bv.prim_p01[e] = p01; bv.prim_p23[e] = p23; bv.prim_rad[e] = rad;
     bv.prim_box[e] = box; bv.prim_thick[e] = thick; bv.prim_meta[e] = pm;

@@ -21,6 +21,8 @@ enum PrimType { PRIM_LINE = 0, PRIM_QUAD = 1, PRIM_CUBIC = 2, PRIM_CIRCLE = 3, P
 #define DVG_PF_APPROX 0x40    // use_distance_approx
 #define DVG_PF_FIRST 0x80     // first primitive of its shape instance
 #define DVG_PF_GFIRST 0x100   // first primitive of its group
+#define DVG_PF_TIGHT 0x200    // stroke-only curved primitive in an untransformed group: tiles are binned against its
+                              // polyline bracket (prim_cap) instead of its bounding box (dvg_build.cu k_bin)
 
 // Polyline bracket of a curved stroke primitive: the curve is cut into DVG_CAP_N pieces; piece i lies
 // within `dev_i` of its chord A_i -> A_i + d_i and every chord point has a curve point within dev_i.
