@@ -72,7 +72,7 @@ def gpu_render(topo, params, width, height, nsx, nsy, seed, background=None, d_r
         n.lib.dvg_scene_destroy(h)
 
 
-def gpu_render_rows(topo, params, width, height, nsx, nsy, seed, row_ranges, d_render_image=None):
+def gpu_render_rows(topo, params, width, height, nsx, nsy, seed, row_ranges, d_render_image=None, use_prefiltering=False):
     """Render the image (and gradient) as independent row shards through the `_rows` entry points,
     the way one-process-per-GPU sharding does, and combine: image rows are disjoint, gradients add."""
     import ctypes
@@ -87,15 +87,15 @@ def gpu_render_rows(topo, params, width, height, nsx, nsy, seed, row_ranges, d_r
         n.check(n.lib.dvg_scene_set_params(h, p.ctypes.data, p.shape[0], 0, stream))
         img = torch.full((height, width, 4), float('nan'), device=dev)
         for (r0, r1) in row_ranges:
-            n.check(n.lib.dvg_render_forward_rows(h, None, img.data_ptr(), width, height, nsx, nsy, int(seed), 0, r0, r1, stream))
+            n.check(n.lib.dvg_render_forward_rows(h, None, img.data_ptr(), width, height, nsx, nsy, int(seed), 1 if use_prefiltering else 0, r0, r1, stream))
         out = {'image': img.cpu().numpy()}
         if d_render_image is not None:
             dimg = torch.from_numpy(np.ascontiguousarray(d_render_image, np.float32)).to(dev)
             total = np.zeros(p.shape[0], np.float64)
             for (r0, r1) in row_ranges:
                 dpar = torch.empty(p.shape[0], device=dev)
-                n.check(n.lib.dvg_render_backward_rows(h, None, dimg.data_ptr(), width, height, nsx, nsy, int(seed), 0,
-                                                       r0, r1, dpar.data_ptr(), None, 0, stream))
+                n.check(n.lib.dvg_render_backward_rows(h, None, dimg.data_ptr(), width, height, nsx, nsy, int(seed),
+                                                       1 if use_prefiltering else 0, r0, r1, dpar.data_ptr(), None, 0, stream))
                 total += dpar.cpu().numpy().astype(np.float64)
             out['d_params'] = total
         torch.cuda.synchronize()

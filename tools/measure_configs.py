@@ -1,0 +1,87 @@
+#!/usr/bin/env python
+"""Device-resident fwd+bwd times of the other BASELINE.json configurations (the bench line is the painterly one):
+
+    python tools/measure_configs.py [--cpu]      # --cpu also times the reference CPU path on a bounded sample
+
+  C1  single circle 256^2, 2x2 spp              (launch-latency floor)
+  C2' 1024 closed cubic blobs 512^2, 4x4 spp    (fill-heavy proxy of tiger.svg)
+  C4' same blobs at 2048^2, 2x2 spp, prefiltered (proxy of flower.svg; no boundary pass)
+  C5  512 scenes x 16 strokes 64^2, 2x2 spp      (one native scene per batch element, sequential)
+Prints one line per config: ms per fwd+bwd (CUDA events, median of 5 after 2 warm-ups)."""
+import ctypes
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, 'tests'), os.path.join(ROOT, 'oracle')):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import scenes  # noqa: E402
+import util  # noqa: E402
+from diffvg_b200 import _native as n  # noqa: E402
+
+
+class Scene:
+    def __init__(self, scene):
+        self.topo, self.params = util.pack(scene)
+        self.h = ctypes.c_void_p()
+        n.check(n.lib.dvg_scene_create(self.topo.ctypes.data, self.topo.shape[0], 0, ctypes.byref(self.h)))
+        self.p = torch.from_numpy(self.params).cuda()
+        self.g = torch.empty_like(self.p)
+
+    def step(self, W, H, nsx, nsy, seed, pf, img, dimg):
+        st = torch.cuda.current_stream().cuda_stream
+        n.check(n.lib.dvg_scene_set_params(self.h, self.p.data_ptr(), self.p.numel(), 1, st))
+        n.check(n.lib.dvg_render_forward(self.h, None, img.data_ptr(), None, W, H, nsx, nsy, seed, pf, None, 0, st))
+        torch.mul(img, 2.0 / img.numel(), out=dimg)
+        n.check(n.lib.dvg_render_backward(self.h, None, dimg.data_ptr(), None, W, H, nsx, nsy, seed, pf, None, 0,
+                                          self.g.data_ptr(), None, None, 0, st))
+
+
+def timed(fn, reps=5, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    out = []
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record(); torch.cuda.synchronize()
+        out.append(a.elapsed_time(b))
+    return float(np.median(out))
+
+
+def main():
+    cpu = '--cpu' in sys.argv
+    import warnings
+    warnings.simplefilter('ignore')
+    rows = []
+    for name, scene, (W, H, nsx, nsy, pf) in (
+            ('C1 single_circle 256^2 2x2', scenes.single_circle(), (256, 256, 2, 2, 0)),
+            ("C2' blobs1024 512^2 4x4", scenes.blobs(), (512, 512, 4, 4, 0)),
+            ("C4' blobs1024 2048^2 2x2 prefilter", scenes.blobs(), (2048, 2048, 2, 2, 1))):
+        s = Scene(scene)
+        img = torch.empty(H, W, 4, device='cuda'); dimg = torch.empty_like(img)
+        ms = timed(lambda: s.step(W, H, nsx, nsy, 0, pf, img, dimg))
+        line = '%-38s %8.3f ms fwd+bwd  %8.1f Msamples/s' % (name, ms, W * H * nsx * nsy * (1 if pf else 2) / ms / 1e3)
+        if cpu:
+            import oracle_check
+            rows_s = min(H, 256)
+            t0 = time.perf_counter()
+            ref = oracle_check.render(s.topo, s.params, W, rows_s, nsx, nsy, 0, use_prefiltering=bool(pf))['image']
+            oracle_check.render(s.topo, s.params, W, rows_s, nsx, nsy, 0, use_prefiltering=bool(pf),
+                                d_render_image=(2.0 * ref / ref.size).astype(np.float32))
+            t = (time.perf_counter() - t0) * (H / rows_s)
+            line += '   reference CPU %.2f s (from a %d-row sample, %d threads) -> %.0fx' % (t, rows_s, os.cpu_count(), t * 1e3 / ms)
+        print(line, flush=True)
+        n.lib.dvg_scene_destroy(s.h)
+    batch = [Scene(scenes.batched_strokes(b)) for b in range(512)]
+    img = torch.empty(64, 64, 4, device='cuda'); dimg = torch.empty_like(img)
+    ms = timed(lambda: [s.step(64, 64, 2, 2, b, 0, img, dimg) for b, s in enumerate(batch)], reps=3, warm=1)
+    print('%-38s %8.3f ms fwd+bwd for 512 scenes (%.3f ms per scene, sequential native scenes)' % ('C5 512x16 strokes 64^2 2x2', ms, ms / 512), flush=True)
+
+
+if __name__ == '__main__':
+    main()
