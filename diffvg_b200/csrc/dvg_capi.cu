@@ -642,7 +642,7 @@ static int render_backward_impl(DvgScene *s, const float *background, const floa
     ra.d_params = d_params; ra.d_background = d_background; ra.d_translation = d_translation;
     ra.debug_out = g_debug_out;
     if (!(flags & DVG_BWD_ACCUMULATE)) CK(cudaMemsetAsync(d_params, 0, sizeof(float) * s->num_params, st));
-    const bool wave_grads = d_render_image && !use_prefiltering && !g_fused;
+    const bool wave_grads = d_render_image && (use_prefiltering || !g_fused);
     if (wave_grads) {   // private copies of the gradient buffer for the wavefront composite kernels (dvg_wave.cu grad_replica)
         ra.grad_reps = 32; ra.num_params = s->num_params;
         CK(s->d_grad_rep.ensure(sizeof(float) * (size_t)ra.grad_reps * s->num_params));
@@ -662,6 +662,8 @@ static int render_backward_impl(DvgScene *s, const float *background, const floa
         if (use_prefiltering) {
             // interior term only: the SDF coverage is differentiable, no boundary pass (diffvg.cpp:1558)
             launch_render_pf_backward(sc, bins, ra, st);
+            CK(cudaGetLastError());
+            launch_wave_reduce_grads(ra, st);
             CK(cudaGetLastError());
         } else {
             if (g_fused) launch_render_backward(sc, bins, ra, st);
@@ -693,7 +695,7 @@ static int render_backward_impl(DvgScene *s, const float *background, const floa
                     if (rc) return rc;
                 }
             }
-            if (wave_grads) {
+            if (wave_grads && !use_prefiltering) {
                 launch_wave_reduce_grads(ra, st);
                 CK(cudaGetLastError());
             }

@@ -9,6 +9,23 @@ DVG_D float warp_sum(float v) {
     return v;
 }
 
+// Gradient scatter straight to global memory (fire-and-forget red.global.add.f32).
+struct GlobalSink {
+    float *D;
+    __device__ __forceinline__ void add(int idx, float v) const {
+        if (v != 0.f) atomicAdd(D + idx, v);
+    }
+};
+
+// Contention: some addresses are hit by EVERY warp of a launch (d_filter.radius; d_shape_to_canvas of a transform
+// tensor shared by all groups, typically the default eye(3)).  Instead of reducing them per block in shared memory
+// behind a barrier (warps of a block finish at very different times: the barrier was 27% of the interior backward
+// kernel), every block adds into one of `grad_reps` private copies of the whole gradient buffer, chosen by block
+// index; k_wave_reduce_grads sums the copies.  32 copies x 155 KB at the painterly config.
+DVG_D float *grad_replica(const RenderArgs &ra) {
+    return ra.d_params_rep + (size_t)(blockIdx.x & (unsigned)(ra.grad_reps - 1)) * (size_t)ra.num_params;
+}
+
 // Splat of one sample's colour (diffvg.cpp:1224-1249).  Must be called by all lanes of the warp.
 // The sample's own pixel is reduced across the `grp` adjacent lanes that hold the samples of that
 // pixel first; the (rare for box 0.5) neighbours go straight to global memory.

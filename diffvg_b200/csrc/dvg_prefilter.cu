@@ -29,14 +29,9 @@ DVG_D PrimRef load_prim(const SceneView &sc, int e) {
 
 template <bool BACKWARD>
 __global__ void __launch_bounds__(PB) k_render_pf(SceneView sc, BinView bins, RenderArgs ra) {
-    GradCache *gcp = nullptr;
-    if constexpr (BACKWARD) {
-        __shared__ GradCache s_gc;
-        gcp = &s_gc;
-        grad_cache_init(s_gc);
-        __syncthreads();
-    }
-    const CacheSink sk{gcp, ra.d_params};
+    // gradients go straight to one of the private copies of the gradient buffer (dvg_kernel_util.cuh grad_replica):
+    // the per-block shared-memory hash + barrier + flush this kernel used before was 40% of its time at 2048^2
+    const GlobalSink sk{BACKWARD ? grad_replica(ra) : nullptr};
     const int tile_row0 = ra.row_begin / bins.tile_h;
     const int spp = ra.nsx * ra.nsy;
     const int ns = bins.tile_w * bins.tile_h * spp;
@@ -97,8 +92,6 @@ __global__ void __launch_bounds__(PB) k_render_pf(SceneView sc, BinView bins, Re
         }
         d_radius_acc = warp_sum(d_radius_acc);
         if ((tid & 31) == 0) sk.add(sc.filter_radius_off, d_radius_acc);
-        __syncthreads();
-        grad_cache_flush(*gcp, ra.d_params);
     }
 }
 

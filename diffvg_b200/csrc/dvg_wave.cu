@@ -55,15 +55,6 @@ DVG_D int warp_reserve(int *counter, int count) {
 // barrier before its flush and, having no native shared-memory float add, spins on CAS: 30% of the boundary
 // composite.  Here lanes that target the same segment are summed with shuffles and the leader issues one
 // fire-and-forget `red.global.add.f32` per address (atomic.h:23-51 does one atomic per component per sample).
-// Contention: some addresses are hit by EVERY warp of a launch (d_filter.radius; d_shape_to_canvas of a transform
-// tensor shared by all groups, typically the default eye(3)).  Instead of reducing them per block in shared memory
-// behind a barrier (warps of a block finish at very different times: the barrier was 27% of the interior backward
-// kernel), every block adds into one of `grad_reps` private copies of the whole gradient buffer, chosen by block
-// index; k_wave_reduce_grads sums the copies.  32 copies x 155 KB at the painterly config.
-DVG_D float *grad_replica(const RenderArgs &ra) {
-    return ra.d_params_rep + (size_t)(blockIdx.x & (unsigned)(ra.grad_reps - 1)) * (size_t)ra.num_params;
-}
-
 __global__ void k_wave_reduce_grads(const float *rep, int reps, int n, float *out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -71,13 +62,6 @@ __global__ void k_wave_reduce_grads(const float *rep, int reps, int n, float *ou
     for (int r = 0; r < reps; r++) s += rep[(size_t)r * n + i];
     if (s != 0.f) out[i] += s;
 }
-
-struct GlobalSink {
-    float *D;
-    __device__ __forceinline__ void add(int idx, float v) const {
-        if (v != 0.f) atomicAdd(D + idx, v);
-    }
-};
 
 DVG_D void warp_scatter_grouped(const GradRec &gr, float *D) {
     const unsigned FULL = 0xffffffffu;
