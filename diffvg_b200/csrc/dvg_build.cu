@@ -124,6 +124,19 @@ __global__ void k_bin(BuildView bv, BinBuild bb) {
     int count = 0;
     int *out = nullptr;
     if (PASS == 1) out = bb.items + bb.offsets[warp];
+    if (bb.flat) {
+        // few primitives per group (painterly strokes: 2 per group): walk the primitives directly, 32 per trip;
+        // their canvas boxes are already clipped to the group's scene-BVH leaf box, so the group test adds nothing
+        for (int e0 = 0; e0 < bv.num_prims; e0 += 32) {
+            const int e = e0 + lane;
+            bool ph = e < bv.num_prims && overlaps(bb.prefilter ? bv.prim_cbox_pf[e] : bv.prim_cbox[e], x0, y0, x1, y1);
+            if (ph && !bb.prefilter && (bv.prim_meta[e].type_flags & DVG_PF_TIGHT))
+                ph = bracket_reaches_tile(bv.prim_cap + (size_t)e * DVG_CAP_F4, x0, y0, x1, y1);
+            const unsigned pmask = __ballot_sync(0xffffffffu, ph);
+            if (PASS == 1 && ph) out[count + __popc(pmask & ((1u << lane) - 1))] = e;
+            count += __popc(pmask);
+        }
+    } else
     for (int g0 = 0; g0 < bv.num_groups; g0 += 32) {
         int g = g0 + lane;
         bool hit = false;

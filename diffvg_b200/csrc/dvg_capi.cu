@@ -275,6 +275,7 @@ int ensure_bins(DvgScene *s, int width, int height, int spp, int pf, cudaStream_
     if (s->bin_w == width && s->bin_h == height && s->bin_tw == tw && s->bin_th == th && s->bin_pf == pf) return DVG_OK;
     BinBuild bb;
     bb.width = width; bb.height = height; bb.tile_w = tw; bb.tile_h = th; bb.prefilter = pf;
+    bb.flat = s->num_prims <= 4 * s->num_groups ? 1 : 0;
     bb.tiles_x = (width + tw - 1) / tw; bb.tiles_y = (height + th - 1) / th;
     const int ntiles = bb.tiles_x * bb.tiles_y;
     CK(s->d_bin_counts.ensure(sizeof(int) * ntiles));
