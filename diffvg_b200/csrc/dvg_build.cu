@@ -106,10 +106,9 @@ DVG_D bool bracket_reaches_tile(const F4 *cap, float x0, float y0, float x1, flo
 
 template <int PASS>
 __global__ void k_bin(BuildView bv, BinBuild bb) {
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    const int ntiles = bb.tiles_x * bb.tiles_y;
-    if (warp >= ntiles) return;
+    const int warp = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) + bb.tile_row0 * bb.tiles_x;   // = tile
+    if (warp >= bb.tile_row1 * bb.tiles_x) return;
     const int tx = warp % bb.tiles_x, ty = warp / bb.tiles_x;
     // tile rectangle in canvas units, with a margin that also covers the +-1e-4 (normalised)
     // offsets of boundary samples (diffvg.cpp:1416,1420) and float rounding of pt/W*canvas_w
@@ -200,14 +199,16 @@ void launch_build(const BuildView &bv, cudaStream_t st) {
 
 void launch_bin_count(const BuildView &bv, const BinBuild &bb, cudaStream_t st) {
     const int ntiles = bb.tiles_x * bb.tiles_y;
+    const int nbin = (bb.tile_row1 - bb.tile_row0) * bb.tiles_x;
     const int B = 128;  // 4 warps = 4 tiles per block
-    DVG_LAUNCH(k_bin<0>, dim3((ntiles * 32 + B - 1) / B), dim3(B), 0, st, bv, bb);
+    if (nbin < ntiles) cudaMemsetAsync(bb.counts, 0, sizeof(int) * ntiles, st);
+    if (nbin > 0) DVG_LAUNCH(k_bin<0>, dim3((nbin * 32 + B - 1) / B), dim3(B), 0, st, bv, bb);
     DVG_LAUNCH(k_exclusive_scan, dim3(1), dim3(1024), 0, st, bb.counts, bb.offsets, ntiles);
 }
 void launch_bin_fill(const BuildView &bv, const BinBuild &bb, cudaStream_t st) {
-    const int ntiles = bb.tiles_x * bb.tiles_y;
+    const int nbin = (bb.tile_row1 - bb.tile_row0) * bb.tiles_x;
     const int B = 128;
-    DVG_LAUNCH(k_bin<1>, dim3((ntiles * 32 + B - 1) / B), dim3(B), 0, st, bv, bb);
+    if (nbin > 0) DVG_LAUNCH(k_bin<1>, dim3((nbin * 32 + B - 1) / B), dim3(B), 0, st, bv, bb);
 }
 void launch_scan(const int *in, int *out, int n, cudaStream_t st) {
     DVG_LAUNCH(k_exclusive_scan, dim3(1), dim3(1024), 0, st, in, out, n);

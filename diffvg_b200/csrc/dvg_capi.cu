@@ -20,7 +20,7 @@ namespace {
 
 thread_local std::string g_err;
 float *g_debug_out = nullptr;  // dvg_debug_set_boundary_dump
-bool g_fast_accept = false;    // dvg_set_fast_stroke_accept
+bool g_fast_accept = getenv("DVG_FAST_ACCEPT") != nullptr && getenv("DVG_FAST_ACCEPT")[0] == '1';   // dvg_set_fast_stroke_accept (env: measurements only)
 // A/B switch for measurements: DVG_FUSED=1 in the environment selects the one-kernel-per-pass form of
 // dvg_render.cu instead of the wavefront passes of dvg_wave.cu (same arithmetic, same results).
 bool g_fused = getenv("DVG_FUSED") != nullptr && getenv("DVG_FUSED")[0] == '1';
@@ -79,6 +79,7 @@ struct DvgScene {
     // bins
     DevBuf d_bin_counts, d_bin_offsets, d_bin_items;
     int bin_w = 0, bin_h = 0, bin_tw = 0, bin_th = 0, bin_pf = 0;  // configuration the bins were built for (0 = none)
+    int bin_r0 = 0, bin_r1 = 0;                                    // tile rows that were binned
     // per-render workspaces
     DevBuf d_weight;
     int w_w = 0, w_h = 0, w_nsx = 0, w_nsy = 0, w_ftype = -1;
@@ -269,13 +270,20 @@ int finish_build(DvgScene *s, cudaStream_t st) {
     return DVG_OK;
 }
 
-int ensure_bins(DvgScene *s, int width, int height, int spp, int pf, cudaStream_t st) {
+// `row_begin, row_end`: pixel rows the caller will render.  The prefiltered path has no boundary pass, so a row shard
+// only ever looks at the tiles of its own rows and only those are binned (at 8 GPUs binning the whole 2048^2 image
+// on every rank was 10% of the step); the boundary pass of the sampled path lands anywhere, so it bins everything.
+int ensure_bins(DvgScene *s, int width, int height, int spp, int pf, cudaStream_t st, int row_begin, int row_end) {
     int tw, th;
     choose_tile(spp, &tw, &th);
-    if (s->bin_w == width && s->bin_h == height && s->bin_tw == tw && s->bin_th == th && s->bin_pf == pf) return DVG_OK;
+    const int tiles_y_all = (height + th - 1) / th;
+    const int r0 = pf ? row_begin / th : 0, r1 = pf ? std::min(tiles_y_all, (row_end + th - 1) / th) : tiles_y_all;
+    if (s->bin_w == width && s->bin_h == height && s->bin_tw == tw && s->bin_th == th && s->bin_pf == pf &&
+        s->bin_r0 <= r0 && s->bin_r1 >= r1) return DVG_OK;
     BinBuild bb;
     bb.width = width; bb.height = height; bb.tile_w = tw; bb.tile_h = th; bb.prefilter = pf;
     bb.flat = s->num_prims <= 4 * s->num_groups ? 1 : 0;
+    bb.tile_row0 = r0; bb.tile_row1 = r1;
     bb.tiles_x = (width + tw - 1) / tw; bb.tiles_y = (height + th - 1) / th;
     const int ntiles = bb.tiles_x * bb.tiles_y;
     CK(s->d_bin_counts.ensure(sizeof(int) * ntiles));
@@ -299,7 +307,7 @@ int ensure_bins(DvgScene *s, int width, int height, int spp, int pf, cudaStream_
     bb.items = s->d_bin_items.as<int>();
     launch_bin_fill(bv, bb, st);
     CK(cudaGetLastError());
-    s->bin_w = width; s->bin_h = height; s->bin_tw = tw; s->bin_th = th; s->bin_pf = pf;
+    s->bin_w = width; s->bin_h = height; s->bin_tw = tw; s->bin_th = th; s->bin_pf = pf; s->bin_r0 = r0; s->bin_r1 = r1;
     return DVG_OK;
 }
 
@@ -576,7 +584,7 @@ static int render_forward_impl(DvgScene *s, const float *background, float *rend
     ra.background = background; ra.render_image = render_image;
     if (g_fast_accept) ra.flags |= DVG_RF_FAST_ACCEPT;
     if (render_image) {
-        rc = ensure_bins(s, width, height, nsx * nsy, use_prefiltering ? 1 : 0, st);
+        rc = ensure_bins(s, width, height, nsx * nsy, use_prefiltering ? 1 : 0, st, row_begin, row_end);
         if (rc) return rc;
         if (row_begin % s->bin_th != 0) return fail(DVG_ERR_INVALID, "row_begin must be a multiple of the tile height");
         rc = ensure_weight(s, sc, ra, st);
@@ -654,7 +662,7 @@ static int render_backward_impl(DvgScene *s, const float *background, const floa
         CK(cudaMemsetAsync(d_background + 4 * (size_t)row_begin * width, 0, sizeof(float) * 4 * (size_t)width * (row_end - row_begin), st));
     if (d_translation) CK(cudaMemsetAsync(d_translation, 0, sizeof(float) * 2 * (size_t)width * height, st));
     if (d_render_image) {
-        rc = ensure_bins(s, width, height, nsx * nsy, use_prefiltering ? 1 : 0, st);
+        rc = ensure_bins(s, width, height, nsx * nsy, use_prefiltering ? 1 : 0, st, row_begin, row_end);
         if (rc) return rc;
         if (row_begin % s->bin_th != 0) return fail(DVG_ERR_INVALID, "row_begin must be a multiple of the tile height");
         BinView bins = s->bin_view();

@@ -32,6 +32,7 @@ void prof_end(cudaStream_t st);
 struct BinBuild {
     int width, height, tile_w, tile_h, tiles_x, tiles_y;
     int prefilter;  // 1: bin with prim_cbox_pf (SDF-prefiltering candidate regions)
+    int tile_row0, tile_row1;  // tile rows to bin (the others get empty lists)
     int flat;       // 1: test every primitive (few primitives per group); 0: groups first, then their primitives
     int *counts;   // [tiles]
     int *offsets;  // [tiles+1]

@@ -144,6 +144,8 @@ class RenderFunction(torch.autograd.Function):
         # d_shape_to_canvas is only worth accumulating when some transform tensor takes part in autograd (every
         # boundary sample adds to the 9 entries of its group's transform; groups usually share one constant eye(3))
         packed.needs_xform_grad = any(t.requires_grad for t in tensors[scene_pack.B_MAT3])
+        # rows of d_image a pixel-row shard needs from its neighbours (diffvg_b200/sharded.py)
+        packed.halo_rows = max(1, int(np.ceil(float(filter.radius))))
         return [packed, params]
 
     @staticmethod

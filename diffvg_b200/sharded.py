@@ -87,10 +87,17 @@ def allreduce_gradients(d_params, group=None):
 class ShardedRenderFunction(torch.autograd.Function):
     """`RenderFunction.apply` for one large render split by pixel rows over the ranks of `group`.
     Every rank calls it with the same scene / seed and gets the full image; gradients w.r.t. the packed
-    parameters are complete (summed over ranks) on every rank.  Colour output only."""
+    parameters are complete (summed over ranks) on every rank.  Colour output only.
+
+    `gather=False` returns only the rank's own band `[rows, W, 4]` (rows = `row_partition(...)[rank]`) for a loss
+    that is itself computed per band: no image exchange in the forward pass.  The backward pass then needs the
+    other ranks' d_image rows only for the boundary samples of the sampled path (they land anywhere in the image):
+    with `use_prefiltering` nothing is exchanged but the gradient all-reduce; otherwise the d_image bands are
+    all-gathered."""
 
     @staticmethod
-    def forward(ctx, width, height, num_samples_x, num_samples_y, seed, background_image, packed, params, group=None):
+    def forward(ctx, width, height, num_samples_x, num_samples_y, seed, background_image, packed, params, group=None,
+                gather=True):
         from .pydiffvg import render_pytorch as rp
         n = rp._native()
         dev = rp._cuda_device()
@@ -112,10 +119,14 @@ class ShardedRenderFunction(torch.autograd.Function):
                 ns.handle, background_image.data_ptr() if background_image is not None else None, full.data_ptr(),
                 width, height, num_samples_x, num_samples_y, int(seed), 1 if packed.use_prefiltering else 0,
                 rb, re, stream))
-            img = allgather_rows(full[rb:re], bands, group) if world > 1 else full
+            if not gather:
+                img = full[rb:re]
+            else:
+                img = allgather_rows(full[rb:re], bands, group) if world > 1 else full
         ctx.native_scene, ctx.scene_version, ctx.packed = ns, version, packed
         ctx.background_image = background_image
         ctx.geom = (width, height, num_samples_x, num_samples_y, seed, rb, re)
+        ctx.gather, ctx.bands, ctx.world = gather, bands, world
         ctx.device, ctx.params_device, ctx.group = dev, params.device, group
         ctx.save_for_backward(params)
         return img
@@ -130,6 +141,26 @@ class ShardedRenderFunction(torch.autograd.Function):
         bg = ctx.background_image
         grad_img = grad_img.to(dev).float().contiguous()
         with torch.cuda.device(dev):
+            if not ctx.gather:   # band-shaped gradient -> full-size d_image
+                hl = int(getattr(ctx.packed, 'halo_rows', 1))
+                if ctx.world == 1:
+                    pass
+                elif ctx.packed.use_prefiltering and min(e - b for b, e in ctx.bands) >= hl:
+                    # own rows + a halo of ceil(filter radius) rows from the two neighbours: d_filter.radius reads
+                    # d_image over the whole (2*ceil(r)+1)^2 footprint of a sample (diffvg.cpp:1250-1268)
+                    rank = dist.get_rank(ctx.group)
+                    edge = torch.cat([grad_img[:hl], grad_img[-hl:]], dim=0).contiguous()
+                    buf = torch.empty((ctx.world,) + tuple(edge.shape), dtype=edge.dtype, device=edge.device)
+                    dist.all_gather_into_tensor(buf, edge, group=ctx.group)
+                    full = torch.zeros(height, width, 4, device=dev, dtype=torch.float32)
+                    full[rb:re] = grad_img
+                    if rank > 0:
+                        full[rb - hl:rb] = buf[rank - 1, hl:]
+                    if rank < ctx.world - 1:
+                        full[re:re + hl] = buf[rank + 1, :hl]
+                    grad_img = full
+                else:
+                    grad_img = allgather_rows(grad_img, ctx.bands, ctx.group)
             stream = torch.cuda.current_stream().cuda_stream
             if ns.version != ctx.scene_version:
                 ctx.scene_version = ns.set_params(params, stream)
@@ -145,7 +176,7 @@ class ShardedRenderFunction(torch.autograd.Function):
                 allreduce_gradients(d_bg, ctx.group)
         if d_params.device != ctx.params_device:
             d_params = d_params.to(ctx.params_device)
-        return None, None, None, None, None, d_bg, None, d_params, None
+        return None, None, None, None, None, d_bg, None, d_params, None, None
 
 
 def tile_height(spp):
