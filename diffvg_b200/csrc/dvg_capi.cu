@@ -82,7 +82,7 @@ struct DvgScene {
     int bin_r0 = 0, bin_r1 = 0;                                    // tile rows that were binned
     // per-render workspaces
     DevBuf d_weight;
-    int w_w = 0, w_h = 0, w_nsx = 0, w_nsy = 0, w_ftype = -1;
+    int w_w = 0, w_h = 0, w_nsx = 0, w_nsy = 0, w_ftype = -1, w_r0 = 0, w_r1 = 0;
     uint64_t w_seed = 0; float w_radius = 0; bool w_valid = false;
     DevBuf d_keys, d_tile_counts, d_tile_offsets, d_tile_fill, d_blk_counts, d_blk_offsets, d_sorted;
     // wavefront passes (dvg_wave.cu)
@@ -311,16 +311,19 @@ int ensure_bins(DvgScene *s, int width, int height, int spp, int pf, cudaStream_
     return DVG_OK;
 }
 
-int ensure_weight(DvgScene *s, const SceneView &sc, RenderArgs &ra, cudaStream_t st) {
+// rows [r0, r1): the pixel rows whose weights the caller reads.  A forward row shard and the prefiltered backward pass
+// read their own rows; the boundary pass of the sampled backward path gathers d_image anywhere: whole image.
+int ensure_weight(DvgScene *s, const SceneView &sc, RenderArgs &ra, int r0, int r1, cudaStream_t st) {
     CK(s->d_weight.ensure(sizeof(float) * (size_t)ra.width * ra.height));
     ra.weight_image = s->d_weight.as<float>();
     if (s->w_valid && s->w_w == ra.width && s->w_h == ra.height && s->w_nsx == ra.nsx && s->w_nsy == ra.nsy &&
-        s->w_seed == ra.seed && s->w_ftype == sc.filter.type && s->w_radius == sc.filter.radius)
-        return DVG_OK;  // weights depend only on (size, spp, seed, filter): reuse forward's in backward
+        s->w_seed == ra.seed && s->w_ftype == sc.filter.type && s->w_radius == sc.filter.radius &&
+        s->w_r0 <= r0 && s->w_r1 >= r1)
+        return DVG_OK;  // weights depend only on (size, spp, seed, filter, rows): reuse forward's in backward
     CK(cudaMemsetAsync(ra.weight_image, 0, sizeof(float) * (size_t)ra.width * ra.height, st));
-    launch_weight(sc, ra, st);
+    launch_weight(sc, ra, r0, r1, st);
     s->w_valid = true; s->w_w = ra.width; s->w_h = ra.height; s->w_nsx = ra.nsx; s->w_nsy = ra.nsy;
-    s->w_seed = ra.seed; s->w_ftype = sc.filter.type; s->w_radius = sc.filter.radius;
+    s->w_seed = ra.seed; s->w_ftype = sc.filter.type; s->w_radius = sc.filter.radius; s->w_r0 = r0; s->w_r1 = r1;
     return DVG_OK;
 }
 
@@ -587,7 +590,7 @@ static int render_forward_impl(DvgScene *s, const float *background, float *rend
         rc = ensure_bins(s, width, height, nsx * nsy, use_prefiltering ? 1 : 0, st, row_begin, row_end);
         if (rc) return rc;
         if (row_begin % s->bin_th != 0) return fail(DVG_ERR_INVALID, "row_begin must be a multiple of the tile height");
-        rc = ensure_weight(s, sc, ra, st);
+        rc = ensure_weight(s, sc, ra, row_begin, row_end, st);
         if (rc) return rc;
         CK(cudaMemsetAsync(render_image + 4 * (size_t)row_begin * width, 0, sizeof(float) * 4 * (size_t)width * (row_end - row_begin), st));
         if (use_prefiltering) launch_render_pf_forward(sc, s->bin_view(), ra, st);
@@ -666,7 +669,7 @@ static int render_backward_impl(DvgScene *s, const float *background, const floa
         if (rc) return rc;
         if (row_begin % s->bin_th != 0) return fail(DVG_ERR_INVALID, "row_begin must be a multiple of the tile height");
         BinView bins = s->bin_view();
-        rc = ensure_weight(s, sc, ra, st);
+        rc = use_prefiltering ? ensure_weight(s, sc, ra, row_begin, row_end, st) : ensure_weight(s, sc, ra, 0, height, st);
         if (rc) return rc;
         if (use_prefiltering) {
             // interior term only: the SDF coverage is differentiable, no boundary pass (diffvg.cpp:1558)

@@ -85,7 +85,7 @@ void launch_bin_count(const BuildView &bv, const BinBuild &bb, cudaStream_t st);
 void launch_bin_fill(const BuildView &bv, const BinBuild &bb, cudaStream_t st);
 void launch_scan(const int *in, int *out, int n, cudaStream_t st);
 
-void launch_weight(const SceneView &sc, const RenderArgs &ra, cudaStream_t st);
+void launch_weight(const SceneView &sc, const RenderArgs &ra, int row_begin, int row_end, cudaStream_t st);
 void launch_render_forward(const SceneView &sc, const BinView &bins, const RenderArgs &ra, cudaStream_t st);
 void launch_render_backward(const SceneView &sc, const BinView &bins, const RenderArgs &ra, cudaStream_t st);
 void launch_render_pf_forward(const SceneView &sc, const BinView &bins, const RenderArgs &ra, cudaStream_t st);

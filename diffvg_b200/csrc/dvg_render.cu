@@ -40,10 +40,9 @@ struct WarpScratch {
 // ------------------------------------------------------------------------------------------
 // weight_kernel (diffvg.cpp:1115-1158).  Q1: always uses the jittered position, even when
 // the render kernel uses pixel centres for prefiltering.
-__global__ void k_weight(SceneView sc, RenderArgs ra) {
-    const int n = ra.width * ra.height * ra.nsx * ra.nsy;
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= n) return;
+__global__ void k_weight(SceneView sc, RenderArgs ra, int idx_begin, int idx_end) {
+    const int idx = idx_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= idx_end) return;
     Pcg32 rng = pcg32_init(idx, ra.seed);
     const int sx = idx % ra.nsx;
     const int sy = (idx / ra.nsx) % ra.nsy;
@@ -493,9 +492,16 @@ __global__ void __launch_bounds__(RB, DVG_MINB) k_edge(SceneView sc, BinView bin
 // ------------------------------------------------------------------------------------------
 int edge_samples_per_block() { return EDGE_SPB; }
 
-void launch_weight(const SceneView &sc, const RenderArgs &ra, cudaStream_t st) {
-    const int n = ra.width * ra.height * ra.nsx * ra.nsy;
-    DVG_LAUNCH(k_weight, dim3((n + 255) / 256), dim3(256), 0, st, sc, ra);
+// Weights of the pixels of rows [row_begin, row_end): the samples of those rows and of ceil(radius) rows either side
+// splat onto them (a row shard does not need the rest of the image).
+void launch_weight(const SceneView &sc, const RenderArgs &ra, int row_begin, int row_end, cudaStream_t st) {
+    // pixels up to ri rows outside the band are read (gather_d_color, splat); their weights need samples ri rows further
+    const int ri = 2 * (int)ceilf(sc.filter.radius);
+    const int y0 = max(0, row_begin - ri), y1 = min(ra.height, row_end + ri);
+    const int per_row = ra.width * ra.nsx * ra.nsy;
+    const int n = (y1 - y0) * per_row;
+    if (n <= 0) return;
+    DVG_LAUNCH(k_weight, dim3((n + 255) / 256), dim3(256), 0, st, sc, ra, y0 * per_row, y1 * per_row);
 }
 
 static int parts_per_tile(const BinView &bins, const RenderArgs &ra) {
