@@ -344,6 +344,13 @@ def main():
                             'peak_gbs': peaks.get('hbm_gbs', 6650.0),
                             'peak_source': 'measured' if 'hbm_gbs' in peaks else 'fallback'},
                     'traffic': None}
+        try:   # DRAM bytes of this kernel's longest launch, from the committed ncu --set full capture
+            tr = json.load(open(os.path.join(ROOT, 'profiles', 'r1_ncu_traffic.json')))['kernels'].get(top)
+            if tr:
+                roofline['traffic'] = tr['dram_bytes']
+                roofline['traffic_note'] = 'dram__bytes_read+write of the longest launch of %s (%.3f ms) in profiles/r1_ncu_traffic.json' % (top, tr['ms'])
+        except Exception:
+            pass
 
     # ---- CPU baseline (rank 0, N = 1): the reference's CPU path on a bounded sample
     cpu_baseline = None
