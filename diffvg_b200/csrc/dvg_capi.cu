@@ -270,6 +270,9 @@ int finish_build(DvgScene *s, cudaStream_t st) {
     return DVG_OK;
 }
 
+constexpr int64_t kSmallBins = 1 << 20;    // tiles x primitives below which bins are sized for the worst case
+constexpr int64_t kSmallPairs = 1 << 21;   // worst-case exact tests of a pass below which the pair queues are, too
+
 // `row_begin, row_end`: pixel rows the caller will render.  The prefiltered path has no boundary pass, so a row shard
 // only ever looks at the tiles of its own rows and only those are binned (at 8 GPUs binning the whole 2048^2 image
 // on every rank was 10% of the step); the boundary pass of the sampled path lands anywhere, so it bins everything.
@@ -295,13 +298,23 @@ int ensure_bins(DvgScene *s, int width, int height, int spp, int pf, cudaStream_
     CK(s->d_tile_choff.ensure(sizeof(int) * (ntiles + 1)));
     CK(s->d_wave_max.ensure(sizeof(int)));
     launch_wave_tile_chunks(bb.offsets, s->d_tile_nch.as<int>(), s->d_tile_choff.as<int>(), s->d_wave_max.as<int>(), ntiles, st);
-    CK(cudaMemcpyAsync(s->h_pinned + 3, bb.offsets + ntiles, 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(s->h_pinned + 4, s->d_tile_choff.as<int>() + ntiles, 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(s->h_pinned + 5, s->d_wave_max.p, 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    const int total = s->h_pinned[3];
-    s->total_chunks = s->h_pinned[4];
-    s->max_nch = s->h_pinned[5];
+    int total;
+    const int64_t nbin = (int64_t)(r1 - r0) * bb.tiles_x;
+    if (nbin * s->num_prims <= kSmallBins) {
+        // small scene (batched 64x64 scenes, single shapes): size everything for the worst case -- every primitive in
+        // every tile -- and skip the read-back, so that the whole iteration stays asynchronous
+        total = (int)(nbin * s->num_prims);
+        s->max_nch = (s->num_prims + 31) / 32;
+        s->total_chunks = (int)nbin * s->max_nch;
+    } else {
+        CK(cudaMemcpyAsync(s->h_pinned + 3, bb.offsets + ntiles, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(s->h_pinned + 4, s->d_tile_choff.as<int>() + ntiles, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(s->h_pinned + 5, s->d_wave_max.p, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        total = s->h_pinned[3];
+        s->total_chunks = s->h_pinned[4];
+        s->max_nch = s->h_pinned[5];
+    }
     s->wpx_valid = false;
     CK(s->d_bin_items.ensure(sizeof(int) * std::max(total, 1)));
     bb.items = s->d_bin_items.as<int>();
@@ -354,7 +367,29 @@ int wave_view(DvgScene *s, int64_t chunk_slots, int64_t evals, WaveView *out) {
 // Runs `classify` (W1), reads the two pair counts back (the one synchronisation of a pass), grows a queue and
 // repeats W1 if it overflowed, then launches the exact tests (W2).
 template <typename Classify>
-int wave_classify_and_solve(DvgScene *s, const SceneView &sc, WaveView &wv, cudaStream_t st, const Classify &classify) {
+int wave_classify_and_solve(DvgScene *s, const SceneView &sc, WaveView &wv, int64_t chunk_slots, cudaStream_t st,
+                            const Classify &classify) {
+    // worst case: every lane of every chunk slot asks for an exact test of all 32 candidates
+    const int64_t worst = chunk_slots * 32 * 32;
+    if (worst <= kSmallPairs) {
+        // small pass: queues sized for the worst case can not overflow, so nothing is read back; the solve kernels
+        // cover the capacity and take the actual counts from device memory
+        const int cap = (int)std::max<int64_t>(worst, 1);
+        CK(s->d_wave_pairs_s.ensure(sizeof(WavePair) * (size_t)cap));
+        if (s->has_fills) CK(s->d_wave_pairs_f.ensure(sizeof(WavePair) * (size_t)cap));
+        wv.pairs_s = s->d_wave_pairs_s.as<WavePair>(); wv.cap_s = cap;
+        wv.pairs_f = s->d_wave_pairs_f.as<WavePair>(); wv.cap_f = s->has_fills ? cap : 0;
+        wv.cap_ua = cap + cap / 2 + 1024; wv.cap_ud = cap - cap / 4 + 1024;
+        CK(s->d_wave_units_a.ensure(sizeof(WaveUnit) * (size_t)wv.cap_ua));
+        CK(s->d_wave_units_d.ensure(sizeof(WaveUnit) * (size_t)wv.cap_ud));
+        wv.units_a = s->d_wave_units_a.as<WaveUnit>(); wv.units_d = s->d_wave_units_d.as<WaveUnit>();
+        CK(cudaMemsetAsync(wv.counters, 0, sizeof(int) * 2, st));
+        classify(wv);
+        CK(cudaGetLastError());
+        launch_wave_solve(sc, wv, -1, s->has_fills ? -1 : 0, st);
+        CK(cudaGetLastError());
+        return DVG_OK;
+    }
     for (int attempt = 0; attempt < 3; attempt++) {
         CK(cudaMemsetAsync(wv.counters, 0, sizeof(int) * 2, st));
         classify(wv);
@@ -401,7 +436,8 @@ int wave_pixel_pass(DvgScene *s, const SceneView &sc, const BinView &bins, const
                        s->wpx_pf == ra.use_prefiltering && s->wpx_fast == fast;
     if (!reuse) {
         s->wpx_valid = false;
-        rc = wave_classify_and_solve(s, sc, wv, st, [&](const WaveView &v) { launch_wave_classify_px(sc, bins, ra, v, st); });
+        rc = wave_classify_and_solve(s, sc, wv, (int64_t)s->total_chunks * wpt, st,
+                                     [&](const WaveView &v) { launch_wave_classify_px(sc, bins, ra, v, st); });
         if (rc) return rc;
         s->wpx_valid = true; s->wpx_w = ra.width; s->wpx_h = ra.height; s->wpx_nsx = ra.nsx; s->wpx_nsy = ra.nsy;
         s->wpx_seed = ra.seed; s->wpx_r0 = ra.row_begin; s->wpx_r1 = ra.row_end; s->wpx_pf = ra.use_prefiltering; s->wpx_fast = fast;
@@ -429,7 +465,8 @@ int wave_edge_pass(DvgScene *s, const SceneView &sc, const BinView &bins, const 
     s->wpx_valid = false;   // the result words are about to be overwritten
     launch_wave_boundary_sort(sc, bins, ra, bw, wv, s->d_edge_chunks.as<int>(), st);
     CK(cudaGetLastError());
-    rc = wave_classify_and_solve(s, sc, wv, st, [&](const WaveView &v) { launch_wave_classify_edge(sc, bins, ra, bw, v, st); });
+    rc = wave_classify_and_solve(s, sc, wv, (int64_t)bw.max_blocks * std::max(s->max_nch, 1), st,
+                                 [&](const WaveView &v) { launch_wave_classify_edge(sc, bins, ra, bw, v, st); });
     if (rc) return rc;
     launch_wave_composite_edge(sc, bins, ra, bw, wv, st);
     CK(cudaGetLastError());

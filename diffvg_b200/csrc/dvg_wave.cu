@@ -290,7 +290,9 @@ __global__ void __launch_bounds__(WB, DVG_WB_MIN) k_wave_classify_edge(SceneView
 // Per-bracket arithmetic is dvg_geom.cuh's, evaluated on the same inputs: results are unchanged.
 constexpr int W2A_B = 256;
 
+// `count` < 0: take the number of pairs from the device counter (queues sized for the worst case, no read-back).
 __global__ void __launch_bounds__(W2A_B) k_wave_stroke_setup(SceneView sc, WaveView wv, int count) {
+    if (count < 0) count = min(wv.counters[0], wv.cap_s);
     __shared__ int s_wsum[2][W2A_B / 32];
     __shared__ int s_base[2];
     const int i = blockIdx.x * W2A_B + threadIdx.x;
@@ -418,6 +420,7 @@ __global__ void __launch_bounds__(256) k_wave_stroke_newton(SceneView sc, WaveVi
 }
 
 __global__ void __launch_bounds__(128) k_wave_solve_fill(SceneView sc, WaveView wv, int count) {
+    if (count < 0) count = min(wv.counters[1], wv.cap_f);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
     const WavePair p = wv.pairs_f[i];
@@ -711,14 +714,19 @@ void launch_wave_classify_px(const SceneView &sc, const BinView &bins, const Ren
 }
 
 void launch_wave_solve(const SceneView &sc, const WaveView &wv, int n_stroke, int n_fill, cudaStream_t st) {
-    if (n_stroke > 0) {
+    // n < 0: the count stays on the device, the grid covers the queue capacity
+    if (n_stroke != 0) {
+        const int cover = n_stroke < 0 ? wv.cap_s : n_stroke;
         cudaMemsetAsync(wv.counters + 2, 0, sizeof(int) * 2, st);
-        DVG_LAUNCH(k_wave_stroke_setup, dim3((n_stroke + W2A_B - 1) / W2A_B), dim3(W2A_B), 0, st, sc, wv, n_stroke);
+        DVG_LAUNCH(k_wave_stroke_setup, dim3((cover + W2A_B - 1) / W2A_B), dim3(W2A_B), 0, st, sc, wv, n_stroke);
         // the unit counts stay on the device: grids cover the queue capacities, surplus threads exit at once
         DVG_LAUNCH(k_wave_stroke_newton, dim3((wv.cap_ua + 255) / 256), dim3(256), 0, st, sc, wv, 0);
         DVG_LAUNCH(k_wave_stroke_newton, dim3((wv.cap_ud + 255) / 256), dim3(256), 0, st, sc, wv, 1);
     }
-    if (n_fill > 0) DVG_LAUNCH(k_wave_solve_fill, dim3((n_fill + 127) / 128), dim3(128), 0, st, sc, wv, n_fill);
+    if (n_fill != 0) {
+        const int cover = n_fill < 0 ? wv.cap_f : n_fill;
+        DVG_LAUNCH(k_wave_solve_fill, dim3((cover + 127) / 128), dim3(128), 0, st, sc, wv, n_fill);
+    }
 }
 
 void launch_wave_composite_px(const SceneView &sc, const BinView &bins, const RenderArgs &ra, const WaveView &wv, bool backward,
