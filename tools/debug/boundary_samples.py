@@ -2,7 +2,7 @@
 import sys, os, warnings, ctypes
 import numpy as np, torch
 warnings.simplefilter('ignore')
-R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+R = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path[:0] = [R, os.path.join(R, 'oracle'), os.path.join(R, 'tests')]
 import scenes, util, emul
 from diffvg_b200 import _native as n

@@ -2,8 +2,8 @@
 import sys, time, os, warnings
 import numpy as np, torch
 warnings.simplefilter('ignore')
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'oracle'))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), 'oracle'))
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import scenes, util, ref_oracle
 
