@@ -353,11 +353,11 @@ DVG_D void accumulate_boundary_gradient(const SceneView &sc, const RenderArgs &r
     }
 }
 
-// The same scatter as accumulate_boundary_gradient, as a fixed-slot record: every lane that targets the same
-// (segment, fill / stroke side) produces the same `addr[]`, so a warp can sum the values of such lanes with
-// shuffles and issue ONE atomic per address (dvg_wave.cu warp_scatter_grouped).  Slots: 0-7 point
-// coordinates (circle: centre.x, centre.y, radius; ellipse: centre.xy, radius.xy; rect: the one edge
-// coordinate), 8 stroke width, 9-12 per-point thickness.  addr < 0 = unused.  key < 0 = nothing to add.
+// The same scatter as accumulate_boundary_gradient, as a fixed-slot record that the kernel fills inside its divergent
+// "this lane scatters" branch and adds to the gradient buffer after the warp has re-converged (dvg_wave.cu
+// scatter_record).  Slots: 0-7 point coordinates (circle: centre.x, centre.y, radius; ellipse: centre.xy, radius.xy;
+// rect: the one edge coordinate), 8 stroke width, 9-12 per-point thickness.  addr < 0 = unused.  key < 0 = nothing to
+// add; lanes with equal keys have equal addr[].
 #define DVG_GREC_N 13
 struct GradRec {
     int key;

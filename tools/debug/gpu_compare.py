@@ -4,7 +4,7 @@ import numpy as np, torch
 warnings.simplefilter('ignore')
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), 'oracle'))
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), 'tests'))
 import scenes, util, ref_oracle
 
 def fwd(name, scene, W, H, nsx, nsy, seed, ftype=0, frad=0.5, bg=None):
