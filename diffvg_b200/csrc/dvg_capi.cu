@@ -543,6 +543,7 @@ int dvg_scene_create(const int32_t *topo, int64_t topo_len, int device, DvgScene
     }
     s->inst_prim_begin.push_back((int)s->prim_inst.size());
     s->num_prims = (int)s->prim_inst.size();
+    if (s->prim_inst.size() >= ((size_t)1 << 28)) { delete s; return fail(DVG_ERR_UNSUPPORTED, "more than 2^28 primitives (the pair queue packs the primitive id in 28 bits)"); }
     rc = upload(s->d_topo, s->topo);
     if (!rc) rc = upload(s->d_inst_group, s->inst_group);
     if (!rc) rc = upload(s->d_inst_shape, s->inst_shape);

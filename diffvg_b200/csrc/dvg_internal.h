@@ -55,7 +55,7 @@ struct BoundaryWork {
 };
 
 // Wavefront passes (dvg_wave.cu): queues and result words in global memory.
-struct WavePair { float x, y; int prim; unsigned ref; };   // shape-local sample position, primitive, word << 5 | candidate
+struct WavePair { float x, y; int prim; unsigned ref; };   // shape-local sample position, PrimType << 28 | primitive, word << 5 | candidate
 struct WaveUnit { float lb, ub; int pair; int pad; };     // one root bracket of a cubic pair's closest-point quintic
 struct WaveView {
     WaveUnit *units_a, *units_d;   // ascending brackets (safeguarded Newton) / descending (the reference bisects)

@@ -153,7 +153,7 @@ DVG_D void wave_classify(const SceneView &sc, const BinView &bins, const WaveVie
                     const int pos = warp_reserve(&wv.counters[kind], cnt) + __popc(m & lt);
                     if (keep && pos < cap) {
                         WavePair p;
-                        p.x = lp.x; p.y = lp.y; p.prim = ek;
+                        p.x = lp.x; p.y = lp.y; p.prim = ek | ((tfk & DVG_PF_TYPE_MASK) << 28);   // type rides along: W2 needs no meta load
                         p.ref = ((unsigned)(word0 + owner) << 5) | (unsigned)k;
                         out[pos] = p;
                     }
@@ -276,10 +276,8 @@ constexpr int W2A_B = 256;
 // `count` < 0: take the number of pairs from the device counter (queues sized for the worst case, no read-back).
 __global__ void __launch_bounds__(W2A_B) k_wave_stroke_setup(SceneView sc, WaveView wv, int count) {
     if (count < 0) count = min(wv.counters[0], wv.cap_s);
-    __shared__ int s_wsum[2][W2A_B / 32];
-    __shared__ int s_base[2];
     const int i = blockIdx.x * W2A_B + threadIdx.x;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
     float lbs[5], ubs[5];
     unsigned valid = 0u, desc = 0u;   // bit j: bracket j holds a root / is descending
     bool hit = false;
@@ -287,11 +285,12 @@ __global__ void __launch_bounds__(W2A_B) k_wave_stroke_setup(SceneView sc, WaveV
     F4 p01 = mk4(0, 0, 0, 0), p23 = p01, rad = p01;
     if (i < count) {
         p = wv.pairs_s[i];
-        const PrimMeta pm = sc.prim_meta[p.prim];
-        const int ptype = pm.type_flags & DVG_PF_TYPE_MASK;
+        const int ptype = (int)((unsigned)p.prim >> 28);
+        p.prim &= 0x0fffffff;
         p01 = sc.prim_p01[p.prim]; p23 = sc.prim_p23[p.prim]; rad = sc.prim_rad[p.prim];
         const F2 pt = mk2(p.x, p.y);
         if (ptype != PRIM_CUBIC) {
+            const PrimMeta pm = sc.prim_meta[p.prim];
             bool decided = false;
             hit = prim_stroke_hit_nocubic(ptype, (pm.type_flags & DVG_PF_APPROX) != 0, p01, p23, rad, sc.insts[pm.inst].r, pt, &decided);
         } else {
@@ -326,7 +325,7 @@ __global__ void __launch_bounds__(W2A_B) k_wave_stroke_setup(SceneView sc, WaveV
         }
     }
     if (hit) atomicOr(&wv.hit[p.ref >> 5], 1u << (p.ref & 31u));
-    // block-level append: one atomic per queue per block
+    // warp-aggregated append: one atomic per queue per warp
     const int na = __popc(valid & ~desc), nd = __popc(valid & desc);
     int sa = na, sd = nd;
 #pragma unroll
@@ -334,16 +333,13 @@ __global__ void __launch_bounds__(W2A_B) k_wave_stroke_setup(SceneView sc, WaveV
         const int ta = __shfl_up_sync(0xffffffffu, sa, o), td = __shfl_up_sync(0xffffffffu, sd, o);
         if (lane >= o) { sa += ta; sd += td; }
     }
-    if (lane == 31) { s_wsum[0][warp] = sa; s_wsum[1][warp] = sd; }
-    __syncthreads();
-    if (threadIdx.x < 2) {
-        int tot = 0;
-        for (int w = 0; w < W2A_B / 32; w++) { const int v = s_wsum[threadIdx.x][w]; s_wsum[threadIdx.x][w] = tot; tot += v; }
-        s_base[threadIdx.x] = tot ? atomicAdd(&wv.counters[2 + threadIdx.x], tot) : 0;
+    int base_a = 0, base_d = 0;
+    if (lane == 31) {
+        if (sa) base_a = atomicAdd(&wv.counters[2], sa);
+        if (sd) base_d = atomicAdd(&wv.counters[3], sd);
     }
-    __syncthreads();
-    int pa = s_base[0] + s_wsum[0][warp] + sa - na;
-    int pd = s_base[1] + s_wsum[1][warp] + sd - nd;
+    int pa = __shfl_sync(0xffffffffu, base_a, 31) + sa - na;
+    int pd = __shfl_sync(0xffffffffu, base_d, 31) + sd - nd;
 #pragma unroll
     for (int j = 0; j < 5; j++) {
         if (!((valid >> j) & 1u)) continue;
@@ -380,7 +376,8 @@ __global__ void __launch_bounds__(256) k_wave_stroke_newton(SceneView sc, WaveVi
     const int count = min(wv.counters[2 + which], which ? wv.cap_ud : wv.cap_ua);
     if (u >= count) return;
     const WaveUnit un = (which ? wv.units_d : wv.units_a)[u];
-    const WavePair p = wv.pairs_s[un.pair];
+    WavePair p = wv.pairs_s[un.pair];
+    p.prim &= 0x0fffffff;
     const unsigned bit = 1u << (p.ref & 31u);
     if (wv.hit[p.ref >> 5] & bit) return;   // another bracket of the pair already answered "hit"
     const F4 p01 = sc.prim_p01[p.prim], p23 = sc.prim_p23[p.prim], rad = sc.prim_rad[p.prim];
@@ -406,9 +403,10 @@ __global__ void __launch_bounds__(128) k_wave_solve_fill(SceneView sc, WaveView 
     if (count < 0) count = min(wv.counters[1], wv.cap_f);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
-    const WavePair p = wv.pairs_f[i];
-    const PrimMeta pm = sc.prim_meta[p.prim];
-    const int w = prim_winding(pm.type_flags & DVG_PF_TYPE_MASK, sc.prim_p01[p.prim], sc.prim_p23[p.prim], mk2(p.x, p.y));
+    WavePair p = wv.pairs_f[i];
+    const int ptype = (int)((unsigned)p.prim >> 28);
+    p.prim &= 0x0fffffff;
+    const int w = prim_winding(ptype, sc.prim_p01[p.prim], sc.prim_p23[p.prim], mk2(p.x, p.y));
     const unsigned k = p.ref & 31u;
     if (w != 0) atomicOr(&wv.wind[(size_t)(p.ref >> 5) * 4 + (k >> 3)], (unsigned)(w & 15) << (4 * (k & 7)));
 }
