@@ -145,7 +145,8 @@ class RenderFunction(torch.autograd.Function):
         # boundary sample adds to the 9 entries of its group's transform; groups usually share one constant eye(3))
         packed.needs_xform_grad = any(t.requires_grad for t in tensors[scene_pack.B_MAT3])
         # rows of d_image a pixel-row shard needs from its neighbours (diffvg_b200/sharded.py)
-        packed.halo_rows = max(1, int(np.ceil(float(filter.radius))))
+        packed.filter_radius = float(filter.radius)
+        packed.halo_rows = max(1, int(np.ceil(packed.filter_radius)))
         return [packed, params]
 
     @staticmethod

@@ -119,8 +119,15 @@ class ShardedRenderFunction(torch.autograd.Function):
                 ns.handle, background_image.data_ptr() if background_image is not None else None, full.data_ptr(),
                 width, height, num_samples_x, num_samples_y, int(seed), 1 if packed.use_prefiltering else 0,
                 rb, re, stream))
+            wide = float(getattr(packed, 'filter_radius', 0.5)) > 0.5
             if not gather:
+                assert not wide or world == 1, 'gather=False needs a pixel filter of radius <= 0.5 (samples splat across band edges)'
                 img = full[rb:re]
+            elif world > 1 and wide:
+                # a sample splats onto pixels up to ceil(radius) rows outside its band: every rank's buffer holds the
+                # contributions of ITS samples to the whole image, the image is their sum
+                dist.all_reduce(full, op=dist.ReduceOp.SUM, group=group)
+                img = full
             else:
                 img = allgather_rows(full[rb:re], bands, group) if world > 1 else full
         ctx.native_scene, ctx.scene_version, ctx.packed = ns, version, packed
