@@ -77,7 +77,7 @@ struct DvgScene {
     DevBuf d_insts, d_groups, d_p01, d_p23, d_rad, d_box, d_thick, d_meta, d_cbox, d_cbox_pf, d_cap, d_shape_cdf, d_shape_pmf;
     DevBuf d_flags;  // [0] error flag, [1] total length (float bits)
     // bins
-    DevBuf d_bin_counts, d_bin_offsets, d_bin_items;
+    DevBuf d_bin_counts, d_bin_offsets, d_bin_items, d_sbin_counts, d_sbin_items;
     int bin_w = 0, bin_h = 0, bin_tw = 0, bin_th = 0, bin_pf = 0;  // configuration the bins were built for (0 = none)
     int bin_r0 = 0, bin_r1 = 0;                                    // tile rows that were binned
     // per-render workspaces
@@ -148,7 +148,7 @@ struct DvgScene {
         DevBuf *all[] = {&d_topo, &d_inst_group, &d_inst_shape, &d_inst_prim_begin, &d_prim_inst, &d_prim_seg,
                          &d_prim_point_id, &d_params, &d_shapes_length, &d_shape_box, &d_shape_r0, &d_seg_cdf, &d_seg_pmf,
                          &d_seg_point_id, &d_insts, &d_groups, &d_p01, &d_p23, &d_rad, &d_box, &d_thick, &d_meta, &d_cbox, &d_cbox_pf, &d_cap,
-                         &d_shape_cdf, &d_shape_pmf, &d_flags, &d_bin_counts, &d_bin_offsets, &d_bin_items, &d_weight,
+                         &d_shape_cdf, &d_shape_pmf, &d_flags, &d_bin_counts, &d_bin_offsets, &d_bin_items, &d_sbin_counts, &d_sbin_items, &d_weight,
                          &d_keys, &d_tile_counts, &d_tile_offsets, &d_tile_fill, &d_blk_counts, &d_blk_offsets, &d_sorted,
                          &d_wave_hit, &d_wave_wind, &d_wave_pairs_s, &d_wave_pairs_f, &d_wave_units_a, &d_wave_units_d, &d_wave_counters, &d_tile_nch, &d_tile_choff,
                          &d_edge_chunks, &d_edge_choff, &d_wave_max, &d_bsamples, &d_item_tile, &d_grad_rep};
@@ -292,7 +292,19 @@ int ensure_bins(DvgScene *s, int width, int height, int spp, int pf, cudaStream_
     CK(s->d_bin_counts.ensure(sizeof(int) * ntiles));
     CK(s->d_bin_offsets.ensure(sizeof(int) * (ntiles + 1)));
     bb.counts = s->d_bin_counts.as<int>(); bb.offsets = s->d_bin_offsets.as<int>(); bb.items = nullptr;
+    // two-level binning when the supertile lists fit a fixed stride of num_prims entries each (<= 128 MB)
+    bb.super = 8;
+    bb.stiles_x = (bb.tiles_x + bb.super - 1) / bb.super; bb.stiles_y = (bb.tiles_y + bb.super - 1) / bb.super;
+    const int64_t sentries = (int64_t)bb.stiles_x * bb.stiles_y * s->num_prims;
+    if (ntiles < 256 || s->num_prims < 64 || sentries > ((int64_t)1 << 25)) bb.super = 0;
+    bb.s_counts = nullptr; bb.s_items = nullptr;
+    if (bb.super) {
+        CK(s->d_sbin_counts.ensure(sizeof(int) * (size_t)bb.stiles_x * bb.stiles_y));
+        CK(s->d_sbin_items.ensure(sizeof(int) * (size_t)sentries));
+        bb.s_counts = s->d_sbin_counts.as<int>(); bb.s_items = s->d_sbin_items.as<int>();
+    }
     BuildView bv = s->build_view();
+    launch_bin_coarse(bv, bb, st);
     launch_bin_count(bv, bb, st);
     CK(s->d_tile_nch.ensure(sizeof(int) * ntiles));
     CK(s->d_tile_choff.ensure(sizeof(int) * (ntiles + 1)));

@@ -33,6 +33,10 @@ struct BinBuild {
     int width, height, tile_w, tile_h, tiles_x, tiles_y;
     int prefilter;  // 1: bin with prim_cbox_pf (SDF-prefiltering candidate regions)
     int tile_row0, tile_row1;  // tile rows to bin (the others get empty lists)
+    // two-level binning: supertiles of `super` x `super` tiles get a candidate list first (fixed stride of num_prims
+    // entries per supertile, so no scan / read-back), tiles then test only their supertile's list.  super = 0: off
+    int super, stiles_x, stiles_y;
+    int *s_counts, *s_items;
     int flat;       // 1: test every primitive (few primitives per group); 0: groups first, then their primitives
     int *counts;   // [tiles]
     int *offsets;  // [tiles+1]
@@ -81,6 +85,7 @@ struct SdfArgs {
 void launch_peak_probe(int which, float *out, int iters, cudaStream_t st);
 int edge_samples_per_block();
 void launch_build(const BuildView &bv, cudaStream_t st);
+void launch_bin_coarse(const BuildView &bv, const BinBuild &bb, cudaStream_t st);
 void launch_bin_count(const BuildView &bv, const BinBuild &bb, cudaStream_t st);
 void launch_bin_fill(const BuildView &bv, const BinBuild &bb, cudaStream_t st);
 void launch_scan(const int *in, int *out, int n, cudaStream_t st);
