@@ -85,7 +85,7 @@ class ClockSampler:
             os.close(fd)
             self.f = open(self.path, 'w')
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(gpu_index), '--query-gpu=' + self.Q,
-                                          '--format=csv,noheader,nounits', '-lms', '100'], stdout=self.f,
+                                          '--format=csv,noheader,nounits', '-lms', '20'], stdout=self.f,
                                          stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
