@@ -33,7 +33,7 @@ def main():
     dev = torch.device('cuda', local_rank)
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        os.environ['NCCL_DEBUG'] = 'WARN'
+        os.environ.pop('NCCL_DEBUG', None)
         dist.init_process_group('nccl', device_id=dev)
     from diffvg_b200 import pydiffvg, sharded
     import scenes
