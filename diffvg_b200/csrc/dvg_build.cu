@@ -72,38 +72,6 @@ DVG_D bool overlaps(Box a, float x0, float y0, float x1, float y1) {
     return a.x0 <= x1 && a.x1 >= x0 && a.y0 <= y1 && a.y1 >= y0;
 }
 
-// Tight binning of curved strokes.  A diagonal 40-px stroke has a 900 px^2 bounding box and a 100 px^2
-// footprint; binned by box, two thirds of a tile's candidates are strokes that no sample of the tile can touch,
-// and every one of them costs each sample a leaf test + an 8-piece bracket test in the classify kernels.  The
-// polyline bracket (dvg_scene.cuh) proves "farther than R_out from every chord => the exact stroke test returns
-// false"; here the same statement is made for a whole tile: the tile is cut into squares, and a square whose
-// centre is farther than R_out + half-diagonal from a chord cannot contain such a point.  NaN records keep.
-DVG_D bool bracket_reaches_tile(const F4 *cap, float x0, float y0, float x1, float y1) {
-    const float w = x1 - x0, h = y1 - y0;
-    const bool wide = w >= h;
-    const float side = wide ? h : w;
-    const int nsq = min(8, max(1, (int)ceilf((wide ? w : h) / fmaxf(side, 1e-6f))));
-    const float step = (wide ? w : h) / nsq;
-    const float hd = 0.5f * sqrtf(step * step + side * side);   // half diagonal of one piece of the tile
-    bool far_all = true;
-#pragma unroll 1
-    for (int i = 0; i < DVG_CAP_N; i++) {
-        const F4 ca = cap[2 * i], cb = cap[2 * i + 1];   // A.xy, d.xy | 1/|d|^2, R_out^2, R_in^2, pad
-        const float R = sqrtf(cb.y) + hd;
-        const float thr = R * R;
-        for (int q = 0; q < nsq; q++) {
-            const float cx = wide ? x0 + (q + 0.5f) * step : 0.5f * (x0 + x1);
-            const float cy = wide ? 0.5f * (y0 + y1) : y0 + (q + 0.5f) * step;
-            const float wx = cx - ca.x, wy = cy - ca.y;
-            float t = (wx * ca.z + wy * ca.w) * cb.x;
-            t = t < 0.f ? 0.f : (t > 1.f ? 1.f : t);
-            const float ex = wx - t * ca.z, ey = wy - t * ca.w;
-            far_all = far_all && (ex * ex + ey * ey > thr);   // false for NaN / inf
-        }
-    }
-    return !far_all;
-}
-
 // Canvas-space rectangle of tiles [tx0, tx1] x [ty0, ty1] (inclusive), with a margin that also covers the +-1e-4
 // (normalised) offsets of boundary samples (diffvg.cpp:1416,1420) and float rounding of pt/W*canvas_w.
 // int(-0.9) == 0: the reference attributes boundary samples lying up to one pixel left of / above the image to pixel

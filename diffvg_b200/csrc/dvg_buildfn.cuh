@@ -242,6 +242,38 @@ DVG_HD void build_capsules(int type, F4 p01, F4 p23, float rmax, float rmin, flo
     }
 }
 
+// Tight binning of curved strokes.  A diagonal 40-px stroke has a 900 px^2 bounding box and a 100 px^2
+// footprint; binned by box, two thirds of a tile's candidates are strokes that no sample of the tile can touch,
+// and every one of them costs each sample a leaf test + an 8-piece bracket test in the classify kernels.  The
+// polyline bracket (dvg_scene.cuh) proves "farther than R_out from every chord => the exact stroke test returns
+// false"; here the same statement is made for a whole tile: the tile is cut into squares, and a square whose
+// centre is farther than R_out + half-diagonal from a chord cannot contain such a point.  NaN records keep.
+DVG_HD bool bracket_reaches_tile(const F4 *cap, float x0, float y0, float x1, float y1) {
+    const float w = x1 - x0, h = y1 - y0;
+    const bool wide = w >= h;
+    const float side = wide ? h : w;
+    int nsq = (int)ceilf((wide ? w : h) / (side > 1e-6f ? side : 1e-6f));
+    nsq = nsq < 1 ? 1 : (nsq > 8 ? 8 : nsq);
+    const float step = (wide ? w : h) / nsq;
+    const float hd = 0.5f * sqrtf(step * step + side * side);   // half diagonal of one piece of the tile
+    bool far_all = true;
+    for (int i = 0; i < DVG_CAP_N; i++) {
+        const F4 ca = cap[2 * i], cb = cap[2 * i + 1];   // A.xy, d.xy | 1/|d|^2, R_out^2, R_in^2, pad
+        const float R = sqrtf(cb.y) + hd;
+        const float thr = R * R;
+        for (int q = 0; q < nsq; q++) {
+            const float cx = wide ? x0 + (q + 0.5f) * step : 0.5f * (x0 + x1);
+            const float cy = wide ? 0.5f * (y0 + y1) : y0 + (q + 0.5f) * step;
+            const float wx = cx - ca.x, wy = cy - ca.y;
+            float t = (wx * ca.z + wy * ca.w) * cb.x;
+            t = t < 0.f ? 0.f : (t > 1.f ? 1.f : t);
+            const float ex = wx - t * ca.z, ey = wy - t * ca.w;
+            far_all = far_all && (ex * ex + ey * ey > thr);   // false for NaN / inf
+        }
+    }
+    return !far_all;
+}
+
 // ------------------------------------------------------------------ primitives
 // Leaf boxes and radii follow scene.cpp:527-600 (topology-only maps prim -> inst / segment /
 // first point come from the host).

@@ -364,6 +364,20 @@ EXPORT int64_t emul_scene_dump(const int32_t *topo, const float *params, int wha
 }
 
 // PCG known-answer helper: state after init and the first two floats.
+// Test support for the tight tile binning (dvg_buildfn.cuh bracket_reaches_tile): brackets of one cubic stroke,
+// the tile test, and the per-point bracket classification the kernels use.
+EXPORT void emul_bracket_build(const float *pts8, float rmax, float rmin, float *cap_out) {
+    build_capsules(PRIM_CUBIC, mk4(pts8[0], pts8[1], pts8[2], pts8[3]), mk4(pts8[4], pts8[5], pts8[6], pts8[7]), rmax, rmin, cap_out);
+}
+EXPORT int emul_bracket_reaches_tile(const float *cap, float x0, float y0, float x1, float y1) {
+    return bracket_reaches_tile(reinterpret_cast<const F4 *>(cap), x0, y0, x1, y1) ? 1 : 0;
+}
+EXPORT int emul_bracket_classify(const float *cap, float x, float y) { return capsule_classify(cap, mk2(x, y)); }
+EXPORT int emul_stroke_hit_cubic(const float *pts8, const float *rad4, float x, float y) {
+    return stroke_hit_cubic(mk2(pts8[0], pts8[1]), mk2(pts8[2], pts8[3]), mk2(pts8[4], pts8[5]), mk2(pts8[6], pts8[7]),
+                            mk4(rad4[0], rad4[1], rad4[2], rad4[3]), mk2(x, y)) ? 1 : 0;
+}
+
 EXPORT void emul_pcg(int idx, uint64_t seed, uint64_t *state, float *rx, float *ry) {
     Pcg32 r = pcg32_init(idx, seed);
     *state = r.state;

@@ -333,3 +333,43 @@ def test_c_restatement_refuses_what_it_does_not_restate():
     topo, params = util.pack(scenes.single_circle())
     with pytest.raises(RuntimeError):
         c.render(topo, params, 32, 32, 1, 1, 0, d_render_image=np.zeros((32, 32, 4), np.float32))
+
+
+def test_tight_binning_never_drops_a_stroke_a_sample_could_touch():
+    """dvg_buildfn.cuh bracket_reaches_tile (used by k_bin): a tile may drop a curved stroke only if NO point of the tile
+    can be within the stroke.  Property check on random cubics and tiles with the product's own host-compiled code:
+    whenever the tile test says "cannot reach", every sampled point of the tile is classified "certainly outside" by the
+    polyline bracket and the exact closest-point test (the reference's algorithm) agrees."""
+    import ctypes
+    lib = emul._load()
+    fp = ctypes.POINTER(ctypes.c_float)
+    lib.emul_bracket_build.argtypes = [fp, ctypes.c_float, ctypes.c_float, fp]
+    lib.emul_bracket_reaches_tile.argtypes = [fp] + [ctypes.c_float] * 4
+    lib.emul_bracket_classify.argtypes = [fp, ctypes.c_float, ctypes.c_float]
+    lib.emul_stroke_hit_cubic.argtypes = [fp, fp, ctypes.c_float, ctypes.c_float]
+    rng = np.random.RandomState(12)
+    dropped = kept = 0
+    for _ in range(300):
+        p0 = rng.rand(2) * 64
+        pts = [p0]
+        for _k in range(3):
+            pts.append(pts[-1] + (rng.rand(2) - 0.5) * 25.6)
+        pts = np.asarray(pts, np.float32).reshape(-1)
+        r = np.float32(0.5 + 3.5 * rng.rand())
+        cap = np.zeros(64, np.float32)
+        lib.emul_bracket_build(pts.ctypes.data_as(fp), r, r, cap.ctypes.data_as(fp))
+        rad = np.full(4, r, np.float32)
+        for _t in range(40):
+            tw, th = [(8, 2), (8, 8), (16, 8), (16, 16)][rng.randint(4)]
+            x0 = np.float32(rng.randint(-8, 72)); y0 = np.float32(rng.randint(-8, 72))
+            x1, y1 = np.float32(x0 + tw), np.float32(y0 + th)
+            if lib.emul_bracket_reaches_tile(cap.ctypes.data_as(fp), x0, y0, x1, y1):
+                kept += 1
+                continue
+            dropped += 1
+            xs = np.concatenate([rng.rand(24) * tw + x0, [x0, x1, x0, x1]]).astype(np.float32)
+            ys = np.concatenate([rng.rand(24) * th + y0, [y0, y0, y1, y1]]).astype(np.float32)
+            for x, y in zip(xs, ys):
+                assert lib.emul_bracket_classify(cap.ctypes.data_as(fp), x, y) < 0
+                assert lib.emul_stroke_hit_cubic(pts.ctypes.data_as(fp), rad.ctypes.data_as(fp), x, y) == 0
+    assert dropped > 1000 and kept > 200   # the test is exercised both ways
