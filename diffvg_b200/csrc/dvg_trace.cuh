@@ -190,6 +190,7 @@ struct SampleTracer {
                         const bool ex = prim_stroke_hit(ptype, (tf & DVG_PF_APPROX) != 0, pr.p01, pr.p23, pr.rad, shape_r, lpt, &dd);
                         dvg_capsule_stats(cls, ex);
                         if (cls > 0 && !ex && ptype == PRIM_CUBIC) dvg_capsule_dump(pr.p01, pr.p23, pr.rad, lpt);
+                        if (cls > 0 && ptype == PRIM_CUBIC) dvg_cert_stats(pr.p01, pr.p23, pr.cap, lpt, ex);
                     }
 #endif
                     const bool h = skip ? false : prim_stroke_hit(ptype, (tf & DVG_PF_APPROX) != 0, pr.p01, pr.p23, pr.rad,

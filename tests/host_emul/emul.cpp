@@ -9,8 +9,11 @@
 #include <atomic>
 static std::atomic<long long> g_cs[6];   // [cls+1][exact]
 static inline void dvg_capsule_stats(int cls, bool ex) { g_cs[(cls + 1) * 2 + (ex ? 1 : 0)]++; }
+static std::atomic<long long> g_cert[4];
+static std::atomic<long long> g_cert2[4];   // [0] bernstein gmin > 0, [1] sampled g > 0 everywhere, [2] total, [3] unused   // [certificate holds][exact]  (research: DESIGN.md section 10, item 1)
 namespace dvg { struct F4; struct F2; }
 static void dvg_capsule_dump(const dvg::F4 &p01, const dvg::F4 &p23, const dvg::F4 &rad, const dvg::F2 &pt);
+static void dvg_cert_stats(const dvg::F4 &p01, const dvg::F4 &p23, const float *cap, const dvg::F2 &pt, bool ex);
 #endif
 #include "../../diffvg_b200/csrc/dvg_common.cuh"
 #include "../../diffvg_b200/csrc/dvg_scene.cuh"
@@ -459,6 +462,54 @@ EXPORT void emul_debug_boundary(const int32_t *topo, const float *params, int W,
 }
 
 #ifdef DVG_CAPSULE_STATS
+// RESEARCH (not used by the product): a per-pair certificate that the reference's closest-point solve succeeds for a
+// sample the bracket proves inside.  g(t) = |q'(t)|^2 + (q(t) - p).q''(t) is the derivative of the quintic
+// f(t) = (q(t) - p).q'(t); if its Bernstein coefficients on [0,1] are all > 0, f is strictly increasing: one root, no
+// near-double root for Newton's |f| < 1e-5 stop to land on.  The stop then leaves |t - t*| <= 1e-5 A / min g, i.e. a
+// displacement of at most max|q'| * that along the curve, which must stay inside the slack the bracket leaves.
+static bool cert_monotone(const F4 &p01, const F4 &p23, const float *cap, const F2 &pt) {
+    const double P[4][2] = {{p01.x, p01.y}, {p01.z, p01.w}, {p23.x, p23.y}, {p23.z, p23.w}};
+    double c[4][2], d[3][2], e[2][2];
+    for (int i = 0; i < 4; i++) { c[i][0] = P[i][0] - pt.x; c[i][1] = P[i][1] - pt.y; }
+    for (int j = 0; j < 3; j++) { d[j][0] = 3 * (P[j + 1][0] - P[j][0]); d[j][1] = 3 * (P[j + 1][1] - P[j][1]); }
+    for (int k = 0; k < 2; k++) { e[k][0] = 6 * (P[k + 2][0] - 2 * P[k + 1][0] + P[k][0]); e[k][1] = 6 * (P[k + 2][1] - 2 * P[k + 1][1] + P[k][1]); }
+    const double C2[3] = {1, 2, 1}, C3[4] = {1, 3, 3, 1}, C1[2] = {1, 1}, C4[5] = {1, 4, 6, 4, 1};
+    double gmin = 1e300, dmax = 0;
+    for (int k = 0; k <= 4; k++) {
+        double g = 0;
+        for (int i = 0; i <= 2; i++) { int j = k - i; if (j < 0 || j > 2) continue; g += C2[i] * C2[j] / C4[k] * (d[i][0] * d[j][0] + d[i][1] * d[j][1]); }
+        for (int i = 0; i <= 3; i++) { int j = k - i; if (j < 0 || j > 1) continue; g += C3[i] * C1[j] / C4[k] * (c[i][0] * e[j][0] + c[i][1] * e[j][1]); }
+        gmin = g < gmin ? g : gmin;
+    }
+    for (int j = 0; j < 3; j++) { double l = sqrt(d[j][0] * d[j][0] + d[j][1] * d[j][1]); dmax = l > dmax ? l : dmax; }
+    g_cert2[2]++;
+    {
+        bool pos = true;
+        for (int i = 0; i <= 64 && pos; i++) {
+            const double t = i / 64.0, u = 1 - t;
+            const double qx = u*u*u*c[0][0] + 3*u*u*t*c[1][0] + 3*u*t*t*c[2][0] + t*t*t*c[3][0], qy = u*u*u*c[0][1] + 3*u*u*t*c[1][1] + 3*u*t*t*c[2][1] + t*t*t*c[3][1];
+            const double dx = u*u*d[0][0] + 2*u*t*d[1][0] + t*t*d[2][0], dy = u*u*d[0][1] + 2*u*t*d[1][1] + t*t*d[2][1];
+            const double ex = u*e[0][0] + t*e[1][0], ey = u*e[0][1] + t*e[1][1];
+            pos = dx*dx + dy*dy + qx*ex + qy*ey > 0;
+        }
+        if (pos) g_cert2[1]++;
+    }
+    if (!(gmin > 0)) return false;
+    g_cert2[0]++;
+    const double q3x = -P[0][0] + 3 * P[1][0] - 3 * P[2][0] + P[3][0], q3y = -P[0][1] + 3 * P[1][1] - 3 * P[2][1] + P[3][1];
+    const double A = 3 * (q3x * q3x + q3y * q3y);
+    double slack = 0;   // r_min - (distance to chord + deviation), best piece
+    for (int i = 0; i < DVG_CAP_N; i++) {
+        const float *cc = cap + 8 * i;
+        const double wx = pt.x - cc[0], wy = pt.y - cc[1];
+        double t = (wx * cc[2] + wy * cc[3]) * cc[4];
+        t = t < 0 ? 0 : (t > 1 ? 1 : t);
+        const double ex = wx - t * cc[2], ey = wy - t * cc[3];
+        const double di = sqrt(ex * ex + ey * ey);
+        if (cc[6] > 0) { const double sl = sqrt((double)cc[6]) - di + 1e-2; slack = sl > slack ? sl : slack; }
+    }
+    return dmax * 1e-5 * A / gmin < 0.5 * slack;
+}
 static std::atomic<int> g_dump_left{12};
 static void dvg_capsule_dump(const F4 &p01, const F4 &p23, const F4 &rad, const F2 &pt) {
     if (g_dump_left-- <= 0) return;
@@ -483,8 +534,13 @@ static void dvg_capsule_dump(const F4 &p01, const F4 &p23, const F4 &rad, const 
     }
     printf("\n");
 }
+static void dvg_cert_stats(const F4 &p01, const F4 &p23, const float *cap, const F2 &pt, bool ex) {
+    g_cert[(cert_monotone(p01, p23, cap, pt) ? 2 : 0) + (ex ? 1 : 0)]++;
+}
 EXPORT void emul_capsule_stats(long long *out, int reset) {
     for (int i = 0; i < 6; i++) { out[i] = g_cs[i]; if (reset) g_cs[i] = 0; }
+    for (int i = 0; i < 4; i++) { out[6 + i] = g_cert[i]; if (reset) g_cert[i] = 0; }
+    for (int i = 0; i < 4; i++) { out[10 + i] = g_cert2[i]; if (reset) g_cert2[i] = 0; }
 }
 #endif
 
