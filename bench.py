@@ -139,11 +139,11 @@ def reference_arm(args, rank):
         oracle_check.render(topo, params, W, rows, NSX, NSY, seed, d_render_image=d_img)
         return time.perf_counter() - t0
 
-    try:
-        t_probe = one(32, 0)
-    except oracle_check.OracleUnavailable as e:   # oracle/_ref absent: the C restatement has no backward pass
-        print(json.dumps({'impl': 'reference', 'unavailable': str(e)}), flush=True)
+    if oracle_check.kind() != 'reference':   # oracle/_ref absent: the C restatement has no backward pass (and no threads)
+        print(json.dumps({'impl': 'reference', 'unavailable': 'oracle/_ref (the compiled reference) is not built here; '
+                          'oracle/dvg_oracle.c restates the forward colour path only'}), flush=True)
         return
+    t_probe = one(32, 0)
     t_full_est = t_probe * (H / 32.0)
     budget = 150.0
     frac = min(1.0, budget / max((args.steps + args.warmup) * t_full_est, 1e-9))
@@ -362,6 +362,8 @@ def main():
         sys.path.insert(0, os.path.join(ROOT, 'oracle'))
         import oracle_check
         try:
+            if oracle_check.kind() != 'reference':
+                raise oracle_check.OracleUnavailable('oracle/_ref is not built here')
             t0 = time.perf_counter()
             ref_img = oracle_check.render(topo, params_np, W, H, NSX, NSY, 0)['image']
             d_img_np = (2.0 * (ref_img - target.cpu().numpy()) / ref_img.size).astype(np.float32)
