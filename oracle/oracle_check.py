@@ -41,6 +41,9 @@ def render(*args, **kwargs):
         raise OracleUnavailable('oracle/_ref (the compiled reference) is not built here and oracle/dvg_oracle.c restates the '
                                 'forward colour path only')
     kwargs.pop('variant', None)
+    topo, _params, width, height, nsx, nsy = args[:6]
+    if float(width) * height * nsx * nsy * int(topo[4]) > 5e9:   # samples x shape groups: single-threaded, no culling
+        raise OracleUnavailable('too large for the single-threaded C restatement; build oracle/_ref')
     return c_oracle.render(*args, **kwargs)
 
 
