@@ -88,6 +88,7 @@ struct DvgScene {
     // wavefront passes (dvg_wave.cu)
     DevBuf d_wave_hit, d_wave_wind, d_wave_pairs_s, d_wave_pairs_f, d_wave_units_a, d_wave_units_d, d_wave_counters, d_tile_nch, d_tile_choff,
         d_edge_chunks, d_edge_choff, d_wave_max, d_bsamples, d_item_tile, d_grad_rep;
+    DevBuf d_bvh_path, d_bvh_group, d_bvh_scene, d_bvh_keys;   // reference-topology trees (dvg_bvh.cu), built on demand by dvg_scene_dump
     int total_chunks = 0, max_nch = 0;   // of the current bins (read back with the bin total)
     bool has_fills = false;
     // which pixel pass the result words currently hold (forward's are reused by the interior backward pass)
@@ -151,7 +152,8 @@ struct DvgScene {
                          &d_shape_cdf, &d_shape_pmf, &d_flags, &d_bin_counts, &d_bin_offsets, &d_bin_items, &d_sbin_counts, &d_sbin_items, &d_weight,
                          &d_keys, &d_tile_counts, &d_tile_offsets, &d_tile_fill, &d_blk_counts, &d_blk_offsets, &d_sorted,
                          &d_wave_hit, &d_wave_wind, &d_wave_pairs_s, &d_wave_pairs_f, &d_wave_units_a, &d_wave_units_d, &d_wave_counters, &d_tile_nch, &d_tile_choff,
-                         &d_edge_chunks, &d_edge_choff, &d_wave_max, &d_bsamples, &d_item_tile, &d_grad_rep};
+                         &d_edge_chunks, &d_edge_choff, &d_wave_max, &d_bsamples, &d_item_tile, &d_grad_rep,
+                         &d_bvh_path, &d_bvh_group, &d_bvh_scene, &d_bvh_keys};
         for (DevBuf *b : all) b->release();
         if (h_pinned) cudaFreeHost(h_pinned);
         h_pinned = nullptr;
@@ -830,9 +832,60 @@ int dvg_measure_peak(int which, int device, double *tflops) {
 }
 
 int64_t dvg_scene_dump(DvgScene *s, int what, int index, uint32_t *out, int64_t cap, void *stream) {
-    (void)s; (void)what; (void)index; (void)out; (void)cap; (void)stream;
-    fail(DVG_ERR_UNSUPPORTED, "dvg_scene_dump: not implemented yet");
-    return -1;
+    // every selector is copied back from DEVICE memory: the tables the kernels read (3-10) and the
+    // reference-topology trees built by dvg_bvh.cu (0-2)
+    auto bad = [&](const char *msg) { fail(DVG_ERR_INVALID, msg); return (int64_t)-1; };
+    if (!s || !out) return bad("null argument");
+    if (!s->params_set) return bad("dvg_scene_set_params has not been called");
+    DeviceGuard guard(s->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int32_t *t = s->topo.data();
+    const void *src = nullptr;
+    int64_t words = 0;
+    auto shape_rec = [&](int sh) { return t + t[DVG_H_OFF_SHAPES] + sh * DVG_SHAPE_REC_LEN; };
+    if (what >= 0 && what <= 2) {
+        DevBuf &dp = s->d_bvh_path, &dg = s->d_bvh_group, &ds = s->d_bvh_scene, &dk = s->d_bvh_keys;
+        if (dp.ensure(sizeof(BvhNode) * 2 * (size_t)std::max(s->total_segs, 1)) != cudaSuccess ||
+            dg.ensure(sizeof(BvhNode) * 2 * (size_t)s->num_insts) != cudaSuccess ||
+            ds.ensure(sizeof(BvhNode) * 2 * (size_t)s->num_groups) != cudaSuccess ||
+            dk.ensure(8 * bvh_key_words(s->total_segs, s->num_insts, s->num_groups)) != cudaSuccess) {
+            fail(DVG_ERR_CUDA, "cudaMalloc failed");
+            return -1;
+        }
+        launch_bvh_build(s->build_view(), dp.as<BvhNode>(), dg.as<BvhNode>(), ds.as<BvhNode>(), dk.as<unsigned long long>(), st);
+        if (what == 0) { src = ds.p; words = 7 * (2 * (int64_t)s->num_groups - 1); }
+        else if (what == 1) {
+            if (index < 0 || index >= s->num_groups) return bad("group index out of range");
+            const int32_t *r = t + t[DVG_H_OFF_GROUPS] + index * DVG_GROUP_REC_LEN;
+            src = dg.as<BvhNode>() + 2 * r[DVG_G_SHAPES_OFF];
+            words = 7 * (2 * (int64_t)r[DVG_G_NUM_SHAPES] - 1);
+        } else {
+            if (index < 0 || index >= s->num_shapes || shape_rec(index)[DVG_S_TYPE] != DVG_SHAPE_PATH) return bad("shape index is not a path");
+            src = dp.as<BvhNode>() + 2 * shape_rec(index)[DVG_S_NCP_OFF];
+            words = 7 * (2 * (int64_t)shape_rec(index)[DVG_S_NUM_SEGS] - 1);
+        }
+    } else if (what >= 3 && what <= 5) {
+        src = what == 3 ? s->d_shapes_length.p : (what == 4 ? s->d_shape_cdf.p : s->d_shape_pmf.p);
+        words = what == 3 ? s->num_shapes : s->num_insts;
+    } else if (what >= 6 && what <= 8) {
+        if (index < 0 || index >= s->num_shapes || shape_rec(index)[DVG_S_TYPE] != DVG_SHAPE_PATH) return bad("shape index is not a path");
+        const int off = shape_rec(index)[DVG_S_NCP_OFF];
+        src = what == 6 ? (const void *)(s->d_seg_cdf.as<float>() + off)
+                        : (what == 7 ? (const void *)(s->d_seg_pmf.as<float>() + off) : (const void *)(s->d_seg_point_id.as<int>() + off));
+        words = shape_rec(index)[DVG_S_NUM_SEGS];
+    } else if (what == 9 || what == 10) {
+        src = what == 9 ? s->d_inst_shape.p : s->d_inst_group.p;
+        words = s->num_insts;
+    } else {
+        return bad("bad dump selector");
+    }
+    if (words > cap) return bad("dump buffer too small");
+    if (cudaMemcpyAsync(out, src, (size_t)words * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+        cudaStreamSynchronize(st) != cudaSuccess) {
+        fail(DVG_ERR_CUDA, std::string("dvg_scene_dump: ") + cudaGetErrorString(cudaGetLastError()));
+        return -1;
+    }
+    return words;
 }
 
 int dvg_scene_destroy(DvgScene *s) {

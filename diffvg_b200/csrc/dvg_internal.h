@@ -82,6 +82,12 @@ struct SdfArgs {
     int num_eval;
 };
 
+// Node of the reference-topology BVHs (scene.h:12-16), 28 bytes; built by dvg_bvh.cu for dvg_scene_dump.
+struct BvhNode { int child0, child1; Box box; float max_radius; };
+size_t bvh_key_words(int total_segs, int num_insts, int num_groups);
+void launch_bvh_build(const BuildView &bv, BvhNode *path_nodes, BvhNode *group_nodes, BvhNode *scene_nodes,
+                      unsigned long long *keys, cudaStream_t st);
+
 void launch_peak_probe(int which, float *out, int iters, cudaStream_t st);
 int edge_samples_per_block();
 void launch_build(const BuildView &bv, cudaStream_t st);

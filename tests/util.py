@@ -102,3 +102,28 @@ def gpu_render_rows(topo, params, width, height, nsx, nsy, seed, row_ranges, d_r
         return out
     finally:
         n.lib.dvg_scene_destroy(h)
+
+
+def gpu_scene_dump(topo, params, selectors):
+    """dvg_scene_dump of the product library for a list of (what, index) selectors -> list of uint32 arrays.
+    Everything comes back from DEVICE memory (the tables the kernels read, the trees of dvg_bvh.cu)."""
+    import ctypes
+    from diffvg_b200 import _native as n
+    h = ctypes.c_void_p()
+    topo = np.ascontiguousarray(topo, np.int32)
+    n.check(n.lib.dvg_scene_create(topo.ctypes.data, topo.shape[0], 0, ctypes.byref(h)))
+    try:
+        stream = torch.cuda.current_stream().cuda_stream
+        p = np.ascontiguousarray(params, np.float32)
+        n.check(n.lib.dvg_scene_set_params(h, p.ctypes.data, p.shape[0], 0, stream))
+        out = []
+        cap = 1 << 22
+        buf = np.zeros(cap, np.uint32)
+        for what, index in selectors:
+            cnt = n.lib.dvg_scene_dump(h, what, index, buf.ctypes.data, cap, stream)
+            if cnt < 0:
+                raise RuntimeError(n.lib.dvg_last_error().decode())
+            out.append(buf[:cnt].copy())
+        return out
+    finally:
+        n.lib.dvg_scene_destroy(h)
