@@ -8,3 +8,4 @@ from .image import *  # noqa: F401,F403
 from .parse_svg import *  # noqa: F401,F403
 from .color import *  # noqa: F401,F403
 from .save_svg import *  # noqa: F401,F403
+from .packed_params import *  # noqa: F401,F403

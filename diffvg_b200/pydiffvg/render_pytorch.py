@@ -24,6 +24,9 @@ from . import pixel_filter as _pixel_filter
 from .diffvg_enums import FilterType
 from .. import scene_pack
 
+__all__ = ['RenderFunction', 'OutputType', 'PackedScene', 'set_print_timing', 'set_check_scene', 'clear_cache',
+           'set_scene_cache_size']
+
 print_timing = False
 check_scene = True
 
@@ -90,6 +93,21 @@ _scene_cache = OrderedDict()
 _SCENE_CACHE_MAX = 32
 
 
+def clear_cache():
+    """Drops every cached native scene (topology + grow-only device workspaces: bins, result words, pair queues,
+    gradient replicas -- hundreds of MB at large render sizes) and the memoised scene packings."""
+    _scene_cache.clear()
+    del scene_pack._MEMO[:]
+
+
+def set_scene_cache_size(n):
+    """How many native scenes (distinct topologies per device) stay alive; least recently used go first."""
+    global _SCENE_CACHE_MAX
+    _SCENE_CACHE_MAX = max(1, int(n))
+    while len(_scene_cache) > _SCENE_CACHE_MAX:
+        _scene_cache.popitem(last=False)
+
+
 def _get_native_scene(packed, device_index):
     key = (packed.topo_key, device_index)
     ns = _scene_cache.get(key)
@@ -106,9 +124,9 @@ def _get_native_scene(packed, device_index):
 class PackedScene:
     """First element of `scene_args`: everything about the scene that is not a float parameter."""
 
-    def __init__(self, topo, canvas_width, canvas_height, output_type, use_prefiltering, eval_positions):
+    def __init__(self, topo, canvas_width, canvas_height, output_type, use_prefiltering, eval_positions, topo_key=None):
         self.topo = topo
-        self.topo_key = topo.tobytes()
+        self.topo_key = topo.tobytes() if topo_key is None else topo_key
         self.canvas_width = canvas_width
         self.canvas_height = canvas_height
         self.output_type = output_type
@@ -210,6 +228,10 @@ class RenderFunction(torch.autograd.Function):
         ctx.device = dev
         ctx.params_device = params.device
         ctx.save_for_backward(params)
+        if _get_device().type != 'cuda':
+            # set_use_gpu(False) / set_device(cpu): there is no CPU renderer here, but the apps then expect CPU tensors
+            # back (losses against CPU targets); rendering stays on the GPU, the image is copied to the host
+            rendered_image = rendered_image.to(_get_device())
         return rendered_image
 
     @staticmethod

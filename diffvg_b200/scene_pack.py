@@ -222,7 +222,9 @@ def _pack_scene_full(canvas_width, canvas_height, shapes, shape_groups, filter_t
 
     fr = filter_radius if filter_radius is not None else torch.tensor(0.5)
     bk.at(SRC_FILTER, 0)
-    frb, froff = _add_width(bk, fr, None)
+    # with "everything else", not with the stroke widths: an optimiser stepping the scalar bucket of a PackedParams
+    # must not move the pixel filter along
+    frb, froff = B_GENERIC, bk.add_generic(fr, 1, None)
 
     # bucket bases in the final concatenation order
     base = [0] * NUM_BUCKETS

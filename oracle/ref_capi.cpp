@@ -148,8 +148,13 @@ std::unique_ptr<RefScene> build(const int32_t *topo, const float *params) {
     for (auto &s : rs->shapes) sl.push_back(&s);
     for (auto &g : rs->groups) gl.push_back(&g);
     Filter filt{(FilterType)topo[DVG_H_FILTER_TYPE], p[topo[DVG_H_FILTER_RADIUS_OFF]]};
+#ifdef DVGREF_CUDA   // the reference's own CUDA path (oracle/Makefile target ref_cuda): timing only, see dvgref_cuda_bench
+    rs->scene = std::make_shared<Scene>(topo[DVG_H_CANVAS_W], topo[DVG_H_CANVAS_H], sl, gl, filt,
+                                        /*use_gpu*/ true, /*gpu_index*/ -1);
+#else
     rs->scene = std::make_shared<Scene>(topo[DVG_H_CANVAS_W], topo[DVG_H_CANVAS_H], sl, gl, filt,
                                         /*use_gpu*/ false, /*gpu_index*/ -1);
+#endif
     return rs;
 }
 
@@ -312,3 +317,54 @@ EXPORT int64_t dvgref_scene_dump(const int32_t *topo, const float *params, int w
         return -1;
     }
 }
+
+#ifdef DVGREF_CUDA
+#include <chrono>
+#include <cuda_runtime.h>
+// The reference's GPU path (diffvg.cpp:1477-1649 with Scene::use_gpu, the "mega-kernel" build SURVEY 2b names as the
+// GPU bar) timed on the same workload as bench.py: per step Scene() + forward render, Scene() + backward render, as
+// RenderFunction.forward / .backward do (render_pytorch.py:366-409, 692-707).  Images live in device memory (the
+// reference is handed torch CUDA tensors); `d_image_host` is uploaded once.  Returns 0 and the mean wall-clock
+// milliseconds per step (every render() ends with a device synchronisation); the last image / gradient come back
+// for a sanity check.  TIMING ONLY: the nvcc build contracts FMAs, it is not a parity oracle.
+EXPORT int dvgref_cuda_bench(const int32_t *topo, const float *params, int width, int height, int nsx, int nsy,
+                             uint64_t seed0, const float *d_image_host, int warmup, int steps, double *ms_per_step,
+                             float *image_out, float *d_params_out) {
+    try {
+        const size_t npx = (size_t)width * height * 4;
+        float *img = nullptr, *dimg = nullptr;
+        if (cudaMalloc(&img, npx * 4) != cudaSuccess || cudaMalloc(&dimg, npx * 4) != cudaSuccess)
+            throw std::runtime_error("cudaMalloc failed");
+        cudaMemcpy(dimg, d_image_host, npx * 4, cudaMemcpyHostToDevice);
+        std::vector<float> grads(topo[DVG_H_NUM_PARAMS]);
+        double total = 0;
+        for (int it = 0; it < warmup + steps; it++) {
+            cudaDeviceSynchronize();
+            auto t0 = std::chrono::steady_clock::now();
+            {
+                auto rs = build(topo, params);
+                cudaMemset(img, 0, npx * 4);
+                render(rs->scene, ptr<float>(nullptr), ptr<float>(img), ptr<float>(nullptr), width, height, nsx, nsy, seed0 + it,
+                       ptr<float>(nullptr), ptr<float>(nullptr), ptr<float>(nullptr), ptr<float>(nullptr), false, ptr<float>(nullptr), 0);
+            }
+            {
+                auto rs = build(topo, params);
+                render(rs->scene, ptr<float>(nullptr), ptr<float>(nullptr), ptr<float>(nullptr), width, height, nsx, nsy, seed0 + it,
+                       ptr<float>(nullptr), ptr<float>(dimg), ptr<float>(nullptr), ptr<float>(nullptr), false, ptr<float>(nullptr), 0);
+                std::fill(grads.begin(), grads.end(), 0.f);
+                read_grads(topo, *rs->scene, grads.data());
+            }
+            auto t1 = std::chrono::steady_clock::now();
+            if (it >= warmup) total += std::chrono::duration<double, std::milli>(t1 - t0).count();
+        }
+        if (image_out) cudaMemcpy(image_out, img, npx * 4, cudaMemcpyDeviceToHost);
+        if (d_params_out) memcpy(d_params_out, grads.data(), grads.size() * 4);
+        cudaFree(img); cudaFree(dimg);
+        *ms_per_step = total / (steps > 0 ? steps : 1);
+        return 0;
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        return 1;
+    }
+}
+#endif

@@ -96,3 +96,32 @@ def scene_dump(topo, params, what, index=0, cap=1 << 22):
     if n < 0:
         raise RuntimeError(lib.dvgref_last_error().decode())
     return buf[:n].copy()
+
+
+def cuda_available():
+    return os.path.exists(os.path.join(_HERE, '_ref', 'diffvg_cuda.so'))
+
+
+def cuda_bench(topo, params, width, height, nsx, nsy, seed0, d_render_image, warmup, steps):
+    """Times the reference's own CUDA path (oracle/_ref/diffvg_cuda.so, `make -C oracle ref_cuda`): per step
+    Scene() + forward render + Scene() + backward render on the GPU.  -> (ms_per_step, image, d_params)."""
+    lib = _libs.get('cuda')
+    if lib is None:
+        lib = ctypes.CDLL(os.path.join(_HERE, '_ref', 'diffvg_cuda.so'))
+        fp = ctypes.POINTER(ctypes.c_float)
+        lib.dvgref_cuda_bench.argtypes = [ctypes.POINTER(ctypes.c_int32), fp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                          ctypes.c_uint64, fp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double), fp, fp]
+        lib.dvgref_cuda_bench.restype = ctypes.c_int
+        lib.dvgref_last_error.restype = ctypes.c_char_p
+        _libs['cuda'] = lib
+    topo = np.ascontiguousarray(topo, dtype=np.int32)
+    params = np.ascontiguousarray(params, dtype=np.float32)
+    d_img = np.ascontiguousarray(d_render_image, dtype=np.float32)
+    image = np.zeros((height, width, 4), np.float32)
+    d_params = np.zeros(params.shape[0], np.float32)
+    ms = ctypes.c_double()
+    rc = lib.dvgref_cuda_bench(topo.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), _f(params), width, height, nsx, nsy,
+                               int(seed0), _f(d_img), int(warmup), int(steps), ctypes.byref(ms), _f(image), _f(d_params))
+    if rc != 0:
+        raise RuntimeError(lib.dvgref_last_error().decode())
+    return ms.value, image, d_params

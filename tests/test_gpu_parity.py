@@ -39,8 +39,8 @@ def grad_close(ref, got, rel=GRAD_REL_L2, topo=None):
         assert abs(ref[i] - got[i]) <= 2e-2 * abs(ref[i]) + 1e-12, 'd_filter.radius %g vs %g' % (ref[i], got[i])
         ref[i] = got[i] = 0.0
     assert util.rel_l2(ref, got) <= rel, 'rel-L2 %g' % util.rel_l2(ref, got)
-    floor = 1e-3 * np.abs(ref).max()
-    assert (np.abs(ref - got) <= 1e-3 * np.abs(ref) + floor).all()
+    floor = 1e-3 * np.abs(ref).max()   # |delta| <= 1e-4 |g| + 1e-3 max|g|
+    assert (np.abs(ref - got) <= 1e-4 * np.abs(ref) + floor).all()
 
 
 @pytest.mark.parametrize('path', GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
@@ -148,6 +148,59 @@ def test_painterly_c3_full_size_vs_oracle():
     from diffvg_b200 import scene_pack
     i = int(topo[scene_pack.H_FRAD_OFF])
     assert abs(eb['d_params'][i] - gb['d_params'][i]) <= 1e-4 * abs(eb['d_params'][i])
+
+
+@pytest.mark.parametrize('seed', range(16))
+def test_painterly_256_seed_sweep_vs_oracle(seed):
+    """The closest-point quintic is evaluated with FMA Horner steps, one reciprocal instead of five divisions and
+    float-seeded isolator roots (-DDVG_FMA_QUINTIC): deviations from the reference's arithmetic
+    INSIDE a predicate.  Sixteen sample sets of 1 M samples each (x ~5 exact cubic tests per sample) on the C3 scene:
+    not one sample may classify differently (a flip moves a pixel by 1/16 >> 1e-5)."""
+    topo, params = util.pack(scenes.painterly())
+    ref = oracle_check.render(topo, params, 256, 256, 4, 4, seed)['image']
+    got = util.gpu_render(topo, params, 256, 256, 4, 4, seed)['image']
+    d = np.abs(ref - got)
+    assert d.max() <= FWD_TOL, 'seed %d: %d pixels differ, max %g' % (seed, (d.max(axis=2) > FWD_TOL).sum(), d.max())
+
+
+def test_packed_params_api_matches_stock_api():
+    """pydiffvg.PackedParams (five leaves in the renderer's layout) against the per-tensor serialize_scene path:
+    same image, same gradients on every parameter kind, holders follow an optimiser step."""
+    from diffvg_b200 import pydiffvg
+    pydiffvg.set_use_gpu(True)
+    pydiffvg.set_device(torch.device('cuda', 0))
+    target = torch.rand(128, 128, 4, generator=torch.Generator().manual_seed(3)).cuda()
+    cw, ch, shapes, groups = scenes.painterly(96, 128)
+    leaves = [s.points.requires_grad_(True) for s in shapes] + [s.stroke_width.requires_grad_(True) for s in shapes] + \
+        [g.stroke_color.requires_grad_(True) for g in groups]
+    args = pydiffvg.RenderFunction.serialize_scene(cw, ch, shapes, groups)
+    img0 = pydiffvg.RenderFunction.apply(128, 128, 2, 2, 5, None, *args)
+    (img0 - target).pow(2).mean().backward()
+    g_pts = torch.cat([s.points.grad.reshape(-1) for s in shapes])
+    g_w = torch.stack([s.stroke_width.grad for s in shapes])
+    g_c = torch.cat([g.stroke_color.grad for g in groups])
+    for t in leaves:
+        t.requires_grad_(False)
+    pp = pydiffvg.PackedParams(cw, ch, shapes, groups, device=torch.device('cpu'))   # host leaves: H2D inside apply
+    img1 = pydiffvg.RenderFunction.apply(128, 128, 2, 2, 5, None, *pp.scene_args())
+    assert torch.equal(img0.detach(), img1.detach())
+    (img1 - target).pow(2).mean().backward()
+    assert pp.points.grad.device.type == 'cpu'
+    for a, b in ((g_pts, pp.points.grad), (g_w, pp.scalars.grad), (g_c, pp.colors.grad)):
+        assert util.rel_l2(a.numpy(), b.numpy()) <= 1e-5    # float-atomic order noise between two runs
+    assert pp.transforms.grad is None
+    opt = torch.optim.Adam(pp.parameters(), lr=0.1)
+    before = shapes[0].points.clone()
+    opt.step()
+    assert not torch.equal(before, shapes[0].points)          # the holder is a view of the stepped leaf
+    img2 = pydiffvg.RenderFunction.apply(128, 128, 2, 2, 5, None, *pp.scene_args())
+    assert not torch.equal(img1.detach(), img2.detach())
+    # leaves on the GPU work the same way
+    pp2 = pydiffvg.PackedParams(cw, ch, shapes, groups, device=torch.device('cuda', 0))
+    img3 = pydiffvg.RenderFunction.apply(128, 128, 2, 2, 5, None, *pp2.scene_args())
+    assert torch.equal(img2.detach(), img3.detach())
+    (img3 - target).pow(2).mean().backward()
+    assert pp2.points.grad.is_cuda and torch.isfinite(pp2.points.grad).all()
 
 
 def test_pydiffvg_api_single_circle_gradients():
