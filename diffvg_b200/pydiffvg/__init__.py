@@ -3,6 +3,7 @@
 from .device import *  # noqa: F401,F403
 from .shape import *  # noqa: F401,F403
 from .pixel_filter import *  # noqa: F401,F403
+from .diffvg_enums import FilterType, ShapeType, ColorType  # noqa: F401  (the reference keeps these in its pybind module `diffvg`)
 from .render_pytorch import *  # noqa: F401,F403
 from .image import *  # noqa: F401,F403
 from .parse_svg import *  # noqa: F401,F403
