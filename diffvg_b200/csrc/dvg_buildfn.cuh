@@ -48,7 +48,9 @@ DVG_HD_NOINLINE void build_shape(const BuildView &bv, int s) {
             break;
         case DVG_SHAPE_ELLIPSE: {
             float a = p[0], b = p[1];
-            len += pi_f * (3 * (a + b) - sqrtf((3 * a + b) * (a + 3 * b)));
+            // scene.cpp:130: the unqualified sqrt is ::sqrt(double), so the difference and the product with float(M_PI)
+            // are formed in double and rounded once, by the += into the float length
+            len = (float)((double)len + (double)pi_f * ((double)(3 * (a + b)) - sqrt((double)((3 * a + b) * (a + 3 * b)))));
             box.x0 = p[2] - p[0]; box.y0 = p[3] - p[1]; box.x1 = p[2] + p[0]; box.y1 = p[3] + p[1];
             break;
         }

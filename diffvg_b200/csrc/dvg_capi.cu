@@ -793,6 +793,32 @@ int dvg_render_backward(DvgScene *s, const float *background, const float *d_ren
 
 int dvg_debug_set_boundary_dump(float *device_buf) { g_debug_out = device_buf; return DVG_OK; }
 
+int dvg_debug_prim_tests(DvgScene *s, int width, int height, int nsx, int nsy, uint64_t seed, int x, int y,
+                         int32_t *out_host, float *pos_host, void *stream) {
+    int rc = check_render_args(s, width, height, nsx, nsy);
+    if (rc) return rc;
+    if (!out_host || !pos_host || x < 0 || y < 0 || x >= width || y >= height) return fail(DVG_ERR_INVALID, "bad argument");
+    DeviceGuard guard(s->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    rc = finish_build(s, st);
+    if (rc) return rc;
+    rc = ensure_bins(s, width, height, nsx * nsy, 0, st, 0, height);
+    if (rc) return rc;
+    RenderArgs ra;
+    memset(&ra, 0, sizeof ra);
+    ra.width = width; ra.height = height; ra.nsx = nsx; ra.nsy = nsy; ra.seed = seed; ra.row_end = height;
+    const size_t n = (size_t)nsx * nsy * s->num_prims;
+    int *d_out = nullptr; float *d_pos = nullptr;
+    CK(cudaMalloc((void **)&d_out, n * 4));
+    CK(cudaMalloc((void **)&d_pos, (size_t)nsx * nsy * 8));
+    launch_debug_prim_tests(s->view(), s->bin_view(), ra, x, y, d_out, d_pos, st);
+    CK(cudaMemcpyAsync(out_host, d_out, n * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(pos_host, d_pos, (size_t)nsx * nsy * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    cudaFree(d_out); cudaFree(d_pos);
+    return DVG_OK;
+}
+
 int dvg_set_fast_stroke_accept(int on) { g_fast_accept = on != 0; return DVG_OK; }
 
 int dvg_profile_enable(int on) {

@@ -5,6 +5,7 @@
 // changes a pixel by 1/spp.
 #pragma once
 #include "dvg_scene.cuh"
+#include "dvg_crmath.cuh"
 
 namespace dvg {
 
@@ -344,6 +345,30 @@ DVG_HD_NOINLINE bool prim_stroke_hit_nocubic(int type, bool approx, F4 p01, F4 p
     return prim_stroke_hit(type, approx, p01, p23, rad, r_shape, pt, decided);
 }
 
+// solve.h:29-59 with T = double, the reference's operation sequence with correctly rounded acos / cos / pow (cold path of
+// the winding test, see prim_winding).
+DVG_HD_NOINLINE int solve_cubic_cr(double a, double b, double c, double d, double t[3]) {
+    if (fabs(a) < 1e-6f) {
+        if (solve_quadratic_d(b, c, d, &t[0], &t[1])) return 2;
+        return 0;
+    }
+    b /= a; c /= a; d /= a;
+    double Q = (b * b - 3 * c) / 9.f;
+    double R = (2 * b * b * b - 9 * b * c + 27 * d) / 54.f;
+    if (R * R < Q * Q * Q) {
+        double theta = cr_acos(R / sqrt(Q * Q * Q));
+        t[0] = -2.f * sqrt(Q) * cr_cos(theta / 3.f) - b / 3.f;
+        t[1] = -2.f * sqrt(Q) * cr_cos((theta + 2.f * DVG_PI_D) / 3.f) - b / 3.f;
+        t[2] = -2.f * sqrt(Q) * cr_cos((theta - 2.f * DVG_PI_D) / 3.f) - b / 3.f;
+        return 3;
+    } else {
+        double A = R > 0 ? -cr_pow13(R + sqrt(R * R - Q * Q * Q)) : cr_pow13(-R + sqrt(R * R - Q * Q * Q));
+        double B = fabs(A) > 1e-6f ? Q / A : 0.0;
+        t[0] = (A + B) - b / 3.0;
+        return 1;
+    }
+}
+
 // winding_number.h:62-156 per leaf type + 9-31, 176-186 for the closed-form shapes.
 DVG_HD_NOINLINE int prim_winding(int type, F4 p01, F4 p23, F2 pt) {
     switch (type) {
@@ -378,14 +403,27 @@ DVG_HD_NOINLINE int prim_winding(int type, F4 p01, F4 p23, F2 pt) {
         case PRIM_CUBIC: {
             F2 p0 = mk2(p01.x, p01.y), p1 = mk2(p01.z, p01.w), p2 = mk2(p23.x, p23.y), p3 = mk2(p23.z, p23.w);
             double t[3];
-            int num_sol = solve_cubic_d((double)(-p0.y + 3 * p1.y - 3 * p2.y + p3.y),
-                                        (double)(3 * p0.y - 6 * p1.y + 3 * p2.y),
-                                        (double)(-3 * p0.y + 3 * p1.y),
-                                        (double)(p0.y - pt.y), t);
-            int w = 0;
+            const double ca = (double)(-p0.y + 3 * p1.y - 3 * p2.y + p3.y), cb = (double)(3 * p0.y - 6 * p1.y + 3 * p2.y),
+                         cc = (double)(-3 * p0.y + 3 * p1.y), cd = (double)(p0.y - pt.y);
+            int num_sol = solve_cubic_d(ca, cb, cc, cd, t);
             // float coefficient * double t: the products are formed in double (winding_number.h:142-149)
             float cx3 = -p0.x + 3 * p1.x - 3 * p2.x + p3.x, cx2 = 3 * p0.x - 6 * p1.x + 3 * p2.x, cx1 = -3 * p0.x + 3 * p1.x;
             float cy3 = -p0.y + 3 * p1.y - 3 * p2.y + p3.y, cy2 = 3 * p0.y - 6 * p1.y + 3 * p2.y, cy1 = -3 * p0.y + 3 * p1.y;
+            // A root within 1e-9 of a decision boundary (t = 0, t = 1, crossing exactly at the sample, horizontal tangent at
+            // the crossing): the verdict hangs on the last bit of acos / cos / pow; solve again with correctly rounded
+            // ones (dvg_crmath.cuh), which is what glibc returns for 99.9% of the arguments
+            bool near = false;
+            for (int j = 0; j < num_sol; j++) {
+                const double tj = t[j];
+                if (fabs(tj) < 1e-9 || fabs(tj - 1.0) < 1e-9) near = true;
+                else if (tj > 0 && tj < 1) {
+                    const double tp = (double)cx3 * tj * tj * tj + (double)cx2 * tj * tj + (double)cx1 * tj + (double)p0.x - (double)pt.x;
+                    const double dy = (double)(3 * cy3) * tj * tj + (double)(2 * cy2) * tj + (double)cy1;
+                    if (fabs(tp) < 1e-9 * (1.0 + fabs((double)pt.x)) || fabs(dy) < 1e-9 * (fabs((double)cy1) + fabs((double)cy2) + fabs((double)cy3))) near = true;
+                }
+            }
+            if (near) num_sol = solve_cubic_cr(ca, cb, cc, cd, t);
+            int w = 0;
             for (int j = 0; j < num_sol; j++) {
                 if (t[j] >= 0 && t[j] <= 1) {
                     double tp = (double)cx3 * t[j] * t[j] * t[j] + (double)cx2 * t[j] * t[j] + (double)cx1 * t[j] +

@@ -88,6 +88,7 @@ size_t bvh_key_words(int total_segs, int num_insts, int num_groups);
 void launch_bvh_build(const BuildView &bv, BvhNode *path_nodes, BvhNode *group_nodes, BvhNode *scene_nodes,
                       unsigned long long *keys, cudaStream_t st);
 
+void launch_debug_prim_tests(const SceneView &sc, const BinView &bins, const RenderArgs &ra, int x, int y, int *out, float *pos, cudaStream_t st);
 void launch_peak_probe(int which, float *out, int iters, cudaStream_t st);
 int edge_samples_per_block();
 void launch_build(const BuildView &bv, cudaStream_t st);

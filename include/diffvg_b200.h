@@ -138,6 +138,12 @@ int dvg_set_fast_stroke_accept(int on);
 /* Test support: when non-NULL, the boundary pass also writes (contrib, hit bits, normal.xy) per boundary
  * sample index into this DEVICE buffer of 4*W*H*spp floats (sample-level parity debugging). */
 int dvg_debug_set_boundary_dump(float *device_buf);
+/* Test support: for every sample of pixel (x, y) and EVERY primitive of the scene (no culling), the exact stroke test and
+ * winding contribution as the device computes them: out_host[s * num_prims + e] = hit (bit 0) | group strokes (bit 1) |
+ * group fills (bit 2) | primitive is in the pixel's tile bin (bit 3) | (winding & 0xff) << 8; pos_host[2 s .. 2 s + 1] =
+ * canvas-space sample position.  HOST buffers of nsx*nsy*num_prims ints and 2*nsx*nsy floats.  Synchronises `stream`. */
+int dvg_debug_prim_tests(DvgScene *scene, int width, int height, int num_samples_x, int num_samples_y, uint64_t seed,
+                         int x, int y, int32_t *out_host, float *pos_host, void *stream);
 int64_t dvg_profile_report(char *buf, int64_t cap);
 int dvg_measure_peak(int which, int device, double *tflops);
 

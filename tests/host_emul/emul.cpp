@@ -366,6 +366,47 @@ EXPORT int64_t emul_scene_dump(const int32_t *topo, const float *params, int wha
     return (int64_t)w.size();
 }
 
+// Counterpart of dvg_debug_prim_tests (csrc/dvg_debug.cu): the same raw per-primitive predicates on the host.
+EXPORT void emul_debug_prim_tests(const int32_t *topo, const float *params, int W, int H, int nsx, int nsy, uint64_t seed, int x, int y,
+                                  int32_t *out, float *pos) {
+    HostScene hs;
+    build(hs, topo, params);
+    const SceneView &sc = hs.sc;
+    for (int s = 0; s < nsx * nsy; s++) {
+        const int sx = s % nsx, sy = s / nsx;
+        const int idx = ((y * W + x) * nsy + sy) * nsx + sx;
+        F2 pt, cpt;
+        sample_position(sc.canvas_w, sc.canvas_h, W, H, nsx, nsy, seed, false, x, y, sx, sy, idx, pt, cpt);
+        pos[2 * s] = cpt.x; pos[2 * s + 1] = cpt.y;
+        for (int e = 0; e < sc.num_prims; e++) {
+            const PrimMeta pm = sc.prim_meta[e];
+            const InstInfo &ii = sc.insts[pm.inst];
+            const GroupInfo &g = sc.groups[ii.group];
+            const F2 lp = (g.flags & DVG_GF_IDENTITY) ? cpt : xform_pt(g.c2s, cpt);
+            const int type = pm.type_flags & DVG_PF_TYPE_MASK;
+            int r = 0;
+            if (g.stroke_type >= 0) {
+                bool decided = false;
+                r |= 2;
+                if (type != PRIM_ELLIPSE && prim_stroke_hit(type, (pm.type_flags & DVG_PF_APPROX) != 0, sc.prim_p01[e], sc.prim_p23[e], sc.prim_rad[e], ii.r, lp, &decided)) r |= 1;
+            }
+            if (g.fill_type >= 0) {
+                r |= 4;
+                r |= (prim_winding(type, sc.prim_p01[e], sc.prim_p23[e], lp) & 0xff) << 8;
+            }
+            out[(size_t)s * sc.num_prims + e] = r;
+        }
+    }
+}
+
+// dvg_crmath.cuh on the host, for the accuracy test against 200-bit arithmetic (which: 0 cos, 1 acos, 2 pow(x, 1./3.))
+EXPORT void emul_crmath(int which, const double *x, double *y, int n) {
+    for (int i = 0; i < n; i++) y[i] = which == 0 ? cr_cos(x[i]) : (which == 1 ? cr_acos(x[i]) : cr_pow13(x[i]));
+}
+EXPORT int emul_solve_cubic(int accurate, double a, double b, double c, double d, double *t) {
+    return accurate ? solve_cubic_cr(a, b, c, d, t) : solve_cubic_d(a, b, c, d, t);
+}
+
 // PCG known-answer helper: state after init and the first two floats.
 // Test support for the tight tile binning (dvg_buildfn.cuh bracket_reaches_tile): brackets of one cubic stroke,
 // the tile test, and the per-point bracket classification the kernels use.

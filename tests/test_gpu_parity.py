@@ -183,7 +183,7 @@ def test_packed_params_api_matches_stock_api():
         t.requires_grad_(False)
     pp = pydiffvg.PackedParams(cw, ch, shapes, groups, device=torch.device('cpu'))   # host leaves: H2D inside apply
     img1 = pydiffvg.RenderFunction.apply(128, 128, 2, 2, 5, None, *pp.scene_args())
-    assert torch.equal(img0.detach(), img1.detach())
+    assert (img0.detach() - img1.detach()).abs().max() <= 1e-6   # float atomics of the splat: order noise only
     (img1 - target).pow(2).mean().backward()
     assert pp.points.grad.device.type == 'cpu'
     for a, b in ((g_pts, pp.points.grad), (g_w, pp.scalars.grad), (g_c, pp.colors.grad)):
@@ -198,7 +198,7 @@ def test_packed_params_api_matches_stock_api():
     # leaves on the GPU work the same way
     pp2 = pydiffvg.PackedParams(cw, ch, shapes, groups, device=torch.device('cuda', 0))
     img3 = pydiffvg.RenderFunction.apply(128, 128, 2, 2, 5, None, *pp2.scene_args())
-    assert torch.equal(img2.detach(), img3.detach())
+    assert (img2.detach() - img3.detach()).abs().max() <= 1e-6
     (img3 - target).pow(2).mean().backward()
     assert pp2.points.grad.is_cuda and torch.isfinite(pp2.points.grad).all()
 

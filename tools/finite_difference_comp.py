@@ -46,14 +46,25 @@ def finite_difference_comp(scene, w, h, num_spp=4, use_prefiltering=False, epsil
                                                        use_prefiltering=use_prefiltering)
         return pydiffvg.RenderFunction.apply(w, h, nsx, nsy, seed, None, *args), args
 
+    def moved_tensors():
+        out = []
+        for s in shapes:
+            out += [getattr(s, a) for a in ('center', 'points', 'p_min', 'p_max') if hasattr(s, a)]
+        for g in shape_groups:
+            if isinstance(g.fill_color, pydiffvg.LinearGradient):
+                out += [g.fill_color.begin, g.fill_color.end]
+        return out
+
     fd = []
     with torch.no_grad():
+        saved = [t.clone() for t in moved_tensors()]
         for axis in (0, 1):
             perturb_scene(pydiffvg, shapes, shape_groups, axis, epsilon)
             img0, _ = render()
             perturb_scene(pydiffvg, shapes, shape_groups, axis, -2 * epsilon)
             img1, _ = render()
-            perturb_scene(pydiffvg, shapes, shape_groups, axis, epsilon)
+            for t, t0 in zip(moved_tensors(), saved):   # the reference adds +epsilon back, which leaves the scene an ulp off
+                t.copy_(t0)
             fd.append(((img0 - img1) / (2 * epsilon)).sum(dim=2))
         _, args = render()
         grad = pydiffvg.RenderFunction.render_grad(torch.ones(h, w, 4, device=pydiffvg.get_device()), w, h, nsx, nsy, seed, None, *args)
