@@ -14,13 +14,13 @@ ONE gradient array of the same layout, so the fast path is to keep the parameter
     for t in range(num_iter):
         optim.zero_grad()
         img = pydiffvg.RenderFunction.apply(w, h, 2, 2, t, None, *pp.scene_args())     # O(1), no scene walk
-        loss(img).backward()                                                           # 5 leaves, not 6144
+        loss(img).backward()                                                           # a handful of leaves, not 6144
         optim.step()
         pp.scalars.data.clamp_(1.0, max_width)     # the holders see every update: they are views
 
 One leaf per KIND of parameter (all path points / all scalar stroke widths / all constant colours / the
-transforms / everything else: per-point thickness, circle, ellipse, rect and gradient-colour parameters,
-the pixel-filter radius), so that the usual per-kind learning rates stay one optimiser group each.
+transforms / everything else: per-point thickness, circle, ellipse, rect and gradient-colour parameters /
+the pixel-filter radius; the last two kinds of leaves do not require a gradient unless asked to), so that the usual per-kind learning rates stay one optimiser group each.
 The stock `serialize_scene` path is unchanged and accepts these holders too (it just gathers the views).
 """
 import numpy as np
@@ -37,7 +37,7 @@ class PackedParams:
     def __init__(self, canvas_width, canvas_height, shapes, shape_groups,
                  filter=None, device=None, requires_grad=True):
         """Packs the scene once (same walk and validation as `serialize_scene`), moves every parameter into one of
-        five flat leaf tensors and replaces the holders' tensor attributes by views into them.  `device`: where the
+        six flat leaf tensors and replaces the holders' tensor attributes by views into them.  `device`: where the
         leaves live (default: where the first parameter tensor lives; CPU leaves are uploaded per iteration as one
         pinned copy).  The topology (shape counts, segment types, which colours are gradients, ...) is frozen."""
         if filter is None:
@@ -83,6 +83,7 @@ class PackedParams:
             if leaf.numel():
                 leaf.requires_grad_(requires_grad)
         self.leaves[scene_pack.B_MAT3].requires_grad_(False)   # opt in: every boundary sample adds 9 terms to its group's transform
+        self.leaves[scene_pack.B_FILTER].requires_grad_(False)   # opt in (apps/optimize_pixel_filter.py)
         self.num_params = int(topo[scene_pack.H_NPARAMS])
         assert sum(l.numel() for l in self.leaves) == self.num_params
 
@@ -92,7 +93,8 @@ class PackedParams:
     colors = property(lambda self: self.leaves[scene_pack.B_VEC4], doc='constant fill / stroke colours, flat [4 * n]')
     transforms = property(lambda self: self.leaves[scene_pack.B_MAT3], doc='shape_to_canvas matrices, flat [9 * n]; requires_grad off by default')
     others = property(lambda self: self.leaves[scene_pack.B_GENERIC],
-                      doc='per-point thickness, circle / ellipse / rect parameters, gradient-colour parameters, the pixel-filter radius')
+                      doc='per-point thickness, circle / ellipse / rect parameters, gradient-colour parameters')
+    filter_radius = property(lambda self: self.leaves[scene_pack.B_FILTER], doc='the pixel-filter radius [1]; requires_grad off by default')
 
     def parameters(self):
         """The non-empty leaves that require a gradient (what to hand to an optimiser)."""

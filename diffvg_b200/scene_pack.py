@@ -40,7 +40,7 @@ _OPEN_FILL_WARNING = 'Detected non-closed paths with fill color. This might caus
 # A tensor OBJECT that occurs several times (typically the default `shape_to_canvas`
 # torch.eye(3) shared by every ShapeGroup) is stored once; autograd then sums the gradients
 # of all its uses, which is exactly what sharing a tensor means.
-B_POINTS, B_SCALAR, B_VEC4, B_MAT3, B_GENERIC, NUM_BUCKETS = 0, 1, 2, 3, 4, 5
+B_POINTS, B_SCALAR, B_VEC4, B_MAT3, B_GENERIC, B_FILTER, NUM_BUCKETS = 0, 1, 2, 3, 4, 5, 6
 SRC_SHAPE, SRC_GROUP, SRC_FILTER = 0, 1, 2
 
 
@@ -222,9 +222,9 @@ def _pack_scene_full(canvas_width, canvas_height, shapes, shape_groups, filter_t
 
     fr = filter_radius if filter_radius is not None else torch.tensor(0.5)
     bk.at(SRC_FILTER, 0)
-    # with "everything else", not with the stroke widths: an optimiser stepping the scalar bucket of a PackedParams
-    # must not move the pixel filter along
-    frb, froff = B_GENERIC, bk.add_generic(fr, 1, None)
+    # a bucket of its own (the last float of `params`): an optimiser stepping the stroke widths or the other leaves of a
+    # PackedParams must not move the pixel filter along
+    frb, froff = B_FILTER, bk.add(B_FILTER, fr if isinstance(fr, torch.Tensor) else torch.as_tensor(fr, dtype=torch.float32), 1, None)
 
     # bucket bases in the final concatenation order
     base = [0] * NUM_BUCKETS
@@ -427,7 +427,7 @@ def _flatten_bucket(bucket, tensors, device):
         if bucket == B_POINTS:
             return torch.cat(tensors, dim=0).reshape(-1).to(device=device, dtype=torch.float32)
         if bucket != B_GENERIC:
-            return torch.stack(tensors).reshape(-1).to(device=device, dtype=torch.float32)
+            return torch.stack([t.reshape(()) if bucket in (B_SCALAR, B_FILTER) else t for t in tensors]).reshape(-1).to(device=device, dtype=torch.float32)
     except (RuntimeError, TypeError):
         pass
     return torch.cat([t.to(device=device, dtype=torch.float32).reshape(-1) for t in tensors])

@@ -41,9 +41,9 @@ def test_leaves_by_kind_and_in_place_clamp():
     pp = pydiffvg.PackedParams(cw, ch, shapes, groups)
     assert pp.points.numel() == sum(2 * s.points.shape[0] for s in shapes)
     assert pp.scalars.numel() == 32 and pp.colors.numel() == 4 * 32 and pp.transforms.numel() == 9
-    assert pp.others.numel() == 1                      # the pixel-filter radius: not with the stroke widths
-    assert [l.requires_grad for l in pp.leaves] == [True, True, True, False, True]
-    assert len(pp.parameters()) == 4
+    assert pp.others.numel() == 0 and pp.filter_radius.numel() == 1      # the pixel-filter radius: a leaf of its own
+    assert [l.requires_grad for l in pp.leaves] == [True, True, True, False, False, False]
+    assert len(pp.parameters()) == 3
     shapes[3].stroke_width.data.clamp_(0.0, 0.25)      # painterly_rendering.py clamps through the holders
     assert float(pp.scalars.detach()[3]) == 0.25
     with torch.no_grad():

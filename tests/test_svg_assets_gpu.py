@@ -66,13 +66,19 @@ def test_tiger_c2_full_size_vs_oracle():
     ones = np.ones((H, W, 4), np.float32)
     rb = oracle_check.render(topo, params, W, H, 4, 4, 0, d_render_image=ones, want_d_translation=True)
     gb = util.gpu_render(topo, params, W, H, 4, 4, 0, d_render_image=ones, want_d_translation=True)
+    # d_filter.radius: with d_image = 1 every one of the 4 M samples adds a term of the same sign and the reference's
+    # sequential float sum stops growing at exactly -2^23 (the terms fall below half an ulp); not comparable
+    from diffvg_b200 import scene_pack
+    i = int(topo[scene_pack.H_FRAD_OFF])
+    assert rb['d_params'][i] == -2.0 ** 23 and gb['d_params'][i] < -2.0 ** 23
+    rb['d_params'][i] = gb['d_params'][i] = 0.0
     assert util.rel_l2(rb['d_params'], gb['d_params']) <= 1e-4
     assert util.rel_l2(rb['d_translation'], gb['d_translation']) <= 1e-4
     # a loss-like d_image as well (the ones image cancels most interior terms)
     d_img = np.random.RandomState(3).rand(H, W, 4).astype(np.float32) - 0.5
     rb = oracle_check.render(topo, params, W, H, 4, 4, 0, d_render_image=d_img)
     gb = util.gpu_render(topo, params, W, H, 4, 4, 0, d_render_image=d_img)
-    assert util.rel_l2(rb['d_params'], gb['d_params']) <= 1e-4
+    _radius_apart(topo, rb['d_params'], gb['d_params'], 0.1)
 
 
 @needs_ref
@@ -104,7 +110,7 @@ def test_flower_sampled_512_vs_oracle():
     d_img = np.random.RandomState(5).rand(H, W, 4).astype(np.float32) - 0.5
     rb = oracle_check.render(topo, params, W, H, 2, 2, 1, d_render_image=d_img)
     gb = util.gpu_render(topo, params, W, H, 2, 2, 1, d_render_image=d_img)
-    assert util.rel_l2(rb['d_params'], gb['d_params']) <= 1e-4
+    _radius_apart(topo, rb['d_params'], gb['d_params'], 0.1)
 
 
 def test_flower_c4_2048_2x2_properties():
@@ -116,7 +122,7 @@ def test_flower_c4_2048_2x2_properties():
     assert np.isfinite(a).all() and a[:, :, 3].max() <= 1.0 + 1e-5
     rows = util.gpu_render_rows(topo, params, W, H, 2, 2, 0, [(0, 512), (512, 1536), (1536, 2048)], use_prefiltering=True)['image']
     assert np.abs(rows - a).max() <= 1e-6
-    d_img = (np.random.RandomState(6).rand(H, W, 4).astype(np.float32) - 0.5) / a.size
+    d_img = np.random.RandomState(6).rand(H, W, 4).astype(np.float32) - 0.5
     g1 = util.gpu_render(topo, params, W, H, 2, 2, 0, use_prefiltering=True, d_render_image=d_img)['d_params']
     g2 = util.gpu_render(topo, params, W, H, 2, 2, 0, use_prefiltering=True, d_render_image=2 * d_img)['d_params']
     assert np.isfinite(g1).all()
