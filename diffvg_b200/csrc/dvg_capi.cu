@@ -20,6 +20,8 @@ namespace {
 
 thread_local std::string g_err;
 float *g_debug_out = nullptr;  // dvg_debug_set_boundary_dump
+long long g_debug_edge_pass_samples = 0;   // dvg_debug_set_limits
+long long g_debug_pair_capacity = 0;
 bool g_fast_accept = getenv("DVG_FAST_ACCEPT") != nullptr && getenv("DVG_FAST_ACCEPT")[0] == '1';   // dvg_set_fast_stroke_accept (env: measurements only)
 // A/B switch for measurements: DVG_FUSED=1 in the environment selects the one-kernel-per-pass form of
 // dvg_render.cu instead of the wavefront passes of dvg_wave.cu (same arithmetic, same results).
@@ -97,9 +99,14 @@ struct DvgScene {
     int32_t *h_pinned = nullptr;  // [0] error flag, [1] total bin items
     float *h_params_pinned = nullptr;  // staging for host-resident params (true async H2D)
     cudaEvent_t h_params_free = nullptr;  // recorded after the H2D copy that last read the staging buffer
+    int32_t *h_counts = nullptr;         // pinned [2][4]: the wave counters of the last pixel / boundary pass (pair-queue feedback)
+    cudaEvent_t ev_counts[2] = {nullptr, nullptr};
+    bool counts_pending[2] = {false, false};
+    int64_t want_s = 0, want_f = 0;      // most pairs any pass of this scene asked for so far
     bool params_set = false;
     bool checked = false;
     int scene_error = 0;
+    std::string scene_error_msg;
     float filter_radius_host = 0.5f;  // refreshed with the error-flag read-back
 
     BuildView build_view() {
@@ -161,6 +168,9 @@ struct DvgScene {
         h_params_pinned = nullptr;
         if (h_params_free) cudaEventDestroy(h_params_free);
         h_params_free = nullptr;
+        if (h_counts) cudaFreeHost(h_counts);
+        h_counts = nullptr;
+        for (int k = 0; k < 2; k++) { if (ev_counts[k]) cudaEventDestroy(ev_counts[k]); ev_counts[k] = nullptr; }
     }
 };
 
@@ -249,14 +259,10 @@ void choose_tile(int spp, int *tw, int *th) {
     else { *tw = 16; *th = 16; }
 }
 
-// Synchronise once after the build to learn (a) whether the scene is degenerate
-// (scene.cpp:231-240 throws) and (b) the filter radius / bin size needed by later launches.
-int finish_build(DvgScene *s, cudaStream_t st) {
-    if (s->checked) return s->scene_error ? fail(DVG_ERR_SCENE, g_err) : DVG_OK;
-    CK(cudaMemcpyAsync(s->h_pinned, s->d_flags.p, 8, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(s->h_pinned + 2, s->d_params.as<float>() + s->topo[DVG_H_FILTER_RADIUS_OFF], 4,
-                       cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+// After the build the host needs (a) whether the scene is degenerate (scene.cpp:231-240 throws) and (b) the filter
+// radius.  Both are read back together with the bin totals by ensure_bins -- ONE synchronisation per set_params, early
+// in the forward pass -- or here when no bins are needed (SDF output) or they are sized for the worst case.
+int parse_build_flags(DvgScene *s) {
     s->checked = true;
     s->scene_error = s->h_pinned[0];
     float total; memcpy(&total, &s->h_pinned[1], 4);
@@ -267,9 +273,25 @@ int finish_build(DvgScene *s, cudaStream_t st) {
             snprintf(buf, sizeof buf, "The total length of the shape boundaries in the scene is equal or less than 0. Length = %f", total);
         else
             snprintf(buf, sizeof buf, "The total length of the shape boundaries in the scene is not a number. Length = %f", total);
+        s->scene_error_msg = buf;
         return fail(DVG_ERR_SCENE, buf);
     }
     return DVG_OK;
+}
+
+int queue_build_flags(DvgScene *s, cudaStream_t st) {
+    CK(cudaMemcpyAsync(s->h_pinned, s->d_flags.p, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(s->h_pinned + 2, s->d_params.as<float>() + s->topo[DVG_H_FILTER_RADIUS_OFF], 4,
+                       cudaMemcpyDeviceToHost, st));
+    return DVG_OK;
+}
+
+int finish_build(DvgScene *s, cudaStream_t st) {
+    if (s->checked) return s->scene_error ? fail(DVG_ERR_SCENE, s->scene_error_msg) : DVG_OK;
+    int rc = queue_build_flags(s, st);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(st));
+    return parse_build_flags(s);
 }
 
 constexpr int64_t kSmallBins = 1 << 20;    // tiles x primitives below which bins are sized for the worst case
@@ -278,13 +300,14 @@ constexpr int64_t kSmallPairs = 1 << 21;   // worst-case exact tests of a pass b
 // `row_begin, row_end`: pixel rows the caller will render.  The prefiltered path has no boundary pass, so a row shard
 // only ever looks at the tiles of its own rows and only those are binned (at 8 GPUs binning the whole 2048^2 image
 // on every rank was 10% of the step); the boundary pass of the sampled path lands anywhere, so it bins everything.
+// Also completes the scene build (finish_build) with the same synchronisation.
 int ensure_bins(DvgScene *s, int width, int height, int spp, int pf, cudaStream_t st, int row_begin, int row_end) {
     int tw, th;
     choose_tile(spp, &tw, &th);
     const int tiles_y_all = (height + th - 1) / th;
     const int r0 = pf ? row_begin / th : 0, r1 = pf ? std::min(tiles_y_all, (row_end + th - 1) / th) : tiles_y_all;
     if (s->bin_w == width && s->bin_h == height && s->bin_tw == tw && s->bin_th == th && s->bin_pf == pf &&
-        s->bin_r0 <= r0 && s->bin_r1 >= r1) return DVG_OK;
+        s->bin_r0 <= r0 && s->bin_r1 >= r1) return finish_build(s, st);
     BinBuild bb;
     bb.width = width; bb.height = height; bb.tile_w = tw; bb.tile_h = th; bb.prefilter = pf;
     bb.flat = s->num_prims <= 4 * s->num_groups ? 1 : 0;
@@ -316,18 +339,24 @@ int ensure_bins(DvgScene *s, int width, int height, int spp, int pf, cudaStream_
     const int64_t nbin = (int64_t)(r1 - r0) * bb.tiles_x;
     if (nbin * s->num_prims <= kSmallBins) {
         // small scene (batched 64x64 scenes, single shapes): size everything for the worst case -- every primitive in
-        // every tile -- and skip the read-back, so that the whole iteration stays asynchronous
+        // every tile -- and skip the read-back of the totals
         total = (int)(nbin * s->num_prims);
         s->max_nch = (s->num_prims + 31) / 32;
         s->total_chunks = (int)nbin * s->max_nch;
+        int rc = finish_build(s, st);
+        if (rc) return rc;
     } else {
+        const bool flags_too = !s->checked;
+        if (flags_too) { int rc = queue_build_flags(s, st); if (rc) return rc; }
         CK(cudaMemcpyAsync(s->h_pinned + 3, bb.offsets + ntiles, 4, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(s->h_pinned + 4, s->d_tile_choff.as<int>() + ntiles, 4, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(s->h_pinned + 5, s->d_wave_max.p, 4, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
+        CK(cudaStreamSynchronize(st));   // the one synchronisation of an iteration
         total = s->h_pinned[3];
         s->total_chunks = s->h_pinned[4];
         s->max_nch = s->h_pinned[5];
+        int rc = flags_too ? parse_build_flags(s) : finish_build(s, st);
+        if (rc) return rc;
     }
     s->wpx_valid = false;
     CK(s->d_bin_items.ensure(sizeof(int) * std::max(total, 1)));
@@ -354,7 +383,22 @@ int ensure_weight(DvgScene *s, const SceneView &sc, RenderArgs &ra, int r0, int 
     return DVG_OK;
 }
 
-// ---- wavefront passes: workspace sizing and the classify -> (count read-back) -> solve sequence
+// ---- wavefront passes: workspace sizing and the classify -> solve sequence.
+// Nothing is read back inside a pass.  The pair queues keep the capacity that earlier passes asked for: every pass copies
+// its counters to pinned memory when it ends, and the next pass -- whenever that copy has landed -- grows a queue that
+// was too small.  A pass that still overflows (the first one of a scene; a sudden change of the geometry) answers the
+// surplus pairs in place (wave_exact_in_place): slower, same results.
+void wave_feedback_poll(DvgScene *s) {
+    for (int slot = 0; slot < 2; slot++) {
+        if (!s->counts_pending[slot] || cudaEventQuery(s->ev_counts[slot]) != cudaSuccess) continue;
+        s->counts_pending[slot] = false;
+        const int32_t *c = s->h_counts + 4 * slot;
+        // a counter that wrapped negative asked for more than 2^31 pairs: keep the in-place path for the surplus
+        s->want_s = std::max<int64_t>(s->want_s, c[0] < 0 ? 0x7fffffff : c[0]);
+        s->want_f = std::max<int64_t>(s->want_f, c[1] < 0 ? 0x7fffffff : c[1]);
+    }
+}
+
 int wave_view(DvgScene *s, int64_t chunk_slots, int64_t evals, WaveView *out) {
     const int64_t words = chunk_slots * 32;
     if (words >= ((int64_t)1 << 27)) return fail(DVG_ERR_UNSUPPORTED, "render too large for the 27-bit result-word index of the pair queue");
@@ -362,15 +406,39 @@ int wave_view(DvgScene *s, int64_t chunk_slots, int64_t evals, WaveView *out) {
     if (s->has_fills) CK(s->d_wave_wind.ensure(sizeof(unsigned) * 4 * (size_t)std::max<int64_t>(words, 1)));
     CK(s->d_wave_counters.ensure(sizeof(int) * 4));
     CK(s->d_edge_choff.ensure(sizeof(int) * 4));   // real size set by the boundary pass
-    // first guess for the pair queues: two exact tests per evaluation; grown on demand (wave_classify_and_solve)
-    if (!s->d_wave_pairs_s.p) CK(s->d_wave_pairs_s.ensure(sizeof(WavePair) * (size_t)std::max<int64_t>(2 * evals, 1 << 16)));
-    if (s->has_fills && !s->d_wave_pairs_f.p) CK(s->d_wave_pairs_f.ensure(sizeof(WavePair) * (size_t)std::max<int64_t>(4 * evals, 1 << 16)));
+    wave_feedback_poll(s);
+    // worst case: every lane of every chunk slot asks for an exact test of all 32 candidates.  Small passes get queues
+    // of that size (they can not overflow); otherwise what earlier passes asked for plus a margin, and for the first pass
+    // a guess of two stroke tests / four winding tests per evaluation
+    const int64_t worst = chunk_slots * 32 * 32;
+    const int64_t lim = (int64_t)1 << 30;
+    int64_t need_s, need_f;
+    if (worst <= kSmallPairs) need_s = need_f = std::max<int64_t>(worst, 1);
+    else {
+        need_s = s->want_s ? s->want_s + s->want_s / 8 + 4096 : std::max<int64_t>(2 * evals, 1 << 16);
+        need_f = s->want_f ? s->want_f + s->want_f / 8 + 4096 : std::max<int64_t>(4 * evals, 1 << 16);
+        need_s = std::min(std::min(need_s, worst), lim);
+        need_f = std::min(std::min(need_f, worst), lim);
+    }
+    if (g_debug_pair_capacity > 0 && worst > kSmallPairs) need_s = need_f = g_debug_pair_capacity;
+    if ((int64_t)(s->d_wave_pairs_s.cap / sizeof(WavePair)) < need_s) CK(s->d_wave_pairs_s.ensure(sizeof(WavePair) * (size_t)need_s));
+    if (s->has_fills && (int64_t)(s->d_wave_pairs_f.cap / sizeof(WavePair)) < need_f) CK(s->d_wave_pairs_f.ensure(sizeof(WavePair) * (size_t)need_f));
     WaveView wv;
-    wv.units_a = wv.units_d = nullptr; wv.cap_ua = wv.cap_ud = 0;
     wv.hit = s->d_wave_hit.as<unsigned>();
     wv.wind = s->has_fills ? s->d_wave_wind.as<unsigned>() : nullptr;
-    wv.pairs_s = s->d_wave_pairs_s.as<WavePair>(); wv.cap_s = (int)std::min<size_t>(s->d_wave_pairs_s.cap / sizeof(WavePair), 0x7fffffff);
-    wv.pairs_f = s->d_wave_pairs_f.as<WavePair>(); wv.cap_f = (int)std::min<size_t>(s->d_wave_pairs_f.cap / sizeof(WavePair), 0x7fffffff);
+    wv.pairs_s = s->d_wave_pairs_s.as<WavePair>(); wv.cap_s = (int)std::min<int64_t>(s->d_wave_pairs_s.cap / sizeof(WavePair), lim);
+    wv.pairs_f = s->d_wave_pairs_f.as<WavePair>(); wv.cap_f = s->has_fills ? (int)std::min<int64_t>(s->d_wave_pairs_f.cap / sizeof(WavePair), lim) : 0;
+    if (g_debug_pair_capacity > 0 && worst > kSmallPairs) {
+        wv.cap_s = (int)std::min<int64_t>(wv.cap_s, g_debug_pair_capacity);
+        wv.cap_f = (int)std::min<int64_t>(wv.cap_f, g_debug_pair_capacity);
+    }
+    // root-bracket queues of the cubic pairs: 1.5 ascending / 0.75 descending brackets per pair cover every scene
+    // measured (1.0 / 0.25 at the painterly config); a fuller queue is answered in place by W2a
+    wv.cap_ua = (int)std::min<int64_t>((int64_t)wv.cap_s + wv.cap_s / 2 + 1024, lim);
+    wv.cap_ud = (int)std::min<int64_t>((int64_t)wv.cap_s - wv.cap_s / 4 + 1024, lim);
+    CK(s->d_wave_units_a.ensure(sizeof(WaveUnit) * (size_t)wv.cap_ua));
+    CK(s->d_wave_units_d.ensure(sizeof(WaveUnit) * (size_t)wv.cap_ud));
+    wv.units_a = s->d_wave_units_a.as<WaveUnit>(); wv.units_d = s->d_wave_units_d.as<WaveUnit>();
     wv.counters = s->d_wave_counters.as<int>();
     wv.tile_choff = s->d_tile_choff.as<int>();
     wv.edge_choff = s->d_edge_choff.as<int>();
@@ -378,62 +446,20 @@ int wave_view(DvgScene *s, int64_t chunk_slots, int64_t evals, WaveView *out) {
     return DVG_OK;
 }
 
-// Runs `classify` (W1), reads the two pair counts back (the one synchronisation of a pass), grows a queue and
-// repeats W1 if it overflowed, then launches the exact tests (W2).
+// Runs `classify` (W1) and the exact tests (W2); `slot`: 0 pixel pass, 1 boundary pass (where its counters are parked).
 template <typename Classify>
-int wave_classify_and_solve(DvgScene *s, const SceneView &sc, WaveView &wv, int64_t chunk_slots, cudaStream_t st,
-                            const Classify &classify) {
-    // worst case: every lane of every chunk slot asks for an exact test of all 32 candidates
-    const int64_t worst = chunk_slots * 32 * 32;
-    if (worst <= kSmallPairs) {
-        // small pass: queues sized for the worst case can not overflow, so nothing is read back; the solve kernels
-        // cover the capacity and take the actual counts from device memory
-        const int cap = (int)std::max<int64_t>(worst, 1);
-        CK(s->d_wave_pairs_s.ensure(sizeof(WavePair) * (size_t)cap));
-        if (s->has_fills) CK(s->d_wave_pairs_f.ensure(sizeof(WavePair) * (size_t)cap));
-        wv.pairs_s = s->d_wave_pairs_s.as<WavePair>(); wv.cap_s = cap;
-        wv.pairs_f = s->d_wave_pairs_f.as<WavePair>(); wv.cap_f = s->has_fills ? cap : 0;
-        wv.cap_ua = cap + cap / 2 + 1024; wv.cap_ud = cap - cap / 4 + 1024;
-        CK(s->d_wave_units_a.ensure(sizeof(WaveUnit) * (size_t)wv.cap_ua));
-        CK(s->d_wave_units_d.ensure(sizeof(WaveUnit) * (size_t)wv.cap_ud));
-        wv.units_a = s->d_wave_units_a.as<WaveUnit>(); wv.units_d = s->d_wave_units_d.as<WaveUnit>();
-        CK(cudaMemsetAsync(wv.counters, 0, sizeof(int) * 2, st));
-        classify(wv);
-        CK(cudaGetLastError());
-        launch_wave_solve(sc, wv, -1, s->has_fills ? -1 : 0, st);
-        CK(cudaGetLastError());
-        return DVG_OK;
+int wave_classify_and_solve(DvgScene *s, const SceneView &sc, WaveView &wv, int slot, cudaStream_t st, const Classify &classify) {
+    CK(cudaMemsetAsync(wv.counters, 0, sizeof(int) * 2, st));
+    classify(wv);
+    CK(cudaGetLastError());
+    launch_wave_solve(sc, wv, true, s->has_fills, st);
+    CK(cudaGetLastError());
+    if (!s->counts_pending[slot]) {   // an unread copy of an earlier pass is still in flight: skip this one
+        CK(cudaMemcpyAsync(s->h_counts + 4 * slot, wv.counters, sizeof(int) * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaEventRecord(s->ev_counts[slot], st));
+        s->counts_pending[slot] = true;
     }
-    for (int attempt = 0; attempt < 3; attempt++) {
-        CK(cudaMemsetAsync(wv.counters, 0, sizeof(int) * 2, st));
-        classify(wv);
-        CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(s->h_pinned + 6, wv.counters, sizeof(int) * 2, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        const int ns = s->h_pinned[6], nf = s->h_pinned[7];
-        if (ns < 0 || nf < 0) return fail(DVG_ERR_UNSUPPORTED, "more than 2^31 exact tests in one pass");
-        if (ns <= wv.cap_s && nf <= wv.cap_f) {
-            // root-bracket queues of the cubic pairs: 1.5 ascending / 0.75 descending brackets per pair cover every
-            // scene measured (1.0 / 0.25 at the painterly config); a fuller queue is answered inline by W2a
-            wv.cap_ua = (int)std::min<int64_t>((int64_t)ns + ns / 2 + 1024, 0x7fffffff);
-            wv.cap_ud = (int)std::min<int64_t>((int64_t)ns - ns / 4 + 1024, 0x7fffffff);
-            CK(s->d_wave_units_a.ensure(sizeof(WaveUnit) * (size_t)wv.cap_ua));
-            CK(s->d_wave_units_d.ensure(sizeof(WaveUnit) * (size_t)wv.cap_ud));
-            wv.units_a = s->d_wave_units_a.as<WaveUnit>(); wv.units_d = s->d_wave_units_d.as<WaveUnit>();
-            launch_wave_solve(sc, wv, ns, nf, st);
-            CK(cudaGetLastError());
-            return DVG_OK;
-        }
-        if (ns > wv.cap_s) {
-            CK(s->d_wave_pairs_s.ensure(sizeof(WavePair) * (size_t)ns));
-            wv.pairs_s = s->d_wave_pairs_s.as<WavePair>(); wv.cap_s = (int)std::min<size_t>(s->d_wave_pairs_s.cap / sizeof(WavePair), 0x7fffffff);
-        }
-        if (nf > wv.cap_f) {
-            CK(s->d_wave_pairs_f.ensure(sizeof(WavePair) * (size_t)nf));
-            wv.pairs_f = s->d_wave_pairs_f.as<WavePair>(); wv.cap_f = (int)std::min<size_t>(s->d_wave_pairs_f.cap / sizeof(WavePair), 0x7fffffff);
-        }
-    }
-    return fail(DVG_ERR_CUDA, "pair queue kept overflowing");
+    return DVG_OK;
 }
 
 // Pixel pass (forward, or the interior term of the backward pass): the result words of a forward pass are
@@ -450,8 +476,7 @@ int wave_pixel_pass(DvgScene *s, const SceneView &sc, const BinView &bins, const
                        s->wpx_pf == ra.use_prefiltering && s->wpx_fast == fast;
     if (!reuse) {
         s->wpx_valid = false;
-        rc = wave_classify_and_solve(s, sc, wv, (int64_t)s->total_chunks * wpt, st,
-                                     [&](const WaveView &v) { launch_wave_classify_px(sc, bins, ra, v, st); });
+        rc = wave_classify_and_solve(s, sc, wv, 0, st, [&](const WaveView &v) { launch_wave_classify_px(sc, bins, ra, v, st); });
         if (rc) return rc;
         s->wpx_valid = true; s->wpx_w = ra.width; s->wpx_h = ra.height; s->wpx_nsx = ra.nsx; s->wpx_nsy = ra.nsy;
         s->wpx_seed = ra.seed; s->wpx_r0 = ra.row_begin; s->wpx_r1 = ra.row_end; s->wpx_pf = ra.use_prefiltering; s->wpx_fast = fast;
@@ -461,7 +486,8 @@ int wave_pixel_pass(DvgScene *s, const SceneView &sc, const BinView &bins, const
     return DVG_OK;
 }
 
-// Boundary pass (diffvg.cpp:1558-1626).  `bw` comes with its sort buffers bound.
+// Boundary pass (diffvg.cpp:1558-1626) over the boundary-sample indices [bw.sample_begin, + bw.num_samples).  `bw` comes
+// with its sort buffers bound.
 int wave_edge_pass(DvgScene *s, const SceneView &sc, const BinView &bins, const RenderArgs &ra, BoundaryWork &bw, cudaStream_t st) {
     const int ntiles = bins.tiles_x * bins.tiles_y;
     const int spi = wave_edge_samples_per_item();
@@ -479,12 +505,21 @@ int wave_edge_pass(DvgScene *s, const SceneView &sc, const BinView &bins, const 
     s->wpx_valid = false;   // the result words are about to be overwritten
     launch_wave_boundary_sort(sc, bins, ra, bw, wv, s->d_edge_chunks.as<int>(), st);
     CK(cudaGetLastError());
-    rc = wave_classify_and_solve(s, sc, wv, (int64_t)bw.max_blocks * std::max(s->max_nch, 1), st,
-                                 [&](const WaveView &v) { launch_wave_classify_edge(sc, bins, ra, bw, v, st); });
+    rc = wave_classify_and_solve(s, sc, wv, 1, st, [&](const WaveView &v) { launch_wave_classify_edge(sc, bins, ra, bw, v, st); });
     if (rc) return rc;
     launch_wave_composite_edge(sc, bins, ra, bw, wv, st);
     CK(cudaGetLastError());
     return DVG_OK;
+}
+
+// How many boundary samples one boundary pass may take: its result words are sized for the bound
+// (samples / 16 + tiles) items x the chunk count of the densest tile, and must stay below 2^26 words (256 MB of hit
+// words, 1 GB of winding words with fills; the pair records address 2^27).  Larger renders (2048^2 at 4x4 spp) run
+// several passes over consecutive sample ranges.
+int64_t edge_pass_samples(DvgScene *s, int ntiles) {
+    const int64_t word_cap = (int64_t)1 << 26;
+    const int64_t items = word_cap / 32 / std::max(s->max_nch, 1) - ntiles;
+    return items * wave_edge_samples_per_item();
 }
 
 int check_render_args(DvgScene *s, int width, int height, int nsx, int nsy) {
@@ -575,6 +610,13 @@ int dvg_scene_create(const int32_t *topo, int64_t topo_len, int device, DvgScene
     ens(s->d_thick, 4 * npr); ens(s->d_meta, sizeof(PrimMeta) * npr); ens(s->d_cbox, 16 * npr); ens(s->d_cbox_pf, 16 * npr); ens(s->d_cap, 16 * DVG_CAP_F4 * npr);
     ens(s->d_shape_cdf, 4 * ni); ens(s->d_shape_pmf, 4 * ni); ens(s->d_flags, 16);
     if (!rc && cudaMallocHost((void **)&s->h_pinned, 64) != cudaSuccess) rc = fail(DVG_ERR_CUDA, "cudaMallocHost failed");
+    if (!rc && cudaMallocHost((void **)&s->h_counts, 32) != cudaSuccess) rc = fail(DVG_ERR_CUDA, "cudaMallocHost failed");
+    for (int k = 0; k < 2 && !rc; k++)
+        if (cudaEventCreateWithFlags(&s->ev_counts[k], cudaEventDisableTiming) != cudaSuccess) rc = fail(DVG_ERR_CUDA, "cudaEventCreate failed");
+    if (!rc) {
+        int sms = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) dvg::g_num_sms = sms;
+    }
     if (rc) { s->release_all(); delete s; return rc; }
     *out_scene = s;
     return DVG_OK;
@@ -629,7 +671,8 @@ static int render_forward_impl(DvgScene *s, const float *background, float *rend
     if (row_begin < 0 || row_end > height || row_begin > row_end) return fail(DVG_ERR_INVALID, "bad row range");
     DeviceGuard guard(s->device);
     cudaStream_t st = (cudaStream_t)stream;
-    rc = finish_build(s, st);
+    // bins first: their read-back also completes the scene build (error flag, filter radius) -- one synchronisation
+    rc = render_image ? ensure_bins(s, width, height, nsx * nsy, use_prefiltering ? 1 : 0, st, row_begin, row_end) : finish_build(s, st);
     if (rc) return rc;
     SceneView sc = s->view();
     RenderArgs ra;
@@ -639,8 +682,6 @@ static int render_forward_impl(DvgScene *s, const float *background, float *rend
     ra.background = background; ra.render_image = render_image;
     if (g_fast_accept) ra.flags |= DVG_RF_FAST_ACCEPT;
     if (render_image) {
-        rc = ensure_bins(s, width, height, nsx * nsy, use_prefiltering ? 1 : 0, st, row_begin, row_end);
-        if (rc) return rc;
         if (row_begin % s->bin_th != 0) return fail(DVG_ERR_INVALID, "row_begin must be a multiple of the tile height");
         rc = ensure_weight(s, sc, ra, row_begin, row_end, st);
         if (rc) return rc;
@@ -694,7 +735,7 @@ static int render_backward_impl(DvgScene *s, const float *background, const floa
     if (!whole && (d_render_sdf || d_translation)) return fail(DVG_ERR_UNSUPPORTED, "the SDF output / d_translation are not row-sharded");
     DeviceGuard guard(s->device);
     cudaStream_t st = (cudaStream_t)stream;
-    rc = finish_build(s, st);
+    rc = d_render_image ? ensure_bins(s, width, height, nsx * nsy, use_prefiltering ? 1 : 0, st, row_begin, row_end) : finish_build(s, st);
     if (rc) return rc;
     SceneView sc = s->view();
     RenderArgs ra;
@@ -717,8 +758,6 @@ static int render_backward_impl(DvgScene *s, const float *background, const floa
         CK(cudaMemsetAsync(d_background + 4 * (size_t)row_begin * width, 0, sizeof(float) * 4 * (size_t)width * (row_end - row_begin), st));
     if (d_translation) CK(cudaMemsetAsync(d_translation, 0, sizeof(float) * 2 * (size_t)width * height, st));
     if (d_render_image) {
-        rc = ensure_bins(s, width, height, nsx * nsy, use_prefiltering ? 1 : 0, st, row_begin, row_end);
-        if (rc) return rc;
         if (row_begin % s->bin_th != 0) return fail(DVG_ERR_INVALID, "row_begin must be a multiple of the tile height");
         BinView bins = s->bin_view();
         rc = use_prefiltering ? ensure_weight(s, sc, ra, row_begin, row_end, st) : ensure_weight(s, sc, ra, 0, height, st);
@@ -736,11 +775,17 @@ static int render_backward_impl(DvgScene *s, const float *background, const floa
             // boundary term (diffvg.cpp:1558-1626): boundary-sample indices of the owned rows
             const int spp = nsx * nsy;
             const int ntiles = bins.tiles_x * bins.tiles_y;
-            BoundaryWork bw;
-            bw.samples = nullptr; bw.item_tile = nullptr;
-            bw.sample_begin = row_begin * width * spp;
-            bw.num_samples = (row_end - row_begin) * width * spp;
-            if (bw.num_samples > 0) {
+            const int64_t all_begin = (int64_t)row_begin * width * spp;
+            const int64_t all_count = (int64_t)(row_end - row_begin) * width * spp;
+            int64_t per_pass = g_fused ? all_count : edge_pass_samples(s, ntiles);
+            if (g_debug_edge_pass_samples > 0) per_pass = std::min<int64_t>(per_pass, g_debug_edge_pass_samples);
+            if (all_count > 0 && per_pass < 4096)
+                return fail(DVG_ERR_UNSUPPORTED, "a tile holds too many candidate primitives for the boundary pass at this render size");
+            for (int64_t done = 0; done < all_count; done += per_pass) {
+                BoundaryWork bw;
+                bw.samples = nullptr; bw.item_tile = nullptr;
+                bw.sample_begin = (int)(all_begin + done);
+                bw.num_samples = (int)std::min<int64_t>(per_pass, all_count - done);
                 CK(s->d_keys.ensure(sizeof(int) * (size_t)bw.num_samples));
                 CK(s->d_sorted.ensure(sizeof(int) * (size_t)bw.num_samples));
                 CK(s->d_tile_counts.ensure(sizeof(int) * ntiles)); CK(s->d_tile_fill.ensure(sizeof(int) * ntiles));
@@ -792,6 +837,11 @@ int dvg_render_backward(DvgScene *s, const float *background, const float *d_ren
 }
 
 int dvg_debug_set_boundary_dump(float *device_buf) { g_debug_out = device_buf; return DVG_OK; }
+
+int dvg_debug_set_limits(int64_t pair_capacity, int64_t edge_pass_samples) {
+    g_debug_pair_capacity = pair_capacity; g_debug_edge_pass_samples = edge_pass_samples;
+    return DVG_OK;
+}
 
 int dvg_debug_prim_tests(DvgScene *s, int width, int height, int nsx, int nsy, uint64_t seed, int x, int y,
                          int32_t *out_host, float *pos_host, void *stream) {

@@ -68,8 +68,8 @@ struct WaveView {
     unsigned *wind;       // four words per (evaluation, chunk): 4-bit signed winding per candidate; null without fills
     WavePair *pairs_s, *pairs_f;   // exact stroke tests / winding tests still to run
     int cap_s, cap_f;
-    int *counters;        // [0] stroke pairs appended, [1] fill pairs appended (may exceed the capacity: host re-runs),
-                          // [2] ascending units, [3] descending units (never exceed: overflow is solved inline)
+    int *counters;        // [0] stroke pairs wanted, [1] fill pairs wanted (may exceed the capacity: the surplus was answered in
+                          // place by W1), [2] ascending units, [3] descending units (surplus answered in place by W2a)
     int *tile_choff;      // [tiles+1] exclusive scan of chunks per tile
     int *edge_choff;      // [tiles+1] exclusive scan of boundary items * chunks per tile
 };
@@ -112,7 +112,8 @@ void launch_wave_reduce_grads(const RenderArgs &ra, cudaStream_t st);
 int wave_items_per_tile(const BinView &bins, const RenderArgs &ra);
 int wave_edge_samples_per_item();
 void launch_wave_classify_px(const SceneView &sc, const BinView &bins, const RenderArgs &ra, const WaveView &wv, cudaStream_t st);
-void launch_wave_solve(const SceneView &sc, const WaveView &wv, int n_stroke, int n_fill, cudaStream_t st);
+void launch_wave_solve(const SceneView &sc, const WaveView &wv, bool strokes, bool fills, cudaStream_t st);
+extern int g_num_sms;
 void launch_wave_composite_px(const SceneView &sc, const BinView &bins, const RenderArgs &ra, const WaveView &wv, bool backward,
                               cudaStream_t st);
 void launch_wave_boundary_sort(const SceneView &sc, const BinView &bins, const RenderArgs &ra, const BoundaryWork &bw,

@@ -25,7 +25,11 @@
 #include "dvg_internal.h"
 #include "dvg_kernel_util.cuh"
 
+#include <algorithm>
+
 namespace dvg {
+
+int g_num_sms = 148;   // set from the device properties at scene creation (dvg_capi.cu)
 
 #ifndef DVG_WB_MIN
 #define DVG_WB_MIN 4
@@ -76,6 +80,20 @@ DVG_D void scatter_record(const GradRec &gr, float *D) {
         if (gr.addr[j] >= 0 && gr.val[j] != 0.f) atomicAdd(D + gr.addr[j], gr.val[j]);
 }
 
+// Cold path of W1: the pair queue is full, so the exact test runs in the classifying lane (same functions as W2).
+__device__ __noinline__ void wave_exact_in_place(const SceneView &sc, const WaveView &wv, int kind, int e, int tf, int inst, F2 lp,
+                                                 unsigned *hit_word, int64_t word, int k) {
+    const int ptype = tf & DVG_PF_TYPE_MASK;
+    if (kind == 0) {
+        bool decided = false;
+        if (prim_stroke_hit(ptype, (tf & DVG_PF_APPROX) != 0, sc.prim_p01[e], sc.prim_p23[e], sc.prim_rad[e], sc.insts[inst].r, lp, &decided))
+            atomicOr(hit_word, 1u << k);
+    } else {
+        const int w = prim_winding(ptype, sc.prim_p01[e], sc.prim_p23[e], lp);
+        if (w != 0) atomicOr(&wv.wind[(size_t)word * 4 + (k >> 3)], (unsigned)(w & 15) << (4 * (k & 7)));
+    }
+}
+
 // ------------------------------------------------------------------------------------------ W1
 // Classification of one item.  `cb` = first chunk slot of the item; the word of (lane, chunk c) is
 // (cb + c) * 32 + lane.  Reproduces the tests of sample_color's traversal (diffvg.cpp:544-594,
@@ -116,6 +134,11 @@ DVG_D void wave_classify(const SceneView &sc, const BinView &bins, const WaveVie
         }
         ws.hit[lane] = 0u;
         const int64_t word0 = (cb + c) * 32;
+        if (wv.wind) {   // zeroed first: a pair that finds its queue full is answered in place and ORs into these words
+            uint4 z; z.x = z.y = z.z = z.w = 0u;
+            reinterpret_cast<uint4 *>(wv.wind)[word0 + lane] = z;
+        }
+        __syncwarp();
 #pragma unroll 1
         for (int kind = 0; kind < 2; kind++) {
             const unsigned need = kind == 0 ? need_s : need_f;
@@ -135,6 +158,7 @@ DVG_D void wave_classify(const SceneView &sc, const BinView &bins, const WaveVie
                 const int it = have ? ws.queue[r + lane] : 0;
                 const int k = it & 31, owner = it >> 5;
                 const int ek = __shfl_sync(FULL, e, k), tfk = __shfl_sync(FULL, tf, k), gk = __shfl_sync(FULL, group, k);
+                const int ik = __shfl_sync(FULL, inst, k);
                 const F2 op = mk2(__shfl_sync(FULL, cpt.x, owner), __shfl_sync(FULL, cpt.y, owner));
                 bool keep = have;
                 F2 lp = mk2(0, 0);
@@ -153,11 +177,16 @@ DVG_D void wave_classify(const SceneView &sc, const BinView &bins, const WaveVie
                 const int cnt = __popc(m);
                 if (cnt) {
                     const int pos = warp_reserve(&wv.counters[kind], cnt) + __popc(m & lt);
-                    if (keep && pos < cap) {
-                        WavePair p;
-                        p.x = lp.x; p.y = lp.y; p.prim = ek | ((tfk & DVG_PF_TYPE_MASK) << 28);   // type rides along: W2 needs no meta load
-                        p.ref = ((unsigned)(word0 + owner) << 5) | (unsigned)k;
-                        out[pos] = p;
+                    if (keep) {
+                        if (pos < cap) {
+                            WavePair p;
+                            p.x = lp.x; p.y = lp.y; p.prim = ek | ((tfk & DVG_PF_TYPE_MASK) << 28);   // type rides along: W2 needs no meta load
+                            p.ref = ((unsigned)(word0 + owner) << 5) | (unsigned)k;
+                            out[pos] = p;
+                        } else {
+                            // queue full (its capacity follows the counts of earlier passes, see dvg_capi.cu): answered here
+                            wave_exact_in_place(sc, wv, kind, ek, tfk, ik, lp, &ws.hit[owner], word0 + owner, k);
+                        }
                     }
                 }
             }
@@ -165,10 +194,6 @@ DVG_D void wave_classify(const SceneView &sc, const BinView &bins, const WaveVie
         }
         __syncwarp();
         wv.hit[word0 + lane] = ws.hit[lane];
-        if (wv.wind) {
-            uint4 z; z.x = z.y = z.z = z.w = 0u;
-            reinterpret_cast<uint4 *>(wv.wind)[word0 + lane] = z;
-        }
         __syncwarp();
     }
 }
@@ -275,11 +300,13 @@ __global__ void __launch_bounds__(WB, DVG_WB_MIN) k_wave_classify_edge(SceneView
 // Per-bracket arithmetic is dvg_geom.cuh's, evaluated on the same inputs: results are unchanged.
 constexpr int W2A_B = 256;
 
-// `count` < 0: take the number of pairs from the device counter (queues sized for the worst case, no read-back).
-__global__ void __launch_bounds__(W2A_B) k_wave_stroke_setup(SceneView sc, WaveView wv, int count) {
-    if (count < 0) count = min(wv.counters[0], wv.cap_s);
-    const int i = blockIdx.x * W2A_B + threadIdx.x;
+// The number of pairs is read from the device counter (nothing is read back to size a launch): the grid is a fixed
+// multiple of the SM count and every block strides over the queue.
+__global__ void __launch_bounds__(W2A_B) k_wave_stroke_setup(SceneView sc, WaveView wv) {
+    const int count = min(wv.counters[0], wv.cap_s);
     const int lane = threadIdx.x & 31;
+  for (int base = blockIdx.x * W2A_B; base < count; base += gridDim.x * W2A_B) {
+    const int i = base + threadIdx.x;
     float lbs[5], ubs[5];
     unsigned valid = 0u, desc = 0u;   // bit j: bracket j holds a root / is descending
     bool hit = false;
@@ -371,46 +398,52 @@ __global__ void __launch_bounds__(W2A_B) k_wave_stroke_setup(SceneView sc, WaveV
                 atomicOr(&wv.hit[p.ref >> 5], 1u << (p.ref & 31u));
         }
     }
+  }
 }
 
-__global__ void __launch_bounds__(256) k_wave_stroke_newton(SceneView sc, WaveView wv, int which) {
-    const int u = blockIdx.x * blockDim.x + threadIdx.x;
-    const int count = min(wv.counters[2 + which], which ? wv.cap_ud : wv.cap_ua);
-    if (u >= count) return;
-    const WaveUnit un = (which ? wv.units_d : wv.units_a)[u];
-    WavePair p = wv.pairs_s[un.pair];
-    p.prim &= 0x0fffffff;
-    const unsigned bit = 1u << (p.ref & 31u);
-    if (wv.hit[p.ref >> 5] & bit) return;   // another bracket of the pair already answered "hit"
-    const F4 p01 = sc.prim_p01[p.prim], p23 = sc.prim_p23[p.prim], rad = sc.prim_rad[p.prim];
-    const F2 p0 = mk2(p01.x, p01.y), p1 = mk2(p01.z, p01.w), p2 = mk2(p23.x, p23.y), p3 = mk2(p23.z, p23.w);
-    const F2 pt = mk2(p.x, p.y);
-    const Quintic q = cubic_quintic(p0, p1, p2, p3, pt);
-    float lb = un.lb, ub = un.ub;
-    float t = 0.5f * (lb + ub);
-    for (int it = 0; it < 20; it++) {                              // within_distance.h:244-262
-        if (!(t >= lb && t <= ub)) t = 0.5f * (lb + ub);
-        const double value = quintic_eval(q, t);
-        if (fabs(value) < 1e-5f || it == 19) break;
-        if (value > 0.f) ub = t; else lb = t;
-        const double derivative = quintic_deriv(q, t);
-        t = (float)((double)t - newton_quotient(value, derivative));
+// WHICH = 1: descending brackets.  After the reference's swap lb > ub, so its "t in [lb, ub]" guard fails on every trip and
+// the Newton iterate is always replaced by the midpoint before it is used: the derivative never matters and is not formed.
+template <int WHICH>
+__global__ void __launch_bounds__(256) k_wave_stroke_newton(SceneView sc, WaveView wv) {
+    const int count = min(wv.counters[2 + WHICH], WHICH ? wv.cap_ud : wv.cap_ua);
+    for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < count; u += gridDim.x * blockDim.x) {
+        const WaveUnit un = (WHICH ? wv.units_d : wv.units_a)[u];
+        WavePair p = wv.pairs_s[un.pair];
+        p.prim &= 0x0fffffff;
+        const unsigned bit = 1u << (p.ref & 31u);
+        if (wv.hit[p.ref >> 5] & bit) continue;   // another bracket of the pair already answered "hit"
+        const F4 p01 = sc.prim_p01[p.prim], p23 = sc.prim_p23[p.prim], rad = sc.prim_rad[p.prim];
+        const F2 p0 = mk2(p01.x, p01.y), p1 = mk2(p01.z, p01.w), p2 = mk2(p23.x, p23.y), p3 = mk2(p23.z, p23.w);
+        const F2 pt = mk2(p.x, p.y);
+        const Quintic q = cubic_quintic(p0, p1, p2, p3, pt);
+        float lb = un.lb, ub = un.ub;
+        float t = 0.5f * (lb + ub);
+        for (int it = 0; it < 20; it++) {                              // within_distance.h:244-262
+            if (WHICH || !(t >= lb && t <= ub)) t = 0.5f * (lb + ub);
+            const double value = quintic_eval(q, t);
+            if (fabs(value) < 1e-5f || it == 19) break;
+            if (value > 0.f) ub = t; else lb = t;
+            if (!WHICH) {
+                const double derivative = quintic_deriv(q, t);
+                t = (float)((double)t - newton_quotient(value, derivative));
+            }
+        }
+        const float tt = 1 - t;                                        // :263-267
+        const float rr = (tt * tt * tt) * rad.x + (3 * tt * tt * t) * rad.y + (3 * tt * t * t) * rad.z + (t * t * t) * rad.w;
+        if (dist_sq(eval_cubic(p0, p1, p2, p3, t), pt) < rr * rr) atomicOr(&wv.hit[p.ref >> 5], bit);
     }
-    const float tt = 1 - t;                                        // :263-267
-    const float rr = (tt * tt * tt) * rad.x + (3 * tt * tt * t) * rad.y + (3 * tt * t * t) * rad.z + (t * t * t) * rad.w;
-    if (dist_sq(eval_cubic(p0, p1, p2, p3, t), pt) < rr * rr) atomicOr(&wv.hit[p.ref >> 5], bit);
 }
 
-__global__ void __launch_bounds__(128) k_wave_solve_fill(SceneView sc, WaveView wv, int count) {
-    if (count < 0) count = min(wv.counters[1], wv.cap_f);
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= count) return;
-    WavePair p = wv.pairs_f[i];
-    const int ptype = (int)((unsigned)p.prim >> 28);
-    p.prim &= 0x0fffffff;
-    const int w = prim_winding(ptype, sc.prim_p01[p.prim], sc.prim_p23[p.prim], mk2(p.x, p.y));
-    const unsigned k = p.ref & 31u;
-    if (w != 0) atomicOr(&wv.wind[(size_t)(p.ref >> 5) * 4 + (k >> 3)], (unsigned)(w & 15) << (4 * (k & 7)));
+__global__ void __launch_bounds__(128) k_wave_solve_fill(SceneView sc, WaveView wv) {
+    const int count = min(wv.counters[1], wv.cap_f);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+        WavePair p = wv.pairs_f[i];
+        const int ptype = (int)((unsigned)p.prim >> 28);
+        p.prim &= 0x0fffffff;
+        const int w = prim_winding(ptype, sc.prim_p01[p.prim], sc.prim_p23[p.prim], mk2(p.x, p.y));
+        const unsigned k = p.ref & 31u;
+        if (w != 0) atomicOr(&wv.wind[(size_t)(p.ref >> 5) * 4 + (k >> 3)], (unsigned)(w & 15) << (4 * (k & 7)));
+    }
 }
 
 // ------------------------------------------------------------------------------------------ W3
@@ -679,20 +712,21 @@ void launch_wave_classify_px(const SceneView &sc, const BinView &bins, const Ren
     DVG_LAUNCH(k_wave_classify_px, dim3((items + WNW - 1) / WNW), dim3(WB), 0, st, sc, bins, ra, wv, items);
 }
 
-void launch_wave_solve(const SceneView &sc, const WaveView &wv, int n_stroke, int n_fill, cudaStream_t st) {
-    // n < 0: the count stays on the device, the grid covers the queue capacity
-    if (n_stroke != 0) {
-        const int cover = n_stroke < 0 ? wv.cap_s : n_stroke;
+// Grids are a fixed multiple of the SM count (bounded by the queue capacity); the counts stay on the device.
+static int stride_grid(int64_t cap, int block, int per_sm) {
+    const int64_t need = (cap + block - 1) / block;
+    const int64_t persistent = (int64_t)g_num_sms * per_sm;
+    return (int)std::max<int64_t>(1, std::min(need, persistent));
+}
+
+void launch_wave_solve(const SceneView &sc, const WaveView &wv, bool strokes, bool fills, cudaStream_t st) {
+    if (strokes && wv.cap_s > 0) {
         cudaMemsetAsync(wv.counters + 2, 0, sizeof(int) * 2, st);
-        DVG_LAUNCH(k_wave_stroke_setup, dim3((cover + W2A_B - 1) / W2A_B), dim3(W2A_B), 0, st, sc, wv, n_stroke);
-        // the unit counts stay on the device: grids cover the queue capacities, surplus threads exit at once
-        DVG_LAUNCH(k_wave_stroke_newton, dim3((wv.cap_ua + 255) / 256), dim3(256), 0, st, sc, wv, 0);
-        DVG_LAUNCH(k_wave_stroke_newton, dim3((wv.cap_ud + 255) / 256), dim3(256), 0, st, sc, wv, 1);
+        DVG_LAUNCH(k_wave_stroke_setup, dim3(stride_grid(wv.cap_s, W2A_B, 12)), dim3(W2A_B), 0, st, sc, wv);
+        DVG_LAUNCH(k_wave_stroke_newton<0>, dim3(stride_grid(wv.cap_ua, 256, 16)), dim3(256), 0, st, sc, wv);
+        DVG_LAUNCH(k_wave_stroke_newton<1>, dim3(stride_grid(wv.cap_ud, 256, 16)), dim3(256), 0, st, sc, wv);
     }
-    if (n_fill != 0) {
-        const int cover = n_fill < 0 ? wv.cap_f : n_fill;
-        DVG_LAUNCH(k_wave_solve_fill, dim3((cover + 127) / 128), dim3(128), 0, st, sc, wv, n_fill);
-    }
+    if (fills && wv.cap_f > 0) DVG_LAUNCH(k_wave_solve_fill, dim3(stride_grid(wv.cap_f, 128, 32)), dim3(128), 0, st, sc, wv);
 }
 
 void launch_wave_composite_px(const SceneView &sc, const BinView &bins, const RenderArgs &ra, const WaveView &wv, bool backward,

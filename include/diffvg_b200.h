@@ -138,6 +138,10 @@ int dvg_set_fast_stroke_accept(int on);
 /* Test support: when non-NULL, the boundary pass also writes (contrib, hit bits, normal.xy) per boundary
  * sample index into this DEVICE buffer of 4*W*H*spp floats (sample-level parity debugging). */
 int dvg_debug_set_boundary_dump(float *device_buf);
+/* Test support: cap the exact-test pair queues at `pair_capacity` records (0 = off: sized from earlier passes), which
+ * forces the answer-in-place path of the classifier, and the boundary pass at `edge_pass_samples` samples per sub-pass
+ * (0 = off: as many as the result words allow).  Process-wide. */
+int dvg_debug_set_limits(int64_t pair_capacity, int64_t edge_pass_samples);
 /* Test support: for every sample of pixel (x, y) and EVERY primitive of the scene (no culling), the exact stroke test and
  * winding contribution as the device computes them: out_host[s * num_prims + e] = hit (bit 0) | group strokes (bit 1) |
  * group fills (bit 2) | primitive is in the pixel's tile bin (bit 3) | (winding & 0xff) << 8; pos_host[2 s .. 2 s + 1] =

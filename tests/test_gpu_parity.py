@@ -203,6 +203,63 @@ def test_packed_params_api_matches_stock_api():
     assert pp2.points.grad.is_cuda and torch.isfinite(pp2.points.grad).all()
 
 
+@pytest.fixture
+def debug_limits():
+    from diffvg_b200 import _native
+    yield _native.lib.dvg_debug_set_limits
+    _native.lib.dvg_debug_set_limits(0, 0)
+
+
+@pytest.mark.parametrize('mk,W,H,ns', [(lambda: scenes.painterly(256, 256), 256, 256, 4), (lambda: scenes.blobs(128, 256), 256, 256, 2),
+                                        (scenes.zoo, 192, 192, 3)], ids=['painterly256', 'blobs128', 'zoo'])
+def test_full_pair_queue_is_answered_in_place(debug_limits, mk, W, H, ns):
+    """No pass reads its pair counts back: the queues keep the capacity earlier passes asked for, and a pass that
+    overflows answers the surplus (sample, primitive) tests inside the classifier.  Forced here with a queue of 1500
+    records (thousands of times too small): image and gradients must not change."""
+    topo, params = util.pack(mk())
+    d_img = np.random.RandomState(1).rand(H, W, 4).astype(np.float32) - 0.5
+    ref = oracle_check.render(topo, params, W, H, ns, ns, 2)['image']
+    rb = oracle_check.render(topo, params, W, H, ns, ns, 2, d_render_image=d_img)
+    debug_limits(1500, 0)
+    got = util.gpu_render(topo, params, W, H, ns, ns, 2)['image']
+    assert np.abs(ref - got).max() <= FWD_TOL
+    gb = util.gpu_render(topo, params, W, H, ns, ns, 2, d_render_image=d_img)
+    grad_close(rb['d_params'], gb['d_params'])
+
+
+def test_boundary_pass_in_sample_ranges(debug_limits):
+    """Large renders run the boundary pass over consecutive sample ranges (its result words are bounded); forced here
+    with 5000 samples per range on a small render."""
+    topo, params = util.pack(scenes.zoo())
+    d_img = np.random.RandomState(1).rand(128, 128, 4).astype(np.float32) - 0.5
+    rb = oracle_check.render(topo, params, 128, 128, 2, 2, 3, d_render_image=d_img)
+    debug_limits(0, 5000)
+    gb = util.gpu_render(topo, params, 128, 128, 2, 2, 3, d_render_image=d_img)
+    grad_close(rb['d_params'], gb['d_params'])
+
+
+def test_sampled_backward_at_2048_4x4():
+    """67 M pixel samples + 67 M boundary samples (the largest sampled configuration of a 2048^2 render): the boundary
+    pass splits into sample ranges by itself.  Checked through properties: finite, non-trivial, and equal to the sum of
+    two row shards (which split the boundary samples differently)."""
+    topo, params = util.pack(scenes.painterly())
+    W = H = 2048
+    d_img = (np.random.RandomState(2).rand(H, W, 4).astype(np.float32) - 0.5)
+    g = util.gpu_render(topo, params, W, H, 4, 4, 1, d_render_image=d_img, skip_xform_grad=True)['d_params']
+    assert np.isfinite(g).all() and np.count_nonzero(g) > 30000
+    parts = util.gpu_render_rows(topo, params, W, H, 4, 4, 1, [(0, 1024), (1024, 2048)], d_render_image=d_img)
+    from diffvg_b200 import scene_pack
+    a = g.astype(np.float64)
+    b = parts['d_params'].copy()
+    goff = int(topo[scene_pack.H_OFF_GROUPS])
+    for gi in range(int(topo[scene_pack.H_NG])):    # the shards accumulate d_shape_to_canvas, the whole render skipped it
+        xo = int(topo[goff + gi * scene_pack.G_LEN + 9])
+        b[xo:xo + 9] = 0.0
+    i = int(topo[scene_pack.H_FRAD_OFF])
+    a[i] = b[i] = 0.0
+    assert util.rel_l2(a, b) <= 1e-4
+
+
 def test_pydiffvg_api_single_circle_gradients():
     """apps/single_circle.py through the pydiffvg surface; known answers from SURVEY 8c."""
     from diffvg_b200 import pydiffvg
