@@ -386,8 +386,9 @@ int ensure_weight(DvgScene *s, const SceneView &sc, RenderArgs &ra, int r0, int 
 // ---- wavefront passes: workspace sizing and the classify -> solve sequence.
 // Nothing is read back inside a pass.  The pair queues keep the capacity that earlier passes asked for: every pass copies
 // its counters to pinned memory when it ends, and the next pass -- whenever that copy has landed -- grows a queue that
-// was too small.  A pass that still overflows (the first one of a scene; a sudden change of the geometry) answers the
-// surplus pairs in place (wave_exact_in_place): slower, same results.
+// was too small.  A pass that still overflows (the first one of a scene; a sudden change of the geometry) is followed by
+// a retry kernel that answers every pair in place and rewrites the result words (dvg_wave.cu wave_classify<true>):
+// slower, same results; when nothing overflowed that kernel exits at once.
 void wave_feedback_poll(DvgScene *s) {
     for (int slot = 0; slot < 2; slot++) {
         if (!s->counts_pending[slot] || cudaEventQuery(s->ev_counts[slot]) != cudaSuccess) continue;
@@ -447,13 +448,18 @@ int wave_view(DvgScene *s, int64_t chunk_slots, int64_t evals, WaveView *out) {
 }
 
 // Runs `classify` (W1) and the exact tests (W2); `slot`: 0 pixel pass, 1 boundary pass (where its counters are parked).
-template <typename Classify>
-int wave_classify_and_solve(DvgScene *s, const SceneView &sc, WaveView &wv, int slot, cudaStream_t st, const Classify &classify) {
+template <typename Classify, typename Retry>
+int wave_classify_and_solve(DvgScene *s, const SceneView &sc, WaveView &wv, int slot, cudaStream_t st, const Classify &classify,
+                            const Retry &retry, bool small) {
     CK(cudaMemsetAsync(wv.counters, 0, sizeof(int) * 2, st));
     classify(wv);
     CK(cudaGetLastError());
     launch_wave_solve(sc, wv, true, s->has_fills, st);
     CK(cudaGetLastError());
+    if (!small) {   // worst-case-sized queues can not overflow
+        retry(wv);  // exits at once unless a queue overflowed
+        CK(cudaGetLastError());
+    }
     if (!s->counts_pending[slot]) {   // an unread copy of an earlier pass is still in flight: skip this one
         CK(cudaMemcpyAsync(s->h_counts + 4 * slot, wv.counters, sizeof(int) * 4, cudaMemcpyDeviceToHost, st));
         CK(cudaEventRecord(s->ev_counts[slot], st));
@@ -476,7 +482,9 @@ int wave_pixel_pass(DvgScene *s, const SceneView &sc, const BinView &bins, const
                        s->wpx_pf == ra.use_prefiltering && s->wpx_fast == fast;
     if (!reuse) {
         s->wpx_valid = false;
-        rc = wave_classify_and_solve(s, sc, wv, 0, st, [&](const WaveView &v) { launch_wave_classify_px(sc, bins, ra, v, st); });
+        const bool small = (int64_t)s->total_chunks * wpt * 32 * 32 <= kSmallPairs;
+        rc = wave_classify_and_solve(s, sc, wv, 0, st, [&](const WaveView &v) { launch_wave_classify_px(sc, bins, ra, v, st); },
+                                     [&](const WaveView &v) { launch_wave_retry_px(sc, bins, ra, v, st); }, small);
         if (rc) return rc;
         s->wpx_valid = true; s->wpx_w = ra.width; s->wpx_h = ra.height; s->wpx_nsx = ra.nsx; s->wpx_nsy = ra.nsy;
         s->wpx_seed = ra.seed; s->wpx_r0 = ra.row_begin; s->wpx_r1 = ra.row_end; s->wpx_pf = ra.use_prefiltering; s->wpx_fast = fast;
@@ -505,7 +513,9 @@ int wave_edge_pass(DvgScene *s, const SceneView &sc, const BinView &bins, const 
     s->wpx_valid = false;   // the result words are about to be overwritten
     launch_wave_boundary_sort(sc, bins, ra, bw, wv, s->d_edge_chunks.as<int>(), st);
     CK(cudaGetLastError());
-    rc = wave_classify_and_solve(s, sc, wv, 1, st, [&](const WaveView &v) { launch_wave_classify_edge(sc, bins, ra, bw, v, st); });
+    const bool small = (int64_t)bw.max_blocks * std::max(s->max_nch, 1) * 32 * 32 <= kSmallPairs;
+    rc = wave_classify_and_solve(s, sc, wv, 1, st, [&](const WaveView &v) { launch_wave_classify_edge(sc, bins, ra, bw, v, st); },
+                                 [&](const WaveView &v) { launch_wave_retry_edge(sc, bins, ra, bw, v, st); }, small);
     if (rc) return rc;
     launch_wave_composite_edge(sc, bins, ra, bw, wv, st);
     CK(cudaGetLastError());

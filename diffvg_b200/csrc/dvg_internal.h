@@ -113,6 +113,9 @@ int wave_items_per_tile(const BinView &bins, const RenderArgs &ra);
 int wave_edge_samples_per_item();
 void launch_wave_classify_px(const SceneView &sc, const BinView &bins, const RenderArgs &ra, const WaveView &wv, cudaStream_t st);
 void launch_wave_solve(const SceneView &sc, const WaveView &wv, bool strokes, bool fills, cudaStream_t st);
+void launch_wave_retry_px(const SceneView &sc, const BinView &bins, const RenderArgs &ra, const WaveView &wv, cudaStream_t st);
+void launch_wave_retry_edge(const SceneView &sc, const BinView &bins, const RenderArgs &ra, const BoundaryWork &bw,
+                            const WaveView &wv, cudaStream_t st);
 extern int g_num_sms;
 void launch_wave_composite_px(const SceneView &sc, const BinView &bins, const RenderArgs &ra, const WaveView &wv, bool backward,
                               cudaStream_t st);

@@ -99,6 +99,11 @@ __device__ __noinline__ void wave_exact_in_place(const SceneView &sc, const Wave
 // (cb + c) * 32 + lane.  Reproduces the tests of sample_color's traversal (diffvg.cpp:544-594,
 // within_distance.h:278-285, 362-388, winding_number.h:162-169) up to, not including, the exact
 // per-segment tests.
+// INPLACE: the retry form.  It runs after W1 + W2 and only does anything when a pair queue overflowed (a pass whose
+// geometry asked for more exact tests than any pass before it): every pair is then answered in the classifying lane and
+// the result words of the whole pass are rewritten.  Keeping this out of the hot form keeps that one free of calls
+// (the call alone cost it 300 bytes of spills and 60% of its speed).
+template <bool INPLACE>
 DVG_D void wave_classify(const SceneView &sc, const BinView &bins, const WaveView &wv, int tile, int64_t cb,
                          F2 cpt, bool active, WaveScratch &ws, bool fast_accept) {
     const unsigned FULL = 0xffffffffu;
@@ -158,7 +163,8 @@ DVG_D void wave_classify(const SceneView &sc, const BinView &bins, const WaveVie
                 const int it = have ? ws.queue[r + lane] : 0;
                 const int k = it & 31, owner = it >> 5;
                 const int ek = __shfl_sync(FULL, e, k), tfk = __shfl_sync(FULL, tf, k), gk = __shfl_sync(FULL, group, k);
-                const int ik = __shfl_sync(FULL, inst, k);
+                int ik = 0;
+                if (INPLACE) ik = __shfl_sync(FULL, inst, k);
                 const F2 op = mk2(__shfl_sync(FULL, cpt.x, owner), __shfl_sync(FULL, cpt.y, owner));
                 bool keep = have;
                 F2 lp = mk2(0, 0);
@@ -173,20 +179,20 @@ DVG_D void wave_classify(const SceneView &sc, const BinView &bins, const WaveVie
                         if (cls > 0 && fast_accept) atomicOr(&ws.hit[owner], 1u << k);
                     }
                 }
+                if (INPLACE) {
+                    if (keep) wave_exact_in_place(sc, wv, kind, ek, tfk, ik, lp, &ws.hit[owner], word0 + owner, k);
+                    continue;
+                }
                 const unsigned m = __ballot_sync(FULL, keep);
                 const int cnt = __popc(m);
                 if (cnt) {
+                    // the counter keeps counting past the capacity: that is how the retry form and the host learn of it
                     const int pos = warp_reserve(&wv.counters[kind], cnt) + __popc(m & lt);
-                    if (keep) {
-                        if (pos < cap) {
-                            WavePair p;
-                            p.x = lp.x; p.y = lp.y; p.prim = ek | ((tfk & DVG_PF_TYPE_MASK) << 28);   // type rides along: W2 needs no meta load
-                            p.ref = ((unsigned)(word0 + owner) << 5) | (unsigned)k;
-                            out[pos] = p;
-                        } else {
-                            // queue full (its capacity follows the counts of earlier passes, see dvg_capi.cu): answered here
-                            wave_exact_in_place(sc, wv, kind, ek, tfk, ik, lp, &ws.hit[owner], word0 + owner, k);
-                        }
+                    if (keep && pos < cap) {
+                        WavePair p;
+                        p.x = lp.x; p.y = lp.y; p.prim = ek | ((tfk & DVG_PF_TYPE_MASK) << 28);   // type rides along: W2 needs no meta load
+                        p.ref = ((unsigned)(word0 + owner) << 5) | (unsigned)k;
+                        out[pos] = p;
                     }
                 }
             }
@@ -226,16 +232,20 @@ DVG_D PixelItem pixel_item(const BinView &bins, const RenderArgs &ra, const Wave
     return pi;
 }
 
+DVG_D bool wave_overflowed(const WaveView &wv) { return wv.counters[0] > wv.cap_s || wv.counters[1] > wv.cap_f; }
+
+template <bool INPLACE>
 __global__ void __launch_bounds__(WB, DVG_WB_MIN) k_wave_classify_px(SceneView sc, BinView bins, RenderArgs ra, WaveView wv, int num_items) {
     __shared__ WaveScratch s_ws[WNW];
-    const int item = blockIdx.x * WNW + (threadIdx.x >> 5);
-    if (item >= num_items) return;
-    const PixelItem pi = pixel_item(bins, ra, wv, item);
-    F2 pt = mk2(0, 0), cpt = mk2(0, 0);
-    if (pi.active)
-        sample_position(sc.canvas_w, sc.canvas_h, ra.width, ra.height, ra.nsx, ra.nsy, ra.seed, ra.use_prefiltering != 0,
-                        pi.x, pi.y, pi.sx, pi.sy, pi.idx, pt, cpt);
-    wave_classify(sc, bins, wv, pi.tile, pi.cb, cpt, pi.active, s_ws[threadIdx.x >> 5], (ra.flags & DVG_RF_FAST_ACCEPT) != 0);
+    if (INPLACE && !wave_overflowed(wv)) return;
+    for (int item = blockIdx.x * WNW + (threadIdx.x >> 5); item < num_items; item += gridDim.x * WNW) {
+        const PixelItem pi = pixel_item(bins, ra, wv, item);
+        F2 pt = mk2(0, 0), cpt = mk2(0, 0);
+        if (pi.active)
+            sample_position(sc.canvas_w, sc.canvas_h, ra.width, ra.height, ra.nsx, ra.nsy, ra.seed, ra.use_prefiltering != 0,
+                            pi.x, pi.y, pi.sx, pi.sy, pi.idx, pt, cpt);
+        wave_classify<INPLACE>(sc, bins, wv, pi.tile, pi.cb, cpt, pi.active, s_ws[threadIdx.x >> 5], (ra.flags & DVG_RF_FAST_ACCEPT) != 0);
+    }
 }
 
 // Geometry of a boundary item: 16 boundary samples of one tile; lanes 2k / 2k+1 = the two sides of sample k.
@@ -277,14 +287,17 @@ DVG_D EdgeLane edge_lane(const SceneView &sc, const RenderArgs &ra, const Bounda
     return el;
 }
 
+template <bool INPLACE>
 __global__ void __launch_bounds__(WB, DVG_WB_MIN) k_wave_classify_edge(SceneView sc, BinView bins, RenderArgs ra, BoundaryWork bw, WaveView wv) {
     __shared__ WaveScratch s_ws[WNW];
+    if (INPLACE && !wave_overflowed(wv)) return;
     const int ntiles = bins.tiles_x * bins.tiles_y;
-    const int item = blockIdx.x * WNW + (threadIdx.x >> 5);
-    if (item >= bw.blk_offsets[ntiles]) return;
-    const EdgeItem ei = edge_item(bins, bw, wv, item);
-    const EdgeLane el = edge_lane(sc, ra, bw, ei);
-    wave_classify(sc, bins, wv, ei.tile, ei.cb, el.cpt, el.active, s_ws[threadIdx.x >> 5], (ra.flags & DVG_RF_FAST_ACCEPT) != 0);
+    const int num_items = bw.blk_offsets[ntiles];
+    for (int item = blockIdx.x * WNW + (threadIdx.x >> 5); item < num_items; item += gridDim.x * WNW) {
+        const EdgeItem ei = edge_item(bins, bw, wv, item);
+        const EdgeLane el = edge_lane(sc, ra, bw, ei);
+        wave_classify<INPLACE>(sc, bins, wv, ei.tile, ei.cb, el.cpt, el.active, s_ws[threadIdx.x >> 5], (ra.flags & DVG_RF_FAST_ACCEPT) != 0);
+    }
 }
 
 // ------------------------------------------------------------------------------------------ W2
@@ -299,6 +312,12 @@ __global__ void __launch_bounds__(WB, DVG_WB_MIN) k_wave_classify_edge(SceneView
 //        descending bracket has lb > ub, its "t in [lb, ub]" guard never holds and it bisects (~3x the trips).
 // Per-bracket arithmetic is dvg_geom.cuh's, evaluated on the same inputs: results are unchanged.
 constexpr int W2A_B = 256;
+#ifndef DVG_SETUP_PER_SM
+#define DVG_SETUP_PER_SM 64
+#endif
+#ifndef DVG_NEWTON_PER_SM
+#define DVG_NEWTON_PER_SM 64
+#endif
 
 // The number of pairs is read from the device counter (nothing is read back to size a launch): the grid is a fixed
 // multiple of the SM count and every block strides over the queue.
@@ -709,7 +728,12 @@ int wave_edge_samples_per_item() { return W_EDGE_SPI; }
 void launch_wave_classify_px(const SceneView &sc, const BinView &bins, const RenderArgs &ra, const WaveView &wv, cudaStream_t st) {
     const int items = wave_pixel_items(bins, ra);
     if (items <= 0) return;
-    DVG_LAUNCH(k_wave_classify_px, dim3((items + WNW - 1) / WNW), dim3(WB), 0, st, sc, bins, ra, wv, items);
+    DVG_LAUNCH(k_wave_classify_px<false>, dim3((items + WNW - 1) / WNW), dim3(WB), 0, st, sc, bins, ra, wv, items);
+}
+void launch_wave_retry_px(const SceneView &sc, const BinView &bins, const RenderArgs &ra, const WaveView &wv, cudaStream_t st) {
+    const int items = wave_pixel_items(bins, ra);
+    if (items <= 0) return;
+    DVG_LAUNCH(k_wave_classify_px<true>, dim3(std::min((items + WNW - 1) / WNW, g_num_sms * DVG_WB_MIN)), dim3(WB), 0, st, sc, bins, ra, wv, items);
 }
 
 // Grids are a fixed multiple of the SM count (bounded by the queue capacity); the counts stay on the device.
@@ -722,9 +746,9 @@ static int stride_grid(int64_t cap, int block, int per_sm) {
 void launch_wave_solve(const SceneView &sc, const WaveView &wv, bool strokes, bool fills, cudaStream_t st) {
     if (strokes && wv.cap_s > 0) {
         cudaMemsetAsync(wv.counters + 2, 0, sizeof(int) * 2, st);
-        DVG_LAUNCH(k_wave_stroke_setup, dim3(stride_grid(wv.cap_s, W2A_B, 12)), dim3(W2A_B), 0, st, sc, wv);
-        DVG_LAUNCH(k_wave_stroke_newton<0>, dim3(stride_grid(wv.cap_ua, 256, 16)), dim3(256), 0, st, sc, wv);
-        DVG_LAUNCH(k_wave_stroke_newton<1>, dim3(stride_grid(wv.cap_ud, 256, 16)), dim3(256), 0, st, sc, wv);
+        DVG_LAUNCH(k_wave_stroke_setup, dim3(stride_grid(wv.cap_s, W2A_B, DVG_SETUP_PER_SM)), dim3(W2A_B), 0, st, sc, wv);
+        DVG_LAUNCH(k_wave_stroke_newton<0>, dim3(stride_grid(wv.cap_ua, 256, DVG_NEWTON_PER_SM)), dim3(256), 0, st, sc, wv);
+        DVG_LAUNCH(k_wave_stroke_newton<1>, dim3(stride_grid(wv.cap_ud, 256, DVG_NEWTON_PER_SM)), dim3(256), 0, st, sc, wv);
     }
     if (fills && wv.cap_f > 0) DVG_LAUNCH(k_wave_solve_fill, dim3(stride_grid(wv.cap_f, 128, 32)), dim3(128), 0, st, sc, wv);
 }
@@ -751,7 +775,11 @@ void launch_wave_boundary_sort(const SceneView &sc, const BinView &bins, const R
 
 void launch_wave_classify_edge(const SceneView &sc, const BinView &bins, const RenderArgs &ra, const BoundaryWork &bw,
                                const WaveView &wv, cudaStream_t st) {
-    DVG_LAUNCH(k_wave_classify_edge, dim3((bw.max_blocks + WNW - 1) / WNW), dim3(WB), 0, st, sc, bins, ra, bw, wv);
+    DVG_LAUNCH(k_wave_classify_edge<false>, dim3((bw.max_blocks + WNW - 1) / WNW), dim3(WB), 0, st, sc, bins, ra, bw, wv);
+}
+void launch_wave_retry_edge(const SceneView &sc, const BinView &bins, const RenderArgs &ra, const BoundaryWork &bw,
+                            const WaveView &wv, cudaStream_t st) {
+    DVG_LAUNCH(k_wave_classify_edge<true>, dim3(std::min((bw.max_blocks + WNW - 1) / WNW, g_num_sms * DVG_WB_MIN)), dim3(WB), 0, st, sc, bins, ra, bw, wv);
 }
 
 void launch_wave_composite_edge(const SceneView &sc, const BinView &bins, const RenderArgs &ra, const BoundaryWork &bw,
