@@ -252,6 +252,7 @@ def main():
     ap.add_argument('--impl', default='own', choices=['own', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-strong', action='store_true', help='N > 1: skip the 2048^2 strong-scaling sub-records')
+    ap.add_argument('--quick', action='store_true', help='development: device-timed value and per-kernel times only (no e2e legs)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'own' else args.warmup
 
@@ -381,7 +382,7 @@ def main():
             dist.all_reduce(flat)
         return loss.item()
 
-    e2e_stock_ms = time_e2e(e2e_stock_step, max(3, args.steps // 2))
+    e2e_stock_ms = time_e2e(e2e_stock_step, max(3, args.steps // 2)) if not args.quick else float('nan')
     for t in leaves:
         t.requires_grad_(False)
         t.grad = None
@@ -404,7 +405,7 @@ def main():
         e2e_bytes['d2h'] = sargs[1].numel() * 4 + 4
         return loss.item()                           # D2H of the loss
 
-    e2e_ms = time_e2e(e2e_step, args.steps)
+    e2e_ms = time_e2e(e2e_step, args.steps if not args.quick else 1)
     e2e_value = world * 1e3 / e2e_ms
 
     # ---- N > 1: strong scaling of one 2048^2 render split by rows

@@ -35,6 +35,12 @@ lib.dvg_render_forward_rows.argtypes = [_vp, _vp, _vp, _i, _i, _i, _i, _u64, _i,
 lib.dvg_render_forward_rows.restype = _i
 lib.dvg_render_backward_rows.argtypes = [_vp, _vp, _vp, _i, _i, _i, _i, _u64, _i, _i, _i, _vp, _vp, ctypes.c_uint32, _vp]
 lib.dvg_render_backward_rows.restype = _i
+lib.dvg_scene_create_batch.argtypes = [_vp, _i64, _i, _i, ctypes.POINTER(_vp)]
+lib.dvg_scene_create_batch.restype = _i
+lib.dvg_render_forward_batch.argtypes = [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]
+lib.dvg_render_forward_batch.restype = _i
+lib.dvg_render_backward_batch.argtypes = [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, ctypes.c_uint32, _vp]
+lib.dvg_render_backward_batch.restype = _i
 lib.dvg_scene_destroy.argtypes = [_vp]
 lib.dvg_scene_destroy.restype = _i
 lib.dvg_scene_dump.argtypes = [_vp, _i, _i, _vp, _i64, _vp]

@@ -48,7 +48,13 @@ struct BoundarySample {
 // multiplied by a float radius in double, rounded on store (sample_boundary.h:31-34).
 DVG_HD_NOINLINE F2 circle_offset(float radius, float t) {
     float arg = 2 * (float)DVG_PI_D * t;
+#if defined(__CUDA_ARCH__)
+    double sn, cs;
+    sincos((double)arg, &sn, &cs);   // one argument reduction for both
+    return mk2((float)((double)radius * cs), (float)((double)radius * sn));
+#else
     return mk2((float)((double)radius * cos((double)arg)), (float)((double)radius * sin((double)arg)));
+#endif
 }
 
 // sample_boundary.h:80-307.  `pts` = path points, `thick` = per-point thickness or null.
@@ -161,23 +167,28 @@ DVG_HD F2 stroke_offset(F2 ret, F2 &normal, float dir, float stroke_radius) {
 }
 
 // diffvg.cpp:1325-1386 + sample_boundary.h:386-453.  Fills `bs`; bs.inst = -1 when invalid.
-DVG_HD void make_boundary_sample(const SceneView &sc, int idx, uint64_t seed, BoundarySample &bs) {
+// `scene`: which scene of a batch (SceneView): its CDF / instance / shape / segment tables and parameters; `idx` and `seed`
+// are that scene's own.  bs.inst comes back batch-wide.
+DVG_HD void make_boundary_sample(const SceneView &sc, int idx, uint64_t seed, BoundarySample &bs, const float *shape_cdf = nullptr,
+                                 int scene = 0) {
     bs.inst = -1;
     bs.pt = mk2(0, 0);
     Pcg32 rng = pcg32_init(idx, seed);
     float u = pcg32_next_float(rng);
-    int sample_id = cdf_sample(sc.shape_cdf, sc.num_insts, u, nullptr);
-    const InstInfo ii = sc.insts[sample_id];
+    const int inst_base = scene * sc.num_insts;
+    int sample_id = cdf_sample(shape_cdf ? shape_cdf : sc.shape_cdf + inst_base, sc.num_insts, u, nullptr);   // (a staged copy of the same table)
+    const InstInfo ii = sc.insts[inst_base + sample_id];
     int shape_id = ii.shape;
     // Q11: the pmf is looked up by *shape id*, not by sample id (diffvg.cpp:1343).
     // shape_id < num_shapes <= num_insts is not guaranteed by the reference either; clamp the read.
-    float shape_pmf = sc.shape_pmf[shape_id < sc.num_insts ? shape_id : sc.num_insts - 1];
+    float shape_pmf = sc.shape_pmf[inst_base + (shape_id < sc.num_insts ? shape_id : sc.num_insts - 1)];
     if (shape_pmf <= 0) return;
     float t = pcg32_next_float(rng);
     const float t_orig = t;
     const GroupInfo &g = sc.groups[ii.group];
     const int *srec = sc.topo + sc.topo[DVG_H_OFF_SHAPES] + shape_id * DVG_SHAPE_REC_LEN;
-    float stroke_width = srec[DVG_S_WIDTH_OFF] >= 0 ? sc.params[srec[DVG_S_WIDTH_OFF]] : 0.f;
+    const float *params = sc.params + (size_t)scene * sc.num_params;   // this scene's parameters
+    float stroke_width = srec[DVG_S_WIDTH_OFF] >= 0 ? params[srec[DVG_S_WIDTH_OFF]] : 0.f;
     float pdf = 1;
     bool stroke_perturb = false;
     bool has_fill = g.fill_type >= 0, has_stroke = g.stroke_type >= 0;
@@ -196,7 +207,7 @@ DVG_HD void make_boundary_sample(const SceneView &sc, int idx, uint64_t seed, Bo
     F2 local;
     int base_point_id = 0, point_id = 0;
     float path_t = 0;
-    const float *p = sc.params + srec[DVG_S_PARAM_OFF];
+    const float *p = params + srec[DVG_S_PARAM_OFF];
     const float two_pi = 2 * (float)DVG_PI_D;
     switch (srec[DVG_S_TYPE]) {
         case DVG_SHAPE_CIRCLE: {  // sample_boundary.h:20-46
@@ -218,12 +229,12 @@ DVG_HD void make_boundary_sample(const SceneView &sc, int idx, uint64_t seed, Bo
             break;
         }
         case DVG_SHAPE_PATH: {
-            const float *thick = srec[DVG_S_THICK_OFF] >= 0 ? sc.params + srec[DVG_S_THICK_OFF] : nullptr;
+            const float *thick = srec[DVG_S_THICK_OFF] >= 0 ? params + srec[DVG_S_THICK_OFF] : nullptr;
             const int *ncp = sc.topo + sc.topo[DVG_H_OFF_NCP] + srec[DVG_S_NCP_OFF];
-            int so = srec[DVG_S_NCP_OFF];
+            int so = scene * sc.total_segs + srec[DVG_S_NCP_OFF];
             local = sample_boundary_path(p, thick, ncp, srec[DVG_S_NUM_POINTS], srec[DVG_S_NUM_SEGS],
                                          (srec[DVG_S_FLAGS] & DVG_SF_CLOSED) != 0, sc.seg_cdf + so, sc.seg_pmf + so,
-                                         sc.seg_point_id + so, sc.shapes_length[shape_id], t, normal, pdf,
+                                         sc.seg_point_id + so, sc.shapes_length[scene * sc.num_shapes + shape_id], t, normal, pdf,
                                          base_point_id, point_id, path_t, dir, stroke_width);
             break;
         }
@@ -255,7 +266,7 @@ DVG_HD void make_boundary_sample(const SceneView &sc, int idx, uint64_t seed, Bo
     bs.t = t_orig;
     bs.pdf = shape_pmf * pdf;
     bs.path_t = path_t;
-    bs.inst = sample_id;
+    bs.inst = inst_base + sample_id;
     bs.base_point_id = base_point_id;
     bs.point_id_stroke = point_id | (stroke_perturb ? (int)0x80000000 : 0);
 }
@@ -374,7 +385,8 @@ DVG_HD void boundary_gradient_record(const SceneView &sc, const BoundarySample &
     const bool is_stroke = bs.point_id_stroke < 0;
     const int point_id = bs.point_id_stroke & 0x7fffffff;
     const int type = srec[DVG_S_TYPE];
-    const int poff = srec[DVG_S_PARAM_OFF];
+    const int pbase = ii.scene * sc.num_params;   // the scene's slice of the gradient buffer (0 outside batches)
+    const int poff = pbase + srec[DVG_S_PARAM_OFF];
     const float nx = normal.x, ny = normal.y;
     if (type == DVG_SHAPE_PATH) {
         const int np = srec[DVG_S_NUM_POINTS];
@@ -400,16 +412,16 @@ DVG_HD void boundary_gradient_record(const SceneView &sc, const BoundarySample &
         if (is_stroke) {
             const int toff = srec[DVG_S_THICK_OFF];
             if (toff >= 0) {  // diffvg.cpp:110-144
-                gr.addr[9] = toff + i0; gr.val[9] = w0 * contrib;
-                gr.addr[10] = toff + i1; gr.val[10] = w1 * contrib;
-                if (i2 >= 0) { gr.addr[11] = toff + i2; gr.val[11] = w2 * contrib; }
-                if (i3 >= 0) { gr.addr[12] = toff + i3; gr.val[12] = w3 * contrib; }
+                gr.addr[9] = pbase + toff + i0; gr.val[9] = w0 * contrib;
+                gr.addr[10] = pbase + toff + i1; gr.val[10] = w1 * contrib;
+                if (i2 >= 0) { gr.addr[11] = pbase + toff + i2; gr.val[11] = w2 * contrib; }
+                if (i3 >= 0) { gr.addr[12] = pbase + toff + i3; gr.val[12] = w3 * contrib; }
             } else if (srec[DVG_S_WIDTH_OFF] >= 0) {
-                gr.addr[8] = srec[DVG_S_WIDTH_OFF]; gr.val[8] = contrib;
+                gr.addr[8] = pbase + srec[DVG_S_WIDTH_OFF]; gr.val[8] = contrib;
             }
         }
     } else {
-        if (is_stroke && srec[DVG_S_WIDTH_OFF] >= 0) { gr.addr[8] = srec[DVG_S_WIDTH_OFF]; gr.val[8] = contrib; }
+        if (is_stroke && srec[DVG_S_WIDTH_OFF] >= 0) { gr.addr[8] = pbase + srec[DVG_S_WIDTH_OFF]; gr.val[8] = contrib; }
         if (type == DVG_SHAPE_CIRCLE) {
             gr.addr[0] = poff + 1; gr.val[0] = nx * contrib;
             gr.addr[1] = poff + 2; gr.val[1] = ny * contrib;

@@ -10,17 +10,18 @@
 
 namespace dvg {
 
+// (indices run over all scenes of a batch: scene = index / per-scene count, see SceneView)
 __global__ void k_build_shapes(BuildView bv) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s < bv.num_shapes) build_shape(bv, s);
+    if (s < bv.num_shapes * bv.batch) build_shape(bv, s);
 }
 __global__ void k_build_groups(BuildView bv) {
     int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g < bv.num_groups) build_group(bv, g);
+    if (g < bv.num_groups * bv.batch) build_group(bv, g);
 }
 __global__ void k_build_prims(BuildView bv) {
     int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e < bv.num_prims) build_prim(bv, e);
+    if (e < bv.num_prims * bv.batch) build_prim(bv, e);
 }
 
 // scene.cpp:207-246.  Sequential float prefix sum in the reference's order (single thread),
@@ -30,14 +31,18 @@ __global__ void k_build_shape_cdf(BuildView bv) {
     // picks depends on it bit for bit), but its operands need not be fetched by the summing thread: the block
     // stages 4096 lengths at a time in shared memory (two dependent global loads per element would cost the
     // lone thread ~0.3 ms at 2048 shapes), thread 0 sums them there, and the block writes the results back.
+    // One block per scene of a batch.
     constexpr int CH = 4096;
     __shared__ float s_len[CH];
     __shared__ float s_cdf[CH];
     __shared__ float s_carry;
+    const int scene = blockIdx.x;
+    const float *shapes_length = bv.shapes_length + scene * bv.num_shapes;
+    float *shape_cdf = bv.shape_cdf + scene * bv.num_insts, *shape_pmf = bv.shape_pmf + scene * bv.num_insts;
     if (threadIdx.x == 0) s_carry = 0.f;
     for (int base = 0; base < bv.num_insts; base += CH) {
         const int n = min(CH, bv.num_insts - base);
-        for (int i = threadIdx.x; i < n; i += blockDim.x) s_len[i] = bv.shapes_length[bv.inst_shape[base + i]];
+        for (int i = threadIdx.x; i < n; i += blockDim.x) s_len[i] = shapes_length[bv.inst_shape[base + i]];
         __syncthreads();
         if (threadIdx.x == 0) {
             float c = s_carry;
@@ -48,20 +53,20 @@ __global__ void k_build_shape_cdf(BuildView bv) {
             s_carry = c;
         }
         __syncthreads();
-        for (int i = threadIdx.x; i < n; i += blockDim.x) { bv.shape_cdf[base + i] = s_cdf[i]; bv.shape_pmf[base + i] = s_len[i]; }
+        for (int i = threadIdx.x; i < n; i += blockDim.x) { shape_cdf[base + i] = s_cdf[i]; shape_pmf[base + i] = s_len[i]; }
         __syncthreads();
     }
     const float norm = s_carry;
     if (threadIdx.x == 0) {
-        if (!(norm > 0.f)) *bv.error_flag = 1;            // scene.cpp:231-235 (also catches NaN)
-        else if (isinf(norm)) *bv.error_flag = 2;         // scene.cpp:236-240
-        else *bv.error_flag = 0;
-        *bv.total_length = norm;
+        // error flag of the batch: the first degenerate scene wins (flags start at 0, see launch_build)
+        if (!(norm > 0.f)) atomicCAS(bv.error_flag, 0, 1);            // scene.cpp:231-235 (also catches NaN)
+        else if (isinf(norm)) atomicCAS(bv.error_flag, 0, 2);         // scene.cpp:236-240
+        if (scene == 0 || !(norm > 0.f) || isinf(norm)) *bv.total_length = norm;
     }
     __syncthreads();
     for (int i = threadIdx.x; i < bv.num_insts; i += blockDim.x) {
-        bv.shape_cdf[i] /= norm;
-        bv.shape_pmf[i] /= norm;
+        shape_cdf[i] /= norm;
+        shape_pmf[i] /= norm;
     }
 }
 
@@ -110,15 +115,18 @@ __global__ void k_bin_coarse(BuildView bv, BinBuild bb) {
 template <int PASS>
 __global__ void k_bin(BuildView bv, BinBuild bb) {
     const int lane = threadIdx.x & 31;
-    const int warp = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) + bb.tile_row0 * bb.tiles_x;   // = tile
-    if (warp >= bb.tile_row1 * bb.tiles_x) return;
-    const int tx = warp % bb.tiles_x, ty = warp / bb.tiles_x;
+    const int tiles_scene = bb.tiles_x * bb.tiles_y;
+    const int warp = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) + bb.tile_row0 * bb.tiles_x;   // = tile, over all scenes of a batch
+    if (warp >= (bb.batch - 1) * tiles_scene + bb.tile_row1 * bb.tiles_x) return;
+    const int scene = warp / tiles_scene, ltile = warp - scene * tiles_scene;
+    const int tx = ltile % bb.tiles_x, ty = ltile / bb.tiles_x;
+    const int e_base = scene * bv.num_prims, g_base = scene * bv.num_groups;   // this scene's slice of the primitive / group tables
     float x0, y0, x1, y1;
     tiles_rect(bv, bb, tx, ty, tx, ty, x0, y0, x1, y1);
     int count = 0;
     int *out = nullptr;
     if (PASS == 1) out = bb.items + bb.offsets[warp];
-    if (bb.super) {
+    if (bb.super) {   // (single scenes only)
         const int si = (ty / bb.super) * bb.stiles_x + tx / bb.super;
         const int *list = bb.s_items + (size_t)si * bv.num_prims;
         const int n = bb.s_counts[si];
@@ -135,8 +143,8 @@ __global__ void k_bin(BuildView bv, BinBuild bb) {
         // few primitives per group (painterly strokes: 2 per group): walk the primitives directly, 32 per trip;
         // their canvas boxes are already clipped to the group's scene-BVH leaf box, so the group test adds nothing
         for (int e0 = 0; e0 < bv.num_prims; e0 += 32) {
-            const int e = e0 + lane;
-            bool ph = e < bv.num_prims && overlaps(bb.prefilter ? bv.prim_cbox_pf[e] : bv.prim_cbox[e], x0, y0, x1, y1);
+            const int e = e_base + e0 + lane;
+            bool ph = e0 + lane < bv.num_prims && overlaps(bb.prefilter ? bv.prim_cbox_pf[e] : bv.prim_cbox[e], x0, y0, x1, y1);
             if (ph && !bb.prefilter && (bv.prim_meta[e].type_flags & DVG_PF_TIGHT))
                 ph = bracket_reaches_tile(bv.prim_cap + (size_t)e * DVG_CAP_F4, x0, y0, x1, y1);
             const unsigned pmask = __ballot_sync(0xffffffffu, ph);
@@ -150,7 +158,7 @@ __global__ void k_bin(BuildView bv, BinBuild bb) {
         if (g < bv.num_groups) {
             if (bv.num_groups == 1) hit = true;
             else {
-                const GroupInfo &gi = bv.groups[g];
+                const GroupInfo &gi = bv.groups[g_base + g];
                 Box b = gi.scene_box; float r = gi.scene_r;
                 b.x0 -= r; b.y0 -= r; b.x1 += r; b.y1 += r;
                 hit = overlaps(b, x0, y0, x1, y1) || !(b.x0 == b.x0 && b.x1 == b.x1 && b.y0 == b.y0 && b.y1 == b.y1);
@@ -160,7 +168,7 @@ __global__ void k_bin(BuildView bv, BinBuild bb) {
         while (gm) {
             int gl = __ffs(gm) - 1;
             gm &= gm - 1;
-            const GroupInfo &gi = bv.groups[g0 + gl];
+            const GroupInfo &gi = bv.groups[g_base + g0 + gl];
             for (int e0 = gi.prim_begin; e0 < gi.prim_end; e0 += 32) {
                 int e = e0 + lane;
                 bool ph = e < gi.prim_end && overlaps(bb.prefilter ? bv.prim_cbox_pf[e] : bv.prim_cbox[e], x0, y0, x1, y1);
@@ -175,34 +183,69 @@ __global__ void k_bin(BuildView bv, BinBuild bb) {
     if (PASS == 0 && lane == 0) bb.counts[warp] = count;
 }
 
-// Single-block exclusive scan of `n` ints (n up to a few hundred thousand tiles): each thread
-// scans a contiguous slice, then a block-level scan of the slice totals.  out has n+1 entries.
-__global__ void k_exclusive_scan(const int *in, int *out, int n) {
-    __shared__ int s_tot[1024];
-    const int T = blockDim.x, t = threadIdx.x;
-    const int per = (n + T - 1) / T;
-    const int b = t * per, e = min(b + per, n);
-    int sum = 0;
-    for (int i = b; i < e; i++) sum += in[i];
-    s_tot[t] = sum;
+// Single-block exclusive scan of `n` ints (tile counts: 16 k at 512^2, 262 k at 2048^2); out has n+1 entries.  The block
+// walks the array in rounds of 1024 x 4 elements: coalesced 16-byte loads, a shuffle scan per warp, one shared-memory step
+// across the 32 warps, a running carry.
+__global__ void __launch_bounds__(1024) k_exclusive_scan(const int *in, int *out, int n) {
+    __shared__ int s_warp[32];
+    __shared__ int s_carry;
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    if (t == 0) s_carry = 0;
     __syncthreads();
-    for (int off = 1; off < T; off <<= 1) {
-        int v = t >= off ? s_tot[t - off] : 0;
+    for (int base = 0; base < n; base += 4096) {
+        const int i = base + 4 * t;
+        int v0 = 0, v1 = 0, v2 = 0, v3 = 0;
+        if (i + 3 < n && ((reinterpret_cast<uintptr_t>(in) & 15) == 0)) {
+            const int4 q = *reinterpret_cast<const int4 *>(in + i);
+            v0 = q.x; v1 = q.y; v2 = q.z; v3 = q.w;
+        } else {
+            if (i < n) v0 = in[i];
+            if (i + 1 < n) v1 = in[i + 1];
+            if (i + 2 < n) v2 = in[i + 2];
+            if (i + 3 < n) v3 = in[i + 3];
+        }
+        const int mine = v0 + v1 + v2 + v3;
+        int incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += u;
+        }
+        if (lane == 31) s_warp[w] = incl;
         __syncthreads();
-        s_tot[t] += v;
+        if (w == 0) {
+            int x = s_warp[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_up_sync(0xffffffffu, x, o);
+                if (lane >= o) x += u;
+            }
+            s_warp[lane] = x;   // inclusive over warps
+        }
+        __syncthreads();
+        const int carry = s_carry;
+        int run = carry + (w ? s_warp[w - 1] : 0) + incl - mine;
+        if (i < n) out[i] = run;
+        run += v0;
+        if (i + 1 < n) out[i + 1] = run;
+        run += v1;
+        if (i + 2 < n) out[i + 2] = run;
+        run += v2;
+        if (i + 3 < n) out[i + 3] = run;
+        __syncthreads();
+        if (t == 1023) s_carry = carry + s_warp[31];
         __syncthreads();
     }
-    int run = s_tot[t] - sum;
-    for (int i = b; i < e; i++) { out[i] = run; run += in[i]; }
-    if (t == T - 1) out[n] = s_tot[T - 1];
+    if (t == 0) out[n] = s_carry;
 }
 
 void launch_build(const BuildView &bv, cudaStream_t st) {
     const int B = 128;
-    DVG_LAUNCH(k_build_shapes, dim3((bv.num_shapes + B - 1) / B), dim3(B), 0, st, bv);
-    DVG_LAUNCH(k_build_groups, dim3((bv.num_groups + B - 1) / B), dim3(B), 0, st, bv);
-    DVG_LAUNCH(k_build_prims, dim3((bv.num_prims + B - 1) / B), dim3(B), 0, st, bv);
-    DVG_LAUNCH(k_build_shape_cdf, dim3(1), dim3(256), 0, st, bv);
+    cudaMemsetAsync(bv.error_flag, 0, sizeof(int), st);
+    DVG_LAUNCH(k_build_shapes, dim3((bv.num_shapes * bv.batch + B - 1) / B), dim3(B), 0, st, bv);
+    DVG_LAUNCH(k_build_groups, dim3((bv.num_groups * bv.batch + B - 1) / B), dim3(B), 0, st, bv);
+    DVG_LAUNCH(k_build_prims, dim3((bv.num_prims * bv.batch + B - 1) / B), dim3(B), 0, st, bv);
+    DVG_LAUNCH(k_build_shape_cdf, dim3(bv.batch), dim3(256), 0, st, bv);
 }
 
 void launch_bin_coarse(const BuildView &bv, const BinBuild &bb, cudaStream_t st) {
@@ -211,15 +254,15 @@ void launch_bin_coarse(const BuildView &bv, const BinBuild &bb, cudaStream_t st)
     DVG_LAUNCH(k_bin_coarse, dim3((ns * 32 + 127) / 128), dim3(128), 0, st, bv, bb);
 }
 void launch_bin_count(const BuildView &bv, const BinBuild &bb, cudaStream_t st) {
-    const int ntiles = bb.tiles_x * bb.tiles_y;
-    const int nbin = (bb.tile_row1 - bb.tile_row0) * bb.tiles_x;
+    const int ntiles = bb.tiles_x * bb.tiles_y * bb.batch;
+    const int nbin = bb.batch > 1 ? ntiles : (bb.tile_row1 - bb.tile_row0) * bb.tiles_x;
     const int B = 128;  // 4 warps = 4 tiles per block
     if (nbin < ntiles) cudaMemsetAsync(bb.counts, 0, sizeof(int) * ntiles, st);
     if (nbin > 0) DVG_LAUNCH(k_bin<0>, dim3((nbin * 32 + B - 1) / B), dim3(B), 0, st, bv, bb);
     DVG_LAUNCH(k_exclusive_scan, dim3(1), dim3(1024), 0, st, bb.counts, bb.offsets, ntiles);
 }
 void launch_bin_fill(const BuildView &bv, const BinBuild &bb, cudaStream_t st) {
-    const int nbin = (bb.tile_row1 - bb.tile_row0) * bb.tiles_x;
+    const int nbin = bb.batch > 1 ? bb.tiles_x * bb.tiles_y * bb.batch : (bb.tile_row1 - bb.tile_row0) * bb.tiles_x;
     const int B = 128;
     if (nbin > 0) DVG_LAUNCH(k_bin<1>, dim3((nbin * 32 + B - 1) / B), dim3(B), 0, st, bv, bb);
 }

@@ -10,7 +10,8 @@ namespace dvg {
 // Mutable view used by the build kernels (same arrays as SceneView, non-const).
 struct BuildView {
     int canvas_w, canvas_h;
-    int num_shapes, num_groups, num_insts, num_prims;
+    int num_shapes, num_groups, num_insts, num_prims;   // per scene
+    int batch, num_params, total_segs;                  // scenes of this topology laid out back to back (SceneView)
     const int *topo;
     const float *params;
     // topology-only maps (host-built at scene creation)
@@ -31,9 +32,11 @@ struct BuildView {
 // shapes_length (scene.cpp:113-205), shapes_bbox (499-629), per-path segment pmf/cdf/point-id
 // map (248-333) and the "first leaf after the y-sort" radius the reference uses as the group
 // radius of thickness paths (scene.cpp:602-618, 650-667).
-DVG_HD_NOINLINE void build_shape(const BuildView &bv, int s) {
+DVG_HD_NOINLINE void build_shape(const BuildView &bv, int s_batch) {
     const int *topo = bv.topo;
-    const float *P = bv.params;
+    const int scene = s_batch / bv.num_shapes, s = s_batch - scene * bv.num_shapes;
+    const float *P = bv.params + (size_t)scene * bv.num_params;
+    const int seg_base = scene * bv.total_segs;
     const int *r = topo + topo[DVG_H_OFF_SHAPES] + s * DVG_SHAPE_REC_LEN;
     const float *p = P + r[DVG_S_PARAM_OFF];
     float stroke_width = r[DVG_S_WIDTH_OFF] >= 0 ? P[r[DVG_S_WIDTH_OFF]] : 0.f;
@@ -62,9 +65,9 @@ DVG_HD_NOINLINE void build_shape(const BuildView &bv, int s) {
             const int np = r[DVG_S_NUM_POINTS], nseg = r[DVG_S_NUM_SEGS];
             const int *ncp = topo + topo[DVG_H_OFF_NCP] + r[DVG_S_NCP_OFF];
             const float *thick = r[DVG_S_THICK_OFF] >= 0 ? P + r[DVG_S_THICK_OFF] : nullptr;
-            float *seg_pmf = bv.seg_pmf + r[DVG_S_NCP_OFF];
-            float *seg_cdf = bv.seg_cdf + r[DVG_S_NCP_OFF];
-            int *seg_pid = bv.seg_point_id + r[DVG_S_NCP_OFF];
+            float *seg_pmf = bv.seg_pmf + seg_base + r[DVG_S_NCP_OFF];
+            float *seg_cdf = bv.seg_cdf + seg_base + r[DVG_S_NCP_OFF];
+            int *seg_pid = bv.seg_point_id + seg_base + r[DVG_S_NCP_OFF];
             box.x0 = box.y0 = INFINITY; box.x1 = box.y1 = -INFINITY;
             if (np > 0) { box.x0 = box.x1 = p[0]; box.y0 = box.y1 = p[1]; }
             for (int i = 1; i < np; i++) {
@@ -125,9 +128,9 @@ DVG_HD_NOINLINE void build_shape(const BuildView &bv, int s) {
             break;
         }
     }
-    bv.shapes_length[s] = len;
-    bv.shape_box[s] = box;
-    bv.shape_r0[s] = r0q;
+    bv.shapes_length[s_batch] = len;
+    bv.shape_box[s_batch] = box;
+    bv.shape_r0[s_batch] = r0q;
 }
 
 DVG_HD Box box_merge(Box a, Box b) {
@@ -152,19 +155,23 @@ DVG_HD Box box_transform(const float *m, Box b) {  // aabb.h:52-60
 
 // ------------------------------------------------------------------ groups
 // transforms, group root box, scene-BVH leaf box and radius (scene.cpp:632-682, shape.h:122-124)
-DVG_HD_NOINLINE void build_group(const BuildView &bv, int g) {
+DVG_HD_NOINLINE void build_group(const BuildView &bv, int g_batch) {
     const int *topo = bv.topo;
-    const float *P = bv.params;
+    const int scene = g_batch / bv.num_groups, g = g_batch - scene * bv.num_groups;
+    const int pbase = scene * bv.num_params;   // colour / transform offsets are stored absolute (see SceneView)
+    const float *P = bv.params + pbase;
     const int *r = topo + topo[DVG_H_OFF_GROUPS] + g * DVG_GROUP_REC_LEN;
     const int *ids = topo + topo[DVG_H_OFF_GSHAPES] + r[DVG_G_SHAPES_OFF];
+    const Box *shape_box = bv.shape_box + scene * bv.num_shapes;
+    const float *shape_r0 = bv.shape_r0 + scene * bv.num_shapes;
     GroupInfo gi;
-    gi.fill_type = r[DVG_G_FILL_TYPE]; gi.fill_off = r[DVG_G_FILL_OFF]; gi.fill_stops = r[DVG_G_FILL_STOPS];
-    gi.stroke_type = r[DVG_G_STROKE_TYPE]; gi.stroke_off = r[DVG_G_STROKE_OFF]; gi.stroke_stops = r[DVG_G_STROKE_STOPS];
+    gi.fill_type = r[DVG_G_FILL_TYPE]; gi.fill_off = pbase + r[DVG_G_FILL_OFF]; gi.fill_stops = r[DVG_G_FILL_STOPS];
+    gi.stroke_type = r[DVG_G_STROKE_TYPE]; gi.stroke_off = pbase + r[DVG_G_STROKE_OFF]; gi.stroke_stops = r[DVG_G_STROKE_STOPS];
     gi.num_shapes = r[DVG_G_NUM_SHAPES];
-    gi.inst_begin = r[DVG_G_SHAPES_OFF];
-    gi.prim_begin = bv.inst_prim_begin[gi.inst_begin];
-    gi.prim_end = bv.inst_prim_begin[gi.inst_begin + gi.num_shapes];
-    gi.xform_off = r[DVG_G_XFORM_OFF];
+    gi.inst_begin = scene * bv.num_insts + r[DVG_G_SHAPES_OFF];
+    gi.prim_begin = scene * bv.num_prims + bv.inst_prim_begin[r[DVG_G_SHAPES_OFF]];
+    gi.prim_end = scene * bv.num_prims + bv.inst_prim_begin[r[DVG_G_SHAPES_OFF] + gi.num_shapes];
+    gi.xform_off = pbase + r[DVG_G_XFORM_OFF];
     gi.pad = 0;
     const float *m = P + r[DVG_G_XFORM_OFF];
     for (int k = 0; k < 9; k++) gi.s2c[k] = m[k];
@@ -173,17 +180,17 @@ DVG_HD_NOINLINE void build_group(const BuildView &bv, int g) {
                  m[6] == 0.f && m[7] == 0.f && m[8] == 1.f;
     bool affine = m[6] == 0.f && m[7] == 0.f && m[8] == 1.f;
     gi.flags = (r[DVG_G_EVEN_ODD] ? DVG_GF_EVEN_ODD : 0) | (ident ? DVG_GF_IDENTITY : 0) | (affine ? DVG_GF_AFFINE : 0);
-    Box lb = bv.shape_box[ids[0]];
-    float max_radius = bv.shape_r0[ids[0]];
+    Box lb = shape_box[ids[0]];
+    float max_radius = shape_r0[ids[0]];
     for (int k = 1; k < gi.num_shapes; k++) {
-        lb = box_merge(lb, bv.shape_box[ids[k]]);
-        float rr = bv.shape_r0[ids[k]];
+        lb = box_merge(lb, shape_box[ids[k]]);
+        float rr = shape_r0[ids[k]];
         max_radius = max_radius > rr ? max_radius : rr;  // std::max(a, b): (a < b) ? b : a
     }
     gi.local_box = lb;
     gi.scene_box = box_transform(gi.s2c, lb);
     gi.scene_r = gi.stroke_type < 0 ? 0.f : max_radius;
-    bv.groups[g] = gi;
+    bv.groups[g_batch] = gi;
 }
 
 // ------------------------------------------------------------------ reject capsules
@@ -279,11 +286,15 @@ DVG_HD bool bracket_reaches_tile(const F4 *cap, float x0, float y0, float x1, fl
 // ------------------------------------------------------------------ primitives
 // Leaf boxes and radii follow scene.cpp:527-600 (topology-only maps prim -> inst / segment /
 // first point come from the host).
-DVG_HD_NOINLINE void build_prim(const BuildView &bv, int e) {
+DVG_HD_NOINLINE void build_prim(const BuildView &bv, int e_batch) {
     const int *topo = bv.topo;
-    const float *P = bv.params;
-    const int inst = bv.prim_inst[e];
-    const int g = bv.inst_group[inst], s = bv.inst_shape[inst];
+    const int scene = e_batch / bv.num_prims, e_local = e_batch - scene * bv.num_prims;
+    const float *P = bv.params + (size_t)scene * bv.num_params;
+    const int inst_local = bv.prim_inst[e_local];
+    const int inst = scene * bv.num_insts + inst_local;                       // batch-wide ids from here on
+    const int g = scene * bv.num_groups + bv.inst_group[inst_local], s = bv.inst_shape[inst_local];   // s: id inside the scene
+    const int e = e_batch;
+    const Box *shape_boxes = bv.shape_box + scene * bv.num_shapes;
     const GroupInfo &gi = bv.groups[g];
     const int *r = topo + topo[DVG_H_OFF_SHAPES] + s * DVG_SHAPE_REC_LEN;
     const float *p = P + r[DVG_S_PARAM_OFF];
@@ -295,26 +306,26 @@ DVG_HD_NOINLINE void build_prim(const BuildView &bv, int e) {
     PrimMeta pm;
     pm.inst = inst; pm.point_id = 0; pm.base_id = 0;
     int tf;
-    const bool first_in_inst = (e == bv.inst_prim_begin[inst]);
+    const bool first_in_inst = (e_local == bv.inst_prim_begin[inst_local]);
     switch (r[DVG_S_TYPE]) {
         case DVG_SHAPE_CIRCLE:
             tf = PRIM_CIRCLE | DVG_PF_SINGLE;
             p01 = mk4(p[1], p[2], p[0], 0.f);
-            box = bv.shape_box[s];
+            box = shape_boxes[s];
             break;
         case DVG_SHAPE_ELLIPSE:
             tf = PRIM_ELLIPSE | DVG_PF_SINGLE;
             p01 = mk4(p[2], p[3], p[0], p[1]);
-            box = bv.shape_box[s];
+            box = shape_boxes[s];
             break;
         case DVG_SHAPE_RECT:
             tf = PRIM_RECT | DVG_PF_SINGLE;
             p01 = mk4(p[0], p[1], p[2], p[3]);
-            box = bv.shape_box[s];
+            box = shape_boxes[s];
             break;
         default: {
             const int np = r[DVG_S_NUM_POINTS], nseg = r[DVG_S_NUM_SEGS];
-            const int seg = bv.prim_seg[e], pid = bv.prim_point_id[e];
+            const int seg = bv.prim_seg[e_local], pid = bv.prim_point_id[e_local];
             const int *ncp = topo + topo[DVG_H_OFF_NCP] + r[DVG_S_NCP_OFF];
             const float *th = r[DVG_S_THICK_OFF] >= 0 ? P + r[DVG_S_THICK_OFF] : nullptr;
             pm.point_id = pid; pm.base_id = seg;
@@ -370,9 +381,9 @@ DVG_HD_NOINLINE void build_prim(const BuildView &bv, int e) {
     }
     if (first_in_inst) {
         InstInfo ii;
-        ii.box = bv.shape_box[s];
+        ii.box = shape_boxes[s];
         ii.r = has_stroke ? sw : 0.f;   // scene.cpp:638
-        ii.group = g; ii.shape = s; ii.prim_begin = e;
+        ii.group = g; ii.shape = s; ii.prim_begin = e; ii.scene = scene;
         bv.insts[inst] = ii;
     }
     // Conservative canvas-space bound of the region where this primitive can change a sample

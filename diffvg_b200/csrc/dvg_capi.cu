@@ -23,9 +23,6 @@ float *g_debug_out = nullptr;  // dvg_debug_set_boundary_dump
 long long g_debug_edge_pass_samples = 0;   // dvg_debug_set_limits
 long long g_debug_pair_capacity = 0;
 bool g_fast_accept = getenv("DVG_FAST_ACCEPT") != nullptr && getenv("DVG_FAST_ACCEPT")[0] == '1';   // dvg_set_fast_stroke_accept (env: measurements only)
-// A/B switch for measurements: DVG_FUSED=1 in the environment selects the one-kernel-per-pass form of
-// dvg_render.cu instead of the wavefront passes of dvg_wave.cu (same arithmetic, same results).
-bool g_fused = getenv("DVG_FUSED") != nullptr && getenv("DVG_FUSED")[0] == '1';
 
 int fail(int code, const std::string &msg) {
     g_err = msg;
@@ -69,7 +66,14 @@ struct DvgScene {
     int device = 0;
     std::vector<int32_t> topo;
     int canvas_w = 0, canvas_h = 0, num_shapes = 0, num_groups = 0, num_insts = 0, num_prims = 0;
-    int num_params = 0, total_segs = 0;
+    int num_params = 0, total_segs = 0;   // per scene
+    // BATCH (dvg_scene_create_batch): `batch` scenes of this topology live back to back in every table below (SceneView);
+    // the counts above stay per scene.  Seeds: one per scene, uploaded when they change; `seeds_version` stands in for
+    // the seed in the reuse keys of the weight image and of the forward pass's result words.
+    int batch = 1;
+    DevBuf d_seeds;
+    std::vector<uint64_t> seeds_host;
+    uint64_t seeds_version = 0;
     // host topology maps
     std::vector<int> inst_group, inst_shape, inst_prim_begin, prim_inst, prim_seg, prim_point_id;
     // device: topology
@@ -89,7 +93,7 @@ struct DvgScene {
     DevBuf d_keys, d_tile_counts, d_tile_offsets, d_tile_fill, d_blk_counts, d_blk_offsets, d_sorted;
     // wavefront passes (dvg_wave.cu)
     DevBuf d_wave_hit, d_wave_wind, d_wave_pairs_s, d_wave_pairs_f, d_wave_units_a, d_wave_units_d, d_wave_counters, d_tile_nch, d_tile_choff,
-        d_edge_chunks, d_edge_choff, d_wave_max, d_bsamples, d_item_tile, d_grad_rep;
+        d_edge_chunks, d_edge_choff, d_wave_max, d_bsamples, d_bsamples_raw, d_item_tile, d_grad_rep;
     DevBuf d_bvh_path, d_bvh_group, d_bvh_scene, d_bvh_keys;   // reference-topology trees (dvg_bvh.cu), built on demand by dvg_scene_dump
     int total_chunks = 0, max_nch = 0;   // of the current bins (read back with the bin total)
     bool has_fills = false;
@@ -113,6 +117,7 @@ struct DvgScene {
         BuildView bv;
         bv.canvas_w = canvas_w; bv.canvas_h = canvas_h;
         bv.num_shapes = num_shapes; bv.num_groups = num_groups; bv.num_insts = num_insts; bv.num_prims = num_prims;
+        bv.batch = batch; bv.num_params = num_params; bv.total_segs = total_segs;
         bv.topo = d_topo.as<int>(); bv.params = d_params.as<float>();
         bv.inst_group = d_inst_group.as<int>(); bv.inst_shape = d_inst_shape.as<int>();
         bv.inst_prim_begin = d_inst_prim_begin.as<int>();
@@ -131,6 +136,7 @@ struct DvgScene {
         SceneView sc;
         sc.canvas_w = canvas_w; sc.canvas_h = canvas_h;
         sc.num_shapes = num_shapes; sc.num_groups = num_groups; sc.num_insts = num_insts; sc.num_prims = num_prims;
+        sc.batch = batch; sc.num_params = num_params; sc.total_segs = total_segs;
         sc.filter.type = topo[DVG_H_FILTER_TYPE];
         sc.filter.radius = filter_radius_host;
         sc.filter_radius_off = topo[DVG_H_FILTER_RADIUS_OFF];
@@ -147,7 +153,7 @@ struct DvgScene {
     }
     BinView bin_view() {
         BinView b;
-        b.tile_w = bin_tw; b.tile_h = bin_th;
+        b.tile_w = bin_tw; b.tile_h = bin_th; b.batch = batch;
         b.tiles_x = (bin_w + bin_tw - 1) / bin_tw; b.tiles_y = (bin_h + bin_th - 1) / bin_th;
         b.offsets = d_bin_offsets.as<int>(); b.items = d_bin_items.as<int>();
         return b;
@@ -159,8 +165,8 @@ struct DvgScene {
                          &d_shape_cdf, &d_shape_pmf, &d_flags, &d_bin_counts, &d_bin_offsets, &d_bin_items, &d_sbin_counts, &d_sbin_items, &d_weight,
                          &d_keys, &d_tile_counts, &d_tile_offsets, &d_tile_fill, &d_blk_counts, &d_blk_offsets, &d_sorted,
                          &d_wave_hit, &d_wave_wind, &d_wave_pairs_s, &d_wave_pairs_f, &d_wave_units_a, &d_wave_units_d, &d_wave_counters, &d_tile_nch, &d_tile_choff,
-                         &d_edge_chunks, &d_edge_choff, &d_wave_max, &d_bsamples, &d_item_tile, &d_grad_rep,
-                         &d_bvh_path, &d_bvh_group, &d_bvh_scene, &d_bvh_keys};
+                         &d_edge_chunks, &d_edge_choff, &d_wave_max, &d_bsamples, &d_bsamples_raw, &d_item_tile, &d_grad_rep,
+                         &d_bvh_path, &d_bvh_group, &d_bvh_scene, &d_bvh_keys, &d_seeds};
         for (DevBuf *b : all) b->release();
         if (h_pinned) cudaFreeHost(h_pinned);
         h_pinned = nullptr;
@@ -310,10 +316,11 @@ int ensure_bins(DvgScene *s, int width, int height, int spp, int pf, cudaStream_
         s->bin_r0 <= r0 && s->bin_r1 >= r1) return finish_build(s, st);
     BinBuild bb;
     bb.width = width; bb.height = height; bb.tile_w = tw; bb.tile_h = th; bb.prefilter = pf;
+    bb.batch = s->batch;
     bb.flat = s->num_prims <= 4 * s->num_groups ? 1 : 0;
     bb.tile_row0 = r0; bb.tile_row1 = r1;
     bb.tiles_x = (width + tw - 1) / tw; bb.tiles_y = (height + th - 1) / th;
-    const int ntiles = bb.tiles_x * bb.tiles_y;
+    const int ntiles = bb.tiles_x * bb.tiles_y * s->batch;   // a batch: every scene's tiles, scene after scene
     CK(s->d_bin_counts.ensure(sizeof(int) * ntiles));
     CK(s->d_bin_offsets.ensure(sizeof(int) * (ntiles + 1)));
     bb.counts = s->d_bin_counts.as<int>(); bb.offsets = s->d_bin_offsets.as<int>(); bb.items = nullptr;
@@ -321,7 +328,7 @@ int ensure_bins(DvgScene *s, int width, int height, int spp, int pf, cudaStream_
     bb.super = 8;
     bb.stiles_x = (bb.tiles_x + bb.super - 1) / bb.super; bb.stiles_y = (bb.tiles_y + bb.super - 1) / bb.super;
     const int64_t sentries = (int64_t)bb.stiles_x * bb.stiles_y * s->num_prims;
-    if (ntiles < 256 || s->num_prims < 64 || sentries > ((int64_t)1 << 25)) bb.super = 0;
+    if (ntiles < 256 || s->num_prims < 64 || sentries > ((int64_t)1 << 25) || s->batch > 1) bb.super = 0;
     bb.s_counts = nullptr; bb.s_items = nullptr;
     if (bb.super) {
         CK(s->d_sbin_counts.ensure(sizeof(int) * (size_t)bb.stiles_x * bb.stiles_y));
@@ -336,7 +343,7 @@ int ensure_bins(DvgScene *s, int width, int height, int spp, int pf, cudaStream_
     CK(s->d_wave_max.ensure(sizeof(int)));
     launch_wave_tile_chunks(bb.offsets, s->d_tile_nch.as<int>(), s->d_tile_choff.as<int>(), s->d_wave_max.as<int>(), ntiles, st);
     int total;
-    const int64_t nbin = (int64_t)(r1 - r0) * bb.tiles_x;
+    const int64_t nbin = s->batch > 1 ? ntiles : (int64_t)(r1 - r0) * bb.tiles_x;
     if (nbin * s->num_prims <= kSmallBins) {
         // small scene (batched 64x64 scenes, single shapes): size everything for the worst case -- every primitive in
         // every tile -- and skip the read-back of the totals
@@ -370,13 +377,14 @@ int ensure_bins(DvgScene *s, int width, int height, int spp, int pf, cudaStream_
 // rows [r0, r1): the pixel rows whose weights the caller reads.  A forward row shard and the prefiltered backward pass
 // read their own rows; the boundary pass of the sampled backward path gathers d_image anywhere: whole image.
 int ensure_weight(DvgScene *s, const SceneView &sc, RenderArgs &ra, int r0, int r1, cudaStream_t st) {
-    CK(s->d_weight.ensure(sizeof(float) * (size_t)ra.width * ra.height));
+    const size_t wpx = (size_t)ra.width * ra.height * s->batch;
+    CK(s->d_weight.ensure(sizeof(float) * wpx));
     ra.weight_image = s->d_weight.as<float>();
     if (s->w_valid && s->w_w == ra.width && s->w_h == ra.height && s->w_nsx == ra.nsx && s->w_nsy == ra.nsy &&
         s->w_seed == ra.seed && s->w_ftype == sc.filter.type && s->w_radius == sc.filter.radius &&
         s->w_r0 <= r0 && s->w_r1 >= r1)
         return DVG_OK;  // weights depend only on (size, spp, seed, filter, rows): reuse forward's in backward
-    CK(cudaMemsetAsync(ra.weight_image, 0, sizeof(float) * (size_t)ra.width * ra.height, st));
+    CK(cudaMemsetAsync(ra.weight_image, 0, sizeof(float) * wpx, st));
     launch_weight(sc, ra, r0, r1, st);
     s->w_valid = true; s->w_w = ra.width; s->w_h = ra.height; s->w_nsx = ra.nsx; s->w_nsy = ra.nsy;
     s->w_seed = ra.seed; s->w_ftype = sc.filter.type; s->w_radius = sc.filter.radius; s->w_r0 = r0; s->w_r1 = r1;
@@ -497,14 +505,16 @@ int wave_pixel_pass(DvgScene *s, const SceneView &sc, const BinView &bins, const
 // Boundary pass (diffvg.cpp:1558-1626) over the boundary-sample indices [bw.sample_begin, + bw.num_samples).  `bw` comes
 // with its sort buffers bound.
 int wave_edge_pass(DvgScene *s, const SceneView &sc, const BinView &bins, const RenderArgs &ra, BoundaryWork &bw, cudaStream_t st) {
-    const int ntiles = bins.tiles_x * bins.tiles_y;
+    const int ntiles = bin_total_tiles(bins);
     const int spi = wave_edge_samples_per_item();
     bw.max_blocks = bw.num_samples / spi + ntiles;        // upper bound on the boundary items
     CK(s->d_edge_chunks.ensure(sizeof(int) * ntiles));
     CK(s->d_edge_choff.ensure(sizeof(int) * (ntiles + 1)));
     CK(s->d_bsamples.ensure(sizeof(BoundarySample) * (size_t)bw.num_samples));
+    CK(s->d_bsamples_raw.ensure(sizeof(BoundarySample) * (size_t)bw.num_samples));
     CK(s->d_item_tile.ensure(sizeof(int) * (size_t)bw.max_blocks));
     bw.samples = s->d_bsamples.as<BoundarySample>();
+    bw.samples_unsorted = s->d_bsamples_raw.as<BoundarySample>();
     bw.item_tile = s->d_item_tile.as<int>();
     WaveView wv;
     // every item of a tile has that tile's chunk count: bounded by max_nch without another read-back
@@ -552,7 +562,12 @@ const char *dvg_last_error(void) { return g_err.c_str(); }
 int64_t dvg_kernel_launch_count(void) { return dvg::g_launch_count; }
 
 int dvg_scene_create(const int32_t *topo, int64_t topo_len, int device, DvgScene **out_scene) {
+    return dvg_scene_create_batch(topo, topo_len, device, 1, out_scene);
+}
+
+int dvg_scene_create_batch(const int32_t *topo, int64_t topo_len, int device, int batch, DvgScene **out_scene) {
     if (!topo || !out_scene) return fail(DVG_ERR_INVALID, "null argument");
+    if (batch < 1) return fail(DVG_ERR_INVALID, "batch must be at least 1");
     int rc = validate_topo(topo, topo_len);
     if (rc) return rc;
     int ndev = 0;
@@ -561,6 +576,7 @@ int dvg_scene_create(const int32_t *topo, int64_t topo_len, int device, DvgScene
     DeviceGuard guard(device);
     DvgScene *s = new DvgScene();
     s->device = device;
+    s->batch = batch;
     s->topo.assign(topo, topo + topo_len);
     const int32_t *t = s->topo.data();
     s->canvas_w = t[DVG_H_CANVAS_W]; s->canvas_h = t[DVG_H_CANVAS_H];
@@ -602,7 +618,7 @@ int dvg_scene_create(const int32_t *topo, int64_t topo_len, int device, DvgScene
     }
     s->inst_prim_begin.push_back((int)s->prim_inst.size());
     s->num_prims = (int)s->prim_inst.size();
-    if (s->prim_inst.size() >= ((size_t)1 << 28)) { delete s; return fail(DVG_ERR_UNSUPPORTED, "more than 2^28 primitives (the pair queue packs the primitive id in 28 bits)"); }
+    if (s->prim_inst.size() * (size_t)batch >= ((size_t)1 << 28)) { delete s; return fail(DVG_ERR_UNSUPPORTED, "more than 2^28 primitives (the pair queue packs the primitive id in 28 bits)"); }
     rc = upload(s->d_topo, s->topo);
     if (!rc) rc = upload(s->d_inst_group, s->inst_group);
     if (!rc) rc = upload(s->d_inst_shape, s->inst_shape);
@@ -611,8 +627,9 @@ int dvg_scene_create(const int32_t *topo, int64_t topo_len, int device, DvgScene
     if (!rc) rc = upload(s->d_prim_seg, s->prim_seg);
     if (!rc) rc = upload(s->d_prim_point_id, s->prim_point_id);
     auto ens = [&](DevBuf &b, size_t bytes) { if (!rc && b.ensure(std::max<size_t>(bytes, 16)) != cudaSuccess) rc = fail(DVG_ERR_CUDA, "cudaMalloc failed"); };
-    const size_t ns = s->num_shapes, ng = s->num_groups, ni = s->num_insts, npr = s->num_prims, nsg = std::max(s->total_segs, 1);
-    ens(s->d_params, sizeof(float) * s->num_params);
+    const size_t B = (size_t)batch;   // every derived table holds the scenes of a batch back to back
+    const size_t ns = s->num_shapes * B, ng = s->num_groups * B, ni = s->num_insts * B, npr = s->num_prims * B, nsg = std::max(s->total_segs, 1) * B;
+    ens(s->d_params, sizeof(float) * s->num_params * B);
     ens(s->d_shapes_length, 4 * ns); ens(s->d_shape_box, sizeof(Box) * ns); ens(s->d_shape_r0, 4 * ns);
     ens(s->d_seg_cdf, 4 * nsg); ens(s->d_seg_pmf, 4 * nsg); ens(s->d_seg_point_id, 4 * nsg);
     ens(s->d_insts, sizeof(InstInfo) * ni); ens(s->d_groups, sizeof(GroupInfo) * ng);
@@ -634,7 +651,7 @@ int dvg_scene_create(const int32_t *topo, int64_t topo_len, int device, DvgScene
 
 int dvg_scene_set_params(DvgScene *s, const float *params, int64_t num_params, int params_on_device, void *stream) {
     if (!s || !params) return fail(DVG_ERR_INVALID, "null argument");
-    if (num_params != s->num_params) return fail(DVG_ERR_INVALID, "params length does not match the topology");
+    if (num_params != (int64_t)s->num_params * s->batch) return fail(DVG_ERR_INVALID, "params length does not match the topology (x batch)");
     DeviceGuard guard(s->device);
     cudaStream_t st = (cudaStream_t)stream;
     if (params_on_device) {
@@ -642,7 +659,7 @@ int dvg_scene_set_params(DvgScene *s, const float *params, int64_t num_params, i
     } else {
         // pageable host memory -> pinned staging -> async H2D (the caller may reuse `params` on return)
         if (!s->h_params_pinned) {
-            CK(cudaMallocHost((void **)&s->h_params_pinned, sizeof(float) * std::max(s->num_params, 1)));
+            CK(cudaMallocHost((void **)&s->h_params_pinned, sizeof(float) * std::max<size_t>((size_t)num_params, 1)));
             CK(cudaEventCreateWithFlags(&s->h_params_free, cudaEventDisableTiming));
         } else {
             CK(cudaEventSynchronize(s->h_params_free));
@@ -668,10 +685,37 @@ static int sdf_args_check(const float *eval_positions, int num_eval_positions) {
     return DVG_OK;
 }
 
+// Batch scenes: one seed per scene (host array), uploaded when it differs from the last call's.
+static int bind_seeds(DvgScene *s, const uint64_t *seeds, RenderArgs &ra, cudaStream_t st) {
+    if (s->batch == 1) return DVG_OK;
+    if (!seeds) return fail(DVG_ERR_INVALID, "a batch scene needs one seed per scene (dvg_render_*_batch)");
+    if (s->seeds_host.size() != (size_t)s->batch || memcmp(s->seeds_host.data(), seeds, 8 * (size_t)s->batch) != 0) {
+        s->seeds_host.assign(seeds, seeds + s->batch);
+        CK(s->d_seeds.ensure(8 * (size_t)s->batch));
+        CK(cudaMemcpyAsync(s->d_seeds.p, s->seeds_host.data(), 8 * (size_t)s->batch, cudaMemcpyHostToDevice, st));
+        s->seeds_version++;
+    }
+    ra.seeds = s->d_seeds.as<uint64_t>();
+    ra.seed = s->seeds_version;   // stands in for the seeds in the reuse keys (weight image, forward result words)
+    return DVG_OK;
+}
+
+static int check_batch_args(DvgScene *s, int width, int height, int nsx, int nsy, bool plain) {
+    if (s->batch == 1) return DVG_OK;
+    if (!plain) return fail(DVG_ERR_UNSUPPORTED, "batch scenes render colour images with the sampled path only (no prefiltering, SDF, eval_positions, d_translation or row ranges)");
+    if ((int64_t)width * height * nsx * nsy * s->batch >= (int64_t)1 << 31)
+        return fail(DVG_ERR_INVALID, "batch*width*height*samples must fit a 32-bit index");
+    return DVG_OK;
+}
+
 static int render_forward_impl(DvgScene *s, const float *background, float *render_image, float *render_sdf,
                                int width, int height, int nsx, int nsy, uint64_t seed, int use_prefiltering,
-                               const float *eval_positions, int num_eval_positions, int row_begin, int row_end, void *stream) {
+                               const float *eval_positions, int num_eval_positions, int row_begin, int row_end, void *stream,
+                               const uint64_t *seeds = nullptr) {
     int rc = check_render_args(s, width, height, nsx, nsy);
+    if (rc) return rc;
+    rc = check_batch_args(s, width, height, nsx, nsy, render_image && !render_sdf && !use_prefiltering && !eval_positions &&
+                                                          row_begin == 0 && row_end == height);
     if (rc) return rc;
     if (!render_image && !render_sdf) return fail(DVG_ERR_INVALID, "render_image and render_sdf are both null");
     rc = sdf_args_check(eval_positions, num_eval_positions);
@@ -691,13 +735,15 @@ static int render_forward_impl(DvgScene *s, const float *background, float *rend
     ra.use_prefiltering = use_prefiltering; ra.row_begin = row_begin; ra.row_end = row_end;
     ra.background = background; ra.render_image = render_image;
     if (g_fast_accept) ra.flags |= DVG_RF_FAST_ACCEPT;
+    rc = bind_seeds(s, seeds, ra, st);
+    if (rc) return rc;
     if (render_image) {
         if (row_begin % s->bin_th != 0) return fail(DVG_ERR_INVALID, "row_begin must be a multiple of the tile height");
         rc = ensure_weight(s, sc, ra, row_begin, row_end, st);
         if (rc) return rc;
-        CK(cudaMemsetAsync(render_image + 4 * (size_t)row_begin * width, 0, sizeof(float) * 4 * (size_t)width * (row_end - row_begin), st));
+        CK(cudaMemsetAsync(render_image + 4 * (size_t)row_begin * width, 0,
+                           sizeof(float) * 4 * (size_t)width * (row_end - row_begin) * s->batch, st));
         if (use_prefiltering) launch_render_pf_forward(sc, s->bin_view(), ra, st);
-        else if (g_fused) launch_render_forward(sc, s->bin_view(), ra, st);
         else { rc = wave_pixel_pass(s, sc, s->bin_view(), ra, false, st); if (rc) return rc; }
         CK(cudaGetLastError());
     }
@@ -731,8 +777,12 @@ int dvg_render_forward(DvgScene *s, const float *background, float *render_image
 static int render_backward_impl(DvgScene *s, const float *background, const float *d_render_image, const float *d_render_sdf,
                                 int width, int height, int nsx, int nsy, uint64_t seed, int use_prefiltering,
                                 const float *eval_positions, int num_eval_positions, int row_begin, int row_end,
-                                float *d_params, float *d_background, float *d_translation, uint32_t flags, void *stream) {
+                                float *d_params, float *d_background, float *d_translation, uint32_t flags, void *stream,
+                                const uint64_t *seeds = nullptr) {
     int rc = check_render_args(s, width, height, nsx, nsy);
+    if (rc) return rc;
+    rc = check_batch_args(s, width, height, nsx, nsy, d_render_image && !d_render_sdf && !use_prefiltering && !eval_positions &&
+                                                          !d_translation && row_begin == 0 && row_end == height);
     if (rc) return rc;
     if (!d_params) return fail(DVG_ERR_INVALID, "d_params is null");
     if (!d_render_image && !d_render_sdf) return fail(DVG_ERR_INVALID, "d_render_image and d_render_sdf are both null");
@@ -756,16 +806,21 @@ static int render_backward_impl(DvgScene *s, const float *background, const floa
     ra.background = background; ra.d_render_image = d_render_image;
     ra.d_params = d_params; ra.d_background = d_background; ra.d_translation = d_translation;
     ra.debug_out = g_debug_out;
-    if (!(flags & DVG_BWD_ACCUMULATE)) CK(cudaMemsetAsync(d_params, 0, sizeof(float) * s->num_params, st));
-    const bool wave_grads = d_render_image && (use_prefiltering || !g_fused);
-    if (wave_grads) {   // private copies of the gradient buffer for the wavefront composite kernels (dvg_wave.cu grad_replica)
-        ra.grad_reps = 32; ra.num_params = s->num_params;
-        CK(s->d_grad_rep.ensure(sizeof(float) * (size_t)ra.grad_reps * s->num_params));
+    rc = bind_seeds(s, seeds, ra, st);
+    if (rc) return rc;
+    const size_t all_params = (size_t)s->num_params * s->batch;   // a batch: scene b's gradients at b * num_params
+    if (!(flags & DVG_BWD_ACCUMULATE)) CK(cudaMemsetAsync(d_params, 0, sizeof(float) * all_params, st));
+    const bool wave_grads = d_render_image != nullptr;
+    if (wave_grads) {   // private copies of the gradient buffer for the composite kernels (dvg_wave.cu grad_replica)
+        // the copies exist to spread same-address atomics; the scenes of a batch already spread them
+        ra.grad_reps = s->batch >= 8 ? 4 : 32; ra.num_params = (int)all_params;
+        CK(s->d_grad_rep.ensure(sizeof(float) * (size_t)ra.grad_reps * all_params));
         ra.d_params_rep = s->d_grad_rep.as<float>();
-        CK(cudaMemsetAsync(ra.d_params_rep, 0, sizeof(float) * (size_t)ra.grad_reps * s->num_params, st));
+        CK(cudaMemsetAsync(ra.d_params_rep, 0, sizeof(float) * (size_t)ra.grad_reps * all_params, st));
     }
     if (d_background)
-        CK(cudaMemsetAsync(d_background + 4 * (size_t)row_begin * width, 0, sizeof(float) * 4 * (size_t)width * (row_end - row_begin), st));
+        CK(cudaMemsetAsync(d_background + 4 * (size_t)row_begin * width, 0,
+                           sizeof(float) * 4 * (size_t)width * (row_end - row_begin) * s->batch, st));
     if (d_translation) CK(cudaMemsetAsync(d_translation, 0, sizeof(float) * 2 * (size_t)width * height, st));
     if (d_render_image) {
         if (row_begin % s->bin_th != 0) return fail(DVG_ERR_INVALID, "row_begin must be a multiple of the tile height");
@@ -779,21 +834,20 @@ static int render_backward_impl(DvgScene *s, const float *background, const floa
             launch_wave_reduce_grads(ra, st);
             CK(cudaGetLastError());
         } else {
-            if (g_fused) launch_render_backward(sc, bins, ra, st);
-            else { rc = wave_pixel_pass(s, sc, bins, ra, true, st); if (rc) return rc; }
-            CK(cudaGetLastError());
+            rc = wave_pixel_pass(s, sc, bins, ra, true, st);
+            if (rc) return rc;
             // boundary term (diffvg.cpp:1558-1626): boundary-sample indices of the owned rows
             const int spp = nsx * nsy;
-            const int ntiles = bins.tiles_x * bins.tiles_y;
+            const int ntiles = bin_total_tiles(bins);
             const int64_t all_begin = (int64_t)row_begin * width * spp;
-            const int64_t all_count = (int64_t)(row_end - row_begin) * width * spp;
-            int64_t per_pass = g_fused ? all_count : edge_pass_samples(s, ntiles);
+            const int64_t all_count = (int64_t)(row_end - row_begin) * width * spp * s->batch;   // (batch: whole images, scene after scene)
+            int64_t per_pass = edge_pass_samples(s, ntiles);
             if (g_debug_edge_pass_samples > 0) per_pass = std::min<int64_t>(per_pass, g_debug_edge_pass_samples);
             if (all_count > 0 && per_pass < 4096)
                 return fail(DVG_ERR_UNSUPPORTED, "a tile holds too many candidate primitives for the boundary pass at this render size");
             for (int64_t done = 0; done < all_count; done += per_pass) {
                 BoundaryWork bw;
-                bw.samples = nullptr; bw.item_tile = nullptr;
+                bw.samples = nullptr; bw.samples_unsorted = nullptr; bw.item_tile = nullptr;
                 bw.sample_begin = (int)(all_begin + done);
                 bw.num_samples = (int)std::min<int64_t>(per_pass, all_count - done);
                 CK(s->d_keys.ensure(sizeof(int) * (size_t)bw.num_samples));
@@ -805,19 +859,11 @@ static int render_backward_impl(DvgScene *s, const float *background, const floa
                 bw.tile_counts = s->d_tile_counts.as<int>(); bw.tile_fill = s->d_tile_fill.as<int>();
                 bw.blk_counts = s->d_blk_counts.as<int>();
                 bw.tile_offsets = s->d_tile_offsets.as<int>(); bw.blk_offsets = s->d_blk_offsets.as<int>();
-                if (g_fused) {
-                    bw.max_blocks = bw.num_samples / edge_samples_per_block() + ntiles;
-                    launch_boundary(sc, bins, ra, bw, st);
-                    CK(cudaGetLastError());
-                } else {
-                    rc = wave_edge_pass(s, sc, bins, ra, bw, st);
-                    if (rc) return rc;
-                }
+                rc = wave_edge_pass(s, sc, bins, ra, bw, st);
+                if (rc) return rc;
             }
-            if (wave_grads && !use_prefiltering) {
-                launch_wave_reduce_grads(ra, st);
-                CK(cudaGetLastError());
-            }
+            launch_wave_reduce_grads(ra, st);
+            CK(cudaGetLastError());
         }
     }
     if (d_render_sdf) {
@@ -846,6 +892,23 @@ int dvg_render_backward(DvgScene *s, const float *background, const float *d_ren
                                 eval_positions, num_eval_positions, 0, height, d_params, d_background, d_translation, flags, stream);
 }
 
+int dvg_render_forward_batch(DvgScene *s, const float *background, float *render_image, int width, int height, int nsx, int nsy,
+                             const uint64_t *seeds, void *stream) {
+    if (!render_image) return fail(DVG_ERR_INVALID, "render_image is null");
+    if (s && s->batch == 1) return render_forward_impl(s, background, render_image, nullptr, width, height, nsx, nsy, seeds ? seeds[0] : 0, 0,
+                                                       nullptr, 0, 0, height, stream);
+    return render_forward_impl(s, background, render_image, nullptr, width, height, nsx, nsy, 0, 0, nullptr, 0, 0, height, stream, seeds);
+}
+
+int dvg_render_backward_batch(DvgScene *s, const float *background, const float *d_render_image, int width, int height, int nsx, int nsy,
+                              const uint64_t *seeds, float *d_params, float *d_background, uint32_t flags, void *stream) {
+    if (!d_render_image) return fail(DVG_ERR_INVALID, "d_render_image is null");
+    if (s && s->batch == 1) return render_backward_impl(s, background, d_render_image, nullptr, width, height, nsx, nsy, seeds ? seeds[0] : 0, 0,
+                                                        nullptr, 0, 0, height, d_params, d_background, nullptr, flags, stream);
+    return render_backward_impl(s, background, d_render_image, nullptr, width, height, nsx, nsy, 0, 0, nullptr, 0, 0, height,
+                                d_params, d_background, nullptr, flags, stream, seeds);
+}
+
 int dvg_debug_set_boundary_dump(float *device_buf) { g_debug_out = device_buf; return DVG_OK; }
 
 int dvg_debug_set_limits(int64_t pair_capacity, int64_t edge_pass_samples) {
@@ -858,6 +921,7 @@ int dvg_debug_prim_tests(DvgScene *s, int width, int height, int nsx, int nsy, u
     int rc = check_render_args(s, width, height, nsx, nsy);
     if (rc) return rc;
     if (!out_host || !pos_host || x < 0 || y < 0 || x >= width || y >= height) return fail(DVG_ERR_INVALID, "bad argument");
+    if (s->batch > 1) return fail(DVG_ERR_UNSUPPORTED, "dvg_debug_prim_tests reads single scenes");
     DeviceGuard guard(s->device);
     cudaStream_t st = (cudaStream_t)stream;
     rc = finish_build(s, st);
@@ -923,6 +987,7 @@ int64_t dvg_scene_dump(DvgScene *s, int what, int index, uint32_t *out, int64_t 
     auto bad = [&](const char *msg) { fail(DVG_ERR_INVALID, msg); return (int64_t)-1; };
     if (!s || !out) return bad("null argument");
     if (!s->params_set) return bad("dvg_scene_set_params has not been called");
+    if (s->batch > 1) return bad("dvg_scene_dump reads single scenes");
     DeviceGuard guard(s->device);
     cudaStream_t st = (cudaStream_t)stream;
     const int32_t *t = s->topo.data();

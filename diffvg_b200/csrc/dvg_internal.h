@@ -31,6 +31,7 @@ void prof_end(cudaStream_t st);
 
 struct BinBuild {
     int width, height, tile_w, tile_h, tiles_x, tiles_y;
+    int batch;      // scenes of one topology back to back (SceneView): tiles_x * tiles_y tiles each; row ranges only with batch 1
     int prefilter;  // 1: bin with prim_cbox_pf (SDF-prefiltering candidate regions)
     int tile_row0, tile_row1;  // tile rows to bin (the others get empty lists)
     // two-level binning: supertiles of `super` x `super` tiles get a candidate list first (fixed stride of num_prims
@@ -54,7 +55,8 @@ struct BoundaryWork {
     int *blk_offsets;     // [tiles+1]
     int *sorted_idx;      // [num_samples]
     int max_blocks;
-    BoundarySample *samples;  // [num_samples] by index - sample_begin, or null (wavefront path: made once, read twice)
+    BoundarySample *samples;           // [num_samples] in TILE order (wavefront path: made once, sorted, read twice), or null
+    BoundarySample *samples_unsorted;  // [num_samples] by index - sample_begin: staging of the counting sort, or null
     int *item_tile;           // [max_blocks] tile of every boundary item, or null
 };
 
@@ -90,7 +92,6 @@ void launch_bvh_build(const BuildView &bv, BvhNode *path_nodes, BvhNode *group_n
 
 void launch_debug_prim_tests(const SceneView &sc, const BinView &bins, const RenderArgs &ra, int x, int y, int *out, float *pos, cudaStream_t st);
 void launch_peak_probe(int which, float *out, int iters, cudaStream_t st);
-int edge_samples_per_block();
 void launch_build(const BuildView &bv, cudaStream_t st);
 void launch_bin_coarse(const BuildView &bv, const BinBuild &bb, cudaStream_t st);
 void launch_bin_count(const BuildView &bv, const BinBuild &bb, cudaStream_t st);
@@ -98,12 +99,9 @@ void launch_bin_fill(const BuildView &bv, const BinBuild &bb, cudaStream_t st);
 void launch_scan(const int *in, int *out, int n, cudaStream_t st);
 
 void launch_weight(const SceneView &sc, const RenderArgs &ra, int row_begin, int row_end, cudaStream_t st);
-void launch_render_forward(const SceneView &sc, const BinView &bins, const RenderArgs &ra, cudaStream_t st);
-void launch_render_backward(const SceneView &sc, const BinView &bins, const RenderArgs &ra, cudaStream_t st);
 void launch_render_pf_forward(const SceneView &sc, const BinView &bins, const RenderArgs &ra, cudaStream_t st);
 void launch_render_pf_backward(const SceneView &sc, const BinView &bins, const RenderArgs &ra, cudaStream_t st);
 void launch_sdf(const SceneView &sc, const RenderArgs &ra, const SdfArgs &sa, bool backward, cudaStream_t st);
-void launch_boundary(const SceneView &sc, const BinView &bins, const RenderArgs &ra, const BoundaryWork &bw, cudaStream_t st);
 void launch_boundary_sort(const SceneView &sc, const BinView &bins, const RenderArgs &ra, const BoundaryWork &bw, cudaStream_t st);
 
 void launch_wave_tile_chunks(const int *bin_offsets, int *nch, int *choff, int *max_nch, int ntiles, cudaStream_t st);

@@ -61,19 +61,33 @@ struct GroupInfo {
 #define DVG_GF_IDENTITY 2   // shape_to_canvas is exactly the identity: xform_pt is exact, skip it
 #define DVG_GF_AFFINE 4     // last row is exactly (0,0,1)
 
-// Per shape *instance* (a shape referenced by a group).
+// Per shape *instance* (a shape referenced by a group).  In a batch (SceneView::batch scenes of one topology laid out
+// back to back, see SceneView) `group` and `prim_begin` are batch-wide indices, `shape` stays the id inside its scene (it
+// indexes the shared topology) and `scene` says which scene: scene * num_shapes + shape, scene * num_params + offset, ...
+// address that scene's slice of the per-shape tables and of the parameter / gradient buffers.
 struct InstInfo {
     Box box;        // shapes_bbox[shape], scene.cpp:499-629
     float r;        // leaf radius in the group BVH: stroke_width if the group strokes else 0, scene.cpp:638
     int group;
     int shape;
     int prim_begin;
+    int scene;
 };
 
 // Everything the kernels need, passed by value.
+//
+// BATCH: `batch` scenes that share one topology (the stroke scenes of apps/generative_models/rendering.py:170-307: same
+// shape and group lists, different parameters and seeds) live in ONE set of tables, scene b occupying slice b of every
+// array: parameters [b * num_params, ...), shapes [b * num_shapes, ...), instances, groups, primitives, segment tables.
+// The counts below are PER SCENE.  Primitive, instance and group ids that travel through bins, pair queues and fragment
+// records are batch-wide (slice offset included), colour / transform offsets in GroupInfo are absolute, so the traversal
+// and the exact-test kernels never need to know about scenes; only the code that maps work items to pixels (one tile list
+// per (scene, tile)), draws random numbers (per-scene seed, sample index local to the scene) or reads the shared
+// topology does.  batch == 1 is the plain single-scene case: every slice offset is 0.
 struct SceneView {
     int canvas_w, canvas_h;
     int num_shapes, num_groups, num_insts, num_prims;
+    int batch, num_params, total_segs;
     Filter filter;
     int filter_radius_off;
     const int *topo;       // device copy of the topology blob
@@ -100,12 +114,15 @@ struct SceneView {
     int *error_flag;
 };
 
-// Tile bins for one render configuration.
+// Tile bins for one render configuration: tiles_x * tiles_y tiles per scene, scene b's tiles at b * tiles_x * tiles_y.
 struct BinView {
     int tile_w, tile_h, tiles_x, tiles_y;
+    int batch;
     const int *offsets;   // [tiles+1]
     const int *items;     // ascending primitive ids per tile
 };
+DVG_HD int bin_scene_tiles(const BinView &b) { return b.tiles_x * b.tiles_y; }
+DVG_HD int bin_total_tiles(const BinView &b) { return b.tiles_x * b.tiles_y * b.batch; }
 
 // RenderArgs.flags: low bits = DVG_BWD_* of the C ABI; internal bits from 16 up
 #define DVG_RF_FAST_ACCEPT (1u << 16)
@@ -114,6 +131,7 @@ struct BinView {
 struct RenderArgs {
     int width, height, nsx, nsy;
     uint64_t seed;
+    const uint64_t *seeds;         // batch: one seed per scene (device), else null; images below are then [batch, H, W, C]
     int use_prefiltering;
     int row_begin, row_end;        // pixel rows owned by this call (sharding); whole image by default
     uint32_t flags;
@@ -128,5 +146,19 @@ struct RenderArgs {
     float *d_translation;
     float *debug_out;              // [n,4] per boundary sample (contrib, hit bits, normal) -- debug builds of the tests only
 };
+
+// The arguments as scene `b` of a batch sees them: its own seed and its own slice of every image.
+DVG_HD RenderArgs args_of_scene(const RenderArgs &ra, int b) {
+    if (!ra.seeds) return ra;
+    RenderArgs r = ra;
+    const size_t px = (size_t)ra.width * ra.height * (size_t)b;
+    r.seed = ra.seeds[b];
+    if (ra.background) r.background = ra.background + 4 * px;
+    if (ra.weight_image) r.weight_image = ra.weight_image + px;
+    if (ra.render_image) r.render_image = ra.render_image + 4 * px;
+    if (ra.d_render_image) r.d_render_image = ra.d_render_image + 4 * px;
+    if (ra.d_background) r.d_background = ra.d_background + 4 * px;
+    return r;
+}
 
 }  // namespace dvg

@@ -204,9 +204,10 @@ DVG_D void wave_classify(const SceneView &sc, const BinView &bins, const WaveVie
     }
 }
 
-// Geometry of a pixel item: item -> tile, lane -> sample.
+// Geometry of a pixel item: item -> (scene, tile), lane -> sample.  `tile` is the batch-wide tile (the index of its bin
+// and of its chunk offsets); x, y, idx are the scene's own pixel and sample index (RNG streams are per scene).
 struct PixelItem {
-    int tile, x, y, sx, sy, idx;
+    int tile, scene, x, y, sx, sy, idx;
     bool active;
     int64_t cb;
 };
@@ -218,7 +219,10 @@ DVG_D PixelItem pixel_item(const BinView &bins, const RenderArgs &ra, const Wave
     const int tile_row0 = ra.row_begin / bins.tile_h;
     pi.tile = item / wpt + tile_row0 * bins.tiles_x;
     const int part = item % wpt;
-    const int tx = pi.tile % bins.tiles_x, ty = pi.tile / bins.tiles_x;
+    const int tiles_scene = bin_scene_tiles(bins);
+    pi.scene = pi.tile / tiles_scene;
+    const int ltile = pi.tile - pi.scene * tiles_scene;
+    const int tx = ltile % bins.tiles_x, ty = ltile / bins.tiles_x;
     const int l = part * 32 + (threadIdx.x & 31);
     const int s = l % spp, p = l / spp;
     pi.x = tx * bins.tile_w + p % bins.tile_w;
@@ -242,8 +246,8 @@ __global__ void __launch_bounds__(WB, DVG_WB_MIN) k_wave_classify_px(SceneView s
         const PixelItem pi = pixel_item(bins, ra, wv, item);
         F2 pt = mk2(0, 0), cpt = mk2(0, 0);
         if (pi.active)
-            sample_position(sc.canvas_w, sc.canvas_h, ra.width, ra.height, ra.nsx, ra.nsy, ra.seed, ra.use_prefiltering != 0,
-                            pi.x, pi.y, pi.sx, pi.sy, pi.idx, pt, cpt);
+            sample_position(sc.canvas_w, sc.canvas_h, ra.width, ra.height, ra.nsx, ra.nsy, ra.seeds ? ra.seeds[pi.scene] : ra.seed,
+                            ra.use_prefiltering != 0, pi.x, pi.y, pi.sx, pi.sy, pi.idx, pt, cpt);
         wave_classify<INPLACE>(sc, bins, wv, pi.tile, pi.cb, cpt, pi.active, s_ws[threadIdx.x >> 5], (ra.flags & DVG_RF_FAST_ACCEPT) != 0);
     }
 }
@@ -275,7 +279,7 @@ struct EdgeLane {
 DVG_D EdgeLane edge_lane(const SceneView &sc, const RenderArgs &ra, const BoundaryWork &bw, const EdgeItem &ei) {
     EdgeLane el;
     el.bs.inst = -1; el.bs.pt = mk2(0, 0); el.bs.normal = mk2(0, 0);
-    if (ei.valid) el.bs = bw.samples[bw.sorted_idx[bw.tile_offsets[ei.tile] + ei.k] - bw.sample_begin];   // made by k_boundary_keys
+    if (ei.valid) el.bs = bw.samples[bw.tile_offsets[ei.tile] + ei.k];   // made by k_boundary_keys, moved into tile order by k_boundary_scatter
     el.active = ei.valid && el.bs.inst >= 0;
     el.cpt = mk2(0, 0); el.bx = el.by = 0;
     if (el.active) {
@@ -291,7 +295,7 @@ template <bool INPLACE>
 __global__ void __launch_bounds__(WB, DVG_WB_MIN) k_wave_classify_edge(SceneView sc, BinView bins, RenderArgs ra, BoundaryWork bw, WaveView wv) {
     __shared__ WaveScratch s_ws[WNW];
     if (INPLACE && !wave_overflowed(wv)) return;
-    const int ntiles = bins.tiles_x * bins.tiles_y;
+    const int ntiles = bin_total_tiles(bins);
     const int num_items = bw.blk_offsets[ntiles];
     for (int item = blockIdx.x * WNW + (threadIdx.x >> 5); item < num_items; item += gridDim.x * WNW) {
         const EdgeItem ei = edge_item(bins, bw, wv, item);
@@ -321,7 +325,10 @@ constexpr int W2A_B = 256;
 
 // The number of pairs is read from the device counter (nothing is read back to size a launch): the grid is a fixed
 // multiple of the SM count and every block strides over the queue.
-__global__ void __launch_bounds__(W2A_B) k_wave_stroke_setup(SceneView sc, WaveView wv) {
+#ifndef DVG_SETUP_MINB
+#define DVG_SETUP_MINB 1
+#endif
+__global__ void __launch_bounds__(W2A_B, DVG_SETUP_MINB) k_wave_stroke_setup(SceneView sc, WaveView wv) {
     const int count = min(wv.counters[0], wv.cap_s);
     const int lane = threadIdx.x & 31;
   for (int base = blockIdx.x * W2A_B; base < count; base += gridDim.x * W2A_B) {
@@ -500,18 +507,21 @@ DVG_D void wave_consume(const SceneView &sc, const BinView &bins, const WaveView
 
 // render_kernel (diffvg.cpp:1161-1272), colour output, after the candidates have been answered.
 template <bool BACKWARD>
-__global__ void __launch_bounds__(WB, DVG_WB_MIN + 1) k_wave_composite_px(SceneView sc, BinView bins, RenderArgs ra, WaveView wv, int num_items) {
-    const GlobalSink sk{BACKWARD ? grad_replica(ra) : nullptr};
+__global__ void __launch_bounds__(WB, DVG_WB_MIN + 1) k_wave_composite_px(SceneView sc, BinView bins, RenderArgs ra_all, WaveView wv, int num_items) {
+    const GlobalSink sk{BACKWARD ? grad_replica(ra_all) : nullptr};
     const int lane = threadIdx.x & 31;
     const int item = blockIdx.x * WNW + (threadIdx.x >> 5);
-    const int spp = ra.nsx * ra.nsy;
+    const int spp = ra_all.nsx * ra_all.nsy;
     const bool pow2 = (spp & (spp - 1)) == 0;
     const int grp = pow2 ? (spp < 32 ? spp : 32) : 1;
     int fkey[BACKWARD ? W_MAXF : 1];
     F4 fprev[BACKWARD ? W_MAXF : 1];
     float d_radius_acc = 0.f;
+    int radius_off = sc.filter_radius_off;
     if (item < num_items) {
-        const PixelItem pi = pixel_item(bins, ra, wv, item);
+        const PixelItem pi = pixel_item(bins, ra_all, wv, item);
+        const RenderArgs ra = args_of_scene(ra_all, pi.scene);   // the scene's seed and image slices (batch)
+        radius_off += pi.scene * sc.num_params;
         const int x = pi.x, y = pi.y;
         const bool active = pi.active;
         F2 pt = mk2(0, 0), cpt = mk2(0, 0);
@@ -580,20 +590,21 @@ __global__ void __launch_bounds__(WB, DVG_WB_MIN + 1) k_wave_composite_px(SceneV
     }
     if (BACKWARD) {   // every sample adds to d_filter.radius
         d_radius_acc = warp_sum(d_radius_acc);
-        if (lane == 0) sk.add(sc.filter_radius_off, d_radius_acc);
+        if (lane == 0) sk.add(radius_off, d_radius_acc);
     }
 }
 
 // render_edge_kernel (diffvg.cpp:1388-1475) after the candidates of both sides have been answered.
-__global__ void __launch_bounds__(WB, DVG_WB_MIN + 1) k_wave_composite_edge(SceneView sc, BinView bins, RenderArgs ra, BoundaryWork bw, WaveView wv) {
-    float *const D = grad_replica(ra);
+__global__ void __launch_bounds__(WB, DVG_WB_MIN + 1) k_wave_composite_edge(SceneView sc, BinView bins, RenderArgs ra_all, BoundaryWork bw, WaveView wv) {
+    float *const D = grad_replica(ra_all);
     const GlobalSink sk{D};
     const int lane = threadIdx.x & 31;
-    const int ntiles = bins.tiles_x * bins.tiles_y;
+    const int ntiles = bin_total_tiles(bins);
     const int item = blockIdx.x * WNW + (threadIdx.x >> 5);
     if (item >= bw.blk_offsets[ntiles]) return;
     {
         const EdgeItem ei = edge_item(bins, bw, wv, item);
+        const RenderArgs ra = args_of_scene(ra_all, ei.tile / bin_scene_tiles(bins));   // the scene's image slices (batch)
         const EdgeLane el = edge_lane(sc, ra, bw, ei);
         const BoundarySample &bs = el.bs;
         const bool active = el.active;
@@ -718,7 +729,7 @@ int wave_pixel_items(const BinView &bins, const RenderArgs &ra) {
     const int wpt = (ns + 31) / 32;
     const int r0 = ra.row_begin / bins.tile_h;
     const int r1 = (ra.row_end + bins.tile_h - 1) / bins.tile_h;
-    return (r1 - r0) * bins.tiles_x * wpt;
+    return bins.batch > 1 ? bin_total_tiles(bins) * wpt : (r1 - r0) * bins.tiles_x * wpt;   // (a batch renders whole images)
 }
 int wave_items_per_tile(const BinView &bins, const RenderArgs &ra) {
     return (bins.tile_w * bins.tile_h * ra.nsx * ra.nsy + 31) / 32;
@@ -765,7 +776,7 @@ void launch_wave_composite_px(const SceneView &sc, const BinView &bins, const Re
 // sort, then per-tile item counts and chunk-slot offsets.
 void launch_wave_boundary_sort(const SceneView &sc, const BinView &bins, const RenderArgs &ra, const BoundaryWork &bw,
                                const WaveView &wv, int *edge_chunks, cudaStream_t st) {
-    const int ntiles = bins.tiles_x * bins.tiles_y;
+    const int ntiles = bin_total_tiles(bins);
     launch_boundary_sort(sc, bins, ra, bw, st);
     DVG_LAUNCH(k_wave_edge_counts, dim3((ntiles + 255) / 256), dim3(256), 0, st, bw, wv.tile_choff, edge_chunks, ntiles);
     launch_scan(bw.blk_counts, bw.blk_offsets, ntiles, st);

@@ -10,3 +10,4 @@ from .parse_svg import *  # noqa: F401,F403
 from .color import *  # noqa: F401,F403
 from .save_svg import *  # noqa: F401,F403
 from .packed_params import *  # noqa: F401,F403
+from .batched import *  # noqa: F401,F403

@@ -57,14 +57,14 @@ def _native():
 class _NativeScene:
     """Owns one DvgScene* (topology uploaded once) and remembers which params it holds."""
 
-    def __init__(self, topo, device_index):
+    def __init__(self, topo, device_index, batch=1):
         import ctypes
         n = _native()
         self.n = n
         self.handle = ctypes.c_void_p()
         self.topo = np.ascontiguousarray(topo, dtype=np.int32)
-        n.check(n.lib.dvg_scene_create(self.topo.ctypes.data, self.topo.shape[0], device_index,
-                                       ctypes.byref(self.handle)))
+        n.check(n.lib.dvg_scene_create_batch(self.topo.ctypes.data, self.topo.shape[0], device_index, batch,
+                                             ctypes.byref(self.handle)))
         self.version = 0
         self.device_index = device_index
 

@@ -98,6 +98,30 @@ int dvg_render_backward(DvgScene *scene, const float *background,
                         float *d_params, float *d_background, float *d_translation,
                         uint32_t flags, void *stream);
 
+/*
+ * BATCHED SCENES.  Replaces the per-sample Python loops of the reference's batched front end
+ * (apps/generative_models/rendering.py:170-237 line_render, :239-307 bezier_render, :101-167 stroke2diffvg): `batch`
+ * scenes that share ONE topology (same shapes, groups and segment counts; only the continuous parameters and the seeds
+ * differ) are built, rendered and differentiated by one set of kernel launches, where the reference constructs a
+ * diffvg.Scene and calls diffvg.render twice per sample.
+ *   dvg_scene_create_batch   as dvg_scene_create; `batch` >= 1 (1 = dvg_scene_create)
+ *   dvg_scene_set_params     takes float[batch * num_params]: scene b's parameters at b * num_params (same layout each).
+ *                            The pixel-filter radius is scene 0's.
+ *   images                   float[batch * H * W * 4], scene after scene (background, render_image, d_render_image,
+ *                            d_background)
+ *   seeds                    HOST uint64[batch]: scene b renders exactly what a single scene with seed seeds[b] renders
+ *   d_params                 float[batch * num_params]
+ * Colour images of the sampled path only: no prefiltering, SDF output, eval_positions, d_translation or row ranges
+ * (DVG_ERR_UNSUPPORTED).  A degenerate scene anywhere in the batch fails the call (DVG_ERR_SCENE).
+ */
+int dvg_scene_create_batch(const int32_t *topo, int64_t topo_len, int device, int batch, DvgScene **out_scene);
+int dvg_render_forward_batch(DvgScene *scene, const float *background, float *render_image,
+                             int width, int height, int num_samples_x, int num_samples_y, const uint64_t *seeds,
+                             void *stream);
+int dvg_render_backward_batch(DvgScene *scene, const float *background, const float *d_render_image,
+                              int width, int height, int num_samples_x, int num_samples_y, const uint64_t *seeds,
+                              float *d_params, float *d_background, uint32_t flags, void *stream);
+
 /* Destroy the scene and its device buffers (Scene::~Scene, scene.cpp:1000-1022). */
 int dvg_scene_destroy(DvgScene *scene);
 

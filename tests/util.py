@@ -127,3 +127,40 @@ def gpu_scene_dump(topo, params, selectors):
         return out
     finally:
         n.lib.dvg_scene_destroy(h)
+
+
+def gpu_render_batch(topo, params_rows, width, height, nsx, nsy, seeds, backgrounds=None, d_render_images=None,
+                     skip_xform_grad=False):
+    """`batch` scenes of one topology through dvg_scene_create_batch / dvg_render_*_batch.  params_rows [B, N],
+    seeds [B]; images [B, H, W, 4]."""
+    import ctypes
+    from diffvg_b200 import _native as n
+    dev = torch.device('cuda', 0)
+    h = ctypes.c_void_p()
+    topo = np.ascontiguousarray(topo, np.int32)
+    p = np.ascontiguousarray(params_rows, np.float32)
+    B = p.shape[0]
+    n.check(n.lib.dvg_scene_create_batch(topo.ctypes.data, topo.shape[0], 0, B, ctypes.byref(h)))
+    try:
+        stream = torch.cuda.current_stream().cuda_stream
+        n.check(n.lib.dvg_scene_set_params(h, p.ctypes.data, p.size, 0, stream))
+        sd = np.ascontiguousarray(np.asarray(seeds, np.uint64))
+        bg = torch.from_numpy(np.ascontiguousarray(backgrounds, np.float32)).to(dev) if backgrounds is not None else None
+        ptr = lambda t: t.data_ptr() if t is not None else None
+        out = {}
+        if d_render_images is None:
+            img = torch.empty(B, height, width, 4, device=dev)
+            n.check(n.lib.dvg_render_forward_batch(h, ptr(bg), img.data_ptr(), width, height, nsx, nsy, sd.ctypes.data, stream))
+            out['image'] = img.cpu().numpy()
+        else:
+            dimg = torch.from_numpy(np.ascontiguousarray(d_render_images, np.float32)).to(dev)
+            dpar = torch.empty(B, p.shape[1], device=dev)
+            dbg = torch.empty_like(bg) if bg is not None else None
+            n.check(n.lib.dvg_render_backward_batch(h, ptr(bg), dimg.data_ptr(), width, height, nsx, nsy, sd.ctypes.data,
+                                                    dpar.data_ptr(), ptr(dbg), 1 if skip_xform_grad else 0, stream))
+            out['d_params'] = dpar.cpu().numpy()
+            out['d_background'] = dbg.cpu().numpy() if dbg is not None else None
+        torch.cuda.synchronize()
+        return out
+    finally:
+        n.lib.dvg_scene_destroy(h)

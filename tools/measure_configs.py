@@ -81,6 +81,33 @@ def main():
     img = torch.empty(64, 64, 4, device='cuda'); dimg = torch.empty_like(img)
     ms = timed(lambda: [s.step(64, 64, 2, 2, b, 0, img, dimg) for b, s in enumerate(batch)], reps=3, warm=1)
     print('%-38s %8.3f ms fwd+bwd for 512 scenes (%.3f ms per scene, sequential native scenes)' % ('C5 512x16 strokes 64^2 2x2', ms, ms / 512), flush=True)
+    # the same 512 scenes as ONE batch scene (dvg_scene_create_batch)
+    B = len(batch)
+    rows = torch.stack([s.p for s in batch]).contiguous()
+    for s in batch:
+        n.lib.dvg_scene_destroy(s.h)
+    h = ctypes.c_void_p()
+    n.check(n.lib.dvg_scene_create_batch(batch[0].topo.ctypes.data, batch[0].topo.shape[0], 0, B, ctypes.byref(h)))
+    seeds = np.arange(B, dtype=np.uint64)
+    imgs = torch.empty(B, 64, 64, 4, device='cuda'); dimgs = torch.empty_like(imgs)
+    grads = torch.empty_like(rows)
+
+    def bstep():
+        st = torch.cuda.current_stream().cuda_stream
+        n.check(n.lib.dvg_scene_set_params(h, rows.data_ptr(), rows.numel(), 1, st))
+        n.check(n.lib.dvg_render_forward_batch(h, None, imgs.data_ptr(), 64, 64, 2, 2, seeds.ctypes.data, st))
+        torch.mul(imgs, 2.0 / imgs[0].numel(), out=dimgs)
+        n.check(n.lib.dvg_render_backward_batch(h, None, dimgs.data_ptr(), 64, 64, 2, 2, seeds.ctypes.data, grads.data_ptr(), None, 1, st))
+    ms = timed(bstep, reps=5, warm=2)
+    print('%-38s %8.3f ms fwd+bwd for 512 scenes (%.4f ms per scene, one batch scene)' % ('C5 512x16 strokes 64^2 2x2 BATCH', ms, ms / 512), flush=True)
+    n.profile_enable(True)
+    bstep(); torch.cuda.synchronize()
+    n.profile_report()
+    bstep(); torch.cuda.synchronize()
+    rep = n.profile_report()
+    n.profile_enable(False)
+    print('   per kernel (ms): ' + ', '.join('%s %.3f' % (k.replace('k_wave_', 'w_').replace('k_', ''), v[1]) for k, v in sorted(rep.items(), key=lambda kv: -kv[1][1])[:12]))
+    n.lib.dvg_scene_destroy(h)
 
 
 if __name__ == '__main__':
