@@ -23,7 +23,7 @@ struct BuildView {
     float *seg_cdf, *seg_pmf; int *seg_point_id;
     // per instance / group / primitive
     InstInfo *insts; GroupInfo *groups;
-    F4 *prim_p01, *prim_p23, *prim_rad; Box *prim_box; float *prim_thick; PrimMeta *prim_meta; Box *prim_cbox; Box *prim_cbox_pf; F4 *prim_cap;
+    F4 *prim_p01, *prim_p23, *prim_rad; Box *prim_box; float *prim_thick; PrimMeta *prim_meta; Box *prim_cbox; Box *prim_cbox_pf; F4 *prim_cap; PrimQuintic *prim_quint;
     float *shape_cdf, *shape_pmf;
     int *error_flag; float *total_length;
 };
@@ -367,6 +367,8 @@ DVG_HD_NOINLINE void build_prim(const BuildView &bv, int e_batch) {
     pm.type_flags = tf;
     bv.prim_p01[e] = p01; bv.prim_p23[e] = p23; bv.prim_rad[e] = rad;
     bv.prim_box[e] = box; bv.prim_thick[e] = thick; bv.prim_meta[e] = pm;
+    if ((tf & DVG_PF_TYPE_MASK) == PRIM_CUBIC && has_stroke)   // read by the exact stroke test of cubic segments only
+        bv.prim_quint[e] = prim_quintic(mk2(p01.x, p01.y), mk2(p01.z, p01.w), mk2(p23.x, p23.y), mk2(p23.z, p23.w));
     {
         float cap[DVG_CAP_N * 8];
         const int ptype = tf & DVG_PF_TYPE_MASK;

@@ -80,7 +80,7 @@ struct DvgScene {
     DevBuf d_topo, d_inst_group, d_inst_shape, d_inst_prim_begin, d_prim_inst, d_prim_seg, d_prim_point_id;
     // device: parameters + derived tables
     DevBuf d_params, d_shapes_length, d_shape_box, d_shape_r0, d_seg_cdf, d_seg_pmf, d_seg_point_id;
-    DevBuf d_insts, d_groups, d_p01, d_p23, d_rad, d_box, d_thick, d_meta, d_cbox, d_cbox_pf, d_cap, d_shape_cdf, d_shape_pmf;
+    DevBuf d_insts, d_groups, d_p01, d_p23, d_rad, d_box, d_thick, d_meta, d_cbox, d_cbox_pf, d_cap, d_quint, d_shape_cdf, d_shape_pmf;
     DevBuf d_flags;  // [0] error flag, [1] total length (float bits)
     // bins
     DevBuf d_bin_counts, d_bin_offsets, d_bin_items, d_sbin_counts, d_sbin_items;
@@ -92,7 +92,7 @@ struct DvgScene {
     uint64_t w_seed = 0; float w_radius = 0; bool w_valid = false;
     DevBuf d_keys, d_tile_counts, d_tile_offsets, d_tile_fill, d_blk_counts, d_blk_offsets, d_sorted;
     // wavefront passes (dvg_wave.cu)
-    DevBuf d_wave_hit, d_wave_wind, d_wave_pairs_s, d_wave_pairs_f, d_wave_units_a, d_wave_units_d, d_wave_counters, d_tile_nch, d_tile_choff,
+    DevBuf d_wave_hit, d_wave_wind, d_wave_pairs_s, d_wave_pairs_f, d_wave_counters, d_tile_nch, d_tile_choff,
         d_edge_chunks, d_edge_choff, d_wave_max, d_bsamples, d_bsamples_raw, d_item_tile, d_grad_rep;
     DevBuf d_bvh_path, d_bvh_group, d_bvh_scene, d_bvh_keys;   // reference-topology trees (dvg_bvh.cu), built on demand by dvg_scene_dump
     int total_chunks = 0, max_nch = 0;   // of the current bins (read back with the bin total)
@@ -127,7 +127,7 @@ struct DvgScene {
         bv.insts = d_insts.as<InstInfo>(); bv.groups = d_groups.as<GroupInfo>();
         bv.prim_p01 = d_p01.as<F4>(); bv.prim_p23 = d_p23.as<F4>(); bv.prim_rad = d_rad.as<F4>();
         bv.prim_box = d_box.as<Box>(); bv.prim_thick = d_thick.as<float>(); bv.prim_meta = d_meta.as<PrimMeta>();
-        bv.prim_cbox = d_cbox.as<Box>(); bv.prim_cbox_pf = d_cbox_pf.as<Box>(); bv.prim_cap = d_cap.as<F4>();
+        bv.prim_cbox = d_cbox.as<Box>(); bv.prim_cbox_pf = d_cbox_pf.as<Box>(); bv.prim_cap = d_cap.as<F4>(); bv.prim_quint = d_quint.as<PrimQuintic>();
         bv.shape_cdf = d_shape_cdf.as<float>(); bv.shape_pmf = d_shape_pmf.as<float>();
         bv.error_flag = d_flags.as<int>(); bv.total_length = d_flags.as<float>() + 1;
         return bv;
@@ -143,7 +143,7 @@ struct DvgScene {
         sc.topo = d_topo.as<int>(); sc.params = d_params.as<float>();
         sc.prim_p01 = d_p01.as<F4>(); sc.prim_p23 = d_p23.as<F4>(); sc.prim_rad = d_rad.as<F4>();
         sc.prim_box = d_box.as<Box>(); sc.prim_thick = d_thick.as<float>(); sc.prim_meta = d_meta.as<PrimMeta>();
-        sc.prim_cbox = d_cbox.as<Box>(); sc.prim_cbox_pf = d_cbox_pf.as<Box>(); sc.prim_cap = d_cap.as<F4>();
+        sc.prim_cbox = d_cbox.as<Box>(); sc.prim_cbox_pf = d_cbox_pf.as<Box>(); sc.prim_cap = d_cap.as<F4>(); sc.prim_quint = d_quint.as<PrimQuintic>();
         sc.insts = d_insts.as<InstInfo>(); sc.groups = d_groups.as<GroupInfo>();
         sc.shapes_length = d_shapes_length.as<float>();
         sc.shape_cdf = d_shape_cdf.as<float>(); sc.shape_pmf = d_shape_pmf.as<float>();
@@ -161,10 +161,10 @@ struct DvgScene {
     void release_all() {
         DevBuf *all[] = {&d_topo, &d_inst_group, &d_inst_shape, &d_inst_prim_begin, &d_prim_inst, &d_prim_seg,
                          &d_prim_point_id, &d_params, &d_shapes_length, &d_shape_box, &d_shape_r0, &d_seg_cdf, &d_seg_pmf,
-                         &d_seg_point_id, &d_insts, &d_groups, &d_p01, &d_p23, &d_rad, &d_box, &d_thick, &d_meta, &d_cbox, &d_cbox_pf, &d_cap,
+                         &d_seg_point_id, &d_insts, &d_groups, &d_p01, &d_p23, &d_rad, &d_box, &d_thick, &d_meta, &d_cbox, &d_cbox_pf, &d_cap, &d_quint,
                          &d_shape_cdf, &d_shape_pmf, &d_flags, &d_bin_counts, &d_bin_offsets, &d_bin_items, &d_sbin_counts, &d_sbin_items, &d_weight,
                          &d_keys, &d_tile_counts, &d_tile_offsets, &d_tile_fill, &d_blk_counts, &d_blk_offsets, &d_sorted,
-                         &d_wave_hit, &d_wave_wind, &d_wave_pairs_s, &d_wave_pairs_f, &d_wave_units_a, &d_wave_units_d, &d_wave_counters, &d_tile_nch, &d_tile_choff,
+                         &d_wave_hit, &d_wave_wind, &d_wave_pairs_s, &d_wave_pairs_f, &d_wave_counters, &d_tile_nch, &d_tile_choff,
                          &d_edge_chunks, &d_edge_choff, &d_wave_max, &d_bsamples, &d_bsamples_raw, &d_item_tile, &d_grad_rep,
                          &d_bvh_path, &d_bvh_group, &d_bvh_scene, &d_bvh_keys, &d_seeds};
         for (DevBuf *b : all) b->release();
@@ -441,13 +441,6 @@ int wave_view(DvgScene *s, int64_t chunk_slots, int64_t evals, WaveView *out) {
         wv.cap_s = (int)std::min<int64_t>(wv.cap_s, g_debug_pair_capacity);
         wv.cap_f = (int)std::min<int64_t>(wv.cap_f, g_debug_pair_capacity);
     }
-    // root-bracket queues of the cubic pairs: 1.5 ascending / 0.75 descending brackets per pair cover every scene
-    // measured (1.0 / 0.25 at the painterly config); a fuller queue is answered in place by W2a
-    wv.cap_ua = (int)std::min<int64_t>((int64_t)wv.cap_s + wv.cap_s / 2 + 1024, lim);
-    wv.cap_ud = (int)std::min<int64_t>((int64_t)wv.cap_s - wv.cap_s / 4 + 1024, lim);
-    CK(s->d_wave_units_a.ensure(sizeof(WaveUnit) * (size_t)wv.cap_ua));
-    CK(s->d_wave_units_d.ensure(sizeof(WaveUnit) * (size_t)wv.cap_ud));
-    wv.units_a = s->d_wave_units_a.as<WaveUnit>(); wv.units_d = s->d_wave_units_d.as<WaveUnit>();
     wv.counters = s->d_wave_counters.as<int>();
     wv.tile_choff = s->d_tile_choff.as<int>();
     wv.edge_choff = s->d_edge_choff.as<int>();
@@ -634,7 +627,7 @@ int dvg_scene_create_batch(const int32_t *topo, int64_t topo_len, int device, in
     ens(s->d_seg_cdf, 4 * nsg); ens(s->d_seg_pmf, 4 * nsg); ens(s->d_seg_point_id, 4 * nsg);
     ens(s->d_insts, sizeof(InstInfo) * ni); ens(s->d_groups, sizeof(GroupInfo) * ng);
     ens(s->d_p01, 16 * npr); ens(s->d_p23, 16 * npr); ens(s->d_rad, 16 * npr); ens(s->d_box, 16 * npr);
-    ens(s->d_thick, 4 * npr); ens(s->d_meta, sizeof(PrimMeta) * npr); ens(s->d_cbox, 16 * npr); ens(s->d_cbox_pf, 16 * npr); ens(s->d_cap, 16 * DVG_CAP_F4 * npr);
+    ens(s->d_thick, 4 * npr); ens(s->d_meta, sizeof(PrimMeta) * npr); ens(s->d_cbox, 16 * npr); ens(s->d_cbox_pf, 16 * npr); ens(s->d_cap, 16 * DVG_CAP_F4 * npr); ens(s->d_quint, sizeof(PrimQuintic) * npr);
     ens(s->d_shape_cdf, 4 * ni); ens(s->d_shape_pmf, 4 * ni); ens(s->d_flags, 16);
     if (!rc && cudaMallocHost((void **)&s->h_pinned, 64) != cudaSuccess) rc = fail(DVG_ERR_CUDA, "cudaMallocHost failed");
     if (!rc && cudaMallocHost((void **)&s->h_counts, 32) != cudaSuccess) rc = fail(DVG_ERR_CUDA, "cudaMallocHost failed");

@@ -194,6 +194,101 @@ DVG_HD int quintic_intervals(const Quintic &q, float intervals[4], float stale0 
     }
     return n;
 }
+// ---- the same quintic and split points, with everything that does not depend on the sample formed ONCE PER PRIMITIVE.
+// Of cubic_quintic's inputs only pp = p0 - pt changes from sample to sample; it enters D, E and F through three float dot
+// products.  A, B, C, the float vectors q1 q2 q3, the float sums sum(q2 q1) and sum(q1 q1), the isolator's leading
+// coefficient p1A, both reciprocals (1 / A, 1 / p1A) and the split point -B / 5 are the primitive's.  Every float
+// expression below is the one cubic_quintic evaluates, in the same order, so D, E, F -- and with DVG_FQ_RECIP the
+// normalised coefficients -- are bit-identical to cubic_quintic's (tests/test_cpu_oracle_and_host.py checks that on the
+// host build of this header).  The exact-test kernel (dvg_wave.cu) reads this 80-byte record instead of redoing ~100
+// float operations and two double divisions per (sample, primitive) pair.
+struct alignas(16) PrimQuintic {
+    double inv_A, B, C, p1A, inv_p1A;
+    float q1x, q1y, q2x, q2y, q3x, q3y, s21, s11;
+    float iv0;   // (float)(-B / 5) when that lies in [0, 1], else -1 ("no split point", Q10)
+    int degenerate;   // |p1A| < 1e-6: the isolator is (at most) a quadratic (solve.h:30-36)
+};
+DVG_HD PrimQuintic prim_quintic(F2 p0, F2 p1, F2 p2, F2 p3) {
+    const F2 q3 = -p0 + 3 * p1 - 3 * p2 + p3;
+    const F2 q2 = 3 * p0 - 6 * p1 + 3 * p2;
+    const F2 q1 = -3 * p0 + 3 * p1;
+    const double A = 3 * sum2(q3 * q3);
+    const double B = 5 * sum2(q3 * q2);
+    const double C = 4 * sum2(q3 * q1) + 2 * sum2(q2 * q2);
+    PrimQuintic k;
+    k.inv_A = 1.0 / A;
+    k.B = B * k.inv_A; k.C = C * k.inv_A;
+    k.q1x = q1.x; k.q1y = q1.y; k.q2x = q2.x; k.q2y = q2.y; k.q3x = q3.x; k.q3y = q3.y;
+    k.s21 = sum2(q2 * q1); k.s11 = sum2(q1 * q1);
+    k.p1A = ((2 / 5.f) * k.C - (4 / 25.f) * k.B * k.B);
+    k.degenerate = fabs(k.p1A) < 1e-6f ? 1 : 0;
+    k.inv_p1A = 1.0 / k.p1A;
+    const double q_root = -k.B / 5.f;
+    k.iv0 = (q_root >= 0 && q_root <= 1) ? (float)q_root : -1.f;
+    return k;
+}
+DVG_HD Quintic quintic_of(const PrimQuintic &k, F2 p0, F2 pt) {
+    const F2 pp = p0 - pt;
+    const F2 q1 = mk2(k.q1x, k.q1y), q2 = mk2(k.q2x, k.q2y), q3 = mk2(k.q3x, k.q3y);
+    const double D = 3 * (k.s21 + sum2(q3 * pp));
+    const double E = k.s11 + 2 * sum2(pp * q2);
+    const double F = sum2(pp * q1);
+    Quintic q;
+    q.B = k.B; q.C = k.C; q.D = D * k.inv_A; q.E = E * k.inv_A; q.F = F * k.inv_A;
+    return q;
+}
+// isolator_roots for the normalised cubic x^3 + b x^2 + c x + d (the caller divided by the leading coefficient): same
+// estimate-then-polish scheme, divisions by constants written as multiplications (the closed form is only the
+// starting point of cubic_polish).
+DVG_HD int isolator_roots_monic(double b, double c, double d, double t[3]) {
+    const double Q = (b * b - 3 * c) * (1.0 / 9.0);
+    const double R = (2 * b * b * b - 9 * b * c + 27 * d) * (1.0 / 54.0);
+    const double Q3 = Q * Q * Q;
+    const double b3 = b * (1.0 / 3.0);
+    if (R * R < Q3) {
+        const float sq = sqrtf((float)Q);
+        float x = (float)R / (sq * sq * sq);
+        x = x < -1.f ? -1.f : (x > 1.f ? 1.f : x);
+        const float theta = acosf(x);
+        const float two_pi = 6.28318530717958647692f;
+        const double m2sq = -2.0 * (double)sq;
+        t[0] = cubic_polish(b, c, d, m2sq * (double)cosf(theta / 3.f) - b3);
+        t[1] = cubic_polish(b, c, d, m2sq * (double)cosf((theta + two_pi) / 3.f) - b3);
+        t[2] = cubic_polish(b, c, d, m2sq * (double)cosf((theta - two_pi) / 3.f) - b3);
+        return 3;
+    } else {
+        const float s = (float)sqrt(R * R - Q3);
+        const float Af = R > 0 ? -cbrtf((float)R + s) : cbrtf((float)(-R) + s);
+        const float Bf = fabsf(Af) > 1e-6f ? (float)Q / Af : 0.f;
+        t[0] = cubic_polish(b, c, d, (double)(Af + Bf) - b3);
+        return 1;
+    }
+}
+// quintic_intervals (fast isolator roots) from the per-primitive record
+DVG_HD int quintic_intervals_of(const PrimQuintic &k, const Quintic &q, float intervals[4]) {
+    const double p1B = ((3 / 5.f) * q.D - (3 / 25.f) * q.B * q.C);
+    const double p1C = ((4 / 5.f) * q.E - (2 / 25.f) * q.B * q.D);
+    const double p1D = q.F - (q.B * q.E) * (1.0 / 25.0);   // (a coefficient of the cubic whose roots are polished: 1 ulp is immaterial)
+    double p_roots[3];
+    int num_sol;
+    if (k.degenerate) num_sol = solve_quadratic_d(p1B, p1C, p1D, &p_roots[0], &p_roots[1]) ? 2 : 0;
+    else num_sol = isolator_roots_monic(p1B * k.inv_p1A, p1C * k.inv_p1A, p1D * k.inv_p1A, p_roots);
+    intervals[0] = k.iv0;
+    const int n = 1 + num_sol;
+    // fixed trip counts (everything stays in registers); the insertion sort of within_distance.h:201-209 step for step,
+    // including where it stops
+    for (int j = 0; j < 3; j++) intervals[j + 1] = j < num_sol ? (float)p_roots[j] : 0.f;
+    for (int j = 1; j < 4; j++) {
+        bool go = j < n;
+        for (int kk = j; kk > 0; kk--) {
+            const float a = intervals[kk - 1], b = intervals[kk];
+            go = go && a > b;
+            intervals[kk - 1] = go ? b : a; intervals[kk] = go ? a : b;
+        }
+    }
+    return n;
+}
+
 // Safeguarded Newton inside one bracket (within_distance.h:233-262).  Returns false when the
 // bracket holds no sign change.
 DVG_HD bool quintic_root_in(const Quintic &q, float lower, float upper, float *t_out) {

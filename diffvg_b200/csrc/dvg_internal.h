@@ -62,16 +62,13 @@ struct BoundaryWork {
 
 // Wavefront passes (dvg_wave.cu): queues and result words in global memory.
 struct WavePair { float x, y; int prim; unsigned ref; };   // shape-local sample position, PrimType << 28 | primitive, word << 5 | candidate
-struct WaveUnit { float lb, ub; int pair; int pad; };     // one root bracket of a cubic pair's closest-point quintic
 struct WaveView {
-    WaveUnit *units_a, *units_d;   // ascending brackets (safeguarded Newton) / descending (the reference bisects)
-    int cap_ua, cap_ud;
     unsigned *hit;        // one word per (evaluation, chunk of 32 candidates): bit k = stroke test of candidate k hit
     unsigned *wind;       // four words per (evaluation, chunk): 4-bit signed winding per candidate; null without fills
     WavePair *pairs_s, *pairs_f;   // exact stroke tests / winding tests still to run
     int cap_s, cap_f;
-    int *counters;        // [0] stroke pairs wanted, [1] fill pairs wanted (may exceed the capacity: the surplus was answered in
-                          // place by W1), [2] ascending units, [3] descending units (surplus answered in place by W2a)
+    int *counters;        // [0] stroke pairs wanted, [1] fill pairs wanted (may exceed the capacity: the surplus is answered in
+                          // place by the retry form of W1)
     int *tile_choff;      // [tiles+1] exclusive scan of chunks per tile
     int *edge_choff;      // [tiles+1] exclusive scan of boundary items * chunks per tile
 };

@@ -74,6 +74,8 @@ struct InstInfo {
     int scene;
 };
 
+struct PrimQuintic;
+
 // Everything the kernels need, passed by value.
 //
 // BATCH: `batch` scenes that share one topology (the stroke scenes of apps/generative_models/rendering.py:170-307: same
@@ -102,6 +104,7 @@ struct SceneView {
     const Box *prim_cbox;  // canvas-space conservative bound of where this primitive can matter (binning only)
     const Box *prim_cbox_pf;  // same for the prefiltering path (binning only)
     const F4 *prim_cap;    // DVG_CAP_F4 float4 per primitive: conservative stroke-reject capsules (dvg_geom.cuh)
+    const PrimQuintic *prim_quint;   // cubic segments: the sample-independent part of the closest-point quintic (dvg_geom.cuh)
     const InstInfo *insts;
     const GroupInfo *groups;
     // boundary sampling tables (scene.cpp:207-333)

@@ -305,158 +305,157 @@ __global__ void __launch_bounds__(WB, DVG_WB_MIN) k_wave_classify_edge(SceneView
 }
 
 // ------------------------------------------------------------------------------------------ W2
-// Exact stroke tests, cubic segments (within_distance.h:119-272), in two steps so that every lane stays busy:
-//   W2a (thread = pair)   end-point checks, the monic quintic of the stationary points of the squared
-//        distance, the isolator split points, and the sign tests of ALL brackets.  Which brackets hold a root,
-//        and where each starts (`lower` only advances past a bracket that held one, :233-271), is a function of
-//        those signs alone, so the brackets of a pair are independent UNITS; the pair's answer is the OR of their
-//        radius tests (the reference's early return only skips work).  Other segment types are answered here.
-//   W2b (thread = unit)   the reference's safeguarded Newton on one bracket (<= 20 evaluations), then the radius
-//        test at the root found.  Ascending and descending brackets are queued apart: after the reference's swap a
-//        descending bracket has lb > ub, its "t in [lb, ub]" guard never holds and it bisects (~3x the trips).
+// Exact stroke tests of the queued pairs (within_distance.h:119-272 for cubic segments), one block round = 256 pairs,
+// in two phases that both keep their lanes busy and talk through shared memory only:
+//   A (thread = pair)     end-point checks; the monic quintic of the stationary points of the squared distance -- its
+//        sample-independent part comes from the primitive's PrimQuintic record (dvg_geom.cuh), the sample adds three
+//        float dot products; the isolator split points; the sign tests of ALL brackets.  Which brackets hold a root, and
+//        where each starts (`lower` only advances past a bracket that held one, :233-271), is a function of those signs
+//        alone, so the brackets of a pair are independent UNITS; the pair's answer is the OR of their radius tests (the
+//        reference's early return only skips work).  Other segment types are answered here.
+//   B (thread = unit)     the block's units, compacted (ascending brackets first, then descending): the reference's
+//        safeguarded Newton on one bracket (<= 20 evaluations), then the radius test at the root found.  After the
+//        reference's swap a descending bracket has lb > ub, its "t in [lb, ub]" guard never holds and it bisects (~3x the
+//        trips, no derivative needed): keeping the two kinds apart keeps the trip counts of a warp alike.
+// An earlier form ran A and B as separate kernels with the units in a global queue: B then re-derived the quintic from a
+// random 16-byte pair gather plus three 16-byte primitive gathers (L2 hit rate 12-27%, 0.9 GB of DRAM reads per step) and
+// A serialised a per-lane append; both kernels sat at ~20% of the FP64 pipe.
 // Per-bracket arithmetic is dvg_geom.cuh's, evaluated on the same inputs: results are unchanged.
-constexpr int W2A_B = 256;
-#ifndef DVG_SETUP_PER_SM
-#define DVG_SETUP_PER_SM 64
+constexpr int SV_B = 256;
+constexpr int SV_MAXU = SV_B * 5;   // a quintic has at most five brackets
+#ifndef DVG_SOLVE_PER_SM
+#define DVG_SOLVE_PER_SM 64
 #endif
-#ifndef DVG_NEWTON_PER_SM
-#define DVG_NEWTON_PER_SM 64
+#ifndef DVG_SOLVE_MINB
+#define DVG_SOLVE_MINB 3
 #endif
+
+struct SolveShared {
+    double qB[SV_B], qC[SV_B], qD[SV_B], qE[SV_B], qF[SV_B];
+    float px[SV_B], py[SV_B];
+    int prim[SV_B];
+    unsigned hit[SV_B];
+    float ulb[SV_MAXU], uub[SV_MAXU];
+    unsigned short upair[SV_MAXU];
+    unsigned warp_tot[SV_B / 32];
+};
 
 // The number of pairs is read from the device counter (nothing is read back to size a launch): the grid is a fixed
 // multiple of the SM count and every block strides over the queue.
-#ifndef DVG_SETUP_MINB
-#define DVG_SETUP_MINB 1
-#endif
-__global__ void __launch_bounds__(W2A_B, DVG_SETUP_MINB) k_wave_stroke_setup(SceneView sc, WaveView wv) {
+__global__ void __launch_bounds__(SV_B, DVG_SOLVE_MINB) k_wave_stroke_solve(SceneView sc, WaveView wv) {
+    __shared__ SolveShared sh;
     const int count = min(wv.counters[0], wv.cap_s);
-    const int lane = threadIdx.x & 31;
-  for (int base = blockIdx.x * W2A_B; base < count; base += gridDim.x * W2A_B) {
-    const int i = base + threadIdx.x;
-    float lbs[5], ubs[5];
-    unsigned valid = 0u, desc = 0u;   // bit j: bracket j holds a root / is descending
-    bool hit = false;
-    WavePair p; p.x = p.y = 0.f; p.prim = 0; p.ref = 0u;
-    F4 p01 = mk4(0, 0, 0, 0), p23 = p01, rad = p01;
-    if (i < count) {
-        p = wv.pairs_s[i];
-        const int ptype = (int)((unsigned)p.prim >> 28);
-        p.prim &= 0x0fffffff;
-        p01 = sc.prim_p01[p.prim]; p23 = sc.prim_p23[p.prim]; rad = sc.prim_rad[p.prim];
-        const F2 pt = mk2(p.x, p.y);
-        if (ptype != PRIM_CUBIC) {
-            const PrimMeta pm = sc.prim_meta[p.prim];
-            bool decided = false;
-            hit = prim_stroke_hit_nocubic(ptype, (pm.type_flags & DVG_PF_APPROX) != 0, p01, p23, rad, sc.insts[pm.inst].r, pt, &decided);
-        } else {
-            const F2 p0 = mk2(p01.x, p01.y), p1 = mk2(p01.z, p01.w), p2 = mk2(p23.x, p23.y), p3 = mk2(p23.z, p23.w);
-            if (dist_sq(p0, pt) < rad.x * rad.x || dist_sq(p3, pt) < rad.w * rad.w) {
-                hit = true;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int base = blockIdx.x * SV_B; base < count; base += gridDim.x * SV_B) {
+        // ---- phase A
+        const int i = base + tid;
+        float lbs[5], ubs[5];
+        unsigned valid = 0u, desc = 0u;   // bit j: bracket j holds a root / is descending
+        bool hit = false;
+        unsigned ref = 0u;
+        if (i < count) {
+            const WavePair p = wv.pairs_s[i];
+            const int ptype = (int)((unsigned)p.prim >> 28);
+            const int e = p.prim & 0x0fffffff;
+            ref = p.ref;
+            const F2 pt = mk2(p.x, p.y);
+            if (ptype != PRIM_CUBIC) {
+                const PrimMeta pm = sc.prim_meta[e];
+                bool decided = false;
+                hit = prim_stroke_hit_nocubic(ptype, (pm.type_flags & DVG_PF_APPROX) != 0, sc.prim_p01[e], sc.prim_p23[e], sc.prim_rad[e],
+                                              sc.insts[pm.inst].r, pt, &decided);
             } else {
-                const Quintic q = cubic_quintic(p0, p1, p2, p3, pt);
-                float iv[4];
-                const int n = quintic_intervals(q, iv);
-                float lower = 0.f;
-                double f_lower = quintic_eval(q, lower);
-                bool open = true;
+                const F4 p01 = sc.prim_p01[e], p23 = sc.prim_p23[e], rad = sc.prim_rad[e];
+                const F2 p0 = mk2(p01.x, p01.y), p3 = mk2(p23.z, p23.w);
+                if (dist_sq(p0, pt) < rad.x * rad.x || dist_sq(p3, pt) < rad.w * rad.w) {
+                    hit = true;
+                } else {
+                    const PrimQuintic k = sc.prim_quint[e];
+                    const Quintic q = quintic_of(k, p0, pt);
+                    float iv[4];
+                    const int n = quintic_intervals_of(k, q, iv);
+                    float lower = 0.f;
+                    double f_lower = quintic_eval(q, lower);
+                    bool open = true;
 #pragma unroll
-                for (int j = 0; j < 5; j++) {
-                    lbs[j] = 0.f; ubs[j] = 0.f;
-                    const float ivj = iv[j < 4 ? j : 3];
-                    if (open && j < n + 1 && !(j < n && ivj < 0.f)) {
-                        const float upper = j < n ? rminf(ivj, 1.f) : 1.f;
-                        const double f_upper = quintic_eval(q, upper);
-                        if (!(f_lower * f_upper > 0)) {                 // :238 (a NaN product counts as a bracket)
-                            const bool d = f_lower > f_upper;         // :239-242
-                            lbs[j] = d ? upper : lower; ubs[j] = d ? lower : upper;
-                            valid |= 1u << j;
-                            if (d) desc |= 1u << j;
-                            if (upper >= 1.f) open = false;            // :268
-                            lower = upper; f_lower = f_upper;
+                    for (int j = 0; j < 5; j++) {
+                        lbs[j] = 0.f; ubs[j] = 0.f;
+                        const float ivj = iv[j < 4 ? j : 3];
+                        if (open && j < n + 1 && !(j < n && ivj < 0.f)) {
+                            const float upper = j < n ? rminf(ivj, 1.f) : 1.f;
+                            const double f_upper = quintic_eval(q, upper);
+                            if (!(f_lower * f_upper > 0)) {                 // :238 (a NaN product counts as a bracket)
+                                const bool d = f_lower > f_upper;         // :239-242
+                                lbs[j] = d ? upper : lower; ubs[j] = d ? lower : upper;
+                                valid |= 1u << j;
+                                if (d) desc |= 1u << j;
+                                if (upper >= 1.f) open = false;            // :268
+                                lower = upper; f_lower = f_upper;
+                            }
                         }
                     }
+                    sh.qB[tid] = q.B; sh.qC[tid] = q.C; sh.qD[tid] = q.D; sh.qE[tid] = q.E; sh.qF[tid] = q.F;
+                    sh.px[tid] = p.x; sh.py[tid] = p.y; sh.prim[tid] = e;
                 }
             }
         }
-    }
-    if (hit) atomicOr(&wv.hit[p.ref >> 5], 1u << (p.ref & 31u));
-    // warp-aggregated append: one atomic per queue per warp
-    const int na = __popc(valid & ~desc), nd = __popc(valid & desc);
-    int sa = na, sd = nd;
+        sh.hit[tid] = hit ? 1u : 0u;
+        // ---- compaction: ascending units from 0, descending ones after them (counts packed 16 + 16 bits)
+        const unsigned mine = (unsigned)__popc(valid & ~desc) | ((unsigned)__popc(valid & desc) << 16);
+        unsigned incl = mine;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int ta = __shfl_up_sync(0xffffffffu, sa, o), td = __shfl_up_sync(0xffffffffu, sd, o);
-        if (lane >= o) { sa += ta; sd += td; }
-    }
-    int base_a = 0, base_d = 0;
-    if (lane == 31) {
-        if (sa) base_a = atomicAdd(&wv.counters[2], sa);
-        if (sd) base_d = atomicAdd(&wv.counters[3], sd);
-    }
-    int pa = __shfl_sync(0xffffffffu, base_a, 31) + sa - na;
-    int pd = __shfl_sync(0xffffffffu, base_d, 31) + sd - nd;
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned u = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += u;
+        }
+        if (lane == 31) sh.warp_tot[warp] = incl;
+        __syncthreads();
+        unsigned before = 0u, total = 0u;
 #pragma unroll
-    for (int j = 0; j < 5; j++) {
-        if (!((valid >> j) & 1u)) continue;
-        const bool d = (desc >> j) & 1u;
-        const int pos = d ? pd++ : pa++;
-        WaveUnit *dst = d ? wv.units_d : wv.units_a;
-        if (pos < (d ? wv.cap_ud : wv.cap_ua)) {
-            WaveUnit u; u.lb = lbs[j]; u.ub = ubs[j]; u.pair = i; u.pad = 0;
-            dst[pos] = u;
-        } else {
-            // queue full (sized 1.5 / 0.75 units per pair): answer the bracket here, same arithmetic as W2b
-            const F2 pt = mk2(p.x, p.y);
-            const Quintic q = cubic_quintic(mk2(p01.x, p01.y), mk2(p01.z, p01.w), mk2(p23.x, p23.y), mk2(p23.z, p23.w), pt);
-            float lb = lbs[j], ub = ubs[j];
+        for (int w = 0; w < SV_B / 32; w++) {
+            const unsigned t = sh.warp_tot[w];
+            if (w < warp) before += t;
+            total += t;
+        }
+        const int total_a = (int)(total & 0xffffu), total_u = total_a + (int)(total >> 16);
+        const unsigned excl = before + incl - mine;
+        int pa = (int)(excl & 0xffffu), pd = total_a + (int)(excl >> 16);
+#pragma unroll
+        for (int j = 0; j < 5; j++) {
+            if (!((valid >> j) & 1u)) continue;
+            const int pos = ((desc >> j) & 1u) ? pd++ : pa++;
+            sh.ulb[pos] = lbs[j]; sh.uub[pos] = ubs[j]; sh.upair[pos] = (unsigned short)tid;
+        }
+        __syncthreads();
+        // ---- phase B
+        for (int u = tid; u < total_u; u += SV_B) {
+            const int pr = sh.upair[u];
+            if (*(volatile unsigned *)&sh.hit[pr]) continue;   // another bracket of the pair already answered "hit"
+            const bool descending = u >= total_a;
+            Quintic q;
+            q.B = sh.qB[pr]; q.C = sh.qC[pr]; q.D = sh.qD[pr]; q.E = sh.qE[pr]; q.F = sh.qF[pr];
+            float lb = sh.ulb[u], ub = sh.uub[u];
             float t = 0.5f * (lb + ub);
-            for (int it = 0; it < 20; it++) {
-                if (!(t >= lb && t <= ub)) t = 0.5f * (lb + ub);
+            for (int it = 0; it < 20; it++) {                              // within_distance.h:244-262
+                if (descending || !(t >= lb && t <= ub)) t = 0.5f * (lb + ub);
                 const double value = quintic_eval(q, t);
                 if (fabs(value) < 1e-5f || it == 19) break;
                 if (value > 0.f) ub = t; else lb = t;
-                const double derivative = quintic_deriv(q, t);
-                t = (float)((double)t - newton_quotient(value, derivative));
+                if (!descending) {   // (a descending bracket replaces the Newton iterate by the midpoint before using it)
+                    const double derivative = quintic_deriv(q, t);
+                    t = (float)((double)t - newton_quotient(value, derivative));
+                }
             }
-            const float tt = 1 - t;
+            const int e = sh.prim[pr];
+            const F4 p01 = sc.prim_p01[e], p23 = sc.prim_p23[e], rad = sc.prim_rad[e];
+            const F2 pt = mk2(sh.px[pr], sh.py[pr]);
+            const float tt = 1 - t;                                        // :263-267
             const float rr = (tt * tt * tt) * rad.x + (3 * tt * tt * t) * rad.y + (3 * tt * t * t) * rad.z + (t * t * t) * rad.w;
             if (dist_sq(eval_cubic(mk2(p01.x, p01.y), mk2(p01.z, p01.w), mk2(p23.x, p23.y), mk2(p23.z, p23.w), t), pt) < rr * rr)
-                atomicOr(&wv.hit[p.ref >> 5], 1u << (p.ref & 31u));
+                sh.hit[pr] = 1u;
         }
-    }
-  }
-}
-
-// WHICH = 1: descending brackets.  After the reference's swap lb > ub, so its "t in [lb, ub]" guard fails on every trip and
-// the Newton iterate is always replaced by the midpoint before it is used: the derivative never matters and is not formed.
-template <int WHICH>
-__global__ void __launch_bounds__(256) k_wave_stroke_newton(SceneView sc, WaveView wv) {
-    const int count = min(wv.counters[2 + WHICH], WHICH ? wv.cap_ud : wv.cap_ua);
-    for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < count; u += gridDim.x * blockDim.x) {
-        const WaveUnit un = (WHICH ? wv.units_d : wv.units_a)[u];
-        WavePair p = wv.pairs_s[un.pair];
-        p.prim &= 0x0fffffff;
-        const unsigned bit = 1u << (p.ref & 31u);
-        if (wv.hit[p.ref >> 5] & bit) continue;   // another bracket of the pair already answered "hit"
-        const F4 p01 = sc.prim_p01[p.prim], p23 = sc.prim_p23[p.prim], rad = sc.prim_rad[p.prim];
-        const F2 p0 = mk2(p01.x, p01.y), p1 = mk2(p01.z, p01.w), p2 = mk2(p23.x, p23.y), p3 = mk2(p23.z, p23.w);
-        const F2 pt = mk2(p.x, p.y);
-        const Quintic q = cubic_quintic(p0, p1, p2, p3, pt);
-        float lb = un.lb, ub = un.ub;
-        float t = 0.5f * (lb + ub);
-        for (int it = 0; it < 20; it++) {                              // within_distance.h:244-262
-            if (WHICH || !(t >= lb && t <= ub)) t = 0.5f * (lb + ub);
-            const double value = quintic_eval(q, t);
-            if (fabs(value) < 1e-5f || it == 19) break;
-            if (value > 0.f) ub = t; else lb = t;
-            if (!WHICH) {
-                const double derivative = quintic_deriv(q, t);
-                t = (float)((double)t - newton_quotient(value, derivative));
-            }
-        }
-        const float tt = 1 - t;                                        // :263-267
-        const float rr = (tt * tt * tt) * rad.x + (3 * tt * tt * t) * rad.y + (3 * tt * t * t) * rad.z + (t * t * t) * rad.w;
-        if (dist_sq(eval_cubic(p0, p1, p2, p3, t), pt) < rr * rr) atomicOr(&wv.hit[p.ref >> 5], bit);
+        __syncthreads();
+        if (sh.hit[tid]) atomicOr(&wv.hit[ref >> 5], 1u << (ref & 31u));
     }
 }
 
@@ -755,12 +754,8 @@ static int stride_grid(int64_t cap, int block, int per_sm) {
 }
 
 void launch_wave_solve(const SceneView &sc, const WaveView &wv, bool strokes, bool fills, cudaStream_t st) {
-    if (strokes && wv.cap_s > 0) {
-        cudaMemsetAsync(wv.counters + 2, 0, sizeof(int) * 2, st);
-        DVG_LAUNCH(k_wave_stroke_setup, dim3(stride_grid(wv.cap_s, W2A_B, DVG_SETUP_PER_SM)), dim3(W2A_B), 0, st, sc, wv);
-        DVG_LAUNCH(k_wave_stroke_newton<0>, dim3(stride_grid(wv.cap_ua, 256, DVG_NEWTON_PER_SM)), dim3(256), 0, st, sc, wv);
-        DVG_LAUNCH(k_wave_stroke_newton<1>, dim3(stride_grid(wv.cap_ud, 256, DVG_NEWTON_PER_SM)), dim3(256), 0, st, sc, wv);
-    }
+    if (strokes && wv.cap_s > 0)
+        DVG_LAUNCH(k_wave_stroke_solve, dim3(stride_grid(wv.cap_s, SV_B, DVG_SOLVE_PER_SM)), dim3(SV_B), 0, st, sc, wv);
     if (fills && wv.cap_f > 0) DVG_LAUNCH(k_wave_solve_fill, dim3(stride_grid(wv.cap_f, 128, 32)), dim3(128), 0, st, sc, wv);
 }
 

@@ -46,6 +46,7 @@ struct HostScene {
     std::vector<InstInfo> insts;
     std::vector<GroupInfo> groups;
     std::vector<F4> p01, p23, rad, cap;
+    std::vector<PrimQuintic> quint;
     std::vector<PrimMeta> meta;
     int error_flag = 0;
     float total_length = 0;
@@ -85,7 +86,7 @@ void build(HostScene &hs, const int32_t *topo, const float *params) {
     hs.seg_cdf.resize(nsg); hs.seg_pmf.resize(nsg); hs.seg_point_id.resize(nsg);
     hs.insts.resize(ni); hs.groups.resize(ng);
     hs.p01.resize(np); hs.p23.resize(np); hs.rad.resize(np); hs.prim_box.resize(np); hs.prim_thick.resize(np);
-    hs.meta.resize(np); hs.prim_cbox.resize(np); hs.prim_cbox_pf.resize(np); hs.cap.resize((size_t)np * DVG_CAP_F4); hs.shape_cdf.resize(ni); hs.shape_pmf.resize(ni);
+    hs.meta.resize(np); hs.prim_cbox.resize(np); hs.prim_cbox_pf.resize(np); hs.cap.resize((size_t)np * DVG_CAP_F4); hs.quint.resize(np); hs.shape_cdf.resize(ni); hs.shape_pmf.resize(ni);
     BuildView bv;
     bv.canvas_w = t[DVG_H_CANVAS_W]; bv.canvas_h = t[DVG_H_CANVAS_H];
     bv.num_shapes = ns; bv.num_groups = ng; bv.num_insts = ni; bv.num_prims = np;
@@ -96,7 +97,7 @@ void build(HostScene &hs, const int32_t *topo, const float *params) {
     bv.seg_cdf = hs.seg_cdf.data(); bv.seg_pmf = hs.seg_pmf.data(); bv.seg_point_id = hs.seg_point_id.data();
     bv.insts = hs.insts.data(); bv.groups = hs.groups.data();
     bv.prim_p01 = hs.p01.data(); bv.prim_p23 = hs.p23.data(); bv.prim_rad = hs.rad.data(); bv.prim_box = hs.prim_box.data();
-    bv.prim_thick = hs.prim_thick.data(); bv.prim_meta = hs.meta.data(); bv.prim_cbox = hs.prim_cbox.data(); bv.prim_cbox_pf = hs.prim_cbox_pf.data(); bv.prim_cap = hs.cap.data();
+    bv.prim_thick = hs.prim_thick.data(); bv.prim_meta = hs.meta.data(); bv.prim_cbox = hs.prim_cbox.data(); bv.prim_cbox_pf = hs.prim_cbox_pf.data(); bv.prim_cap = hs.cap.data(); bv.prim_quint = hs.quint.data();
     bv.shape_cdf = hs.shape_cdf.data(); bv.shape_pmf = hs.shape_pmf.data();
     bv.error_flag = &hs.error_flag; bv.total_length = &hs.total_length;
     for (int s = 0; s < ns; s++) build_shape(bv, s);
@@ -111,7 +112,7 @@ void build(HostScene &hs, const int32_t *topo, const float *params) {
     sc.filter_radius_off = t[DVG_H_FILTER_RADIUS_OFF];
     sc.topo = t; sc.params = hs.params.data();
     sc.prim_p01 = hs.p01.data(); sc.prim_p23 = hs.p23.data(); sc.prim_rad = hs.rad.data(); sc.prim_box = hs.prim_box.data();
-    sc.prim_thick = hs.prim_thick.data(); sc.prim_meta = hs.meta.data(); sc.prim_cbox = hs.prim_cbox.data(); sc.prim_cbox_pf = hs.prim_cbox_pf.data(); sc.prim_cap = hs.cap.data();
+    sc.prim_thick = hs.prim_thick.data(); sc.prim_meta = hs.meta.data(); sc.prim_cbox = hs.prim_cbox.data(); sc.prim_cbox_pf = hs.prim_cbox_pf.data(); sc.prim_cap = hs.cap.data(); sc.prim_quint = hs.quint.data();
     sc.insts = hs.insts.data(); sc.groups = hs.groups.data();
     sc.shapes_length = hs.shapes_length.data(); sc.shape_cdf = hs.shape_cdf.data(); sc.shape_pmf = hs.shape_pmf.data();
     sc.seg_cdf = hs.seg_cdf.data(); sc.seg_pmf = hs.seg_pmf.data(); sc.seg_point_id = hs.seg_point_id.data();
@@ -420,6 +421,43 @@ EXPORT int emul_bracket_classify(const float *cap, float x, float y) { return ca
 EXPORT int emul_stroke_hit_cubic(const float *pts8, const float *rad4, float x, float y) {
     return stroke_hit_cubic(mk2(pts8[0], pts8[1]), mk2(pts8[2], pts8[3]), mk2(pts8[4], pts8[5]), mk2(pts8[6], pts8[7]),
                             mk4(rad4[0], rad4[1], rad4[2], rad4[3]), mk2(x, y)) ? 1 : 0;
+}
+
+// The per-primitive split of the closest-point quintic (dvg_geom.cuh prim_quintic / quintic_of / quintic_intervals_of)
+// against cubic_quintic / quintic_intervals on the same inputs.  out[0]: pairs whose five normalised coefficients are not
+// bit-identical; out[1]: pairs whose split points differ (count or any float); out[2]: pairs whose verdict through the
+// kernel's bracket enumeration differs from stroke_hit_cubic's.
+EXPORT void emul_quintic_split_check(const float *pts8, const float *rad4, const float *xy, int n, long long *out) {
+    const F2 p0 = mk2(pts8[0], pts8[1]), p1 = mk2(pts8[2], pts8[3]), p2 = mk2(pts8[4], pts8[5]), p3 = mk2(pts8[6], pts8[7]);
+    const F4 r = mk4(rad4[0], rad4[1], rad4[2], rad4[3]);
+    const PrimQuintic k = prim_quintic(p0, p1, p2, p3);
+    out[0] = out[1] = out[2] = 0;
+    for (int i = 0; i < n; i++) {
+        const F2 pt = mk2(xy[2 * i], xy[2 * i + 1]);
+        const Quintic a = cubic_quintic(p0, p1, p2, p3, pt), b = quintic_of(k, p0, pt);
+        if (memcmp(&a, &b, sizeof a) != 0) out[0]++;
+        float ia[4] = {0, 0, 0, 0}, ib[4] = {0, 0, 0, 0};
+        const int na = quintic_intervals(a, ia), nb = quintic_intervals_of(k, b, ib);
+        if (na != nb || memcmp(ia, ib, sizeof(float) * na) != 0) out[1]++;
+        // the kernel's enumeration: brackets from the signs at the split points, answer = OR of the radius tests
+        bool hit = dist_sq(p0, pt) < r.x * r.x || dist_sq(p3, pt) < r.w * r.w;
+        if (!hit) {
+            float lower = 0.f;
+            for (int j = 0; j < nb + 1 && !hit; j++) {
+                if (j < nb && ib[j] < 0.f) continue;
+                const float upper = j < nb ? rminf(ib[j], 1.f) : 1.f;
+                float t;
+                if (quintic_root_in(b, lower, upper, &t)) {
+                    const float tt = 1 - t;
+                    const float rr = (tt * tt * tt) * r.x + (3 * tt * tt * t) * r.y + (3 * tt * t * t) * r.z + (t * t * t) * r.w;
+                    if (dist_sq(eval_cubic(p0, p1, p2, p3, t), pt) < rr * rr) hit = true;
+                    if (upper >= 1.f) break;
+                    lower = upper;
+                }
+            }
+        }
+        if (hit != stroke_hit_cubic(p0, p1, p2, p3, r, pt)) out[2]++;
+    }
 }
 
 EXPORT void emul_pcg(int idx, uint64_t seed, uint64_t *state, float *rx, float *ry) {

@@ -373,3 +373,35 @@ def test_tight_binning_never_drops_a_stroke_a_sample_could_touch():
                 assert lib.emul_bracket_classify(cap.ctypes.data_as(fp), x, y) < 0
                 assert lib.emul_stroke_hit_cubic(pts.ctypes.data_as(fp), rad.ctypes.data_as(fp), x, y) == 0
     assert dropped > 1000 and kept > 200   # the test is exercised both ways
+
+
+def test_per_primitive_quintic_split_is_bit_identical():
+    """dvg_geom.cuh prim_quintic / quintic_of: the sample-independent part of the closest-point quintic formed once per
+    primitive (what the exact-test kernel reads) gives the SAME five normalised coefficients, bit for bit, as
+    cubic_quintic on every (cubic, sample) pair; the split points from the per-primitive isolator record agree with
+    quintic_intervals' floats except where a root sits on a float rounding boundary (the two closed forms differ by
+    ~1e-16 before the polish); the verdict through the kernel's bracket enumeration equals stroke_hit_cubic's."""
+    import ctypes
+    lib = emul._load()
+    fp = ctypes.POINTER(ctypes.c_float)
+    lib.emul_quintic_split_check.argtypes = [fp, fp, fp, ctypes.c_int, ctypes.POINTER(ctypes.c_longlong)]
+    rng = np.random.RandomState(21)
+    total = coeff = split = verdict = 0
+    for c in range(400):
+        p0 = rng.rand(2) * 512
+        pts = [p0]
+        for _k in range(3):
+            pts.append(pts[-1] + (rng.rand(2) - 0.5) * (25.6 if c % 4 else 200.0))
+        if c % 50 == 7:
+            pts[3] = pts[0] + 3 * (pts[2] - pts[1])       # q3 == 0: a quadratic in disguise (A = 0)
+        pts = np.asarray(pts, np.float32).reshape(-1)
+        rad = (0.5 + 3.5 * rng.rand(4)).astype(np.float32)
+        n = 2000
+        lo, hi = pts.reshape(4, 2).min(0) - 6, pts.reshape(4, 2).max(0) + 6
+        xy = (rng.rand(n, 2) * (hi - lo) + lo).astype(np.float32)
+        out = (ctypes.c_longlong * 3)()
+        lib.emul_quintic_split_check(pts.ctypes.data_as(fp), rad.ctypes.data_as(fp), xy.ctypes.data_as(fp), n, out)
+        total += n; coeff += out[0]; split += out[1]; verdict += out[2]
+    assert coeff == 0
+    assert split <= total * 1e-4, (split, total)
+    assert verdict == 0
