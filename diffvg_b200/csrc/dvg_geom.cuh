@@ -97,11 +97,21 @@ DVG_HD double quintic_deriv(const Quintic &q, double t) {  // within_distance.h:
 // float (the next iterate), so ~45 correct bits are as good as 53: reciprocal seed in float, one
 // Newton step in double.  Falls back to the IEEE division outside the float range.
 DVG_HD_NOINLINE double ieee_quotient(double value, double derivative) { return value / derivative; }
+// float reciprocal used as a SEED only (one MUFU.RCP on the device; the callers keep |x| within [1e-30, 1e30])
+DVG_HD float seed_rcp(float x) {
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return 1.0f / x;
+#endif
+}
 DVG_HD double newton_quotient(double value, double derivative) {
 #if defined(DVG_FQ_NEWTON)
     const float df = (float)derivative;
     if (fabsf(df) > 1e-30f && fabsf(df) < 1e30f) {
-        const double r0 = (double)(1.0f / df);
+        const double r0 = (double)seed_rcp(df);
         const double r1 = fma(r0, fma(-derivative, r0, 1.0), r0);
         return value * r1;
     }
@@ -129,6 +139,12 @@ DVG_HD double cubic_polish(double b, double c, double d, double x) {
     for (int it = 0; it < DVG_POLISH_STEPS; it++) {
         const double f = fma(fma(fma(x, 1.0, b), x, c), x, d);
         const double fp = fma(fma(3.0, x, 2.0 * b), x, c);
+#if defined(DVG_FQ_NEWTON)
+        // the correction f / fp is ~1e-6 |x| in the first step and ~1e-12 |x| in the second: a quotient good to float
+        // precision moves x by less than a double ulp of what the exact quotient would (f itself is formed in double)
+        const float fpf = (float)fp, ff = (float)f;
+        if (fabsf(fpf) > 1e-30f && fabsf(fpf) < 1e30f && fabsf(ff) < 1e30f) { x -= (double)(ff * seed_rcp(fpf)); continue; }
+#endif
         if (fp != 0.0) x -= newton_quotient(f, fp);
     }
     return x;

@@ -305,24 +305,33 @@ __global__ void __launch_bounds__(WB, DVG_WB_MIN) k_wave_classify_edge(SceneView
 }
 
 // ------------------------------------------------------------------------------------------ W2
-// Exact stroke tests of the queued pairs (within_distance.h:119-272 for cubic segments), one block round = 256 pairs,
-// in two phases that both keep their lanes busy and talk through shared memory only:
-//   A (thread = pair)     end-point checks; the monic quintic of the stationary points of the squared distance -- its
+// Exact stroke tests of the queued pairs (within_distance.h:119-272 for cubic segments).  One WARP takes 64 pairs at a
+// time through two phases that both keep its lanes busy and talk through the warp's slice of shared memory only (no
+// block-level barrier: the warps of a block drift apart freely):
+//   A (lane = pair, twice)  end-point checks; the monic quintic of the stationary points of the squared distance -- its
 //        sample-independent part comes from the primitive's PrimQuintic record (dvg_geom.cuh), the sample adds three
 //        float dot products; the isolator split points; the sign tests of ALL brackets.  Which brackets hold a root, and
 //        where each starts (`lower` only advances past a bracket that held one, :233-271), is a function of those signs
 //        alone, so the brackets of a pair are independent UNITS; the pair's answer is the OR of their radius tests (the
 //        reference's early return only skips work).  Other segment types are answered here.
-//   B (thread = unit)     the block's units, compacted (ascending brackets first, then descending): the reference's
-//        safeguarded Newton on one bracket (<= 20 evaluations), then the radius test at the root found.  After the
-//        reference's swap a descending bracket has lb > ub, its "t in [lb, ub]" guard never holds and it bisects (~3x the
-//        trips, no derivative needed): keeping the two kinds apart keeps the trip counts of a warp alike.
-// An earlier form ran A and B as separate kernels with the units in a global queue: B then re-derived the quintic from a
-// random 16-byte pair gather plus three 16-byte primitive gathers (L2 hit rate 12-27%, 0.9 GB of DRAM reads per step) and
-// A serialised a per-lane append; both kernels sat at ~20% of the FP64 pipe.
+//   B (lane = unit)         the warp's units, compacted (ascending brackets from the front of the list, descending ones
+//        from its back): the reference's safeguarded Newton on one bracket (<= 20 evaluations), then the radius test at
+//        the root found.  After the reference's swap a descending bracket has lb > ub, its "t in [lb, ub]" guard never
+//        holds and it bisects (~3x the trips, no derivative needed): keeping the two kinds apart keeps the trip counts
+//        of a round alike.
+// Earlier forms: (1) A and B as separate kernels with the units in a global queue -- B re-derived the quintic from a random
+// 16-byte pair gather plus three 16-byte primitive gathers (L2 hit rate 12-27%, 0.9 GB of DRAM reads per step) and A
+// serialised a per-lane append: 2.58 ms per step at the painterly config; (2) one kernel, one block round = 256 pairs with
+// a block-wide compaction: 2.12 ms, a fifth of it at the two barriers.
 // Per-bracket arithmetic is dvg_geom.cuh's, evaluated on the same inputs: results are unchanged.
-constexpr int SV_B = 256;
-constexpr int SV_MAXU = SV_B * 5;   // a quintic has at most five brackets
+constexpr int SV_B = 256;                 // threads per block
+constexpr int SV_NW = SV_B / 32;
+#ifndef DVG_SOLVE_PPL
+#define DVG_SOLVE_PPL 2
+#endif
+constexpr int SV_PPL = DVG_SOLVE_PPL;     // pairs per lane and round
+constexpr int SV_PAIRS = 32 * SV_PPL;     // pairs per warp and round
+constexpr int SV_MAXU = SV_PAIRS * 5;     // a quintic has at most five brackets
 #ifndef DVG_SOLVE_PER_SM
 #define DVG_SOLVE_PER_SM 64
 #endif
@@ -330,132 +339,146 @@ constexpr int SV_MAXU = SV_B * 5;   // a quintic has at most five brackets
 #define DVG_SOLVE_MINB 3
 #endif
 
-struct SolveShared {
-    double qB[SV_B], qC[SV_B], qD[SV_B], qE[SV_B], qF[SV_B];
-    float px[SV_B], py[SV_B];
-    int prim[SV_B];
-    unsigned hit[SV_B];
+struct SolveWarp {
+    double qD[SV_PAIRS], qE[SV_PAIRS], qF[SV_PAIRS];   // (B and C are the primitive's: read from its record)
+    float px[SV_PAIRS], py[SV_PAIRS];
+    int prim[SV_PAIRS];
     float ulb[SV_MAXU], uub[SV_MAXU];
     unsigned short upair[SV_MAXU];
-    unsigned warp_tot[SV_B / 32];
+    unsigned hit[SV_PPL];                 // bit l of word h: pair h * 32 + l answered "hit"
 };
 
 // The number of pairs is read from the device counter (nothing is read back to size a launch): the grid is a fixed
-// multiple of the SM count and every block strides over the queue.
+// multiple of the SM count and every warp strides over the queue.
 __global__ void __launch_bounds__(SV_B, DVG_SOLVE_MINB) k_wave_stroke_solve(SceneView sc, WaveView wv) {
-    __shared__ SolveShared sh;
+    __shared__ SolveWarp s_sw[SV_NW];
+    const unsigned FULL = 0xffffffffu;
     const int count = min(wv.counters[0], wv.cap_s);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int base = blockIdx.x * SV_B; base < count; base += gridDim.x * SV_B) {
+    const int lane = threadIdx.x & 31;
+        SolveWarp &sw = s_sw[threadIdx.x >> 5];
+    const int gwarp = blockIdx.x * SV_NW + (threadIdx.x >> 5), nwarps = gridDim.x * SV_NW;
+    for (int base = gwarp * SV_PAIRS; base < count; base += nwarps * SV_PAIRS) {
         // ---- phase A
-        const int i = base + tid;
-        float lbs[5], ubs[5];
-        unsigned valid = 0u, desc = 0u;   // bit j: bracket j holds a root / is descending
-        bool hit = false;
-        unsigned ref = 0u;
-        if (i < count) {
-            const WavePair p = wv.pairs_s[i];
-            const int ptype = (int)((unsigned)p.prim >> 28);
-            const int e = p.prim & 0x0fffffff;
-            ref = p.ref;
-            const F2 pt = mk2(p.x, p.y);
-            if (ptype != PRIM_CUBIC) {
-                const PrimMeta pm = sc.prim_meta[e];
-                bool decided = false;
-                hit = prim_stroke_hit_nocubic(ptype, (pm.type_flags & DVG_PF_APPROX) != 0, sc.prim_p01[e], sc.prim_p23[e], sc.prim_rad[e],
-                                              sc.insts[pm.inst].r, pt, &decided);
-            } else {
-                const F4 p01 = sc.prim_p01[e], p23 = sc.prim_p23[e], rad = sc.prim_rad[e];
-                const F2 p0 = mk2(p01.x, p01.y), p3 = mk2(p23.z, p23.w);
-                if (dist_sq(p0, pt) < rad.x * rad.x || dist_sq(p3, pt) < rad.w * rad.w) {
-                    hit = true;
+        int na = 0, nd = 0;               // units so far: ascending from the front, descending from the back
+        unsigned refs[SV_PPL];
+#pragma unroll 1
+        for (int h = 0; h < SV_PPL; h++) {
+            const int i = base + h * 32 + lane, slot = h * 32 + lane;
+            float lbs[5], ubs[5];
+            unsigned valid = 0u, desc = 0u;   // bit j: bracket j holds a root / is descending
+            bool hit = false;
+            unsigned ref = 0u;
+            if (i < count) {
+                const WavePair p = wv.pairs_s[i];
+                const int ptype = (int)((unsigned)p.prim >> 28);
+                const int e = p.prim & 0x0fffffff;
+                ref = p.ref;
+                const F2 pt = mk2(p.x, p.y);
+                if (ptype != PRIM_CUBIC) {
+                    const PrimMeta pm = sc.prim_meta[e];
+                    bool decided = false;
+                    hit = prim_stroke_hit_nocubic(ptype, (pm.type_flags & DVG_PF_APPROX) != 0, sc.prim_p01[e], sc.prim_p23[e], sc.prim_rad[e],
+                                                  sc.insts[pm.inst].r, pt, &decided);
                 } else {
-                    const PrimQuintic k = sc.prim_quint[e];
-                    const Quintic q = quintic_of(k, p0, pt);
-                    float iv[4];
-                    const int n = quintic_intervals_of(k, q, iv);
-                    float lower = 0.f;
-                    double f_lower = quintic_eval(q, lower);
-                    bool open = true;
+                    const F4 p01 = sc.prim_p01[e], p23 = sc.prim_p23[e], rad = sc.prim_rad[e];
+                    const F2 p0 = mk2(p01.x, p01.y), p3 = mk2(p23.z, p23.w);
+                    if (dist_sq(p0, pt) < rad.x * rad.x || dist_sq(p3, pt) < rad.w * rad.w) {
+                        hit = true;
+                    } else {
+                        const PrimQuintic k = sc.prim_quint[e];
+                        const Quintic q = quintic_of(k, p0, pt);
+                        float iv[4];
+                        const int n = quintic_intervals_of(k, q, iv);
+                        float lower = 0.f;
+                        double f_lower = quintic_eval(q, lower);
+                        bool open = true;
 #pragma unroll
-                    for (int j = 0; j < 5; j++) {
-                        lbs[j] = 0.f; ubs[j] = 0.f;
-                        const float ivj = iv[j < 4 ? j : 3];
-                        if (open && j < n + 1 && !(j < n && ivj < 0.f)) {
-                            const float upper = j < n ? rminf(ivj, 1.f) : 1.f;
-                            const double f_upper = quintic_eval(q, upper);
-                            if (!(f_lower * f_upper > 0)) {                 // :238 (a NaN product counts as a bracket)
-                                const bool d = f_lower > f_upper;         // :239-242
-                                lbs[j] = d ? upper : lower; ubs[j] = d ? lower : upper;
-                                valid |= 1u << j;
-                                if (d) desc |= 1u << j;
-                                if (upper >= 1.f) open = false;            // :268
-                                lower = upper; f_lower = f_upper;
+                        for (int j = 0; j < 5; j++) {
+                            lbs[j] = 0.f; ubs[j] = 0.f;
+                            const float ivj = iv[j < 4 ? j : 3];
+                            if (open && j < n + 1 && !(j < n && ivj < 0.f)) {
+                                const float upper = j < n ? rminf(ivj, 1.f) : 1.f;
+                                const double f_upper = quintic_eval(q, upper);
+                                if (!(f_lower * f_upper > 0)) {                 // :238 (a NaN product counts as a bracket)
+                                    const bool d = f_lower > f_upper;         // :239-242
+                                    lbs[j] = d ? upper : lower; ubs[j] = d ? lower : upper;
+                                    valid |= 1u << j;
+                                    if (d) desc |= 1u << j;
+                                    if (upper >= 1.f) open = false;            // :268
+                                    lower = upper; f_lower = f_upper;
+                                }
                             }
                         }
+                        sw.qD[slot] = q.D; sw.qE[slot] = q.E; sw.qF[slot] = q.F;
+                        sw.px[slot] = p.x; sw.py[slot] = p.y; sw.prim[slot] = e;
                     }
-                    sh.qB[tid] = q.B; sh.qC[tid] = q.C; sh.qD[tid] = q.D; sh.qE[tid] = q.E; sh.qF[tid] = q.F;
-                    sh.px[tid] = p.x; sh.py[tid] = p.y; sh.prim[tid] = e;
                 }
             }
-        }
-        sh.hit[tid] = hit ? 1u : 0u;
-        // ---- compaction: ascending units from 0, descending ones after them (counts packed 16 + 16 bits)
-        const unsigned mine = (unsigned)__popc(valid & ~desc) | ((unsigned)__popc(valid & desc) << 16);
-        unsigned incl = mine;
+            refs[h] = ref;
+            const unsigned hm = __ballot_sync(FULL, hit);
+            if (lane == 0) sw.hit[h] = hm;
+            // compaction of this half's units (counts packed 16 + 16 bits)
+            const unsigned mine = (unsigned)__popc(valid & ~desc) | ((unsigned)__popc(valid & desc) << 16);
+            unsigned incl = mine;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned u = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += u;
-        }
-        if (lane == 31) sh.warp_tot[warp] = incl;
-        __syncthreads();
-        unsigned before = 0u, total = 0u;
-#pragma unroll
-        for (int w = 0; w < SV_B / 32; w++) {
-            const unsigned t = sh.warp_tot[w];
-            if (w < warp) before += t;
-            total += t;
-        }
-        const int total_a = (int)(total & 0xffffu), total_u = total_a + (int)(total >> 16);
-        const unsigned excl = before + incl - mine;
-        int pa = (int)(excl & 0xffffu), pd = total_a + (int)(excl >> 16);
-#pragma unroll
-        for (int j = 0; j < 5; j++) {
-            if (!((valid >> j) & 1u)) continue;
-            const int pos = ((desc >> j) & 1u) ? pd++ : pa++;
-            sh.ulb[pos] = lbs[j]; sh.uub[pos] = ubs[j]; sh.upair[pos] = (unsigned short)tid;
-        }
-        __syncthreads();
-        // ---- phase B
-        for (int u = tid; u < total_u; u += SV_B) {
-            const int pr = sh.upair[u];
-            if (*(volatile unsigned *)&sh.hit[pr]) continue;   // another bracket of the pair already answered "hit"
-            const bool descending = u >= total_a;
-            Quintic q;
-            q.B = sh.qB[pr]; q.C = sh.qC[pr]; q.D = sh.qD[pr]; q.E = sh.qE[pr]; q.F = sh.qF[pr];
-            float lb = sh.ulb[u], ub = sh.uub[u];
-            float t = 0.5f * (lb + ub);
-            for (int it = 0; it < 20; it++) {                              // within_distance.h:244-262
-                if (descending || !(t >= lb && t <= ub)) t = 0.5f * (lb + ub);
-                const double value = quintic_eval(q, t);
-                if (fabs(value) < 1e-5f || it == 19) break;
-                if (value > 0.f) ub = t; else lb = t;
-                if (!descending) {   // (a descending bracket replaces the Newton iterate by the midpoint before using it)
-                    const double derivative = quintic_deriv(q, t);
-                    t = (float)((double)t - newton_quotient(value, derivative));
-                }
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned u = __shfl_up_sync(FULL, incl, o);
+                if (lane >= o) incl += u;
             }
-            const int e = sh.prim[pr];
-            const F4 p01 = sc.prim_p01[e], p23 = sc.prim_p23[e], rad = sc.prim_rad[e];
-            const F2 pt = mk2(sh.px[pr], sh.py[pr]);
-            const float tt = 1 - t;                                        // :263-267
-            const float rr = (tt * tt * tt) * rad.x + (3 * tt * tt * t) * rad.y + (3 * tt * t * t) * rad.z + (t * t * t) * rad.w;
-            if (dist_sq(eval_cubic(mk2(p01.x, p01.y), mk2(p01.z, p01.w), mk2(p23.x, p23.y), mk2(p23.z, p23.w), t), pt) < rr * rr)
-                sh.hit[pr] = 1u;
+            const unsigned total = __shfl_sync(FULL, incl, 31), excl = incl - mine;
+            int pa = na + (int)(excl & 0xffffu), pd = SV_MAXU - 1 - (nd + (int)(excl >> 16));
+#pragma unroll
+            for (int j = 0; j < 5; j++) {
+                if (!((valid >> j) & 1u)) continue;
+                const int pos = ((desc >> j) & 1u) ? pd-- : pa++;
+                sw.ulb[pos] = lbs[j]; sw.uub[pos] = ubs[j]; sw.upair[pos] = (unsigned short)slot;
+            }
+            na += (int)(total & 0xffffu); nd += (int)(total >> 16);
         }
-        __syncthreads();
-        if (sh.hit[tid]) atomicOr(&wv.hit[ref >> 5], 1u << (ref & 31u));
+        __syncwarp();
+        // ---- phase B: ascending units in rounds of 32, then the descending ones
+#pragma unroll 1
+        for (int rr0 = 0; rr0 < ((na + 31) & ~31) + nd; rr0 += 32) {
+            const bool descending = rr0 >= ((na + 31) & ~31);   // (a round never mixes the two kinds)
+            const int k = (descending ? rr0 - ((na + 31) & ~31) : rr0) + lane;
+            bool have = k < (descending ? nd : na);
+            const int u = descending ? SV_MAXU - 1 - k : k;
+            int pr = 0;
+            if (have) {
+                pr = sw.upair[u];
+                have = !((*(volatile unsigned *)&sw.hit[pr >> 5] >> (pr & 31)) & 1u);   // another bracket of the pair already answered "hit"
+            }
+            bool pass = false;
+            if (have) {
+                const int e = sw.prim[pr];
+                Quintic q;
+                q.B = sc.prim_quint[e].B; q.C = sc.prim_quint[e].C; q.D = sw.qD[pr]; q.E = sw.qE[pr]; q.F = sw.qF[pr];
+                float lb = sw.ulb[u], ub = sw.uub[u];
+                float t = 0.5f * (lb + ub);
+                for (int it = 0; it < 20; it++) {                              // within_distance.h:244-262
+                    if (descending || !(t >= lb && t <= ub)) t = 0.5f * (lb + ub);
+                    const double value = quintic_eval(q, t);
+                    if (fabs(value) < 1e-5f || it == 19) break;
+                    if (value > 0.f) ub = t; else lb = t;
+                    if (!descending) {   // (a descending bracket replaces the Newton iterate by the midpoint before using it)
+                        const double derivative = quintic_deriv(q, t);
+                        t = (float)((double)t - newton_quotient(value, derivative));
+                    }
+                }
+                const F4 p01 = sc.prim_p01[e], p23 = sc.prim_p23[e], rad = sc.prim_rad[e];
+                const F2 pt = mk2(sw.px[pr], sw.py[pr]);
+                const float tt = 1 - t;                                        // :263-267
+                const float rr = (tt * tt * tt) * rad.x + (3 * tt * tt * t) * rad.y + (3 * tt * t * t) * rad.z + (t * t * t) * rad.w;
+                pass = dist_sq(eval_cubic(mk2(p01.x, p01.y), mk2(p01.z, p01.w), mk2(p23.x, p23.y), mk2(p23.z, p23.w), t), pt) < rr * rr;
+            }
+            if (pass) atomicOr(&sw.hit[pr >> 5], 1u << (pr & 31));
+            __syncwarp();
+        }
+        __syncwarp();
+#pragma unroll
+        for (int h = 0; h < SV_PPL; h++)
+            if ((sw.hit[h] >> lane) & 1u) atomicOr(&wv.hit[refs[h] >> 5], 1u << (refs[h] & 31u));
+        __syncwarp();
     }
 }
 
@@ -755,7 +778,7 @@ static int stride_grid(int64_t cap, int block, int per_sm) {
 
 void launch_wave_solve(const SceneView &sc, const WaveView &wv, bool strokes, bool fills, cudaStream_t st) {
     if (strokes && wv.cap_s > 0)
-        DVG_LAUNCH(k_wave_stroke_solve, dim3(stride_grid(wv.cap_s, SV_B, DVG_SOLVE_PER_SM)), dim3(SV_B), 0, st, sc, wv);
+        DVG_LAUNCH(k_wave_stroke_solve, dim3(stride_grid(wv.cap_s, SV_NW * SV_PAIRS, DVG_SOLVE_PER_SM)), dim3(SV_B), 0, st, sc, wv);
     if (fills && wv.cap_f > 0) DVG_LAUNCH(k_wave_solve_fill, dim3(stride_grid(wv.cap_f, 128, 32)), dim3(128), 0, st, sc, wv);
 }
 
