@@ -58,6 +58,7 @@ lib.dvg_measure_peak.restype = _i
 DVG_ERR_UNSUPPORTED = 4
 DVG_BWD_SKIP_XFORM_GRAD = 1
 DVG_BWD_ACCUMULATE = 2
+DVG_BWD_SKIP_FILTER_GRAD = 4
 
 
 def check(rc):

@@ -256,6 +256,22 @@ DVG_HD Quintic quintic_of(const PrimQuintic &k, F2 p0, F2 pt) {
 // isolator_roots for the normalised cubic x^3 + b x^2 + c x + d (the caller divided by the leading coefficient): same
 // estimate-then-polish scheme, divisions by constants written as multiplications (the closed form is only the
 // starting point of cubic_polish).
+// Cosine of the closed-form ESTIMATE (|x| <= pi): one MUFU on the device (absolute error ~5e-7), the polish removes it.
+DVG_HD float est_cos(float x) {
+#if defined(__CUDA_ARCH__)
+    return __cosf(x);
+#else
+    return cosf(x);
+#endif
+}
+// A split point only matters inside [0, 1]: negative ones are skipped and every one above 1 closes the last bracket at 1
+// (within_distance.h:229-232), whatever its value.  An estimate that lies outside [0, 1] by far more than the closed
+// form's error (<= 2e-4 of the magnitudes it subtracts, reached next to a double root) is therefore used as it is.
+DVG_HD double polish_if_in_range(double b, double c, double d, double est, float scale) {
+    const float m = 0.02f * scale + 0.01f;
+    if (est < -(double)m || est > 1.0 + (double)m) return est;
+    return cubic_polish(b, c, d, est);
+}
 DVG_HD int isolator_roots_monic(double b, double c, double d, double t[3]) {
     const double Q = (b * b - 3 * c) * (1.0 / 9.0);
     const double R = (2 * b * b * b - 9 * b * c + 27 * d) * (1.0 / 54.0);
@@ -268,15 +284,16 @@ DVG_HD int isolator_roots_monic(double b, double c, double d, double t[3]) {
         const float theta = acosf(x);
         const float two_pi = 6.28318530717958647692f;
         const double m2sq = -2.0 * (double)sq;
-        t[0] = cubic_polish(b, c, d, m2sq * (double)cosf(theta / 3.f) - b3);
-        t[1] = cubic_polish(b, c, d, m2sq * (double)cosf((theta + two_pi) / 3.f) - b3);
-        t[2] = cubic_polish(b, c, d, m2sq * (double)cosf((theta - two_pi) / 3.f) - b3);
+        const float scale = 2.f * sq + fabsf((float)b3);
+        t[0] = polish_if_in_range(b, c, d, m2sq * (double)est_cos(theta / 3.f) - b3, scale);
+        t[1] = polish_if_in_range(b, c, d, m2sq * (double)est_cos((theta + two_pi) / 3.f) - b3, scale);
+        t[2] = polish_if_in_range(b, c, d, m2sq * (double)est_cos((theta - two_pi) / 3.f) - b3, scale);
         return 3;
     } else {
         const float s = (float)sqrt(R * R - Q3);
         const float Af = R > 0 ? -cbrtf((float)R + s) : cbrtf((float)(-R) + s);
         const float Bf = fabsf(Af) > 1e-6f ? (float)Q / Af : 0.f;
-        t[0] = cubic_polish(b, c, d, (double)(Af + Bf) - b3);
+        t[0] = polish_if_in_range(b, c, d, (double)(Af + Bf) - b3, fabsf(Af) + fabsf(Bf) + fabsf((float)b3));
         return 1;
     }
 }

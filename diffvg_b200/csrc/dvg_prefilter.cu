@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(PB) k_render_pf(SceneView sc, BinView bins, Re
                 float *d = ra.d_background + 4 * (y * ra.width + x);
                 atomicAdd(d + 0, d_color.x); atomicAdd(d + 1, d_color.y); atomicAdd(d + 2, d_color.z); atomicAdd(d + 3, d_color.w);
             }
-            d_radius_acc = filter_radius_grad(sc, ra, x, y, pt, color);
+            if (!(ra.flags & 4u)) d_radius_acc = filter_radius_grad(sc, ra, x, y, pt, color);   // DVG_BWD_SKIP_FILTER_GRAD
         }
         d_radius_acc = warp_sum(d_radius_acc);
         if ((tid & 31) == 0) sk.add(sc.filter_radius_off, d_radius_acc);

@@ -607,7 +607,7 @@ __global__ void __launch_bounds__(WB, DVG_WB_MIN + 1) k_wave_composite_px(SceneV
                 float *d = ra.d_background + 4 * (y * ra.width + x);
                 atomicAdd(d + 0, dcr); atomicAdd(d + 1, dcg); atomicAdd(d + 2, dcb); atomicAdd(d + 3, dca);
             }
-            if (active) d_radius_acc += filter_radius_grad(sc, ra, x, y, pt, color);
+            if (active && !(ra.flags & 4u)) d_radius_acc += filter_radius_grad(sc, ra, x, y, pt, color);   // DVG_BWD_SKIP_FILTER_GRAD
         }
     }
     if (BACKWARD) {   // every sample adds to d_filter.radius

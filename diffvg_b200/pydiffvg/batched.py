@@ -99,7 +99,7 @@ class BatchRenderFunction(torch.autograd.Function):
             n.check(n.lib.dvg_render_backward_batch(
                 ns.handle, bg.data_ptr() if bg is not None else None, grad_images.data_ptr(), width, height, nsx, nsy,
                 ctx.seeds.ctypes.data, d_params.data_ptr(), d_bg.data_ptr() if d_bg is not None else None,
-                0 if ctx.packed.needs_xform_grad else n.DVG_BWD_SKIP_XFORM_GRAD, stream))
+                _rp.backward_flags(ctx.packed), stream))
         if d_params.device != ctx.params_device:
             d_params = d_params.to(ctx.params_device)
         return None, None, None, None, None, d_bg, None, d_params
@@ -111,7 +111,7 @@ render_batch = BatchRenderFunction.apply
 def serialize_scenes(canvas_width, canvas_height, scenes, filter_type=0, filter_radius=None):
     """`scenes`: list of (shapes, shape_groups) with one common structure.  Returns [PackedScene, params[batch, N]]
     (differentiable with respect to the holders' tensors), to splat into `render_batch`."""
-    topo0, rows, xform_grad = None, [], False
+    topo0, rows, xform_grad, filter_grad = None, [], False, False
     for shapes, groups in scenes:
         topo, tensors = scene_pack.pack_scene(canvas_width, canvas_height, shapes, groups, filter_type, filter_radius)
         if topo0 is None:
@@ -119,9 +119,10 @@ def serialize_scenes(canvas_width, canvas_height, scenes, filter_type=0, filter_
         elif topo.shape != topo0.shape or not np.array_equal(topo, topo0):
             raise ValueError('the scenes of a batch must share one topology (shape types, segment counts, groups, colour kinds)')
         xform_grad = xform_grad or any(t.requires_grad for t in tensors[scene_pack.B_MAT3])
+        filter_grad = filter_grad or any(t.requires_grad for t in tensors[scene_pack.B_FILTER])
         rows.append(scene_pack.concat_params(tensors))
     packed = PackedScene(topo0, canvas_width, canvas_height, OutputType.color, False, torch.tensor([]))
-    packed.needs_xform_grad = xform_grad
+    packed.needs_xform_grad, packed.needs_filter_grad = xform_grad, filter_grad
     return [packed, torch.stack(rows)]
 
 
@@ -150,7 +151,7 @@ def stroke_scene_args(all_points, all_widths, all_colors, canvas_size, num_contr
         assert bk.sizes == [2 * num_pts * num_strokes, num_strokes, 4 * num_strokes, 9, 0, 1]
         topo.setflags(write=False)
         packed = PackedScene(topo, canvas_size, canvas_size, OutputType.color, False, torch.tensor([]))
-        packed.needs_xform_grad = False
+        packed.needs_xform_grad = packed.needs_filter_grad = False
         _STROKE_TOPO[key] = packed
     dev, dt = all_points.device, torch.float32
     tail = torch.cat([torch.eye(3, device=dev, dtype=dt).reshape(-1), torch.full((1,), 0.5, device=dev, dtype=dt)])

@@ -115,6 +115,7 @@ class PackedParams:
         packed = PackedScene(self.topo, self.canvas_width, self.canvas_height, output_type, use_prefiltering, eval_positions,
                              topo_key=self._topo_key())
         packed.needs_xform_grad = bool(self.transforms.requires_grad)
+        packed.needs_filter_grad = bool(self.filter_radius.requires_grad)
         packed.filter_radius = float(self.filter.radius)
         packed.halo_rows = max(1, int(np.ceil(packed.filter_radius)))
         return [packed, self.flat()]

@@ -121,6 +121,12 @@ def _get_native_scene(packed, device_index):
     return ns
 
 
+def backward_flags(packed):
+    """DVG_BWD_* flags of a backward call: gradients nobody asked for are not accumulated."""
+    n = _native()
+    return (0 if packed.needs_xform_grad else n.DVG_BWD_SKIP_XFORM_GRAD) | (0 if packed.needs_filter_grad else n.DVG_BWD_SKIP_FILTER_GRAD)
+
+
 class PackedScene:
     """First element of `scene_args`: everything about the scene that is not a float parameter."""
 
@@ -134,6 +140,7 @@ class PackedScene:
         self.eval_positions = eval_positions
         self.num_params = int(topo[scene_pack.H_NPARAMS])
         self.needs_xform_grad = True
+        self.needs_filter_grad = True
 
 
 def _cuda_device():
@@ -162,6 +169,8 @@ class RenderFunction(torch.autograd.Function):
         # d_shape_to_canvas is only worth accumulating when some transform tensor takes part in autograd (every
         # boundary sample adds to the 9 entries of its group's transform; groups usually share one constant eye(3))
         packed.needs_xform_grad = any(t.requires_grad for t in tensors[scene_pack.B_MAT3])
+        # likewise d_filter.radius (a 3x3-pixel gather per sample): only when the radius tensor takes part in autograd
+        packed.needs_filter_grad = any(t.requires_grad for t in tensors[scene_pack.B_FILTER])
         # rows of d_image a pixel-row shard needs from its neighbours (diffvg_b200/sharded.py)
         packed.filter_radius = float(filter.radius)
         packed.halo_rows = max(1, int(np.ceil(packed.filter_radius)))
@@ -305,7 +314,7 @@ class RenderFunction(torch.autograd.Function):
                 int(ctx.seed), 1 if ctx.packed.use_prefiltering else 0,
                 eval_dev.data_ptr() if eval_dev is not None else None, eval_dev.shape[0] if eval_dev is not None else 0,
                 d_params.data_ptr(), d_background.data_ptr() if d_background is not None else None, None,
-                0 if ctx.packed.needs_xform_grad else n.DVG_BWD_SKIP_XFORM_GRAD, stream))
+                backward_flags(ctx.packed), stream))
             if print_timing:
                 torch.cuda.synchronize(dev)
                 print('Backward pass, time: %.5f s' % (time.time() - start))

@@ -177,7 +177,7 @@ class ShardedRenderFunction(torch.autograd.Function):
                 ns.handle, bg.data_ptr() if bg is not None else None, grad_img.data_ptr(),
                 width, height, nsx, nsy, int(seed), 1 if ctx.packed.use_prefiltering else 0, rb, re,
                 d_params.data_ptr(), d_bg.data_ptr() if d_bg is not None else None,
-                0 if ctx.packed.needs_xform_grad else n.DVG_BWD_SKIP_XFORM_GRAD, stream))
+                rp.backward_flags(ctx.packed), stream))
             allreduce_gradients(d_params, ctx.group)
             if d_bg is not None:
                 allreduce_gradients(d_bg, ctx.group)

@@ -35,6 +35,7 @@ typedef enum DvgStatus {
 /* flags for dvg_render_backward */
 #define DVG_BWD_SKIP_XFORM_GRAD 1u   /* do not accumulate d(shape_to_canvas) (saves 9 scatters / boundary sample) */
 #define DVG_BWD_ACCUMULATE      2u   /* add into d_params instead of overwriting it                               */
+#define DVG_BWD_SKIP_FILTER_GRAD 4u   /* do not accumulate d(filter.radius) (a 3x3-pixel gather per sample at radius 0.5): its entry of d_params stays 0 */
 
 /* Version of this ABI; bumped on incompatible change. */
 int dvg_abi_version(void);

@@ -425,7 +425,7 @@ EXPORT int emul_stroke_hit_cubic(const float *pts8, const float *rad4, float x, 
 
 // The per-primitive split of the closest-point quintic (dvg_geom.cuh prim_quintic / quintic_of / quintic_intervals_of)
 // against cubic_quintic / quintic_intervals on the same inputs.  out[0]: pairs whose five normalised coefficients are not
-// bit-identical; out[1]: pairs whose split points differ (count or any float); out[2]: pairs whose verdict through the
+// bit-identical; out[1]: pairs whose split points inside [0, 1] differ (count or any float); out[2]: pairs whose verdict through the
 // kernel's bracket enumeration differs from stroke_hit_cubic's.
 EXPORT void emul_quintic_split_check(const float *pts8, const float *rad4, const float *xy, int n, long long *out) {
     const F2 p0 = mk2(pts8[0], pts8[1]), p1 = mk2(pts8[2], pts8[3]), p2 = mk2(pts8[4], pts8[5]), p3 = mk2(pts8[6], pts8[7]);
@@ -438,6 +438,12 @@ EXPORT void emul_quintic_split_check(const float *pts8, const float *rad4, const
         if (memcmp(&a, &b, sizeof a) != 0) out[0]++;
         float ia[4] = {0, 0, 0, 0}, ib[4] = {0, 0, 0, 0};
         const int na = quintic_intervals(a, ia), nb = quintic_intervals_of(k, b, ib);
+        // only split points inside [0, 1] matter (negative: skipped; above 1: the bracket ends at 1): the per-primitive form
+        // leaves roots far outside unpolished
+        for (int j = 0; j < 4; j++) {
+            if (ia[j] < 0.f) ia[j] = -1.f; else if (ia[j] >= 1.f) ia[j] = 1.f;
+            if (ib[j] < 0.f) ib[j] = -1.f; else if (ib[j] >= 1.f) ib[j] = 1.f;
+        }
         if (na != nb || memcmp(ia, ib, sizeof(float) * na) != 0) out[1]++;
         // the kernel's enumeration: brackets from the signs at the split points, answer = OR of the radius tests
         bool hit = dist_sq(p0, pt) < r.x * r.x || dist_sq(p3, pt) < r.w * r.w;

@@ -317,10 +317,11 @@ def test_pydiffvg_backward_reuses_forward_result_words_and_matches_oracle():
     cw, ch, shapes, groups = scenes.zoo()
     args = pydiffvg.RenderFunction.serialize_scene(cw, ch, shapes, groups)
     packed, params0 = args
-    assert packed.needs_xform_grad is False
+    assert packed.needs_xform_grad is False and packed.needs_filter_grad is False
     topo, params_np = util.pack((cw, ch, shapes, groups))
     target = torch.rand(96, 96, 4, generator=torch.Generator().manual_seed(11))
     for seed in (3, 4):
+        packed.needs_filter_grad = seed == 4      # likewise d_filter.radius: skipped unless the radius takes part in autograd
         params = params0.detach().clone().requires_grad_(True)
         img = pydiffvg.RenderFunction.apply(96, 96, 2, 2, seed, None, packed, params)
         loss = (img.cpu() - target).pow(2).mean()
@@ -336,6 +337,12 @@ def test_pydiffvg_backward_reuses_forward_result_words_and_matches_oracle():
             xo = int(topo[goff + gi * scene_pack.G_LEN + 9])
             assert not got[xo:xo + 9].any()
             rb[xo:xo + 9] = 0.0
+        ro = int(topo[scene_pack.H_FRAD_OFF])
+        if not packed.needs_filter_grad:
+            assert got[ro] == 0.0 and rb[ro] != 0.0
+            rb[ro] = 0.0
+        else:
+            assert got[ro] != 0.0
         grad_close(rb, got, topo=topo)
     # with a transform that requires a gradient nothing is skipped
     xf = torch.eye(3, requires_grad=True)

@@ -132,3 +132,18 @@ def test_c5_batched_stroke_scenes_vs_oracle():
         rb = oracle_check.render(topo, params, 64, 64, 2, 2, b, d_render_image=d_img)
         gb = util.gpu_render(topo, params, 64, 64, 2, 2, b, d_render_image=d_img)
         assert util.rel_l2(rb['d_params'], gb['d_params']) <= 1e-4
+
+
+def test_skip_filter_grad_flag_only_drops_the_radius_entry():
+    """DVG_BWD_SKIP_FILTER_GRAD (what pydiffvg passes when the filter radius takes no part in autograd): every other
+    gradient is unchanged, the radius entry stays 0; sampled and prefiltered paths."""
+    for pf in (False, True):
+        topo, params = util.pack(scenes.zoo_prefilter() if pf else scenes.zoo(), filter_type=1, filter_radius=1.5)
+        rng = np.random.RandomState(2)
+        d_img = (rng.rand(128, 128, 4).astype(np.float32) - 0.5)
+        full = util.gpu_render(topo, params, 128, 128, 2, 2, 4, d_render_image=d_img, use_prefiltering=pf)['d_params']
+        skip = util.gpu_render(topo, params, 128, 128, 2, 2, 4, d_render_image=d_img, use_prefiltering=pf, extra_flags=4)['d_params']
+        roff = int(topo[6])      # DVG_H_FILTER_RADIUS_OFF
+        assert full[roff] != 0.0 and skip[roff] == 0.0
+        keep = np.arange(full.shape[0]) != roff
+        assert util.rel_l2(full[keep], skip[keep]) <= 2e-5

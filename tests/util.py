@@ -26,7 +26,7 @@ def image_report(ref, got, spp):
 
 def gpu_render(topo, params, width, height, nsx, nsy, seed, background=None, d_render_image=None,
                skip_xform_grad=False, use_prefiltering=False, want_image=True, want_sdf=False, eval_positions=None,
-               d_render_sdf=None, want_d_translation=False):
+               d_render_sdf=None, want_d_translation=False, extra_flags=0):
     """Drive the product C ABI directly (ctypes) with device buffers managed through torch.  Same
     keyword surface as oracle/ref_oracle.render."""
     import ctypes
@@ -62,7 +62,7 @@ def gpu_render(topo, params, width, height, nsx, nsy, seed, background=None, d_r
             dtr = torch.empty(height, width, 2, device=dev) if want_d_translation else None
             n.check(n.lib.dvg_render_backward(h, ptr(bg), ptr(dimg), ptr(dsdf), width, height, nsx, nsy, int(seed), pf,
                                               ptr(ep), n_eval, dpar.data_ptr(), ptr(dbg), ptr(dtr),
-                                              1 if skip_xform_grad else 0, stream))
+                                              (1 if skip_xform_grad else 0) | extra_flags, stream))
             out['d_params'] = dpar.cpu().numpy()
             out['d_background'] = dbg.cpu().numpy() if dbg is not None else None
             out['d_translation'] = dtr.cpu().numpy() if dtr is not None else None

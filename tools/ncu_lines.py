@@ -64,6 +64,9 @@ def main():
         for k, v in mangled.items():
             if k in norm:
                 key = v
+        m2 = re.search(r'(k_\w+)<\(?(?:bool)?\)?([01])>', name)
+        if key is None and m2:      # template<bool>: the mangled name carries ILb0E / ILb1E
+            key = '%sILb%sE' % (m2.group(1), m2.group(2))
         sass = [s for s in sass_lines(key or ksub)]
         if len(sass) != len(data):
             print('warning: %d SASS rows in report vs %d in library for %s' % (len(data), len(sass), name[:60]))
