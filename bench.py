@@ -54,8 +54,7 @@ EVALS = {'fwd': 1.0, 'interior': 1.0, 'edge': 1.918}   # colour evaluations per 
 KERNEL_MODEL = {
     'k_wave_classify_px': (115.0, 0.0, ('fwd',)),
     'k_wave_classify_edge': (115.0, 0.0, ('edge',)),
-    'k_wave_stroke_setup': (542.0, 997.0, ('fwd', 'edge')),
-    'k_wave_stroke_newton': (350.0, 1277.0, ('fwd', 'edge')),     # both instantiations (ascending / descending brackets) together
+    'k_wave_stroke_solve': (542.0 + 350.0, 997.0 + 1277.0, ('fwd', 'edge')),   # E4 + E5 (set-up, bracket evaluations) and E6 + E7 (Newton, accepted roots)
     'k_wave_composite_px<false>': (63.0, 0.0, ('fwd',)),
     'k_wave_composite_px<true>': (63.0, 0.0, ('interior',)),
     'k_wave_composite_edge': (63.0, 0.0, ('edge',)),
@@ -429,7 +428,7 @@ def main():
         n.profile_enable(False)
         kernels = {}
         for k, (c, ms) in rep.items():
-            k = 'k_wave_stroke_newton' if k.startswith('k_wave_stroke_newton') else k
+            k = k[:-len('<false>')] if k.startswith('k_wave_classify') and k.endswith('<false>') else k   # (the <true> forms are the overflow retries)
             e = kernels.setdefault(k, {'launches': 0, 'ms_per_step': 0.0})
             e['launches'] += c
             e['ms_per_step'] += ms / args.steps

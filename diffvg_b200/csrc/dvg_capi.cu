@@ -106,6 +106,7 @@ struct DvgScene {
     int32_t *h_counts = nullptr;         // pinned [2][4]: the wave counters of the last pixel / boundary pass (pair-queue feedback)
     cudaEvent_t ev_counts[2] = {nullptr, nullptr};
     bool counts_pending[2] = {false, false};
+    cudaStream_t counts_stream[2] = {nullptr, nullptr};   // where each pending copy was queued
     int64_t want_s = 0, want_f = 0;      // most pairs any pass of this scene asked for so far
     bool params_set = false;
     bool checked = false;
@@ -300,6 +301,8 @@ int finish_build(DvgScene *s, cudaStream_t st) {
     return parse_build_flags(s);
 }
 
+void wave_feedback_poll(DvgScene *s, cudaStream_t synced = nullptr, bool have_synced = false);   // (pair-queue sizing, below)
+
 constexpr int64_t kSmallBins = 1 << 20;    // tiles x primitives below which bins are sized for the worst case
 constexpr int64_t kSmallPairs = 1 << 21;   // worst-case exact tests of a pass below which the pair queues are, too
 
@@ -359,6 +362,7 @@ int ensure_bins(DvgScene *s, int width, int height, int spp, int pf, cudaStream_
         CK(cudaMemcpyAsync(s->h_pinned + 4, s->d_tile_choff.as<int>() + ntiles, 4, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(s->h_pinned + 5, s->d_wave_max.p, 4, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));   // the one synchronisation of an iteration
+        wave_feedback_poll(s, st, true);
         total = s->h_pinned[3];
         s->total_chunks = s->h_pinned[4];
         s->max_nch = s->h_pinned[5];
@@ -397,9 +401,13 @@ int ensure_weight(DvgScene *s, const SceneView &sc, RenderArgs &ra, int r0, int 
 // was too small.  A pass that still overflows (the first one of a scene; a sudden change of the geometry) is followed by
 // a retry kernel that answers every pair in place and rewrites the result words (dvg_wave.cu wave_classify<true>):
 // slower, same results; when nothing overflowed that kernel exits at once.
-void wave_feedback_poll(DvgScene *s) {
+// `synced`: a stream the caller has just synchronised (copies queued on it have landed whatever the event query says:
+// under a profiler that serialises launches the query was seen to stay "not ready"), or null.
+void wave_feedback_poll(DvgScene *s, cudaStream_t synced, bool have_synced) {
     for (int slot = 0; slot < 2; slot++) {
-        if (!s->counts_pending[slot] || cudaEventQuery(s->ev_counts[slot]) != cudaSuccess) continue;
+        if (!s->counts_pending[slot]) continue;
+        const bool landed = (have_synced && s->counts_stream[slot] == synced) || cudaEventQuery(s->ev_counts[slot]) == cudaSuccess;
+        if (!landed) continue;
         s->counts_pending[slot] = false;
         const int32_t *c = s->h_counts + 4 * slot;
         // a counter that wrapped negative asked for more than 2^31 pairs: keep the in-place path for the surplus
@@ -465,6 +473,7 @@ int wave_classify_and_solve(DvgScene *s, const SceneView &sc, WaveView &wv, int 
         CK(cudaMemcpyAsync(s->h_counts + 4 * slot, wv.counters, sizeof(int) * 4, cudaMemcpyDeviceToHost, st));
         CK(cudaEventRecord(s->ev_counts[slot], st));
         s->counts_pending[slot] = true;
+        s->counts_stream[slot] = st;
     }
     return DVG_OK;
 }
