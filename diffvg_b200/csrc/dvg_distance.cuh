@@ -548,8 +548,9 @@ DVG_D void prefilter_backward(const SceneView &sc, const PrefilterTracer<true> &
             d_alpha_i *= w;
             const F4 dc = mk4(dci.x, dci.y, dci.z, d_alpha_i);
             if (ctype == 0) add4(sk, coff, dc);
-            else if (!is_stroke) d_eval_gradient(ctype, sc.params + coff, cstops, tr.cpt, dc, sk, coff, d_translation);
-            // Q4: gradient STROKE colours have no gradient storage in the reference
+            // Q4: gradient STROKE colours have no gradient storage in the reference (it faults there: scene.cpp:866-889);
+            // accumulated like a fill's
+            else d_eval_gradient(ctype, sc.params + coff, cstops, tr.cpt, dc, sk, coff, d_translation);
             if (is_stroke) {
                 const float d_apw = d_smoothstep(apw, d_w);
                 const float d_amw = -d_smoothstep(amw, d_w);

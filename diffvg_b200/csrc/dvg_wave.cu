@@ -600,7 +600,9 @@ __global__ void __launch_bounds__(WB, DVG_WB_MIN + 1) k_wave_composite_px(SceneV
                 dcr = dcr * (1 - fc.w); dcg = dcg * (1 - fc.w); dcb = dcb * (1 - fc.w);
                 dca = d_prev_alpha;
                 if (ctype == 0) { sk.add(coff + 0, dc.x); sk.add(coff + 1, dc.y); sk.add(coff + 2, dc.z); sk.add(coff + 3, dc.w); }
-                else if (!(key & 1)) d_eval_gradient(ctype, sc.params + coff, cstops, cpt, dc, sk, coff,
+                // (Q4: the reference has no storage for the gradient of a gradient-typed STROKE colour -- scene.cpp:866-889
+                // never assigns d_shape_groups[g].stroke_color -- and faults there; the gradient is accumulated like a fill's)
+                else d_eval_gradient(ctype, sc.params + coff, cstops, cpt, dc, sk, coff,
                                                      ra.d_translation ? ra.d_translation + 2 * (y * ra.width + x) : nullptr);
             }
             if (active && had_frags && bg_px && ra.d_background) {  // diffvg.cpp:699-704

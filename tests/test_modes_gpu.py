@@ -147,3 +147,77 @@ def test_skip_filter_grad_flag_only_drops_the_radius_entry():
         assert full[roff] != 0.0 and skip[roff] == 0.0
         keep = np.arange(full.shape[0]) != roff
         assert util.rel_l2(full[keep], skip[keep]) <= 2e-5
+
+
+def test_gradient_stroke_colour_gradients_match_finite_differences():
+    """Q4: the reference has no defined behaviour for the gradient of a Linear/RadialGradient STROKE colour (scene.cpp:866-889
+    never assigns d_shape_groups[g].stroke_color and the backward pass faults).  Here it is accumulated like a fill's; the
+    colour parameters move the image smoothly, so central finite differences are the check (sampled and prefiltered)."""
+    from diffvg_b200 import pydiffvg
+    pydiffvg.set_use_gpu(True)
+    lin = dict(begin=torch.tensor([10.0, 12.0]), end=torch.tensor([52.0, 47.0]), offsets=torch.tensor([0.1, 0.5, 0.95]),
+               stop_colors=torch.tensor([[0.9, 0.1, 0.2, 0.9], [0.2, 0.8, 0.3, 0.6], [0.1, 0.2, 0.9, 1.0]]))
+    rad = dict(center=torch.tensor([40.0, 24.0]), radius=torch.tensor([20.0, 14.0]), offsets=torch.tensor([0.2, 0.8]),
+               stop_colors=torch.tensor([[0.8, 0.7, 0.1, 1.0], [0.1, 0.5, 0.6, 0.5]]))
+    leaves = {('lin', k): v.clone().requires_grad_(True) for k, v in lin.items()}
+    leaves.update({('rad', k): v.clone().requires_grad_(True) for k, v in rad.items()})
+
+    def scene(vals):
+        shapes = [pydiffvg.Path(num_control_points=torch.tensor([2, 0]), points=torch.tensor([[8.0, 50.0], [20.0, 5.0], [40.0, 60.0], [55.0, 12.0], [58.0, 40.0]]),
+                                is_closed=False, stroke_width=torch.tensor(5.0)),
+                  pydiffvg.Circle(radius=torch.tensor(13.0), center=torch.tensor([40.0, 26.0]), stroke_width=torch.tensor(4.0))]
+        groups = [pydiffvg.ShapeGroup(torch.tensor([0]), fill_color=None, stroke_color=pydiffvg.LinearGradient(
+                      vals[('lin', 'begin')], vals[('lin', 'end')], vals[('lin', 'offsets')], vals[('lin', 'stop_colors')])),
+                  pydiffvg.ShapeGroup(torch.tensor([1]), fill_color=torch.tensor([0.3, 0.3, 0.3, 0.4]), stroke_color=pydiffvg.RadialGradient(
+                      vals[('rad', 'center')], vals[('rad', 'radius')], vals[('rad', 'offsets')], vals[('rad', 'stop_colors')]))]
+        return shapes, groups
+
+    wt = torch.rand(64, 64, 4, generator=torch.Generator().manual_seed(9)).double()
+    for pf in (False, True):
+        def loss_of(vals):
+            shapes, groups = scene(vals)
+            args = pydiffvg.RenderFunction.serialize_scene(64, 64, shapes, groups, use_prefiltering=pf)
+            img = pydiffvg.RenderFunction.apply(64, 64, 2, 2, 5, None, *args)
+            return (img.cpu().double() * wt).sum()
+        for t in leaves.values():
+            t.grad = None
+        loss_of(leaves).backward()
+        checked = 0
+        for key, t in leaves.items():
+            flat = t.detach().clone().reshape(-1)
+            g = t.grad.reshape(-1)
+            for i in range(flat.numel()):
+                eps = 0.02 if key[1] in ('offsets', 'stop_colors') else 0.25
+                vals = {k: v.detach() for k, v in leaves.items()}
+                hi, lo = flat.clone(), flat.clone()
+                hi[i] += eps; lo[i] -= eps
+                vals[key] = hi.reshape(t.shape); lp = float(loss_of(vals))
+                vals[key] = lo.reshape(t.shape); lm = float(loss_of(vals))
+                fd = (lp - lm) / (2 * eps)
+                assert abs(fd - float(g[i])) <= 0.03 * abs(fd) + 0.02, (pf, key, i, fd, float(g[i]))
+                checked += 1 if abs(fd) > 0.05 else 0
+        assert checked >= 15
+
+
+def test_fast_stroke_accept_mode_differs_by_whole_samples_only():
+    """dvg_set_fast_stroke_accept(1) (opt-in, DESIGN 'arithmetic contract'): samples the polyline bracket proves inside a
+    curved stroke skip the reference's closest-point solve.  Geometrically right; the reference's solver misses a few
+    near-tangent cases (Q21), so a handful of pixels may differ from the exact mode -- each by whole samples' weights,
+    and only towards MORE coverage -- and the gradients stay within the usual tolerance."""
+    from diffvg_b200 import _native as n
+    topo, params = util.pack(scenes.painterly(512, 256))
+    exact = util.gpu_render(topo, params, 256, 256, 4, 4, 0)['image']
+    d_img = (np.random.RandomState(4).rand(256, 256, 4).astype(np.float32) - 0.5)
+    g_exact = util.gpu_render(topo, params, 256, 256, 4, 4, 0, d_render_image=d_img)['d_params']
+    assert n.lib.dvg_set_fast_stroke_accept(1) == 0
+    try:
+        fast = util.gpu_render(topo, params, 256, 256, 4, 4, 0)['image']
+        g_fast = util.gpu_render(topo, params, 256, 256, 4, 4, 0, d_render_image=d_img)['d_params']
+    finally:
+        n.lib.dvg_set_fast_stroke_accept(0)
+    diff = np.abs(fast - exact).max(axis=2)
+    assert (diff > 1e-6).sum() <= 64                   # a handful of pixels
+    assert diff.max() <= 3.0 / 16 + 1e-5              # a few samples of 16 at most
+    assert util.rel_l2(g_exact, g_fast) <= 1e-3
+    again = util.gpu_render(topo, params, 256, 256, 4, 4, 0)['image']
+    assert np.array_equal(again, exact)                # the switch is off again
