@@ -41,6 +41,8 @@ lib.dvg_render_forward_batch.argtypes = [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp
 lib.dvg_render_forward_batch.restype = _i
 lib.dvg_render_backward_batch.argtypes = [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, ctypes.c_uint32, _vp]
 lib.dvg_render_backward_batch.restype = _i
+lib.dvg_scene_row_costs.argtypes = [_vp, _i, _i, _i, _i, _i, _vp, _i, ctypes.POINTER(_i), _vp]
+lib.dvg_scene_row_costs.restype = _i
 lib.dvg_scene_destroy.argtypes = [_vp]
 lib.dvg_scene_destroy.restype = _i
 lib.dvg_scene_dump.argtypes = [_vp, _i, _i, _vp, _i64, _vp]

@@ -239,6 +239,19 @@ __global__ void __launch_bounds__(1024) k_exclusive_scan(const int *in, int *out
     if (t == 0) out[n] = s_carry;
 }
 
+// Candidate count of every tile ROW (one warp per row): the cost profile a row partition is balanced with.
+__global__ void k_tile_row_costs(const int *offsets, int tiles_x, int tiles_y, float *out) {
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (row >= tiles_y) return;
+    int sum = 0;
+    for (int t = lane; t < tiles_x; t += 32) sum += offsets[row * tiles_x + t + 1] - offsets[row * tiles_x + t];
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) out[row] = (float)sum;
+}
+void launch_tile_row_costs(const int *offsets, int tiles_x, int tiles_y, float *out, cudaStream_t st) {
+    DVG_LAUNCH(k_tile_row_costs, dim3((tiles_y * 32 + 127) / 128), dim3(128), 0, st, offsets, tiles_x, tiles_y, out);
+}
+
 void launch_build(const BuildView &bv, cudaStream_t st) {
     const int B = 128;
     cudaMemsetAsync(bv.error_flag, 0, sizeof(int), st);
@@ -259,15 +272,110 @@ void launch_bin_count(const BuildView &bv, const BinBuild &bb, cudaStream_t st) 
     const int B = 128;  // 4 warps = 4 tiles per block
     if (nbin < ntiles) cudaMemsetAsync(bb.counts, 0, sizeof(int) * ntiles, st);
     if (nbin > 0) DVG_LAUNCH(k_bin<0>, dim3((nbin * 32 + B - 1) / B), dim3(B), 0, st, bv, bb);
-    DVG_LAUNCH(k_exclusive_scan, dim3(1), dim3(1024), 0, st, bb.counts, bb.offsets, ntiles);
+    launch_scan(bb.counts, bb.offsets, ntiles, bb.scan_ws, st);
 }
 void launch_bin_fill(const BuildView &bv, const BinBuild &bb, cudaStream_t st) {
     const int nbin = bb.batch > 1 ? bb.tiles_x * bb.tiles_y * bb.batch : (bb.tile_row1 - bb.tile_row0) * bb.tiles_x;
     const int B = 128;
     if (nbin > 0) DVG_LAUNCH(k_bin<1>, dim3((nbin * 32 + B - 1) / B), dim3(B), 0, st, bv, bb);
 }
-void launch_scan(const int *in, int *out, int n, cudaStream_t st) {
-    DVG_LAUNCH(k_exclusive_scan, dim3(1), dim3(1024), 0, st, in, out, n);
+// Multi-block form: block b scans its 4096 elements and parks its total in ws[b]; the LAST block to finish (ticket in
+// ws[DVG_SCAN_WS_BLOCKS]) turns the totals into exclusive block offsets and writes the grand total to out[n]; a second
+// kernel adds the block offsets.  Two short launches instead of one block walking 64 chunks at 2048^2 (33 -> ~8 us per
+// scan; five scans per iteration, all of it work every rank of a row-sharded render repeats).
+__global__ void __launch_bounds__(1024) k_scan_blocks(const int *in, int *out, int n, int *ws) {
+    __shared__ int s_warp[32];
+    __shared__ int s_last;
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const int i = blockIdx.x * 4096 + 4 * t;
+    int v0 = 0, v1 = 0, v2 = 0, v3 = 0;
+    if (i + 3 < n && ((reinterpret_cast<uintptr_t>(in) & 15) == 0)) {
+        const int4 q = *reinterpret_cast<const int4 *>(in + i);
+        v0 = q.x; v1 = q.y; v2 = q.z; v3 = q.w;
+    } else {
+        if (i < n) v0 = in[i];
+        if (i + 1 < n) v1 = in[i + 1];
+        if (i + 2 < n) v2 = in[i + 2];
+        if (i + 3 < n) v3 = in[i + 3];
+    }
+    const int mine = v0 + v1 + v2 + v3;
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += u;
+    }
+    if (lane == 31) s_warp[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+        int x = s_warp[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += u;
+        }
+        s_warp[lane] = x;   // inclusive over warps
+    }
+    __syncthreads();
+    int run = (w ? s_warp[w - 1] : 0) + incl - mine;
+    if (i < n) out[i] = run;
+    run += v0;
+    if (i + 1 < n) out[i + 1] = run;
+    run += v1;
+    if (i + 2 < n) out[i + 2] = run;
+    run += v2;
+    if (i + 3 < n) out[i + 3] = run;
+    if (t == 1023) {
+        ws[blockIdx.x] = s_warp[31];
+        __threadfence();
+        s_last = atomicAdd(&ws[DVG_SCAN_WS_BLOCKS], 1) == (int)gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    // last block: exclusive scan of the block totals (<= 1024 of them), in place
+    __threadfence();
+    const int nb = gridDim.x;
+    const int mine_b = t < nb ? *(volatile int *)&ws[t] : 0;
+    int inc_b = mine_b;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, inc_b, o);
+        if (lane >= o) inc_b += u;
+    }
+    __syncthreads();
+    if (lane == 31) s_warp[w] = inc_b;
+    __syncthreads();
+    if (w == 0) {
+        int x = s_warp[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += u;
+        }
+        s_warp[lane] = x;
+    }
+    __syncthreads();
+    const int excl_b = (w ? s_warp[w - 1] : 0) + inc_b - mine_b;
+    if (t < nb) ws[t] = excl_b;
+    if (t == nb - 1) out[n] = excl_b + mine_b;
+    if (t == 0) ws[DVG_SCAN_WS_BLOCKS] = 0;   // the ticket, for the next scan
+}
+__global__ void __launch_bounds__(1024) k_scan_add(int *out, int n, const int *ws) {
+    const int add = ws[blockIdx.x + 1];
+    const int i = (blockIdx.x + 1) * 4096 + 4 * threadIdx.x;
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+        if (i + k < n) out[i + k] += add;
+}
+
+void launch_scan(const int *in, int *out, int n, int *ws, cudaStream_t st) {
+    const int nb = (n + 4095) / 4096;
+    if (!ws || nb > DVG_SCAN_WS_BLOCKS || nb <= 4) {   // (up to 16 k elements the single block is as fast as two launches)
+        DVG_LAUNCH(k_exclusive_scan, dim3(1), dim3(1024), 0, st, in, out, n);
+        return;
+    }
+    DVG_LAUNCH(k_scan_blocks, dim3(nb), dim3(1024), 0, st, in, out, n, ws);
+    if (nb > 1) DVG_LAUNCH(k_scan_add, dim3(nb - 1), dim3(1024), 0, st, out, n, ws);
 }
 
 }  // namespace dvg

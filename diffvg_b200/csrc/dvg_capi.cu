@@ -72,6 +72,7 @@ struct DvgScene {
     // the seed in the reuse keys of the weight image and of the forward pass's result words.
     int batch = 1;
     DevBuf d_seeds;
+    DevBuf d_scan_ws;   // launch_scan workspace (zeroed once; every scan leaves it zeroed)
     std::vector<uint64_t> seeds_host;
     uint64_t seeds_version = 0;
     // host topology maps
@@ -167,7 +168,7 @@ struct DvgScene {
                          &d_keys, &d_tile_counts, &d_tile_offsets, &d_tile_fill, &d_blk_counts, &d_blk_offsets, &d_sorted,
                          &d_wave_hit, &d_wave_wind, &d_wave_pairs_s, &d_wave_pairs_f, &d_wave_counters, &d_tile_nch, &d_tile_choff,
                          &d_edge_chunks, &d_edge_choff, &d_wave_max, &d_bsamples, &d_bsamples_raw, &d_item_tile, &d_grad_rep,
-                         &d_bvh_path, &d_bvh_group, &d_bvh_scene, &d_bvh_keys, &d_seeds};
+                         &d_bvh_path, &d_bvh_group, &d_bvh_scene, &d_bvh_keys, &d_seeds, &d_scan_ws};
         for (DevBuf *b : all) b->release();
         if (h_pinned) cudaFreeHost(h_pinned);
         h_pinned = nullptr;
@@ -320,6 +321,7 @@ int ensure_bins(DvgScene *s, int width, int height, int spp, int pf, cudaStream_
     BinBuild bb;
     bb.width = width; bb.height = height; bb.tile_w = tw; bb.tile_h = th; bb.prefilter = pf;
     bb.batch = s->batch;
+    bb.scan_ws = s->d_scan_ws.as<int>();
     bb.flat = s->num_prims <= 4 * s->num_groups ? 1 : 0;
     bb.tile_row0 = r0; bb.tile_row1 = r1;
     bb.tiles_x = (width + tw - 1) / tw; bb.tiles_y = (height + th - 1) / th;
@@ -344,7 +346,7 @@ int ensure_bins(DvgScene *s, int width, int height, int spp, int pf, cudaStream_
     CK(s->d_tile_nch.ensure(sizeof(int) * ntiles));
     CK(s->d_tile_choff.ensure(sizeof(int) * (ntiles + 1)));
     CK(s->d_wave_max.ensure(sizeof(int)));
-    launch_wave_tile_chunks(bb.offsets, s->d_tile_nch.as<int>(), s->d_tile_choff.as<int>(), s->d_wave_max.as<int>(), ntiles, st);
+    launch_wave_tile_chunks(bb.offsets, s->d_tile_nch.as<int>(), s->d_tile_choff.as<int>(), s->d_wave_max.as<int>(), ntiles, bb.scan_ws, st);
     int total;
     const int64_t nbin = s->batch > 1 ? ntiles : (int64_t)(r1 - r0) * bb.tiles_x;
     if (nbin * s->num_prims <= kSmallBins) {
@@ -638,6 +640,8 @@ int dvg_scene_create_batch(const int32_t *topo, int64_t topo_len, int device, in
     ens(s->d_p01, 16 * npr); ens(s->d_p23, 16 * npr); ens(s->d_rad, 16 * npr); ens(s->d_box, 16 * npr);
     ens(s->d_thick, 4 * npr); ens(s->d_meta, sizeof(PrimMeta) * npr); ens(s->d_cbox, 16 * npr); ens(s->d_cbox_pf, 16 * npr); ens(s->d_cap, 16 * DVG_CAP_F4 * npr); ens(s->d_quint, sizeof(PrimQuintic) * npr);
     ens(s->d_shape_cdf, 4 * ni); ens(s->d_shape_pmf, 4 * ni); ens(s->d_flags, 16);
+    ens(s->d_scan_ws, sizeof(int) * (DVG_SCAN_WS_BLOCKS + 1));
+    if (!rc && cudaMemset(s->d_scan_ws.p, 0, sizeof(int) * (DVG_SCAN_WS_BLOCKS + 1)) != cudaSuccess) rc = fail(DVG_ERR_CUDA, "cudaMemset failed");
     if (!rc && cudaMallocHost((void **)&s->h_pinned, 64) != cudaSuccess) rc = fail(DVG_ERR_CUDA, "cudaMallocHost failed");
     if (!rc && cudaMallocHost((void **)&s->h_counts, 32) != cudaSuccess) rc = fail(DVG_ERR_CUDA, "cudaMallocHost failed");
     for (int k = 0; k < 2 && !rc; k++)
@@ -850,6 +854,7 @@ static int render_backward_impl(DvgScene *s, const float *background, const floa
             for (int64_t done = 0; done < all_count; done += per_pass) {
                 BoundaryWork bw;
                 bw.samples = nullptr; bw.samples_unsorted = nullptr; bw.item_tile = nullptr;
+                bw.scan_ws = s->d_scan_ws.as<int>();
                 bw.sample_begin = (int)(all_begin + done);
                 bw.num_samples = (int)std::min<int64_t>(per_pass, all_count - done);
                 CK(s->d_keys.ensure(sizeof(int) * (size_t)bw.num_samples));
@@ -909,6 +914,27 @@ int dvg_render_backward_batch(DvgScene *s, const float *background, const float 
                                                         nullptr, 0, 0, height, d_params, d_background, nullptr, flags, stream);
     return render_backward_impl(s, background, d_render_image, nullptr, width, height, nsx, nsy, 0, 0, nullptr, 0, 0, height,
                                 d_params, d_background, nullptr, flags, stream, seeds);
+}
+
+int dvg_scene_row_costs(DvgScene *s, int width, int height, int nsx, int nsy, int use_prefiltering, float *out_host, int cap,
+                        int *tile_h_out, void *stream) {
+    int rc = check_render_args(s, width, height, nsx, nsy);
+    if (rc) return rc;
+    if (!out_host || !tile_h_out) return fail(DVG_ERR_INVALID, "null argument");
+    if (s->batch > 1) return fail(DVG_ERR_UNSUPPORTED, "batch scenes are split by scene, not by rows");
+    DeviceGuard guard(s->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    rc = ensure_bins(s, width, height, nsx * nsy, use_prefiltering ? 1 : 0, st, 0, height);   // whole image
+    if (rc) return rc;
+    const BinView bins = s->bin_view();
+    if (cap < bins.tiles_y) return fail(DVG_ERR_INVALID, "row-cost buffer too small");
+    CK(s->d_item_tile.ensure(sizeof(float) * (size_t)bins.tiles_y));   // (scratch: rebound by the next boundary pass)
+    launch_tile_row_costs(bins.offsets, bins.tiles_x, bins.tiles_y, s->d_item_tile.as<float>(), st);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out_host, s->d_item_tile.p, sizeof(float) * (size_t)bins.tiles_y, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    *tile_h_out = bins.tile_h;
+    return bins.tiles_y > 0 ? DVG_OK : fail(DVG_ERR_INVALID, "empty image");
 }
 
 int dvg_debug_set_boundary_dump(float *device_buf) { g_debug_out = device_buf; return DVG_OK; }

@@ -39,6 +39,7 @@ struct BinBuild {
     int super, stiles_x, stiles_y;
     int *s_counts, *s_items;
     int flat;       // 1: test every primitive (few primitives per group); 0: groups first, then their primitives
+    int *scan_ws;  // launch_scan workspace (DVG_SCAN_WS_BLOCKS + 1 ints, zeroed at allocation), or null
     int *counts;   // [tiles]
     int *offsets;  // [tiles+1]
     int *items;    // [capacity]
@@ -58,6 +59,7 @@ struct BoundaryWork {
     BoundarySample *samples;           // [num_samples] in TILE order (wavefront path: made once, sorted, read twice), or null
     BoundarySample *samples_unsorted;  // [num_samples] by index - sample_begin: staging of the counting sort, or null
     int *item_tile;           // [max_blocks] tile of every boundary item, or null
+    int *scan_ws;             // launch_scan workspace, or null
 };
 
 // Wavefront passes (dvg_wave.cu): queues and result words in global memory.
@@ -93,7 +95,9 @@ void launch_build(const BuildView &bv, cudaStream_t st);
 void launch_bin_coarse(const BuildView &bv, const BinBuild &bb, cudaStream_t st);
 void launch_bin_count(const BuildView &bv, const BinBuild &bb, cudaStream_t st);
 void launch_bin_fill(const BuildView &bv, const BinBuild &bb, cudaStream_t st);
-void launch_scan(const int *in, int *out, int n, cudaStream_t st);
+#define DVG_SCAN_WS_BLOCKS 1024   // launch_scan workspace: this many block totals + one ticket (ints, zeroed once)
+void launch_scan(const int *in, int *out, int n, int *ws, cudaStream_t st);
+void launch_tile_row_costs(const int *offsets, int tiles_x, int tiles_y, float *out, cudaStream_t st);
 
 void launch_weight(const SceneView &sc, const RenderArgs &ra, int row_begin, int row_end, cudaStream_t st);
 void launch_render_pf_forward(const SceneView &sc, const BinView &bins, const RenderArgs &ra, cudaStream_t st);
@@ -101,7 +105,7 @@ void launch_render_pf_backward(const SceneView &sc, const BinView &bins, const R
 void launch_sdf(const SceneView &sc, const RenderArgs &ra, const SdfArgs &sa, bool backward, cudaStream_t st);
 void launch_boundary_sort(const SceneView &sc, const BinView &bins, const RenderArgs &ra, const BoundaryWork &bw, cudaStream_t st);
 
-void launch_wave_tile_chunks(const int *bin_offsets, int *nch, int *choff, int *max_nch, int ntiles, cudaStream_t st);
+void launch_wave_tile_chunks(const int *bin_offsets, int *nch, int *choff, int *max_nch, int ntiles, int *scan_ws, cudaStream_t st);
 int wave_pixel_items(const BinView &bins, const RenderArgs &ra);
 void launch_wave_reduce_grads(const RenderArgs &ra, cudaStream_t st);
 int wave_items_per_tile(const BinView &bins, const RenderArgs &ra);

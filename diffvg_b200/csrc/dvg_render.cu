@@ -114,7 +114,7 @@ void launch_boundary_sort(const SceneView &sc, const BinView &bins, const Render
     cudaMemsetAsync(bw.tile_counts, 0, sizeof(int) * ntiles, st);
     cudaMemsetAsync(bw.tile_fill, 0, sizeof(int) * ntiles, st);
     DVG_LAUNCH(k_boundary_keys, dim3(std::min((bw.num_samples + KEYS_B - 1) / KEYS_B, g_num_sms * 8)), dim3(KEYS_B), 0, st, sc, bins, ra, bw);
-    launch_scan(bw.tile_counts, bw.tile_offsets, ntiles, st);
+    launch_scan(bw.tile_counts, bw.tile_offsets, ntiles, bw.scan_ws, st);
     DVG_LAUNCH(k_boundary_scatter, dim3((bw.num_samples + 255) / 256), dim3(256), 0, st, bw);
 }
 

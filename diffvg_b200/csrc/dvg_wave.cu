@@ -737,10 +737,10 @@ __global__ void k_wave_edge_items(BoundaryWork bw, int ntiles) {
     for (int i = b; i < e; i++) bw.item_tile[i] = t;
 }
 
-void launch_wave_tile_chunks(const int *bin_offsets, int *nch, int *choff, int *max_nch, int ntiles, cudaStream_t st) {
+void launch_wave_tile_chunks(const int *bin_offsets, int *nch, int *choff, int *max_nch, int ntiles, int *scan_ws, cudaStream_t st) {
     cudaMemsetAsync(max_nch, 0, sizeof(int), st);
     DVG_LAUNCH(k_wave_tile_chunks, dim3((ntiles + 255) / 256), dim3(256), 0, st, bin_offsets, nch, max_nch, ntiles);
-    launch_scan(nch, choff, ntiles, st);
+    launch_scan(nch, choff, ntiles, scan_ws, st);
 }
 
 void launch_wave_reduce_grads(const RenderArgs &ra, cudaStream_t st) {
@@ -799,8 +799,8 @@ void launch_wave_boundary_sort(const SceneView &sc, const BinView &bins, const R
     const int ntiles = bin_total_tiles(bins);
     launch_boundary_sort(sc, bins, ra, bw, st);
     DVG_LAUNCH(k_wave_edge_counts, dim3((ntiles + 255) / 256), dim3(256), 0, st, bw, wv.tile_choff, edge_chunks, ntiles);
-    launch_scan(bw.blk_counts, bw.blk_offsets, ntiles, st);
-    launch_scan(edge_chunks, wv.edge_choff, ntiles, st);
+    launch_scan(bw.blk_counts, bw.blk_offsets, ntiles, bw.scan_ws, st);
+    launch_scan(edge_chunks, wv.edge_choff, ntiles, bw.scan_ws, st);
     DVG_LAUNCH(k_wave_edge_items, dim3((ntiles + 255) / 256), dim3(256), 0, st, bw, ntiles);
 }
 

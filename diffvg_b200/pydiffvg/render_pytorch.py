@@ -98,6 +98,7 @@ def clear_cache():
     gradient replicas -- hundreds of MB at large render sizes) and the memoised scene packings."""
     _scene_cache.clear()
     del scene_pack._MEMO[:]
+    del _TOPO_KEYS[:]
 
 
 def set_scene_cache_size(n):
@@ -127,12 +128,26 @@ def backward_flags(packed):
     return (0 if packed.needs_xform_grad else n.DVG_BWD_SKIP_XFORM_GRAD) | (0 if packed.needs_filter_grad else n.DVG_BWD_SKIP_FILTER_GRAD)
 
 
+_TOPO_KEYS = []   # (topology array, its bytes): scene_pack hands back the SAME read-only array while the structure is unchanged
+
+
+def _topo_key(topo):
+    for t, k in _TOPO_KEYS:
+        if t is topo:
+            return k
+    key = topo.tobytes()
+    if not topo.flags.writeable:      # only memoised (frozen) arrays can be trusted to keep their contents
+        _TOPO_KEYS.insert(0, (topo, key))
+        del _TOPO_KEYS[8:]
+    return key
+
+
 class PackedScene:
     """First element of `scene_args`: everything about the scene that is not a float parameter."""
 
     def __init__(self, topo, canvas_width, canvas_height, output_type, use_prefiltering, eval_positions, topo_key=None):
         self.topo = topo
-        self.topo_key = topo.tobytes() if topo_key is None else topo_key
+        self.topo_key = _topo_key(topo) if topo_key is None else topo_key
         self.canvas_width = canvas_width
         self.canvas_height = canvas_height
         self.output_type = output_type

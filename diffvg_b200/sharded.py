@@ -36,6 +36,60 @@ def row_partition(height, world, align=1):
     return out
 
 
+def balanced_row_partition(costs, height, world, align, per_unit=0.0):
+    """Bands of equal COST instead of equal height: `costs[k]` = cost of pixel rows [k * align, (k + 1) * align) (the tile
+    rows of dvg_scene_row_costs), `per_unit` = cost every tile row carries whatever its content (sample generation, splat,
+    the boundary samples of its pixels).  Cuts lie on multiples of `align`; every rank gets at least one unit while there
+    are enough of them.  Deterministic, so ranks that see the same costs agree on the bands."""
+    import numpy as np
+    c = np.asarray(costs, np.float64) + float(per_unit)
+    units = c.shape[0]
+    assert units == (height + align - 1) // align and world >= 1
+    if units <= world:
+        return row_partition(height, world, align)
+    cum = np.concatenate([[0.0], np.cumsum(c)])
+    total = cum[-1]
+    cuts = [0]
+    for r in range(1, world):
+        k = int(np.searchsorted(cum, total * r / world, side='left'))
+        if k > 0 and abs(cum[k - 1] - total * r / world) <= abs(cum[min(k, units)] - total * r / world):
+            k -= 1
+        k = max(k, cuts[-1] + 1)                 # at least one unit per rank ...
+        k = min(k, units - (world - r))          # ... and enough left for the ranks after this one
+        cuts.append(k)
+    cuts.append(units)
+    return [(min(height, cuts[r] * align), min(height, cuts[r + 1] * align)) for r in range(world)]
+
+
+def balanced_bands(packed, params, width, height, num_samples_x, num_samples_y, world, per_tile=4.0, group=None):
+    """Row bands of equal estimated cost for the scene's CURRENT parameters (one whole-image binning + a read-back:
+    call it every few dozen iterations, not every step -- the content of an optimisation moves slowly -- and hand the
+    result to `ShardedRenderFunction.apply(..., bands=...)`).  `per_tile`: fixed cost of a tile in candidate units.
+    Every rank must call it (rank 0's answer is broadcast so that all ranks cut at the same rows)."""
+    import ctypes
+    import numpy as np
+    from .pydiffvg import render_pytorch as rp
+    n = rp._native()
+    dev = rp._cuda_device()
+    ns = rp._get_native_scene(packed, dev.index)
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream().cuda_stream
+        ns.set_params(params, stream)
+        cap = height + 1
+        costs = np.zeros(cap, np.float32)
+        th = ctypes.c_int()
+        n.check(n.lib.dvg_scene_row_costs(ns.handle, width, height, num_samples_x, num_samples_y,
+                                          1 if packed.use_prefiltering else 0, costs.ctypes.data, cap, ctypes.byref(th), stream))
+    align = th.value
+    units = (height + align - 1) // align
+    bands = balanced_row_partition(costs[:units], height, world, align, per_unit=per_tile * ((width + 7) // 8))
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        t = torch.tensor(bands, dtype=torch.int64, device=dev if dist.get_backend(group) == 'nccl' else 'cpu')
+        dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        bands = [tuple(int(v) for v in row) for row in t.cpu().tolist()]
+    return bands
+
+
 def stripe_partition(height, world, stripe=16):
     """Round-robin stripes of `stripe` rows: [[(b, e), ...]] * world.  Balances non-uniform content
     (SURVEY 8e 'efficiency risks'); each stripe is one *_rows call."""
@@ -97,7 +151,7 @@ class ShardedRenderFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, width, height, num_samples_x, num_samples_y, seed, background_image, packed, params, group=None,
-                gather=True):
+                gather=True, bands=None):
         from .pydiffvg import render_pytorch as rp
         n = rp._native()
         dev = rp._cuda_device()
@@ -106,7 +160,12 @@ class ShardedRenderFunction(torch.autograd.Function):
         rank = dist.get_rank(group) if dist.is_initialized() else 0
         ns = rp._get_native_scene(packed, dev.index)
         tile_h = tile_height(num_samples_x * num_samples_y)
-        bands = row_partition(height, world, tile_h)
+        if bands is None:
+            bands = row_partition(height, world, tile_h)
+        else:   # e.g. balanced_bands(...): cuts must lie on tile rows
+            bands = [(int(b), int(e)) for b, e in bands]
+            assert len(bands) == world and bands[0][0] == 0 and bands[-1][1] == height
+            assert all(b % tile_h == 0 for b, _ in bands) and all(bands[k][1] == bands[k + 1][0] for k in range(world - 1))
         rb, re = bands[rank]
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream().cuda_stream
@@ -183,7 +242,7 @@ class ShardedRenderFunction(torch.autograd.Function):
                 allreduce_gradients(d_bg, ctx.group)
         if d_params.device != ctx.params_device:
             d_params = d_params.to(ctx.params_device)
-        return None, None, None, None, None, d_bg, None, d_params, None, None
+        return None, None, None, None, None, d_bg, None, d_params, None, None, None
 
 
 def tile_height(spp):

@@ -192,6 +192,16 @@ int dvg_render_backward_rows(DvgScene *scene, const float *background, const flo
                              int use_prefiltering, int row_begin, int row_end,
                              float *d_params, float *d_background, uint32_t flags, void *stream);
 
+/*
+ * Cost profile for a BALANCED row partition (no reference counterpart: scene.cpp / diffvg.cpp are single-device).  Bins
+ * the whole image for the scene's current parameters and writes, per tile row (tile_h_out pixel rows each, top to
+ * bottom), the number of (tile, candidate primitive) entries of that row to the HOST array `out_costs` (`cap` >= number
+ * of tile rows = ceil(height / tile height)).  The render passes cost about that much per row plus a constant per tile;
+ * diffvg_b200/sharded.py cuts the bands so that every rank gets the same share.  Synchronises `stream`.
+ */
+int dvg_scene_row_costs(DvgScene *scene, int width, int height, int num_samples_x, int num_samples_y,
+                        int use_prefiltering, float *out_costs, int cap, int *tile_h_out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

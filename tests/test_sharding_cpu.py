@@ -115,3 +115,31 @@ def test_row_split_reproduces_whole_render_on_the_oracle():
         part[b:e] = d_img[b:e]
         acc += oracle_check.render(topo, params, w, h, 2, 2, 5, d_render_image=part)['d_params'].astype(np.float64)
     assert np.linalg.norm(acc - whole) <= 1e-4 * np.linalg.norm(whole)
+
+
+def test_balanced_row_partition_equalises_cost():
+    import numpy as np
+    rng = np.random.RandomState(0)
+    for height, align, world in ((2048, 8, 8), (2048, 2, 8), (512, 8, 4), (510, 8, 3), (64, 8, 8), (40, 8, 8)):
+        units = (height + align - 1) // align
+        x = np.linspace(-1, 1, units)
+        costs = 50.0 * np.exp(-6 * x * x) + rng.rand(units)         # dense in the middle, like flower.svg
+        bands = sharded.balanced_row_partition(costs, height, world, align, per_unit=1.0)
+        assert len(bands) == world and bands[0][0] == 0 and bands[-1][1] == height
+        for k, (b, e) in enumerate(bands):
+            assert b % align == 0 and b <= e
+            if k:
+                assert bands[k - 1][1] == b
+        if units > world:
+            assert all(e > b for b, e in bands)
+            c = costs + 1.0
+            share = [c[b // align:(e + align - 1) // align].sum() for b, e in bands]
+            even = [c[b // align:(e + align - 1) // align].sum() for b, e in sharded.row_partition(height, world, align)]
+            assert max(share) <= max(even) + 1e-9
+            if units >= 16 * world:
+                assert max(share) <= 1.15 * c.sum() / world
+        else:
+            assert bands == sharded.row_partition(height, world, align)
+    # uniform cost: the plain partition (up to one unit)
+    bands = sharded.balanced_row_partition(np.ones(256), 2048, 8, 8)
+    assert bands == sharded.row_partition(2048, 8, 8)
