@@ -199,15 +199,17 @@ def strong_scaling(dev, rank, world, barrier, max_over_ranks, steps=6, warmup=3)
             packed, params = pydiffvg.RenderFunction.serialize_scene(cw, ch, shapes, groups)
             params = params.detach().to(dev).requires_grad_(True)
         target = torch.rand(SH, SW, 4, generator=torch.Generator().manual_seed(1)).to(dev)
-        rb, re = sharded.row_partition(SH, world, sharded.tile_height(4))[rank]
+        # bands of equal estimated cost (whole-image bin counts of the start parameters), cut once outside the timed region
+        bands = sharded.balanced_bands(packed, params.detach(), SW, SH, 2, 2, world)
+        rb, re = bands[rank]
 
         def step_sharded(seed):
             params.grad = None
             if pf:    # loss per band: no image exchange, halo rows of d_image only (sharded.py)
-                img = sharded.ShardedRenderFunction.apply(SW, SH, 2, 2, seed, None, packed, params, None, False)
+                img = sharded.ShardedRenderFunction.apply(SW, SH, 2, 2, seed, None, packed, params, None, False, bands)
                 ((img - target[rb:re]).pow(2).sum() / target.numel()).backward()
             else:
-                img = sharded.ShardedRenderFunction.apply(SW, SH, 2, 2, seed, None, packed, params)
+                img = sharded.ShardedRenderFunction.apply(SW, SH, 2, 2, seed, None, packed, params, None, True, bands)
                 (img - target).pow(2).mean().backward()
 
         def step_single(seed):
@@ -237,6 +239,7 @@ def strong_scaling(dev, rank, world, barrier, max_over_ranks, steps=6, warmup=3)
         gn = float(params.grad.norm())
         out.append({'workload': label, 'ms_per_step_1gpu': ms1, 'ms_per_step': msn, 'n_gpus': world, 'speedup': ms1 / msn,
                     'efficiency': ms1 / msn / world, 'it_per_s': 1e3 / msn, 'grad_norm_1gpu': g1, 'grad_norm': gn,
+                    'bands': 'rows balanced by whole-image bin counts (sharded.balanced_bands): %s' % (bands,),
                     'timing': 'CUDA events around %d steps after %d warm-up steps, max over ranks; 1-GPU figure on rank 0 of the same run' % (steps, warmup)})
         del target, params
     return out

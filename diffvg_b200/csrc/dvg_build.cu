@@ -11,9 +11,98 @@
 namespace dvg {
 
 // (indices run over all scenes of a batch: scene = index / per-scene count, see SceneView)
+// One WARP per shape.  Paths: the lanes measure the segments (dvg_buildfn.cuh path_segment_measure: the arithmetic of the
+// sequential build_shape) and take the bounding box in parallel; lane 0 then forms the float sums in the reference's
+// sequential order (scene.cpp:132-191, 257-326: which segment a boundary sample picks depends on them bit for bit).  One
+// thread per shape walking a 100-segment path alone took 0.12 ms at flower.svg, on every rank of a row-sharded render.
 __global__ void k_build_shapes(BuildView bv) {
-    int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s < bv.num_shapes * bv.batch) build_shape(bv, s);
+    const int s_batch = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (s_batch >= bv.num_shapes * bv.batch) return;
+    const unsigned FULL = 0xffffffffu;
+    const int *topo = bv.topo;
+    const int scene = s_batch / bv.num_shapes, s = s_batch - scene * bv.num_shapes;
+    const int *r = topo + topo[DVG_H_OFF_SHAPES] + s * DVG_SHAPE_REC_LEN;
+    if (r[DVG_S_TYPE] != DVG_SHAPE_PATH) {
+        if (lane == 0) build_shape(bv, s_batch);
+        return;
+    }
+    const float *P = bv.params + (size_t)scene * bv.num_params;
+    const int seg_base = scene * bv.total_segs;
+    const float *p = P + r[DVG_S_PARAM_OFF];
+    const float stroke_width = r[DVG_S_WIDTH_OFF] >= 0 ? P[r[DVG_S_WIDTH_OFF]] : 0.f;
+    const int np = r[DVG_S_NUM_POINTS], nseg = r[DVG_S_NUM_SEGS];
+    const int *ncp = topo + topo[DVG_H_OFF_NCP] + r[DVG_S_NCP_OFF];
+    const float *thick = r[DVG_S_THICK_OFF] >= 0 ? P + r[DVG_S_THICK_OFF] : nullptr;
+    float *seg_pmf = bv.seg_pmf + seg_base + r[DVG_S_NCP_OFF];
+    float *seg_cdf = bv.seg_cdf + seg_base + r[DVG_S_NCP_OFF];
+    int *seg_pid = bv.seg_point_id + seg_base + r[DVG_S_NCP_OFF];
+    // bounding box of the control points
+    Box box; box.x0 = box.y0 = INFINITY; box.x1 = box.y1 = -INFINITY;
+    for (int i = lane; i < np; i += 32) {
+        const float x = p[2 * i], y = p[2 * i + 1];
+        box.x0 = rminf(x, box.x0); box.y0 = rminf(y, box.y0);
+        box.x1 = rmaxf(x, box.x1); box.y1 = rmaxf(y, box.y1);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        box.x0 = rminf(__shfl_xor_sync(FULL, box.x0, o), box.x0); box.y0 = rminf(__shfl_xor_sync(FULL, box.y0, o), box.y0);
+        box.x1 = rmaxf(__shfl_xor_sync(FULL, box.x1, o), box.x1); box.y1 = rmaxf(__shfl_xor_sync(FULL, box.y1, o), box.y1);
+    }
+    // segments: first point by a running scan of the control-point counts, raw lengths parked in seg_pmf, the y-sort
+    // key of thickness paths in seg_cdf
+    int carry = 0;
+    for (int base = 0; base < nseg; base += 32) {
+        const int i = base + lane;
+        const int n = i < nseg ? ncp[i] : -1;
+        int incl = n + 1;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += u;
+        }
+        const int pid = carry + incl - (n + 1);
+        if (i < nseg) {
+            float d, yc, th;
+            path_segment_measure(p, thick, np, n, pid, stroke_width, d, yc, th);
+            seg_pid[i] = pid;
+            seg_pmf[i] = d;
+            if (thick) seg_cdf[i] = yc;
+        }
+        carry += __shfl_sync(FULL, incl, 31);
+    }
+    __syncwarp();
+    float inv_length = 0.f, len = 0.f, r0q = stroke_width;
+    if (lane == 0) {
+        float length = 0.f;
+        for (int i = 0; i < nseg; i++) length += seg_pmf[i];
+        len += length;
+        if (thick) {   // radius of the first leaf after the reference's y-sort (scene.cpp:602-618): the first minimum
+            float best_y = INFINITY;
+            int best = -1;
+            for (int i = 0; i < nseg; i++) {
+                const float yc = seg_cdf[i];
+                if (yc < best_y) { best_y = yc; best = i; }
+            }
+            if (best >= 0) {
+                float d, yc, th;
+                path_segment_measure(p, thick, np, ncp[best], seg_pid[best], stroke_width, d, yc, th);
+                r0q = th;
+            }
+        }
+        inv_length = 1.f / len;
+    }
+    inv_length = __shfl_sync(FULL, inv_length, 0);
+    for (int i = lane; i < nseg; i += 32) seg_pmf[i] = seg_pmf[i] * inv_length;
+    __syncwarp();
+    if (lane == 0) {
+        float c = 0.f;
+        for (int i = 0; i < nseg; i++) {
+            const float d = seg_pmf[i];
+            c = (i == 0) ? d : d + c;
+            seg_cdf[i] = c;
+        }
+        bv.shapes_length[s_batch] = len;
+        bv.shape_box[s_batch] = box;
+        bv.shape_r0[s_batch] = r0q;
+    }
 }
 __global__ void k_build_groups(BuildView bv) {
     int g = blockIdx.x * blockDim.x + threadIdx.x;
@@ -90,26 +179,41 @@ DVG_D void tiles_rect(const BuildView &bv, const BinBuild &bb, int tx0, int ty0,
     y1 = ((float)((ty1 + 1) * bb.tile_h) / (float)bb.height) * ch + margin;
 }
 
-// Level 1 of the two-level binning: one warp per supertile walks ALL primitives once (bounding boxes only); the
-// per-tile kernel then walks ~1% of them.  Without it every one of 16 k (512^2) .. 65 k (2048^2) tiles walked every
-// primitive: 0.42 ms of a 7.2 ms step, and the largest cost a row shard repeats on every GPU.
-__global__ void k_bin_coarse(BuildView bv, BinBuild bb) {
-    const int lane = threadIdx.x & 31;
-    const int si = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (si >= bb.stiles_x * bb.stiles_y) return;
+// Level 1 of the two-level binning: one BLOCK per supertile walks ALL primitives (bounding boxes only); the per-tile
+// kernel then walks ~1% of them.  Without it every one of 16 k (512^2) .. 65 k (2048^2) tiles walked every primitive:
+// 0.42 ms of a 7.2 ms step, and the largest cost a row shard repeats on every GPU.  The eight warps of the block take
+// consecutive slices of the primitive list (count, block offsets, write: the supertile's list stays ascending); only the
+// supertile rows of the tile rows that will be binned are visited.  (One warp per supertile walking 10 k primitives alone
+// took 0.1 ms whatever the size of the band.)
+constexpr int BC_B = 256;
+__global__ void __launch_bounds__(BC_B) k_bin_coarse(BuildView bv, BinBuild bb, int srow0) {
+    __shared__ int s_cnt[BC_B / 32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int si = blockIdx.x + srow0 * bb.stiles_x;
     const int sx = si % bb.stiles_x, sy = si / bb.stiles_x;
     float x0, y0, x1, y1;
     tiles_rect(bv, bb, sx * bb.super, sy * bb.super, min((sx + 1) * bb.super, bb.tiles_x) - 1, min((sy + 1) * bb.super, bb.tiles_y) - 1, x0, y0, x1, y1);
     int *out = bb.s_items + (size_t)si * bv.num_prims;
+    const int slice = ((bv.num_prims + BC_B - 1) / BC_B) * 32;   // primitives per warp, a multiple of 32
+    const int e_begin = w * slice, e_end = min(bv.num_prims, e_begin + slice);
+    const Box *boxes = bb.prefilter ? bv.prim_cbox_pf : bv.prim_cbox;
     int count = 0;
-    for (int e0 = 0; e0 < bv.num_prims; e0 += 32) {
+    for (int e0 = e_begin; e0 < e_end; e0 += 32) {
         const int e = e0 + lane;
-        const bool ph = e < bv.num_prims && overlaps(bb.prefilter ? bv.prim_cbox_pf[e] : bv.prim_cbox[e], x0, y0, x1, y1);
-        const unsigned pmask = __ballot_sync(0xffffffffu, ph);
-        if (ph) out[count + __popc(pmask & ((1u << lane) - 1))] = e;
-        count += __popc(pmask);
+        count += __popc(__ballot_sync(0xffffffffu, e < e_end && overlaps(boxes[e], x0, y0, x1, y1)));
     }
-    if (lane == 0) bb.s_counts[si] = count;
+    if (lane == 0) s_cnt[w] = count;
+    __syncthreads();
+    int at = 0, total = 0;
+    for (int j = 0; j < BC_B / 32; j++) { if (j < w) at += s_cnt[j]; total += s_cnt[j]; }
+    for (int e0 = e_begin; e0 < e_end; e0 += 32) {
+        const int e = e0 + lane;
+        const bool ph = e < e_end && overlaps(boxes[e], x0, y0, x1, y1);
+        const unsigned pmask = __ballot_sync(0xffffffffu, ph);
+        if (ph) out[at + __popc(pmask & ((1u << lane) - 1))] = e;
+        at += __popc(pmask);
+    }
+    if (threadIdx.x == 0) bb.s_counts[si] = total;
 }
 
 template <int PASS>
@@ -255,7 +359,7 @@ void launch_tile_row_costs(const int *offsets, int tiles_x, int tiles_y, float *
 void launch_build(const BuildView &bv, cudaStream_t st) {
     const int B = 128;
     cudaMemsetAsync(bv.error_flag, 0, sizeof(int), st);
-    DVG_LAUNCH(k_build_shapes, dim3((bv.num_shapes * bv.batch + B - 1) / B), dim3(B), 0, st, bv);
+    DVG_LAUNCH(k_build_shapes, dim3((bv.num_shapes * bv.batch * 32 + B - 1) / B), dim3(B), 0, st, bv);   // a warp per shape
     DVG_LAUNCH(k_build_groups, dim3((bv.num_groups * bv.batch + B - 1) / B), dim3(B), 0, st, bv);
     DVG_LAUNCH(k_build_prims, dim3((bv.num_prims * bv.batch + B - 1) / B), dim3(B), 0, st, bv);
     DVG_LAUNCH(k_build_shape_cdf, dim3(bv.batch), dim3(256), 0, st, bv);
@@ -263,8 +367,9 @@ void launch_build(const BuildView &bv, cudaStream_t st) {
 
 void launch_bin_coarse(const BuildView &bv, const BinBuild &bb, cudaStream_t st) {
     if (!bb.super) return;
-    const int ns = bb.stiles_x * bb.stiles_y;
-    DVG_LAUNCH(k_bin_coarse, dim3((ns * 32 + 127) / 128), dim3(128), 0, st, bv, bb);
+    const int srow0 = bb.tile_row0 / bb.super, srow1 = (bb.tile_row1 + bb.super - 1) / bb.super;   // supertile rows of the binned tile rows
+    const int ns = bb.stiles_x * (srow1 - srow0);
+    if (ns > 0) DVG_LAUNCH(k_bin_coarse, dim3(ns), dim3(BC_B), 0, st, bv, bb, srow0);
 }
 void launch_bin_count(const BuildView &bv, const BinBuild &bb, cudaStream_t st) {
     const int ntiles = bb.tiles_x * bb.tiles_y * bb.batch;

@@ -29,6 +29,39 @@ struct BuildView {
 };
 
 // ------------------------------------------------------------------ shapes
+// One path segment (scene.cpp:132-191, 602-618): its length estimate `d` (chord of a line, two / three chords of a
+// quadratic / cubic through the curve points at 1/2 resp. 1/3 and 2/3), the centre `yc` of its y-extent (the key of the
+// reference's y-sort) and the largest control-point radius `th`.  `n` = number of control points, `pid` = first point.
+DVG_HD void path_segment_measure(const float *p, const float *thick, int np, int n, int pid, float stroke_width,
+                                 float &d, float &yc, float &th) {
+    float ymin, ymax;
+    if (n == 0) {
+        int i0 = pid, i1 = (i0 + 1) % np;
+        F2 p0 = mk2(p[2 * i0], p[2 * i0 + 1]), p1 = mk2(p[2 * i1], p[2 * i1 + 1]);
+        d = distance2(p1, p0);
+        ymin = rminf(p1.y, rminf(p0.y, INFINITY)); ymax = rmaxf(p1.y, rmaxf(p0.y, -INFINITY));
+        th = thick ? rmaxf(thick[i0], thick[i1]) : stroke_width;
+    } else if (n == 1) {
+        int i0 = pid, i1 = i0 + 1, i2 = (i0 + 2) % np;
+        F2 p0 = mk2(p[2 * i0], p[2 * i0 + 1]), p1 = mk2(p[2 * i1], p[2 * i1 + 1]), p2 = mk2(p[2 * i2], p[2 * i2 + 1]);
+        F2 v1 = eval_quad(p0, p1, p2, 0.5f);
+        d = distance2(v1, p0) + distance2(v1, p2);
+        ymin = rminf(p2.y, rminf(p1.y, rminf(p0.y, INFINITY)));
+        ymax = rmaxf(p2.y, rmaxf(p1.y, rmaxf(p0.y, -INFINITY)));
+        th = thick ? rmaxf(rmaxf(thick[i0], thick[i1]), thick[i2]) : stroke_width;
+    } else {
+        int i0 = pid, i1 = i0 + 1, i2 = i0 + 2, i3 = (i0 + 3) % np;
+        F2 p0 = mk2(p[2 * i0], p[2 * i0 + 1]), p1 = mk2(p[2 * i1], p[2 * i1 + 1]);
+        F2 p2 = mk2(p[2 * i2], p[2 * i2 + 1]), p3 = mk2(p[2 * i3], p[2 * i3 + 1]);
+        F2 v1 = eval_cubic(p0, p1, p2, p3, 1.f / 3.f), v2 = eval_cubic(p0, p1, p2, p3, 2.f / 3.f);
+        d = distance2(v1, p0) + distance2(v1, v2) + distance2(v2, p3);
+        ymin = rminf(p3.y, rminf(p2.y, rminf(p1.y, rminf(p0.y, INFINITY))));
+        ymax = rmaxf(p3.y, rmaxf(p2.y, rmaxf(p1.y, rmaxf(p0.y, -INFINITY))));
+        th = thick ? rmaxf(rmaxf(rmaxf(thick[i0], thick[i1]), thick[i2]), thick[i3]) : stroke_width;
+    }
+    yc = 0.5f * (ymin + ymax);
+}
+
 // shapes_length (scene.cpp:113-205), shapes_bbox (499-629), per-path segment pmf/cdf/point-id
 // map (248-333) and the "first leaf after the y-sort" radius the reference uses as the group
 // radius of thickness paths (scene.cpp:602-618, 650-667).
@@ -81,38 +114,11 @@ DVG_HD_NOINLINE void build_shape(const BuildView &bv, int s_batch) {
             // pass 1: total length (scene.cpp:132-191); raw segment lengths parked in seg_pmf
             for (int i = 0; i < nseg; i++) {
                 seg_pid[i] = pid;
-                float d;
-                float ymin, ymax, th;
-                if (ncp[i] == 0) {
-                    int i0 = pid, i1 = (i0 + 1) % np;
-                    F2 p0 = mk2(p[2 * i0], p[2 * i0 + 1]), p1 = mk2(p[2 * i1], p[2 * i1 + 1]);
-                    d = distance2(p1, p0);
-                    ymin = rminf(p1.y, rminf(p0.y, INFINITY)); ymax = rmaxf(p1.y, rmaxf(p0.y, -INFINITY));
-                    th = thick ? rmaxf(thick[i0], thick[i1]) : stroke_width;
-                    pid += 1;
-                } else if (ncp[i] == 1) {
-                    int i0 = pid, i1 = i0 + 1, i2 = (i0 + 2) % np;
-                    F2 p0 = mk2(p[2 * i0], p[2 * i0 + 1]), p1 = mk2(p[2 * i1], p[2 * i1 + 1]), p2 = mk2(p[2 * i2], p[2 * i2 + 1]);
-                    F2 v1 = eval_quad(p0, p1, p2, 0.5f);
-                    d = distance2(v1, p0) + distance2(v1, p2);
-                    ymin = rminf(p2.y, rminf(p1.y, rminf(p0.y, INFINITY)));
-                    ymax = rmaxf(p2.y, rmaxf(p1.y, rmaxf(p0.y, -INFINITY)));
-                    th = thick ? rmaxf(rmaxf(thick[i0], thick[i1]), thick[i2]) : stroke_width;
-                    pid += 2;
-                } else {
-                    int i0 = pid, i1 = i0 + 1, i2 = i0 + 2, i3 = (i0 + 3) % np;
-                    F2 p0 = mk2(p[2 * i0], p[2 * i0 + 1]), p1 = mk2(p[2 * i1], p[2 * i1 + 1]);
-                    F2 p2 = mk2(p[2 * i2], p[2 * i2 + 1]), p3 = mk2(p[2 * i3], p[2 * i3 + 1]);
-                    F2 v1 = eval_cubic(p0, p1, p2, p3, 1.f / 3.f), v2 = eval_cubic(p0, p1, p2, p3, 2.f / 3.f);
-                    d = distance2(v1, p0) + distance2(v1, v2) + distance2(v2, p3);
-                    ymin = rminf(p3.y, rminf(p2.y, rminf(p1.y, rminf(p0.y, INFINITY))));
-                    ymax = rmaxf(p3.y, rmaxf(p2.y, rmaxf(p1.y, rmaxf(p0.y, -INFINITY))));
-                    th = thick ? rmaxf(rmaxf(rmaxf(thick[i0], thick[i1]), thick[i2]), thick[i3]) : stroke_width;
-                    pid += 3;
-                }
+                float d, yc, th;
+                path_segment_measure(p, thick, np, ncp[i], pid, stroke_width, d, yc, th);
+                pid += ncp[i] + 1;
                 length += d;
                 seg_pmf[i] = d;
-                float yc = 0.5f * (ymin + ymax);
                 if (yc < best_y) { best_y = yc; if (thick) r0q = th; }
             }
             len += length;
