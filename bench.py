@@ -233,13 +233,29 @@ def strong_scaling(dev, rank, world, barrier, max_over_ranks, steps=6, warmup=3)
             barrier()
             return a.elapsed_time(b) / steps
 
+        # bands re-cut from measured per-rank times (three rounds, outside the timed region): the bin-count estimate cannot
+        # see how expensive a tile's candidates are
+        for rnd in range(3):
+            step_sharded(100 + rnd)
+            barrier()
+            ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ea.record()
+            for i in range(2):
+                step_sharded(110 + 2 * rnd + i)
+            eb.record()
+            torch.cuda.synchronize(dev)
+            mine = torch.tensor([ea.elapsed_time(eb)], dtype=torch.float64, device=dev)
+            allt = [torch.zeros_like(mine) for _ in range(world)]
+            dist.all_gather(allt, mine)
+            bands = sharded.rebalance_bands(bands, [float(t.item()) for t in allt], SH, sharded.tile_height(4))
+            rb, re = bands[rank]
         ms1 = max_over_ranks(timed(step_single, True))
         g1 = float(params.grad.norm()) if rank == 0 else 0.0
         msn = max_over_ranks(timed(step_sharded, False))
         gn = float(params.grad.norm())
         out.append({'workload': label, 'ms_per_step_1gpu': ms1, 'ms_per_step': msn, 'n_gpus': world, 'speedup': ms1 / msn,
                     'efficiency': ms1 / msn / world, 'it_per_s': 1e3 / msn, 'grad_norm_1gpu': g1, 'grad_norm': gn,
-                    'bands': 'rows balanced by whole-image bin counts (sharded.balanced_bands): %s' % (bands,),
+                    'bands': 'rows balanced by whole-image bin counts (sharded.balanced_bands), then re-cut three times from measured per-rank times during warm-up (sharded.rebalance_bands): %s' % (bands,),
                     'timing': 'CUDA events around %d steps after %d warm-up steps, max over ranks; 1-GPU figure on rank 0 of the same run' % (steps, warmup)})
         del target, params
     return out

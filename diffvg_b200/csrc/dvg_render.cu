@@ -11,30 +11,40 @@ namespace dvg {
 // ------------------------------------------------------------------------------------------
 // weight_kernel (diffvg.cpp:1115-1158).  Q1: always uses the jittered position, even when
 // the render kernel uses pixel centres for prefiltering.
-__global__ void k_weight(SceneView sc, RenderArgs ra_all, int idx_begin, int idx_end) {
-    const int per_scene = ra_all.width * ra_all.height * ra_all.nsx * ra_all.nsy;
-    const int gidx = idx_begin + blockIdx.x * blockDim.x + threadIdx.x;   // batch: scenes back to back
-    if (gidx >= idx_end) return;
-    const int scene = gidx / per_scene, idx = gidx - scene * per_scene;
+// One thread per PIXEL: it draws the pixel's samples (same RNG streams: one per sample index), sums what they add to
+// their own pixel in a register and sends only the rest -- nothing at all for a filter of radius <= 0.5 unless a sample
+// lands exactly on a pixel edge -- to the neighbours with atomics.  (One thread and one atomic per SAMPLE cost 0.25 ms
+// at 2048^2 x 4 spp, all of it repeated by every rank of a row-sharded sampled render.)
+__global__ void k_weight(SceneView sc, RenderArgs ra_all, int px_begin, int px_end) {
+    const int per_scene = ra_all.width * ra_all.height;
+    const int gpx = px_begin + blockIdx.x * blockDim.x + threadIdx.x;   // batch: scenes back to back
+    if (gpx >= px_end) return;
+    const int scene = gpx / per_scene, pix = gpx - scene * per_scene;
     const RenderArgs ra = args_of_scene(ra_all, scene);
-    Pcg32 rng = pcg32_init(idx, ra.seed);
-    const int sx = idx % ra.nsx;
-    const int sy = (idx / ra.nsx) % ra.nsy;
-    const int x = (idx / (ra.nsx * ra.nsy)) % ra.width;
-    const int y = idx / (ra.nsx * ra.nsy * ra.width);
-    float rx = pcg32_next_float(rng);
-    float ry = pcg32_next_float(rng);
-    F2 pt = mk2(x + ((float)sx + rx) / ra.nsx, y + ((float)sy + ry) / ra.nsy);
+    const int x = pix % ra.width, y = pix / ra.width;
+    const int spp = ra.nsx * ra.nsy;
     const int ri = (int)ceilf(sc.filter.radius);
-    for (int dy = -ri; dy <= ri; dy++) {
-        for (int dx = -ri; dx <= ri; dx++) {
-            int xx = x + dx, yy = y + dy;
-            if (xx >= 0 && xx < ra.width && yy >= 0 && yy < ra.height) {
-                float w = filter_weight(sc.filter, (xx + 0.5f) - pt.x, (yy + 0.5f) - pt.y);
-                if (w != 0.f) atomicAdd(&ra.weight_image[yy * ra.width + xx], w);
+    float own = 0.f;
+    for (int s = 0; s < spp; s++) {
+        const int idx = pix * spp + s;                 // ((y * W + x) * nsy + sy) * nsx + sx
+        Pcg32 rng = pcg32_init(idx, ra.seed);
+        const int sx = s % ra.nsx, sy = s / ra.nsx;
+        const float rx = pcg32_next_float(rng);
+        const float ry = pcg32_next_float(rng);
+        const F2 pt = mk2(x + ((float)sx + rx) / ra.nsx, y + ((float)sy + ry) / ra.nsy);
+        for (int dy = -ri; dy <= ri; dy++) {
+            for (int dx = -ri; dx <= ri; dx++) {
+                const int xx = x + dx, yy = y + dy;
+                if (xx >= 0 && xx < ra.width && yy >= 0 && yy < ra.height) {
+                    const float w = filter_weight(sc.filter, (xx + 0.5f) - pt.x, (yy + 0.5f) - pt.y);
+                    if (w == 0.f) continue;
+                    if (dx == 0 && dy == 0) own += w;
+                    else atomicAdd(&ra.weight_image[yy * ra.width + xx], w);
+                }
             }
         }
     }
+    if (own != 0.f) atomicAdd(&ra.weight_image[pix], own);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -96,15 +106,14 @@ void launch_weight(const SceneView &sc, const RenderArgs &ra, int row_begin, int
     // pixels up to ri rows outside the band are read (gather_d_color, splat); their weights need samples ri rows further
     const int ri = 2 * (int)ceilf(sc.filter.radius);
     const int y0 = max(0, row_begin - ri), y1 = min(ra.height, row_end + ri);
-    const int per_row = ra.width * ra.nsx * ra.nsy;
     if (sc.batch > 1) {   // every scene, whole images
-        const int n = ra.height * per_row * sc.batch;
+        const int n = ra.height * ra.width * sc.batch;
         DVG_LAUNCH(k_weight, dim3((n + 255) / 256), dim3(256), 0, st, sc, ra, 0, n);
         return;
     }
-    const int n = (y1 - y0) * per_row;
+    const int n = (y1 - y0) * ra.width;
     if (n <= 0) return;
-    DVG_LAUNCH(k_weight, dim3((n + 255) / 256), dim3(256), 0, st, sc, ra, y0 * per_row, y1 * per_row);
+    DVG_LAUNCH(k_weight, dim3((n + 255) / 256), dim3(256), 0, st, sc, ra, y0 * ra.width, y1 * ra.width);
 }
 
 // tile keys + counting sort of the boundary samples by tile (fills tile_counts, tile_offsets, sorted_idx)

@@ -61,6 +61,34 @@ def balanced_row_partition(costs, height, world, align, per_unit=0.0):
     return [(min(height, cuts[r] * align), min(height, cuts[r + 1] * align)) for r in range(world)]
 
 
+def rebalance_bands(bands, times, height, align, damping=1.0):
+    """Bands re-cut from MEASURED per-rank times: rank r took `times[r]` for rows `bands[r]`, so its rows cost
+    times[r] / rows each; the new cuts give every rank the same share of that piecewise-constant cost profile (cuts on
+    multiples of `align`, at least one unit per rank).  Two or three rounds during warm-up settle within a few per cent
+    of even: the bin-count estimate of `balanced_bands` cannot see how expensive a tile's candidates are.  `damping` < 1
+    moves only part of the way (noisy timings).  Deterministic in its inputs: gather the times, then call it on every rank."""
+    import numpy as np
+    world = len(bands)
+    units = (height + align - 1) // align
+    if units <= world:
+        return list(bands)
+    dens = np.zeros(units, np.float64)
+    for (b, e), t in zip(bands, times):
+        u0, u1 = b // align, (e + align - 1) // align
+        if u1 > u0:
+            dens[u0:u1] = max(float(t), 1e-9) / (u1 - u0)
+    new = balanced_row_partition(dens, height, world, align)
+    if damping < 1.0:
+        cuts = [int(round(((1 - damping) * ob + damping * nb) / align)) * align for (ob, _), (nb, _) in zip(bands, new)]
+        cuts = cuts + [height]
+        for r in range(1, world):                     # keep the cuts increasing by at least one unit
+            cuts[r] = max(cuts[r], cuts[r - 1] + align)
+        for r in range(world - 1, 0, -1):
+            cuts[r] = min(cuts[r], cuts[r + 1] - align if r + 1 < world else ((height - 1) // align) * align)
+        new = [(cuts[r], cuts[r + 1]) for r in range(world)]
+    return new
+
+
 def balanced_bands(packed, params, width, height, num_samples_x, num_samples_y, world, per_tile=4.0, group=None):
     """Row bands of equal estimated cost for the scene's CURRENT parameters (one whole-image binning + a read-back:
     call it every few dozen iterations, not every step -- the content of an optimisation moves slowly -- and hand the
@@ -173,12 +201,13 @@ class ShardedRenderFunction(torch.autograd.Function):
             if background_image is not None:
                 background_image = background_image.to(dev).contiguous().float()
                 assert background_image.shape == (height, width, 4)
-            full = torch.zeros(height, width, 4, device=dev, dtype=torch.float32)
+            wide = float(getattr(packed, 'filter_radius', 0.5)) > 0.5
+            # the call zeroes and fills the rows of its band; only the all-reduce of wide filters reads the other rows
+            full = (torch.zeros if (wide and world > 1) else torch.empty)(height, width, 4, device=dev, dtype=torch.float32)
             n.check(n.lib.dvg_render_forward_rows(
                 ns.handle, background_image.data_ptr() if background_image is not None else None, full.data_ptr(),
                 width, height, num_samples_x, num_samples_y, int(seed), 1 if packed.use_prefiltering else 0,
                 rb, re, stream))
-            wide = float(getattr(packed, 'filter_radius', 0.5)) > 0.5
             if not gather:
                 assert not wide or world == 1, 'gather=False needs a pixel filter of radius <= 0.5 (samples splat across band edges)'
                 img = full[rb:re]
@@ -218,8 +247,11 @@ class ShardedRenderFunction(torch.autograd.Function):
                     edge = torch.cat([grad_img[:hl], grad_img[-hl:]], dim=0).contiguous()
                     buf = torch.empty((ctx.world,) + tuple(edge.shape), dtype=edge.dtype, device=edge.device)
                     dist.all_gather_into_tensor(buf, edge, group=ctx.group)
-                    full = torch.zeros(height, width, 4, device=dev, dtype=torch.float32)
+                    # (the prefiltered backward pass reads d_image on its own rows and the halo only)
+                    full = torch.empty(height, width, 4, device=dev, dtype=torch.float32)
                     full[rb:re] = grad_img
+                    full[max(0, rb - hl):rb].zero_()            # halo rows: the neighbours' rows below, zero at the image edge
+                    full[re:min(height, re + hl)].zero_()
                     if rank > 0:
                         full[rb - hl:rb] = buf[rank - 1, hl:]
                     if rank < ctx.world - 1:

@@ -143,3 +143,25 @@ def test_balanced_row_partition_equalises_cost():
     # uniform cost: the plain partition (up to one unit)
     bands = sharded.balanced_row_partition(np.ones(256), 2048, 8, 8)
     assert bands == sharded.row_partition(2048, 8, 8)
+
+
+def test_rebalance_bands_converges_on_a_hidden_cost_profile():
+    import numpy as np
+    height, align, world = 2048, 8, 8
+    units = height // align
+    x = np.linspace(-1, 1, units)
+    true = 1.0 + 6.0 * np.exp(-5 * (x - 0.2) ** 2)                 # cost per tile row, unknown to the partitioner
+    fixed = 0.05 * true.sum() / world                              # plus a constant per rank
+
+    def times(bands):
+        return [true[b // align:e // align].sum() + fixed for b, e in bands]
+    bands = sharded.row_partition(height, world, align)
+    first = max(times(bands))
+    for _ in range(3):
+        bands = sharded.rebalance_bands(bands, times(bands), height, align)
+        assert bands[0][0] == 0 and bands[-1][1] == height and all(b % align == 0 and e > b for b, e in bands)
+        assert all(bands[k][1] == bands[k + 1][0] for k in range(world - 1))
+    t = times(bands)
+    assert max(t) < 0.8 * first and max(t) <= 1.04 * (sum(t) / world)
+    damped = sharded.rebalance_bands(sharded.row_partition(height, world, align), times(sharded.row_partition(height, world, align)), height, align, damping=0.5)
+    assert damped[0][0] == 0 and damped[-1][1] == height and all(e > b for b, e in damped)
