@@ -497,6 +497,137 @@ DVG_HD_NOINLINE int solve_cubic_cr(double a, double b, double c, double d, doubl
     }
 }
 
+// winding_number.h:118-156: the reference's operation sequence for a cubic segment.
+DVG_HD_NOINLINE int cubic_winding_exact(F2 p0, F2 p1, F2 p2, F2 p3, F2 pt) {
+    double t[3];
+    const double ca = (double)(-p0.y + 3 * p1.y - 3 * p2.y + p3.y), cb = (double)(3 * p0.y - 6 * p1.y + 3 * p2.y),
+                 cc = (double)(-3 * p0.y + 3 * p1.y), cd = (double)(p0.y - pt.y);
+    int num_sol = solve_cubic_d(ca, cb, cc, cd, t);
+    // float coefficient * double t: the products are formed in double (winding_number.h:142-149)
+    float cx3 = -p0.x + 3 * p1.x - 3 * p2.x + p3.x, cx2 = 3 * p0.x - 6 * p1.x + 3 * p2.x, cx1 = -3 * p0.x + 3 * p1.x;
+    float cy3 = -p0.y + 3 * p1.y - 3 * p2.y + p3.y, cy2 = 3 * p0.y - 6 * p1.y + 3 * p2.y, cy1 = -3 * p0.y + 3 * p1.y;
+    // A root within 1e-9 of a decision boundary (t = 0, t = 1, crossing exactly at the sample, horizontal tangent at
+    // the crossing): the verdict hangs on the last bit of acos / cos / pow; solve again with correctly rounded
+    // ones (dvg_crmath.cuh), which is what glibc returns for 99.9% of the arguments
+    bool near = false;
+    for (int j = 0; j < num_sol; j++) {
+        const double tj = t[j];
+        if (fabs(tj) < 1e-9 || fabs(tj - 1.0) < 1e-9) near = true;
+        else if (tj > 0 && tj < 1) {
+            const double tp = (double)cx3 * tj * tj * tj + (double)cx2 * tj * tj + (double)cx1 * tj + (double)p0.x - (double)pt.x;
+            const double dy = (double)(3 * cy3) * tj * tj + (double)(2 * cy2) * tj + (double)cy1;
+            if (fabs(tp) < 1e-9 * (1.0 + fabs((double)pt.x)) || fabs(dy) < 1e-9 * (fabs((double)cy1) + fabs((double)cy2) + fabs((double)cy3))) near = true;
+        }
+    }
+    if (near) num_sol = solve_cubic_cr(ca, cb, cc, cd, t);
+    int w = 0;
+    for (int j = 0; j < num_sol; j++) {
+        if (t[j] >= 0 && t[j] <= 1) {
+            double tp = (double)cx3 * t[j] * t[j] * t[j] + (double)cx2 * t[j] * t[j] + (double)cx1 * t[j] +
+                        (double)p0.x - (double)pt.x;
+            if (tp > 0) {  // Q13: strict here, >= for lines and quadratics
+                if ((double)(3 * cy3) * t[j] * t[j] + (double)(2 * cy2) * t[j] + (double)cy1 > 0) w += 1;
+                else w -= 1;
+            }
+        }
+    }
+    return w;
+}
+
+// Winding contribution of a cubic segment, FAST form.  The reference (winding_number.h:118-156) solves y(t) = pt.y with the
+// closed-form double solve_cubic (acos / cos / pow in double: several hundred FP64 instructions) and then takes four
+// DECISIONS per root: t in [0, 1], crossing to the right of the sample (tp > 0), crossing direction (dy > 0).  Only the
+// decisions matter.  Here the roots inside a window slightly wider than [0, 1] are found directly: the critical points
+// of y cut the window into monotone pieces, a sign change across a piece is one root, found by a bracketed Newton in
+// double (closer to the true root than the closed form, for any size of the leading coefficient).  The answer is
+// taken only when every decision is clear by a margin 100 x wider than the band in which the reference's own verdict
+// depends on its last bits (the 1e-9 band of cubic_winding_exact's correctly-rounded fall-back): roots 1e-7 away from
+// 0 and 1, |tp| and |dy| 1e-7 (relative) away from 0 -- which also excludes near-double roots --, the Newton
+// converged.  Anything else (about 1% of the pairs of an SVG asset rendered on a regular sample grid) returns false and
+// takes the reference's operation sequence.
+DVG_HD bool cubic_winding_fast(F2 p0, F2 p1, F2 p2, F2 p3, F2 pt, int *w_out) {
+#if defined(DVG_FQ_ISOL)
+    const float cx3 = -p0.x + 3 * p1.x - 3 * p2.x + p3.x, cx2 = 3 * p0.x - 6 * p1.x + 3 * p2.x, cx1 = -3 * p0.x + 3 * p1.x;
+    const float cy3 = -p0.y + 3 * p1.y - 3 * p2.y + p3.y, cy2 = 3 * p0.y - 6 * p1.y + 3 * p2.y, cy1 = -3 * p0.y + 3 * p1.y;
+    const double a = (double)cy3, b = (double)cy2, c = (double)cy1, d = (double)(p0.y - pt.y);
+    if (!(fabs(a) >= 1e-5f)) return false;       // (at or next to the quadratic branch of solve.h:30-36 -- cheap there --, or NaN)
+    // Where the reference's closed form is ill-conditioned its roots are NOT close to the true ones and the verdict is
+    // whatever its arithmetic gives: R / sqrt(Q^3) next to +-1 (acos loses half its digits), which is a near-double root
+    // or a leading coefficient that is small against the others (one root far away).  Qn, Rn: Q a^2 and R a^3.
+    {
+        const double Qn = (b * b - 3.0 * a * c) * (1.0 / 9.0);
+        const double Rn = (2.0 * b * b * b - 9.0 * a * b * c + 27.0 * a * a * d) * (1.0 / 54.0);
+        const double R2 = Rn * Rn, Q3 = Qn * Qn * Qn;
+        // acos' error near +-1 is eps / sqrt(2 x relative discriminant), scaled into t by |b / 3a|: the threshold keeps the
+        // reference's roots within ~1e-9 of the true ones (the margins below are 1e-7)
+        const double thr_a2 = fmax(1e-10 * a * a, 1e-14 * b * b);
+        if (!(fabs(R2 - Q3) * (a * a) > thr_a2 * (R2 + fabs(Q3)))) return false;
+    }
+    const double lo = -0.01, hi = 1.01;          // roots outside are clearly outside [0, 1]
+    // monotone pieces: break the window at the critical points of y (float precision is enough for a break point: two
+    // roots closer than that to a critical point are a near-double root, whose |dy| fails the margin below)
+    double brk[4];
+    int nb = 0;
+    brk[nb++] = lo;
+    const double D = b * b - 3.0 * a * c;
+    if (D > 0) {
+        const double sD = (double)sqrtf((float)D);
+        const double q = -(b + (b >= 0 ? sD : -sD));
+        double t1 = (double)((float)q / (float)(3.0 * a)), t2 = q != 0.0 ? (double)((float)c / (float)q) : t1;
+        if (t1 > t2) { const double tmp = t1; t1 = t2; t2 = tmp; }
+        if (t1 > lo && t1 < hi) brk[nb++] = t1;
+        if (t2 > lo && t2 < hi && t2 > t1) brk[nb++] = t2;
+    }
+    brk[nb++] = hi;
+    const double dy_scale = (double)(fabsf(cy1) + fabsf(cy2) + fabsf(cy3));
+    int w = 0;
+    double yu = fma(fma(fma(a, lo, b), lo, c), lo, d);
+    for (int k = 0; k + 1 < nb; k++) {
+        double u = brk[k], v = brk[k + 1];
+        const double yv = fma(fma(fma(a, v, b), v, c), v, d);
+        const double yu0 = yu;
+        yu = yv;
+        if (yu0 == 0.0 || yv == 0.0 || yu0 != yu0 || yv != yv) return false;
+        if ((yu0 > 0) == (yv > 0)) continue;                 // no sign change: no root in this piece
+        // the root of this piece: four bracketed Newton steps in float from the secant point (fixed trip count: the lanes
+        // of a warp stay together), then three steps in double whose correction needs float precision only, then a check
+        // that one more step would not move it
+        float uf = (float)u, vf = (float)v, fuf = (float)yu0;
+        const float df = (float)d;
+        float tf = uf - fuf * (vf - uf) / ((float)yv - fuf);
+        for (int it = 0; it < 4; it++) {
+            if (!(tf > uf && tf < vf)) tf = 0.5f * (uf + vf);
+            const float ff = ((cy3 * tf + cy2) * tf + cy1) * tf + df;
+            const float fpf = (3.f * cy3 * tf + 2.f * cy2) * tf + cy1;
+            if ((ff > 0.f) == (fuf > 0.f)) { uf = tf; fuf = ff; } else vf = tf;
+            if (fabsf(fpf) > 1e-30f) tf -= ff * seed_rcp(fpf);
+        }
+        double t = (double)tf;
+        if (!(t > u && t < v)) t = 0.5 * ((double)uf + (double)vf);
+        bool converged = false;
+        for (int it = 0; it < 4; it++) {
+            const double f = fma(fma(fma(a, t, b), t, c), t, d);
+            const double fp = fma(fma(3.0 * a, t, 2.0 * b), t, c);
+            if (it == 3) { converged = fabs(f) <= 1e-11 * fabs(fp); break; }
+            const float fpf = (float)fp;
+            if (!(fabsf(fpf) > 1e-30f && fabsf(fpf) < 1e30f)) break;
+            t -= (double)((float)f * seed_rcp(fpf));
+        }
+        if (!converged) return false;
+        if (!(fabs(t) > 1e-7 && fabs(t - 1.0) > 1e-7)) return false;
+        if (t < 0 || t > 1) continue;
+        const double tp = (double)cx3 * t * t * t + (double)cx2 * t * t + (double)cx1 * t + (double)p0.x - (double)pt.x;
+        const double dy = (double)(3 * cy3) * t * t + (double)(2 * cy2) * t + (double)cy1;
+        if (!(fabs(tp) > 1e-7 * (1.0 + fabs((double)pt.x)) && fabs(dy) > 1e-7 * dy_scale)) return false;
+        if (tp > 0) w += dy > 0 ? 1 : -1;
+    }
+    *w_out = w;
+    return true;
+#else
+    return false;
+#endif
+}
+
 // winding_number.h:62-156 per leaf type + 9-31, 176-186 for the closed-form shapes.
 DVG_HD_NOINLINE int prim_winding(int type, F4 p01, F4 p23, F2 pt) {
     switch (type) {
@@ -529,40 +660,10 @@ DVG_HD_NOINLINE int prim_winding(int type, F4 p01, F4 p23, F2 pt) {
             return w;
         }
         case PRIM_CUBIC: {
-            F2 p0 = mk2(p01.x, p01.y), p1 = mk2(p01.z, p01.w), p2 = mk2(p23.x, p23.y), p3 = mk2(p23.z, p23.w);
-            double t[3];
-            const double ca = (double)(-p0.y + 3 * p1.y - 3 * p2.y + p3.y), cb = (double)(3 * p0.y - 6 * p1.y + 3 * p2.y),
-                         cc = (double)(-3 * p0.y + 3 * p1.y), cd = (double)(p0.y - pt.y);
-            int num_sol = solve_cubic_d(ca, cb, cc, cd, t);
-            // float coefficient * double t: the products are formed in double (winding_number.h:142-149)
-            float cx3 = -p0.x + 3 * p1.x - 3 * p2.x + p3.x, cx2 = 3 * p0.x - 6 * p1.x + 3 * p2.x, cx1 = -3 * p0.x + 3 * p1.x;
-            float cy3 = -p0.y + 3 * p1.y - 3 * p2.y + p3.y, cy2 = 3 * p0.y - 6 * p1.y + 3 * p2.y, cy1 = -3 * p0.y + 3 * p1.y;
-            // A root within 1e-9 of a decision boundary (t = 0, t = 1, crossing exactly at the sample, horizontal tangent at
-            // the crossing): the verdict hangs on the last bit of acos / cos / pow; solve again with correctly rounded
-            // ones (dvg_crmath.cuh), which is what glibc returns for 99.9% of the arguments
-            bool near = false;
-            for (int j = 0; j < num_sol; j++) {
-                const double tj = t[j];
-                if (fabs(tj) < 1e-9 || fabs(tj - 1.0) < 1e-9) near = true;
-                else if (tj > 0 && tj < 1) {
-                    const double tp = (double)cx3 * tj * tj * tj + (double)cx2 * tj * tj + (double)cx1 * tj + (double)p0.x - (double)pt.x;
-                    const double dy = (double)(3 * cy3) * tj * tj + (double)(2 * cy2) * tj + (double)cy1;
-                    if (fabs(tp) < 1e-9 * (1.0 + fabs((double)pt.x)) || fabs(dy) < 1e-9 * (fabs((double)cy1) + fabs((double)cy2) + fabs((double)cy3))) near = true;
-                }
-            }
-            if (near) num_sol = solve_cubic_cr(ca, cb, cc, cd, t);
-            int w = 0;
-            for (int j = 0; j < num_sol; j++) {
-                if (t[j] >= 0 && t[j] <= 1) {
-                    double tp = (double)cx3 * t[j] * t[j] * t[j] + (double)cx2 * t[j] * t[j] + (double)cx1 * t[j] +
-                                (double)p0.x - (double)pt.x;
-                    if (tp > 0) {  // Q13: strict here, >= for lines and quadratics
-                        if ((double)(3 * cy3) * t[j] * t[j] + (double)(2 * cy2) * t[j] + (double)cy1 > 0) w += 1;
-                        else w -= 1;
-                    }
-                }
-            }
-            return w;
+            const F2 p0 = mk2(p01.x, p01.y), p1 = mk2(p01.z, p01.w), p2 = mk2(p23.x, p23.y), p3 = mk2(p23.z, p23.w);
+            int wf;
+            if (cubic_winding_fast(p0, p1, p2, p3, pt, &wf)) return wf;
+            return cubic_winding_exact(p0, p1, p2, p3, pt);
         }
         case PRIM_CIRCLE:
             return dist_sq(mk2(p01.x, p01.y), pt) < p01.z * p01.z ? 1 : 0;

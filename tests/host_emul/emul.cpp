@@ -466,6 +466,21 @@ EXPORT void emul_quintic_split_check(const float *pts8, const float *rad4, const
     }
 }
 
+// cubic_winding_fast against cubic_winding_exact (dvg_geom.cuh): out[0] = pairs the fast form answered, out[1] = answered
+// pairs whose winding differs from the reference's operation sequence.
+EXPORT void emul_winding_fast_check(const float *pts8, const float *xy, int n, long long *out) {
+    const F2 p0 = mk2(pts8[0], pts8[1]), p1 = mk2(pts8[2], pts8[3]), p2 = mk2(pts8[4], pts8[5]), p3 = mk2(pts8[6], pts8[7]);
+    out[0] = out[1] = 0;
+    for (int i = 0; i < n; i++) {
+        const F2 pt = mk2(xy[2 * i], xy[2 * i + 1]);
+        int wf = 0;
+        if (cubic_winding_fast(p0, p1, p2, p3, pt, &wf)) {
+            out[0]++;
+            if (wf != cubic_winding_exact(p0, p1, p2, p3, pt)) out[1]++;
+        }
+    }
+}
+
 EXPORT void emul_pcg(int idx, uint64_t seed, uint64_t *state, float *rx, float *ry) {
     Pcg32 r = pcg32_init(idx, seed);
     *state = r.state;

@@ -405,3 +405,54 @@ def test_per_primitive_quintic_split_is_bit_identical():
     assert coeff == 0
     assert split <= total * 1e-4, (split, total)
     assert verdict == 0
+
+
+def test_fast_cubic_winding_agrees_with_the_reference_sequence_whenever_it_answers():
+    """dvg_geom.cuh cubic_winding_fast: roots from a polished float closed form, answered only when every decision (t in
+    [0, 1], crossing right of the sample, crossing direction) is clear by a margin; otherwise the reference's operation
+    sequence runs (cubic_winding_exact, with its correctly-rounded fall-back).  On random cubics, cubics with round
+    coordinates sampled on a regular grid (crossings exactly at control points: the adversarial case of SVG assets under
+    prefiltering), near-degenerate (almost quadratic / almost straight) ones and samples at the curve's own y-extrema:
+    every answered pair must agree, and most pairs must be answered."""
+    import ctypes
+    lib = emul._load()
+    fp = ctypes.POINTER(ctypes.c_float)
+    lib.emul_winding_fast_check.argtypes = [fp, fp, ctypes.c_int, ctypes.POINTER(ctypes.c_longlong)]
+    rng = np.random.RandomState(33)
+    tot = ans = bad = 0
+    common = [0, 0]      # random / round-coordinate / monotone cubics: what assets are made of
+    for c in range(600):
+        kind = c % 6
+        if kind == 0:      # random
+            pts = (rng.rand(4, 2) * 200).astype(np.float32)
+        elif kind == 1:    # round coordinates, grid samples
+            pts = rng.randint(0, 64, (4, 2)).astype(np.float32)
+        elif kind == 2:    # almost quadratic in y
+            pts = (rng.rand(4, 2) * 100).astype(np.float32)
+            pts[3, 1] = pts[0, 1] + 3 * (pts[2, 1] - pts[1, 1]) + np.float32(rng.randn() * 1e-4)
+        elif kind == 3:    # almost horizontal
+            pts = (rng.rand(4, 2) * 100).astype(np.float32)
+            pts[:, 1] = np.float32(40.0) + (rng.randn(4) * 1e-3).astype(np.float32)
+        elif kind == 4:    # monotone, long
+            pts = np.stack([rng.rand(4) * 500, np.sort(rng.rand(4) * 500)], axis=1).astype(np.float32)
+        else:              # loop / cusp
+            pts = np.asarray([[10, 10], [90, 80], [10, 80], [90, 10]], np.float32) + (rng.randn(4, 2) * 3).astype(np.float32)
+        n = 3000
+        if kind == 1:
+            xs = rng.randint(0, 128, n) * 0.5 + 0.25
+            ys = rng.randint(0, 128, n) * 0.5 + (0.25 if c % 12 == 1 else 0.0)     # on and off the control points' rows
+        else:
+            lo, hi = pts.min(0) - 5, pts.max(0) + 5
+            xs = rng.rand(n) * (hi[0] - lo[0]) + lo[0]
+            ys = rng.rand(n) * (hi[1] - lo[1]) + lo[1]
+            # samples exactly at the y of control points and of the curve's end points
+            ys[:8] = np.repeat(pts[:, 1], 2)
+        xy = np.stack([xs, ys], axis=1).astype(np.float32)
+        out = (ctypes.c_longlong * 2)()
+        lib.emul_winding_fast_check(np.ascontiguousarray(pts.reshape(-1)).ctypes.data_as(fp), np.ascontiguousarray(xy).ctypes.data_as(fp), n, out)
+        tot += n; ans += out[0]; bad += out[1]
+        if kind in (0, 1, 4):
+            common[0] += n; common[1] += out[0]
+    assert bad == 0, (bad, ans, tot)
+    assert ans >= 0.7 * tot, (ans, tot)                 # (the almost-quadratic kind never takes the fast form)
+    assert common[1] >= 0.97 * common[0], common
