@@ -23,7 +23,7 @@ struct BuildView {
     float *seg_cdf, *seg_pmf; int *seg_point_id;
     // per instance / group / primitive
     InstInfo *insts; GroupInfo *groups;
-    F4 *prim_p01, *prim_p23, *prim_rad; Box *prim_box; float *prim_thick; PrimMeta *prim_meta; Box *prim_cbox; Box *prim_cbox_pf; F4 *prim_cap; PrimQuintic *prim_quint;
+    F4 *prim_p01, *prim_p23, *prim_rad; Box *prim_box; float *prim_thick; PrimMeta *prim_meta; Box *prim_cbox; Box *prim_cbox_pf; F4 *prim_cap; PrimQuintic *prim_quint; PrimWindCert *prim_wcert;
     float *shape_cdf, *shape_pmf;
     int *error_flag; float *total_length;
 };
@@ -369,6 +369,11 @@ DVG_HD_NOINLINE void build_prim(const BuildView &bv, int e_batch) {
         const int pt0 = tf & DVG_PF_TYPE_MASK;
         if (has_stroke && !has_fill && (gi.flags & DVG_GF_IDENTITY) && (pt0 == PRIM_CUBIC || pt0 == PRIM_QUAD) && !(tf & DVG_PF_APPROX))
             tf |= DVG_PF_TIGHT;
+    }
+    if ((tf & DVG_PF_TYPE_MASK) == PRIM_CUBIC && has_fill) {   // winding certificate of the classifier (dvg_geom.cuh)
+        PrimWindCert wc;
+        tf |= prim_wind_cert(mk2(p01.x, p01.y), mk2(p01.z, p01.w), mk2(p23.x, p23.y), mk2(p23.z, p23.w), wc);
+        bv.prim_wcert[e] = wc;
     }
     pm.type_flags = tf;
     bv.prim_p01[e] = p01; bv.prim_p23[e] = p23; bv.prim_rad[e] = rad;

@@ -545,8 +545,11 @@ DVG_HD_NOINLINE int cubic_winding_exact(F2 p0, F2 p1, F2 p2, F2 p3, F2 pt) {
 // 0 and 1, |tp| and |dy| 1e-7 (relative) away from 0 -- which also excludes near-double roots --, the Newton
 // converged.  Anything else (about 1% of the pairs of an SVG asset rendered on a regular sample grid) returns false and
 // takes the reference's operation sequence.
-DVG_HD bool cubic_winding_fast(F2 p0, F2 p1, F2 p2, F2 p3, F2 pt, int *w_out) {
-#if defined(DVG_FQ_ISOL)
+// `shortcut`: also try the no-root answer below (worth it where the lanes of a warp test the SAME segment -- the prefiltered
+// kernels: -6% at flower.svg --, not in the pair-per-thread kernel of the sampled path, where it only adds divergence: +3%
+// at tiger.svg).
+DVG_HD bool cubic_winding_fast(F2 p0, F2 p1, F2 p2, F2 p3, F2 pt, int *w_out, bool shortcut = true) {
+#if defined(DVG_FQ_ISOL) && !defined(DVG_WINDING_EXACT_ONLY)
     const float cx3 = -p0.x + 3 * p1.x - 3 * p2.x + p3.x, cx2 = 3 * p0.x - 6 * p1.x + 3 * p2.x, cx1 = -3 * p0.x + 3 * p1.x;
     const float cy3 = -p0.y + 3 * p1.y - 3 * p2.y + p3.y, cy2 = 3 * p0.y - 6 * p1.y + 3 * p2.y, cy1 = -3 * p0.y + 3 * p1.y;
     const double a = (double)cy3, b = (double)cy2, c = (double)cy1, d = (double)(p0.y - pt.y);
@@ -562,6 +565,35 @@ DVG_HD bool cubic_winding_fast(F2 p0, F2 p1, F2 p2, F2 p3, F2 pt, int *w_out) {
         // reference's roots within ~1e-9 of the true ones (the margins below are 1e-7)
         const double thr_a2 = fmax(1e-10 * a * a, 1e-14 * b * b);
         if (!(fabs(R2 - Q3) * (a * a) > thr_a2 * (R2 + fabs(Q3)))) return false;
+    }
+    const double dy_scale = (double)(fabsf(cy1) + fabsf(cy2) + fabsf(cy3));
+    // The whole segment to the right of the sample and y strictly monotone on [0, 1]: every crossing counts (tp > 0) and
+    // there is exactly one if pt.y lies between the end points' y, none if it lies outside: no root needed.  Margins:
+    // |y'| >= 1e-6 of its scale on [0, 1] (end values and, when the vertex of y' falls inside, the vertex value), pt.y
+    // 1e-5 of that scale away from both end points (the root is then > 3e-6 away from 0 and 1), the sample 1e-6 left
+    // of the control polygon.
+    {
+        const float min_x = fminf(fminf(p0.x, p1.x), fminf(p2.x, p3.x));
+        if (shortcut && pt.x < min_x - 1e-6f * (1.f + fabsf(pt.x))) {
+            const double d0 = c, d1 = 3.0 * a + 2.0 * b + c;     // y'(0), y'(1)
+            const double m = 1e-6 * dy_scale;
+            bool mono = (d0 > m && d1 > m) || (d0 < -m && d1 < -m);
+            if (mono) {
+                const double tv = -b / (3.0 * a);                 // vertex of y'
+                if (tv > -0.01 && tv < 1.01) {
+                    const double dv = c - b * b / (3.0 * a);
+                    mono = d0 > 0 ? dv > m : dv < -m;
+                }
+            }
+            if (mono) {
+                const double e0 = d, e1 = a + b + c + d;      // y(0) - pt.y, y(1) - pt.y of the polynomial the reference solves
+                const double my = 1e-5 * dy_scale;
+                if (fabs(e0) > my && fabs(e1) > my) {
+                    *w_out = ((e0 < 0) != (e1 < 0)) ? (d0 > 0 ? 1 : -1) : 0;
+                    return true;
+                }
+            }
+        }
     }
     const double lo = -0.01, hi = 1.01;          // roots outside are clearly outside [0, 1]
     // monotone pieces: break the window at the critical points of y (float precision is enough for a break point: two
@@ -579,7 +611,6 @@ DVG_HD bool cubic_winding_fast(F2 p0, F2 p1, F2 p2, F2 p3, F2 pt, int *w_out) {
         if (t2 > lo && t2 < hi && t2 > t1) brk[nb++] = t2;
     }
     brk[nb++] = hi;
-    const double dy_scale = (double)(fabsf(cy1) + fabsf(cy2) + fabsf(cy3));
     int w = 0;
     double yu = fma(fma(fma(a, lo, b), lo, c), lo, d);
     for (int k = 0; k + 1 < nb; k++) {
@@ -628,8 +659,57 @@ DVG_HD bool cubic_winding_fast(F2 p0, F2 p1, F2 p2, F2 p3, F2 pt, int *w_out) {
 #endif
 }
 
+// The no-root answer of cubic_winding_fast with its sample-independent part formed once per primitive, for the
+// CLASSIFIER (dvg_wave.cu): all lanes of a warp test the same segment there, so answering a winding test in place costs a
+// dozen FP64 operations and saves a 16-byte pair record written, read and solved later -- at tiger.svg the winding pairs
+// were 5 GB of queue traffic per step.  Valid for primitives flagged DVG_PF_YMONO (y strictly monotone on [0, 1] by
+// the margins of cubic_winding_fast, leading coefficient not small).
+struct alignas(16) PrimWindCert {
+    double Q3, R0, K, thr, s;     // Qn^3; Rn = R0 + K d; threshold on the relative discriminant; a + b + c
+    float p0y, my;                // d = p0y - pt.y; margin of pt.y against the end points
+};
+// returns the flags to add to the primitive (0, or DVG_PF_YMONO [| DVG_PF_YUP])
+DVG_HD int prim_wind_cert(F2 p0, F2 p1, F2 p2, F2 p3, PrimWindCert &k) {
+    const float cy3 = -p0.y + 3 * p1.y - 3 * p2.y + p3.y, cy2 = 3 * p0.y - 6 * p1.y + 3 * p2.y, cy1 = -3 * p0.y + 3 * p1.y;
+    const double a = (double)cy3, b = (double)cy2, c = (double)cy1;
+    k.Q3 = k.R0 = k.K = k.thr = k.s = 0.0; k.p0y = p0.y; k.my = 0.f;
+    if (!(fabs(a) >= 1e-5f)) return 0;
+    const double dy_scale = (double)(fabsf(cy1) + fabsf(cy2) + fabsf(cy3));
+    const double d0 = c, d1 = 3.0 * a + 2.0 * b + c;
+    const double m = 1e-6 * dy_scale;
+    bool mono = (d0 > m && d1 > m) || (d0 < -m && d1 < -m);
+    if (mono) {
+        const double tv = -b / (3.0 * a);
+        if (tv > -0.01 && tv < 1.01) {
+            const double dv = c - b * b / (3.0 * a);
+            mono = d0 > 0 ? dv > m : dv < -m;
+        }
+    }
+    if (!mono) return 0;
+    const double Qn = (b * b - 3.0 * a * c) * (1.0 / 9.0);
+    k.Q3 = Qn * Qn * Qn;
+    k.R0 = (2.0 * b * b * b - 9.0 * a * b * c) * (1.0 / 54.0);
+    k.K = 0.5 * a * a;
+    k.thr = fmax(1e-10, 1e-14 * (b * b) / (a * a));
+    k.s = a + b + c;
+    k.my = (float)(1e-5 * dy_scale) * 1.0001f + 1e-30f;    // (rounded up: never below the double margin)
+    return DVG_PF_YMONO | (d0 > 0 ? DVG_PF_YUP : 0);
+}
+// The classifier's test: true when the winding contribution of the flagged segment is certain (*w = -1, 0, +1).
+// `box_x0` = the smallest x of the control points (the primitive's leaf box).
+DVG_HD bool wind_cert_answer(const PrimWindCert &k, bool up, float box_x0, F2 pt, int *w) {
+    if (!(pt.x < box_x0 - 1e-6f * (1.f + fabsf(pt.x)))) return false;
+    const double d = (double)(k.p0y - pt.y);
+    const double Rn = k.R0 + k.K * d, R2 = Rn * Rn;
+    if (!(fabs(R2 - k.Q3) > k.thr * (R2 + fabs(k.Q3)))) return false;
+    const double e1 = k.s + d, my = (double)k.my;
+    if (!(fabs(d) > my && fabs(e1) > my)) return false;
+    *w = ((d < 0) != (e1 < 0)) ? (up ? 1 : -1) : 0;
+    return true;
+}
+
 // winding_number.h:62-156 per leaf type + 9-31, 176-186 for the closed-form shapes.
-DVG_HD_NOINLINE int prim_winding(int type, F4 p01, F4 p23, F2 pt) {
+DVG_HD_NOINLINE int prim_winding(int type, F4 p01, F4 p23, F2 pt, bool shortcut = true) {
     switch (type) {
         case PRIM_LINE: {
             F2 p0 = mk2(p01.x, p01.y), p1 = mk2(p01.z, p01.w);
@@ -662,7 +742,7 @@ DVG_HD_NOINLINE int prim_winding(int type, F4 p01, F4 p23, F2 pt) {
         case PRIM_CUBIC: {
             const F2 p0 = mk2(p01.x, p01.y), p1 = mk2(p01.z, p01.w), p2 = mk2(p23.x, p23.y), p3 = mk2(p23.z, p23.w);
             int wf;
-            if (cubic_winding_fast(p0, p1, p2, p3, pt, &wf)) return wf;
+            if (cubic_winding_fast(p0, p1, p2, p3, pt, &wf, shortcut)) return wf;
             return cubic_winding_exact(p0, p1, p2, p3, pt);
         }
         case PRIM_CIRCLE:

@@ -29,6 +29,15 @@ void prof_end(cudaStream_t st);
         ::dvg::g_launch_count++;                                      \
     } while (0)
 
+// the same with the reported name given apart (template instantiations with several arguments do not survive as ONE macro argument)
+#define DVG_LAUNCH_AS(name, kernel, grid, block, smem, stream, ...)   \
+    do {                                                              \
+        if (::dvg::g_profile_on) ::dvg::prof_begin(name, stream);     \
+        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);   \
+        if (::dvg::g_profile_on) ::dvg::prof_end(stream);             \
+        ::dvg::g_launch_count++;                                      \
+    } while (0)
+
 struct BinBuild {
     int width, height, tile_w, tile_h, tiles_x, tiles_y;
     int batch;      // scenes of one topology back to back (SceneView): tiles_x * tiles_y tiles each; row ranges only with batch 1

@@ -14,6 +14,9 @@
 namespace dvg {
 
 constexpr int PB = 256;  // threads per block
+#ifndef DVG_PF_MINB
+#define DVG_PF_MINB 2
+#endif
 
 DVG_D PrimRef load_prim(const SceneView &sc, int e) {
     PrimRef pr;
@@ -28,7 +31,7 @@ DVG_D PrimRef load_prim(const SceneView &sc, int e) {
 }
 
 template <bool BACKWARD>
-__global__ void __launch_bounds__(PB) k_render_pf(SceneView sc, BinView bins, RenderArgs ra) {
+__global__ void __launch_bounds__(PB, DVG_PF_MINB) k_render_pf(SceneView sc, BinView bins, RenderArgs ra) {
     // gradients go straight to one of the private copies of the gradient buffer (dvg_kernel_util.cuh grad_replica):
     // the per-block shared-memory hash + barrier + flush this kernel used before was 40% of its time at 2048^2
     const GlobalSink sk{BACKWARD ? grad_replica(ra) : nullptr};

@@ -21,6 +21,8 @@ enum PrimType { PRIM_LINE = 0, PRIM_QUAD = 1, PRIM_CUBIC = 2, PRIM_CIRCLE = 3, P
 #define DVG_PF_APPROX 0x40    // use_distance_approx
 #define DVG_PF_FIRST 0x80     // first primitive of its shape instance
 #define DVG_PF_GFIRST 0x100   // first primitive of its group
+#define DVG_PF_YMONO 0x400    // filled cubic whose y(t) is strictly monotone on [0, 1] by a margin: prim_wcert is valid
+#define DVG_PF_YUP 0x800      // ... and increasing
 #define DVG_PF_TIGHT 0x200    // stroke-only curved primitive in an untransformed group: tiles are binned against its
                               // polyline bracket (prim_cap) instead of its bounding box (dvg_build.cu k_bin)
 
@@ -75,6 +77,7 @@ struct InstInfo {
 };
 
 struct PrimQuintic;
+struct PrimWindCert;
 
 // Everything the kernels need, passed by value.
 //
@@ -104,7 +107,8 @@ struct SceneView {
     const Box *prim_cbox;  // canvas-space conservative bound of where this primitive can matter (binning only)
     const Box *prim_cbox_pf;  // same for the prefiltering path (binning only)
     const F4 *prim_cap;    // DVG_CAP_F4 float4 per primitive: conservative stroke-reject capsules (dvg_geom.cuh)
-    const PrimQuintic *prim_quint;   // cubic segments: the sample-independent part of the closest-point quintic (dvg_geom.cuh)
+    const PrimQuintic *prim_quint;
+    const PrimWindCert *prim_wcert;  // filled cubic segments flagged DVG_PF_YMONO: what the classifier needs to answer their winding test itself (dvg_geom.cuh)   // cubic segments: the sample-independent part of the closest-point quintic (dvg_geom.cuh)
     const InstInfo *insts;
     const GroupInfo *groups;
     // boundary sampling tables (scene.cpp:207-333)

@@ -103,7 +103,10 @@ __device__ __noinline__ void wave_exact_in_place(const SceneView &sc, const Wave
 // geometry asked for more exact tests than any pass before it): every pair is then answered in the classifying lane and
 // the result words of the whole pass are rewritten.  Keeping this out of the hot form keeps that one free of calls
 // (the call alone cost it 300 bytes of spills and 60% of its speed).
-template <bool INPLACE>
+// FILLS: the scene has filled groups.  The winding test of a y-monotone cubic (DVG_PF_YMONO) whose control points all lie
+// to the right of the sample is answered here from the primitive's PrimWindCert record (dvg_geom.cuh wind_cert_answer:
+// a dozen FP64 operations, warp-coherent because all lanes test the same segment) instead of being queued.
+template <bool INPLACE, bool FILLS>
 DVG_D void wave_classify(const SceneView &sc, const BinView &bins, const WaveView &wv, int tile, int64_t cb,
                          F2 cpt, bool active, WaveScratch &ws, bool fast_accept) {
     const unsigned FULL = 0xffffffffu;
@@ -127,6 +130,7 @@ DVG_D void wave_classify(const SceneView &sc, const BinView &bins, const WaveVie
             thick = sc.prim_thick[e];
         }
         unsigned need_s = 0, need_f = 0;
+        unsigned wn0 = 0u, wn1 = 0u, wn2 = 0u, wn3 = 0u;   // winding nibbles answered here
         for (int k = 0; k < n; k++) {
             PrimRef pr;
             pr.box.x0 = __shfl_sync(FULL, box.x0, k); pr.box.y0 = __shfl_sync(FULL, box.y0, k);
@@ -135,12 +139,22 @@ DVG_D void wave_classify(const SceneView &sc, const BinView &bins, const WaveVie
             pr.tf = __shfl_sync(FULL, tf, k); pr.inst = __shfl_sync(FULL, inst, k); pr.group = __shfl_sync(FULL, group, k);
             const int nd = ct.template step<TM_CLASSIFY>(sc, pr);
             need_s |= (unsigned)(nd & 1) << k;
-            need_f |= (unsigned)((nd >> 1) & 1) << k;
+            bool nf = ((nd >> 1) & 1) != 0;
+            if (FILLS && (pr.tf & DVG_PF_YMONO)) {   // (uniform: every lane holds the same candidate)
+                const int ek = __shfl_sync(FULL, e, k);
+                int w = 0;
+                if (nf && wind_cert_answer(sc.prim_wcert[ek], (pr.tf & DVG_PF_YUP) != 0, pr.box.x0, ct.lpt, &w)) {
+                    nf = false;
+                    const unsigned bits = (unsigned)(w & 15) << (4 * (k & 7));
+                    if (k < 8) wn0 |= bits; else if (k < 16) wn1 |= bits; else if (k < 24) wn2 |= bits; else wn3 |= bits;
+                }
+            }
+            need_f |= (unsigned)(nf ? 1u : 0u) << k;
         }
         ws.hit[lane] = 0u;
         const int64_t word0 = (cb + c) * 32;
-        if (wv.wind) {   // zeroed first: a pair that finds its queue full is answered in place and ORs into these words
-            uint4 z; z.x = z.y = z.z = z.w = 0u;
+        if (FILLS) {   // written first: the exact tests (and a pair that finds its queue full and is answered in place) OR into these words
+            uint4 z; z.x = wn0; z.y = wn1; z.z = wn2; z.w = wn3;
             reinterpret_cast<uint4 *>(wv.wind)[word0 + lane] = z;
         }
         __syncwarp();
@@ -238,7 +252,7 @@ DVG_D PixelItem pixel_item(const BinView &bins, const RenderArgs &ra, const Wave
 
 DVG_D bool wave_overflowed(const WaveView &wv) { return wv.counters[0] > wv.cap_s || wv.counters[1] > wv.cap_f; }
 
-template <bool INPLACE>
+template <bool INPLACE, bool FILLS>
 __global__ void __launch_bounds__(WB, DVG_WB_MIN) k_wave_classify_px(SceneView sc, BinView bins, RenderArgs ra, WaveView wv, int num_items) {
     __shared__ WaveScratch s_ws[WNW];
     if (INPLACE && !wave_overflowed(wv)) return;
@@ -248,7 +262,7 @@ __global__ void __launch_bounds__(WB, DVG_WB_MIN) k_wave_classify_px(SceneView s
         if (pi.active)
             sample_position(sc.canvas_w, sc.canvas_h, ra.width, ra.height, ra.nsx, ra.nsy, ra.seeds ? ra.seeds[pi.scene] : ra.seed,
                             ra.use_prefiltering != 0, pi.x, pi.y, pi.sx, pi.sy, pi.idx, pt, cpt);
-        wave_classify<INPLACE>(sc, bins, wv, pi.tile, pi.cb, cpt, pi.active, s_ws[threadIdx.x >> 5], (ra.flags & DVG_RF_FAST_ACCEPT) != 0);
+        wave_classify<INPLACE, FILLS>(sc, bins, wv, pi.tile, pi.cb, cpt, pi.active, s_ws[threadIdx.x >> 5], (ra.flags & DVG_RF_FAST_ACCEPT) != 0);
     }
 }
 
@@ -291,7 +305,7 @@ DVG_D EdgeLane edge_lane(const SceneView &sc, const RenderArgs &ra, const Bounda
     return el;
 }
 
-template <bool INPLACE>
+template <bool INPLACE, bool FILLS>
 __global__ void __launch_bounds__(WB, DVG_WB_MIN) k_wave_classify_edge(SceneView sc, BinView bins, RenderArgs ra, BoundaryWork bw, WaveView wv) {
     __shared__ WaveScratch s_ws[WNW];
     if (INPLACE && !wave_overflowed(wv)) return;
@@ -300,9 +314,15 @@ __global__ void __launch_bounds__(WB, DVG_WB_MIN) k_wave_classify_edge(SceneView
     for (int item = blockIdx.x * WNW + (threadIdx.x >> 5); item < num_items; item += gridDim.x * WNW) {
         const EdgeItem ei = edge_item(bins, bw, wv, item);
         const EdgeLane el = edge_lane(sc, ra, bw, ei);
-        wave_classify<INPLACE>(sc, bins, wv, ei.tile, ei.cb, el.cpt, el.active, s_ws[threadIdx.x >> 5], (ra.flags & DVG_RF_FAST_ACCEPT) != 0);
+        wave_classify<INPLACE, FILLS>(sc, bins, wv, ei.tile, ei.cb, el.cpt, el.active, s_ws[threadIdx.x >> 5], (ra.flags & DVG_RF_FAST_ACCEPT) != 0);
     }
 }
+
+// (the launch macro takes one token per argument: names for the instantiations)
+constexpr auto kc_px = k_wave_classify_px<false, false>, kc_px_fills = k_wave_classify_px<false, true>;
+constexpr auto kr_px = k_wave_classify_px<true, false>, kr_px_fills = k_wave_classify_px<true, true>;
+constexpr auto kc_edge = k_wave_classify_edge<false, false>, kc_edge_fills = k_wave_classify_edge<false, true>;
+constexpr auto kr_edge = k_wave_classify_edge<true, false>, kr_edge_fills = k_wave_classify_edge<true, true>;
 
 // ------------------------------------------------------------------------------------------ W2
 // Exact stroke tests of the queued pairs (within_distance.h:119-272 for cubic segments).  One WARP takes 64 pairs at a
@@ -488,7 +508,7 @@ __global__ void __launch_bounds__(128) k_wave_solve_fill(SceneView sc, WaveView 
         WavePair p = wv.pairs_f[i];
         const int ptype = (int)((unsigned)p.prim >> 28);
         p.prim &= 0x0fffffff;
-        const int w = prim_winding(ptype, sc.prim_p01[p.prim], sc.prim_p23[p.prim], mk2(p.x, p.y));
+        const int w = prim_winding(ptype, sc.prim_p01[p.prim], sc.prim_p23[p.prim], mk2(p.x, p.y), false);
         const unsigned k = p.ref & 31u;
         if (w != 0) atomicOr(&wv.wind[(size_t)(p.ref >> 5) * 4 + (k >> 3)], (unsigned)(w & 15) << (4 * (k & 7)));
     }
@@ -763,12 +783,15 @@ int wave_edge_samples_per_item() { return W_EDGE_SPI; }
 void launch_wave_classify_px(const SceneView &sc, const BinView &bins, const RenderArgs &ra, const WaveView &wv, cudaStream_t st) {
     const int items = wave_pixel_items(bins, ra);
     if (items <= 0) return;
-    DVG_LAUNCH(k_wave_classify_px<false>, dim3((items + WNW - 1) / WNW), dim3(WB), 0, st, sc, bins, ra, wv, items);
+    if (wv.wind) DVG_LAUNCH_AS("k_wave_classify_px<false>", kc_px_fills, dim3((items + WNW - 1) / WNW), dim3(WB), 0, st, sc, bins, ra, wv, items);
+    else DVG_LAUNCH_AS("k_wave_classify_px<false>", kc_px, dim3((items + WNW - 1) / WNW), dim3(WB), 0, st, sc, bins, ra, wv, items);
 }
 void launch_wave_retry_px(const SceneView &sc, const BinView &bins, const RenderArgs &ra, const WaveView &wv, cudaStream_t st) {
     const int items = wave_pixel_items(bins, ra);
     if (items <= 0) return;
-    DVG_LAUNCH(k_wave_classify_px<true>, dim3(std::min((items + WNW - 1) / WNW, g_num_sms * DVG_WB_MIN)), dim3(WB), 0, st, sc, bins, ra, wv, items);
+    const dim3 grid(std::min((items + WNW - 1) / WNW, g_num_sms * DVG_WB_MIN));
+    if (wv.wind) DVG_LAUNCH_AS("k_wave_classify_px<true>", kr_px_fills, grid, dim3(WB), 0, st, sc, bins, ra, wv, items);
+    else DVG_LAUNCH_AS("k_wave_classify_px<true>", kr_px, grid, dim3(WB), 0, st, sc, bins, ra, wv, items);
 }
 
 // Grids are a fixed multiple of the SM count (bounded by the queue capacity); the counts stay on the device.
@@ -806,11 +829,14 @@ void launch_wave_boundary_sort(const SceneView &sc, const BinView &bins, const R
 
 void launch_wave_classify_edge(const SceneView &sc, const BinView &bins, const RenderArgs &ra, const BoundaryWork &bw,
                                const WaveView &wv, cudaStream_t st) {
-    DVG_LAUNCH(k_wave_classify_edge<false>, dim3((bw.max_blocks + WNW - 1) / WNW), dim3(WB), 0, st, sc, bins, ra, bw, wv);
+    if (wv.wind) DVG_LAUNCH_AS("k_wave_classify_edge<false>", kc_edge_fills, dim3((bw.max_blocks + WNW - 1) / WNW), dim3(WB), 0, st, sc, bins, ra, bw, wv);
+    else DVG_LAUNCH_AS("k_wave_classify_edge<false>", kc_edge, dim3((bw.max_blocks + WNW - 1) / WNW), dim3(WB), 0, st, sc, bins, ra, bw, wv);
 }
 void launch_wave_retry_edge(const SceneView &sc, const BinView &bins, const RenderArgs &ra, const BoundaryWork &bw,
                             const WaveView &wv, cudaStream_t st) {
-    DVG_LAUNCH(k_wave_classify_edge<true>, dim3(std::min((bw.max_blocks + WNW - 1) / WNW, g_num_sms * DVG_WB_MIN)), dim3(WB), 0, st, sc, bins, ra, bw, wv);
+    const dim3 grid(std::min((bw.max_blocks + WNW - 1) / WNW, g_num_sms * DVG_WB_MIN));
+    if (wv.wind) DVG_LAUNCH_AS("k_wave_classify_edge<true>", kr_edge_fills, grid, dim3(WB), 0, st, sc, bins, ra, bw, wv);
+    else DVG_LAUNCH_AS("k_wave_classify_edge<true>", kr_edge, grid, dim3(WB), 0, st, sc, bins, ra, bw, wv);
 }
 
 void launch_wave_composite_edge(const SceneView &sc, const BinView &bins, const RenderArgs &ra, const BoundaryWork &bw,

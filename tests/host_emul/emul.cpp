@@ -47,6 +47,7 @@ struct HostScene {
     std::vector<GroupInfo> groups;
     std::vector<F4> p01, p23, rad, cap;
     std::vector<PrimQuintic> quint;
+    std::vector<PrimWindCert> wcert;
     std::vector<PrimMeta> meta;
     int error_flag = 0;
     float total_length = 0;
@@ -86,7 +87,7 @@ void build(HostScene &hs, const int32_t *topo, const float *params) {
     hs.seg_cdf.resize(nsg); hs.seg_pmf.resize(nsg); hs.seg_point_id.resize(nsg);
     hs.insts.resize(ni); hs.groups.resize(ng);
     hs.p01.resize(np); hs.p23.resize(np); hs.rad.resize(np); hs.prim_box.resize(np); hs.prim_thick.resize(np);
-    hs.meta.resize(np); hs.prim_cbox.resize(np); hs.prim_cbox_pf.resize(np); hs.cap.resize((size_t)np * DVG_CAP_F4); hs.quint.resize(np); hs.shape_cdf.resize(ni); hs.shape_pmf.resize(ni);
+    hs.meta.resize(np); hs.prim_cbox.resize(np); hs.prim_cbox_pf.resize(np); hs.cap.resize((size_t)np * DVG_CAP_F4); hs.quint.resize(np); hs.wcert.resize(np); hs.shape_cdf.resize(ni); hs.shape_pmf.resize(ni);
     BuildView bv;
     bv.canvas_w = t[DVG_H_CANVAS_W]; bv.canvas_h = t[DVG_H_CANVAS_H];
     bv.num_shapes = ns; bv.num_groups = ng; bv.num_insts = ni; bv.num_prims = np;
@@ -97,7 +98,7 @@ void build(HostScene &hs, const int32_t *topo, const float *params) {
     bv.seg_cdf = hs.seg_cdf.data(); bv.seg_pmf = hs.seg_pmf.data(); bv.seg_point_id = hs.seg_point_id.data();
     bv.insts = hs.insts.data(); bv.groups = hs.groups.data();
     bv.prim_p01 = hs.p01.data(); bv.prim_p23 = hs.p23.data(); bv.prim_rad = hs.rad.data(); bv.prim_box = hs.prim_box.data();
-    bv.prim_thick = hs.prim_thick.data(); bv.prim_meta = hs.meta.data(); bv.prim_cbox = hs.prim_cbox.data(); bv.prim_cbox_pf = hs.prim_cbox_pf.data(); bv.prim_cap = hs.cap.data(); bv.prim_quint = hs.quint.data();
+    bv.prim_thick = hs.prim_thick.data(); bv.prim_meta = hs.meta.data(); bv.prim_cbox = hs.prim_cbox.data(); bv.prim_cbox_pf = hs.prim_cbox_pf.data(); bv.prim_cap = hs.cap.data(); bv.prim_quint = hs.quint.data(); bv.prim_wcert = hs.wcert.data();
     bv.shape_cdf = hs.shape_cdf.data(); bv.shape_pmf = hs.shape_pmf.data();
     bv.error_flag = &hs.error_flag; bv.total_length = &hs.total_length;
     for (int s = 0; s < ns; s++) build_shape(bv, s);
@@ -112,7 +113,7 @@ void build(HostScene &hs, const int32_t *topo, const float *params) {
     sc.filter_radius_off = t[DVG_H_FILTER_RADIUS_OFF];
     sc.topo = t; sc.params = hs.params.data();
     sc.prim_p01 = hs.p01.data(); sc.prim_p23 = hs.p23.data(); sc.prim_rad = hs.rad.data(); sc.prim_box = hs.prim_box.data();
-    sc.prim_thick = hs.prim_thick.data(); sc.prim_meta = hs.meta.data(); sc.prim_cbox = hs.prim_cbox.data(); sc.prim_cbox_pf = hs.prim_cbox_pf.data(); sc.prim_cap = hs.cap.data(); sc.prim_quint = hs.quint.data();
+    sc.prim_thick = hs.prim_thick.data(); sc.prim_meta = hs.meta.data(); sc.prim_cbox = hs.prim_cbox.data(); sc.prim_cbox_pf = hs.prim_cbox_pf.data(); sc.prim_cap = hs.cap.data(); sc.prim_quint = hs.quint.data(); sc.prim_wcert = hs.wcert.data();
     sc.insts = hs.insts.data(); sc.groups = hs.groups.data();
     sc.shapes_length = hs.shapes_length.data(); sc.shape_cdf = hs.shape_cdf.data(); sc.shape_pmf = hs.shape_pmf.data();
     sc.seg_cdf = hs.seg_cdf.data(); sc.seg_pmf = hs.seg_pmf.data(); sc.seg_point_id = hs.seg_point_id.data();
@@ -467,16 +468,25 @@ EXPORT void emul_quintic_split_check(const float *pts8, const float *rad4, const
 }
 
 // cubic_winding_fast against cubic_winding_exact (dvg_geom.cuh): out[0] = pairs the fast form answered, out[1] = answered
-// pairs whose winding differs from the reference's operation sequence.
+// pairs whose winding differs from the reference's operation sequence; out[2], out[3]: the same for the classifier's
+// per-primitive certificate (prim_wind_cert + wind_cert_answer).
 EXPORT void emul_winding_fast_check(const float *pts8, const float *xy, int n, long long *out) {
     const F2 p0 = mk2(pts8[0], pts8[1]), p1 = mk2(pts8[2], pts8[3]), p2 = mk2(pts8[4], pts8[5]), p3 = mk2(pts8[6], pts8[7]);
-    out[0] = out[1] = 0;
+    out[0] = out[1] = out[2] = out[3] = 0;
+    PrimWindCert wc;
+    const int flags = prim_wind_cert(p0, p1, p2, p3, wc);      // the classifier's per-primitive certificate (dvg_wave.cu)
+    const float box_x0 = rminf(rminf(p0.x, p1.x), rminf(p2.x, p3.x));
     for (int i = 0; i < n; i++) {
         const F2 pt = mk2(xy[2 * i], xy[2 * i + 1]);
         int wf = 0;
         if (cubic_winding_fast(p0, p1, p2, p3, pt, &wf)) {
             out[0]++;
             if (wf != cubic_winding_exact(p0, p1, p2, p3, pt)) out[1]++;
+        }
+        int wcw = 0;
+        if ((flags & DVG_PF_YMONO) && wind_cert_answer(wc, (flags & DVG_PF_YUP) != 0, box_x0, pt, &wcw)) {
+            out[2]++;
+            if (wcw != cubic_winding_exact(p0, p1, p2, p3, pt)) out[3]++;
         }
     }
 }

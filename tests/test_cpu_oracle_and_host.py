@@ -421,6 +421,7 @@ def test_fast_cubic_winding_agrees_with_the_reference_sequence_whenever_it_answe
     rng = np.random.RandomState(33)
     tot = ans = bad = 0
     common = [0, 0]      # random / round-coordinate / monotone cubics: what assets are made of
+    cert = [0, 0]        # pairs answered by the classifier's per-primitive certificate / of them wrong
     for c in range(600):
         kind = c % 6
         if kind == 0:      # random
@@ -448,11 +449,16 @@ def test_fast_cubic_winding_agrees_with_the_reference_sequence_whenever_it_answe
             # samples exactly at the y of control points and of the curve's end points
             ys[:8] = np.repeat(pts[:, 1], 2)
         xy = np.stack([xs, ys], axis=1).astype(np.float32)
-        out = (ctypes.c_longlong * 2)()
+        if kind == 4:      # monotone: a share of the samples left of the control polygon (what the classifier's certificate answers)
+            xs[: n // 2] = pts[:, 0].min() - 1.0 - rng.rand(n // 2) * 40
+            xy = np.stack([xs, ys], axis=1).astype(np.float32)
+        out = (ctypes.c_longlong * 4)()
         lib.emul_winding_fast_check(np.ascontiguousarray(pts.reshape(-1)).ctypes.data_as(fp), np.ascontiguousarray(xy).ctypes.data_as(fp), n, out)
         tot += n; ans += out[0]; bad += out[1]
+        cert[0] += out[2]; cert[1] += out[3]
         if kind in (0, 1, 4):
             common[0] += n; common[1] += out[0]
     assert bad == 0, (bad, ans, tot)
+    assert cert[1] == 0 and cert[0] > 50000, cert           # the certificate: never wrong, and exercised
     assert ans >= 0.7 * tot, (ans, tot)                 # (the almost-quadratic kind never takes the fast form)
     assert common[1] >= 0.97 * common[0], common

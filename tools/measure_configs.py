@@ -4,9 +4,11 @@
     python tools/measure_configs.py [--cpu]      # --cpu also times the reference CPU path on a bounded sample
 
   C1  single circle 256^2, 2x2 spp              (launch-latency floor)
-  C2' 1024 closed cubic blobs 512^2, 4x4 spp    (fill-heavy proxy of tiger.svg)
-  C4' same blobs at 2048^2, 2x2 spp, prefiltered (proxy of flower.svg; no boundary pass)
-  C5  512 scenes x 16 strokes 64^2, 2x2 spp      (one native scene per batch element, sequential)
+  C2  tiger.svg at its own size, 4x4 spp         (scene pack of tests/golden_svg)
+  C2' 1024 closed cubic blobs 512^2, 4x4 spp    (synthetic fill-heavy scene)
+  C4  flower.svg 2048^2, 2x2 spp, prefiltered    (scene pack of tests/golden_svg; no boundary pass)
+  C4' the blobs at 2048^2, 2x2 spp, prefiltered
+  C5  512 scenes x 16 strokes 64^2, 2x2 spp      (512 native scenes in a loop, then ONE batch scene)
 Prints one line per config: ms per fwd+bwd (CUDA events, median of 5 after 2 warm-ups)."""
 import ctypes
 import os
@@ -26,7 +28,10 @@ from diffvg_b200 import _native as n  # noqa: E402
 
 class Scene:
     def __init__(self, scene):
-        self.topo, self.params = util.pack(scene)
+        if isinstance(scene, tuple):
+            self.topo, self.params = util.pack(scene)
+        else:   # a scene pack of tests/golden_svg (topology + parameters of a parsed SVG asset)
+            self.topo, self.params = np.ascontiguousarray(scene['topo'], np.int32), np.ascontiguousarray(scene['params'], np.float32)
         self.h = ctypes.c_void_p()
         n.check(n.lib.dvg_scene_create(self.topo.ctypes.data, self.topo.shape[0], 0, ctypes.byref(self.h)))
         self.p = torch.from_numpy(self.params).cuda()
@@ -58,9 +63,13 @@ def main():
     import warnings
     warnings.simplefilter('ignore')
     rows = []
+    assets = {k: np.load(os.path.join(ROOT, 'tests', 'golden_svg', k + '.npz')) for k in ('tiger', 'flower')}
+    tiger_wh = (int(assets['tiger']['topo'][1]), int(assets['tiger']['topo'][2]))
     for name, scene, (W, H, nsx, nsy, pf) in (
             ('C1 single_circle 256^2 2x2', scenes.single_circle(), (256, 256, 2, 2, 0)),
+            ('C2 tiger.svg %dx%d 4x4' % tiger_wh, assets['tiger'], tiger_wh + (4, 4, 0)),
             ("C2' blobs1024 512^2 4x4", scenes.blobs(), (512, 512, 4, 4, 0)),
+            ('C4 flower.svg 2048^2 2x2 prefilter', assets['flower'], (2048, 2048, 2, 2, 1)),
             ("C4' blobs1024 2048^2 2x2 prefilter", scenes.blobs(), (2048, 2048, 2, 2, 1))):
         s = Scene(scene)
         img = torch.empty(H, W, 4, device='cuda'); dimg = torch.empty_like(img)
