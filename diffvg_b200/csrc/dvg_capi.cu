@@ -428,13 +428,13 @@ int wave_view(DvgScene *s, int64_t chunk_slots, int64_t evals, WaveView *out) {
     wave_feedback_poll(s);
     // worst case: every lane of every chunk slot asks for an exact test of all 32 candidates.  Small passes get queues
     // of that size (they can not overflow); otherwise what earlier passes asked for plus a margin, and for the first pass
-    // a guess of two stroke tests / four winding tests per evaluation
+    // a guess of three stroke tests / four winding tests per evaluation
     const int64_t worst = chunk_slots * 32 * 32;
     const int64_t lim = (int64_t)1 << 30;
     int64_t need_s, need_f;
     if (worst <= kSmallPairs) need_s = need_f = std::max<int64_t>(worst, 1);
     else {
-        need_s = s->want_s ? s->want_s + s->want_s / 8 + 4096 : std::max<int64_t>(2 * evals, 1 << 16);
+        need_s = s->want_s ? s->want_s + s->want_s / 8 + 4096 : std::max<int64_t>(3 * evals, 1 << 16);
         need_f = s->want_f ? s->want_f + s->want_f / 8 + 4096 : std::max<int64_t>(4 * evals, 1 << 16);
         need_s = std::min(std::min(need_s, worst), lim);
         need_f = std::min(std::min(need_f, worst), lim);
