@@ -186,7 +186,7 @@ def strong_scaling(dev, rank, world, barrier, max_over_ranks, steps=6, warmup=3)
     out = []
     flower = np.load(os.path.join(ROOT, 'tests', 'golden_svg', 'flower.npz'))
     cases = [('C4 flower.svg (1096 groups, 10.5 k cubics), 2048x2048, use_prefiltering, 2x2 spp, band loss, fwd+bwd', 'flower', True),
-             ('painterly 2048 strokes at 2048x2048, 2x2 spp, sampled path (boundary pass), full-image loss, fwd+bwd', 'painterly', False)]
+             ('painterly 2048 strokes at 2048x2048, 2x2 spp, sampled path (boundary pass), band loss, fwd+bwd', 'painterly', False)]
     for label, which, pf in cases:
         if which == 'flower':
             topo, params_np = flower['topo'], flower['params']
@@ -205,12 +205,10 @@ def strong_scaling(dev, rank, world, barrier, max_over_ranks, steps=6, warmup=3)
 
         def step_sharded(seed):
             params.grad = None
-            if pf:    # loss per band: no image exchange, halo rows of d_image only (sharded.py)
-                img = sharded.ShardedRenderFunction.apply(SW, SH, 2, 2, seed, None, packed, params, None, False, bands)
-                ((img - target[rb:re]).pow(2).sum() / target.numel()).backward()
-            else:
-                img = sharded.ShardedRenderFunction.apply(SW, SH, 2, 2, seed, None, packed, params, None, True, bands)
-                (img - target).pow(2).mean().backward()
+            # loss per band: no image exchange in the forward pass; backward: halo rows of d_image only on the prefiltered
+            # path, an all-gather of the d_image bands on the sampled path (its boundary samples land anywhere)
+            img = sharded.ShardedRenderFunction.apply(SW, SH, 2, 2, seed, None, packed, params, None, False, bands)
+            ((img - target[rb:re]).pow(2).sum() / target.numel()).backward()
 
         def step_single(seed):
             params.grad = None
@@ -238,13 +236,11 @@ def strong_scaling(dev, rank, world, barrier, max_over_ranks, steps=6, warmup=3)
         for rnd in range(3):
             step_sharded(100 + rnd)
             barrier()
-            ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            ea.record()
+            sharded.time_compute(True)      # the rank's own render calls only: the collectives make every rank wait for the slowest
             for i in range(2):
                 step_sharded(110 + 2 * rnd + i)
-            eb.record()
-            torch.cuda.synchronize(dev)
-            mine = torch.tensor([ea.elapsed_time(eb)], dtype=torch.float64, device=dev)
+            mine = torch.tensor([sharded.compute_ms()], dtype=torch.float64, device=dev)
+            sharded.time_compute(False)
             allt = [torch.zeros_like(mine) for _ in range(world)]
             dist.all_gather(allt, mine)
             bands = sharded.rebalance_bands(bands, [float(t.item()) for t in allt], SH, sharded.tile_height(4))

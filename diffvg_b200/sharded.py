@@ -158,6 +158,39 @@ def allgather_rows(band, bands, group=None):
     return torch.cat([buf[r, :e - b] for r, (b, e) in enumerate(bands)], dim=0)
 
 
+# Own render time of a rank (CUDA events around its dvg_render_*_rows calls): what `rebalance_bands` needs.  The step time
+# of a rank is useless for that -- the collectives make every rank wait for the slowest one.
+_TIMING = {'on': False, 'events': []}
+
+
+def time_compute(on=True):
+    """Start / stop recording the device time of this rank's own render calls inside `ShardedRenderFunction`."""
+    _TIMING['on'] = bool(on)
+    _TIMING['events'] = []
+
+
+def compute_ms():
+    """Device milliseconds this rank spent in its own render calls since `time_compute(True)` (synchronises)."""
+    torch.cuda.synchronize()
+    total = sum(a.elapsed_time(b) for a, b in _TIMING['events'])
+    _TIMING['events'] = []
+    return total
+
+
+class _timed:
+    def __enter__(self):
+        if _TIMING['on']:
+            self.a, self.b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            self.a.record()
+        return self
+
+    def __exit__(self, *exc):
+        if _TIMING['on']:
+            self.b.record()
+            _TIMING['events'].append((self.a, self.b))
+        return False
+
+
 def allreduce_gradients(d_params, group=None):
     """Sum the per-rank gradient buffers in place (the only collective on the backward path:
     num_params floats, 155 KB at the painterly config -- latency-bound on NVSwitch)."""
@@ -204,10 +237,11 @@ class ShardedRenderFunction(torch.autograd.Function):
             wide = float(getattr(packed, 'filter_radius', 0.5)) > 0.5
             # the call zeroes and fills the rows of its band; only the all-reduce of wide filters reads the other rows
             full = (torch.zeros if (wide and world > 1) else torch.empty)(height, width, 4, device=dev, dtype=torch.float32)
-            n.check(n.lib.dvg_render_forward_rows(
-                ns.handle, background_image.data_ptr() if background_image is not None else None, full.data_ptr(),
-                width, height, num_samples_x, num_samples_y, int(seed), 1 if packed.use_prefiltering else 0,
-                rb, re, stream))
+            with _timed():
+                n.check(n.lib.dvg_render_forward_rows(
+                    ns.handle, background_image.data_ptr() if background_image is not None else None, full.data_ptr(),
+                    width, height, num_samples_x, num_samples_y, int(seed), 1 if packed.use_prefiltering else 0,
+                    rb, re, stream))
             if not gather:
                 assert not wide or world == 1, 'gather=False needs a pixel filter of radius <= 0.5 (samples splat across band edges)'
                 img = full[rb:re]
@@ -264,11 +298,12 @@ class ShardedRenderFunction(torch.autograd.Function):
                 ctx.scene_version = ns.set_params(params, stream)
             d_params = torch.empty(ctx.packed.num_params, device=dev, dtype=torch.float32)
             d_bg = torch.zeros_like(bg) if bg is not None else None
-            n.check(n.lib.dvg_render_backward_rows(
-                ns.handle, bg.data_ptr() if bg is not None else None, grad_img.data_ptr(),
-                width, height, nsx, nsy, int(seed), 1 if ctx.packed.use_prefiltering else 0, rb, re,
-                d_params.data_ptr(), d_bg.data_ptr() if d_bg is not None else None,
-                rp.backward_flags(ctx.packed), stream))
+            with _timed():
+                n.check(n.lib.dvg_render_backward_rows(
+                    ns.handle, bg.data_ptr() if bg is not None else None, grad_img.data_ptr(),
+                    width, height, nsx, nsy, int(seed), 1 if ctx.packed.use_prefiltering else 0, rb, re,
+                    d_params.data_ptr(), d_bg.data_ptr() if d_bg is not None else None,
+                    rp.backward_flags(ctx.packed), stream))
             allreduce_gradients(d_params, ctx.group)
             if d_bg is not None:
                 allreduce_gradients(d_bg, ctx.group)
