@@ -90,4 +90,49 @@ DVG_D float filter_radius_grad(const SceneView &sc, const RenderArgs &ra, int x,
     return acc;
 }
 
+// The same for the BOX filter with ceil(radius) == 1, the samples of a pixel sitting in `grp` adjacent lanes (a power of
+// two; must be called by all lanes of the warp).  Box: d_compute_filter_weight does not depend on the offset (filter.h:
+// 52-57), so the sample's gradient is K * sum over the 3x3 pixels of d_weight; for the eight NEIGHBOURS a sample's filter
+// weight is 0 (it lies inside its own pixel) and d_weight reduces to (d_pixel / weight_sum) . color -- the vector
+// sum_n d_pixel_n / weight_sum_n is the PIXEL's, formed once by the lanes of the group (one neighbour each) instead of
+// eight loads and divisions per sample.  A sample on a pixel edge (or outside its own pixel's support when radius < 0.5)
+// takes the generic loop.  Summation order differs from the generic form by float rounding only (the reference adds
+// these terms with atomics in arbitrary order).
+DVG_D float filter_radius_grad_box(const SceneView &sc, const RenderArgs &ra, int x, int y, F2 pt, F4 color, bool active, int grp, int lane) {
+    const unsigned FULL = 0xffffffffu;
+    float4 V = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (active) {
+        for (int j = lane & (grp - 1); j < 8; j += grp) {
+            const int n = j < 4 ? j : j + 1;                       // 3x3 offsets without the centre
+            const int xx = x + n % 3 - 1, yy = y + n / 3 - 1;
+            if (xx >= 0 && xx < ra.width && yy >= 0 && yy < ra.height) {
+                const float ws = ra.weight_image[yy * ra.width + xx];
+                if (ws > 0) {
+                    const float4 dp = *reinterpret_cast<const float4 *>(ra.d_render_image + 4 * (yy * ra.width + xx));
+                    const float inv = ws / (ws * ws);              // (dotv * ws) / (ws * ws), diffvg.cpp:1258-1262 with fw = 0
+                    V.x += dp.x * inv; V.y += dp.y * inv; V.z += dp.z * inv; V.w += dp.w * inv;
+                }
+            }
+        }
+    }
+    for (int o = grp >> 1; o > 0; o >>= 1) {
+        V.x += __shfl_xor_sync(FULL, V.x, o); V.y += __shfl_xor_sync(FULL, V.y, o);
+        V.z += __shfl_xor_sync(FULL, V.z, o); V.w += __shfl_xor_sync(FULL, V.w, o);
+    }
+    if (!active) return 0.f;
+    const float r = sc.filter.radius;
+    const float ddx = (x + 0.5f) - pt.x, ddy = (y + 0.5f) - pt.y;
+    // every neighbour outside the sample's support, the own pixel inside it?
+    if (!(1.f - fabsf(ddx) > r && 1.f - fabsf(ddy) > r && fabsf(ddx) <= r && fabsf(ddy) <= r)) return filter_radius_grad(sc, ra, x, y, pt, color);
+    float sum = V.x * color.x + V.y * color.y + V.z * color.z + V.w * color.w;
+    const float ws = ra.weight_image[y * ra.width + x];
+    if (ws > 0) {
+        const float fw = filter_weight(sc.filter, ddx, ddy);
+        const float4 dp = *reinterpret_cast<const float4 *>(ra.d_render_image + 4 * (y * ra.width + x));
+        const float dotv = dp.x * color.x + dp.y * color.y + dp.z * color.z + dp.w * color.w;
+        sum += (dotv * ws - fw * dotv * (ws - fw)) / (ws * ws);
+    }
+    return d_filter_weight_radius(sc.filter, ddx, ddy, sum);
+}
+
 }  // namespace dvg

@@ -556,6 +556,7 @@ __global__ void __launch_bounds__(WB, DVG_WB_MIN + 1) k_wave_composite_px(SceneV
     const int spp = ra_all.nsx * ra_all.nsy;
     const bool pow2 = (spp & (spp - 1)) == 0;
     const int grp = pow2 ? (spp < 32 ? spp : 32) : 1;
+    const bool box_fast = BACKWARD && sc.filter.type == 0 && pow2 && (int)ceilf(sc.filter.radius) == 1;   // filter_radius_grad_box
     int fkey[BACKWARD ? W_MAXF : 1];
     F4 fprev[BACKWARD ? W_MAXF : 1];
     float d_radius_acc = 0.f;
@@ -629,7 +630,11 @@ __global__ void __launch_bounds__(WB, DVG_WB_MIN + 1) k_wave_composite_px(SceneV
                 float *d = ra.d_background + 4 * (y * ra.width + x);
                 atomicAdd(d + 0, dcr); atomicAdd(d + 1, dcg); atomicAdd(d + 2, dcb); atomicAdd(d + 3, dca);
             }
-            if (active && !(ra.flags & 4u)) d_radius_acc += filter_radius_grad(sc, ra, x, y, pt, color);   // DVG_BWD_SKIP_FILTER_GRAD
+            if (!(ra.flags & 4u)) {   // DVG_BWD_SKIP_FILTER_GRAD
+                // (warp-uniform branch: every lane of the warp is in this block, see below)
+                if (box_fast) d_radius_acc += filter_radius_grad_box(sc, ra, x, y, pt, color, active, grp, lane);
+                else if (active) d_radius_acc += filter_radius_grad(sc, ra, x, y, pt, color);
+            }
         }
     }
     if (BACKWARD) {   // every sample adds to d_filter.radius
