@@ -169,6 +169,12 @@ __global__ void k_build_shape_cdf(BuildView bv) {
         shape_cdf[i] /= norm;
         shape_pmf[i] /= norm;
     }
+    // guide table of the normalised cdf for the sample-generation kernel (scene 0: batches search their tables plainly)
+    if (scene == 0 && bv.shape_guide) {
+        __syncthreads();
+        for (int k = threadIdx.x; k <= DVG_CDF_GUIDE; k += blockDim.x)
+            bv.shape_guide[k] = cdf_sample(shape_cdf, bv.num_insts, (float)k / (float)DVG_CDF_GUIDE, nullptr);
+    }
 }
 
 // ------------------------------------------------------------------ tile bins

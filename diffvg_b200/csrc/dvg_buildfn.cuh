@@ -23,7 +23,7 @@ struct BuildView {
     float *seg_cdf, *seg_pmf; int *seg_point_id;
     // per instance / group / primitive
     InstInfo *insts; GroupInfo *groups;
-    F4 *prim_p01, *prim_p23, *prim_rad; Box *prim_box; float *prim_thick; PrimMeta *prim_meta; Box *prim_cbox; Box *prim_cbox_pf; F4 *prim_cap; PrimQuintic *prim_quint; PrimWindCert *prim_wcert;
+    F4 *prim_p01, *prim_p23, *prim_rad; Box *prim_box; float *prim_thick; PrimMeta *prim_meta; Box *prim_cbox; Box *prim_cbox_pf; F4 *prim_cap; PrimQuintic *prim_quint; PrimWindCert *prim_wcert; int *shape_guide;
     float *shape_cdf, *shape_pmf;
     int *error_flag; float *total_length;
 };

@@ -81,7 +81,7 @@ struct DvgScene {
     DevBuf d_topo, d_inst_group, d_inst_shape, d_inst_prim_begin, d_prim_inst, d_prim_seg, d_prim_point_id;
     // device: parameters + derived tables
     DevBuf d_params, d_shapes_length, d_shape_box, d_shape_r0, d_seg_cdf, d_seg_pmf, d_seg_point_id;
-    DevBuf d_insts, d_groups, d_p01, d_p23, d_rad, d_box, d_thick, d_meta, d_cbox, d_cbox_pf, d_cap, d_quint, d_wcert, d_shape_cdf, d_shape_pmf;
+    DevBuf d_insts, d_groups, d_p01, d_p23, d_rad, d_box, d_thick, d_meta, d_cbox, d_cbox_pf, d_cap, d_quint, d_wcert, d_shape_cdf, d_shape_pmf, d_shape_guide;
     DevBuf d_flags;  // [0] error flag, [1] total length (float bits)
     // bins
     DevBuf d_bin_counts, d_bin_offsets, d_bin_items, d_sbin_counts, d_sbin_items;
@@ -129,7 +129,7 @@ struct DvgScene {
         bv.insts = d_insts.as<InstInfo>(); bv.groups = d_groups.as<GroupInfo>();
         bv.prim_p01 = d_p01.as<F4>(); bv.prim_p23 = d_p23.as<F4>(); bv.prim_rad = d_rad.as<F4>();
         bv.prim_box = d_box.as<Box>(); bv.prim_thick = d_thick.as<float>(); bv.prim_meta = d_meta.as<PrimMeta>();
-        bv.prim_cbox = d_cbox.as<Box>(); bv.prim_cbox_pf = d_cbox_pf.as<Box>(); bv.prim_cap = d_cap.as<F4>(); bv.prim_quint = d_quint.as<PrimQuintic>(); bv.prim_wcert = d_wcert.as<PrimWindCert>();
+        bv.prim_cbox = d_cbox.as<Box>(); bv.prim_cbox_pf = d_cbox_pf.as<Box>(); bv.prim_cap = d_cap.as<F4>(); bv.prim_quint = d_quint.as<PrimQuintic>(); bv.prim_wcert = d_wcert.as<PrimWindCert>(); bv.shape_guide = d_shape_guide.as<int>();
         bv.shape_cdf = d_shape_cdf.as<float>(); bv.shape_pmf = d_shape_pmf.as<float>();
         bv.error_flag = d_flags.as<int>(); bv.total_length = d_flags.as<float>() + 1;
         return bv;
@@ -145,7 +145,7 @@ struct DvgScene {
         sc.topo = d_topo.as<int>(); sc.params = d_params.as<float>();
         sc.prim_p01 = d_p01.as<F4>(); sc.prim_p23 = d_p23.as<F4>(); sc.prim_rad = d_rad.as<F4>();
         sc.prim_box = d_box.as<Box>(); sc.prim_thick = d_thick.as<float>(); sc.prim_meta = d_meta.as<PrimMeta>();
-        sc.prim_cbox = d_cbox.as<Box>(); sc.prim_cbox_pf = d_cbox_pf.as<Box>(); sc.prim_cap = d_cap.as<F4>(); sc.prim_quint = d_quint.as<PrimQuintic>(); sc.prim_wcert = d_wcert.as<PrimWindCert>();
+        sc.prim_cbox = d_cbox.as<Box>(); sc.prim_cbox_pf = d_cbox_pf.as<Box>(); sc.prim_cap = d_cap.as<F4>(); sc.prim_quint = d_quint.as<PrimQuintic>(); sc.prim_wcert = d_wcert.as<PrimWindCert>(); sc.shape_guide = d_shape_guide.as<int>();
         sc.insts = d_insts.as<InstInfo>(); sc.groups = d_groups.as<GroupInfo>();
         sc.shapes_length = d_shapes_length.as<float>();
         sc.shape_cdf = d_shape_cdf.as<float>(); sc.shape_pmf = d_shape_pmf.as<float>();
@@ -163,7 +163,7 @@ struct DvgScene {
     void release_all() {
         DevBuf *all[] = {&d_topo, &d_inst_group, &d_inst_shape, &d_inst_prim_begin, &d_prim_inst, &d_prim_seg,
                          &d_prim_point_id, &d_params, &d_shapes_length, &d_shape_box, &d_shape_r0, &d_seg_cdf, &d_seg_pmf,
-                         &d_seg_point_id, &d_insts, &d_groups, &d_p01, &d_p23, &d_rad, &d_box, &d_thick, &d_meta, &d_cbox, &d_cbox_pf, &d_cap, &d_quint, &d_wcert,
+                         &d_seg_point_id, &d_insts, &d_groups, &d_p01, &d_p23, &d_rad, &d_box, &d_thick, &d_meta, &d_cbox, &d_cbox_pf, &d_cap, &d_quint, &d_wcert, &d_shape_guide,
                          &d_shape_cdf, &d_shape_pmf, &d_flags, &d_bin_counts, &d_bin_offsets, &d_bin_items, &d_sbin_counts, &d_sbin_items, &d_weight,
                          &d_keys, &d_tile_counts, &d_tile_offsets, &d_tile_fill, &d_blk_counts, &d_blk_offsets, &d_sorted,
                          &d_wave_hit, &d_wave_wind, &d_wave_pairs_s, &d_wave_pairs_f, &d_wave_counters, &d_tile_nch, &d_tile_choff,
@@ -640,6 +640,7 @@ int dvg_scene_create_batch(const int32_t *topo, int64_t topo_len, int device, in
     ens(s->d_p01, 16 * npr); ens(s->d_p23, 16 * npr); ens(s->d_rad, 16 * npr); ens(s->d_box, 16 * npr);
     ens(s->d_thick, 4 * npr); ens(s->d_meta, sizeof(PrimMeta) * npr); ens(s->d_cbox, 16 * npr); ens(s->d_cbox_pf, 16 * npr); ens(s->d_cap, 16 * DVG_CAP_F4 * npr); ens(s->d_quint, sizeof(PrimQuintic) * npr); ens(s->d_wcert, sizeof(PrimWindCert) * (s->has_fills ? npr : 1));
     ens(s->d_shape_cdf, 4 * ni); ens(s->d_shape_pmf, 4 * ni); ens(s->d_flags, 16);
+    ens(s->d_shape_guide, sizeof(int) * (DVG_CDF_GUIDE + 1));
     ens(s->d_scan_ws, sizeof(int) * (DVG_SCAN_WS_BLOCKS + 1));
     if (!rc && cudaMemset(s->d_scan_ws.p, 0, sizeof(int) * (DVG_SCAN_WS_BLOCKS + 1)) != cudaSuccess) rc = fail(DVG_ERR_CUDA, "cudaMemset failed");
     if (!rc && cudaMallocHost((void **)&s->h_pinned, 64) != cudaSuccess) rc = fail(DVG_ERR_CUDA, "cudaMallocHost failed");

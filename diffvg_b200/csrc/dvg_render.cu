@@ -57,9 +57,11 @@ constexpr int KEYS_B = 256;
 constexpr int KEYS_CDF_MAX = 8192;
 __global__ void __launch_bounds__(KEYS_B) k_boundary_keys(SceneView sc, BinView bins, RenderArgs ra, BoundaryWork bw) {
     __shared__ float s_cdf[KEYS_CDF_MAX];
+    __shared__ int s_guide[DVG_CDF_GUIDE + 1];
     const bool staged = sc.num_insts <= KEYS_CDF_MAX && sc.batch == 1;
     if (staged) {
         for (int i = threadIdx.x; i < sc.num_insts; i += KEYS_B) s_cdf[i] = sc.shape_cdf[i];
+        for (int i = threadIdx.x; i <= DVG_CDF_GUIDE; i += KEYS_B) s_guide[i] = sc.shape_guide[i];
         __syncthreads();
     }
     const int per_scene = ra.width * ra.height * ra.nsx * ra.nsy;
@@ -69,7 +71,7 @@ __global__ void __launch_bounds__(KEYS_B) k_boundary_keys(SceneView sc, BinView 
         const int gk = bw.sample_begin + k;
         const int scene = sc.batch > 1 ? gk / per_scene : 0;
         const int idx = gk - scene * per_scene;
-        make_boundary_sample(sc, idx, ra.seeds ? ra.seeds[scene] : ra.seed, bs, staged ? s_cdf : nullptr, scene);
+        make_boundary_sample(sc, idx, ra.seeds ? ra.seeds[scene] : ra.seed, bs, staged ? s_cdf : nullptr, scene, staged ? s_guide : nullptr);
         int key = -1;
         if (bs.inst >= 0) {
             const int bx = (int)(bs.pt.x * ra.width), by = (int)(bs.pt.y * ra.height);  // diffvg.cpp:1405-1409

@@ -108,6 +108,7 @@ struct SceneView {
     const Box *prim_cbox_pf;  // same for the prefiltering path (binning only)
     const F4 *prim_cap;    // DVG_CAP_F4 float4 per primitive: conservative stroke-reject capsules (dvg_geom.cuh)
     const PrimQuintic *prim_quint;
+    const int *shape_guide;          // [DVG_CDF_GUIDE + 1] guide table of shape_cdf (scene 0 of a batch), dvg_boundary.cuh cdf_sample_guided
     const PrimWindCert *prim_wcert;  // filled cubic segments flagged DVG_PF_YMONO: what the classifier needs to answer their winding test itself (dvg_geom.cuh)   // cubic segments: the sample-independent part of the closest-point quintic (dvg_geom.cuh)
     const InstInfo *insts;
     const GroupInfo *groups;

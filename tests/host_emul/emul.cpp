@@ -100,7 +100,7 @@ void build(HostScene &hs, const int32_t *topo, const float *params) {
     bv.prim_p01 = hs.p01.data(); bv.prim_p23 = hs.p23.data(); bv.prim_rad = hs.rad.data(); bv.prim_box = hs.prim_box.data();
     bv.prim_thick = hs.prim_thick.data(); bv.prim_meta = hs.meta.data(); bv.prim_cbox = hs.prim_cbox.data(); bv.prim_cbox_pf = hs.prim_cbox_pf.data(); bv.prim_cap = hs.cap.data(); bv.prim_quint = hs.quint.data(); bv.prim_wcert = hs.wcert.data();
     bv.shape_cdf = hs.shape_cdf.data(); bv.shape_pmf = hs.shape_pmf.data();
-    bv.error_flag = &hs.error_flag; bv.total_length = &hs.total_length;
+    bv.error_flag = &hs.error_flag; bv.total_length = &hs.total_length; bv.shape_guide = nullptr;
     for (int s = 0; s < ns; s++) build_shape(bv, s);
     for (int g = 0; g < ng; g++) build_group(bv, g);
     for (int e = 0; e < np; e++) build_prim(bv, e);
@@ -113,7 +113,7 @@ void build(HostScene &hs, const int32_t *topo, const float *params) {
     sc.filter_radius_off = t[DVG_H_FILTER_RADIUS_OFF];
     sc.topo = t; sc.params = hs.params.data();
     sc.prim_p01 = hs.p01.data(); sc.prim_p23 = hs.p23.data(); sc.prim_rad = hs.rad.data(); sc.prim_box = hs.prim_box.data();
-    sc.prim_thick = hs.prim_thick.data(); sc.prim_meta = hs.meta.data(); sc.prim_cbox = hs.prim_cbox.data(); sc.prim_cbox_pf = hs.prim_cbox_pf.data(); sc.prim_cap = hs.cap.data(); sc.prim_quint = hs.quint.data(); sc.prim_wcert = hs.wcert.data();
+    sc.prim_thick = hs.prim_thick.data(); sc.prim_meta = hs.meta.data(); sc.prim_cbox = hs.prim_cbox.data(); sc.prim_cbox_pf = hs.prim_cbox_pf.data(); sc.prim_cap = hs.cap.data(); sc.shape_guide = nullptr; sc.prim_quint = hs.quint.data(); sc.prim_wcert = hs.wcert.data();
     sc.insts = hs.insts.data(); sc.groups = hs.groups.data();
     sc.shapes_length = hs.shapes_length.data(); sc.shape_cdf = hs.shape_cdf.data(); sc.shape_pmf = hs.shape_pmf.data();
     sc.seg_cdf = hs.seg_cdf.data(); sc.seg_pmf = hs.seg_pmf.data(); sc.seg_point_id = hs.seg_point_id.data();
@@ -489,6 +489,17 @@ EXPORT void emul_winding_fast_check(const float *pts8, const float *xy, int n, l
             if (wcw != cubic_winding_exact(p0, p1, p2, p3, pt)) out[3]++;
         }
     }
+}
+
+// cdf_sample_guided (the sample-generation kernel's shape pick) against cdf_sample: returns the number of u for which
+// the two differ.  The guide table is built the way k_build_shape_cdf builds it.
+EXPORT long long emul_cdf_guided_check(const float *cdf, int n, const float *us, int m) {
+    std::vector<int> guide(DVG_CDF_GUIDE + 1);
+    for (int k = 0; k <= DVG_CDF_GUIDE; k++) guide[k] = cdf_sample(cdf, n, (float)k / (float)DVG_CDF_GUIDE, nullptr);
+    long long bad = 0;
+    for (int i = 0; i < m; i++)
+        if (cdf_sample_guided(cdf, n, us[i], guide.data()) != cdf_sample(cdf, n, us[i], nullptr)) bad++;
+    return bad;
 }
 
 EXPORT void emul_pcg(int idx, uint64_t seed, uint64_t *state, float *rx, float *ry) {

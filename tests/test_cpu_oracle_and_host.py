@@ -462,3 +462,32 @@ def test_fast_cubic_winding_agrees_with_the_reference_sequence_whenever_it_answe
     assert cert[1] == 0 and cert[0] > 50000, cert           # the certificate: never wrong, and exercised
     assert ans >= 0.7 * tot, (ans, tot)                 # (the almost-quadratic kind never takes the fast form)
     assert common[1] >= 0.97 * common[0], common
+
+
+def test_guided_cdf_search_equals_the_reference_bisection():
+    """dvg_boundary.cuh cdf_sample_guided (2048-entry guide table over the shape cdf) picks the same shape as cdf.h's
+    bisection for every u: random cdfs with runs of equal entries (zero-length shapes), tiny and large tables, u on bucket
+    edges and on cdf values."""
+    import ctypes
+    lib = emul._load()
+    fp = ctypes.POINTER(ctypes.c_float)
+    lib.emul_cdf_guided_check.argtypes = [fp, ctypes.c_int, fp, ctypes.c_int]
+    lib.emul_cdf_guided_check.restype = ctypes.c_longlong
+    rng = np.random.RandomState(3)
+    for n in (1, 2, 3, 17, 2048, 5000, 8192):
+        for trial in range(6):
+            lens = rng.rand(n).astype(np.float32) ** (1 + 3 * trial)
+            lens[rng.rand(n) < 0.2 * (trial % 3)] = 0.0
+            if lens.sum() == 0:
+                lens[0] = 1.0
+            c = np.zeros(n, np.float32)
+            acc = np.float32(0)
+            for i in range(n):                       # sequential float prefix sum, as the scene build
+                acc = np.float32(lens[i]) if i == 0 else np.float32(lens[i] + acc)
+                c[i] = acc
+            c = (c / c[-1]).astype(np.float32)
+            us = np.concatenate([rng.rand(20000).astype(np.float32), (np.arange(2049) / 2048.0).astype(np.float32)[:-1],
+                                 c[:min(n, 3000)], np.nextafter(c[:min(n, 3000)], np.float32(0)),
+                                 np.float32([0.0, np.nextafter(np.float32(1), np.float32(0))])]).astype(np.float32)
+            us = us[(us >= 0) & (us < 1)]
+            assert lib.emul_cdf_guided_check(np.ascontiguousarray(c).ctypes.data_as(fp), n, np.ascontiguousarray(us).ctypes.data_as(fp), len(us)) == 0
