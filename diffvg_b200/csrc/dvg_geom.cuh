@@ -598,28 +598,46 @@ DVG_HD bool cubic_winding_fast(F2 p0, F2 p1, F2 p2, F2 p3, F2 pt, int *w_out, bo
     const double lo = -0.01, hi = 1.01;          // roots outside are clearly outside [0, 1]
     // monotone pieces: break the window at the critical points of y (float precision is enough for a break point: two
     // roots closer than that to a critical point are a near-double root, whose |dy| fails the margin below)
-    double brk[4];
-    int nb = 0;
-    brk[nb++] = lo;
+    // (scalars, not an array: everything below stays in registers)
+    double bk1 = hi, bk2 = hi;       // interior break points in (lo, hi), ascending; unused ones sit at hi
+    int nb = 2;
     const double D = b * b - 3.0 * a * c;
     if (D > 0) {
         const double sD = (double)sqrtf((float)D);
         const double q = -(b + (b >= 0 ? sD : -sD));
         double t1 = (double)((float)q / (float)(3.0 * a)), t2 = q != 0.0 ? (double)((float)c / (float)q) : t1;
         if (t1 > t2) { const double tmp = t1; t1 = t2; t2 = tmp; }
-        if (t1 > lo && t1 < hi) brk[nb++] = t1;
-        if (t2 > lo && t2 < hi && t2 > t1) brk[nb++] = t2;
+        const bool in1 = t1 > lo && t1 < hi, in2 = t2 > lo && t2 < hi && t2 > t1;
+        if (in1) { bk1 = t1; nb = 3; if (in2) { bk2 = t2; nb = 4; } }
+        else if (in2) { bk1 = t2; nb = 3; }
     }
-    brk[nb++] = hi;
+    // values at the break points; the pieces with a sign change are collected first and THEN solved one per trip, so that
+    // the lanes of a warp solve together whichever piece their (usually single) root lies in
+    const double yb0 = fma(fma(fma(a, lo, b), lo, c), lo, d);
+    const double yb1 = fma(fma(fma(a, bk1, b), bk1, c), bk1, d);
+    const double yb2 = fma(fma(fma(a, bk2, b), bk2, c), bk2, d);
+    const double yb3 = fma(fma(fma(a, hi, b), hi, c), hi, d);
+    // piece k = [bk_k, bk_{k+1}] of the nb - 1 pieces (the last break point is hi)
+    if (!(yb0 != 0.0 && yb3 != 0.0 && yb0 == yb0 && yb3 == yb3)) return false;
+    if (nb >= 3 && !(yb1 != 0.0 && yb1 == yb1)) return false;
+    if (nb >= 4 && !(yb2 != 0.0 && yb2 == yb2)) return false;
+    int pieces = 0, np = 0;          // indices of the pieces with a sign change, 2 bits each
+    {
+        const double e1 = nb >= 3 ? yb1 : yb3;                 // end of piece 0
+        if ((yb0 > 0) != (e1 > 0)) { pieces |= 0 << (2 * np); np++; }
+        if (nb >= 3) {
+            const double e2 = nb >= 4 ? yb2 : yb3;             // end of piece 1
+            if ((yb1 > 0) != (e2 > 0)) { pieces |= 1 << (2 * np); np++; }
+            if (nb >= 4 && (yb2 > 0) != (yb3 > 0)) { pieces |= 2 << (2 * np); np++; }
+        }
+    }
     int w = 0;
-    double yu = fma(fma(fma(a, lo, b), lo, c), lo, d);
-    for (int k = 0; k + 1 < nb; k++) {
-        double u = brk[k], v = brk[k + 1];
-        const double yv = fma(fma(fma(a, v, b), v, c), v, d);
-        const double yu0 = yu;
-        yu = yv;
-        if (yu0 == 0.0 || yv == 0.0 || yu0 != yu0 || yv != yv) return false;
-        if ((yu0 > 0) == (yv > 0)) continue;                 // no sign change: no root in this piece
+    for (int sidx = 0; sidx < np; sidx++) {
+        const int k = (pieces >> (2 * sidx)) & 3;
+        const double u = k == 0 ? lo : (k == 1 ? bk1 : bk2);
+        const double v = (k == nb - 2) ? hi : (k == 0 ? bk1 : bk2);
+        const double yu0 = k == 0 ? yb0 : (k == 1 ? yb1 : yb2);
+        const double yv = (k == nb - 2) ? yb3 : (k == 0 ? yb1 : yb2);
         // the root of this piece: four bracketed Newton steps in float from the secant point (fixed trip count: the lanes
         // of a warp stay together), then three steps in double whose correction needs float precision only, then a check
         // that one more step would not move it
