@@ -172,6 +172,10 @@ DVG_D void wave_classify(const SceneView &sc, const BinView &bins, const WaveVie
             __syncwarp();
             WavePair *out = kind == 0 ? wv.pairs_s : wv.pairs_f;
             const int cap = kind == 0 ? wv.cap_s : wv.cap_f;
+            // winding pairs are all queued: ONE reservation for the chunk's qn of them (a fill-heavy scene queues hundreds
+            // per chunk; a reservation per 32 was 6 M atomics on one address per pass at tiger.svg, two thirds of this kernel)
+            int fill_base = 0;
+            if (!INPLACE && kind == 1) fill_base = warp_reserve(&wv.counters[1], qn);
             for (int r = 0; r < qn; r += 32) {
                 const bool have = r + lane < qn;
                 const int it = have ? ws.queue[r + lane] : 0;
@@ -195,6 +199,16 @@ DVG_D void wave_classify(const SceneView &sc, const BinView &bins, const WaveVie
                 }
                 if (INPLACE) {
                     if (keep) wave_exact_in_place(sc, wv, kind, ek, tfk, ik, lp, &ws.hit[owner], word0 + owner, k);
+                    continue;
+                }
+                if (kind == 1) {
+                    const int pos = fill_base + r + lane;
+                    if (keep && pos < cap) {
+                        WavePair p;
+                        p.x = lp.x; p.y = lp.y; p.prim = ek | ((tfk & DVG_PF_TYPE_MASK) << 28);
+                        p.ref = ((unsigned)(word0 + owner) << 5) | (unsigned)k;
+                        out[pos] = p;
+                    }
                     continue;
                 }
                 const unsigned m = __ballot_sync(FULL, keep);
