@@ -174,7 +174,7 @@ DVG_D void wave_classify(const SceneView &sc, const BinView &bins, const WaveVie
             const int cap = kind == 0 ? wv.cap_s : wv.cap_f;
             // winding pairs are all queued: ONE reservation for the chunk's qn of them (a fill-heavy scene queues hundreds
             // per chunk; a reservation per 32 was 6 M atomics on one address per pass at tiger.svg, two thirds of this kernel)
-            int fill_base = 0;
+            int fill_base = 0, kq = 0;
             if (!INPLACE && kind == 1) fill_base = warp_reserve(&wv.counters[1], qn);
             for (int r = 0; r < qn; r += 32) {
                 const bool have = r + lane < qn;
@@ -205,26 +205,39 @@ DVG_D void wave_classify(const SceneView &sc, const BinView &bins, const WaveVie
                     const int pos = fill_base + r + lane;
                     if (keep && pos < cap) {
                         WavePair p;
-                        p.x = lp.x; p.y = lp.y; p.prim = ek | ((tfk & DVG_PF_TYPE_MASK) << 28);
+                        p.x = lp.x; p.y = lp.y; p.prim = ek | ((tfk & DVG_PF_TYPE_MASK) << 28);   // type rides along: W2 needs no meta load
                         p.ref = ((unsigned)(word0 + owner) << 5) | (unsigned)k;
                         out[pos] = p;
                     }
                     continue;
                 }
+                // stroke pairs: the survivors of the bracket are compacted in place (kq <= r: only entries already read are
+                // overwritten) and queued after the loop with ONE reservation for the chunk
                 const unsigned m = __ballot_sync(FULL, keep);
-                const int cnt = __popc(m);
-                if (cnt) {
-                    // the counter keeps counting past the capacity: that is how the retry form and the host learn of it
-                    const int pos = warp_reserve(&wv.counters[kind], cnt) + __popc(m & lt);
-                    if (keep && pos < cap) {
+                if (keep) ws.queue[kq + __popc(m & lt)] = (unsigned short)it;
+                kq += __popc(m);
+            }
+            __syncwarp();
+            if (!INPLACE && kind == 0 && kq > 0) {
+                // the counter keeps counting past the capacity: that is how the retry form and the host learn of it
+                const int base_pos = warp_reserve(&wv.counters[0], kq);
+                for (int r = 0; r < kq; r += 32) {
+                    const bool have = r + lane < kq;
+                    const int it = have ? ws.queue[r + lane] : 0;
+                    const int k = it & 31, owner = it >> 5;
+                    const int ek = __shfl_sync(FULL, e, k), tfk = __shfl_sync(FULL, tf, k), gk = __shfl_sync(FULL, group, k);
+                    const F2 op = mk2(__shfl_sync(FULL, cpt.x, owner), __shfl_sync(FULL, cpt.y, owner));
+                    const int pos = base_pos + r + lane;
+                    if (have && pos < cap) {
+                        const F2 lp = w_local_point(sc.groups[gk], op);
                         WavePair p;
-                        p.x = lp.x; p.y = lp.y; p.prim = ek | ((tfk & DVG_PF_TYPE_MASK) << 28);   // type rides along: W2 needs no meta load
+                        p.x = lp.x; p.y = lp.y; p.prim = ek | ((tfk & DVG_PF_TYPE_MASK) << 28);
                         p.ref = ((unsigned)(word0 + owner) << 5) | (unsigned)k;
                         out[pos] = p;
                     }
                 }
+                __syncwarp();
             }
-            __syncwarp();
         }
         __syncwarp();
         wv.hit[word0 + lane] = ws.hit[lane];
