@@ -50,6 +50,8 @@ lib.dvg_scene_dump.restype = _i64
 
 lib.dvg_debug_set_limits.argtypes = [_i64, _i64]
 lib.dvg_debug_set_limits.restype = _i
+lib.dvg_debug_set_prefilter_inline.argtypes = [_i]
+lib.dvg_debug_set_prefilter_inline.restype = _i
 lib.dvg_profile_enable.argtypes = [_i]
 lib.dvg_profile_enable.restype = _i
 lib.dvg_profile_report.argtypes = [ctypes.c_char_p, _i64]

@@ -22,6 +22,7 @@ thread_local std::string g_err;
 float *g_debug_out = nullptr;  // dvg_debug_set_boundary_dump
 long long g_debug_edge_pass_samples = 0;   // dvg_debug_set_limits
 long long g_debug_pair_capacity = 0;
+bool g_pf_inline = getenv("DVG_PF_INLINE") != nullptr && getenv("DVG_PF_INLINE")[0] == '1';   // dvg_debug_set_prefilter_inline (env: measurements only)
 bool g_fast_accept = getenv("DVG_FAST_ACCEPT") != nullptr && getenv("DVG_FAST_ACCEPT")[0] == '1';   // dvg_set_fast_stroke_accept (env: measurements only)
 
 int fail(int code, const std::string &msg) {
@@ -506,6 +507,49 @@ int wave_pixel_pass(DvgScene *s, const SceneView &sc, const BinView &bins, const
     return DVG_OK;
 }
 
+// Prefiltered pixel pass (sample_color_prefiltered): the winding numbers of the filled groups are answered first by the
+// wavefront pair (classify with the stroke side masked -> k_wave_solve_fill) and k_render_pf reads them as words; the
+// backward pass of the same (scene, size, samples, rows) re-uses the forward pass's words (the prefiltered sample
+// positions do not depend on the seed).  Scenes without fills, and renders whose words would not fit the 27-bit index,
+// run the winding test inline.
+int wave_pf_pass(DvgScene *s, const SceneView &sc, const BinView &bins, const RenderArgs &ra, bool backward, cudaStream_t st) {
+    const int64_t wpt = wave_items_per_tile(bins, ra);
+    const int items = wave_pixel_items(bins, ra);
+    const int64_t words = (int64_t)s->total_chunks * wpt * 32;
+    if (!s->has_fills || g_pf_inline || words >= ((int64_t)1 << 27) || items <= 0) {
+        launch_render_pf(sc, bins, ra, nullptr, nullptr, backward, st);
+        CK(cudaGetLastError());
+        return DVG_OK;
+    }
+    WaveView wv;
+    int rc = wave_view(s, (int64_t)s->total_chunks * wpt, (int64_t)items * 32, &wv);
+    if (rc) return rc;
+    const bool reuse = s->wpx_valid && s->wpx_w == ra.width && s->wpx_h == ra.height && s->wpx_nsx == ra.nsx && s->wpx_nsy == ra.nsy &&
+                       s->wpx_r0 == ra.row_begin && s->wpx_r1 == ra.row_end && s->wpx_pf == ra.use_prefiltering;
+    if (!reuse) {
+        s->wpx_valid = false;
+        const bool small = (int64_t)s->total_chunks * wpt * 32 * 32 <= kSmallPairs;
+        CK(cudaMemsetAsync(wv.counters, 0, sizeof(int) * 2, st));
+        launch_wave_classify_px(sc, bins, ra, wv, st);
+        CK(cudaGetLastError());
+        launch_wave_solve(sc, wv, false, true, st);
+        CK(cudaGetLastError());
+        if (!small) { launch_wave_retry_px(sc, bins, ra, wv, st); CK(cudaGetLastError()); }
+        if (!s->counts_pending[0]) {
+            CK(cudaMemcpyAsync(s->h_counts, wv.counters, sizeof(int) * 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaEventRecord(s->ev_counts[0], st));
+            s->counts_pending[0] = true;
+            s->counts_stream[0] = st;
+        }
+        s->wpx_valid = true; s->wpx_w = ra.width; s->wpx_h = ra.height; s->wpx_nsx = ra.nsx; s->wpx_nsy = ra.nsy;
+        s->wpx_seed = ra.seed; s->wpx_r0 = ra.row_begin; s->wpx_r1 = ra.row_end; s->wpx_pf = ra.use_prefiltering;
+        s->wpx_fast = ra.flags & DVG_RF_FAST_ACCEPT;
+    }
+    launch_render_pf(sc, bins, ra, wv.wind, wv.tile_choff, backward, st);
+    CK(cudaGetLastError());
+    return DVG_OK;
+}
+
 // Boundary pass (diffvg.cpp:1558-1626) over the boundary-sample indices [bw.sample_begin, + bw.num_samples).  `bw` comes
 // with its sort buffers bound.
 int wave_edge_pass(DvgScene *s, const SceneView &sc, const BinView &bins, const RenderArgs &ra, BoundaryWork &bw, cudaStream_t st) {
@@ -750,8 +794,8 @@ static int render_forward_impl(DvgScene *s, const float *background, float *rend
         if (rc) return rc;
         CK(cudaMemsetAsync(render_image + 4 * (size_t)row_begin * width, 0,
                            sizeof(float) * 4 * (size_t)width * (row_end - row_begin) * s->batch, st));
-        if (use_prefiltering) launch_render_pf_forward(sc, s->bin_view(), ra, st);
-        else { rc = wave_pixel_pass(s, sc, s->bin_view(), ra, false, st); if (rc) return rc; }
+        rc = use_prefiltering ? wave_pf_pass(s, sc, s->bin_view(), ra, false, st) : wave_pixel_pass(s, sc, s->bin_view(), ra, false, st);
+        if (rc) return rc;
         CK(cudaGetLastError());
     }
     if (render_sdf) {
@@ -836,8 +880,8 @@ static int render_backward_impl(DvgScene *s, const float *background, const floa
         if (rc) return rc;
         if (use_prefiltering) {
             // interior term only: the SDF coverage is differentiable, no boundary pass (diffvg.cpp:1558)
-            launch_render_pf_backward(sc, bins, ra, st);
-            CK(cudaGetLastError());
+            rc = wave_pf_pass(s, sc, bins, ra, true, st);
+            if (rc) return rc;
             launch_wave_reduce_grads(ra, st);
             CK(cudaGetLastError());
         } else {
@@ -973,6 +1017,7 @@ int dvg_debug_prim_tests(DvgScene *s, int width, int height, int nsx, int nsy, u
 }
 
 int dvg_set_fast_stroke_accept(int on) { g_fast_accept = on != 0; return DVG_OK; }
+int dvg_debug_set_prefilter_inline(int on) { g_pf_inline = on != 0; return DVG_OK; }
 
 int dvg_profile_enable(int on) {
     dvg::g_profile_on = on != 0;

@@ -468,7 +468,10 @@ struct PrefilterTracer {
         sh_base = sh_pid = -1; sh_t = 0.f; sh_cp = mk2(0, 0);
     }
 
-    DVG_HD void step(const SceneView &sc, const PrimRef &pr) {
+    // WORDS: the winding contribution of this candidate was answered by the winding pre-pass (dvg_wave.cu: classify ->
+    // k_wave_solve_fill) and arrives as `nib`; it is zero wherever the gating tests below would not have asked for it.
+    template <bool WORDS = false>
+    DVG_HD void step(const SceneView &sc, const PrimRef &pr, int nib = 0) {
         if (pr.group != cur_g) { end_group(sc); begin_group(sc, pr.group); }
         if (pr.inst != cur_inst) { end_shape(); begin_shape(sc, pr.inst); }
         if (!g_visit) return;
@@ -489,7 +492,9 @@ struct PrefilterTracer {
             prim_closest(type, false, pr.p01, pr.p23, lpt, cp, t_root);
             sh_cp = cp; sh_found = true; sh_rect = true; sh_base = -1; sh_pid = -1; sh_t = 0.f;
         }
-        if (s_fill_ok) {
+        if (WORDS) {
+            w_shape += nib;
+        } else if (s_fill_ok) {
             if ((tf & DVG_PF_SINGLE) || box_ray_intersect(pr.box, lpt)) w_shape += prim_winding(type, pr.p01, pr.p23, lpt);
         }
     }

@@ -30,8 +30,14 @@ DVG_D PrimRef load_prim(const SceneView &sc, int e) {
     return pr;
 }
 
-template <bool BACKWARD>
-__global__ void __launch_bounds__(PB, DVG_PF_MINB) k_render_pf(SceneView sc, BinView bins, RenderArgs ra) {
+// WORDS: the winding contributions come from the winding pre-pass (wave_classify<.., FILLS> with the stroke side masked ->
+// k_wave_solve_fill, dvg_wave.cu): `wind` holds one 4-bit answer per (sample, candidate) in the layout of the wavefront
+// passes (warp = item of 32 samples; word (cb + chunk) * 32 + lane, four 32-bit words each).  Inline, the FP64 root
+// solves of the winding test ran with the lanes that happened to need them, in a 128-register kernel at 22% occupancy,
+// and the backward kernel repeated all of them; now they run one per lane in k_wave_solve_fill and the backward pass
+// re-uses the forward pass's words.
+template <bool BACKWARD, bool WORDS>
+__global__ void __launch_bounds__(PB, DVG_PF_MINB) k_render_pf(SceneView sc, BinView bins, RenderArgs ra, const uint4 *wind, const int *tile_choff) {
     // gradients go straight to one of the private copies of the gradient buffer (dvg_kernel_util.cuh grad_replica):
     // the per-block shared-memory hash + barrier + flush this kernel used before was 40% of its time at 2048^2
     const GlobalSink sk{BACKWARD ? grad_replica(ra) : nullptr};
@@ -68,9 +74,27 @@ __global__ void __launch_bounds__(PB, DVG_PF_MINB) k_render_pf(SceneView sc, Bin
     PrefilterTracer<BACKWARD> tr;
     tr.init(cpt, active, first, frags);
     const int beg = bins.offsets[tile], end = bins.offsets[tile + 1];
-    for (int i = beg; i < end; i++) {
-        const PrimRef pr = load_prim(sc, bins.items[i]);   // block-uniform loads
-        tr.step(sc, pr);
+    if constexpr (WORDS) {
+        const int wpt = (ns + 31) / 32;
+        const int part_w = l >> 5;                 // this warp's item within the tile (pixel_item, dvg_wave.cu)
+        const int c0 = tile_choff[tile];
+        const int nch = tile_choff[tile + 1] - c0;
+        const uint4 *wp = wind + (((int64_t)c0 * wpt + (int64_t)part_w * nch) * 32 + (tid & 31));
+        const bool have_words = part_w < wpt;
+        uint4 wd = make_uint4(0u, 0u, 0u, 0u);
+        for (int i = beg; i < end; i++) {
+            const int k = (i - beg) & 31;
+            if (k == 0 && have_words) wd = wp[(int64_t)((i - beg) >> 5) * 32];
+            const PrimRef pr = load_prim(sc, bins.items[i]);   // block-uniform loads
+            const unsigned ww = (k < 8 ? wd.x : (k < 16 ? wd.y : (k < 24 ? wd.z : wd.w)));
+            const int nib = (int)((ww >> (4 * (k & 7))) & 15u);
+            tr.template step<true>(sc, pr, (nib ^ 8) - 8);
+        }
+    } else {
+        for (int i = beg; i < end; i++) {
+            const PrimRef pr = load_prim(sc, bins.items[i]);   // block-uniform loads
+            tr.step(sc, pr);
+        }
     }
     tr.finish(sc);
     const F4 color = tr.resolve(bg_px);
@@ -168,6 +192,9 @@ __global__ void __launch_bounds__(PB) k_sdf(SceneView sc, RenderArgs ra, SdfArgs
     }
 }
 
+constexpr auto kpf_fwd_words = k_render_pf<false, true>, kpf_fwd_inline = k_render_pf<false, false>;
+constexpr auto kpf_bwd_words = k_render_pf<true, true>, kpf_bwd_inline = k_render_pf<true, false>;
+
 static int pf_blocks(const BinView &bins, const RenderArgs &ra) {
     const int ns = bins.tile_w * bins.tile_h * ra.nsx * ra.nsy;
     const int parts = (ns + PB - 1) / PB;
@@ -176,16 +203,20 @@ static int pf_blocks(const BinView &bins, const RenderArgs &ra) {
     return (r1 - r0) * bins.tiles_x * parts;
 }
 
-void launch_render_pf_forward(const SceneView &sc, const BinView &bins, const RenderArgs &ra, cudaStream_t st) {
+// `wind` / `tile_choff`: the winding words of the pre-pass and the chunk offsets they are laid out by, or null (the
+// winding test then runs inline: scenes without fills, renders beyond the 27-bit word index)
+void launch_render_pf(const SceneView &sc, const BinView &bins, const RenderArgs &ra, const unsigned *wind, const int *tile_choff,
+                      bool backward, cudaStream_t st) {
     const int nblk = pf_blocks(bins, ra);
     if (nblk <= 0) return;
-    DVG_LAUNCH(k_render_pf<false>, dim3(nblk), dim3(PB), 0, st, sc, bins, ra);
-}
-
-void launch_render_pf_backward(const SceneView &sc, const BinView &bins, const RenderArgs &ra, cudaStream_t st) {
-    const int nblk = pf_blocks(bins, ra);
-    if (nblk <= 0) return;
-    DVG_LAUNCH(k_render_pf<true>, dim3(nblk), dim3(PB), 0, st, sc, bins, ra);
+    const uint4 *w4 = reinterpret_cast<const uint4 *>(wind);
+    if (backward) {
+        if (wind) DVG_LAUNCH_AS("k_render_pf<true>", kpf_bwd_words, dim3(nblk), dim3(PB), 0, st, sc, bins, ra, w4, tile_choff);
+        else DVG_LAUNCH_AS("k_render_pf<true>", kpf_bwd_inline, dim3(nblk), dim3(PB), 0, st, sc, bins, ra, w4, tile_choff);
+    } else {
+        if (wind) DVG_LAUNCH_AS("k_render_pf<false>", kpf_fwd_words, dim3(nblk), dim3(PB), 0, st, sc, bins, ra, w4, tile_choff);
+        else DVG_LAUNCH_AS("k_render_pf<false>", kpf_fwd_inline, dim3(nblk), dim3(PB), 0, st, sc, bins, ra, w4, tile_choff);
+    }
 }
 
 void launch_sdf(const SceneView &sc, const RenderArgs &ra, const SdfArgs &sa, bool backward, cudaStream_t st) {

@@ -108,7 +108,7 @@ __device__ __noinline__ void wave_exact_in_place(const SceneView &sc, const Wave
 // a dozen FP64 operations, warp-coherent because all lanes test the same segment) instead of being queued.
 template <bool INPLACE, bool FILLS>
 DVG_D void wave_classify(const SceneView &sc, const BinView &bins, const WaveView &wv, int tile, int64_t cb,
-                         F2 cpt, bool active, WaveScratch &ws, bool fast_accept) {
+                         F2 cpt, bool active, WaveScratch &ws, bool fast_accept, bool winding_only = false) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
@@ -138,7 +138,7 @@ DVG_D void wave_classify(const SceneView &sc, const BinView &bins, const WaveVie
             pr.thick = __shfl_sync(FULL, thick, k);
             pr.tf = __shfl_sync(FULL, tf, k); pr.inst = __shfl_sync(FULL, inst, k); pr.group = __shfl_sync(FULL, group, k);
             const int nd = ct.template step<TM_CLASSIFY>(sc, pr);
-            need_s |= (unsigned)(nd & 1) << k;
+            need_s |= (unsigned)(nd & 1) << k;   // (cleared below for the winding pre-pass of the prefiltered path)
             bool nf = ((nd >> 1) & 1) != 0;
             if (FILLS && (pr.tf & DVG_PF_YMONO)) {   // (uniform: every lane holds the same candidate)
                 const int ek = __shfl_sync(FULL, e, k);
@@ -151,6 +151,9 @@ DVG_D void wave_classify(const SceneView &sc, const BinView &bins, const WaveVie
             }
             need_f |= (unsigned)(nf ? 1u : 0u) << k;
         }
+        // the prefiltered path (sample_color_prefiltered) takes only the winding numbers from here: its gating tests are
+        // those of the sampled path (diffvg.cpp:42-45, 71-78, winding_number.h:162-169); distances are searched by k_render_pf
+        if (winding_only) need_s = 0u;
         ws.hit[lane] = 0u;
         const int64_t word0 = (cb + c) * 32;
         if (FILLS) {   // written first: the exact tests (and a pair that finds its queue full and is answered in place) OR into these words
@@ -289,7 +292,8 @@ __global__ void __launch_bounds__(WB, DVG_WB_MIN) k_wave_classify_px(SceneView s
         if (pi.active)
             sample_position(sc.canvas_w, sc.canvas_h, ra.width, ra.height, ra.nsx, ra.nsy, ra.seeds ? ra.seeds[pi.scene] : ra.seed,
                             ra.use_prefiltering != 0, pi.x, pi.y, pi.sx, pi.sy, pi.idx, pt, cpt);
-        wave_classify<INPLACE, FILLS>(sc, bins, wv, pi.tile, pi.cb, cpt, pi.active, s_ws[threadIdx.x >> 5], (ra.flags & DVG_RF_FAST_ACCEPT) != 0);
+        wave_classify<INPLACE, FILLS>(sc, bins, wv, pi.tile, pi.cb, cpt, pi.active, s_ws[threadIdx.x >> 5], (ra.flags & DVG_RF_FAST_ACCEPT) != 0,
+                                      ra.use_prefiltering != 0);
     }
 }
 

@@ -167,6 +167,10 @@ int dvg_debug_set_boundary_dump(float *device_buf);
  * forces the answer-in-place path of the classifier, and the boundary pass at `edge_pass_samples` samples per sub-pass
  * (0 = off: as many as the result words allow).  Process-wide. */
 int dvg_debug_set_limits(int64_t pair_capacity, int64_t edge_pass_samples);
+/* Test support: 1 = the prefiltered path runs its winding tests inline in the render kernel (what it does anyway for
+ * scenes without fills and for renders beyond the 27-bit word index) instead of through the winding pre-pass.  Same
+ * results either way; process-wide. */
+int dvg_debug_set_prefilter_inline(int on);
 /* Test support: for every sample of pixel (x, y) and EVERY primitive of the scene (no culling), the exact stroke test and
  * winding contribution as the device computes them: out_host[s * num_prims + e] = hit (bit 0) | group strokes (bit 1) |
  * group fills (bit 2) | primitive is in the pixel's tile bin (bit 3) | (winding & 0xff) << 8; pos_host[2 s .. 2 s + 1] =

@@ -9,6 +9,7 @@ import pytest
 import torch
 
 import oracle_check
+from diffvg_b200 import scene_pack
 import ref_oracle
 import scenes
 import util
@@ -258,3 +259,49 @@ def test_row_costs_and_balanced_bands_reproduce_the_whole_render():
         parts = util.gpu_render_rows(topo, params, W, H, ns, ns, 2, bands, d_render_image=d_img, use_prefiltering=pf)
         assert np.abs(parts['image'] - whole).max() <= 1e-6
         assert util.rel_l2(gw, parts['d_params']) <= 1e-4
+
+
+def test_prefilter_winding_prepass_equals_inline_and_backward_reuses_forward_words():
+    """The prefiltered path answers the winding numbers of filled groups in a pre-pass (classify -> k_wave_solve_fill) and
+    the render kernel reads them as words; dvg_debug_set_prefilter_inline(1) runs the same tests inline in the render
+    kernel.  Both evaluate the same functions on the same inputs: images are identical, gradients equal up to the order
+    of the atomic sums.  Then forward + backward on ONE scene object (pydiffvg): the backward pass re-uses the forward
+    pass's words and must give the gradient of a fresh scene; a parameter change must not see stale words."""
+    from diffvg_b200 import _native as n, pydiffvg
+    cases = ((scenes.blobs(), 256, 256, 2, 2), (scenes.zoo(), 96, 96, 2, 2), (scenes.zoo(), 70, 50, 3, 1))
+    for scene, W, H, nsx, nsy in cases:
+        topo, params = util.pack(scene)
+        d_img = np.random.RandomState(2).rand(H, W, 4).astype(np.float32) - 0.5
+        a = util.gpu_render(topo, params, W, H, nsx, nsy, 0, use_prefiltering=True)['image']
+        ga = util.gpu_render(topo, params, W, H, nsx, nsy, 0, use_prefiltering=True, d_render_image=d_img)['d_params']
+        assert n.lib.dvg_debug_set_prefilter_inline(1) == 0
+        try:
+            b = util.gpu_render(topo, params, W, H, nsx, nsy, 0, use_prefiltering=True)['image']
+            gb = util.gpu_render(topo, params, W, H, nsx, nsy, 0, use_prefiltering=True, d_render_image=d_img)['d_params']
+        finally:
+            n.lib.dvg_debug_set_prefilter_inline(0)
+        assert np.array_equal(a, b)
+        assert util.rel_l2(gb, ga) <= 1e-5
+    # one scene object, forward then backward (words re-used), twice with different parameters
+    pydiffvg.set_use_gpu(True)
+    cw, ch, shapes, groups = scenes.blobs()
+    packed, params0 = pydiffvg.RenderFunction.serialize_scene(cw, ch, shapes, groups, use_prefiltering=True)
+    topo, params_np = util.pack((cw, ch, shapes, groups))
+    W = H = 192
+    ro = int(topo[scene_pack.H_FRAD_OFF])
+    target = torch.rand(H, W, 4, generator=torch.Generator().manual_seed(3))
+    for shift in (0.0, 0.25):
+        p_np = params_np.copy()
+        p_np += shift                     # moves every point (and tints every colour): the geometry changes
+        p_np[ro] = params_np[ro]
+        p = torch.from_numpy(p_np.copy()).requires_grad_(True)
+        img = pydiffvg.RenderFunction.apply(W, H, 2, 2, 0, None, packed, p)
+        loss = (img.cpu() - target).pow(2).mean()
+        (g,) = torch.autograd.grad(loss, p)
+        fresh = util.gpu_render(topo, p_np, W, H, 2, 2, 0, use_prefiltering=True)['image']
+        assert np.array_equal(fresh, img.detach().cpu().numpy())
+        d_img = (2.0 * (img.detach().cpu().numpy() - target.numpy()) / target.numel()).astype(np.float32)
+        gf = util.gpu_render(topo, p_np, W, H, 2, 2, 0, use_prefiltering=True, d_render_image=d_img)['d_params']
+        got = g.cpu().numpy().copy()
+        got[ro] = gf[ro] = 0.0      # d_filter.radius is skipped unless the radius takes part in autograd
+        assert util.rel_l2(gf, got) <= 1e-5
