@@ -389,7 +389,11 @@ DVG_HD_NOINLINE void build_prim(const BuildView &bv, int e_batch) {
             if (ptype >= PRIM_QUAD) rmin = rminf(rmin, rad.z);
             if (ptype == PRIM_CUBIC) rmin = rminf(rmin, rad.w);
         }
-        build_capsules(has_stroke ? ptype : -1, p01, p23, thick, rmin, cap);
+        // a fill-only curve gets the bracket of the radius-1 closest-point search of the prefiltered path
+        // (compute_distance(..., 1.f, ...), diffvg.cpp:891-932): PrefilterTracer skips the solve of a segment that is
+        // certainly farther than 1 from the sample
+        if (has_stroke) build_capsules(ptype, p01, p23, thick, rmin, cap);
+        else build_capsules(has_fill ? ptype : -1, p01, p23, 1.f, 0.f, cap);
         for (int k = 0; k < DVG_CAP_F4; k++) bv.prim_cap[(size_t)e * DVG_CAP_F4 + k] = mk4(cap[4 * k], cap[4 * k + 1], cap[4 * k + 2], cap[4 * k + 3]);
     }
     if (first_in_inst) {

@@ -517,7 +517,7 @@ int wave_pf_pass(DvgScene *s, const SceneView &sc, const BinView &bins, const Re
     const int items = wave_pixel_items(bins, ra);
     const int64_t words = (int64_t)s->total_chunks * wpt * 32;
     if (!s->has_fills || g_pf_inline || words >= ((int64_t)1 << 27) || items <= 0) {
-        launch_render_pf(sc, bins, ra, nullptr, nullptr, backward, st);
+        launch_render_pf(sc, bins, ra, nullptr, nullptr, nullptr, backward, st);
         CK(cudaGetLastError());
         return DVG_OK;
     }
@@ -545,7 +545,7 @@ int wave_pf_pass(DvgScene *s, const SceneView &sc, const BinView &bins, const Re
         s->wpx_seed = ra.seed; s->wpx_r0 = ra.row_begin; s->wpx_r1 = ra.row_end; s->wpx_pf = ra.use_prefiltering;
         s->wpx_fast = ra.flags & DVG_RF_FAST_ACCEPT;
     }
-    launch_render_pf(sc, bins, ra, wv.wind, wv.tile_choff, backward, st);
+    launch_render_pf(sc, bins, ra, wv.wind, wv.hit, wv.tile_choff, backward, st);
     CK(cudaGetLastError());
     return DVG_OK;
 }

@@ -480,11 +480,18 @@ struct PrefilterTracer {
         if (type <= PRIM_CUBIC) {
             // path-BVH pruning against the running minimum (compute_distance.h:285-294); a lone leaf is the root
             if ((tf & DVG_PF_SINGLE) || box_within_distance(pr.box, lpt, sh_min)) {
-                F2 cp; float t_root;
-                const float dist = prim_closest(type, (tf & DVG_PF_APPROX) != 0, pr.p01, pr.p23, lpt, cp, t_root);
-                if (dist < sh_min) {
-                    sh_min = dist; sh_cp = cp; sh_t = t_root; sh_found = true;
-                    sh_base = pr.base_id; sh_pid = pr.point_id;
+                // fill-only group: the search radius is 1 (sh_min <= 1), and the polyline bracket of the segment (built for
+                // radius 1, dvg_buildfn.cuh) may prove that every point of the curve is farther than that.  The reference's
+                // answer is the distance to SOME point of the curve (a root it found, or an end point), so it could not
+                // pass `dist < sh_min` either: the solve is skipped, nothing changes.
+                const bool far = !has_stroke && pr.cap != nullptr && type >= PRIM_QUAD && capsule_reject(pr.cap, lpt);
+                if (!far) {
+                    F2 cp; float t_root;
+                    const float dist = prim_closest(type, (tf & DVG_PF_APPROX) != 0, pr.p01, pr.p23, lpt, cp, t_root);
+                    if (dist < sh_min) {
+                        sh_min = dist; sh_cp = cp; sh_t = t_root; sh_found = true;
+                        sh_base = pr.base_id; sh_pid = pr.point_id;
+                    }
                 }
             }
         } else if (type == PRIM_RECT) {

@@ -26,18 +26,19 @@ DVG_D PrimRef load_prim(const SceneView &sc, int e) {
     pr.box = sc.prim_box[e]; pr.thick = 0.f;
     pr.tf = pm.type_flags; pr.inst = pm.inst; pr.group = sc.insts[pm.inst].group;
     pr.base_id = pm.base_id; pr.point_id = pm.point_id;
-    pr.cap = nullptr;
+    pr.cap = reinterpret_cast<const float *>(sc.prim_cap + (size_t)e * DVG_CAP_F4);
     return pr;
 }
 
-// WORDS: the winding contributions come from the winding pre-pass (wave_classify<.., FILLS> with the stroke side masked ->
+// WORDS: `relevant` (one word per (sample, chunk), the same in every lane of a warp: the candidates some sample of the warp
+// can be affected by, wave_classify<.., PF>) and the winding contributions come from the winding pre-pass (wave_classify<.., FILLS> with the stroke side masked ->
 // k_wave_solve_fill, dvg_wave.cu): `wind` holds one 4-bit answer per (sample, candidate) in the layout of the wavefront
 // passes (warp = item of 32 samples; word (cb + chunk) * 32 + lane, four 32-bit words each).  Inline, the FP64 root
 // solves of the winding test ran with the lanes that happened to need them, in a 128-register kernel at 22% occupancy,
 // and the backward kernel repeated all of them; now they run one per lane in k_wave_solve_fill and the backward pass
 // re-uses the forward pass's words.
 template <bool BACKWARD, bool WORDS>
-__global__ void __launch_bounds__(PB, DVG_PF_MINB) k_render_pf(SceneView sc, BinView bins, RenderArgs ra, const uint4 *wind, const int *tile_choff) {
+__global__ void __launch_bounds__(PB, DVG_PF_MINB) k_render_pf(SceneView sc, BinView bins, RenderArgs ra, const uint4 *wind, const unsigned *relevant, const int *tile_choff) {
     // gradients go straight to one of the private copies of the gradient buffer (dvg_kernel_util.cuh grad_replica):
     // the per-block shared-memory hash + barrier + flush this kernel used before was 40% of its time at 2048^2
     const GlobalSink sk{BACKWARD ? grad_replica(ra) : nullptr};
@@ -79,16 +80,23 @@ __global__ void __launch_bounds__(PB, DVG_PF_MINB) k_render_pf(SceneView sc, Bin
         const int part_w = l >> 5;                 // this warp's item within the tile (pixel_item, dvg_wave.cu)
         const int c0 = tile_choff[tile];
         const int nch = tile_choff[tile + 1] - c0;
-        const uint4 *wp = wind + (((int64_t)c0 * wpt + (int64_t)part_w * nch) * 32 + (tid & 31));
+        const int64_t w0 = ((int64_t)c0 * wpt + (int64_t)part_w * nch) * 32 + (tid & 31);
         const bool have_words = part_w < wpt;
-        uint4 wd = make_uint4(0u, 0u, 0u, 0u);
-        for (int i = beg; i < end; i++) {
-            const int k = (i - beg) & 31;
-            if (k == 0 && have_words) wd = wp[(int64_t)((i - beg) >> 5) * 32];
-            const PrimRef pr = load_prim(sc, bins.items[i]);   // block-uniform loads
-            const unsigned ww = (k < 8 ? wd.x : (k < 16 ? wd.y : (k < 24 ? wd.z : wd.w)));
-            const int nib = (int)((ww >> (4 * (k & 7))) & 15u);
-            tr.template step<true>(sc, pr, (nib ^ 8) - 8);
+        for (int c = 0; c < nch; c++) {
+            // candidates that matter to some sample of this warp (the same word in every lane); the others change no
+            // state: no distance within reach, no winding contribution, and a group or shape none of whose candidates is
+            // visited emits nothing
+            unsigned m = have_words ? relevant[w0 + (int64_t)c * 32] : 0u;
+            if (m == 0u) continue;
+            const uint4 wd = wind[w0 + (int64_t)c * 32];
+            while (m) {
+                const int k = __ffs(m) - 1;
+                m &= m - 1u;
+                const PrimRef pr = load_prim(sc, bins.items[beg + c * 32 + k]);   // warp-uniform loads
+                const unsigned ww = (k < 8 ? wd.x : (k < 16 ? wd.y : (k < 24 ? wd.z : wd.w)));
+                const int nib = (int)((ww >> (4 * (k & 7))) & 15u);
+                tr.template step<true>(sc, pr, (nib ^ 8) - 8);
+            }
         }
     } else {
         for (int i = beg; i < end; i++) {
@@ -205,17 +213,17 @@ static int pf_blocks(const BinView &bins, const RenderArgs &ra) {
 
 // `wind` / `tile_choff`: the winding words of the pre-pass and the chunk offsets they are laid out by, or null (the
 // winding test then runs inline: scenes without fills, renders beyond the 27-bit word index)
-void launch_render_pf(const SceneView &sc, const BinView &bins, const RenderArgs &ra, const unsigned *wind, const int *tile_choff,
+void launch_render_pf(const SceneView &sc, const BinView &bins, const RenderArgs &ra, const unsigned *wind, const unsigned *relevant, const int *tile_choff,
                       bool backward, cudaStream_t st) {
     const int nblk = pf_blocks(bins, ra);
     if (nblk <= 0) return;
     const uint4 *w4 = reinterpret_cast<const uint4 *>(wind);
     if (backward) {
-        if (wind) DVG_LAUNCH_AS("k_render_pf<true>", kpf_bwd_words, dim3(nblk), dim3(PB), 0, st, sc, bins, ra, w4, tile_choff);
-        else DVG_LAUNCH_AS("k_render_pf<true>", kpf_bwd_inline, dim3(nblk), dim3(PB), 0, st, sc, bins, ra, w4, tile_choff);
+        if (wind) DVG_LAUNCH_AS("k_render_pf<true>", kpf_bwd_words, dim3(nblk), dim3(PB), 0, st, sc, bins, ra, w4, relevant, tile_choff);
+        else DVG_LAUNCH_AS("k_render_pf<true>", kpf_bwd_inline, dim3(nblk), dim3(PB), 0, st, sc, bins, ra, w4, relevant, tile_choff);
     } else {
-        if (wind) DVG_LAUNCH_AS("k_render_pf<false>", kpf_fwd_words, dim3(nblk), dim3(PB), 0, st, sc, bins, ra, w4, tile_choff);
-        else DVG_LAUNCH_AS("k_render_pf<false>", kpf_fwd_inline, dim3(nblk), dim3(PB), 0, st, sc, bins, ra, w4, tile_choff);
+        if (wind) DVG_LAUNCH_AS("k_render_pf<false>", kpf_fwd_words, dim3(nblk), dim3(PB), 0, st, sc, bins, ra, w4, relevant, tile_choff);
+        else DVG_LAUNCH_AS("k_render_pf<false>", kpf_fwd_inline, dim3(nblk), dim3(PB), 0, st, sc, bins, ra, w4, relevant, tile_choff);
     }
 }
 

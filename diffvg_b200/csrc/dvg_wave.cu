@@ -106,9 +106,15 @@ __device__ __noinline__ void wave_exact_in_place(const SceneView &sc, const Wave
 // FILLS: the scene has filled groups.  The winding test of a y-monotone cubic (DVG_PF_YMONO) whose control points all lie
 // to the right of the sample is answered here from the primitive's PrimWindCert record (dvg_geom.cuh wind_cert_answer:
 // a dozen FP64 operations, warp-coherent because all lanes test the same segment) instead of being queued.
-template <bool INPLACE, bool FILLS>
+// PF: the winding pre-pass of the prefiltered path (sample_color_prefiltered, diffvg.cpp:835-1113).  Only the winding
+// numbers are taken from here -- the gating tests are those of the sampled path (diffvg.cpp:42-45, 71-78,
+// winding_number.h:162-169) -- and the `hit` word of a chunk carries, the same in every lane, the candidates that matter
+// to SOME sample of the item: those with a winding test, and those a closest-point search can reach (rects; path segments
+// whose leaf box is within the search radius -- 1 for a fill-only group, unbounded for a stroked one: compute_distance.h:
+// 285-294 prunes against a running minimum that starts there).  k_render_pf walks only those.
+template <bool INPLACE, bool FILLS, bool PF = false>
 DVG_D void wave_classify(const SceneView &sc, const BinView &bins, const WaveView &wv, int tile, int64_t cb,
-                         F2 cpt, bool active, WaveScratch &ws, bool fast_accept, bool winding_only = false) {
+                         F2 cpt, bool active, WaveScratch &ws, bool fast_accept) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
@@ -129,7 +135,7 @@ DVG_D void wave_classify(const SceneView &sc, const BinView &bins, const WaveVie
             box = sc.prim_box[e];
             thick = sc.prim_thick[e];
         }
-        unsigned need_s = 0, need_f = 0;
+        unsigned need_s = 0, need_f = 0, relevant = 0;
         unsigned wn0 = 0u, wn1 = 0u, wn2 = 0u, wn3 = 0u;   // winding nibbles answered here
         for (int k = 0; k < n; k++) {
             PrimRef pr;
@@ -138,8 +144,14 @@ DVG_D void wave_classify(const SceneView &sc, const BinView &bins, const WaveVie
             pr.thick = __shfl_sync(FULL, thick, k);
             pr.tf = __shfl_sync(FULL, tf, k); pr.inst = __shfl_sync(FULL, inst, k); pr.group = __shfl_sync(FULL, group, k);
             const int nd = ct.template step<TM_CLASSIFY>(sc, pr);
-            need_s |= (unsigned)(nd & 1) << k;   // (cleared below for the winding pre-pass of the prefiltered path)
+            if (!PF) need_s |= (unsigned)(nd & 1) << k;
             bool nf = ((nd >> 1) & 1) != 0;
+            if (PF) {
+                const int type = pr.tf & DVG_PF_TYPE_MASK;
+                const bool reach = type == PRIM_RECT ||
+                    (type <= PRIM_CUBIC && ((pr.tf & DVG_PF_SINGLE) || box_within_distance(pr.box, ct.lpt, ct.has_stroke ? INFINITY : 1.f)));
+                relevant |= (unsigned)((ct.g_visit && (reach || nf)) ? 1u : 0u) << k;
+            }
             if (FILLS && (pr.tf & DVG_PF_YMONO)) {   // (uniform: every lane holds the same candidate)
                 const int ek = __shfl_sync(FULL, e, k);
                 int w = 0;
@@ -151,9 +163,6 @@ DVG_D void wave_classify(const SceneView &sc, const BinView &bins, const WaveVie
             }
             need_f |= (unsigned)(nf ? 1u : 0u) << k;
         }
-        // the prefiltered path (sample_color_prefiltered) takes only the winding numbers from here: its gating tests are
-        // those of the sampled path (diffvg.cpp:42-45, 71-78, winding_number.h:162-169); distances are searched by k_render_pf
-        if (winding_only) need_s = 0u;
         ws.hit[lane] = 0u;
         const int64_t word0 = (cb + c) * 32;
         if (FILLS) {   // written first: the exact tests (and a pair that finds its queue full and is answered in place) OR into these words
@@ -243,7 +252,7 @@ DVG_D void wave_classify(const SceneView &sc, const BinView &bins, const WaveVie
             }
         }
         __syncwarp();
-        wv.hit[word0 + lane] = ws.hit[lane];
+        wv.hit[word0 + lane] = PF ? __reduce_or_sync(FULL, relevant) : ws.hit[lane];
         __syncwarp();
     }
 }
@@ -282,7 +291,7 @@ DVG_D PixelItem pixel_item(const BinView &bins, const RenderArgs &ra, const Wave
 
 DVG_D bool wave_overflowed(const WaveView &wv) { return wv.counters[0] > wv.cap_s || wv.counters[1] > wv.cap_f; }
 
-template <bool INPLACE, bool FILLS>
+template <bool INPLACE, bool FILLS, bool PF = false>
 __global__ void __launch_bounds__(WB, DVG_WB_MIN) k_wave_classify_px(SceneView sc, BinView bins, RenderArgs ra, WaveView wv, int num_items) {
     __shared__ WaveScratch s_ws[WNW];
     if (INPLACE && !wave_overflowed(wv)) return;
@@ -292,8 +301,7 @@ __global__ void __launch_bounds__(WB, DVG_WB_MIN) k_wave_classify_px(SceneView s
         if (pi.active)
             sample_position(sc.canvas_w, sc.canvas_h, ra.width, ra.height, ra.nsx, ra.nsy, ra.seeds ? ra.seeds[pi.scene] : ra.seed,
                             ra.use_prefiltering != 0, pi.x, pi.y, pi.sx, pi.sy, pi.idx, pt, cpt);
-        wave_classify<INPLACE, FILLS>(sc, bins, wv, pi.tile, pi.cb, cpt, pi.active, s_ws[threadIdx.x >> 5], (ra.flags & DVG_RF_FAST_ACCEPT) != 0,
-                                      ra.use_prefiltering != 0);
+        wave_classify<INPLACE, FILLS, PF>(sc, bins, wv, pi.tile, pi.cb, cpt, pi.active, s_ws[threadIdx.x >> 5], (ra.flags & DVG_RF_FAST_ACCEPT) != 0);
     }
 }
 
@@ -352,6 +360,7 @@ __global__ void __launch_bounds__(WB, DVG_WB_MIN) k_wave_classify_edge(SceneView
 // (the launch macro takes one token per argument: names for the instantiations)
 constexpr auto kc_px = k_wave_classify_px<false, false>, kc_px_fills = k_wave_classify_px<false, true>;
 constexpr auto kr_px = k_wave_classify_px<true, false>, kr_px_fills = k_wave_classify_px<true, true>;
+constexpr auto kc_px_pf = k_wave_classify_px<false, true, true>, kr_px_pf = k_wave_classify_px<true, true, true>;
 constexpr auto kc_edge = k_wave_classify_edge<false, false>, kc_edge_fills = k_wave_classify_edge<false, true>;
 constexpr auto kr_edge = k_wave_classify_edge<true, false>, kr_edge_fills = k_wave_classify_edge<true, true>;
 
@@ -819,14 +828,16 @@ int wave_edge_samples_per_item() { return W_EDGE_SPI; }
 void launch_wave_classify_px(const SceneView &sc, const BinView &bins, const RenderArgs &ra, const WaveView &wv, cudaStream_t st) {
     const int items = wave_pixel_items(bins, ra);
     if (items <= 0) return;
-    if (wv.wind) DVG_LAUNCH_AS("k_wave_classify_px<false>", kc_px_fills, dim3((items + WNW - 1) / WNW), dim3(WB), 0, st, sc, bins, ra, wv, items);
+    if (ra.use_prefiltering) DVG_LAUNCH_AS("k_wave_classify_px<false>", kc_px_pf, dim3((items + WNW - 1) / WNW), dim3(WB), 0, st, sc, bins, ra, wv, items);
+    else if (wv.wind) DVG_LAUNCH_AS("k_wave_classify_px<false>", kc_px_fills, dim3((items + WNW - 1) / WNW), dim3(WB), 0, st, sc, bins, ra, wv, items);
     else DVG_LAUNCH_AS("k_wave_classify_px<false>", kc_px, dim3((items + WNW - 1) / WNW), dim3(WB), 0, st, sc, bins, ra, wv, items);
 }
 void launch_wave_retry_px(const SceneView &sc, const BinView &bins, const RenderArgs &ra, const WaveView &wv, cudaStream_t st) {
     const int items = wave_pixel_items(bins, ra);
     if (items <= 0) return;
     const dim3 grid(std::min((items + WNW - 1) / WNW, g_num_sms * DVG_WB_MIN));
-    if (wv.wind) DVG_LAUNCH_AS("k_wave_classify_px<true>", kr_px_fills, grid, dim3(WB), 0, st, sc, bins, ra, wv, items);
+    if (ra.use_prefiltering) DVG_LAUNCH_AS("k_wave_classify_px<true>", kr_px_pf, grid, dim3(WB), 0, st, sc, bins, ra, wv, items);
+    else if (wv.wind) DVG_LAUNCH_AS("k_wave_classify_px<true>", kr_px_fills, grid, dim3(WB), 0, st, sc, bins, ra, wv, items);
     else DVG_LAUNCH_AS("k_wave_classify_px<true>", kr_px, grid, dim3(WB), 0, st, sc, bins, ra, wv, items);
 }
 

@@ -64,9 +64,11 @@ def main():
         for k, v in mangled.items():
             if k in norm:
                 key = v
-        m2 = re.search(r'(k_\w+)<\(?(?:bool)?\)?([01])>', name)
-        if key is None and m2:      # template<bool>: the mangled name carries ILb0E / ILb1E
-            key = '%sILb%sE' % (m2.group(1), m2.group(2))
+        m2 = re.search(r'(k_\w+)<([^>]*)>', name)
+        if key is None and m2:      # template<bool, ...>: the mangled name carries ILb0ELb1E...E
+            bools = re.findall(r'\(bool\)([01])', m2.group(2))
+            if bools:
+                key = '%sI%sE' % (m2.group(1), ''.join('Lb%sE' % b for b in bools))
         sass = [s for s in sass_lines(key or ksub)]
         if len(sass) != len(data):
             print('warning: %d SASS rows in report vs %d in library for %s' % (len(data), len(sass), name[:60]))
