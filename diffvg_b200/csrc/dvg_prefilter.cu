@@ -123,7 +123,11 @@ __global__ void __launch_bounds__(PB, DVG_PF_MINB) k_render_pf(SceneView sc, Bin
                 float *d = ra.d_background + 4 * (y * ra.width + x);
                 atomicAdd(d + 0, d_color.x); atomicAdd(d + 1, d_color.y); atomicAdd(d + 2, d_color.z); atomicAdd(d + 3, d_color.w);
             }
-            if (!(ra.flags & 4u)) d_radius_acc = filter_radius_grad(sc, ra, x, y, pt, color);   // DVG_BWD_SKIP_FILTER_GRAD
+        }
+        if (!(ra.flags & 4u)) {   // DVG_BWD_SKIP_FILTER_GRAD (block-uniform: every lane of the warp is here)
+            const bool box_fast = sc.filter.type == 0 && pow2 && (int)ceilf(sc.filter.radius) == 1;
+            if (box_fast) d_radius_acc = filter_radius_grad_box(sc, ra, x, y, pt, color, active, grp, tid & 31);
+            else if (active) d_radius_acc = filter_radius_grad(sc, ra, x, y, pt, color);
         }
         d_radius_acc = warp_sum(d_radius_acc);
         if ((tid & 31) == 0) sk.add(sc.filter_radius_off, d_radius_acc);
