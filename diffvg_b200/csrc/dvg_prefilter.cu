@@ -17,6 +17,8 @@ constexpr int PB = 256;  // threads per block
 #ifndef DVG_PF_MINB
 #define DVG_PF_MINB 2
 #endif
+// resident blocks per SM: the forward kernel without the inline winding test fits three (80 registers, 2.95 vs 3.40 ms at
+// flower.svg 2048^2); the backward kernel (fragment records, distance gradients) and the inline forms are slower with three
 
 DVG_D PrimRef load_prim(const SceneView &sc, int e) {
     PrimRef pr;
@@ -38,7 +40,7 @@ DVG_D PrimRef load_prim(const SceneView &sc, int e) {
 // and the backward kernel repeated all of them; now they run one per lane in k_wave_solve_fill and the backward pass
 // re-uses the forward pass's words.
 template <bool BACKWARD, bool WORDS>
-__global__ void __launch_bounds__(PB, DVG_PF_MINB) k_render_pf(SceneView sc, BinView bins, RenderArgs ra, const uint4 *wind, const unsigned *relevant, const int *tile_choff) {
+__global__ void __launch_bounds__(PB, (!BACKWARD && WORDS) ? DVG_PF_MINB + 1 : DVG_PF_MINB) k_render_pf(SceneView sc, BinView bins, RenderArgs ra, const uint4 *wind, const unsigned *relevant, const int *tile_choff) {
     // gradients go straight to one of the private copies of the gradient buffer (dvg_kernel_util.cuh grad_replica):
     // the per-block shared-memory hash + barrier + flush this kernel used before was 40% of its time at 2048^2
     const GlobalSink sk{BACKWARD ? grad_replica(ra) : nullptr};
