@@ -22,6 +22,7 @@ thread_local std::string g_err;
 float *g_debug_out = nullptr;  // dvg_debug_set_boundary_dump
 long long g_debug_edge_pass_samples = 0;   // dvg_debug_set_limits
 long long g_debug_pair_capacity = 0;
+bool g_pf_nocache = getenv("DVG_PF_NOCACHE") != nullptr && getenv("DVG_PF_NOCACHE")[0] == '1';   // dvg_debug_set_prefilter_inline bit 1
 bool g_pf_inline = getenv("DVG_PF_INLINE") != nullptr && getenv("DVG_PF_INLINE")[0] == '1';   // dvg_debug_set_prefilter_inline (env: measurements only)
 bool g_fast_accept = getenv("DVG_FAST_ACCEPT") != nullptr && getenv("DVG_FAST_ACCEPT")[0] == '1';   // dvg_set_fast_stroke_accept (env: measurements only)
 
@@ -102,6 +103,10 @@ struct DvgScene {
     // which pixel pass the result words currently hold (forward's are reused by the interior backward pass)
     bool wpx_valid = false;
     int wpx_w = 0, wpx_h = 0, wpx_nsx = 0, wpx_nsy = 0, wpx_r0 = 0, wpx_r1 = 0, wpx_pf = 0; uint64_t wpx_seed = 0; uint32_t wpx_fast = 0;
+    // fragment cache of the prefiltered path (dvg_distance.cuh PfCache): what the forward pass left, and for which render
+    DevBuf d_pf_recs, d_pf_count;
+    bool pfc_valid = false;
+    int pfc_w = 0, pfc_h = 0, pfc_nsx = 0, pfc_nsy = 0, pfc_r0 = 0, pfc_r1 = 0;
     int32_t *h_pinned = nullptr;  // [0] error flag, [1] total bin items
     float *h_params_pinned = nullptr;  // staging for host-resident params (true async H2D)
     cudaEvent_t h_params_free = nullptr;  // recorded after the H2D copy that last read the staging buffer
@@ -372,7 +377,7 @@ int ensure_bins(DvgScene *s, int width, int height, int spp, int pf, cudaStream_
         int rc = flags_too ? parse_build_flags(s) : finish_build(s, st);
         if (rc) return rc;
     }
-    s->wpx_valid = false;
+    s->wpx_valid = false; s->pfc_valid = false;
     CK(s->d_bin_items.ensure(sizeof(int) * std::max(total, 1)));
     bb.items = s->d_bin_items.as<int>();
     launch_bin_fill(bv, bb, st);
@@ -507,45 +512,73 @@ int wave_pixel_pass(DvgScene *s, const SceneView &sc, const BinView &bins, const
     return DVG_OK;
 }
 
-// Prefiltered pixel pass (sample_color_prefiltered): the winding numbers of the filled groups are answered first by the
-// wavefront pair (classify with the stroke side masked -> k_wave_solve_fill) and k_render_pf reads them as words; the
-// backward pass of the same (scene, size, samples, rows) re-uses the forward pass's words (the prefiltered sample
-// positions do not depend on the seed).  Scenes without fills, and renders whose words would not fit the 27-bit index,
-// run the winding test inline.
+// Prefiltered pixel pass (sample_color_prefiltered).  Two things are kept from the forward pass for the backward pass of the
+// same (scene, size, samples, rows) -- the prefiltered sample positions do not depend on the seed:
+//  * the winding numbers of the filled groups, answered by the wavefront pair (classify with the stroke side masked ->
+//    k_wave_solve_fill) and read by k_render_pf as words.  Scenes without fills, and renders whose words would not fit the
+//    27-bit index, run the winding test inline;
+//  * the first DVG_PFC_K fragment records of every sample (PfCache): the backward pass differentiates those samples from
+//    the records (k_pf_backward_cached) and walks the candidate lists only for samples with more fragments.
+constexpr int64_t kPfCacheMaxBytes = (int64_t)8 << 30;
 int wave_pf_pass(DvgScene *s, const SceneView &sc, const BinView &bins, const RenderArgs &ra, bool backward, cudaStream_t st) {
     const int64_t wpt = wave_items_per_tile(bins, ra);
     const int items = wave_pixel_items(bins, ra);
-    const int64_t words = (int64_t)s->total_chunks * wpt * 32;
-    if (!s->has_fills || g_pf_inline || words >= ((int64_t)1 << 27) || items <= 0) {
-        launch_render_pf(sc, bins, ra, nullptr, nullptr, nullptr, backward, st);
+    const int64_t nwords = (int64_t)s->total_chunks * wpt * 32;
+    const bool words = s->has_fills && !g_pf_inline && nwords < ((int64_t)1 << 27) && items > 0;
+    WaveView wv;
+    memset(&wv, 0, sizeof wv);
+    if (words) {
+        int rc = wave_view(s, (int64_t)s->total_chunks * wpt, (int64_t)items * 32, &wv);
+        if (rc) return rc;
+        const bool reuse = s->wpx_valid && s->wpx_w == ra.width && s->wpx_h == ra.height && s->wpx_nsx == ra.nsx && s->wpx_nsy == ra.nsy &&
+                           s->wpx_r0 == ra.row_begin && s->wpx_r1 == ra.row_end && s->wpx_pf == ra.use_prefiltering;
+        if (!reuse) {
+            s->wpx_valid = false;
+            const bool small = (int64_t)s->total_chunks * wpt * 32 * 32 <= kSmallPairs;
+            CK(cudaMemsetAsync(wv.counters, 0, sizeof(int) * 2, st));
+            launch_wave_classify_px(sc, bins, ra, wv, st);
+            CK(cudaGetLastError());
+            launch_wave_solve(sc, wv, false, true, st);
+            CK(cudaGetLastError());
+            if (!small) { launch_wave_retry_px(sc, bins, ra, wv, st); CK(cudaGetLastError()); }
+            if (!s->counts_pending[0]) {
+                CK(cudaMemcpyAsync(s->h_counts, wv.counters, sizeof(int) * 4, cudaMemcpyDeviceToHost, st));
+                CK(cudaEventRecord(s->ev_counts[0], st));
+                s->counts_pending[0] = true;
+                s->counts_stream[0] = st;
+            }
+            s->wpx_valid = true; s->wpx_w = ra.width; s->wpx_h = ra.height; s->wpx_nsx = ra.nsx; s->wpx_nsy = ra.nsy;
+            s->wpx_seed = ra.seed; s->wpx_r0 = ra.row_begin; s->wpx_r1 = ra.row_end; s->wpx_pf = ra.use_prefiltering;
+            s->wpx_fast = ra.flags & DVG_RF_FAST_ACCEPT;
+        }
+    }
+    const int64_t threads = pf_launch_threads(bins, ra);
+    const bool cacheable = !g_pf_nocache && threads > 0 && threads * DVG_PFC_K * 32 <= kPfCacheMaxBytes;
+    PfCache pc;
+    pc.recs = nullptr; pc.count = nullptr;
+    if (!backward) {
+        s->pfc_valid = false;
+        if (cacheable) {
+            CK(s->d_pf_recs.ensure((size_t)threads * DVG_PFC_K * 32));
+            CK(s->d_pf_count.ensure(sizeof(int) * (size_t)threads));
+            pc.recs = s->d_pf_recs.as<U4>(); pc.count = s->d_pf_count.as<int>();
+        }
+        launch_render_pf(sc, bins, ra, wv.wind, wv.hit, wv.tile_choff, pc, false, st);
         CK(cudaGetLastError());
+        if (cacheable) {
+            s->pfc_valid = true; s->pfc_w = ra.width; s->pfc_h = ra.height; s->pfc_nsx = ra.nsx; s->pfc_nsy = ra.nsy;
+            s->pfc_r0 = ra.row_begin; s->pfc_r1 = ra.row_end;
+        }
         return DVG_OK;
     }
-    WaveView wv;
-    int rc = wave_view(s, (int64_t)s->total_chunks * wpt, (int64_t)items * 32, &wv);
-    if (rc) return rc;
-    const bool reuse = s->wpx_valid && s->wpx_w == ra.width && s->wpx_h == ra.height && s->wpx_nsx == ra.nsx && s->wpx_nsy == ra.nsy &&
-                       s->wpx_r0 == ra.row_begin && s->wpx_r1 == ra.row_end && s->wpx_pf == ra.use_prefiltering;
-    if (!reuse) {
-        s->wpx_valid = false;
-        const bool small = (int64_t)s->total_chunks * wpt * 32 * 32 <= kSmallPairs;
-        CK(cudaMemsetAsync(wv.counters, 0, sizeof(int) * 2, st));
-        launch_wave_classify_px(sc, bins, ra, wv, st);
+    const bool cached = cacheable && s->pfc_valid && s->pfc_w == ra.width && s->pfc_h == ra.height && s->pfc_nsx == ra.nsx &&
+                        s->pfc_nsy == ra.nsy && s->pfc_r0 == ra.row_begin && s->pfc_r1 == ra.row_end;
+    if (cached) {
+        pc.recs = s->d_pf_recs.as<U4>(); pc.count = s->d_pf_count.as<int>();
+        launch_pf_backward_cached(sc, bins, ra, pc, st);
         CK(cudaGetLastError());
-        launch_wave_solve(sc, wv, false, true, st);
-        CK(cudaGetLastError());
-        if (!small) { launch_wave_retry_px(sc, bins, ra, wv, st); CK(cudaGetLastError()); }
-        if (!s->counts_pending[0]) {
-            CK(cudaMemcpyAsync(s->h_counts, wv.counters, sizeof(int) * 4, cudaMemcpyDeviceToHost, st));
-            CK(cudaEventRecord(s->ev_counts[0], st));
-            s->counts_pending[0] = true;
-            s->counts_stream[0] = st;
-        }
-        s->wpx_valid = true; s->wpx_w = ra.width; s->wpx_h = ra.height; s->wpx_nsx = ra.nsx; s->wpx_nsy = ra.nsy;
-        s->wpx_seed = ra.seed; s->wpx_r0 = ra.row_begin; s->wpx_r1 = ra.row_end; s->wpx_pf = ra.use_prefiltering;
-        s->wpx_fast = ra.flags & DVG_RF_FAST_ACCEPT;
     }
-    launch_render_pf(sc, bins, ra, wv.wind, wv.hit, wv.tile_choff, backward, st);
+    launch_render_pf(sc, bins, ra, wv.wind, wv.hit, wv.tile_choff, pc, true, st);   // (with a cache: the samples it could not hold)
     CK(cudaGetLastError());
     return DVG_OK;
 }
@@ -725,7 +758,7 @@ int dvg_scene_set_params(DvgScene *s, const float *params, int64_t num_params, i
     s->checked = false;
     s->scene_error = 0;
     s->bin_w = s->bin_h = 0;   // bins depend on the geometry
-    s->wpx_valid = false;
+    s->wpx_valid = false; s->pfc_valid = false;
     s->w_valid = s->w_valid && true;  // the weight image does not depend on the scene, only on the filter (checked later)
     return DVG_OK;
 }
@@ -1017,7 +1050,7 @@ int dvg_debug_prim_tests(DvgScene *s, int width, int height, int nsx, int nsy, u
 }
 
 int dvg_set_fast_stroke_accept(int on) { g_fast_accept = on != 0; return DVG_OK; }
-int dvg_debug_set_prefilter_inline(int on) { g_pf_inline = on != 0; return DVG_OK; }
+int dvg_debug_set_prefilter_inline(int on) { g_pf_inline = (on & 1) != 0; g_pf_nocache = (on & 2) != 0; return DVG_OK; }
 
 int dvg_profile_enable(int on) {
     dvg::g_profile_on = on != 0;

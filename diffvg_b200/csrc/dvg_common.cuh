@@ -9,6 +9,7 @@
 // on float arguments resolve to the double overloads in the reference build) is written
 // out explicitly here.
 #pragma once
+#include <string.h>
 #include <stdint.h>
 #include <math.h>
 
@@ -27,8 +28,23 @@
 namespace dvg {
 
 struct F2 { float x, y; };
+struct alignas(16) U4 { unsigned x, y, z, w; };   // 16-byte record word (one 128-bit load / store on the device)
 struct F4 { float x, y, z, w; };
 
+DVG_HD unsigned dvg_float_bits(float f) {
+#if defined(__CUDA_ARCH__)
+    return __float_as_uint(f);
+#else
+    unsigned u; memcpy(&u, &f, sizeof u); return u;
+#endif
+}
+DVG_HD float dvg_bits_float(unsigned u) {
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(u);
+#else
+    float f; memcpy(&f, &u, sizeof f); return f;
+#endif
+}
 DVG_HD F2 mk2(float x, float y) { F2 r; r.x = x; r.y = y; return r; }
 DVG_HD F4 mk4(float x, float y, float z, float w) { F4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
 DVG_HD F2 operator+(F2 a, F2 b) { return mk2(a.x + b.x, a.y + b.y); }

@@ -352,11 +352,57 @@ struct PfFragment {   // what the backward pass needs per fragment
     F4 prev;          // premultiplied accumulation before this fragment
 };
 
-template <bool RECORD>
+// Colour and coverage of one prefiltered fragment (diffvg.cpp:861-932): what end_group composites, and what the cached
+// backward kernel (dvg_prefilter.cu) replays from a fragment record -- one function, so both form the same floats.
+// `inst`: the closest shape instance (its stroke width enters a stroke fragment's coverage).  Returns the coverage.
+DVG_HD float pf_coverage(const SceneView &sc, bool is_stroke, int inst, float d) {
+    if (!is_stroke) return smoothstep(d);
+    const InstInfo &ii = sc.insts[inst];
+    const int *srec = sc.topo + sc.topo[DVG_H_OFF_SHAPES] + ii.shape * DVG_SHAPE_REC_LEN;
+    const float sw = srec[DVG_S_WIDTH_OFF] >= 0 ? sc.params[srec[DVG_S_WIDTH_OFF]] : 0.f;
+    return smoothstep(fabsf(d) + sw) - smoothstep(fabsf(d) - sw);
+}
+DVG_HD F4 pf_fragment_color(const SceneView &sc, const GroupInfo &g, bool is_stroke, float w, F2 cpt) {
+    F4 c = is_stroke ? eval_color(g.stroke_type, sc.params + g.stroke_off, g.stroke_stops, cpt)
+                     : eval_color(g.fill_type, sc.params + g.fill_off, g.fill_stops, cpt);
+    c.w *= w;
+    return c;
+}
+DVG_HD void pf_composite(F4 &accum, F4 c) {   // "over", premultiplied (diffvg.cpp:944-955)
+    const float oma = 1 - c.w;
+    accum.x = accum.x * oma + c.w * c.x;
+    accum.y = accum.y * oma + c.w * c.y;
+    accum.z = accum.z * oma + c.w * c.z;
+    accum.w = accum.w * oma + c.w;
+}
+
+// Fragment cache of the prefiltered path: the forward kernel leaves the first DVG_PFC_K fragments of every sample (32 bytes
+// each: PfFragment without `prev`, which a replay of the compositing gives back) and the fragment count; the backward pass
+// of the same (scene, size, samples, rows) differentiates from them without walking the candidate lists again.  Samples
+// with more fragments than that go through the full backward kernel.  Layout: thread t of the launch (warp w = t / 32)
+// owns the records [(w * K + slot) * 2 + half][lane] (U4 each: a warp's store is 512 contiguous bytes).
+#define DVG_PFC_K 4
+struct PfCache {
+    U4 *recs;   // null: no cache
+    int *count;    // [threads of the launch] fragments emitted (may exceed DVG_PFC_K)
+};
+DVG_HD void pf_cache_pack(const PfFragment &f, U4 &a, U4 &b) {
+    a.x = (unsigned)((f.key << 1) | (f.within ? 1 : 0)); a.y = (unsigned)f.inst; a.z = dvg_float_bits(f.d); a.w = dvg_float_bits(f.cp.x);
+    b.x = dvg_float_bits(f.cp.y); b.y = (unsigned)f.base_id; b.z = (unsigned)f.point_id; b.w = dvg_float_bits(f.t_root);
+}
+DVG_HD void pf_cache_unpack(U4 a, U4 b, PfFragment &f) {
+    f.key = (int)(a.x >> 1); f.within = (a.x & 1u) != 0u; f.inst = (int)a.y; f.d = dvg_bits_float(a.z); f.cp.x = dvg_bits_float(a.w);
+    f.cp.y = dvg_bits_float(b.x); f.base_id = (int)b.y; f.point_id = (int)b.z; f.t_root = dvg_bits_float(b.w);
+}
+
+// RECORD: 0 colour only; 1 fragment records into `frags` (the full backward kernel); 2 the first DVG_PFC_K fragment records
+// into the cache slots of this thread (the forward kernel; `crec` may be null)
+template <int RECORD>
 struct PrefilterTracer {
     F2 cpt;
     bool active;
     PfFragment *frags;
+    U4 *crec;             // RECORD == 2: this thread's first cache record (slot stride 64 U4), or null
     F4 accum;
     int nfrag, sp;
     // current group
@@ -371,7 +417,7 @@ struct PrefilterTracer {
     float sh_radius;
 
     DVG_HD void init(F2 cpt_, bool active_, F4 first, PfFragment *frags_) {
-        cpt = cpt_; active = active_; frags = frags_; accum = first; nfrag = 0; sp = 0;
+        cpt = cpt_; active = active_; frags = frags_; crec = nullptr; accum = first; nfrag = 0; sp = 0;
         cur_g = -1; cur_inst = -1; gp = nullptr; lpt = cpt_;
         g_visit = g_fill_ok = s_fill_ok = has_stroke = has_fill = multi = false;
         winding = w_shape = 0;
@@ -380,7 +426,7 @@ struct PrefilterTracer {
     }
 
     DVG_HD void emit(F4 c, int is_stroke, const DistHit &h, float d) {
-        if (RECORD) {
+        if (RECORD == 1) {
             if (sp < DVG_MAXPF) {
                 PfFragment &f = frags[sp];
                 f.key = (cur_g << 1) | is_stroke; f.inst = h.inst; f.d = d; f.cp = h.cp;
@@ -388,11 +434,17 @@ struct PrefilterTracer {
                 sp++;
             }
         }
-        const float oma = 1 - c.w;
-        accum.x = accum.x * oma + c.w * c.x;
-        accum.y = accum.y * oma + c.w * c.y;
-        accum.z = accum.z * oma + c.w * c.z;
-        accum.w = accum.w * oma + c.w;
+        if (RECORD == 2) {
+            if (crec != nullptr && nfrag < DVG_PFC_K) {
+                PfFragment f;
+                f.key = (cur_g << 1) | is_stroke; f.inst = h.inst; f.d = d; f.cp = h.cp;
+                f.base_id = h.base_id; f.point_id = h.point_id; f.t_root = h.t_root; f.within = h.found;
+                U4 a, b;
+                pf_cache_pack(f, a, b);
+                crec[nfrag * 64] = a; crec[nfrag * 64 + 32] = b;
+            }
+        }
+        pf_composite(accum, c);
         nfrag++;
     }
 
@@ -422,12 +474,10 @@ struct PrefilterTracer {
             const int *srec = sc.topo + sc.topo[DVG_H_OFF_SHAPES] + ii.shape * DVG_SHAPE_REC_LEN;
             const float sw = srec[DVG_S_WIDTH_OFF] >= 0 ? sc.params[srec[DVG_S_WIDTH_OFF]] : 0.f;
             const float d = gs.dist;
-            const float w = smoothstep(fabsf(d) + sw) - smoothstep(fabsf(d) - sw);
+            const float w = smoothstep(fabsf(d) + sw) - smoothstep(fabsf(d) - sw);   // (== pf_coverage(sc, true, gs.inst, d))
             if (w > 0) {
-                F4 c = eval_color(gp->stroke_type, sc.params + gp->stroke_off, gp->stroke_stops, cpt);
-                c.w *= w;
                 DistHit h = gs; h.found = true;
-                emit(c, 1, h, d);
+                emit(pf_fragment_color(sc, *gp, true, w, cpt), 1, h, d);
             }
         }
         if (has_fill) {  // diffvg.cpp:891-932
@@ -437,11 +487,7 @@ struct PrefilterTracer {
                 float d = gf.dist;   // == 1.f (the search radius) when nothing was found
                 if (!inside) d = -d;
                 const float w = smoothstep(d);
-                if (w > 0) {
-                    F4 c = eval_color(gp->fill_type, sc.params + gp->fill_off, gp->fill_stops, cpt);
-                    c.w *= w;
-                    emit(c, 0, gf, d);
-                }
+                if (w > 0) emit(pf_fragment_color(sc, *gp, false, w, cpt), 0, gf, d);
             }
         }
     }

@@ -109,8 +109,10 @@ void launch_scan(const int *in, int *out, int n, int *ws, cudaStream_t st);
 void launch_tile_row_costs(const int *offsets, int tiles_x, int tiles_y, float *out, cudaStream_t st);
 
 void launch_weight(const SceneView &sc, const RenderArgs &ra, int row_begin, int row_end, cudaStream_t st);
-void launch_render_pf(const SceneView &sc, const BinView &bins, const RenderArgs &ra, const unsigned *wind, const unsigned *relevant, const int *tile_choff,
-                      bool backward, cudaStream_t st);
+void launch_render_pf(const SceneView &sc, const BinView &bins, const RenderArgs &ra, const unsigned *wind, const unsigned *relevant,
+                      const int *tile_choff, const PfCache &pc, bool backward, cudaStream_t st);
+void launch_pf_backward_cached(const SceneView &sc, const BinView &bins, const RenderArgs &ra, const PfCache &pc, cudaStream_t st);
+int64_t pf_launch_threads(const BinView &bins, const RenderArgs &ra);
 void launch_sdf(const SceneView &sc, const RenderArgs &ra, const SdfArgs &sa, bool backward, cudaStream_t st);
 void launch_boundary_sort(const SceneView &sc, const BinView &bins, const RenderArgs &ra, const BoundaryWork &bw, cudaStream_t st);
 

@@ -32,50 +32,96 @@ DVG_D PrimRef load_prim(const SceneView &sc, int e) {
     return pr;
 }
 
-// WORDS: `relevant` (one word per (sample, chunk), the same in every lane of a warp: the candidates some sample of the warp
-// can be affected by, wave_classify<.., PF>) and the winding contributions come from the winding pre-pass (wave_classify<.., FILLS> with the stroke side masked ->
-// k_wave_solve_fill, dvg_wave.cu): `wind` holds one 4-bit answer per (sample, candidate) in the layout of the wavefront
-// passes (warp = item of 32 samples; word (cb + chunk) * 32 + lane, four 32-bit words each).  Inline, the FP64 root
-// solves of the winding test ran with the lanes that happened to need them, in a 128-register kernel at 22% occupancy,
-// and the backward kernel repeated all of them; now they run one per lane in k_wave_solve_fill and the backward pass
-// re-uses the forward pass's words.
-template <bool BACKWARD, bool WORDS>
-__global__ void __launch_bounds__(PB, (!BACKWARD && WORDS) ? DVG_PF_MINB + 1 : DVG_PF_MINB) k_render_pf(SceneView sc, BinView bins, RenderArgs ra, const uint4 *wind, const unsigned *relevant, const int *tile_choff) {
-    // gradients go straight to one of the private copies of the gradient buffer (dvg_kernel_util.cuh grad_replica):
-    // the per-block shared-memory hash + barrier + flush this kernel used before was 40% of its time at 2048^2
-    const GlobalSink sk{BACKWARD ? grad_replica(ra) : nullptr};
+// Geometry of one thread's sample: block -> (tile, part), thread -> sample of the tile (the layout of pixel_item, dvg_wave.cu).
+struct PfSample {
+    int tile, l, x, y, gthread;
+    bool active;
+    F2 pt, cpt;
+    const float *bg_px;
+    F4 first;
+};
+DVG_D PfSample pf_sample(const SceneView &sc, const BinView &bins, const RenderArgs &ra) {
+    PfSample ps;
     const int tile_row0 = ra.row_begin / bins.tile_h;
     const int spp = ra.nsx * ra.nsy;
     const int ns = bins.tile_w * bins.tile_h * spp;
     const int parts = (ns + PB - 1) / PB;
-    const int tile = blockIdx.x / parts + tile_row0 * bins.tiles_x;
+    ps.tile = blockIdx.x / parts + tile_row0 * bins.tiles_x;
     const int part = blockIdx.x % parts;
-    const int tx = tile % bins.tiles_x, ty = tile / bins.tiles_x;
+    const int tx = ps.tile % bins.tiles_x, ty = ps.tile / bins.tiles_x;
+    ps.l = part * PB + threadIdx.x;
+    ps.gthread = blockIdx.x * PB + threadIdx.x;
+    const int s = ps.l % spp, p = ps.l / spp;
+    ps.x = tx * bins.tile_w + p % bins.tile_w;
+    ps.y = ty * bins.tile_h + p / bins.tile_w;
+    ps.active = ps.l < ns && ps.x < ra.width && ps.y < ra.height && ps.y >= ra.row_begin && ps.y < ra.row_end;
+    ps.pt = mk2(0, 0); ps.cpt = mk2(0, 0);
+    ps.bg_px = nullptr;
+    ps.first = mk4(0, 0, 0, 0);
+    if (ps.active) {
+        const int sx = s % ra.nsx, sy = s / ra.nsx;
+        const int idx = ((ps.y * ra.width + ps.x) * ra.nsy + sy) * ra.nsx + sx;
+        sample_position(sc.canvas_w, sc.canvas_h, ra.width, ra.height, ra.nsx, ra.nsy, ra.seed, true, ps.x, ps.y, sx, sy, idx, ps.pt, ps.cpt);
+        if (ra.background) {
+            ps.bg_px = ra.background + 4 * (ps.y * ra.width + ps.x);
+            ps.first = mk4(ps.bg_px[0], ps.bg_px[1], ps.bg_px[2], ps.bg_px[3]);
+        }
+    }
+    return ps;
+}
+
+// The backward pass of one sample from its fragment records (diffvg.cpp:985-1111) and what surrounds it in the kernels.
+template <typename Tracer>
+DVG_D void pf_sample_backward(const SceneView &sc, const RenderArgs &ra, const PfSample &ps, const Tracer &tr, F4 color, const GlobalSink &sk) {
+    const F4 d_color = gather_d_color(sc.filter, ra.d_render_image, ra.weight_image, ra.width, ra.height, ps.pt);
+    float *dtr = ra.d_translation ? ra.d_translation + 2 * (ps.y * ra.width + ps.x) : nullptr;
+    if (tr.nfrag > 0) {
+        F4 d_bg;
+        prefilter_backward(sc, tr, color, d_color, sk, dtr, d_bg);
+        if (ps.bg_px && ra.d_background) {
+            float *d = ra.d_background + 4 * (ps.y * ra.width + ps.x);
+            atomicAdd(d + 0, d_bg.x); atomicAdd(d + 1, d_bg.y); atomicAdd(d + 2, d_bg.z); atomicAdd(d + 3, d_bg.w);
+        }
+    } else if (ps.bg_px && ra.d_background) {
+        float *d = ra.d_background + 4 * (ps.y * ra.width + ps.x);
+        atomicAdd(d + 0, d_color.x); atomicAdd(d + 1, d_color.y); atomicAdd(d + 2, d_color.z); atomicAdd(d + 3, d_color.w);
+    }
+}
+
+// WORDS: `relevant` (one word per (sample, chunk), the same in every lane of a warp: the candidates some sample of the warp
+// can be affected by, wave_classify<.., PF>) and the winding contributions come from the winding pre-pass
+// (wave_classify<.., FILLS, PF> -> k_wave_solve_fill, dvg_wave.cu): `wind` holds one 4-bit answer per (sample, candidate) in
+// the layout of the wavefront passes (warp = item of 32 samples; word (cb + chunk) * 32 + lane, four 32-bit words each).
+// Inline, the FP64 root solves of the winding test ran with the lanes that happened to need them, in a 128-register kernel
+// at 22% occupancy, and the backward kernel repeated all of them; now they run one per lane in k_wave_solve_fill and the
+// backward pass re-uses the forward pass's words.
+// `pc` (fragment cache, dvg_distance.cuh): the FORWARD kernel leaves every sample's first DVG_PFC_K fragment records and its
+// fragment count there; the BACKWARD kernel, when given one, only differentiates the samples with more fragments than that
+// (k_pf_backward_cached has done the others) and its warps leave at once when they hold none.
+template <bool BACKWARD, bool WORDS>
+__global__ void __launch_bounds__(PB, (!BACKWARD && WORDS) ? DVG_PF_MINB + 1 : DVG_PF_MINB) k_render_pf(SceneView sc, BinView bins, RenderArgs ra, const uint4 *wind, const unsigned *relevant, const int *tile_choff, PfCache pc) {
+    // gradients go straight to one of the private copies of the gradient buffer (dvg_kernel_util.cuh grad_replica):
+    // the per-block shared-memory hash + barrier + flush this kernel used before was 40% of its time at 2048^2
+    const GlobalSink sk{BACKWARD ? grad_replica(ra) : nullptr};
+    const int spp = ra.nsx * ra.nsy;
+    const int ns = bins.tile_w * bins.tile_h * spp;
     const int tid = threadIdx.x;
     const bool pow2 = (spp & (spp - 1)) == 0;
     const int grp = pow2 ? (spp < 32 ? spp : 32) : 1;
     PfFragment frags[BACKWARD ? DVG_MAXPF : 1];
     float d_radius_acc = 0.f;
-
-    const int l = part * PB + tid;
-    const int s = l % spp, p = l / spp;
-    const int px = p % bins.tile_w, py = p / bins.tile_w;
-    const int x = tx * bins.tile_w + px, y = ty * bins.tile_h + py;
-    const bool active = l < ns && x < ra.width && y < ra.height && y >= ra.row_begin && y < ra.row_end;
-    F2 pt = mk2(0, 0), cpt = mk2(0, 0);
-    const float *bg_px = nullptr;
-    F4 first = mk4(0, 0, 0, 0);
-    if (active) {
-        const int sx = s % ra.nsx, sy = s / ra.nsx;
-        const int idx = ((y * ra.width + x) * ra.nsy + sy) * ra.nsx + sx;
-        sample_position(sc.canvas_w, sc.canvas_h, ra.width, ra.height, ra.nsx, ra.nsy, ra.seed, true, x, y, sx, sy, idx, pt, cpt);
-        if (ra.background) {
-            bg_px = ra.background + 4 * (y * ra.width + x);
-            first = mk4(bg_px[0], bg_px[1], bg_px[2], bg_px[3]);
-        }
+    PfSample ps = pf_sample(sc, bins, ra);
+    if (BACKWARD && pc.count) {   // the samples the cached kernel could not take
+        ps.active = ps.active && pc.count[ps.gthread] > DVG_PFC_K;
+        if (!__any_sync(0xffffffffu, ps.active)) return;
     }
-    PrefilterTracer<BACKWARD> tr;
-    tr.init(cpt, active, first, frags);
+    const int tile = ps.tile, l = ps.l, x = ps.x, y = ps.y;
+    const bool active = ps.active;
+    const F2 pt = ps.pt, cpt = ps.cpt;
+    const float *bg_px = ps.bg_px;
+    PrefilterTracer<BACKWARD ? 1 : 2> tr;
+    tr.init(cpt, active, ps.first, frags);
+    if (!BACKWARD && pc.recs) tr.crec = reinterpret_cast<U4 *>(pc.recs) + ((size_t)(ps.gthread >> 5) * (DVG_PFC_K * 64) + (tid & 31));
     const int beg = bins.offsets[tile], end = bins.offsets[tile + 1];
     if constexpr (WORDS) {
         const int wpt = (ns + 31) / 32;
@@ -109,31 +155,63 @@ __global__ void __launch_bounds__(PB, (!BACKWARD && WORDS) ? DVG_PF_MINB + 1 : D
     tr.finish(sc);
     const F4 color = tr.resolve(bg_px);
     if constexpr (!BACKWARD) {
+        if (pc.count) pc.count[ps.gthread] = active ? tr.nfrag : 0;
         splat_color(sc, ra, x, y, pt, color, active, grp, tid);
     } else {
-        if (active) {
-            const F4 d_color = gather_d_color(sc.filter, ra.d_render_image, ra.weight_image, ra.width, ra.height, pt);
-            float *dtr = ra.d_translation ? ra.d_translation + 2 * (y * ra.width + x) : nullptr;
-            if (tr.nfrag > 0) {
-                F4 d_bg;
-                prefilter_backward(sc, tr, color, d_color, sk, dtr, d_bg);
-                if (bg_px && ra.d_background) {
-                    float *d = ra.d_background + 4 * (y * ra.width + x);
-                    atomicAdd(d + 0, d_bg.x); atomicAdd(d + 1, d_bg.y); atomicAdd(d + 2, d_bg.z); atomicAdd(d + 3, d_bg.w);
-                }
-            } else if (bg_px && ra.d_background) {
-                float *d = ra.d_background + 4 * (y * ra.width + x);
-                atomicAdd(d + 0, d_color.x); atomicAdd(d + 1, d_color.y); atomicAdd(d + 2, d_color.z); atomicAdd(d + 3, d_color.w);
-            }
-        }
+        if (active) pf_sample_backward(sc, ra, ps, tr, color, sk);
         if (!(ra.flags & 4u)) {   // DVG_BWD_SKIP_FILTER_GRAD (block-uniform: every lane of the warp is here)
-            const bool box_fast = sc.filter.type == 0 && pow2 && (int)ceilf(sc.filter.radius) == 1;
+            // (the box form sums over the lanes of a pixel: only when every sample of the launch is taken here)
+            const bool box_fast = !pc.count && sc.filter.type == 0 && pow2 && (int)ceilf(sc.filter.radius) == 1;
             if (box_fast) d_radius_acc = filter_radius_grad_box(sc, ra, x, y, pt, color, active, grp, tid & 31);
             else if (active) d_radius_acc = filter_radius_grad(sc, ra, x, y, pt, color);
         }
         d_radius_acc = warp_sum(d_radius_acc);
         if ((tid & 31) == 0) sk.add(sc.filter_radius_off, d_radius_acc);
     }
+}
+
+// Backward pass of the samples whose fragments the forward kernel cached (at most DVG_PFC_K of them: 99-100% of the samples
+// of the fill scenes): no candidate walk, no closest-point search -- the records are read back, a replay of the compositing
+// gives every fragment's `prev` (the same functions on the same floats as the forward kernel's, pf_fragment_color /
+// pf_composite), and prefilter_backward differentiates as it does in the full kernel.
+__global__ void __launch_bounds__(PB) k_pf_backward_cached(SceneView sc, BinView bins, RenderArgs ra, PfCache pc) {
+    const GlobalSink sk{grad_replica(ra)};
+    const int spp = ra.nsx * ra.nsy;
+    const int tid = threadIdx.x;
+    const bool pow2 = (spp & (spp - 1)) == 0;
+    const int grp = pow2 ? (spp < 32 ? spp : 32) : 1;
+    const PfSample ps = pf_sample(sc, bins, ra);
+    const int n = ps.active ? pc.count[ps.gthread] : 0;
+    const bool mine = ps.active && n <= DVG_PFC_K;
+    PfFragment frags[DVG_PFC_K];
+    PrefilterTracer<1> tr;
+    tr.init(ps.cpt, mine, ps.first, frags);
+    if (mine) {
+        const U4 *rec = reinterpret_cast<const U4 *>(pc.recs) + ((size_t)(ps.gthread >> 5) * (DVG_PFC_K * 64) + (tid & 31));
+#pragma unroll
+        for (int j = 0; j < DVG_PFC_K; j++) {
+            if (j < n) {
+                pf_cache_unpack(rec[j * 64], rec[j * 64 + 32], frags[j]);
+                frags[j].prev = tr.accum;
+                const bool is_stroke = (frags[j].key & 1) != 0;
+                const float w = pf_coverage(sc, is_stroke, frags[j].inst, frags[j].d);
+                pf_composite(tr.accum, pf_fragment_color(sc, sc.groups[frags[j].key >> 1], is_stroke, w, ps.cpt));
+                tr.nfrag++; tr.sp++;
+            }
+        }
+    }
+    const F4 color = tr.resolve(ps.bg_px);
+    if (mine) pf_sample_backward(sc, ra, ps, tr, color, sk);
+    float d_radius_acc = 0.f;
+    if (!(ra.flags & 4u)) {   // DVG_BWD_SKIP_FILTER_GRAD
+        const bool box_fast = sc.filter.type == 0 && pow2 && (int)ceilf(sc.filter.radius) == 1;
+        // (box form: the neighbour sum of a pixel is formed by ALL the lanes of the pixel, also those the full kernel takes)
+        if (box_fast) d_radius_acc = filter_radius_grad_box(sc, ra, ps.x, ps.y, ps.pt, color, ps.active, grp, tid & 31);
+        else if (mine) d_radius_acc = filter_radius_grad(sc, ra, ps.x, ps.y, ps.pt, color);
+        if (!mine) d_radius_acc = 0.f;
+    }
+    d_radius_acc = warp_sum(d_radius_acc);
+    if ((tid & 31) == 0) sk.add(sc.filter_radius_off, d_radius_acc);
 }
 
 // sample_distance for every pixel sample (eval_positions == null) or every evaluation position.
@@ -217,21 +295,28 @@ static int pf_blocks(const BinView &bins, const RenderArgs &ra) {
     return (r1 - r0) * bins.tiles_x * parts;
 }
 
-// `wind` / `tile_choff`: the winding words of the pre-pass and the chunk offsets they are laid out by, or null (the
-// winding test then runs inline: scenes without fills, renders beyond the 27-bit word index)
-void launch_render_pf(const SceneView &sc, const BinView &bins, const RenderArgs &ra, const unsigned *wind, const unsigned *relevant, const int *tile_choff,
-                      bool backward, cudaStream_t st) {
+// `wind` / `relevant` / `tile_choff`: the words of the winding pre-pass and the chunk offsets they are laid out by, or null
+// (the winding test then runs inline: scenes without fills, renders beyond the 27-bit word index).  `pc`: fragment cache to
+// fill (forward) or to skip the cached samples by (backward), or nulls.
+void launch_render_pf(const SceneView &sc, const BinView &bins, const RenderArgs &ra, const unsigned *wind, const unsigned *relevant,
+                      const int *tile_choff, const PfCache &pc, bool backward, cudaStream_t st) {
     const int nblk = pf_blocks(bins, ra);
     if (nblk <= 0) return;
     const uint4 *w4 = reinterpret_cast<const uint4 *>(wind);
     if (backward) {
-        if (wind) DVG_LAUNCH_AS("k_render_pf<true>", kpf_bwd_words, dim3(nblk), dim3(PB), 0, st, sc, bins, ra, w4, relevant, tile_choff);
-        else DVG_LAUNCH_AS("k_render_pf<true>", kpf_bwd_inline, dim3(nblk), dim3(PB), 0, st, sc, bins, ra, w4, relevant, tile_choff);
+        if (wind) DVG_LAUNCH_AS("k_render_pf<true>", kpf_bwd_words, dim3(nblk), dim3(PB), 0, st, sc, bins, ra, w4, relevant, tile_choff, pc);
+        else DVG_LAUNCH_AS("k_render_pf<true>", kpf_bwd_inline, dim3(nblk), dim3(PB), 0, st, sc, bins, ra, w4, relevant, tile_choff, pc);
     } else {
-        if (wind) DVG_LAUNCH_AS("k_render_pf<false>", kpf_fwd_words, dim3(nblk), dim3(PB), 0, st, sc, bins, ra, w4, relevant, tile_choff);
-        else DVG_LAUNCH_AS("k_render_pf<false>", kpf_fwd_inline, dim3(nblk), dim3(PB), 0, st, sc, bins, ra, w4, relevant, tile_choff);
+        if (wind) DVG_LAUNCH_AS("k_render_pf<false>", kpf_fwd_words, dim3(nblk), dim3(PB), 0, st, sc, bins, ra, w4, relevant, tile_choff, pc);
+        else DVG_LAUNCH_AS("k_render_pf<false>", kpf_fwd_inline, dim3(nblk), dim3(PB), 0, st, sc, bins, ra, w4, relevant, tile_choff, pc);
     }
 }
+void launch_pf_backward_cached(const SceneView &sc, const BinView &bins, const RenderArgs &ra, const PfCache &pc, cudaStream_t st) {
+    const int nblk = pf_blocks(bins, ra);
+    if (nblk <= 0) return;
+    DVG_LAUNCH(k_pf_backward_cached, dim3(nblk), dim3(PB), 0, st, sc, bins, ra, pc);
+}
+int64_t pf_launch_threads(const BinView &bins, const RenderArgs &ra) { return (int64_t)pf_blocks(bins, ra) * PB; }
 
 void launch_sdf(const SceneView &sc, const RenderArgs &ra, const SdfArgs &sa, bool backward, cudaStream_t st) {
     const int n = sa.eval_positions ? sa.num_eval : ra.width * ra.height * ra.nsx * ra.nsy;

@@ -167,9 +167,10 @@ int dvg_debug_set_boundary_dump(float *device_buf);
  * forces the answer-in-place path of the classifier, and the boundary pass at `edge_pass_samples` samples per sub-pass
  * (0 = off: as many as the result words allow).  Process-wide. */
 int dvg_debug_set_limits(int64_t pair_capacity, int64_t edge_pass_samples);
-/* Test support: 1 = the prefiltered path runs its winding tests inline in the render kernel (what it does anyway for
- * scenes without fills and for renders beyond the 27-bit word index) instead of through the winding pre-pass.  Same
- * results either way; process-wide. */
+/* Test support, bit mask: 1 = the prefiltered path runs its winding tests inline in the render kernel (what it does anyway
+ * for scenes without fills and for renders beyond the 27-bit word index) instead of through the winding pre-pass; 2 = its
+ * backward pass walks the candidate lists of every sample again instead of differentiating from the fragment records the
+ * forward pass cached.  Same results either way (gradients up to the order of the atomic sums); process-wide. */
 int dvg_debug_set_prefilter_inline(int on);
 /* Test support: for every sample of pixel (x, y) and EVERY primitive of the scene (no culling), the exact stroke test and
  * winding contribution as the device computes them: out_host[s * num_prims + e] = hit (bit 0) | group strokes (bit 1) |

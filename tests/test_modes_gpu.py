@@ -285,6 +285,32 @@ def test_prefilter_winding_prepass_equals_inline_and_backward_reuses_forward_wor
         else:
             assert np.array_equal(a, b)
         assert util.rel_l2(gb, ga) <= 1e-4    # (atomic sums in a different order)
+    # fragment cache: forward + backward on one scene object differentiate most samples from the records the forward kernel
+    # left (at most 4 fragments per sample; the others go through the full kernel) -- against the full kernel for all
+    import ctypes
+    tiger = np.load(os.path.join(ROOT, 'tests', 'golden_svg', 'tiger.npz'))
+    for topo, params, W, H in ((tiger['topo'], tiger['params'], 250, 256), util.pack(scenes.painterly(256, 128)) + (128, 128),
+                               util.pack(scenes.zoo()) + (96, 96)):
+        topo = np.ascontiguousarray(topo, np.int32); params = np.ascontiguousarray(params, np.float32)
+        d_img = torch.from_numpy(np.random.RandomState(5).rand(H, W, 4).astype(np.float32) - 0.5).cuda()
+        grads = []
+        for mode in (0, 2):
+            assert n.lib.dvg_debug_set_prefilter_inline(mode) == 0
+            try:
+                h = ctypes.c_void_p()
+                n.check(n.lib.dvg_scene_create(topo.ctypes.data, topo.shape[0], 0, ctypes.byref(h)))
+                st = torch.cuda.current_stream().cuda_stream
+                n.check(n.lib.dvg_scene_set_params(h, params.ctypes.data, params.shape[0], 0, st))
+                img = torch.empty(H, W, 4, device='cuda'); g = torch.empty(params.shape[0], device='cuda')
+                n.check(n.lib.dvg_render_forward(h, None, img.data_ptr(), None, W, H, 2, 2, 0, 1, None, 0, st))
+                n.check(n.lib.dvg_render_backward(h, None, d_img.data_ptr(), None, W, H, 2, 2, 0, 1, None, 0, g.data_ptr(), None, None, 0, st))
+                torch.cuda.synchronize()
+                grads.append(g.cpu().numpy())
+                n.lib.dvg_scene_destroy(h)
+            finally:
+                n.lib.dvg_debug_set_prefilter_inline(0)
+        assert np.linalg.norm(grads[1]) > 0
+        assert util.rel_l2(grads[1], grads[0]) <= 1e-4
     # one scene object, forward then backward (words re-used), twice with different parameters
     pydiffvg.set_use_gpu(True)
     cw, ch, shapes, groups = scenes.blobs()
