@@ -13,12 +13,19 @@
 
 namespace dvg {
 
+// (an opportunistic warp-level sum before the atomics -- all 32 lanes adding to one address inside a large filled shape --
+// measured no faster: 4.42 vs 4.46 ms for the cached backward kernel at flower.svg 2048^2)
+typedef GlobalSink PfSink;
 constexpr int PB = 256;  // threads per block
 #ifndef DVG_PF_MINB
 #define DVG_PF_MINB 2
 #endif
-// resident blocks per SM: the forward kernel without the inline winding test fits three (80 registers, 2.95 vs 3.40 ms at
-// flower.svg 2048^2); the backward kernel (fragment records, distance gradients) and the inline forms are slower with three
+#ifndef DVG_PF_FWD_MINB
+#define DVG_PF_FWD_MINB 2
+#endif
+// resident blocks per SM of the forward kernel with the winding words: two (with the fragment-cache stores three blocks spill:
+// 3.72 vs 3.56 ms at flower.svg 2048^2; without the stores three were faster, 2.95 vs 3.40); the full backward kernel
+// (fragment records, distance gradients) and the inline forms are slower with three; the cached backward kernel takes three
 
 DVG_D PrimRef load_prim(const SceneView &sc, int e) {
     PrimRef pr;
@@ -71,8 +78,8 @@ DVG_D PfSample pf_sample(const SceneView &sc, const BinView &bins, const RenderA
 }
 
 // The backward pass of one sample from its fragment records (diffvg.cpp:985-1111) and what surrounds it in the kernels.
-template <typename Tracer>
-DVG_D void pf_sample_backward(const SceneView &sc, const RenderArgs &ra, const PfSample &ps, const Tracer &tr, F4 color, const GlobalSink &sk) {
+template <typename Tracer, typename Sink>
+DVG_D void pf_sample_backward(const SceneView &sc, const RenderArgs &ra, const PfSample &ps, const Tracer &tr, F4 color, const Sink &sk) {
     const F4 d_color = gather_d_color(sc.filter, ra.d_render_image, ra.weight_image, ra.width, ra.height, ps.pt);
     float *dtr = ra.d_translation ? ra.d_translation + 2 * (ps.y * ra.width + ps.x) : nullptr;
     if (tr.nfrag > 0) {
@@ -99,10 +106,10 @@ DVG_D void pf_sample_backward(const SceneView &sc, const RenderArgs &ra, const P
 // fragment count there; the BACKWARD kernel, when given one, only differentiates the samples with more fragments than that
 // (k_pf_backward_cached has done the others) and its warps leave at once when they hold none.
 template <bool BACKWARD, bool WORDS>
-__global__ void __launch_bounds__(PB, (!BACKWARD && WORDS) ? DVG_PF_MINB + 1 : DVG_PF_MINB) k_render_pf(SceneView sc, BinView bins, RenderArgs ra, const uint4 *wind, const unsigned *relevant, const int *tile_choff, PfCache pc) {
+__global__ void __launch_bounds__(PB, (!BACKWARD && WORDS) ? DVG_PF_FWD_MINB : DVG_PF_MINB) k_render_pf(SceneView sc, BinView bins, RenderArgs ra, const uint4 *wind, const unsigned *relevant, const int *tile_choff, PfCache pc) {
     // gradients go straight to one of the private copies of the gradient buffer (dvg_kernel_util.cuh grad_replica):
     // the per-block shared-memory hash + barrier + flush this kernel used before was 40% of its time at 2048^2
-    const GlobalSink sk{BACKWARD ? grad_replica(ra) : nullptr};
+    const PfSink sk{BACKWARD ? grad_replica(ra) : nullptr};
     const int spp = ra.nsx * ra.nsy;
     const int ns = bins.tile_w * bins.tile_h * spp;
     const int tid = threadIdx.x;
@@ -174,8 +181,11 @@ __global__ void __launch_bounds__(PB, (!BACKWARD && WORDS) ? DVG_PF_MINB + 1 : D
 // of the fill scenes): no candidate walk, no closest-point search -- the records are read back, a replay of the compositing
 // gives every fragment's `prev` (the same functions on the same floats as the forward kernel's, pf_fragment_color /
 // pf_composite), and prefilter_backward differentiates as it does in the full kernel.
-__global__ void __launch_bounds__(PB) k_pf_backward_cached(SceneView sc, BinView bins, RenderArgs ra, PfCache pc) {
-    const GlobalSink sk{grad_replica(ra)};
+#ifndef DVG_PFC_MINB
+#define DVG_PFC_MINB 3
+#endif
+__global__ void __launch_bounds__(PB, DVG_PFC_MINB) k_pf_backward_cached(SceneView sc, BinView bins, RenderArgs ra, PfCache pc) {
+    const PfSink sk{grad_replica(ra)};
     const int spp = ra.nsx * ra.nsy;
     const int tid = threadIdx.x;
     const bool pow2 = (spp & (spp - 1)) == 0;
