@@ -115,6 +115,7 @@ struct DvgScene {
     bool counts_pending[2] = {false, false};
     cudaStream_t counts_stream[2] = {nullptr, nullptr};   // where each pending copy was queued
     int64_t want_s = 0, want_f = 0;      // most pairs any pass of this scene asked for so far
+    bool slot_seen[2] = {false, false};  // the pixel / boundary pass has reported its counts at least once
     bool params_set = false;
     bool checked = false;
     int scene_error = 0;
@@ -419,12 +420,13 @@ void wave_feedback_poll(DvgScene *s, cudaStream_t synced, bool have_synced) {
         s->counts_pending[slot] = false;
         const int32_t *c = s->h_counts + 4 * slot;
         // a counter that wrapped negative asked for more than 2^31 pairs: keep the in-place path for the surplus
+        s->slot_seen[slot] = true;
         s->want_s = std::max<int64_t>(s->want_s, c[0] < 0 ? 0x7fffffff : c[0]);
         s->want_f = std::max<int64_t>(s->want_f, c[1] < 0 ? 0x7fffffff : c[1]);
     }
 }
 
-int wave_view(DvgScene *s, int64_t chunk_slots, int64_t evals, WaveView *out) {
+int wave_view(DvgScene *s, int64_t chunk_slots, int64_t evals, WaveView *out, int slot = 0) {
     const int64_t words = chunk_slots * 32;
     if (words >= ((int64_t)1 << 27)) return fail(DVG_ERR_UNSUPPORTED, "render too large for the 27-bit result-word index of the pair queue");
     CK(s->d_wave_hit.ensure(sizeof(unsigned) * (size_t)std::max<int64_t>(words, 1)));
@@ -440,8 +442,12 @@ int wave_view(DvgScene *s, int64_t chunk_slots, int64_t evals, WaveView *out) {
     int64_t need_s, need_f;
     if (worst <= kSmallPairs) need_s = need_f = std::max<int64_t>(worst, 1);
     else {
-        need_s = s->want_s ? s->want_s + s->want_s / 8 + 4096 : std::max<int64_t>(3 * evals, 1 << 16);
-        need_f = s->want_f ? s->want_f + s->want_f / 8 + 4096 : std::max<int64_t>(4 * evals, 1 << 16);
+        need_s = s->want_s ? s->want_s + s->want_s / 8 + 4096 : 0;
+        need_f = s->want_f ? s->want_f + s->want_f / 8 + 4096 : 0;
+        if (!s->slot_seen[slot]) {   // this kind of pass has no history yet (the boundary pass asks for ~3x the pixel pass's pairs)
+            need_s = std::max<int64_t>(need_s, std::max<int64_t>(3 * evals + evals / 2, 1 << 16));
+            need_f = std::max<int64_t>(need_f, std::max<int64_t>(4 * evals, 1 << 16));
+        }
         need_s = std::min(std::min(need_s, worst), lim);
         need_f = std::min(std::min(need_f, worst), lim);
     }
@@ -599,7 +605,7 @@ int wave_edge_pass(DvgScene *s, const SceneView &sc, const BinView &bins, const 
     bw.item_tile = s->d_item_tile.as<int>();
     WaveView wv;
     // every item of a tile has that tile's chunk count: bounded by max_nch without another read-back
-    int rc = wave_view(s, (int64_t)bw.max_blocks * std::max(s->max_nch, 1), (int64_t)bw.max_blocks * 32, &wv);
+    int rc = wave_view(s, (int64_t)bw.max_blocks * std::max(s->max_nch, 1), (int64_t)bw.max_blocks * 32, &wv, 1);
     if (rc) return rc;
     s->wpx_valid = false;   // the result words are about to be overwritten
     launch_wave_boundary_sort(sc, bins, ra, bw, wv, s->d_edge_chunks.as<int>(), st);
