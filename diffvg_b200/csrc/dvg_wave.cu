@@ -365,10 +365,10 @@ constexpr auto kc_edge = k_wave_classify_edge<false, false>, kc_edge_fills = k_w
 constexpr auto kr_edge = k_wave_classify_edge<true, false>, kr_edge_fills = k_wave_classify_edge<true, true>;
 
 // ------------------------------------------------------------------------------------------ W2
-// Exact stroke tests of the queued pairs (within_distance.h:119-272 for cubic segments).  One WARP takes 64 pairs at a
+// Exact stroke tests of the queued pairs (within_distance.h:119-272 for cubic segments).  One WARP takes 32 * SV_PPL pairs at a
 // time through two phases that both keep its lanes busy and talk through the warp's slice of shared memory only (no
 // block-level barrier: the warps of a block drift apart freely):
-//   A (lane = pair, twice)  end-point checks; the monic quintic of the stationary points of the squared distance -- its
+//   A (lane = pair, SV_PPL times)  end-point checks; the monic quintic of the stationary points of the squared distance -- its
 //        sample-independent part comes from the primitive's PrimQuintic record (dvg_geom.cuh), the sample adds three
 //        float dot products; the isolator split points; the sign tests of ALL brackets.  Which brackets hold a root, and
 //        where each starts (`lower` only advances past a bracket that held one, :233-271), is a function of those signs
@@ -387,7 +387,7 @@ constexpr auto kr_edge = k_wave_classify_edge<true, false>, kr_edge_fills = k_wa
 constexpr int SV_B = 256;                 // threads per block
 constexpr int SV_NW = SV_B / 32;
 #ifndef DVG_SOLVE_PPL
-#define DVG_SOLVE_PPL 2
+#define DVG_SOLVE_PPL 1      // measured (tools/sweep.sh): 1 pair per lane and round at 4 blocks per SM 1.50 ms, 2 at 3 blocks 1.68 ms
 #endif
 constexpr int SV_PPL = DVG_SOLVE_PPL;     // pairs per lane and round
 constexpr int SV_PAIRS = 32 * SV_PPL;     // pairs per warp and round
@@ -396,7 +396,7 @@ constexpr int SV_MAXU = SV_PAIRS * 5;     // a quintic has at most five brackets
 #define DVG_SOLVE_PER_SM 64
 #endif
 #ifndef DVG_SOLVE_MINB
-#define DVG_SOLVE_MINB 3
+#define DVG_SOLVE_MINB 4
 #endif
 
 struct SolveWarp {
