@@ -192,6 +192,7 @@ def strong_scaling(dev, rank, world, barrier, max_over_ranks, steps=6, warmup=3)
             topo, params_np = flower['topo'], flower['params']
             packed = PackedScene(np.ascontiguousarray(topo), int(topo[1]), int(topo[2]), OutputType.color, True, torch.tensor([]))
             packed.needs_xform_grad = False
+            packed.needs_filter_grad = False      # the pixel-filter radius is a constant, as in every reference app (both arms)
             packed.filter_radius, packed.halo_rows = 0.5, 1
             params = torch.from_numpy(params_np).to(dev).requires_grad_(True)
         else:

@@ -207,8 +207,8 @@ class ShardedRenderFunction(torch.autograd.Function):
     `gather=False` returns only the rank's own band `[rows, W, 4]` (rows = `row_partition(...)[rank]`) for a loss
     that is itself computed per band: no image exchange in the forward pass.  The backward pass then needs the
     other ranks' d_image rows only for the boundary samples of the sampled path (they land anywhere in the image):
-    with `use_prefiltering` nothing is exchanged but the gradient all-reduce; otherwise the d_image bands are
-    all-gathered."""
+    with `use_prefiltering` only `halo_rows` rows either side of the band are exchanged, and only when the gradient of
+    the pixel-filter radius is asked for (`packed.needs_filter_grad`); otherwise the d_image bands are all-gathered."""
 
     @staticmethod
     def forward(ctx, width, height, num_samples_x, num_samples_y, seed, background_image, packed, params, group=None,
@@ -274,6 +274,12 @@ class ShardedRenderFunction(torch.autograd.Function):
                 hl = int(getattr(ctx.packed, 'halo_rows', 1))
                 if ctx.world == 1:
                     pass
+                elif ctx.packed.use_prefiltering and not getattr(ctx.packed, 'needs_filter_grad', True) \
+                        and float(getattr(ctx.packed, 'filter_radius', 0.5)) <= 0.5:
+                    # without d_filter.radius a sample reads d_image at its own pixel only: nothing is exchanged
+                    full = torch.empty(height, width, 4, device=dev, dtype=torch.float32)
+                    full[rb:re] = grad_img
+                    grad_img = full
                 elif ctx.packed.use_prefiltering and min(e - b for b, e in ctx.bands) >= hl:
                     # own rows + a halo of ceil(filter radius) rows from the two neighbours: d_filter.radius reads
                     # d_image over the whole (2*ceil(r)+1)^2 footprint of a sample (diffvg.cpp:1250-1268)

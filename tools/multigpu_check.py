@@ -64,6 +64,14 @@ def main():
         if rel3 > 1e-4 or rel > 1e-4:
             print('   rank %d %s: gather rel %.3g, band-loss rel %.3g, worst entry %d of %d: %g vs %g (filter radius at %d)' % (
                 rank, name, rel, rel3, worst, g1.numel(), float(g1[worst]), float(g3[worst]), int(packed.topo[6])), flush=True)
+        if pf is True:   # the same with the gradient of the pixel-filter radius asked for: the backward pass exchanges halo rows
+            packed.needs_filter_grad = True
+            (g1f,) = torch.autograd.grad((pydiffvg.RenderFunction.apply(w, h, nsx, nsy, 7, None, packed, params) - target).pow(2).mean(), params)
+            img4 = sharded.ShardedRenderFunction.apply(w, h, nsx, nsy, 7, None, packed, params, None, False)
+            (g4,) = torch.autograd.grad((img4 - target[rb:re]).pow(2).sum() / target.numel(), params)
+            packed.needs_filter_grad = False
+            rel3 = max(rel3, float((g1f - g4).norm() / g1f.norm().clamp_min(1e-30)))
+            assert float((g1f - g1).abs().max()) > 0, 'the filter-radius gradient should differ from the masked one'
         rel = max(rel, rel3)
         d_img = max(d_img, float((img1[rb:re] - img3).detach().abs().max()))
         good = d_img <= 1e-6 and rel <= 1e-4
