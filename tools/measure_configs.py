@@ -65,7 +65,8 @@ def main():
     rows = []
     assets = {k: np.load(os.path.join(ROOT, 'tests', 'golden_svg', k + '.npz')) for k in ('tiger', 'flower')}
     tiger_wh = (int(assets['tiger']['topo'][1]), int(assets['tiger']['topo'][2]))
-    for name, scene, (W, H, nsx, nsy, pf) in (
+    c5_only = '--c5-only' in sys.argv    # only the C5 batch scene (for an ncu capture of its kernels)
+    for name, scene, (W, H, nsx, nsy, pf) in () if c5_only else (
             ('C1 single_circle 256^2 2x2', scenes.single_circle(), (256, 256, 2, 2, 0)),
             ('C2 tiger.svg %dx%d 4x4' % tiger_wh, assets['tiger'], tiger_wh + (4, 4, 0)),
             ("C2' blobs1024 512^2 4x4", scenes.blobs(), (512, 512, 4, 4, 0)),
@@ -88,8 +89,9 @@ def main():
         n.lib.dvg_scene_destroy(s.h)
     batch = [Scene(scenes.batched_strokes(b)) for b in range(512)]
     img = torch.empty(64, 64, 4, device='cuda'); dimg = torch.empty_like(img)
-    ms = timed(lambda: [s.step(64, 64, 2, 2, b, 0, img, dimg) for b, s in enumerate(batch)], reps=3, warm=1)
-    print('%-38s %8.3f ms fwd+bwd for 512 scenes (%.3f ms per scene, sequential native scenes)' % ('C5 512x16 strokes 64^2 2x2', ms, ms / 512), flush=True)
+    if not c5_only:
+        ms = timed(lambda: [s.step(64, 64, 2, 2, b, 0, img, dimg) for b, s in enumerate(batch)], reps=3, warm=1)
+        print('%-38s %8.3f ms fwd+bwd for 512 scenes (%.3f ms per scene, sequential native scenes)' % ('C5 512x16 strokes 64^2 2x2', ms, ms / 512), flush=True)
     # the same 512 scenes as ONE batch scene (dvg_scene_create_batch)
     B = len(batch)
     rows = torch.stack([s.p for s in batch]).contiguous()
