@@ -191,6 +191,46 @@ class _timed:
         return False
 
 
+def band_gradient_mode(packed, bands):
+    """What a rank needs of the other ranks' `d_image` rows in the backward pass of a band loss (`gather=False`):
+    'own'    -- nothing: prefiltered path without the gradient of the pixel-filter radius (a sample reads d_image at its
+                own pixel only);
+    'halo'   -- `halo_rows` = ceil(filter radius) rows either side of the band: prefiltered path with `d_filter.radius`,
+                which reads d_image over the whole (2 ceil(r) + 1)^2 footprint of a sample (diffvg.cpp:1250-1268);
+    'gather' -- every row: the boundary samples of the sampled path land anywhere in the image."""
+    if not packed.use_prefiltering:
+        return 'gather'
+    if not getattr(packed, 'needs_filter_grad', True) and float(getattr(packed, 'filter_radius', 0.5)) <= 0.5:
+        return 'own'
+    return 'halo' if min(e - b for b, e in bands) >= int(getattr(packed, 'halo_rows', 1)) else 'gather'
+
+
+def band_gradient_image(grad_band, bands, rank, height, width, mode, halo=1, group=None):
+    """Full-size `d_image [height, width, 4]` for the backward call of rank `rank` from its band's gradient
+    `[rows, width, 4]` (see `band_gradient_mode`).  Rows the mode does not fill are left uninitialised: the backward
+    pass does not read them."""
+    world = len(bands)
+    rb, re = bands[rank]
+    if mode == 'gather':
+        return allgather_rows(grad_band, bands, group)
+    full = torch.empty(height, width, 4, device=grad_band.device, dtype=grad_band.dtype)
+    full[rb:re] = grad_band
+    if mode == 'own':
+        return full
+    hl = halo
+    edge = torch.cat([grad_band[:hl], grad_band[-hl:]], dim=0).contiguous()
+    buf = torch.empty((world,) + tuple(edge.shape), dtype=edge.dtype, device=edge.device)
+    dist.all_gather_into_tensor(buf, edge, group=group) if edge.is_cuda else \
+        dist.all_gather(list(buf.unbind(0)), edge, group=group)
+    full[max(0, rb - hl):rb].zero_()            # halo rows: the neighbours' rows below, zero at the image edge
+    full[re:min(height, re + hl)].zero_()
+    if rank > 0:
+        full[rb - hl:rb] = buf[rank - 1, hl:]
+    if rank < world - 1:
+        full[re:re + hl] = buf[rank + 1, :hl]
+    return full
+
+
 def allreduce_gradients(d_params, group=None):
     """Sum the per-rank gradient buffers in place (the only collective on the backward path:
     num_params floats, 155 KB at the painterly config -- latency-bound on NVSwitch)."""
@@ -270,35 +310,9 @@ class ShardedRenderFunction(torch.autograd.Function):
         bg = ctx.background_image
         grad_img = grad_img.to(dev).float().contiguous()
         with torch.cuda.device(dev):
-            if not ctx.gather:   # band-shaped gradient -> full-size d_image
-                hl = int(getattr(ctx.packed, 'halo_rows', 1))
-                if ctx.world == 1:
-                    pass
-                elif ctx.packed.use_prefiltering and not getattr(ctx.packed, 'needs_filter_grad', True) \
-                        and float(getattr(ctx.packed, 'filter_radius', 0.5)) <= 0.5:
-                    # without d_filter.radius a sample reads d_image at its own pixel only: nothing is exchanged
-                    full = torch.empty(height, width, 4, device=dev, dtype=torch.float32)
-                    full[rb:re] = grad_img
-                    grad_img = full
-                elif ctx.packed.use_prefiltering and min(e - b for b, e in ctx.bands) >= hl:
-                    # own rows + a halo of ceil(filter radius) rows from the two neighbours: d_filter.radius reads
-                    # d_image over the whole (2*ceil(r)+1)^2 footprint of a sample (diffvg.cpp:1250-1268)
-                    rank = dist.get_rank(ctx.group)
-                    edge = torch.cat([grad_img[:hl], grad_img[-hl:]], dim=0).contiguous()
-                    buf = torch.empty((ctx.world,) + tuple(edge.shape), dtype=edge.dtype, device=edge.device)
-                    dist.all_gather_into_tensor(buf, edge, group=ctx.group)
-                    # (the prefiltered backward pass reads d_image on its own rows and the halo only)
-                    full = torch.empty(height, width, 4, device=dev, dtype=torch.float32)
-                    full[rb:re] = grad_img
-                    full[max(0, rb - hl):rb].zero_()            # halo rows: the neighbours' rows below, zero at the image edge
-                    full[re:min(height, re + hl)].zero_()
-                    if rank > 0:
-                        full[rb - hl:rb] = buf[rank - 1, hl:]
-                    if rank < ctx.world - 1:
-                        full[re:re + hl] = buf[rank + 1, :hl]
-                    grad_img = full
-                else:
-                    grad_img = allgather_rows(grad_img, ctx.bands, ctx.group)
+            if not ctx.gather and ctx.world > 1:   # band-shaped gradient -> full-size d_image
+                grad_img = band_gradient_image(grad_img, ctx.bands, dist.get_rank(ctx.group), height, width,
+                                               band_gradient_mode(ctx.packed, ctx.bands), int(getattr(ctx.packed, 'halo_rows', 1)), ctx.group)
             stream = torch.cuda.current_stream().cuda_stream
             if ns.version != ctx.scene_version:
                 ctx.scene_version = ns.set_params(params, stream)

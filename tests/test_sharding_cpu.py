@@ -94,6 +94,64 @@ def test_allgather_rows_and_gradient_allreduce_world2():
     assert all(r[1] and r[2] for r in res)
 
 
+def _worker_band_gradient(rank, world, port, height, width, q):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        full = torch.arange(height * width * 4, dtype=torch.float32).reshape(height, width, 4) + 1.0
+        bands = sharded.row_partition(height, world, 2)
+        b, e = bands[rank]
+        band = full[b:e].clone()
+        ok = {}
+        g = sharded.band_gradient_image(band, bands, rank, height, width, 'gather')
+        ok['gather'] = bool(torch.equal(g, full))
+        g = sharded.band_gradient_image(band, bands, rank, height, width, 'own')
+        ok['own'] = g.shape == full.shape and bool(torch.equal(g[b:e], band))
+        for hl in (1, 2):
+            g = sharded.band_gradient_image(band, bands, rank, height, width, 'halo', hl)
+            lo, hi = max(0, b - hl), min(height, e + hl)
+            # own rows and the neighbours' halo rows are the true d_image; nothing else is promised
+            ok['halo%d' % hl] = bool(torch.equal(g[lo:hi], full[lo:hi]))
+        q.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_band_gradient_image_world2():
+    """Backward pass of a band loss: what each rank assembles of d_image in the three exchange modes."""
+    world = 2
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_band_gradient, args=(r, world, port, 12, 3, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sorted(r[0] for r in res) == [0, 1]
+    for _, ok in res:
+        assert all(ok.values()), ok
+
+
+def test_band_gradient_mode_follows_the_scene():
+    class P:
+        pass
+    bands = [(0, 8), (8, 16)]
+    p = P(); p.use_prefiltering = False
+    assert sharded.band_gradient_mode(p, bands) == 'gather'            # boundary samples land anywhere
+    p.use_prefiltering = True; p.needs_filter_grad = True; p.filter_radius = 0.5; p.halo_rows = 1
+    assert sharded.band_gradient_mode(p, bands) == 'halo'              # d_filter.radius reads the 3x3 footprint
+    p.needs_filter_grad = False
+    assert sharded.band_gradient_mode(p, bands) == 'own'
+    p.filter_radius = 1.5; p.halo_rows = 2
+    assert sharded.band_gradient_mode(p, bands) == 'halo'              # (a wide filter: samples read beyond their pixel)
+    p.halo_rows = 9
+    assert sharded.band_gradient_mode(p, bands) == 'gather'            # bands thinner than the halo
+
+
 def test_row_split_reproduces_whole_render_on_the_oracle():
     """The property the sharding relies on, checked on the checker itself: rendering with the canvas
     height and image height scaled to a band is NOT what *_rows does -- *_rows keeps the global sample
