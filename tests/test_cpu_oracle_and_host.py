@@ -176,6 +176,82 @@ def test_pack_gradients_flow_to_user_tensors():
     assert torch.equal(col.grad, g[grec[6]:grec[6] + 4])
 
 
+def _plain_concat(buckets, device):
+    """The plain torch graph concat_params replaced (stack / cat per bucket): the reference for values and gradients."""
+    parts = [f for f in (scene_pack._flatten_bucket(b, ts, device) for b, ts in enumerate(buckets)) if f is not None]
+    return torch.cat(parts) if len(parts) > 1 else parts[0].clone()
+
+
+def _leaves(buckets):
+    seen, out = set(), []
+    for b in buckets:
+        for t in b:
+            if id(t) not in seen and t.is_leaf and t.dtype.is_floating_point:
+                seen.add(id(t))
+                out.append(t)
+    return out
+
+
+@pytest.mark.parametrize('which', ['zoo', 'painterly', 'blobs'])
+def test_concat_params_single_node_equals_plain_graph(which):
+    scene = {'zoo': scenes.zoo, 'painterly': lambda: scenes.painterly(32, 64), 'blobs': lambda: scenes.blobs(16, 48)}[which]()
+    cw, ch, shapes, groups = scene
+    topo, buckets = scene_pack.pack_scene(cw, ch, shapes, groups, 0, torch.tensor(0.5, requires_grad=True))
+    leaves = _leaves(buckets)
+    was = [t.requires_grad for t in leaves]
+    res = []
+    try:
+        for t in leaves:
+            t.requires_grad_(True)
+        for fn in (lambda: scene_pack.concat_params(buckets), lambda: _plain_concat(buckets, torch.device('cpu'))):
+            for t in leaves:
+                t.grad = None
+            p = fn()
+            assert p.dtype == torch.float32 and p.dim() == 1 and p.numel() == int(topo[scene_pack.H_NPARAMS])
+            w = torch.linspace(-1.0, 2.0, p.numel())
+            (p * w).sum().backward()
+            res.append((p.detach().clone(), [t.grad.clone() for t in leaves]))
+    finally:   # (the default identity transform is shared by every ShapeGroup of the process)
+        for t, r in zip(leaves, was):
+            t.grad = None
+            t.requires_grad_(r)
+    assert torch.equal(res[0][0], res[1][0])
+    assert len(res[0][1]) == len(leaves) and all(g0.shape == t.shape for g0, t in zip(res[0][1], leaves))
+    assert all(torch.equal(a, b) for a, b in zip(res[0][1], res[1][1]))
+
+
+def test_concat_params_mixed_inputs():
+    """Non-leaf inputs, float64 tensors, a tensor used twice, tensors that take no part in autograd, [1]-shaped scalars."""
+    from diffvg_b200 import pydiffvg
+    theta = torch.rand(3, 2, requires_grad=True)
+    pts_a = theta * 20 + 5                                        # not a leaf
+    pts_b = torch.rand(4, 2, dtype=torch.float64).mul(30).requires_grad_(True)
+    wa = torch.tensor([2.0], requires_grad=True)                  # shape [1]
+    wb = torch.tensor(1.5, requires_grad=True)                    # shape []
+    col = torch.rand(4, requires_grad=True)                       # fill AND stroke colour of a group
+    frozen = torch.rand(4)                                        # no gradient asked
+    shapes = [pydiffvg.Path(torch.tensor([1]), pts_a, False, wa), pydiffvg.Path(torch.tensor([2]), pts_b, False, wb)]
+    groups = [pydiffvg.ShapeGroup(torch.tensor([0]), col, stroke_color=col), pydiffvg.ShapeGroup(torch.tensor([1]), None, stroke_color=frozen)]
+    topo, buckets = scene_pack.pack_scene(64, 64, shapes, groups)
+    res = []
+    for fn in (lambda: scene_pack.concat_params(buckets), lambda: _plain_concat(buckets, torch.device('cpu'))):
+        for t in (theta, pts_b, wa, wb, col):
+            t.grad = None
+        p = fn()
+        (p * torch.arange(1, p.numel() + 1, dtype=torch.float32)).sum().backward(retain_graph=True)   # (theta -> pts_a is shared by both runs)
+        res.append((p.detach().clone(), [t.grad.clone() for t in (theta, pts_b, wa, wb, col)]))
+        assert frozen.grad is None
+    assert torch.equal(res[0][0], res[1][0])
+    for a, b, t in zip(res[0][1], res[1][1], (theta, pts_b, wa, wb, col)):
+        assert a.dtype == t.dtype and a.shape == t.shape and torch.equal(a, b)
+    # nothing asks for a gradient: plain tensor out
+    with torch.no_grad():
+        assert not scene_pack.concat_params(buckets).requires_grad
+    topo2, b2 = scene_pack.pack_scene(64, 64, [pydiffvg.Circle(torch.tensor(5.0), torch.tensor([8.0, 9.0]))],
+                                      [pydiffvg.ShapeGroup(torch.tensor([0]), torch.tensor([0.1, 0.2, 0.3, 1.0]))])
+    assert not scene_pack.concat_params(b2).requires_grad
+
+
 def test_shared_transform_is_stored_once():
     cw, ch, shapes, groups = scenes.painterly(8, 64)
     eye = torch.eye(3)
